@@ -1,0 +1,312 @@
+/*
+ * wheeledlab_b200.h -- C-ABI of the B200-native vectorised wheeled-robot step.
+ *
+ * This is the drop-in boundary for ONE path of UWRobotLearning/WheeledLab: the
+ * object `gym.make(<id>, cfg=env_cfg)` returns (isaaclab.envs:ManagerBasedRLEnv,
+ * reference source/wheeledlab_tasks/wheeledlab_tasks/__init__.py:14-63) and its
+ * `step()/reset()/observation_manager.compute()` calls (call stack SURVEY.md 3.3).
+ * The reference has no FFI of its own (pure Python down to omni.physx), so the
+ * entry points below are the ones a Python binding (ctypes)
+ * needs to implement that surface:
+ *
+ *   wl_step      <- ManagerBasedRLEnv.step(action)           (train loop:
+ *                   source/wheeledlab_rl/wheeledlab_rl/utils/modified_rsl_rl_runner.py:73)
+ *   wl_reset     <- ManagerBasedRLEnv.reset() / _reset_idx   (wheeledlab_tasks/test/create_and_step_env.py:31)
+ *   wl_observe   <- observation_manager.compute()            (modified_rsl_rl_runner.py:50)
+ *   wl_startup   <- event_manager.apply(mode="startup")      (drifting/mushr_drift_env_cfg.py:95-154)
+ *   wl_curriculum<- curriculum_manager.compute()             (wheeledlab/envs/mdp/curriculums.py:10-35)
+ *   wl_synth_actions <- sample_space(single_action_space)    (create_and_step_env.py:37-39)
+ *
+ * Plain pointers and sizes only; every device pointer is caller-owned (the Python
+ * host allocates with torch and passes data_ptr()); `stream` is a cudaStream_t
+ * passed as void*. All functions return 0 on success, a negative WL_E* code on
+ * failure, and wl_last_error() gives the message.  Nothing here falls back to CPU.
+ */
+#ifndef WHEELEDLAB_B200_H
+#define WHEELEDLAB_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WL_ABI_VERSION 1
+
+/* tasks (gym ids, wheeledlab_tasks/__init__.py:14-63) */
+#define WL_TASK_DRIFT     0  /* Isaac-MushrDriftRL-v0, Isaac-F1TenthDriftRL-v0 */
+#define WL_TASK_ELEVATION 1  /* Isaac-MushrElevationRL-v0 */
+#define WL_TASK_VISUAL    2  /* Isaac-MushrVisualRL-v0 (physics/reward side; camera out of scope) */
+
+/* action term kinds (wheeledlab/envs/mdp/actions/ *.py) */
+#define WL_ACT_ACKERMANN 0   /* ackermann_actions.py:150-201 */
+#define WL_ACT_RWD       1   /* rc_car_actions.py:12-29 */
+#define WL_ACT_4WD       2   /* rc_car_actions.py:36-64 */
+
+/* bounding strategy (ackermann_actions.py:119-133) */
+#define WL_BOUND_NONE 0
+#define WL_BOUND_CLIP 1
+#define WL_BOUND_TANH 2
+
+/* wheel order everywhere: [back_left, back_right, front_left, front_right]
+ * (the 4WD action's own order, rc_car_actions.py:62) */
+#define WL_BL 0
+#define WL_BR 1
+#define WL_FL 2
+#define WL_FR 3
+
+#define WL_MAX_REW_TERMS  8
+#define WL_MAX_REF_POSES  32
+#define WL_MAX_BUCKETS    32
+#define WL_OBS_DIM_BLIND  14   /* wheeledlab_tasks/common/observations.py:19-56 */
+#define WL_SCAN_SIDE      26   /* 26x26 grid, elevation/mushr_elevation_env_cfg.py:132-142 */
+#define WL_SCAN_RAYS      676
+#define WL_OBS_DIM_ELEV   689  /* 2+3+3+3+2+676, mushr_elevation_env_cfg.py:57-88 */
+
+/* drift reward term slots (drifting/mushr_drift_env_cfg.py:243-299, declaration order) */
+#define WL_DR_SIDE_SLIP   0
+#define WL_DR_VEL         1
+#define WL_DR_PROGRESS    2
+#define WL_DR_TLGR        3
+#define WL_DR_TURN_ENERGY 4
+#define WL_DR_CROSS_TRACK 5
+#define WL_DR_TERM_PENS   6
+/* elevation reward term slots (mushr_elevation_env_cfg.py:283-305) */
+#define WL_ER_GOAL_RATE   0
+#define WL_ER_HEIGHT_Z    1
+#define WL_ER_FALLING     2
+#define WL_ER_TERM_PEN    3
+
+/* error codes */
+#define WL_OK          0
+#define WL_EINVAL     -1
+#define WL_ECUDA      -2
+#define WL_EUNSUPPORTED -3
+
+/*
+ * wl_config: plain-old-data description of one task instance.  Defined by an
+ * X-macro so that wl_config_describe() can hand the exact field list to a
+ * foreign-language binding (the ctypes mirror is generated from it).
+ * XS(type, tag, name)  scalar;   XA(type, tag, name, n)  fixed array.
+ */
+#define WL_CONFIG_FIELDS(XS, XA)                                                                   \
+    XS(int32_t, i32, abi_version)                                                                  \
+    XS(int32_t, i32, task)                                                                         \
+    XS(int32_t, i32, num_envs)        /* envs owned by this handle (one GPU) */                    \
+    XS(int32_t, i32, env_id_offset)   /* global id of local env 0 (multi-GPU sharding) */          \
+    XS(uint64_t, u64, seed)           /* mushr_drift_env_cfg.py:371 */                             \
+    /* --- simulation (mushr_drift_env_cfg.py:393-396) --- */                                      \
+    XS(float, f32, sim_dt)                                                                         \
+    XS(int32_t, i32, decimation)                                                                   \
+    XS(int32_t, i32, substeps)        /* integrator sub-steps per sim step (TGS-like) */           \
+    XS(int32_t, i32, max_episode_length)                                                           \
+    XS(float, f32, gravity)                                                                        \
+    /* --- action term (wheeledlab_tasks/common/actions.py) --- */                                 \
+    XS(int32_t, i32, action_kind)                                                                  \
+    XS(int32_t, i32, bounding)                                                                     \
+    XS(int32_t, i32, no_reverse)                                                                   \
+    XS(int32_t, i32, _pad0)                                                                        \
+    XA(float, f32, act_scale, 2)                                                                   \
+    XA(float, f32, act_offset, 2)                                                                  \
+    XS(float, f32, base_length)                                                                    \
+    XS(float, f32, base_width)                                                                     \
+    XS(float, f32, wheel_radius_cfg)  /* action-map radius (0.05), NOT the collider radius (Q2) */ \
+    /* --- vehicle --- */                                                      \
+    XS(float, f32, mass_nominal)                                                                   \
+    XA(float, f32, inertia_nominal, 3)                                                             \
+    XA(float, f32, com, 3)            /* COM in root(base_footprint) frame */                      \
+    XS(float, f32, hub_x_front)                                                                    \
+    XS(float, f32, hub_x_rear)                                                                     \
+    XS(float, f32, hub_y)                                                                          \
+    XS(float, f32, hub_z)                                                                          \
+    XS(float, f32, wheel_radius)      /* collider radius 0.0525 */                                 \
+    XS(float, f32, wheel_inertia)                                                                  \
+    XS(float, f32, wheel_damping)                                                                  \
+    XS(float, f32, susp_k)                                                                         \
+    XS(float, f32, susp_c)                                                                         \
+    XS(float, f32, susp_travel)                                                                    \
+    XS(float, f32, bump_k)                                                                         \
+    /* --- actuators (wheeledlab_assets/hound.py:4-52) --- */                                      \
+    XS(float, f32, dc_saturation)                                                                  \
+    XS(float, f32, dc_vel_limit)                                                                   \
+    XA(float, f32, dc_effort, 4)      /* per wheel; 0 => passive (hound.py:44-51) */               \
+    XA(float, f32, dc_damping, 4)     /* nominal kd per wheel (before DR) */                       \
+    XS(float, f32, steer_kp)                                                                       \
+    XS(float, f32, steer_kd)                                                                       \
+    XS(float, f32, steer_inertia)                                                                  \
+    XS(float, f32, steer_vel_limit)                                                                \
+    XS(float, f32, steer_pos_limit)                                                                \
+    /* --- tire / contact --- */                                                                   \
+    XS(float, f32, tire_B)                                                                         \
+    XS(float, f32, tire_v0)                                                                        \
+    XS(float, f32, tire_mx)           /* effective mass for the longitudinal stick clamp */        \
+    XS(float, f32, tire_my)                                                                        \
+    XS(float, f32, ground_mu_s)       /* mushr_drift_env_cfg.py:45-49 (combine=multiply) */        \
+    XS(float, f32, ground_mu_d)                                                                    \
+    /* --- startup domain randomisation (mushr_drift_env_cfg.py:95-154) --- */                     \
+    XS(int32_t, i32, dr_enable)                                                                    \
+    XS(int32_t, i32, dr_num_buckets)                                                               \
+    XA(float, f32, dr_bucket_D, WL_MAX_BUCKETS)   /* peak mu of bucket  (mu_s_wheel*mu_s_ground) */ \
+    XA(float, f32, dr_bucket_C, WL_MAX_BUCKETS)   /* Pacejka shape s.t. asymptote = mu_d */        \
+    XA(float, f32, dr_kd_range, 2)                                                                 \
+    XS(int32_t, i32, dr_kd_mask)      /* bit i => wheel i gets randomised damping */               \
+    XS(int32_t, i32, _pad1)                                                                        \
+    XA(float, f32, dr_mass_add, 2)                                                                 \
+    /* --- observation noise (common/observations.py:27-45) --- */                                 \
+    XS(int32_t, i32, enable_corruption)                                                            \
+    XS(int32_t, i32, _pad2)                                                                        \
+    XA(float, f32, noise_std, 4)      /* pos, euler, lin vel, ang vel */                           \
+    /* --- interval pushes (mushr_drift_env_cfg.py:121-143) --- */                                 \
+    XS(int32_t, i32, push_enable)                                                                  \
+    XS(int32_t, i32, _pad3)                                                                        \
+    XA(float, f32, push_hf_interval, 2)                                                            \
+    XA(float, f32, push_hf_range, 3)  /* +-x, +-y, +-yaw */                                        \
+    XA(float, f32, push_lf_interval, 2)                                                            \
+    XS(float, f32, push_lf_yaw)                                                                    \
+    /* --- reset along track (drifting/mdp/events.py:10-133) --- */                                \
+    XS(int32_t, i32, num_ref_poses)                                                                \
+    XS(float, f32, reset_pos_noise)                                                                \
+    XS(float, f32, reset_yaw_noise)                                                                \
+    XA(float, f32, ref_poses, 3 * WL_MAX_REF_POSES) /* x, y, yaw_deg */                            \
+    /* --- drift terminations / rewards (mushr_drift_env_cfg.py:27-32,160-362) --- */              \
+    XS(float, f32, trk_straight)                                                                   \
+    XS(float, f32, trk_corner_in)                                                                  \
+    XS(float, f32, trk_corner_out)                                                                 \
+    XS(float, f32, ctd_track_radius)                                                               \
+    XS(float, f32, ctd_offset)                                                                     \
+    XS(float, f32, slip_min_thresh)                                                                \
+    XS(float, f32, slip_max_thresh)                                                                \
+    XS(float, f32, slip_min_vel_x)                                                                 \
+    XS(float, f32, vel_speed_target)                                                               \
+    XS(float, f32, vel_offset)                                                                     \
+    XS(float, f32, tlgr_ang_vel_thresh)                                                            \
+    XS(float, f32, energy_straight)                                                                \
+    XS(int32_t, i32, num_rew_terms)                                                                \
+    XA(float, f32, rew_weight, WL_MAX_REW_TERMS)  /* initial weights; live copy is on device */    \
+    /* --- elevation task (elevation/mushr_elevation_env_cfg.py) --- */                            \
+    XS(int32_t, i32, hf_nx)           /* height-field raster size */                               \
+    XS(int32_t, i32, hf_ny)                                                                        \
+    XS(float, f32, hf_x0)             /* world coord of sample (0,0) */                            \
+    XS(float, f32, hf_y0)                                                                          \
+    XS(float, f32, hf_cell)                                                                        \
+    XS(float, f32, hf_outside_z)      /* physics ground outside the raster (ground plane z=0) */   \
+    XS(float, f32, scan_offset)       /* 0.084, :78 */                                             \
+    XS(float, f32, scan_plane_init)   /* 0.19,  :79 */                                             \
+    XS(float, f32, scan_sensor_dz)    /* +20 m ray start, :135 */                                  \
+    XS(float, f32, scan_res)          /* 0.1 */                                                    \
+    XS(float, f32, obs_clip)          /* 10, :61-82 */                                             \
+    XA(float, f32, cmd_pos_range, 2)  /* +-19 m, :425-435 */                                       \
+    XS(float, f32, cmd_resample_s)                                                                 \
+    XA(float, f32, elev_reset_xy, 2)  /* +-19 m, :409-419 */                                       \
+    XS(float, f32, elev_reset_yaw)    /* 3.14 */                                                   \
+    XA(float, f32, elev_reset_vel, 2) /* U(0.1,0.2) on v_x and v_y */                              \
+    XS(float, f32, elev_spawn_z)      /* 0.25, :97,147-149 */                                      \
+    XS(float, f32, elev_min_height)   /* 0.15, :354-357 */                                         \
+    XS(float, f32, elev_stuck_min_vel)                                                             \
+    XS(float, f32, elev_stuck_spin)                                                                \
+    XS(float, f32, elev_rollover_cos) /* cos(60 deg), :217-222 */                                  \
+    XS(float, f32, elev_goal_dist)                                                                 \
+    XS(float, f32, elev_fall_vel)                                                                  \
+    XS(float, f32, elev_plane_z)      /* 0.19 in higher_elevation, :166-173 */
+
+typedef struct wl_config {
+#define WL_XS(type, tag, name) type name;
+#define WL_XA(type, tag, name, n) type name[n];
+    WL_CONFIG_FIELDS(WL_XS, WL_XA)
+#undef WL_XS
+#undef WL_XA
+} wl_config;
+
+/*
+ * Device state layout.  One caller-owned buffer of wl_state_bytes() bytes holds
+ * WL_NUM_GROUPS "groups"; group g is an array float4[num_envs] at byte offset
+ * g * num_envs * 16, so env i reads/writes one aligned 128-bit word per group
+ * and a warp touches 512 contiguous bytes (coalesced).  Component meaning:
+ */
+#define WL_G_POS     0  /* root_pos_w x,y,z ; episode_length_buf (int32 bits)          */
+#define WL_G_QUAT    1  /* root_quat_w  w,x,y,z                                       */
+#define WL_G_LINVEL  2  /* root_lin_vel_w x,y,z ; push_hf time_left                   */
+#define WL_G_ANGVEL  3  /* root_ang_vel_w x,y,z ; push_lf time_left                   */
+#define WL_G_WHEEL   4  /* wheel spin rate [bl,br,fl,fr] (joint_vel of *_throttle)    */
+#define WL_G_STEER   5  /* steer pos L,R ; steer vel L,R                              */
+#define WL_G_ACTION  6  /* action_manager.action (2) ; prev_action (2)                */
+#define WL_G_SUM0    7  /* reward episode sums, terms 0-3                             */
+#define WL_G_SUM1    8  /* reward episode sums, terms 4-7                             */
+#define WL_G_PMASS   9  /* mass, 1/mass, spare, spare                    (DR param)   */
+#define WL_G_PMU_D  10  /* Pacejka peak D per wheel                      (DR param)   */
+#define WL_G_PMU_C  11  /* Pacejka shape C per wheel                     (DR param)   */
+#define WL_G_PKD    12  /* DC-motor damping per wheel                    (DR param)   */
+#define WL_G_CMD    13  /* elevation: goal x,y (world), heading, command time_left    */
+#define WL_NUM_GROUPS 14
+
+/* small global (not per-env) device block appended after the groups */
+typedef struct wl_globals {
+    float rew_weight[WL_MAX_REW_TERMS];   /* live reward weights (curriculum mutates)       */
+    float log_sum[2][WL_MAX_REW_TERMS];   /* per-step sum over reset envs of episode sums   */
+    float log_term[2][4];                 /* per-step reset counts: [all, terminated, timeout, spare] */
+    int32_t any_reset[2];                 /* set by step kernel when >=1 env reset          */
+    int32_t _pad[2];
+} wl_globals;
+
+typedef struct wl_sim wl_sim;   /* opaque handle (host memory) */
+
+/* ---- config ---------------------------------------------------------------- */
+/* "name:tag:count:offset;..." for every wl_config field, plus "sizeof:<n>". */
+const char* wl_config_describe(void);
+size_t wl_config_sizeof(void);
+
+/* ---- lifetime -------------------------------------------------------------- */
+size_t wl_state_bytes(int32_t num_envs);     /* groups + globals, 256-byte padded */
+size_t wl_globals_offset(int32_t num_envs);  /* byte offset of wl_globals in the state buffer */
+/* d_state: zero-initialised device buffer of wl_state_bytes(cfg->num_envs) bytes.
+ * d_heightfield: float[hf_ny*hf_nx] on device (row-major, y-major rows) or NULL. */
+int wl_create(const wl_config* cfg, void* d_state, size_t state_bytes, const float* d_heightfield,
+              wl_sim** out);
+int wl_destroy(wl_sim* sim);
+const char* wl_last_error(void);
+/* compiled-for architecture string, e.g. "sm_100a" */
+const char* wl_build_info(void);
+
+/* ---- hot path -------------------------------------------------------------- */
+/* startup events: material buckets / actuator gains / base mass scatter + default joint state
+ * + initial interval timers (mushr_drift_env_cfg.py:95-154; EventManager startup). */
+int wl_startup(wl_sim* sim, void* stream);
+/* reset the listed envs (d_env_ids==NULL => all).  env ids are local int64 indices, as
+ * IsaacLab passes them (_reset_idx).  `step_counter` keys the counter-based RNG. */
+int wl_reset(wl_sim* sim, const int64_t* d_env_ids, int32_t n_ids, int64_t step_counter, void* stream);
+/* one env.step(): action[N,2] f32 -> obs[N,obs_dim] f32, rew[N] f32, terminated[N] u8,
+ * truncated[N] u8.  `step_counter` = common_step_counter BEFORE this step.  Auto-resets
+ * finished envs (reward belongs to the pre-reset state, obs to the post-reset state). */
+int wl_step(wl_sim* sim, const float* d_action, float* d_obs, float* d_rew, uint8_t* d_terminated,
+            uint8_t* d_truncated, int64_t step_counter, void* stream);
+/* observation_manager.compute(): re-samples the noise. call_idx distinguishes
+ * repeated calls at the same step_counter. */
+int wl_observe(wl_sim* sim, float* d_obs, int64_t step_counter, int32_t call_idx, void* stream);
+/* curriculum (curriculums.py:10-35) evaluated on device so that no host sync is needed:
+ * for each term t in [0,n): if any env reset during the last step, rew_weight[slot[t]] += inc[t]
+ * when the host-evaluated counter conditions in fire_mask bit t hold. */
+int wl_curriculum(wl_sim* sim, int64_t step_counter, int32_t n_terms, const int32_t* slots,
+                  const float* increases, uint32_t fire_mask, void* stream);
+/* synthetic actions: U[-1,1]^2 (dist=0) or clip(N(0,1),-1,1) (dist=1) keyed by
+ * (seed, global env id, step_counter); writes d_action[N,2]. */
+int wl_synth_actions(wl_sim* sim, float* d_action, int64_t step_counter, int32_t dist, void* stream);
+/* derived joint state for the Python articulation view: suspension pos/vel [N,4]x2 */
+int wl_derive_suspension(wl_sim* sim, float* d_susp_pos, float* d_susp_vel, void* stream);
+/* observation width for the configured task */
+int32_t wl_obs_dim(const wl_sim* sim);
+/* number of kernel launches issued through this handle since creation */
+int64_t wl_launch_count(const wl_sim* sim);
+
+/* ---- test hooks (bit-exactness of the deterministic math vs the oracle) ------ */
+/* op: 0 sin,1 cos,2 atan,3 atan2(x=in,y=in2),4 log,5 tan,6 asin ; out[n] */
+int wl_test_detmath(int32_t op, const float* d_in, const float* d_in2, float* d_out, int32_t n,
+                    void* stream);
+/* philox4x32-10: out[4*n] for counters (c0_base + i, c1, c2, c3), key from seed */
+int wl_test_philox(uint64_t seed, uint32_t c0_base, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t* d_out,
+                   int32_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WHEELEDLAB_B200_H */

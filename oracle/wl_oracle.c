@@ -1,0 +1,887 @@
+/*
+ * wl_oracle.c -- CPU ORACLE (TEST INFRASTRUCTURE, NOT PRODUCT CODE).
+ *
+ * A plain-C, one-env-at-a-time restatement of the vectorised WheeledLab step that
+ * wheeledlab_b200's CUDA kernels implement.  Only tests/, __graft_entry__.smoke()
+ * and bench.py's cpu_baseline / --impl reference leg may load this library; the
+ * product path never does.
+ *
+ * PARITY STATUS (see DESIGN.md "Oracle"):
+ *   - MDP term math (actions, rewards, terminations, reset poses, curriculum, obs
+ *     assembly) follows the reference files cited at each function and is PINNED by
+ *     golden vectors generated from the reference's own Python
+ *     (tests/golden/, tests/golden/make_golden.py).
+ *   - The rigid-body / tyre / actuator integrator stands in for PhysX-5 (closed
+ *     binary, absent from /root/reference and from this image): PARITY UNPINNED at
+ *     the PhysX boundary.  The model is builder-defined (DESIGN.md "Physics model").
+ *
+ * Arithmetic contract shared with the CUDA path (so results are bit-identical):
+ * IEEE fp32, no FMA contraction (-ffp-contract=off here, -fmad=false there),
+ * correctly rounded / and sqrt, and the polynomial sin/cos/atan/log below instead
+ * of libm.  Build with -DWLO_DOUBLE for a float64 "truth" variant (libm) used by the
+ * tolerance tests.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdio.h>
+#include <stddef.h>
+
+#include "../include/wheeledlab_b200.h"
+
+#ifdef WLO_DOUBLE
+typedef double real;
+#define K(x) x
+#define r_sqrt sqrt
+#define r_fabs fabs
+#define r_floor floor
+#else
+typedef float real;
+#define K(x) x##f
+#define r_sqrt sqrtf
+#define r_fabs fabsf
+#define r_floor floorf
+#endif
+
+#define PI_R K(3.14159265358979323846)
+#define TWO_PI_R K(6.28318530717958647692)
+#define HALF_PI_R K(1.57079632679489661923)
+
+static inline real r_min(real a, real b) { return a < b ? a : b; }
+static inline real r_max(real a, real b) { return a > b ? a : b; }
+static inline real r_clamp(real x, real lo, real hi) { return r_min(r_max(x, lo), hi); }
+
+/* ------------------------------------------------------------------------- */
+/* Philox4x32-10 (Salmon et al. 2011), counter = (global env id, step, stream, sub) */
+/* ------------------------------------------------------------------------- */
+#define RNG_OBS 0u
+#define RNG_RESET 1u
+#define RNG_PUSH_HF 3u
+#define RNG_PUSH_LF 4u
+#define RNG_ACTION 5u
+#define RNG_STARTUP 6u
+#define RNG_OBS_EXTRA 7u
+#define RNG_CMD 8u
+
+static void philox4x32(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t out[4]) {
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    for (int r = 0; r < 10; ++r) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+        uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0;
+        uint32_t hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+        uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+/* [0,1) with 24 random bits (exact in fp32) */
+static inline real u01(uint32_t x) { return (real)(x >> 8) * K(5.9604644775390625e-08); }
+/* (0,1] */
+static inline real u01_open(uint32_t x) { return (real)((x >> 8) + 1u) * K(5.9604644775390625e-08); }
+static inline real uniform(uint32_t x, real lo, real hi) { return lo + (hi - lo) * u01(x); }
+
+/* ------------------------------------------------------------------------- */
+/* deterministic elementary functions (cephes single-precision kernels)      */
+/* ------------------------------------------------------------------------- */
+#ifdef WLO_DOUBLE
+static void det_sincos(real x, real* s, real* c) { *s = sin(x); *c = cos(x); }
+static real det_atan(real x) { return atan(x); }
+static real det_atan2(real y, real x) { return atan2(y, x); }
+static real det_log(real x) { return log(x); }
+#else
+static void det_sincos(float x, float* s, float* c) {
+    float q = floorf(x * 0.63661977236758134f + 0.5f);
+    float y = x - q * 1.5703125f;
+    y = y - q * 4.837512969970703125e-4f;
+    y = y - q * 7.54978995489188216e-8f;
+    int qi = (int)q;
+    float z = y * y;
+    float sp = ((-1.9515295891e-4f * z + 8.3321608736e-3f) * z - 1.6666654611e-1f) * z * y + y;
+    float cp = ((2.443315711809948e-5f * z - 1.388731625493765e-3f) * z + 4.166664568298827e-2f) * z * z -
+               0.5f * z + 1.0f;
+    switch (qi & 3) {
+        case 0: *s = sp; *c = cp; break;
+        case 1: *s = cp; *c = -sp; break;
+        case 2: *s = -sp; *c = -cp; break;
+        default: *s = -cp; *c = sp; break;
+    }
+}
+static float det_atan(float xx) {
+    float sign = 1.0f, x = xx, y;
+    if (x < 0.0f) { sign = -1.0f; x = -x; }
+    if (x > 2.414213562373095f) { y = 1.5707963267948966f; x = -(1.0f / x); }
+    else if (x > 0.4142135623730950f) { y = 0.7853981633974483f; x = (x - 1.0f) / (x + 1.0f); }
+    else y = 0.0f;
+    float z = x * x;
+    y += (((8.05374449538e-2f * z - 1.38776856032e-1f) * z + 1.99777106478e-1f) * z - 3.33329491539e-1f) * z * x + x;
+    return sign * y;
+}
+static float det_atan2(float y, float x) {
+    if (x == 0.0f) {
+        if (y > 0.0f) return 1.5707963267948966f;
+        if (y < 0.0f) return -1.5707963267948966f;
+        return 0.0f;
+    }
+    float z = det_atan(y / x);
+    if (x < 0.0f) z = (y >= 0.0f) ? z + 3.14159265358979323846f : z - 3.14159265358979323846f;
+    return z;
+}
+static float det_log(float xin) {
+    uint32_t bits; memcpy(&bits, &xin, 4);
+    int e = (int)((bits >> 23) & 0xffu) - 126;
+    bits = (bits & 0x807fffffu) | 0x3f000000u;
+    float x; memcpy(&x, &bits, 4);
+    if (x < 0.707106781186547524f) { e -= 1; x = x + x - 1.0f; } else { x = x - 1.0f; }
+    float z = x * x;
+    float y = ((((((((7.0376836292e-2f * x - 1.1514610310e-1f) * x + 1.1676998740e-1f) * x - 1.2420140846e-1f) * x +
+                    1.4249322787e-1f) * x - 1.6668057665e-1f) * x + 2.0000714765e-1f) * x - 2.4999993993e-1f) * x +
+               3.3333331174e-1f) * x * z;
+    float fe = (float)e;
+    y += -2.12194440e-4f * fe;
+    y += -0.5f * z;
+    z = x + y;
+    z += 0.693359375f * fe;
+    return z;
+}
+#endif
+static real det_tan(real x) { real s, c; det_sincos(x, &s, &c); return s / c; }
+static real det_asin(real x) { return det_atan2(x, r_sqrt((K(1.0) - x) * (K(1.0) + x))); }
+
+/* two standard normals from two u32 (Box-Muller) */
+static void box_muller(uint32_t a, uint32_t b, real* z0, real* z1) {
+    real u1 = u01_open(a), u2 = u01(b);
+    real r = r_sqrt(K(-2.0) * det_log(u1));
+    real s, c; det_sincos(TWO_PI_R * u2, &s, &c);
+    *z0 = r * c; *z1 = r * s;
+}
+
+/* ------------------------------------------------------------------------- */
+/* per-env state (AoS here on purpose: readable; the product is AoSoA float4)  */
+/* ------------------------------------------------------------------------- */
+typedef struct {
+    real p[3], q[4], v[3], w[3];            /* root link pos, quat wxyz, COM lin vel (world), ang vel (world) */
+    real omega[4];                          /* wheel spin [bl,br,fl,fr] */
+    real steer[2], steer_vel[2];            /* front left/right steer joint */
+    real action[2], prev_action[2];
+    int32_t ep_len;
+    real t_hf, t_lf;
+    real sums[WL_MAX_REW_TERMS];
+    real mass, inv_mass, spare0, spare1;
+    real D[4], C[4], kd[4];
+    real cmd[4];
+} wlo_env;
+
+typedef struct wlo_sim {
+    wl_config cfg;
+    wlo_env* env;
+    real rew_weight[WL_MAX_REW_TERMS];
+    double log_sum[2][WL_MAX_REW_TERMS];
+    double log_term[2][4];
+    int32_t any_reset[2];
+    float* hf;
+} wlo_sim;
+
+static void rotmat(const real q[4], real R[9]) {
+    real w = q[0], x = q[1], y = q[2], z = q[3];
+    real xx = x * x, yy = y * y, zz = z * z, xy = x * y, xz = x * z, yz = y * z, wx = w * x, wy = w * y, wz = w * z;
+    R[0] = K(1.0) - K(2.0) * (yy + zz); R[1] = K(2.0) * (xy - wz); R[2] = K(2.0) * (xz + wy);
+    R[3] = K(2.0) * (xy + wz); R[4] = K(1.0) - K(2.0) * (xx + zz); R[5] = K(2.0) * (yz - wx);
+    R[6] = K(2.0) * (xz - wy); R[7] = K(2.0) * (yz + wx); R[8] = K(1.0) - K(2.0) * (xx + yy);
+}
+/* out = R a   /   out = R^T a */
+static void rot(const real R[9], const real a[3], real o[3]) {
+    o[0] = R[0] * a[0] + R[1] * a[1] + R[2] * a[2];
+    o[1] = R[3] * a[0] + R[4] * a[1] + R[5] * a[2];
+    o[2] = R[6] * a[0] + R[7] * a[1] + R[8] * a[2];
+}
+static void rotT(const real R[9], const real a[3], real o[3]) {
+    o[0] = R[0] * a[0] + R[3] * a[1] + R[6] * a[2];
+    o[1] = R[1] * a[0] + R[4] * a[1] + R[7] * a[2];
+    o[2] = R[2] * a[0] + R[5] * a[1] + R[8] * a[2];
+}
+static void cross(const real a[3], const real b[3], real o[3]) {
+    o[0] = a[1] * b[2] - a[2] * b[1];
+    o[1] = a[2] * b[0] - a[0] * b[2];
+    o[2] = a[0] * b[1] - a[1] * b[0];
+}
+
+/* ------------------------------------------------------------------------- */
+/* terrain: height z and unit normal n at world (x,y)                          */
+/* Drift/Visual: plane z=0 (mushr_drift_env_cfg.py:39-51).                     */
+/* Elevation: bilinear height-field (raster of Terrains/huge_compact.usd or    */
+/* procedural), ground plane hf_outside_z outside the raster                   */
+/* (elevation/mushr_elevation_env_cfg.py:95-128).                              */
+/* ------------------------------------------------------------------------- */
+static inline real hf_at(const wlo_sim* s, int ix, int iy) { return (real)s->hf[(size_t)iy * s->cfg.hf_nx + ix]; }
+
+/* returns 1 when (x,y) is inside the raster */
+static int hf_sample(const wlo_sim* s, real x, real y, real* z, real* gx, real* gy) {
+    const wl_config* c = &s->cfg;
+    real inv = K(1.0) / (real)c->hf_cell;
+    real fx = (x - (real)c->hf_x0) * inv, fy = (y - (real)c->hf_y0) * inv;
+    if (!(fx >= K(0.0)) || !(fy >= K(0.0)) || !(fx <= (real)(c->hf_nx - 1)) || !(fy <= (real)(c->hf_ny - 1))) return 0;
+    int ix = (int)r_floor(fx), iy = (int)r_floor(fy);
+    if (ix > c->hf_nx - 2) ix = c->hf_nx - 2;
+    if (iy > c->hf_ny - 2) iy = c->hf_ny - 2;
+    real tx = fx - (real)ix, ty = fy - (real)iy;
+    real z00 = hf_at(s, ix, iy), z10 = hf_at(s, ix + 1, iy), z01 = hf_at(s, ix, iy + 1), z11 = hf_at(s, ix + 1, iy + 1);
+    real za = z00 + (z10 - z00) * tx, zb = z01 + (z11 - z01) * tx;
+    *z = za + (zb - za) * ty;
+    *gx = ((z10 - z00) + ((z11 - z01) - (z10 - z00)) * ty) * inv;
+    *gy = (zb - za) * inv;
+    return 1;
+}
+static void terrain(const wlo_sim* s, real x, real y, real* z, real n[3]) {
+    if (s->cfg.task == WL_TASK_ELEVATION && s->hf) {
+        real gx, gy;
+        if (hf_sample(s, x, y, z, &gx, &gy)) {
+            real inv = K(1.0) / r_sqrt(gx * gx + gy * gy + K(1.0));
+            n[0] = -gx * inv; n[1] = -gy * inv; n[2] = inv;
+            return;
+        }
+        *z = (real)s->cfg.hf_outside_z;
+    } else {
+        *z = K(0.0);
+    }
+    n[0] = K(0.0); n[1] = K(0.0); n[2] = K(1.0);
+}
+
+/* ------------------------------------------------------------------------- */
+/* A. action term.  ackermann_actions.py:119-133 (process), :136-145 (apply), */
+/*    rc_car_actions.py:12-29 (RWD), :36-64 (4WD), ackermann_actions.py:150-201 */
+/* ------------------------------------------------------------------------- */
+static int process_action(const wl_config* c, const float a_in[2], real wheel_target[4], real steer_target[2]) {
+    real a0 = (real)a_in[0], a1 = (real)a_in[1];
+    if (c->bounding == WL_BOUND_CLIP) { a0 = r_clamp(a0, K(-1.0), K(1.0)); a1 = r_clamp(a1, K(-1.0), K(1.0)); }
+    else if (c->bounding != WL_BOUND_NONE) return WL_EUNSUPPORTED;
+    real v = a0 * (real)c->act_scale[0] + (real)c->act_offset[0];
+    real delta = a1 * (real)c->act_scale[1] + (real)c->act_offset[1];
+    if (c->no_reverse) v = r_max(v, K(0.0));
+    real tan_d = det_tan(delta);
+    real L = (real)c->base_length, W = (real)c->base_width, r = (real)c->wheel_radius_cfg;
+    if (c->action_kind == WL_ACT_RWD) {
+        real wt = v / r;
+        wheel_target[WL_BL] = wt; wheel_target[WL_BR] = wt; wheel_target[WL_FL] = K(0.0); wheel_target[WL_FR] = K(0.0);
+        steer_target[0] = tan_d; steer_target[1] = tan_d;      /* quirk Q1: tan(delta) is the position target */
+        return 0;
+    }
+    real Rt = (tan_d == K(0.0)) ? K(1.0e6) : L / tan_d;
+    real hw = W / K(2.0);
+    real Rl = Rt - hw, Rr = Rt + hw;
+    real Rrl = r_sqrt(Rl * Rl + L * L), Rrr = r_sqrt(Rr * Rr + L * L);
+    real den = Rt * r;
+    wheel_target[WL_FL] = v * r_fabs(Rrl / den);
+    wheel_target[WL_FR] = v * r_fabs(Rrr / den);
+    wheel_target[WL_BL] = v * r_fabs(Rl / den);
+    wheel_target[WL_BR] = v * r_fabs(Rr / den);
+    if (c->action_kind == WL_ACT_4WD) { steer_target[0] = tan_d; steer_target[1] = tan_d; }
+    else { steer_target[0] = det_atan(L / Rl); steer_target[1] = det_atan(L / Rr); }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------- */
+/* a7 DC motor (hound.py:13-21,40-43; IsaacLab DCMotor._clip_effort [UPSTREAM-RECALL]) */
+/* ------------------------------------------------------------------------- */
+static real dc_motor(const wl_config* c, real kd, real effort_limit, real target, real omega) {
+    if (!(effort_limit > K(0.0))) return K(0.0);        /* passive joint, hound.py:44-51 */
+    real tau = kd * (target - omega);                    /* stiffness = 0 */
+    real sat = (real)c->dc_saturation, vl = (real)c->dc_vel_limit;
+    real ratio = omega / vl;
+    real max_eff = r_clamp(sat * (K(1.0) - ratio), K(0.0), effort_limit);
+    real min_eff = r_clamp(sat * (K(-1.0) - ratio), -effort_limit, K(0.0));
+    return r_clamp(tau, min_eff, max_eff);
+}
+
+/* ------------------------------------------------------------------------- */
+/* a8 one integrator sub-step of length h (builder-defined model)    */
+/* body-frame quantities: vb, wb; pc = COM position (world)                     */
+/* ------------------------------------------------------------------------- */
+typedef struct { real pc[3]; real q[4]; real v[3]; real wb[3]; } chassis_t;
+/* per-env-step invariants (reciprocals are formed ONCE per env step, in this order) */
+typedef struct { real h, inv_h, sden, inv_Iw, I[3], invI[3]; } step_consts;
+
+static void make_step_consts(const wl_config* c, const wlo_env* e, step_consts* k) {
+    k->h = (real)c->sim_dt / (real)c->substeps;
+    k->inv_h = K(1.0) / k->h;
+    k->sden = K(1.0) / ((real)c->steer_inertia + k->h * (real)c->steer_kd + k->h * k->h * (real)c->steer_kp);
+    k->inv_Iw = K(1.0) / (real)c->wheel_inertia;
+    real ms = e->mass / (real)c->mass_nominal;          /* inertia scales with the mass ratio (a14) */
+    for (int a = 0; a < 3; ++a) { k->I[a] = (real)c->inertia_nominal[a] * ms; k->invI[a] = K(1.0) / k->I[a]; }
+}
+
+static void physics_substep(const wlo_sim* s, wlo_env* e, chassis_t* b, const real tau[4], const real steer_target[2],
+                            const step_consts* k) {
+    const wl_config* c = &s->cfg;
+    real h = k->h;
+    real R[9]; rotmat(b->q, R);
+    /* steering: implicit PD on the steer joint (hound.py:5-12) */
+    real J = (real)c->steer_inertia, kp = (real)c->steer_kp;
+    real sden = k->sden;
+    real sn[2], cs[2];
+    for (int j = 0; j < 2; ++j) {
+        real vel = (J * e->steer_vel[j] + h * kp * (steer_target[j] - e->steer[j])) * sden;
+        vel = r_clamp(vel, -(real)c->steer_vel_limit, (real)c->steer_vel_limit);
+        real pos = r_clamp(e->steer[j] + h * vel, -(real)c->steer_pos_limit, (real)c->steer_pos_limit);
+        e->steer_vel[j] = vel; e->steer[j] = pos;
+        det_sincos(pos, &sn[j], &cs[j]);
+    }
+    real vb[3]; rotT(R, b->v, vb);
+    real Fb[3] = {K(0.0), K(0.0), K(0.0)}, Tb[3] = {K(0.0), K(0.0), K(0.0)};
+    real rw = (real)c->wheel_radius, bw = (real)c->wheel_damping;
+    real inv_h = k->inv_h;
+    for (int i = 0; i < 4; ++i) {
+        real rho[3];
+        rho[0] = ((i >= 2) ? (real)c->hub_x_front : (real)c->hub_x_rear) - (real)c->com[0];
+        rho[1] = ((i & 1) ? -(real)c->hub_y : (real)c->hub_y) - (real)c->com[1];
+        rho[2] = (real)c->hub_z - (real)c->com[2];
+        real hubw[3]; rot(R, rho, hubw);
+        hubw[0] += b->pc[0]; hubw[1] += b->pc[1]; hubw[2] += b->pc[2];
+        real zt, nw[3]; terrain(s, hubw[0], hubw[1], &zt, nw);
+        real comp = rw - (hubw[2] - zt) * nw[2];
+        /* drive torque first, then friction against the resulting slip (implicit stick) */
+        real om_star = e->omega[i] + h * ((tau[i] - bw * e->omega[i]) * k->inv_Iw);
+        real Fx = K(0.0);
+        if (comp > K(0.0)) {
+            real nb[3]; rotT(R, nw, nb);
+            real rc[3] = {rho[0] - rw * nb[0], rho[1] - rw * nb[1], rho[2] - rw * nb[2]};
+            real wxr[3]; cross(b->wb, rc, wxr);
+            real vc[3] = {vb[0] + wxr[0], vb[1] + wxr[1], vb[2] + wxr[2]};
+            real sdot = -(nb[0] * vc[0] + nb[1] * vc[1] + nb[2] * vc[2]);
+            real Fz = (real)c->susp_k * comp + (real)c->susp_c * sdot;
+            if (comp > (real)c->susp_travel) Fz += (real)c->bump_k * (comp - (real)c->susp_travel);
+            Fz = r_max(Fz, K(0.0));
+            real hb[3];
+            if (i >= 2) { hb[0] = cs[i - 2]; hb[1] = sn[i - 2]; hb[2] = K(0.0); }
+            else { hb[0] = K(1.0); hb[1] = K(0.0); hb[2] = K(0.0); }
+            real d = hb[0] * nb[0] + hb[1] * nb[1] + hb[2] * nb[2];
+            real ft[3] = {hb[0] - d * nb[0], hb[1] - d * nb[1], hb[2] - d * nb[2]};
+            real finv = K(1.0) / r_sqrt(ft[0] * ft[0] + ft[1] * ft[1] + ft[2] * ft[2]);
+            ft[0] *= finv; ft[1] *= finv; ft[2] *= finv;
+            real lt[3]; cross(nb, ft, lt);
+            real vx = vc[0] * ft[0] + vc[1] * ft[1] + vc[2] * ft[2];
+            real vy = vc[0] * lt[0] + vc[1] * lt[1] + vc[2] * lt[2];
+            real vsx = vx - om_star * rw;
+            real invden = K(1.0) / r_max(r_fabs(vx), (real)c->tire_v0);
+            real kappa = -vsx * invden, ta = -vy * invden;
+            real sigma = r_sqrt(kappa * kappa + ta * ta);
+            real Fy = K(0.0);
+            if (sigma > K(1.0e-9)) {
+                real sm, cm; det_sincos(e->C[i] * det_atan((real)c->tire_B * sigma), &sm, &cm);
+                real Fmag = Fz * (e->D[i] * sm) / sigma;
+                Fx = Fmag * kappa; Fy = Fmag * ta;
+                real fxm = (real)c->tire_mx * r_fabs(vsx) * inv_h, fym = (real)c->tire_my * r_fabs(vy) * inv_h;
+                Fx = r_clamp(Fx, -fxm, fxm); Fy = r_clamp(Fy, -fym, fym);
+            }
+            real F[3] = {Fz * nb[0] + Fx * ft[0] + Fy * lt[0], Fz * nb[1] + Fx * ft[1] + Fy * lt[1],
+                         Fz * nb[2] + Fx * ft[2] + Fy * lt[2]};
+            real T[3]; cross(rc, F, T);
+            Fb[0] += F[0]; Fb[1] += F[1]; Fb[2] += F[2];
+            Tb[0] += T[0]; Tb[1] += T[1]; Tb[2] += T[2];
+        }
+        e->omega[i] = om_star - h * ((rw * Fx) * k->inv_Iw);
+    }
+    /* chassis: semi-implicit Euler, Euler's equations in the body frame (gyroscopic term on, mushr.py:28) */
+    real Fw[3]; rot(R, Fb, Fw);
+    b->v[0] = b->v[0] + h * (Fw[0] * e->inv_mass);
+    b->v[1] = b->v[1] + h * (Fw[1] * e->inv_mass);
+    b->v[2] = b->v[2] + h * (Fw[2] * e->inv_mass - (real)c->gravity);
+    real Iw3[3] = {k->I[0] * b->wb[0], k->I[1] * b->wb[1], k->I[2] * b->wb[2]};
+    real g[3]; cross(b->wb, Iw3, g);
+    b->wb[0] = b->wb[0] + h * ((Tb[0] - g[0]) * k->invI[0]);
+    b->wb[1] = b->wb[1] + h * ((Tb[1] - g[1]) * k->invI[1]);
+    b->wb[2] = b->wb[2] + h * ((Tb[2] - g[2]) * k->invI[2]);
+    b->pc[0] = b->pc[0] + h * b->v[0];
+    b->pc[1] = b->pc[1] + h * b->v[1];
+    b->pc[2] = b->pc[2] + h * b->v[2];
+    real hh = K(0.5) * h;
+    real qw = b->q[0], qx = b->q[1], qy = b->q[2], qz = b->q[3];
+    real ox = b->wb[0], oy = b->wb[1], oz = b->wb[2];
+    real nqw = qw - hh * (qx * ox + qy * oy + qz * oz);
+    real nqx = qx + hh * (qw * ox + qy * oz - qz * oy);
+    real nqy = qy + hh * (qw * oy + qz * ox - qx * oz);
+    real nqz = qz + hh * (qw * oz + qx * oy - qy * ox);
+    real qinv = K(1.0) / r_sqrt(nqw * nqw + nqx * nqx + nqy * nqy + nqz * nqz);
+    b->q[0] = nqw * qinv; b->q[1] = nqx * qinv; b->q[2] = nqy * qinv; b->q[3] = nqz * qinv;
+}
+
+/* ------------------------------------------------------------------------- */
+/* euler_xyz_from_quat [UPSTREAM-RECALL isaaclab.utils.math], each angle % 2pi */
+/* used by root_euler_xyz, wheeledlab/envs/mdp/observations.py:9-12            */
+/* ------------------------------------------------------------------------- */
+static inline real wrap_2pi(real a) { return (a < K(0.0)) ? a + TWO_PI_R : a; }
+static void euler_xyz(const real q[4], real e[3]) {
+    real w = q[0], x = q[1], y = q[2], z = q[3];
+    real sin_roll = K(2.0) * (w * x + y * z), cos_roll = K(1.0) - K(2.0) * (x * x + y * y);
+    real sin_pitch = K(2.0) * (w * y - z * x);
+    real sin_yaw = K(2.0) * (w * z + x * y), cos_yaw = K(1.0) - K(2.0) * (y * y + z * z);
+    real pitch;
+    if (r_fabs(sin_pitch) >= K(1.0)) pitch = (sin_pitch < K(0.0)) ? -HALF_PI_R : HALF_PI_R;
+    else pitch = det_asin(sin_pitch);
+    e[0] = wrap_2pi(det_atan2(sin_roll, cos_roll));
+    e[1] = wrap_2pi(pitch);
+    e[2] = wrap_2pi(det_atan2(sin_yaw, cos_yaw));
+}
+
+/* ------------------------------------------------------------------------- */
+/* drift terminations.  mushr_drift_env_cfg.py:201-217 (in_range/off_track),  */
+/* :343-348 (cart_off_track)                                                   */
+/* ------------------------------------------------------------------------- */
+static int drift_off_track(const wl_config* c, real x, real y) {
+    real st = (real)c->trk_straight, ro = (real)c->trk_corner_out, ri = (real)c->trk_corner_in;
+    int off, in;
+    if (r_fabs(y) < st) { off = r_fabs(x) > ro; in = r_fabs(x) < ri; }
+    else if (y > K(0.0)) {
+        real d2 = (y - st) * (y - st) + x * x;
+        off = d2 > ro * ro; in = d2 < ri * ri;
+    } else {
+        real d2 = (y + st) * (y + st) + x * x;
+        off = d2 > ro * ro; in = d2 < ri * ri;
+    }
+    return off || in;
+}
+
+/* drift reward terms, mushr_drift_env_cfg.py:160-240; returns f_i (unweighted) */
+static void drift_reward_terms(const wl_config* c, const wlo_env* e, const real p[3], const real vb[3], const real wb[3],
+                               real wz_world, int out_of_bounds, int time_out, real f[WL_MAX_REW_TERMS]) {
+    /* side_slip :219-230 (params :246-254) */
+    real slip = r_fabs(det_atan2(vb[1], vb[0]));
+    real valid = (r_fabs(vb[0]) < (real)c->slip_min_vel_x || slip > (real)c->slip_max_thresh) ? K(0.0) : slip;
+    if (valid < (real)c->slip_min_thresh) valid = K(0.0);
+    f[WL_DR_SIDE_SLIP] = valid;
+    /* vel_dist :167-171 */
+    real gs = r_sqrt(vb[0] * vb[0] + vb[1] * vb[1]);
+    real dv = gs - (real)c->vel_speed_target;
+    f[WL_DR_VEL] = dv * dv + (real)c->vel_offset;
+    /* track_progress_rate :160-165: world yaw rate */
+    f[WL_DR_PROGRESS] = wz_world;
+    /* turn_left_go_right :232-240 */
+    real sm = (e->steer[0] + e->steer[1]) / K(2.0);
+    real av = r_clamp(wb[2], -(real)c->tlgr_ang_vel_thresh, (real)c->tlgr_ang_vel_thresh);
+    real tl = sm * av * K(-1.0);
+    f[WL_DR_TLGR] = r_max(tl, K(0.0));
+    /* energy_through_turn :195-199 (3-D body speed, quirk Q7) */
+    real sp = r_sqrt(vb[0] * vb[0] + vb[1] * vb[1] + vb[2] * vb[2]);
+    f[WL_DR_TURN_ENERGY] = (r_fabs(p[1]) > (real)c->energy_straight) ? sp * sp : K(0.0);
+    /* cross_track_dist :173-193 (p = 1) */
+    real st = (real)c->trk_straight, tr = (real)c->ctd_track_radius, sq;
+    if (r_fabs(p[1]) < st) {
+        real d = (p[0] > K(0.0)) ? (p[0] - tr) : (p[0] + tr);
+        sq = d * d;
+    } else {
+        real yy = (p[1] > K(0.0)) ? (p[1] - st) : (p[1] + st);
+        real d = r_sqrt(yy * yy + p[0] * p[0]) - tr;
+        sq = d * d;
+    }
+    f[WL_DR_CROSS_TRACK] = r_sqrt(sq) + (real)c->ctd_offset;
+    /* is_terminated_term(["out_of_bounds"]) :295-299 [UPSTREAM-RECALL: * ~time_outs] */
+    f[WL_DR_TERM_PENS] = (out_of_bounds && !time_out) ? K(1.0) : K(0.0);
+    f[7] = K(0.0);
+}
+
+/* ------------------------------------------------------------------------- */
+/* reset_root_state_along_track.__call__, drifting/mdp/events.py:102-133       */
+/* ------------------------------------------------------------------------- */
+static void sample_interval_timers(const wl_config* c, wlo_env* e, uint32_t a, uint32_t b) {
+    e->t_hf = uniform(a, (real)c->push_hf_interval[0], (real)c->push_hf_interval[1]);
+    e->t_lf = uniform(b, (real)c->push_lf_interval[0], (real)c->push_lf_interval[1]);
+}
+static void drift_reset_env(const wl_config* c, wlo_env* e, uint32_t gid, int64_t t) {
+    uint32_t r[4], r2[4];
+    philox4x32(c->seed, gid, (uint32_t)t, RNG_RESET, 0u, r);
+    uint32_t idx = (uint32_t)(((uint64_t)r[0] * (uint64_t)c->num_ref_poses) >> 32);
+    real nx = (K(2.0) * u01(r[1]) - K(1.0)) * (real)c->reset_pos_noise;
+    real ny = (K(2.0) * u01(r[2]) - K(1.0)) * (real)c->reset_pos_noise;
+    real nyaw = (K(2.0) * u01(r[3]) - K(1.0)) * (real)c->reset_yaw_noise;
+    e->p[0] = (real)c->ref_poses[3 * idx + 0] + nx;
+    e->p[1] = (real)c->ref_poses[3 * idx + 1] + ny;
+    e->p[2] = K(0.0);
+    real yaw = (real)c->ref_poses[3 * idx + 2] * K(0.017453292519943295) + nyaw;   /* deg2rad, :126 */
+    real sh, ch; det_sincos(yaw * K(0.5), &sh, &ch);
+    e->q[0] = ch; e->q[1] = K(0.0); e->q[2] = K(0.0); e->q[3] = sh;                 /* roll = pitch = 0 */
+    for (int k = 0; k < 3; ++k) { e->v[k] = K(0.0); e->w[k] = K(0.0); }
+    /* joint state untouched (quirk Q3).  manager resets [UPSTREAM-RECALL Appendix B]: */
+    e->ep_len = 0;
+    for (int k = 0; k < WL_MAX_REW_TERMS; ++k) e->sums[k] = K(0.0);
+    e->action[0] = e->action[1] = e->prev_action[0] = e->prev_action[1] = K(0.0);
+    philox4x32(c->seed, gid, (uint32_t)t, RNG_RESET, 1u, r2);
+    sample_interval_timers(c, e, r2[0], r2[1]);
+}
+
+/* interval pushes, mushr_drift_env_cfg.py:121-143; push_by_setting_velocity (+=) [UPSTREAM-RECALL a13] */
+static void interval_pushes(const wl_config* c, wlo_env* e, uint32_t gid, int64_t t, real step_dt) {
+    if (!c->push_enable) return;
+    e->t_hf = e->t_hf - step_dt;
+    if (e->t_hf < K(1.0e-6)) {
+        uint32_t r[4]; philox4x32(c->seed, gid, (uint32_t)t, RNG_PUSH_HF, 0u, r);
+        e->v[0] = e->v[0] + uniform(r[0], -(real)c->push_hf_range[0], (real)c->push_hf_range[0]);
+        e->v[1] = e->v[1] + uniform(r[1], -(real)c->push_hf_range[1], (real)c->push_hf_range[1]);
+        e->w[2] = e->w[2] + uniform(r[2], -(real)c->push_hf_range[2], (real)c->push_hf_range[2]);
+        e->t_hf = uniform(r[3], (real)c->push_hf_interval[0], (real)c->push_hf_interval[1]);
+    }
+    e->t_lf = e->t_lf - step_dt;
+    if (e->t_lf < K(1.0e-6)) {
+        uint32_t r[4]; philox4x32(c->seed, gid, (uint32_t)t, RNG_PUSH_LF, 0u, r);
+        e->w[2] = e->w[2] + uniform(r[0], -(real)c->push_lf_yaw, (real)c->push_lf_yaw);
+        e->t_lf = uniform(r[1], (real)c->push_lf_interval[0], (real)c->push_lf_interval[1]);
+    }
+}
+
+/* BlindObsCfg.PolicyCfg, wheeledlab_tasks/common/observations.py:19-56 */
+static void blind_obs(const wl_config* c, const wlo_env* e, uint32_t gid, uint32_t t, uint32_t stream, uint32_t sub0, float* obs) {
+    real R[9]; rotmat(e->q, R);
+    real vb[3], wb[3], eu[3]; rotT(R, e->v, vb); rotT(R, e->w, wb); euler_xyz(e->q, eu);
+    real z[12];
+    for (int k = 0; k < 12; ++k) z[k] = K(0.0);
+    if (c->enable_corruption) {
+        for (uint32_t k = 0; k < 3; ++k) {
+            uint32_t r[4]; philox4x32(c->seed, gid, t, stream, sub0 + k, r);
+            box_muller(r[0], r[1], &z[4 * k + 0], &z[4 * k + 1]);
+            box_muller(r[2], r[3], &z[4 * k + 2], &z[4 * k + 3]);
+        }
+    }
+    for (int k = 0; k < 3; ++k) {
+        obs[0 + k] = (float)(e->p[k] + (real)c->noise_std[0] * z[0 + k]);   /* root_pos_w - env_origin(=0) */
+        obs[3 + k] = (float)(eu[k] + (real)c->noise_std[1] * z[3 + k]);
+        obs[6 + k] = (float)(vb[k] + (real)c->noise_std[2] * z[6 + k]);
+        obs[9 + k] = (float)(wb[k] + (real)c->noise_std[3] * z[9 + k]);
+    }
+    obs[12] = (float)r_clamp(e->action[0], K(-1.0), K(1.0));               /* last_action, clip (-1,1), no noise */
+    obs[13] = (float)r_clamp(e->action[1], K(-1.0), K(1.0));
+}
+
+/* ------------------------------------------------------------------------- */
+/* one env.step() for one env -- ordering per SURVEY 3.3 A..I                  */
+/* ------------------------------------------------------------------------- */
+typedef struct { double sum[WL_MAX_REW_TERMS]; double n_reset, n_term, n_timeout; int any; } step_log;
+
+static int env_step(wlo_sim* s, int li, const float* a_in, int64_t t, float* obs, float* rew, uint8_t* term_o,
+                    uint8_t* trunc_o, step_log* lg) {
+    const wl_config* c = &s->cfg;
+    wlo_env* e = &s->env[li];
+    uint32_t gid = (uint32_t)(c->env_id_offset + li);
+    /* A. action manager: prev <- action <- raw */
+    e->prev_action[0] = e->action[0]; e->prev_action[1] = e->action[1];
+    e->action[0] = (real)a_in[0]; e->action[1] = (real)a_in[1];
+    real wheel_target[4], steer_target[2];
+    int rc = process_action(c, a_in, wheel_target, steer_target);
+    if (rc) return rc;
+    /* B. decimation x (actuators -> physics) */
+    chassis_t b;
+    real R[9]; rotmat(e->q, R);
+    real cw[3]; { real cc[3] = {(real)c->com[0], (real)c->com[1], (real)c->com[2]}; rot(R, cc, cw); }
+    for (int k = 0; k < 3; ++k) { b.pc[k] = e->p[k] + cw[k]; b.v[k] = e->v[k]; }
+    for (int k = 0; k < 4; ++k) b.q[k] = e->q[k];
+    rotT(R, e->w, b.wb);
+    step_consts kc; make_step_consts(c, e, &kc);
+    for (int d = 0; d < c->decimation; ++d) {
+        real tau[4];
+        for (int i = 0; i < 4; ++i) tau[i] = dc_motor(c, e->kd[i], (real)c->dc_effort[i], wheel_target[i], e->omega[i]);
+        for (int j = 0; j < c->substeps; ++j) physics_substep(s, e, &b, tau, steer_target, &kc);
+    }
+    rotmat(b.q, R);
+    { real cc[3] = {(real)c->com[0], (real)c->com[1], (real)c->com[2]}; rot(R, cc, cw); }
+    for (int k = 0; k < 3; ++k) { e->p[k] = b.pc[k] - cw[k]; e->v[k] = b.v[k]; }
+    for (int k = 0; k < 4; ++k) e->q[k] = b.q[k];
+    rot(R, b.wb, e->w);
+    /* C. counters */
+    e->ep_len += 1;
+    /* D. terminations (time_out first in cfg order, :351-362) */
+    int time_out = e->ep_len >= c->max_episode_length;
+    int terminated = 0;
+    real step_dt = (real)c->sim_dt * (real)c->decimation;
+    real f[WL_MAX_REW_TERMS];
+    real vb[3]; rotT(R, e->v, vb);
+    if (c->task == WL_TASK_DRIFT) {
+        terminated = drift_off_track(c, e->p[0], e->p[1]);
+        drift_reward_terms(c, e, e->p, vb, b.wb, e->w[2], terminated, time_out, f);
+    } else {
+        return WL_EUNSUPPORTED;
+    }
+    /* E. reward manager [UPSTREAM-RECALL Appendix B]: value = f*w*dt, skip w==0 */
+    real total = K(0.0);
+    for (int k = 0; k < c->num_rew_terms; ++k) {
+        if (s->rew_weight[k] == K(0.0)) continue;
+        real val = f[k] * s->rew_weight[k] * step_dt;
+        total += val;
+        e->sums[k] += val;
+    }
+    *rew = (float)total;
+    *term_o = (uint8_t)terminated; *trunc_o = (uint8_t)time_out;
+    /* F. auto reset */
+    if (terminated || time_out) {
+        lg->any = 1; lg->n_reset += 1.0; lg->n_term += terminated ? 1.0 : 0.0; lg->n_timeout += time_out ? 1.0 : 0.0;
+        for (int k = 0; k < WL_MAX_REW_TERMS; ++k) lg->sum[k] += (double)e->sums[k];
+        drift_reset_env(c, e, gid, t);
+    }
+    /* H. interval events on the post-reset state */
+    interval_pushes(c, e, gid, t, step_dt);
+    /* I. observations */
+    blind_obs(c, e, gid, (uint32_t)t, RNG_OBS, 0u, obs);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------- */
+/* exported API (host pointers)                                                */
+/* ------------------------------------------------------------------------- */
+wlo_sim* wlo_create(const wl_config* cfg, const float* heightfield) {
+    wlo_sim* s = (wlo_sim*)calloc(1, sizeof(wlo_sim));
+    s->cfg = *cfg;
+    s->env = (wlo_env*)calloc((size_t)cfg->num_envs, sizeof(wlo_env));
+    for (int k = 0; k < WL_MAX_REW_TERMS; ++k) s->rew_weight[k] = (real)cfg->rew_weight[k];
+    if (heightfield && cfg->hf_nx > 0) {
+        size_t n = (size_t)cfg->hf_nx * cfg->hf_ny;
+        s->hf = (float*)malloc(n * sizeof(float));
+        memcpy(s->hf, heightfield, n * sizeof(float));
+    }
+    for (int i = 0; i < cfg->num_envs; ++i) s->env[i].q[0] = K(1.0);
+    return s;
+}
+void wlo_destroy(wlo_sim* s) { if (s) { free(s->env); free(s->hf); free(s); } }
+int wlo_is_double(void) {
+#ifdef WLO_DOUBLE
+    return 1;
+#else
+    return 0;
+#endif
+}
+
+/* startup events a14: material buckets, actuator gains, base mass; initial interval timers */
+int wlo_startup(wlo_sim* s) {
+    const wl_config* c = &s->cfg;
+    for (int li = 0; li < c->num_envs; ++li) {
+        wlo_env* e = &s->env[li];
+        uint32_t gid = (uint32_t)(c->env_id_offset + li);
+        uint32_t r0[4], r1[4], r2[4];
+        philox4x32(c->seed, gid, 0u, RNG_STARTUP, 0u, r0);
+        philox4x32(c->seed, gid, 0u, RNG_STARTUP, 1u, r1);
+        philox4x32(c->seed, gid, 0u, RNG_STARTUP, 2u, r2);
+        for (int i = 0; i < 4; ++i) {
+            uint32_t bk = 0;
+            if (c->dr_enable && c->dr_num_buckets > 1) bk = (uint32_t)(((uint64_t)r0[i] * (uint64_t)c->dr_num_buckets) >> 32);
+            e->D[i] = (real)c->dr_bucket_D[bk];
+            e->C[i] = (real)c->dr_bucket_C[bk];
+            e->kd[i] = (real)c->dc_damping[i];
+            if (c->dr_enable && ((c->dr_kd_mask >> i) & 1)) e->kd[i] = uniform(r1[i], (real)c->dr_kd_range[0], (real)c->dr_kd_range[1]);
+        }
+        e->mass = (real)c->mass_nominal;
+        if (c->dr_enable) e->mass = e->mass + uniform(r2[0], (real)c->dr_mass_add[0], (real)c->dr_mass_add[1]);
+        e->inv_mass = K(1.0) / e->mass;
+        sample_interval_timers(c, e, r2[1], r2[2]);
+        e->q[0] = K(1.0); e->q[1] = e->q[2] = e->q[3] = K(0.0);
+    }
+    return 0;
+}
+
+int wlo_reset(wlo_sim* s, const int64_t* env_ids, int32_t n_ids, int64_t step_counter) {
+    const wl_config* c = &s->cfg;
+    if (c->task != WL_TASK_DRIFT) return WL_EUNSUPPORTED;
+    int n = env_ids ? n_ids : c->num_envs;
+    for (int k = 0; k < n; ++k) {
+        int li = env_ids ? (int)env_ids[k] : k;
+        drift_reset_env(c, &s->env[li], (uint32_t)(c->env_id_offset + li), step_counter);
+    }
+    return 0;
+}
+
+int wlo_step(wlo_sim* s, const float* action, float* obs, float* rew, uint8_t* terminated, uint8_t* truncated,
+             int64_t step_counter, int nthreads) {
+    const wl_config* c = &s->cfg;
+    int od = (c->task == WL_TASK_ELEVATION) ? WL_OBS_DIM_ELEV : WL_OBS_DIM_BLIND;
+    int slot = (int)(step_counter & 1);
+    step_log tot; memset(&tot, 0, sizeof tot);
+    int err = 0;
+    (void)nthreads;
+#ifdef _OPENMP
+#pragma omp parallel num_threads(nthreads > 0 ? nthreads : 1)
+#endif
+    {
+        step_log lg; memset(&lg, 0, sizeof lg);
+#ifdef _OPENMP
+#pragma omp for schedule(static)
+#endif
+        for (int li = 0; li < c->num_envs; ++li) {
+            int rc = env_step(s, li, action + 2 * (size_t)li, step_counter, obs + (size_t)od * li, rew + li, terminated + li,
+                              truncated + li, &lg);
+            if (rc) err = rc;
+        }
+#ifdef _OPENMP
+#pragma omp critical
+#endif
+        {
+            for (int k = 0; k < WL_MAX_REW_TERMS; ++k) tot.sum[k] += lg.sum[k];
+            tot.n_reset += lg.n_reset; tot.n_term += lg.n_term; tot.n_timeout += lg.n_timeout; tot.any |= lg.any;
+        }
+    }
+    for (int k = 0; k < WL_MAX_REW_TERMS; ++k) s->log_sum[slot][k] = tot.sum[k];
+    s->log_term[slot][0] = tot.n_reset; s->log_term[slot][1] = tot.n_term; s->log_term[slot][2] = tot.n_timeout;
+    s->any_reset[slot] = tot.any;
+    return err;
+}
+
+int wlo_observe(wlo_sim* s, float* obs, int64_t step_counter, int32_t call_idx) {
+    const wl_config* c = &s->cfg;
+    if (c->task != WL_TASK_DRIFT) return WL_EUNSUPPORTED;
+    for (int li = 0; li < c->num_envs; ++li)
+        blind_obs(c, &s->env[li], (uint32_t)(c->env_id_offset + li), (uint32_t)step_counter, RNG_OBS_EXTRA,
+                  3u * (uint32_t)call_idx, obs + (size_t)WL_OBS_DIM_BLIND * li);
+    return 0;
+}
+
+/* curriculum, wheeledlab/envs/mdp/curriculums.py:10-35 -- the counter conditions are
+ * evaluated by the caller (fire_mask); the "called only when >=1 env reset" condition
+ *  is applied here from the last step's any_reset flag. */
+int wlo_curriculum(wlo_sim* s, int64_t step_counter, int32_t n_terms, const int32_t* slots, const float* increases,
+                   uint32_t fire_mask) {
+    int slot = (int)((step_counter - 1) & 1);
+    if (!s->any_reset[slot]) return 0;
+    for (int t = 0; t < n_terms; ++t)
+        if ((fire_mask >> t) & 1u) s->rew_weight[slots[t]] += (real)increases[t];
+    return 0;
+}
+
+int wlo_synth_actions(const wl_config* c, float* action, int64_t step_counter, int32_t dist) {
+    for (int li = 0; li < c->num_envs; ++li) {
+        uint32_t r[4]; philox4x32(c->seed, (uint32_t)(c->env_id_offset + li), (uint32_t)step_counter, RNG_ACTION, 0u, r);
+        if (dist == 0) {
+            action[2 * li + 0] = (float)(K(2.0) * u01(r[0]) - K(1.0));
+            action[2 * li + 1] = (float)(K(2.0) * u01(r[1]) - K(1.0));
+        } else {
+            real z0, z1; box_muller(r[0], r[1], &z0, &z1);
+            action[2 * li + 0] = (float)r_clamp(z0, K(-1.0), K(1.0));
+            action[2 * li + 1] = (float)r_clamp(z1, K(-1.0), K(1.0));
+        }
+    }
+    return 0;
+}
+
+/* ---- packed state import / export in the product's AoSoA layout ------------- */
+static inline float* grp(float* buf, int g, int n, int i) { return buf + ((size_t)g * n + i) * 4; }
+void wlo_export_state(const wlo_sim* s, float* buf) {
+    int n = s->cfg.num_envs;
+    for (int i = 0; i < n; ++i) {
+        const wlo_env* e = &s->env[i];
+        float* g;
+        g = grp(buf, WL_G_POS, n, i); g[0] = (float)e->p[0]; g[1] = (float)e->p[1]; g[2] = (float)e->p[2]; memcpy(&g[3], &e->ep_len, 4);
+        g = grp(buf, WL_G_QUAT, n, i); for (int k = 0; k < 4; ++k) g[k] = (float)e->q[k];
+        g = grp(buf, WL_G_LINVEL, n, i); for (int k = 0; k < 3; ++k) g[k] = (float)e->v[k]; g[3] = (float)e->t_hf;
+        g = grp(buf, WL_G_ANGVEL, n, i); for (int k = 0; k < 3; ++k) g[k] = (float)e->w[k]; g[3] = (float)e->t_lf;
+        g = grp(buf, WL_G_WHEEL, n, i); for (int k = 0; k < 4; ++k) g[k] = (float)e->omega[k];
+        g = grp(buf, WL_G_STEER, n, i); g[0] = (float)e->steer[0]; g[1] = (float)e->steer[1]; g[2] = (float)e->steer_vel[0]; g[3] = (float)e->steer_vel[1];
+        g = grp(buf, WL_G_ACTION, n, i); g[0] = (float)e->action[0]; g[1] = (float)e->action[1]; g[2] = (float)e->prev_action[0]; g[3] = (float)e->prev_action[1];
+        g = grp(buf, WL_G_SUM0, n, i); for (int k = 0; k < 4; ++k) g[k] = (float)e->sums[k];
+        g = grp(buf, WL_G_SUM1, n, i); for (int k = 0; k < 4; ++k) g[k] = (float)e->sums[4 + k];
+        g = grp(buf, WL_G_PMASS, n, i); g[0] = (float)e->mass; g[1] = (float)e->inv_mass; g[2] = (float)e->spare0; g[3] = (float)e->spare1;
+        g = grp(buf, WL_G_PMU_D, n, i); for (int k = 0; k < 4; ++k) g[k] = (float)e->D[k];
+        g = grp(buf, WL_G_PMU_C, n, i); for (int k = 0; k < 4; ++k) g[k] = (float)e->C[k];
+        g = grp(buf, WL_G_PKD, n, i); for (int k = 0; k < 4; ++k) g[k] = (float)e->kd[k];
+        g = grp(buf, WL_G_CMD, n, i); for (int k = 0; k < 4; ++k) g[k] = (float)e->cmd[k];
+    }
+}
+void wlo_import_state(wlo_sim* s, const float* cbuf) {
+    int n = s->cfg.num_envs; float* buf = (float*)cbuf;
+    for (int i = 0; i < n; ++i) {
+        wlo_env* e = &s->env[i];
+        const float* g;
+        g = grp(buf, WL_G_POS, n, i); e->p[0] = g[0]; e->p[1] = g[1]; e->p[2] = g[2]; memcpy(&e->ep_len, &g[3], 4);
+        g = grp(buf, WL_G_QUAT, n, i); for (int k = 0; k < 4; ++k) e->q[k] = g[k];
+        g = grp(buf, WL_G_LINVEL, n, i); for (int k = 0; k < 3; ++k) e->v[k] = g[k]; e->t_hf = g[3];
+        g = grp(buf, WL_G_ANGVEL, n, i); for (int k = 0; k < 3; ++k) e->w[k] = g[k]; e->t_lf = g[3];
+        g = grp(buf, WL_G_WHEEL, n, i); for (int k = 0; k < 4; ++k) e->omega[k] = g[k];
+        g = grp(buf, WL_G_STEER, n, i); e->steer[0] = g[0]; e->steer[1] = g[1]; e->steer_vel[0] = g[2]; e->steer_vel[1] = g[3];
+        g = grp(buf, WL_G_ACTION, n, i); e->action[0] = g[0]; e->action[1] = g[1]; e->prev_action[0] = g[2]; e->prev_action[1] = g[3];
+        g = grp(buf, WL_G_SUM0, n, i); for (int k = 0; k < 4; ++k) e->sums[k] = g[k];
+        g = grp(buf, WL_G_SUM1, n, i); for (int k = 0; k < 4; ++k) e->sums[4 + k] = g[k];
+        g = grp(buf, WL_G_PMASS, n, i); e->mass = g[0]; e->inv_mass = g[1]; e->spare0 = g[2]; e->spare1 = g[3];
+        g = grp(buf, WL_G_PMU_D, n, i); for (int k = 0; k < 4; ++k) e->D[k] = g[k];
+        g = grp(buf, WL_G_PMU_C, n, i); for (int k = 0; k < 4; ++k) e->C[k] = g[k];
+        g = grp(buf, WL_G_PKD, n, i); for (int k = 0; k < 4; ++k) e->kd[k] = g[k];
+        g = grp(buf, WL_G_CMD, n, i); for (int k = 0; k < 4; ++k) e->cmd[k] = g[k];
+    }
+}
+void wlo_get_weights(const wlo_sim* s, float* w) { for (int k = 0; k < WL_MAX_REW_TERMS; ++k) w[k] = (float)s->rew_weight[k]; }
+void wlo_set_weights(wlo_sim* s, const float* w) { for (int k = 0; k < WL_MAX_REW_TERMS; ++k) s->rew_weight[k] = (real)w[k]; }
+/* log: [0..7] sum of episode sums over reset envs, [8] n_reset, [9] n_terminated, [10] n_timeout */
+void wlo_get_log(const wlo_sim* s, int64_t step_counter, double* out) {
+    int slot = (int)(step_counter & 1);
+    for (int k = 0; k < WL_MAX_REW_TERMS; ++k) out[k] = s->log_sum[slot][k];
+    out[8] = s->log_term[slot][0]; out[9] = s->log_term[slot][1]; out[10] = s->log_term[slot][2];
+}
+
+/* ---- unit-level hooks for golden-vector and det-math tests -------------------- */
+int wlo_detmath(int32_t op, const float* in, const float* in2, float* out, int32_t n) {
+    for (int i = 0; i < n; ++i) {
+        real x = (real)in[i], s, c;
+        switch (op) {
+            case 0: det_sincos(x, &s, &c); out[i] = (float)s; break;
+            case 1: det_sincos(x, &s, &c); out[i] = (float)c; break;
+            case 2: out[i] = (float)det_atan(x); break;
+            case 3: out[i] = (float)det_atan2((real)in2[i], x); break;
+            case 4: out[i] = (float)det_log(x); break;
+            case 5: out[i] = (float)det_tan(x); break;
+            case 6: out[i] = (float)det_asin(x); break;
+            default: return WL_EINVAL;
+        }
+    }
+    return 0;
+}
+int wlo_philox(uint64_t seed, uint32_t c0_base, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t* out, int32_t n) {
+    for (int i = 0; i < n; ++i) philox4x32(seed, c0_base + (uint32_t)i, c1, c2, c3, out + 4 * (size_t)i);
+    return 0;
+}
+/* action map only: out wheel targets [n,4] (bl,br,fl,fr) and steer targets [n,2] */
+int wlo_action_map(const wl_config* c, const float* action, float* wheel, float* steer, int32_t n) {
+    for (int i = 0; i < n; ++i) {
+        real wt[4], st[2];
+        int rc = process_action(c, action + 2 * i, wt, st);
+        if (rc) return rc;
+        for (int k = 0; k < 4; ++k) wheel[4 * i + k] = (float)wt[k];
+        steer[2 * i] = (float)st[0]; steer[2 * i + 1] = (float)st[1];
+    }
+    return 0;
+}
+/* drift MDP terms on given root states: in[n,13] = pos3 quat4 linvel_w3 angvel_w3, steer[n,2];
+ * out f[n,8] unweighted terms, term[n] out_of_bounds */
+int wlo_drift_terms(const wl_config* c, const float* root, const float* steer, const int32_t* ep_len, float* f_out,
+                    uint8_t* oob, int32_t n) {
+    for (int i = 0; i < n; ++i) {
+        wlo_env e; memset(&e, 0, sizeof e);
+        const float* r = root + 13 * i;
+        real p[3] = {r[0], r[1], r[2]}, q[4] = {r[3], r[4], r[5], r[6]}, v[3] = {r[7], r[8], r[9]}, w[3] = {r[10], r[11], r[12]};
+        e.steer[0] = steer[2 * i]; e.steer[1] = steer[2 * i + 1];
+        real R[9]; rotmat(q, R);
+        real vb[3], wb[3]; rotT(R, v, vb); rotT(R, w, wb);
+        int t = drift_off_track(c, p[0], p[1]);
+        int to = ep_len[i] >= c->max_episode_length;
+        real f[WL_MAX_REW_TERMS];
+        drift_reward_terms(c, &e, p, vb, wb, w[2], t, to, f);
+        for (int k = 0; k < WL_MAX_REW_TERMS; ++k) f_out[WL_MAX_REW_TERMS * i + k] = (float)f[k];
+        oob[i] = (uint8_t)t;
+    }
+    return 0;
+}
+int wlo_euler_xyz(const float* quat, float* out, int32_t n) {
+    for (int i = 0; i < n; ++i) {
+        real q[4] = {quat[4 * i], quat[4 * i + 1], quat[4 * i + 2], quat[4 * i + 3]}, e[3];
+        euler_xyz(q, e);
+        out[3 * i] = (float)e[0]; out[3 * i + 1] = (float)e[1]; out[3 * i + 2] = (float)e[2];
+    }
+    return 0;
+}
+
+/* same X-macro descriptor as the product library, so tests can cross-check the layouts */
+const char* wlo_config_describe(void) {
+    static char buf[16384];
+    if (buf[0] == 0) {
+        size_t off = 0;
+#define WL_XS(type, tag, name) off += (size_t)snprintf(buf + off, sizeof buf - off, "%s:%s:1:%zu;", #name, #tag, offsetof(wl_config, name));
+#define WL_XA(type, tag, name, n) off += (size_t)snprintf(buf + off, sizeof buf - off, "%s:%s:%d:%zu;", #name, #tag, (int)(n), offsetof(wl_config, name));
+        WL_CONFIG_FIELDS(WL_XS, WL_XA)
+#undef WL_XS
+#undef WL_XA
+        snprintf(buf + off, sizeof buf - off, "sizeof:%zu", sizeof(wl_config));
+    }
+    return buf;
+}

@@ -1,0 +1,238 @@
+"""GPU parity tests: the CUDA path (through the C-ABI) against the CPU oracle on the same seeded inputs.
+Bit-exact for every output (the arithmetic contract makes fp32 results identical), including done masks
+and reset indices, over trajectories long enough to contain many auto-resets."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+import oracle_lib as O  # noqa: E402
+
+
+def _need_gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+
+
+def _bits(a):
+    return np.ascontiguousarray(a).view(np.uint32)
+
+
+def _pair(n, seed=42, **kw):
+    import wheeledlab_b200 as wl
+    spec = wl.drift_task(num_envs=n, seed=seed, **kw)
+    sim = wl.WheeledSim(spec, "cuda:0")
+    sim.startup(); sim.reset(None, 0)
+    orc = O.Oracle(spec.cfg)
+    orc.startup(); orc.reset(None, 0)
+    return spec, sim, orc
+
+
+def _state_groups(sim):
+    return sim.groups.detach().cpu().numpy()
+
+
+def test_loaded_native_library_is_in_tree():
+    _need_gpu()
+    import wheeledlab_b200 as wl
+    maps = open("/proc/self/maps").read()
+    assert str(wl.LIB_PATH) in maps
+
+
+def test_detmath_bit_exact():
+    _need_gpu()
+    import wheeledlab_b200 as wl
+    rng = np.random.default_rng(0)
+    cases = {0: rng.uniform(-8, 8, 100000), 1: rng.uniform(-8, 8, 100000), 2: rng.normal(0, 10, 100000),
+             4: rng.uniform(1e-7, 1, 100000), 5: rng.uniform(-0.6, 0.6, 100000), 6: rng.uniform(-1, 1, 100000)}
+    for op, x in cases.items():
+        x = x.astype(np.float32)
+        d_in = torch.from_numpy(x).cuda(); d_out = torch.empty_like(d_in)
+        wl._lib.check(wl.lib.wl_test_detmath(op, d_in.data_ptr(), d_in.data_ptr(), d_out.data_ptr(), x.size, None))
+        torch.cuda.synchronize()
+        assert np.array_equal(_bits(d_out.cpu().numpy()), _bits(O.detmath(op, x))), f"op {op}"
+    x, y = rng.normal(size=100000).astype(np.float32), rng.normal(size=100000).astype(np.float32)
+    dx, dy = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda(); d_out = torch.empty_like(dx)
+    wl._lib.check(wl.lib.wl_test_detmath(3, dx.data_ptr(), dy.data_ptr(), d_out.data_ptr(), x.size, None))
+    torch.cuda.synchronize()
+    assert np.array_equal(_bits(d_out.cpu().numpy()), _bits(O.detmath(3, x, y)))
+
+
+def test_philox_bit_exact_and_kat():
+    _need_gpu()
+    import wheeledlab_b200 as wl
+    out = torch.empty((1000, 4), dtype=torch.int32, device="cuda")
+    wl._lib.check(wl.lib.wl_test_philox(1234567890123, 17, 3, 5, 7, out.data_ptr(), 1000, None))
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy().view(np.uint32), O.philox(1234567890123, 17, 3, 5, 7, 1000))
+    wl._lib.check(wl.lib.wl_test_philox(0, 0, 0, 0, 0, out.data_ptr(), 1, None))
+    torch.cuda.synchronize()
+    assert [hex(x) for x in out[0].cpu().numpy().view(np.uint32)] == ["0x6627e8d5", "0xe169c58d", "0xbc57ac4c", "0x9b00dbd8"]
+
+
+def test_startup_and_reset_state_bit_exact():
+    _need_gpu()
+    spec, sim, orc = _pair(1000, seed=9)
+    torch.cuda.synchronize()
+    assert np.array_equal(_bits(_state_groups(sim)), _bits(orc.export_state()))
+    ids = np.array([3, 999, 17, 500], np.int64)
+    sim.reset(torch.from_numpy(ids).cuda(), 77); orc.reset(ids, 77)
+    torch.cuda.synchronize()
+    assert np.array_equal(_bits(_state_groups(sim)), _bits(orc.export_state()))
+
+
+@pytest.mark.parametrize("n,steps,kw", [
+    (256, 1000, {}),                               # RSS_DRIFT settings, DR + pushes + noise on
+    (333, 300, {"randomize": False}),              # ragged N (not a multiple of the CTA), DR off
+    (64, 300, {"drive": "4wd"}),                   # BASELINE config 4: 4WD action map + 4 driven wheels
+    (1, 260, {}),                                  # single env (BASELINE config 1 plumbing size)
+])
+def test_step_trajectory_bit_exact(n, steps, kw):
+    """1000-step trajectories: obs, reward, done masks, episode log and the full state, every step."""
+    _need_gpu()
+    spec, sim, orc = _pair(n, seed=42, **kw)
+    n_done = 0
+    for t in range(steps):
+        act = sim.synth_actions(t, dist=t % 2)
+        a_np = act.cpu().numpy()
+        assert np.array_equal(_bits(a_np), _bits(orc.synth_actions(t, dist=t % 2)))
+        obs, rew, term, trunc = sim.step(act, t)
+        o_obs, o_rew, o_term, o_trunc = orc.step(a_np, t)
+        torch.cuda.synchronize()
+        assert np.array_equal(term.cpu().numpy(), o_term), f"terminated mask differs at step {t}"
+        assert np.array_equal(trunc.cpu().numpy(), o_trunc), f"time-out mask differs at step {t}"
+        assert np.array_equal(_bits(rew.cpu().numpy()), _bits(o_rew)), f"reward differs at step {t}"
+        assert np.array_equal(_bits(obs.cpu().numpy()), _bits(o_obs)), f"obs differs at step {t}"
+        n_done += int((o_term | o_trunc).sum())
+        sums, terms = sim.step_log(t)
+        lg = orc.log(t)
+        assert np.allclose(sums.cpu().numpy(), lg[:8], rtol=1e-5, atol=1e-4)
+        assert np.array_equal(terms.cpu().numpy()[:3], lg[8:11].astype(np.float32))
+        if t % 50 == 0 or t == steps - 1:
+            assert np.array_equal(_bits(_state_groups(sim)), _bits(orc.export_state())), f"state differs at step {t}"
+    assert n_done >= n, "trajectory too short to exercise auto-reset"
+
+
+def test_relative_l2_over_1000_steps_is_zero():
+    """north_star: state trajectories within 1e-3 relative L2 over 1000 steps (here: exactly 0)."""
+    _need_gpu()
+    spec, sim, orc = _pair(128, seed=1)
+    num = den = 0.0
+    for t in range(1000):
+        act = sim.synth_actions(t)
+        sim.step(act, t); orc.step(act.cpu().numpy(), t)
+        if t % 100 == 99:
+            a, b = _state_groups(sim)[:6].astype(np.float64), orc.export_state()[:6].astype(np.float64)
+            a[0, :, 3] = b[0, :, 3] = 0          # int bits (episode length) excluded from the float norm
+            num += ((a - b) ** 2).sum(); den += (b ** 2).sum()
+    assert (num / den) ** 0.5 <= 1e-3 and num == 0.0
+
+
+def test_observe_resamples_noise_bit_exact():
+    _need_gpu()
+    spec, sim, orc = _pair(200, seed=4)
+    a = sim.observe(0, 0).cpu().numpy(); b = sim.observe(0, 1).cpu().numpy()
+    assert np.array_equal(_bits(a), _bits(orc.observe(0, 0))) and np.array_equal(_bits(b), _bits(orc.observe(0, 1)))
+    assert not np.array_equal(a[:, :12], b[:, :12]) and np.array_equal(a[:, 12:], b[:, 12:])
+
+
+def test_sharding_invariance_two_shards_equal_one():
+    """BASELINE config 5 property: envs keyed by GLOBAL id => concat of shards == one big run, bit for bit."""
+    _need_gpu()
+    import wheeledlab_b200 as wl
+    n, steps = 512, 300
+    whole = wl.WheeledSim(wl.drift_task(num_envs=n, seed=21), "cuda:0")
+    lo = wl.WheeledSim(wl.drift_task(num_envs=n // 2, seed=21, env_id_offset=0), "cuda:0")
+    hi = wl.WheeledSim(wl.drift_task(num_envs=n // 2, seed=21, env_id_offset=n // 2), "cuda:0")
+    for s in (whole, lo, hi):
+        s.startup(); s.reset(None, 0)
+    for t in range(steps):
+        aw = whole.synth_actions(t)
+        ow = whole.step(aw, t)
+        ol = lo.step(lo.synth_actions(t), t); oh = hi.step(hi.synth_actions(t), t)
+        for w, l, h in zip(ow, ol, oh):
+            assert torch.equal(w, torch.cat([l, h], dim=0)), f"shard mismatch at step {t}"
+    assert torch.equal(whole.groups, torch.cat([lo.groups, hi.groups], dim=1))
+
+
+def test_curriculum_on_device_matches_oracle():
+    _need_gpu()
+    spec, sim, orc = _pair(64, seed=2)
+    w0 = sim.rew_weight.cpu().numpy().copy()
+    act = sim.synth_actions(0)
+    sim.step(act, 0); orc.step(act.cpu().numpy(), 0)
+    # no env reset at step 0 -> curriculum call is a no-op even with every fire bit set
+    sim.curriculum(1, [0, 3, 6], [20.0, 10.0, -1000.0], 0b111); orc.curriculum(1, [0, 3, 6], [20.0, 10.0, -1000.0], 0b111)
+    assert np.array_equal(sim.rew_weight.cpu().numpy(), w0)
+    for t in range(1, 250):
+        act = sim.synth_actions(t)
+        sim.step(act, t); orc.step(act.cpu().numpy(), t)
+    # step 249 times out every surviving env -> any_reset set -> weights move
+    sim.curriculum(250, [0, 3, 6], [20.0, 10.0, -1000.0], 0b101); orc.curriculum(250, [0, 3, 6], [20.0, 10.0, -1000.0], 0b101)
+    w = sim.rew_weight.cpu().numpy()
+    assert w[0] == w0[0] + 20 and w[3] == w0[3] and w[6] == w0[6] - 1000
+    assert np.array_equal(w, orc.weights())
+    act = sim.synth_actions(250)
+    _, rew, _, _ = sim.step(act, 250); _, o_rew, _, _ = orc.step(act.cpu().numpy(), 250)
+    assert np.array_equal(_bits(rew.cpu().numpy()), _bits(o_rew))
+
+
+def test_env_api_surface_and_full_size_properties():
+    """RSS_DRIFT_CONFIG size (4096 envs): ManagerBasedRLEnv surface + size-independent properties."""
+    _need_gpu()
+    import wheeledlab_b200 as wl
+    env = wl.make("Isaac-MushrDriftRL-v0", num_envs=4096, seed=42)
+    obs, extras = env.reset()
+    assert obs["policy"].shape == (4096, 14) and env.max_episode_length == 250 and env.num_envs == 4096
+    assert env.action_manager.total_action_dim == 2 and env.observation_manager.group_obs_dim["policy"] == (14,)
+    total_done = torch.zeros((), device="cuda")
+    prev_len = env.episode_length_buf.clone()
+    for t in range(300):
+        a = env.sim.synth_actions(t)
+        obs, rew, term, trunc, extras = env.step(a)
+        assert term.dtype == torch.bool and trunc.dtype == torch.bool and rew.shape == (4096,)
+        done = term | trunc
+        ep = env.episode_length_buf
+        # reset indices: episode length is 0 exactly where done, else previous + 1
+        assert torch.equal(ep == 0, done)
+        assert torch.equal(ep[~done], prev_len[~done] + 1)
+        # a reset env has zero velocity (before pushes) only approximately -> check pose is on the track & upright
+        q = env.scene["robot"].data.root_quat_w
+        assert torch.allclose((q * q).sum(-1), torch.ones(4096, device="cuda"), atol=1e-5)
+        assert torch.isfinite(obs["policy"]).all() and torch.isfinite(rew).all()
+        assert "Episode_Reward/side_slip" in extras["log"]
+        total_done += done.sum(); prev_len = ep.clone()
+    assert total_done.item() >= 4096
+    assert (env.episode_length_buf < 250).all()
+    tc = env.reward_manager.get_term_cfg("side_slip"); tc.weight += 5; env.reward_manager.set_term_cfg("side_slip", tc)
+    assert env.reward_manager.get_term_cfg("side_slip").weight == tc.weight
+    o1, _ = env.get_observations(); o2, _ = env.get_observations()
+    assert not torch.equal(o1, o2)            # noise is re-sampled
+    env.close()
+
+
+def test_cuda_graph_replay_matches_eager():
+    _need_gpu()
+    import wheeledlab_b200 as wl
+    n, k = 1024, 16
+    a = wl.WheeledSim(wl.drift_task(num_envs=n, seed=8), "cuda:0"); b = wl.WheeledSim(wl.drift_task(num_envs=n, seed=8), "cuda:0")
+    for s in (a, b):
+        s.startup(); s.reset(None, 0)
+    acts = torch.stack([a.synth_actions(t) for t in range(k)])
+    outs_a = [tuple(x.clone() for x in a.step(acts[t], t)) for t in range(k)]
+    bufs = [tuple(torch.empty_like(x) for x in outs_a[0]) for _ in range(k)]
+    stream = torch.cuda.Stream()
+    stream.wait_stream(torch.cuda.current_stream())
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(stream):
+        with torch.cuda.graph(g, stream=stream):
+            for t in range(k):
+                b.step(acts[t], t, out=bufs[t])
+    g.replay(); torch.cuda.synchronize()
+    for t in range(k):
+        for x, y in zip(outs_a[t], bufs[t]):
+            assert torch.equal(x, y)
+    assert torch.equal(a.groups, b.groups)

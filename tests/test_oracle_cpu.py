@@ -1,0 +1,212 @@
+"""CPU checks that pin the oracle: Philox known-answer vectors, deterministic-math accuracy,
+closed-form MDP cases (SURVEY 8c "self-consistency checks"), trajectory sanity, f32-vs-f64 tolerance."""
+import math
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+
+
+def _cfg(**kw):
+    import wheeledlab_b200 as wl
+    return wl.drift_task(**kw)
+
+
+# ---- RNG ----------------------------------------------------------------------------------------
+def test_philox_known_answer_vectors():
+    # Random123 kat_vectors, philox4x32-10
+    out = O.philox(0, 0, 0, 0, 0, 1)[0]
+    assert [hex(x) for x in out] == ["0x6627e8d5", "0xe169c58d", "0xbc57ac4c", "0x9b00dbd8"]
+    out = O.philox(0xFFFFFFFFFFFFFFFF, 0xFFFFFFFF, 0xFFFFFFFF, 0xFFFFFFFF, 0xFFFFFFFF, 1)[0]
+    assert [hex(x) for x in out] == ["0x408f276d", "0x41c83b0e", "0xa20bc7c6", "0x6d5451fd"]
+    out = O.philox(0x299F31D0A4093822, 0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344, 1)[0]
+    assert [hex(x) for x in out] == ["0xd16cfe09", "0x94fdcceb", "0x5001e420", "0x24126ea1"]
+
+
+def test_uniform_and_normal_statistics():
+    spec = _cfg(num_envs=20000, seed=3)
+    a = O.Oracle(spec.cfg).synth_actions(5, dist=0)
+    assert a.min() >= -1 and a.max() < 1 and abs(a.mean()) < 0.02 and abs(a.std() - 1 / math.sqrt(3)) < 0.01
+    z = O.Oracle(spec.cfg).synth_actions(5, dist=1)
+    assert abs((np.abs(z) >= 1).mean() - 0.3173) < 0.01      # clip(N(0,1)) mass at the bounds
+
+
+# ---- deterministic math -----------------------------------------------------------------------------
+@pytest.mark.parametrize("op,fn,lo,hi,tol", [
+    (0, np.sin, -8.0, 8.0, 2.5e-7), (1, np.cos, -8.0, 8.0, 2.5e-7), (2, np.arctan, -50.0, 50.0, 3e-7),
+    (4, np.log, 1e-7, 1.0, 5e-7), (5, np.tan, -0.6, 0.6, 3e-7), (6, np.arcsin, -0.999, 0.999, 4e-7),
+])
+def test_detmath_accuracy_vs_libm(op, fn, lo, hi, tol):
+    x = np.linspace(lo, hi, 200001).astype(np.float32)
+    got = O.detmath(op, x).astype(np.float64)
+    ref = fn(x.astype(np.float64))
+    err = np.abs(got - ref) / np.maximum(1.0, np.abs(ref))
+    assert err.max() < tol, err.max()
+
+
+def test_detmath_atan2_quadrants():
+    rng = np.random.default_rng(0)
+    x, y = rng.normal(size=100000).astype(np.float32), rng.normal(size=100000).astype(np.float32)
+    got = O.detmath(3, x, y).astype(np.float64)
+    assert np.abs(got - np.arctan2(y.astype(np.float64), x.astype(np.float64))).max() < 5e-7
+    assert O.detmath(3, np.zeros(1, np.float32), np.ones(1, np.float32))[0] == np.float32(math.pi / 2)
+
+
+# ---- closed-form MDP cases ---------------------------------------------------------------------------
+def test_max_episode_length_and_dims():
+    spec = _cfg(num_envs=4)
+    assert spec.cfg.max_episode_length == 250 and spec.obs_dim == 14
+
+
+def test_reference_pose_perimeter_and_on_track():
+    from wheeledlab_b200.tasks import generate_reference_poses
+    perimeter = 2 * math.pi * 0.8 + 4 * 0.8
+    assert abs(perimeter - 8.2265) < 1e-4
+    poses = generate_reference_poses(2000, 0.8, 0.8, seed=1)
+    x, y, yaw = poses[:, 0], poses[:, 1], poses[:, 2]
+    on_straight = np.abs(y) <= 0.8 + 1e-6
+    assert np.allclose(np.abs(x[on_straight]), 0.8, atol=1e-5)
+    d = np.sqrt(x[~on_straight] ** 2 + (np.abs(y[~on_straight]) - 0.8) ** 2)
+    assert np.allclose(d, 0.8, atol=1e-5)
+    assert yaw.min() >= 90.0 - 1e-3 and yaw.max() <= 450.0 + 1e-3
+    # heading is tangent to a counter-clockwise lap: cross(pos_from_center, heading) > 0 on the corners
+    hx, hy = np.cos(np.radians(yaw)), np.sin(np.radians(yaw))
+    cy = np.where(y > 0, 0.8, -0.8)
+    cross = x[~on_straight] * hy[~on_straight] - (y[~on_straight] - cy[~on_straight]) * hx[~on_straight]
+    assert (cross > 0).all()
+
+
+def test_stadium_termination_hand_picked_points():
+    spec = _cfg(num_envs=4)
+    pts = {  # (x, y) -> out_of_bounds     (mushr_drift_env_cfg.py:201-217,343-348)
+        (0.8, 0.0): 0, (0.0, 0.0): 1, (0.29, 0.5): 1, (0.31, 0.5): 0, (1.99, 0.0): 0, (2.01, 0.0): 1,
+        (0.0, 0.8 + 0.29): 1, (0.0, 0.8 + 0.31): 0, (0.0, 0.8 + 1.99): 0, (0.0, 0.8 + 2.01): 1,
+        (0.0, -0.8 - 1.99): 0, (0.0, -0.8 - 2.01): 1, (1.5, 2.0): 0, (1.7, 2.0): 1, (-0.8, -0.3): 0,
+    }
+    root = np.zeros((len(pts), 13), np.float32)
+    root[:, 3] = 1.0
+    for k, (x, y) in enumerate(pts):
+        root[k, 0], root[k, 1] = x, y
+    f, oob = O.drift_terms(spec.cfg, root, np.zeros((len(pts), 2), np.float32), np.zeros(len(pts), np.int32))
+    assert list(oob) == list(pts.values())
+    assert np.array_equal(f[:, 6], oob.astype(np.float32))       # term_pens = out_of_bounds & ~time_out
+    f2, _ = O.drift_terms(spec.cfg, root, np.zeros((len(pts), 2), np.float32), np.full(len(pts), 250, np.int32))
+    assert (f2[:, 6] == 0).all()
+
+
+def test_drift_reward_terms_closed_form():
+    spec = _cfg(num_envs=4)
+    root = np.zeros((3, 13), np.float32)
+    root[:, 3] = 1.0                                  # identity orientation: body == world
+    root[0, 0:2] = (0.8, 0.0); root[0, 7:10] = (2.0, 1.0, 0.0); root[0, 12] = 1.5
+    root[1, 0:2] = (0.0, 1.9); root[1, 7:10] = (0.5, 0.4, 0.3); root[1, 12] = 2.0
+    root[2, 0:2] = (-1.0, -0.2); root[2, 7:10] = (3.0, 0.1, 0.0)
+    steer = np.array([[0.2, 0.2], [-0.4, -0.2], [0.0, 0.0]], np.float32)
+    f, _ = O.drift_terms(spec.cfg, root, steer, np.zeros(3, np.int32))
+    # side_slip: atan2(1,2)=0.4636 in [0.25,0.55] and |vx|>=1 ; env1 |vx|<1 -> 0 ; env2 slip 0.033 < 0.25 -> 0
+    assert f[0, 0] == pytest.approx(math.atan2(1, 2), abs=1e-6) and f[1, 0] == 0 and f[2, 0] == 0
+    assert f[0, 1] == pytest.approx((math.hypot(2, 1) - 3) ** 2 - 9, abs=1e-5)
+    assert f[0, 2] == 1.5 and f[1, 2] == 2.0
+    assert f[0, 3] == 0.0 and f[1, 3] == pytest.approx(0.3 * 1.0, abs=1e-6)   # -mean(steer)*clamp(wz,+-1)
+    assert f[0, 4] == 0.0 and f[1, 4] == pytest.approx(0.5, abs=1e-6)          # |y|>0.8 -> |v|^2 (3-D)
+    assert f[0, 5] == pytest.approx(-1.0, abs=1e-6)                            # on the line
+    assert f[1, 5] == pytest.approx(abs(1.1 - 0.8) - 1.0, abs=1e-6)
+    assert f[2, 5] == pytest.approx(abs(-1.0 + 0.8) - 1.0, abs=1e-6)
+
+
+def test_action_map_rwd_and_4wd():
+    import wheeledlab_b200 as wl
+    rwd = wl.drift_task(num_envs=4).cfg
+    a = np.array([[1.0, 0.0], [0.5, 1.0], [-1.0, -1.0], [3.0, 0.3]], np.float32)
+    wheel, steer = O.action_map(rwd, a)
+    assert np.allclose(wheel[0], [60, 60, 0, 0]) and steer[0, 0] == 0
+    assert np.allclose(wheel[1, :2], 0.5 * 3 / 0.05) and steer[1, 0] == pytest.approx(math.tan(0.488), rel=1e-6)
+    assert (wheel[2] == 0).all()                                   # no_reverse
+    assert np.allclose(wheel[3, :2], 60) and steer[3, 0] == pytest.approx(math.tan(0.3 * 0.488), rel=1e-6)  # clip
+    fwd = wl.drift_task(num_envs=4, drive="4wd").cfg
+    wheel, steer = O.action_map(fwd, a)
+    assert np.allclose(wheel[0], 60.0, rtol=1e-6)                  # straight: all v/r (R = 1e6)
+    L, W, r, v, d = 0.325, 0.2, 0.05, 1.5, 0.488
+    R = L / math.tan(d)
+    exp = [v * abs((R - W / 2) / (R * r)), v * abs((R + W / 2) / (R * r)),
+           v * abs(math.hypot(R - W / 2, L) / (R * r)), v * abs(math.hypot(R + W / 2, L) / (R * r))]
+    assert np.allclose(wheel[1], exp, rtol=1e-5)
+    assert np.allclose(steer[1], math.tan(d), rtol=1e-6)
+
+
+# ---- trajectories ------------------------------------------------------------------------------------
+def _rollout(kind, n, steps, seed=11, randomize=True):
+    spec = _cfg(num_envs=n, seed=seed, randomize=randomize)
+    o = O.Oracle(spec.cfg, kind=kind)
+    o.startup(); o.reset(None, 0)
+    outs = []
+    for t in range(steps):
+        a = o.synth_actions(t)
+        outs.append(o.step(a, t))
+    return o, outs
+
+
+def test_rollout_sane_resets_and_bounds():
+    o, outs = _rollout("f32", 64, 600)
+    n_done = 0
+    for obs, rew, term, trunc in outs:
+        assert np.isfinite(obs).all() and np.isfinite(rew).all()
+        n_done += int((term | trunc).sum())
+    assert n_done > 64                       # every env resets at least via time-out
+    st = o.export_state()
+    ep_len = st[0, :, 3].view(np.int32)
+    assert (ep_len >= 0).all() and (ep_len < 250).all()
+    assert np.abs(st[0, :, 2]).max() < 0.05  # flat ground: root z stays near 0
+    q = st[1]
+    assert np.allclose((q * q).sum(-1), 1.0, atol=1e-5)
+
+
+def test_startup_randomisation_ranges():
+    spec = _cfg(num_envs=4096, seed=5)
+    o = O.Oracle(spec.cfg); o.startup()
+    st = o.export_state()
+    mass, kd, D, Cs = st[9, :, 0], st[12], st[10], st[11]
+    assert mass.min() >= 4.114 + 0.3 - 1e-5 and mass.max() <= 4.114 + 0.5 + 1e-5
+    assert np.allclose(st[9, :, 1], 1.0 / mass, rtol=1e-6)
+    assert kd[:, :2].min() >= 10 and kd[:, :2].max() <= 50 and (kd[:, 2:] == 0).all()
+    assert D.min() >= 0.3 * 1.1 - 1e-6 and D.max() <= 0.5 * 1.1 + 1e-6
+    assert Cs.min() >= 1.0 and Cs.max() < 2.0
+    assert len(np.unique(D)) <= 20
+    th, tl = st[2, :, 3], st[3, :, 3]
+    assert th.min() >= 0.1 and th.max() <= 0.4 and tl.min() >= 0.8 and tl.max() <= 1.2
+
+
+def test_f32_oracle_tracks_f64_truth_over_short_horizon():
+    """fp32 tolerance of the restatement itself: same model in float64/libm, 40 steps, no resets in window."""
+    n, steps = 32, 40
+    o32, out32 = _rollout("f32", n, steps, randomize=False)
+    o64, out64 = _rollout("f64", n, steps, randomize=False)
+    s32, s64 = o32.export_state(), o64.export_state()
+    same = np.ones(n, bool)
+    for (_, _, t32, u32), (_, _, t64, u64) in zip(out32, out64):
+        same &= (t32 == t64) & (u32 == u64) & (t32 == 0)
+    assert same.sum() >= n // 2
+    for g in (0, 1, 2, 3):
+        a, b = s32[g][same, :3], s64[g][same, :3]
+        rel = np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-6)
+        assert rel < 1e-3, (g, rel)
+
+
+def test_curriculum_counter_semantics():
+    """increase_reward_weight_over_time fires on episode boundaries of the GLOBAL counter (curriculums.py:23-35)."""
+    import wheeledlab_b200 as wl
+    env = wl.ManagerBasedRLEnv.__new__(wl.ManagerBasedRLEnv)
+    env.spec = _cfg(num_envs=4)
+    env.max_episode_length = 250
+    fired = {}
+    for c in range(1, 250 * 120 + 1):
+        env.common_step_counter = c
+        m = env._curriculum_fire_mask()
+        if m:
+            fired[c // 250] = m
+    # term 0/1: episodes_per_increase=20 -> episodes 19,39,...; term 2: 50 -> 49,99
+    assert fired[19] == 0b011 and fired[39] == 0b011 and fired[49] == 0b100 and fired[99] == 0b111
+    assert 20 not in fired and 1 not in fired
+    # max_increases: term1 (5) stops once E//20 > 5 i.e. E >= 120 -> E=119: 119//20=5 not > 5 -> still fires
+    assert fired[119] & 0b010

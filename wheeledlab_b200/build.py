@@ -1,0 +1,48 @@
+"""In-tree build of the CUDA library (and, for tests, the C oracle)."""
+from __future__ import annotations
+
+import os
+import subprocess
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+ROOT = PKG.parent
+CSRC = PKG / "csrc"
+LIB = PKG / "libwheeledlab_b200.so"
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
+    "-fmad=false",                    # bit-exact parity with the oracle (DESIGN.md "Determinism")
+    "-Xcompiler", "-fPIC", "-shared",
+]
+
+
+def _stale(target: Path, sources) -> bool:
+    if not target.exists():
+        return True
+    t = target.stat().st_mtime
+    return any(Path(s).stat().st_mtime > t for s in sources)
+
+
+def build_native(force: bool = False, verbose: bool = False) -> Path:
+    srcs = [CSRC / "wl_api.cu"]
+    deps = srcs + list(CSRC.glob("*.cuh")) + [ROOT / "include" / "wheeledlab_b200.h"]
+    if force or _stale(LIB, deps):
+        cmd = [NVCC, *NVCC_FLAGS, *(["-Xptxas", "-v"] if verbose else []), "-o", str(LIB), *map(str, srcs)]
+        subprocess.run(cmd, check=True, cwd=str(ROOT))
+    return LIB
+
+
+def build_oracle(force: bool = False, native: bool = False) -> Path:
+    odir = ROOT / "oracle"
+    targets = ["libwl_oracle.so", "libwl_oracle_f64.so"] + (["libwl_oracle_native.so"] if native else [])
+    if force:
+        subprocess.run(["make", "-C", str(odir), "clean"], check=True)
+    subprocess.run(["make", "-C", str(odir), *targets], check=True, stdout=subprocess.DEVNULL)
+    return odir / "libwl_oracle.so"
+
+
+if __name__ == "__main__":
+    print(build_native(force=True, verbose=True))
+    print(build_oracle())

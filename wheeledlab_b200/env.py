@@ -1,0 +1,308 @@
+"""ManagerBasedRLEnv-compatible environment backed by the fused CUDA step.
+
+Mirrors the surface of ``isaaclab.envs:ManagerBasedRLEnv`` that the reference's callers touch
+(SURVEY.md 8b): ``train_rl.py:70-116``, ``modified_rsl_rl_runner.py:46-109``,
+``create_and_step_env.py:26-44`` and the term code in ``wheeledlab/envs/mdp`` /
+``wheeledlab_tasks``.  Same names, same argument meaning, same error behaviour (exceptions; no
+silent CPU path).  Step ordering follows SURVEY.md 3.3 (A..I).
+"""
+from __future__ import annotations
+
+import math
+from types import SimpleNamespace
+
+import torch
+
+from .sim import WheeledSim
+from .tasks import TaskSpec, make_task
+
+
+class _Box:
+    """Minimal gymnasium.spaces.Box stand-in (callers assign .low/.high, train_rl.py:73-74)."""
+
+    def __init__(self, low, high, shape, dtype=torch.float32):
+        self.low, self.high, self.shape, self.dtype = low, high, tuple(shape), dtype
+
+    def sample(self, generator=None, device="cpu"):
+        return torch.randn(self.shape, generator=generator, device=device)
+
+
+class RewardTermCfgView:
+    """What reward_manager.get_term_cfg returns: an object with a mutable ``weight`` (curriculums.py:33-35)."""
+
+    def __init__(self, name: str, weight: float):
+        self.name, self.weight = name, weight
+        self.params = {}
+
+
+class RewardManager:
+    def __init__(self, env):
+        self._env = env
+        self.active_terms = list(env.spec.reward_names)
+
+    def _slot(self, name):
+        try:
+            return self.active_terms.index(name)
+        except ValueError:
+            raise ValueError(f"Reward term '{name}' not found.") from None
+
+    def get_term_cfg(self, name) -> RewardTermCfgView:
+        return RewardTermCfgView(name, float(self._env.sim.rew_weight[self._slot(name)].item()))
+
+    def set_term_cfg(self, name, cfg) -> None:
+        self._env.sim.rew_weight[self._slot(name)] = float(cfg.weight)
+
+    @property
+    def weights(self) -> torch.Tensor:
+        return self._env.sim.rew_weight[: len(self.active_terms)]
+
+
+class TerminationManager:
+    def __init__(self, env):
+        self._env = env
+        self.active_terms = [n for n, _ in env.spec.termination_names]
+        self.terminated = torch.zeros(env.num_envs, dtype=torch.bool, device=env.device)
+        self.time_outs = torch.zeros(env.num_envs, dtype=torch.bool, device=env.device)
+
+    @property
+    def dones(self):
+        return self.terminated | self.time_outs
+
+    def get_term(self, name):
+        for n, is_to in self._env.spec.termination_names:
+            if n == name:
+                return self.time_outs if is_to else self.terminated
+        raise ValueError(f"Termination term '{name}' not found.")
+
+
+class ActionManager:
+    def __init__(self, env):
+        self._env = env
+        self.total_action_dim = env.spec.action_dim
+
+    @property
+    def action(self):
+        return self._env.sim.last_action
+
+    @property
+    def prev_action(self):
+        return self._env.sim.prev_action
+
+
+class ObservationManager:
+    def __init__(self, env):
+        self._env = env
+        self.group_obs_dim = {"policy": (env.spec.obs_dim,)}
+        self._calls = 0
+
+    def compute(self):
+        """Re-samples the observation noise, like the reference."""
+        env = self._env
+        obs = env.sim.observe(env.common_step_counter, self._calls)
+        self._calls += 1
+        return {"policy": obs}
+
+
+class _RobotData:
+    def __init__(self, sim: WheeledSim):
+        self._sim = sim
+
+    root_pos_w = property(lambda s: s._sim.root_pos_w)
+    root_quat_w = property(lambda s: s._sim.root_quat_w)
+    root_lin_vel_w = property(lambda s: s._sim.root_lin_vel_w)
+    root_ang_vel_w = property(lambda s: s._sim.root_ang_vel_w)
+    root_link_ang_vel_w = property(lambda s: s._sim.root_ang_vel_w)
+
+    @staticmethod
+    def _rot_inv(q, v):
+        w, xyz = q[:, 0:1], q[:, 1:4]
+        t = 2.0 * torch.cross(xyz, v, dim=-1)
+        return v - w * t + torch.cross(xyz, t, dim=-1)
+
+    @property
+    def root_lin_vel_b(self):
+        return self._rot_inv(self.root_quat_w, self.root_lin_vel_w)
+
+    @property
+    def root_ang_vel_b(self):
+        return self._rot_inv(self.root_quat_w, self.root_ang_vel_w)
+
+    @property
+    def joint_vel(self):
+        n = self._sim.num_envs
+        out = torch.zeros((n, 10), device=self._sim.device)
+        out[:, 0:4] = self._sim.wheel_vel
+        out[:, 4:6] = self._sim.steer_vel
+        return out
+
+    @property
+    def joint_pos(self):
+        n = self._sim.num_envs
+        out = torch.zeros((n, 10), device=self._sim.device)
+        out[:, 4:6] = self._sim.steer_pos
+        return out
+
+
+class _Robot:
+    """Articulation stand-in for env.scene["robot"] (write_root_* used by events.py:132-133)."""
+
+    def __init__(self, env):
+        self._env = env
+        self.data = _RobotData(env.sim)
+        self.joint_names = list(env.spec.joint_names)
+
+    def find_joints(self, name_keys, joint_subset=None, preserve_order=False):
+        import re
+        keys = [name_keys] if isinstance(name_keys, str) else list(name_keys)
+        ids, names = [], []
+        for i, jn in enumerate(self.joint_names):
+            if any(re.fullmatch(k, jn) for k in keys):
+                ids.append(i)
+                names.append(jn)
+        if not ids:
+            raise ValueError(f"Not all regular expressions are matched! {keys} vs {self.joint_names}")
+        return ids, names
+
+    def write_root_pose_to_sim(self, root_pose, env_ids=None):
+        sim = self._env.sim
+        ids = slice(None) if env_ids is None else env_ids
+        sim.root_pos_w[ids] = root_pose[:, 0:3]
+        sim.root_quat_w[ids] = root_pose[:, 3:7]
+
+    def write_root_velocity_to_sim(self, root_velocity, env_ids=None):
+        sim = self._env.sim
+        ids = slice(None) if env_ids is None else env_ids
+        sim.root_lin_vel_w[ids] = root_velocity[:, 0:3]
+        sim.root_ang_vel_w[ids] = root_velocity[:, 3:6]
+
+
+class _Scene:
+    def __init__(self, env):
+        self._assets = {"robot": _Robot(env)}
+        self.env_origins = torch.zeros((env.num_envs, 3), device=env.device)   # env_spacing = 0 (:373)
+        self.num_envs = env.num_envs
+        self.sensors = {}
+
+    def __getitem__(self, key):
+        return self._assets[key]
+
+
+class ManagerBasedRLEnv:
+    """Drop-in for ``isaaclab.envs.ManagerBasedRLEnv`` on the Drift/Elevation/Visual gym ids."""
+
+    metadata = {"render_modes": [None, "human", "rgb_array"], "isaac_sim_version": "b200-native"}
+
+    def __init__(self, cfg: TaskSpec | str = "Isaac-MushrDriftRL-v0", render_mode=None, device="cuda:0", **task_kw):
+        self.spec: TaskSpec = make_task(cfg, **task_kw) if isinstance(cfg, str) else cfg
+        self.cfg = SimpleNamespace(is_finite_horizon=False, seed=int(self.spec.cfg.seed), spec=self.spec)
+        self.render_mode = render_mode
+        self.device = str(torch.device(device))
+        self.sim = WheeledSim(self.spec, device)
+        self.num_envs = self.sim.num_envs
+        self.step_dt = self.spec.step_dt
+        self.physics_dt = float(self.spec.cfg.sim_dt)
+        self.max_episode_length_s = self.spec.episode_length_s
+        self.max_episode_length = math.ceil(self.max_episode_length_s / self.step_dt)
+        self.common_step_counter = 0
+        self.extras = {}
+        self.scene = _Scene(self)
+        self.action_manager = ActionManager(self)
+        self.observation_manager = ObservationManager(self)
+        self.reward_manager = RewardManager(self)
+        self.termination_manager = TerminationManager(self)
+        self.single_action_space = _Box(-math.inf, math.inf, (self.spec.action_dim,))
+        self.action_space = _Box(-math.inf, math.inf, (self.num_envs, self.spec.action_dim))
+        self.single_observation_space = {"policy": _Box(-math.inf, math.inf, (self.spec.obs_dim,))}
+        self.observation_space = {"policy": _Box(-math.inf, math.inf, (self.num_envs, self.spec.obs_dim))}
+        self._curr_slots = [self.reward_manager._slot(t.reward_term_name) for t in self.spec.curriculum]
+        self._curr_inc = [float(t.increase) for t in self.spec.curriculum]
+        self.log_episode_info = True
+        # event_manager.apply(mode="startup")
+        self.sim.startup()
+        self._needs_reset = True
+
+    # -- gym surface ---------------------------------------------------------------------------
+    @property
+    def unwrapped(self):
+        return self
+
+    @property
+    def episode_length_buf(self):
+        return self.sim.episode_length_buf
+
+    @episode_length_buf.setter
+    def episode_length_buf(self, value):
+        # modified_rsl_rl_runner.py:46-49 assigns a randint tensor
+        self.sim.episode_length_buf.copy_(value.to(torch.int32))
+
+    def seed(self, seed: int = -1) -> int:
+        return int(self.spec.cfg.seed)
+
+    def close(self):
+        self.sim.close()
+
+    def render(self, recompute=False):
+        return None
+
+    def reset(self, seed=None, options=None):
+        self.sim.reset(None, self.common_step_counter)
+        self._needs_reset = False
+        obs = self.observation_manager.compute()
+        return obs, self.extras
+
+    def get_observations(self):
+        """RslRlVecEnvWrapper.get_observations."""
+        obs = self.observation_manager.compute()
+        return obs["policy"], {"observations": obs}
+
+    def _curriculum_fire_mask(self) -> int:
+        """Counter conditions of increase_reward_weight_over_time (curriculums.py:23-35)."""
+        c, L = self.common_step_counter, self.max_episode_length
+        if c % L != 0:
+            return 0
+        mask = 0
+        num_episodes = c // L
+        for k, t in enumerate(self.spec.curriculum):
+            num_increases = num_episodes // t.episodes_per_increase
+            if num_increases > t.max_increases:
+                continue
+            if (num_episodes + 1) % t.episodes_per_increase == 0:
+                mask |= 1 << k
+        return mask
+
+    def step(self, action: torch.Tensor):
+        if self._needs_reset:
+            self.reset()
+        if action.dtype != torch.float32 or not action.is_contiguous() or str(action.device) != self.device:
+            action = action.to(self.device, torch.float32).contiguous()
+        t = self.common_step_counter
+        obs, rew, term_u8, trunc_u8 = self.sim.step(action, t)
+        self.common_step_counter = t + 1
+        # curriculum (inside _reset_idx upstream: uses the incremented counter and fires only if >=1 env reset;
+        # the "any reset" test happens on the device, so there is no host sync)
+        mask = self._curriculum_fire_mask()
+        if mask:
+            self.sim.curriculum(self.common_step_counter, self._curr_slots, self._curr_inc, mask)
+        terminated, truncated = term_u8.view(torch.bool), trunc_u8.view(torch.bool)
+        tm = self.termination_manager
+        tm.terminated, tm.time_outs = terminated, truncated
+        if self.log_episode_info:
+            self.extras["log"] = self._episode_log(t)
+        return {"policy": obs}, rew, terminated, truncated, self.extras
+
+    def _episode_log(self, t: int):
+        """extras["log"] (RewardManager/TerminationManager.reset): device tensors, no sync."""
+        sums, terms = self.sim.step_log(t)
+        sums, terms = sums.clone(), terms.clone()
+        denom = torch.clamp(terms[0], min=1.0) * self.max_episode_length_s
+        log = {}
+        for k, name in enumerate(self.spec.reward_names):
+            log["Episode_Reward/" + name] = sums[k] / denom
+        for name, is_to in self.spec.termination_names:
+            log["Episode_Termination/" + name] = terms[2] if is_to else terms[1]
+        return log
+
+
+def make(task_id: str, cfg=None, render_mode=None, device="cuda:0", **kw) -> ManagerBasedRLEnv:
+    """gym.make(<id>, cfg=...) equivalent for the registered WheeledLab ids."""
+    return ManagerBasedRLEnv(cfg if cfg is not None else task_id, render_mode=render_mode, device=device, **kw)

@@ -1,0 +1,178 @@
+"""WheeledSim: thin, allocation-owning wrapper over the C-ABI (one handle = one GPU's env shard).
+
+torch is used for device memory and streams only; every computation is a launch of the
+hand-written sm_100a kernels in ``csrc/`` through ``libwheeledlab_b200.so``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import WlConfig, check, lib
+from .tasks import TaskSpec
+
+# state groups (include/wheeledlab_b200.h)
+G_POS, G_QUAT, G_LINVEL, G_ANGVEL, G_WHEEL, G_STEER, G_ACTION, G_SUM0, G_SUM1 = range(9)
+G_PMASS, G_PMU_D, G_PMU_C, G_PKD, G_CMD = 9, 10, 11, 12, 13
+NUM_GROUPS = 14
+
+
+def _stream_ptr(device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+class WheeledSim:
+    def __init__(self, spec: TaskSpec, device: str | torch.device = "cuda:0", heightfield: torch.Tensor | None = None):
+        self.spec = spec
+        self.cfg: WlConfig = spec.cfg
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.WlError("wheeledlab_b200 runs on CUDA devices only (no CPU fallback)")
+        if not torch.cuda.is_available():
+            raise _lib.WlError("no CUDA device visible: wheeledlab_b200 has no CPU fallback")
+        self.num_envs = int(self.cfg.num_envs)
+        nbytes = lib.wl_state_bytes(self.num_envs)
+        with torch.cuda.device(self.device):
+            self._buf = torch.zeros(nbytes // 4, dtype=torch.float32, device=self.device)
+            assert self._buf.data_ptr() % 256 == 0
+            self._hf = None
+            hf_ptr = None
+            if heightfield is not None:
+                self._hf = heightfield.to(self.device, torch.float32).contiguous()
+                hf_ptr = C.c_void_p(self._hf.data_ptr())
+            handle = C.c_void_p()
+            check(lib.wl_create(C.byref(self.cfg), C.c_void_p(self._buf.data_ptr()), nbytes, hf_ptr, C.byref(handle)),
+                  "wl_create")
+        self._h = handle
+        n = self.num_envs
+        self.groups = self._buf[: NUM_GROUPS * n * 4].view(NUM_GROUPS, n, 4)
+        goff = lib.wl_globals_offset(n) // 4
+        self._globals = self._buf[goff: goff + C.sizeof(_lib.WlGlobals) // 4]
+        self.rew_weight = self._globals[0:8]
+        self._log_sum = self._globals[8:24].view(2, 8)
+        self._log_term = self._globals[24:32].view(2, 4)
+        self.obs_dim = int(lib.wl_obs_dim(self._h))
+
+    # -- lifetime ------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            lib.wl_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- hot path --------------------------------------------------------------------
+    def startup(self):
+        with torch.cuda.device(self.device):
+            check(lib.wl_startup(self._h, _stream_ptr(self.device)), "wl_startup")
+
+    def reset(self, env_ids: torch.Tensor | None, step_counter: int):
+        with torch.cuda.device(self.device):
+            if env_ids is None:
+                check(lib.wl_reset(self._h, None, 0, step_counter, _stream_ptr(self.device)), "wl_reset")
+            else:
+                ids = env_ids.to(self.device, torch.int64).contiguous()
+                check(lib.wl_reset(self._h, C.c_void_p(ids.data_ptr()), ids.numel(), step_counter,
+                                   _stream_ptr(self.device)), "wl_reset")
+
+    def step(self, action: torch.Tensor, step_counter: int, out=None):
+        """action [N,2] f32 (device, contiguous) -> (obs [N,D] f32, rew [N] f32, terminated [N] u8, truncated [N] u8)."""
+        n = self.num_envs
+        if out is None:
+            obs = torch.empty((n, self.obs_dim), dtype=torch.float32, device=self.device)
+            rew = torch.empty((n,), dtype=torch.float32, device=self.device)
+            term = torch.empty((n,), dtype=torch.uint8, device=self.device)
+            trunc = torch.empty((n,), dtype=torch.uint8, device=self.device)
+        else:
+            obs, rew, term, trunc = out
+        check(lib.wl_step(self._h, C.c_void_p(action.data_ptr()), C.c_void_p(obs.data_ptr()), C.c_void_p(rew.data_ptr()),
+                          C.c_void_p(term.data_ptr()), C.c_void_p(trunc.data_ptr()), step_counter,
+                          _stream_ptr(self.device)), "wl_step")
+        return obs, rew, term, trunc
+
+    def observe(self, step_counter: int, call_idx: int = 0, out: torch.Tensor | None = None):
+        obs = out if out is not None else torch.empty((self.num_envs, self.obs_dim), dtype=torch.float32, device=self.device)
+        check(lib.wl_observe(self._h, C.c_void_p(obs.data_ptr()), step_counter, call_idx, _stream_ptr(self.device)),
+              "wl_observe")
+        return obs
+
+    def curriculum(self, step_counter: int, slots, increases, fire_mask: int):
+        n = len(slots)
+        if n == 0 or fire_mask == 0:
+            return
+        a = (C.c_int32 * n)(*slots)
+        b = (C.c_float * n)(*increases)
+        check(lib.wl_curriculum(self._h, step_counter, n, a, b, fire_mask, _stream_ptr(self.device)), "wl_curriculum")
+
+    def synth_actions(self, step_counter: int, dist: int = 0, out: torch.Tensor | None = None):
+        act = out if out is not None else torch.empty((self.num_envs, 2), dtype=torch.float32, device=self.device)
+        check(lib.wl_synth_actions(self._h, C.c_void_p(act.data_ptr()), step_counter, dist, _stream_ptr(self.device)),
+              "wl_synth_actions")
+        return act
+
+    @property
+    def launch_count(self) -> int:
+        return int(lib.wl_launch_count(self._h))
+
+    # -- log of the step with counter value `step_counter` (valid until the step after next) -------
+    def step_log(self, step_counter: int):
+        s = step_counter & 1
+        return self._log_sum[s], self._log_term[s]
+
+    # -- zero-copy state views (IsaacLab ArticulationData names) -------------------------------------
+    @property
+    def root_pos_w(self):
+        return self.groups[G_POS, :, 0:3]
+
+    @property
+    def root_quat_w(self):
+        return self.groups[G_QUAT]
+
+    @property
+    def root_lin_vel_w(self):
+        return self.groups[G_LINVEL, :, 0:3]
+
+    @property
+    def root_ang_vel_w(self):
+        return self.groups[G_ANGVEL, :, 0:3]
+
+    @property
+    def wheel_vel(self):
+        return self.groups[G_WHEEL]
+
+    @property
+    def steer_pos(self):
+        return self.groups[G_STEER, :, 0:2]
+
+    @property
+    def steer_vel(self):
+        return self.groups[G_STEER, :, 2:4]
+
+    @property
+    def episode_length_buf(self):
+        return self.groups[G_POS, :, 3].view(torch.int32)
+
+    @property
+    def last_action(self):
+        return self.groups[G_ACTION, :, 0:2]
+
+    @property
+    def prev_action(self):
+        return self.groups[G_ACTION, :, 2:4]
+
+    @property
+    def episode_sums(self):
+        return torch.cat([self.groups[G_SUM0], self.groups[G_SUM1]], dim=-1)
+
+    def state_snapshot(self) -> torch.Tensor:
+        """Copy of the whole state buffer (groups + globals) for checkpoint / parity tests."""
+        return self._buf.clone()
+
+    def load_state(self, buf: torch.Tensor):
+        self._buf.copy_(buf.to(self.device))

@@ -1,0 +1,239 @@
+"""Task descriptions lowered to the POD ``wl_config`` the kernels consume.
+
+Every number below restates a value from the reference configuration (file:line under
+``/root/reference/source``); nothing is imported from the reference at run time.
+
+  gym ids            wheeledlab_tasks/wheeledlab_tasks/__init__.py:14-63
+  Drift env          wheeledlab_tasks/wheeledlab_tasks/drifting/mushr_drift_env_cfg.py
+  actions            wheeledlab_tasks/wheeledlab_tasks/common/actions.py
+  observations       wheeledlab_tasks/wheeledlab_tasks/common/observations.py
+  actuators          wheeledlab_assets/wheeledlab_assets/hound.py
+  vehicle geometry   SURVEY.md Appendix A (decoded from Robots/UWRLL/mushr_nano_v2.usd)
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from ._lib import WlConfig
+
+WL_ABI_VERSION = 1
+TASK_DRIFT, TASK_ELEVATION, TASK_VISUAL = 0, 1, 2
+ACT_ACKERMANN, ACT_RWD, ACT_4WD = 0, 1, 2
+BOUND_NONE, BOUND_CLIP, BOUND_TANH = 0, 1, 2
+BL, BR, FL, FR = 0, 1, 2, 3
+
+# mushr_drift_env_cfg.py:27-32
+CORNER_IN_RADIUS, CORNER_OUT_RADIUS, LINE_RADIUS, STRAIGHT = 0.3, 2.0, 0.8, 0.8
+SLIP_THRESHOLD, MAX_SPEED = 0.55, 3.0
+
+GYM_IDS = {
+    "Isaac-MushrDriftRL-v0": "drift",
+    "Isaac-F1TenthDriftRL-v0": "f1tenth_drift",
+    "Isaac-MushrElevationRL-v0": "elevation",
+    "Isaac-MushrVisualRL-v0": "visual",
+}
+
+
+@dataclass
+class CurriculumTerm:
+    """increase_reward_weight_over_time params (wheeledlab/envs/mdp/curriculums.py:10-35)."""
+    name: str
+    reward_term_name: str
+    increase: float
+    episodes_per_increase: int = 1
+    max_increases: float = math.inf
+
+
+@dataclass
+class TaskSpec:
+    """Host-side description that accompanies a wl_config."""
+    name: str
+    cfg: WlConfig
+    reward_names: list = field(default_factory=list)
+    termination_names: list = field(default_factory=list)       # [(name, is_time_out)]
+    curriculum: list = field(default_factory=list)
+    obs_dim: int = 14
+    action_dim: int = 2
+    episode_length_s: float = 5.0
+    joint_names: list = field(default_factory=list)
+
+    @property
+    def step_dt(self) -> float:
+        return float(self.cfg.sim_dt) * int(self.cfg.decimation)
+
+
+MUSHR_JOINT_NAMES = [
+    # throttle joints first in the wheel order used by the kernels, then steer, then suspension
+    "back_left_wheel_throttle", "back_right_wheel_throttle", "front_left_wheel_throttle", "front_right_wheel_throttle",
+    "front_left_wheel_steer", "front_right_wheel_steer",
+    "back_left_wheel_suspension", "back_right_wheel_suspension", "front_left_wheel_suspension",
+    "front_right_wheel_suspension",
+]
+
+
+def generate_reference_poses(num_points: int, track_radius: float, track_straight: float, seed: int) -> np.ndarray:
+    """reset_root_state_along_track.generate_reference_poses (drifting/mdp/events.py:33-100).
+
+    Returns [num_points, 3] float32 rows (x, y, yaw_deg).  The reference draws ``torch.rand(num_points)``
+    from the global generator; here the draw is ``numpy.random.default_rng(seed)`` so that every rank of a
+    sharded run builds the same table.
+    """
+    r, s = np.float32(track_radius), np.float32(track_straight)
+    dist_track = np.float32(2.0 * math.pi) * r + np.float32(4.0) * s
+    dists = np.random.default_rng(seed).random(num_points, dtype=np.float32) * dist_track
+    out = np.zeros((num_points, 3), dtype=np.float32)
+    pi = np.float32(math.pi)
+    for k, d in enumerate(dists):
+        if d < 2 * s:                                   # case 1: +x straight, heading 90 deg
+            out[k] = (r, d - s, 90.0)
+        elif d < 2 * s + pi * r:                        # case 2: top half-circle
+            ang = (d - 2 * s) / r
+            out[k] = (r * np.cos(ang), s + r * np.sin(ang), 90.0 + ang * 180.0 / pi)
+        elif d < 4 * s + pi * r:                        # case 3: -x straight, heading 270 deg
+            rem = d - 2 * s - pi * r
+            out[k] = (-r, s - rem, 270.0)
+        else:                                           # case 4: bottom half-circle
+            ang2 = (d - 4 * s - pi * r) / r
+            out[k] = (-r * np.cos(ang2), -s - r * np.sin(ang2), 270.0 + ang2 * 180.0 / pi)
+    return out
+
+
+def material_buckets(num_buckets, static_range, dynamic_range, make_consistent, ground_mu_s, ground_mu_d, seed):
+    """randomize_rigid_body_material bucket table (mushr_drift_env_cfg.py:98-109) lowered to Pacejka (D, C).
+
+    Wheel material (mu_s, mu_d) combined with the ground by MULTIPLY (mushr_drift_env_cfg.py:45-49).  The tyre
+    curve mu(sigma) = D sin(C atan(B sigma)) peaks at D = combined static friction and tends to
+    D sin(C pi/2) = combined dynamic friction.
+    """
+    rng = np.random.default_rng(seed + 0x5EED)
+    mu_s = rng.uniform(static_range[0], static_range[1], num_buckets)
+    mu_d = rng.uniform(dynamic_range[0], dynamic_range[1], num_buckets)
+    if make_consistent:
+        mu_d = np.minimum(mu_d, mu_s)
+    D = mu_s * ground_mu_s
+    ratio = np.clip(mu_d * ground_mu_d / D, 0.0, 1.0)
+    Cshape = (2.0 / math.pi) * (math.pi - np.arcsin(ratio))
+    return D.astype(np.float32), Cshape.astype(np.float32)
+
+
+def _set(arr, values):
+    for k, v in enumerate(values):
+        arr[k] = v
+
+
+def _mushr_vehicle(cfg: WlConfig) -> None:
+    """MuSHR v2 lumped rigid body + wheel geometry and builder-chosen contact constants."""
+    cfg.mass_nominal = 4.114
+    # chassis inertia is "auto" in the USD (SURVEY hard part 3): box 0.44 x 0.24 x 0.12 m about the lumped COM
+    m, a, b, c = 4.114, 0.44, 0.24, 0.12
+    _set(cfg.inertia_nominal, (m / 12 * (b * b + c * c), m / 12 * (a * a + c * c), m / 12 * (a * a + b * b)))
+    _set(cfg.com, (-0.0049, 0.0, 0.1017))
+    cfg.hub_x_front, cfg.hub_x_rear, cfg.hub_y, cfg.hub_z = 0.1385, -0.158, 0.115, 0.0488
+    cfg.wheel_radius = 0.0525
+    cfg.wheel_inertia = 1.378e-4
+    cfg.wheel_damping = 0.0
+    # suspension+tyre vertical compliance: static deflection = wheel penetration at spawn (r - hub_z = 3.7 mm)
+    cfg.susp_k = m * 9.81 / (4 * 0.0037)
+    cfg.susp_c = 2 * 0.7 * math.sqrt(cfg.susp_k * m / 4)
+    cfg.susp_travel = 0.01                       # prismatic limits +-0.01 m
+    cfg.bump_k = 10 * cfg.susp_k
+    cfg.steer_inertia = 1.0e-4
+    cfg.tire_B = 10.0
+    cfg.tire_v0 = 0.5
+    cfg.tire_mx = 1.0 / (cfg.wheel_radius ** 2 / cfg.wheel_inertia + 4.0 / m)
+    cfg.tire_my = m / 4.0
+    cfg.gravity = 9.81
+
+
+def _hound_actuators(cfg: WlConfig, drive: str) -> None:
+    """HOUND_SUS_2WD_ACTUATOR_CFG / HOUND_SUS_ACTUATOR_CFG (wheeledlab_assets/hound.py:4-52)."""
+    cfg.dc_saturation, cfg.dc_vel_limit = 1.05, 450.0
+    if drive == "2wd":
+        _set(cfg.dc_effort, (0.5, 0.5, 0.0, 0.0))          # hound.py:40-43, front passive :44-51
+        _set(cfg.dc_damping, (1000.0, 1000.0, 0.0, 0.0))
+    else:
+        _set(cfg.dc_effort, (0.25, 0.25, 0.25, 0.25))      # hound.py:13-21
+        _set(cfg.dc_damping, (1000.0,) * 4)
+    cfg.steer_kp, cfg.steer_kd = 100.0, 10.0                # hound.py:5-12
+    cfg.steer_vel_limit = 10.0
+    cfg.steer_pos_limit = math.radians(75.0)                # joint limits [DECODED]
+
+
+def drift_task(num_envs: int = 1024, seed: int = 42, env_id_offset: int = 0, randomize: bool = True,
+               drive: str = "2wd") -> TaskSpec:
+    """MushrDriftRLEnvCfg (drifting/mushr_drift_env_cfg.py:368-404); drive='4wd' gives the BASELINE 'HOUND 4WD' variant."""
+    cfg = WlConfig()
+    cfg.abi_version = WL_ABI_VERSION
+    cfg.task = TASK_DRIFT
+    cfg.num_envs, cfg.env_id_offset, cfg.seed = num_envs, env_id_offset, seed
+    sim_dt, decimation = 0.005, 4                                      # :393-394
+    cfg.sim_dt, cfg.decimation, cfg.substeps = sim_dt, decimation, 1
+    episode_length_s = 5.0                                             # :396
+    # ManagerBasedRLEnv.max_episode_length: ceil in Python doubles (NOT on the fp32 copy of dt) -> 250
+    cfg.max_episode_length = math.ceil(episode_length_s / (sim_dt * decimation))
+    # actions: MushrRWDActionCfg (common/actions.py:5-24), scale re-set at :397
+    cfg.action_kind = ACT_RWD if drive == "2wd" else ACT_4WD
+    cfg.bounding, cfg.no_reverse = BOUND_CLIP, 1
+    _set(cfg.act_scale, (MAX_SPEED, 0.488))
+    _set(cfg.act_offset, (0.0, 0.0))
+    cfg.base_length, cfg.base_width, cfg.wheel_radius_cfg = 0.325, 0.2, 0.05
+    _mushr_vehicle(cfg)
+    _hound_actuators(cfg, drive)
+    cfg.ground_mu_s, cfg.ground_mu_d = 1.1, 1.0                       # :45-49
+    # startup DR (DriftEventsRandomCfg :95-154)
+    cfg.dr_enable = 1 if randomize else 0
+    if randomize:
+        cfg.dr_num_buckets = 20
+        D, Cs = material_buckets(20, (0.3, 0.5), (0.3, 0.5), True, cfg.ground_mu_s, cfg.ground_mu_d, seed)
+    else:
+        cfg.dr_num_buckets = 1
+        D, Cs = material_buckets(1, (1.0, 1.0), (1.0, 1.0), True, cfg.ground_mu_s, cfg.ground_mu_d, seed)  # USD wheel mu
+    _set(cfg.dr_bucket_D, D)
+    _set(cfg.dr_bucket_C, Cs)
+    _set(cfg.dr_kd_range, (10.0, 50.0))                                # :111-119
+    cfg.dr_kd_mask = 0b0011 if drive == "2wd" else 0b1111              # ".*back.*throttle"
+    _set(cfg.dr_mass_add, (0.3, 0.5))                                  # :145-154
+    # observations (BlindObsCfg, corruption on at :399)
+    cfg.enable_corruption = 1
+    _set(cfg.noise_std, (0.1, 0.1, 0.5, 0.4))
+    # interval pushes :121-143
+    cfg.push_enable = 1 if randomize else 0
+    _set(cfg.push_hf_interval, (0.1, 0.4))
+    _set(cfg.push_hf_range, (0.1, 0.03, 0.3))
+    _set(cfg.push_lf_interval, (0.8, 1.2))
+    cfg.push_lf_yaw = 0.6
+    # reset along track :82-93
+    cfg.num_ref_poses, cfg.reset_pos_noise, cfg.reset_yaw_noise = 20, 0.5, 1.0
+    _set(cfg.ref_poses, generate_reference_poses(20, LINE_RADIUS, STRAIGHT, seed).reshape(-1))
+    # terminations / rewards
+    cfg.trk_straight, cfg.trk_corner_in, cfg.trk_corner_out = STRAIGHT, CORNER_IN_RADIUS, CORNER_OUT_RADIUS
+    cfg.ctd_track_radius, cfg.ctd_offset = LINE_RADIUS, -1.0          # :284-293
+    cfg.slip_min_thresh, cfg.slip_max_thresh, cfg.slip_min_vel_x = 0.25, SLIP_THRESHOLD, 1.0   # :246-254
+    cfg.vel_speed_target, cfg.vel_offset = MAX_SPEED, -MAX_SPEED ** 2  # :167, :256-263
+    cfg.tlgr_ang_vel_thresh = 1.0                                      # :270-274
+    cfg.energy_straight = STRAIGHT                                     # :276-280
+    reward_names = ["side_slip", "vel", "progress", "tlgr", "turn_energy", "cross_track", "term_pens"]
+    cfg.num_rew_terms = len(reward_names)
+    _set(cfg.rew_weight, (10.0, -5.0, 40.0, 0.0, 20.0, -50.0, -5000.0))  # :243-299
+    curriculum = [                                                     # :306-337
+        CurriculumTerm("more_slip", "side_slip", 20.0, 20, 10),
+        CurriculumTerm("more_tlgr", "tlgr", 10.0, 20, 5),
+        CurriculumTerm("more_term_pens", "term_pens", -1000.0, 50, 5),
+    ]
+    return TaskSpec(
+        name="drift" if drive == "2wd" else "drift_4wd", cfg=cfg, reward_names=reward_names,
+        termination_names=[("time_out", True), ("out_of_bounds", False)], curriculum=curriculum, obs_dim=14,
+        action_dim=2, episode_length_s=episode_length_s, joint_names=list(MUSHR_JOINT_NAMES),
+    )
+
+
+def make_task(name_or_id: str, **kw) -> TaskSpec:
+    name = GYM_IDS.get(name_or_id, name_or_id)
+    if name == "drift":
+        return drift_task(**kw)
+    if name in ("drift_4wd", "hound_4wd"):
+        return drift_task(drive="4wd", **kw)
+    raise NotImplementedError(f"task {name_or_id!r} is not implemented in this build")
