@@ -1,0 +1,302 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/s of the fused WheeledLab step (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--envs E] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one env.step() of the RSS_DRIFT_CONFIG workload (MushrDriftRL: dt 5 ms x 4, DR + pushes +
+obs noise on, auto-reset) over E envs per GPU (default 4096 = BASELINE configs[1]) with synthetic
+U[-1,1]^2 actions from the counter-based generator.  Rank 0 prints ONE JSON line.
+
+  value     whole-job env-steps/s, inputs resident in HBM, L2 flushed between timed steps, per-step CUDA
+            events on the launch stream, max over ranks.
+  e2e       same metric through the public ManagerBasedRLEnv.step() with HOST (pinned) action buffers:
+            H2D of the actions and D2H of reward + done masks inside the timed region, every step.
+  roofline  algorithmic bytes of the step kernel / its measured duration vs the measured HBM peak.
+  cpu_baseline  the CPU oracle (oracle/wl_oracle.c, "port") timed on this box's host cores.
+--impl reference times that same CPU implementation (all host threads) as the reference arm: the
+reference's own PhysX pipeline is a closed binary that is not in /root/reference.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "env_steps_per_sec"
+UNIT = "env-steps/s"
+# algorithmic bytes per env-step of the Drift step kernel (DESIGN.md "Kernels"):
+# reads 13 state/param groups x16 B + action 8 B; writes 9 state groups x16 B + obs 56 + rew 4 + 2 masks
+BYTES_PER_ENV_STEP = (13 * 16 + 8) + (9 * 16 + 56 + 4 + 2)
+
+
+def _peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def _oracle(spec, native=True, threads=1):
+    sys.path.insert(0, str(ROOT / "tests"))
+    from oracle_lib import Oracle
+    return Oracle(spec.cfg, kind="native" if native else "f32", threads=threads)
+
+
+def cpu_baseline(envs: int, seed: int, budget_s: float = 12.0, threads: int | None = None):
+    """Time the CPU oracle on a bounded sample: `envs` envs, as many steps as fit in ~budget_s."""
+    import wheeledlab_b200 as wl
+    threads = threads or (os.cpu_count() or 1)
+    spec = wl.drift_task(num_envs=envs, seed=seed)
+    orc = _oracle(spec, native=True, threads=threads)
+    orc.startup(); orc.reset(None, 0)
+    acts = [orc.synth_actions(t) for t in range(8)]
+    for t in range(3):
+        orc.step(acts[t % 8], t)
+    t0 = time.perf_counter(); steps = 0
+    while True:
+        orc.step(acts[steps % 8], 3 + steps); steps += 1
+        el = time.perf_counter() - t0
+        if el > budget_s or steps >= 2000:
+            break
+    return {"value": envs * steps / el, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{envs} envs x {steps} env-steps of RSS_DRIFT (oracle/wl_oracle.c -O3 -march=native, OpenMP {threads} threads), {el:.1f} s"}
+
+
+def run_reference(args):
+    """Reference arm: the CPU implementation of the path on this box's host cores (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import wheeledlab_b200 as wl
+    threads = os.cpu_count() or 1
+    envs = args.envs
+    spec = wl.drift_task(num_envs=envs, seed=args.seed)
+    orc = _oracle(spec, native=True, threads=threads)
+    orc.startup(); orc.reset(None, 0)
+    acts = [orc.synth_actions(t) for t in range(8)]
+    for t in range(args.warmup):
+        orc.step(acts[t % 8], t)
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        orc.step(acts[k % 8], args.warmup + k)
+    el = time.perf_counter() - t0
+    val = envs * args.steps / el
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"RSS_DRIFT_CONFIG {envs} envs (CPU, one box)", "envs_per_step": envs,
+                   "note": "PhysX is not runnable here; this is the CPU restatement of the same step"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{envs} envs x {args.steps} env-steps, OpenMP {threads} threads"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import wheeledlab_b200 as wl
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+
+    E, K, W = args.envs, args.steps, args.warmup
+    spec = wl.drift_task(num_envs=E, seed=args.seed, env_id_offset=rank * E)
+    sim = wl.WheeledSim(spec, dev)
+    sim.startup(); sim.reset(None, 0)
+    acts = torch.stack([sim.synth_actions(t) for t in range(W + K)])           # resident in HBM
+    outs = tuple(torch.empty_like(x) for x in sim.step(acts[0], 0))
+    sim.load_state(sim.state_snapshot())                                          # (no-op; keeps API exercised)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # 256 MiB > 126 MB L2
+    peak, peak_src = _peaks()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing: per-step events around the step launch, L2 flushed between steps ----
+    t = 1
+    for _ in range(W):
+        sim.step(acts[t % (W + K)], t, out=outs); flush.fill_(0.0); t += 1
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    l0 = sim.launch_count
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    barrier()
+    for k in range(K):
+        ev[k][0].record()
+        sim.step(acts[(W + k) % (W + K)], t, out=outs); t += 1
+        ev[k][1].record()
+        flush.fill_(0.0)
+    barrier()
+    launches = sim.launch_count - l0
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    tot_ms = sum(step_ms)
+    # ---- warm-L2, CUDA-graph replay of K steps (supplementary: how the loop is meant to be driven) ----
+    g = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        with torch.cuda.graph(g, stream=s):
+            for k in range(K):
+                sim.step(acts[(W + k) % (W + K)], t + k, out=outs)
+    torch.cuda.current_stream().wait_stream(s)
+    g.replay(); barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); g.replay(); e1.record(); barrier()
+    graph_ms = e0.elapsed_time(e1)
+    # ---- end-to-end through the public API with host buffers ----
+    env = wl.ManagerBasedRLEnv(wl.drift_task(num_envs=E, seed=args.seed, env_id_offset=rank * E), device=dev)
+    env.reset()
+    h_act = acts.cpu().pin_memory()
+    d_act = torch.empty((E, 2), dtype=torch.float32, device=dev)
+    h_rew = torch.empty(E, dtype=torch.float32).pin_memory()
+    h_term = torch.empty(E, dtype=torch.bool).pin_memory()
+    h_trunc = torch.empty(E, dtype=torch.bool).pin_memory()
+
+    def e2e_step(k):
+        d_act.copy_(h_act[k % (W + K)], non_blocking=True)
+        obs, rew, term, trunc, extras = env.step(d_act)
+        h_rew.copy_(rew, non_blocking=True); h_term.copy_(term, non_blocking=True); h_trunc.copy_(trunc, non_blocking=True)
+        torch.cuda.current_stream().synchronize()          # the caller consumes reward / dones on the host
+
+    for k in range(W):
+        e2e_step(k)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(K):
+        e2e_step(W + k)
+    e1.record(); barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        tt = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    tot_ms, graph_ms, e2e_ms = max_over_ranks(tot_ms), max_over_ranks(graph_ms), max_over_ranks(e2e_ms)
+    if rank == 0:
+        total_envs = E * world
+        value = total_envs * K / (tot_ms * 1e-3)
+        kern_s = statistics.mean(step_ms) * 1e-3
+        achieved = BYTES_PER_ENV_STEP * E / kern_s / 1e9
+        cpu = cpu_baseline(E, args.seed, budget_s=args.cpu_budget) if world == 1 or True else None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": tot_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"RSS_DRIFT_CONFIG MushrDriftRL {E} envs/GPU x {world} GPU, dt 5ms x4, DR+push+noise on",
+                       "envs_per_gpu": E, "global_envs": total_envs, "actions": "U[-1,1]^2 philox(seed,env,step)",
+                       "l2": "flushed between timed steps (256 MiB fill)", "parallelism": f"env-shard x{world}"},
+            "clocks": clocks,
+            "e2e": {"value": total_envs * K / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": E * 8,
+                    "d2h_bytes_per_step": E * 6, "ms_per_step": e2e_ms / K},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "kernel": "wl_step_kernel<DRIFT>",
+                         "bytes_per_env_step": BYTES_PER_ENV_STEP, "avg_kernel_us": kern_s * 1e6,
+                         "note": "N=4096 moves 1.7 MB/launch: launch-latency bound, see profiles/ for the N sweep"},
+            "cpu_baseline": cpu,
+            "warm_l2_graph": {"value": total_envs * K / (graph_ms * 1e-3), "unit": UNIT, "ms_per_step": graph_ms / K,
+                              "note": "K steps captured in one CUDA graph, state L2-resident (supplementary)"},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=100)
+    ap.add_argument("--envs", type=int, default=4096, help="envs per GPU")
+    ap.add_argument("--seed", type=int, default=42)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-budget", type=float, default=12.0)
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

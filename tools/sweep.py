@@ -1,0 +1,57 @@
+#!/usr/bin/env python
+"""N-sweep of the fused step kernel: per-launch duration (CUDA events) and achieved algorithmic HBM GB/s.
+
+    python tools/sweep.py [--sizes 4096,65536,...] [--steps 30] [--task drift]
+Prints one JSON object; run under gpurun and copy the result into profiles/.
+"""
+import argparse, json, statistics, sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+import torch  # noqa: E402
+import wheeledlab_b200 as wl  # noqa: E402
+from bench import BYTES_PER_ENV_STEP, _peaks  # noqa: E402
+
+
+def one(n, steps, warm, flush):
+    sim = wl.WheeledSim(wl.drift_task(num_envs=n, seed=42), "cuda:0")
+    sim.startup(); sim.reset(None, 0)
+    acts = [sim.synth_actions(t) for t in range(4)]
+    outs = tuple(torch.empty_like(x) for x in sim.step(acts[0], 0))
+    for t in range(1, warm + 1):
+        sim.step(acts[t % 4], t, out=outs)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    torch.cuda.synchronize()
+    for k in range(steps):
+        if flush is not None:
+            flush.fill_(0.0)
+        ev[k][0].record(); sim.step(acts[k % 4], warm + 1 + k, out=outs); ev[k][1].record()
+    torch.cuda.synchronize()
+    ms = [a.elapsed_time(b) for a, b in ev]
+    med = statistics.median(ms)
+    return {"envs": n, "kernel_us_median": med * 1e3, "kernel_us_min": min(ms) * 1e3,
+            "env_steps_per_s": n / (med * 1e-3), "achieved_GBps": BYTES_PER_ENV_STEP * n / (med * 1e-3) / 1e9}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--sizes", default="1024,4096,16384,65536,262144,1048576,4194304")
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warm", type=int, default=5)
+    ap.add_argument("--no-flush", action="store_true")
+    a = ap.parse_args()
+    peak, src = _peaks()
+    flush = None if a.no_flush else torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda:0")
+    rows = []
+    for n in [int(x) for x in a.sizes.split(",")]:
+        r = one(n, a.steps, a.warm, flush)
+        r["frac_of_peak"] = r["achieved_GBps"] / peak
+        rows.append(r)
+        print(json.dumps(r), file=sys.stderr, flush=True)
+    print(json.dumps({"kernel": "wl_step_kernel<DRIFT>", "bytes_per_env_step": BYTES_PER_ENV_STEP, "peak_GBps": peak,
+                      "peak_source": src, "l2_flush_between_launches": not a.no_flush, "rows": rows}))
+
+
+if __name__ == "__main__":
+    main()
