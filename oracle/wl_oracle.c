@@ -488,19 +488,23 @@ static void sample_interval_timers(const wl_config* c, wlo_env* e, uint32_t a, u
     e->t_hf = uniform(a, (real)c->push_hf_interval[0], (real)c->push_hf_interval[1]);
     e->t_lf = uniform(b, (real)c->push_lf_interval[0], (real)c->push_lf_interval[1]);
 }
-static void drift_reset_env(const wl_config* c, wlo_env* e, uint32_t gid, int64_t t) {
-    uint32_t r[4], r2[4];
-    philox4x32(c->seed, gid, (uint32_t)t, RNG_RESET, 0u, r);
-    uint32_t idx = (uint32_t)(((uint64_t)r[0] * (uint64_t)c->num_ref_poses) >> 32);
-    real nx = (K(2.0) * u01(r[1]) - K(1.0)) * (real)c->reset_pos_noise;
-    real ny = (K(2.0) * u01(r[2]) - K(1.0)) * (real)c->reset_pos_noise;
-    real nyaw = (K(2.0) * u01(r[3]) - K(1.0)) * (real)c->reset_yaw_noise;
+/* pose part of __call__ (events.py:119-131) from the raw draws: idx, u_x, u_y, u_yaw in [0,1) */
+static void drift_reset_pose(const wl_config* c, wlo_env* e, uint32_t idx, real ux, real uy, real uyaw) {
+    real nx = (K(2.0) * ux - K(1.0)) * (real)c->reset_pos_noise;
+    real ny = (K(2.0) * uy - K(1.0)) * (real)c->reset_pos_noise;
+    real nyaw = (K(2.0) * uyaw - K(1.0)) * (real)c->reset_yaw_noise;
     e->p[0] = (real)c->ref_poses[3 * idx + 0] + nx;
     e->p[1] = (real)c->ref_poses[3 * idx + 1] + ny;
     e->p[2] = K(0.0);
     real yaw = (real)c->ref_poses[3 * idx + 2] * K(0.017453292519943295) + nyaw;   /* deg2rad, :126 */
     real sh, ch; det_sincos(yaw * K(0.5), &sh, &ch);
     e->q[0] = ch; e->q[1] = K(0.0); e->q[2] = K(0.0); e->q[3] = sh;                 /* roll = pitch = 0 */
+}
+static void drift_reset_env(const wl_config* c, wlo_env* e, uint32_t gid, int64_t t) {
+    uint32_t r[4], r2[4];
+    philox4x32(c->seed, gid, (uint32_t)t, RNG_RESET, 0u, r);
+    uint32_t idx = (uint32_t)(((uint64_t)r[0] * (uint64_t)c->num_ref_poses) >> 32);
+    drift_reset_pose(c, e, idx, u01(r[1]), u01(r[2]), u01(r[3]));
     for (int k = 0; k < 3; ++k) { e->v[k] = K(0.0); e->w[k] = K(0.0); }
     /* joint state untouched (quirk Q3).  manager resets [UPSTREAM-RECALL Appendix B]: */
     e->ep_len = 0;
@@ -859,6 +863,16 @@ int wlo_drift_terms(const wl_config* c, const float* root, const float* steer, c
         drift_reward_terms(c, &e, p, vb, wb, w[2], t, to, f);
         for (int k = 0; k < WL_MAX_REW_TERMS; ++k) f_out[WL_MAX_REW_TERMS * i + k] = (float)f[k];
         oob[i] = (uint8_t)t;
+    }
+    return 0;
+}
+/* reset pose from explicit draws: pose[n,7] = pos3 quat4 */
+int wlo_drift_reset_pose(const wl_config* c, const int32_t* idx, const float* u_xy, const float* u_yaw, float* pose, int32_t n) {
+    for (int i = 0; i < n; ++i) {
+        wlo_env e; memset(&e, 0, sizeof e);
+        drift_reset_pose(c, &e, (uint32_t)idx[i], (real)u_xy[2 * i], (real)u_xy[2 * i + 1], (real)u_yaw[i]);
+        for (int k = 0; k < 3; ++k) pose[7 * i + k] = (float)e.p[k];
+        for (int k = 0; k < 4; ++k) pose[7 * i + 3 + k] = (float)e.q[k];
     }
     return 0;
 }

@@ -1,0 +1,204 @@
+#!/usr/bin/env python
+"""Generate golden input/output vectors by EXECUTING THE REFERENCE'S OWN PYTHON (read-only tree at
+/root/reference) on CPU torch tensors, against the IsaacLab stand-in in shims/ (config carriers + trivial
+state accessors only).  Run in the authoring container:
+
+    python tests/golden/make_golden.py          # writes tests/golden/*.npz
+
+The vectors pin the oracle's restatement of: the action terms (ackermann_actions.py, rc_car_actions.py), the
+drift reward/termination terms (mushr_drift_env_cfg.py:160-240,343-348), reset_root_state_along_track
+(drifting/mdp/events.py), increase_reward_weight_over_time (curriculums.py), root_euler_xyz.  They cannot
+travel as code (/root/reference does not exist on the GPU box), hence the committed .npz fixtures.
+"""
+import sys
+import types
+from pathlib import Path
+
+import numpy as np
+import torch
+
+HERE = Path(__file__).resolve().parent
+ROOT = HERE.parent.parent
+REF = Path("/root/reference/source")
+sys.path[:0] = [str(ROOT / "shims"), str(REF / "wheeledlab"), str(REF / "wheeledlab_assets")]
+pkg = types.ModuleType("wheeledlab_tasks")          # skip wheeledlab_tasks/__init__.py (gymnasium/pxr import chain)
+pkg.__path__ = [str(REF / "wheeledlab_tasks" / "wheeledlab_tasks")]
+sys.modules["wheeledlab_tasks"] = pkg
+
+import wheeledlab.envs.mdp as wmdp  # noqa: E402
+from wheeledlab_tasks.common.actions import Mushr4WDActionCfg, MushrRWDActionCfg, F1Tenth4WDActionCfg  # noqa: E402
+from wheeledlab_tasks.drifting import mushr_drift_env_cfg as D  # noqa: E402
+from wheeledlab_tasks.drifting.mdp.events import reset_root_state_along_track  # noqa: E402
+import isaaclab.utils.math as math_utils  # noqa: E402
+
+
+# ---- minimal fake env ---------------------------------------------------------------------------------
+class FakeData:
+    pass
+
+
+class FakeAsset:
+    joint_names = ["back_left_wheel_throttle", "back_right_wheel_throttle", "front_left_wheel_throttle",
+                   "front_right_wheel_throttle", "front_left_wheel_steer", "front_right_wheel_steer",
+                   "wheel_back_left", "wheel_back_right", "wheel_front_left", "wheel_front_right", "rotator_left", "rotator_right"]
+
+    def __init__(self):
+        self.data = FakeData()
+        self.captured = {}
+
+    def find_joints(self, keys, *a, **k):
+        import re
+        keys = [keys] if isinstance(keys, str) else list(keys)
+        ids = [i for i, n in enumerate(self.joint_names) if any(re.fullmatch(kk, n) for kk in keys)]
+        return ids, [self.joint_names[i] for i in ids]
+
+    def set_joint_velocity_target(self, target, joint_ids=None):
+        self.captured["vel"] = target.clone()
+
+    def set_joint_position_target(self, target, joint_ids=None):
+        self.captured["pos"] = target.clone()
+
+    def write_root_pose_to_sim(self, pose, env_ids=None):
+        self.captured["pose"] = pose.clone()
+
+    def write_root_velocity_to_sim(self, vel, env_ids=None):
+        self.captured["velocity"] = vel.clone()
+
+
+class FakeScene(dict):
+    env_origins = None
+
+
+class FakeRewardManager:
+    def __init__(self, weights):
+        self.w = dict(weights)
+
+    def get_term_cfg(self, name):
+        return types.SimpleNamespace(weight=self.w[name])
+
+    def set_term_cfg(self, name, cfg):
+        self.w[name] = cfg.weight
+
+
+class FakeEnv:
+    def __init__(self, n):
+        self.num_envs, self.device = n, "cpu"
+        self.scene = FakeScene(robot=FakeAsset())
+        self.scene.env_origins = torch.zeros(n, 3)
+        self.action_manager = types.SimpleNamespace(action=torch.zeros(n, 2))
+        self.termination_manager = types.SimpleNamespace()
+        self.max_episode_length = 250
+        self.common_step_counter = 0
+
+
+def golden_actions():
+    g = torch.Generator().manual_seed(1)
+    a = (torch.rand(512, 2, generator=g) * 4 - 2)
+    a[:8] = torch.tensor([[1, 0], [0.5, 0], [-1, 0.3], [0, 1], [1, 1], [1, -1], [2, 2], [0.3, -0.7]], dtype=torch.float32)
+    out = {"actions": a.numpy()}
+    for name, cfgcls in (("rwd", MushrRWDActionCfg), ("fwd", Mushr4WDActionCfg), ("f1", F1Tenth4WDActionCfg)):
+        cfg = cfgcls().throttle_steer
+        env = FakeEnv(a.shape[0])
+        term = cfg.class_type(cfg, env)
+        term.process_actions(a.clone())
+        term.apply_actions()
+        out[name + "_processed"] = term.processed_actions.numpy().copy()
+        out[name + "_wheel"] = env.scene["robot"].captured["vel"].numpy()
+        out[name + "_steer"] = env.scene["robot"].captured["pos"].numpy()
+        out[name + "_wheel_ids"] = np.array(term._wheel_ids)
+    # the base-class true-Ackermann map (ackermann_actions.py:150-201)
+    base_cfg = Mushr4WDActionCfg().throttle_steer
+    env = FakeEnv(a.shape[0])
+    term = wmdp.AckermannAction(base_cfg, env)
+    term.process_actions(a.clone()); term.apply_actions()
+    out["ack_wheel"] = env.scene["robot"].captured["vel"].numpy()
+    out["ack_steer"] = env.scene["robot"].captured["pos"].numpy()
+    np.savez(HERE / "actions.npz", **out)
+
+
+def golden_drift_terms():
+    n = 4096
+    g = torch.Generator().manual_seed(2)
+    pos = torch.cat([torch.rand(n, 2, generator=g) * 6 - 3, torch.zeros(n, 1)], -1)
+    vel_b = torch.randn(n, 3, generator=g) * torch.tensor([2.0, 1.0, 0.2])
+    ang_b = torch.randn(n, 3, generator=g) * torch.tensor([0.3, 0.3, 2.0])
+    ang_w = torch.randn(n, 3, generator=g) * 2.0
+    steer = torch.rand(n, 2, generator=g) * 1.2 - 0.6
+    env = FakeEnv(n)
+    d = env.scene["robot"].data
+    d.root_pos_w, d.root_lin_vel_b, d.root_ang_vel_b, d.root_link_ang_vel_w = pos, vel_b, ang_b, ang_w
+    d.joint_pos = torch.zeros(n, 12); d.joint_pos[:, 4:6] = steer
+    R = D.DriftRewardsCfg()
+    T = D.DriftTerminationsCfg()
+    out = {"pos": pos.numpy(), "vel_b": vel_b.numpy(), "ang_b": ang_b.numpy(), "ang_w": ang_w.numpy(), "steer": steer.numpy()}
+    for name in ("side_slip", "vel", "progress", "tlgr", "turn_energy", "cross_track"):
+        t = getattr(R, name)
+        out["f_" + name] = t.func(env, **t.params).float().numpy()
+        out["w_" + name] = np.float32(t.weight)
+    out["w_term_pens"] = np.float32(R.term_pens.weight)
+    oob = T.out_of_bounds.func(env, **T.out_of_bounds.params)
+    out["out_of_bounds"] = oob.numpy().astype(np.uint8)
+    # is_terminated_term via the stand-in manager semantics
+    env.termination_manager.active_terms = ["time_out", "out_of_bounds"]
+    env.termination_manager.get_term = lambda k: oob if k == "out_of_bounds" else torch.zeros(n, dtype=torch.bool)
+    env.termination_manager.time_outs = (torch.arange(n) % 7 == 0)
+    out["time_outs"] = env.termination_manager.time_outs.numpy().astype(np.uint8)
+    out["f_term_pens"] = R.term_pens.func(env, **R.term_pens.params).numpy()
+    np.savez(HERE / "drift_terms.npz", **out)
+
+
+def golden_reset_along_track():
+    from isaaclab.managers import EventTermCfg
+    cfg = D.DriftEventsCfg().reset_root_state
+    env = FakeEnv(64)
+    out = {}
+    torch.manual_seed(123)
+    u = torch.rand(cfg.params["num_points"])
+    torch.manual_seed(123)
+    term = reset_root_state_along_track(cfg, env)
+    out["u"] = u.numpy()
+    out["reference_poses"] = term.reference_poses.numpy()          # [20, 2, 3]: (pos xyz), (roll pitch yaw deg)
+    ids = torch.arange(64)
+    torch.manual_seed(77)
+    idx = torch.randint(term.num_points, (64,))
+    u_xy = torch.rand((64, 2)); u_yaw = torch.rand(64)
+    torch.manual_seed(77)
+    term(env, ids, **cfg.params)
+    out["idx"], out["u_xy"], out["u_yaw"] = idx.numpy(), u_xy.numpy(), u_yaw.numpy()
+    out["pose"] = env.scene["robot"].captured["pose"].numpy()
+    out["velocity"] = env.scene["robot"].captured["velocity"].numpy()
+    out["pos_noise"], out["yaw_noise"] = np.float32(cfg.params["pos_noise"]), np.float32(cfg.params["yaw_noise"])
+    np.savez(HERE / "reset_along_track.npz", **out)
+
+
+def golden_curriculum():
+    C = D.DriftCurriculumCfg()
+    R = D.DriftRewardsCfg()
+    env = FakeEnv(4)
+    env.reward_manager = FakeRewardManager({"side_slip": R.side_slip.weight, "tlgr": R.tlgr.weight, "term_pens": R.term_pens.weight})
+    rows = []
+    for c in range(1, 250 * 260 + 1):
+        env.common_step_counter = c
+        if c % 50 == 0:                      # the manager calls the terms whenever >=1 env resets; sample every 50 steps
+            for name in ("more_slip", "more_tlgr", "more_term_pens"):
+                t = getattr(C, name)
+                t.func(env, torch.arange(4), **t.params)
+            rows.append((c, env.reward_manager.w["side_slip"], env.reward_manager.w["tlgr"], env.reward_manager.w["term_pens"]))
+    np.savez(HERE / "curriculum.npz", rows=np.array(rows, dtype=np.float64))
+
+
+def golden_euler():
+    g = torch.Generator().manual_seed(5)
+    q = torch.randn(2048, 4, generator=g)
+    q = q / q.norm(dim=-1, keepdim=True)
+    q[:4] = torch.tensor([[1, 0, 0, 0], [0.7071068, 0, 0, 0.7071068], [0.7071068, 0, 0, -0.7071068], [0, 0, 0, 1.0]])
+    env = FakeEnv(q.shape[0])
+    env.scene["robot"].data.root_quat_w = q
+    e = wmdp.root_euler_xyz(env)
+    np.savez(HERE / "euler.npz", quat=q.numpy(), euler=e.numpy())
+
+
+if __name__ == "__main__":
+    golden_actions(); golden_drift_terms(); golden_reset_along_track(); golden_curriculum(); golden_euler()
+    for f in sorted(HERE.glob("*.npz")):
+        print(f.name, f.stat().st_size)

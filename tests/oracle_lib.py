@@ -38,6 +38,7 @@ def _load(name):
     lib.wlo_action_map.argtypes = [vp, vp, vp, vp, i32]
     lib.wlo_drift_terms.argtypes = [vp, vp, vp, vp, vp, vp, i32]
     lib.wlo_euler_xyz.argtypes = [vp, vp, i32]
+    lib.wlo_drift_reset_pose.argtypes = [vp, vp, vp, vp, vp, i32]
     lib.wlo_config_describe.restype = C.c_char_p
     return lib
 
@@ -178,3 +179,12 @@ def euler_xyz(quat):
     out = np.empty((q.shape[0], 3), np.float32)
     assert get_lib().wlo_euler_xyz(_p(q), _p(out), q.shape[0]) == 0
     return out
+
+
+def drift_reset_pose(cfg, idx, u_xy, u_yaw):
+    idx = np.ascontiguousarray(idx, np.int32)
+    u_xy = np.ascontiguousarray(u_xy, np.float32)
+    u_yaw = np.ascontiguousarray(u_yaw, np.float32)
+    pose = np.empty((idx.shape[0], 7), np.float32)
+    assert get_lib().wlo_drift_reset_pose(C.byref(cfg), _p(idx), _p(u_xy), _p(u_yaw), _p(pose), idx.shape[0]) == 0
+    return pose

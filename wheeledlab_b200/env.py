@@ -202,7 +202,7 @@ class ManagerBasedRLEnv:
         self.step_dt = self.spec.step_dt
         self.physics_dt = float(self.spec.cfg.sim_dt)
         self.max_episode_length_s = self.spec.episode_length_s
-        self.max_episode_length = math.ceil(self.max_episode_length_s / self.step_dt)
+        self.max_episode_length = int(self.spec.cfg.max_episode_length)   # ceil(episode_length_s/(dt*decimation)) in doubles
         self.common_step_counter = 0
         self.extras = {}
         self.scene = _Scene(self)

@@ -74,19 +74,14 @@ MUSHR_JOINT_NAMES = [
 ]
 
 
-def generate_reference_poses(num_points: int, track_radius: float, track_straight: float, seed: int) -> np.ndarray:
-    """reset_root_state_along_track.generate_reference_poses (drifting/mdp/events.py:33-100).
-
-    Returns [num_points, 3] float32 rows (x, y, yaw_deg).  The reference draws ``torch.rand(num_points)``
-    from the global generator; here the draw is ``numpy.random.default_rng(seed)`` so that every rank of a
-    sharded run builds the same table.
-    """
+def reference_poses_from_dists(dists: np.ndarray, track_radius: float, track_straight: float) -> np.ndarray:
+    """reset_root_state_along_track.generate_reference_poses (drifting/mdp/events.py:33-100) for given arc
+    lengths ``dists``.  Returns [n, 3] float32 rows (x, y, yaw_deg); the four cases are the two straights
+    (heading 90 / 270 deg) and the two half circles of the stadium."""
     r, s = np.float32(track_radius), np.float32(track_straight)
-    dist_track = np.float32(2.0 * math.pi) * r + np.float32(4.0) * s
-    dists = np.random.default_rng(seed).random(num_points, dtype=np.float32) * dist_track
-    out = np.zeros((num_points, 3), dtype=np.float32)
+    out = np.zeros((len(dists), 3), dtype=np.float32)
     pi = np.float32(math.pi)
-    for k, d in enumerate(dists):
+    for k, d in enumerate(np.asarray(dists, dtype=np.float32)):
         if d < 2 * s:                                   # case 1: +x straight, heading 90 deg
             out[k] = (r, d - s, 90.0)
         elif d < 2 * s + pi * r:                        # case 2: top half-circle
@@ -99,6 +94,14 @@ def generate_reference_poses(num_points: int, track_radius: float, track_straigh
             ang2 = (d - 4 * s - pi * r) / r
             out[k] = (-r * np.cos(ang2), -s - r * np.sin(ang2), 270.0 + ang2 * 180.0 / pi)
     return out
+
+
+def generate_reference_poses(num_points: int, track_radius: float, track_straight: float, seed: int) -> np.ndarray:
+    """The reference draws ``torch.rand(num_points) * perimeter`` from the global generator (events.py:34-35);
+    here the draw is ``numpy.random.default_rng(seed)`` so that every rank of a sharded run builds the same table."""
+    perimeter = np.float32(2.0 * math.pi) * np.float32(track_radius) + np.float32(4.0) * np.float32(track_straight)
+    dists = np.random.default_rng(seed).random(num_points, dtype=np.float32) * perimeter
+    return reference_poses_from_dists(dists, track_radius, track_straight)
 
 
 def material_buckets(num_buckets, static_range, dynamic_range, make_consistent, ground_mu_s, ground_mu_d, seed):
