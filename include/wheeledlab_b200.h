@@ -293,6 +293,9 @@ int wl_curriculum(wl_sim* sim, int64_t step_counter, int32_t n_terms, const int3
 int wl_synth_actions(wl_sim* sim, float* d_action, int64_t step_counter, int32_t dist, void* stream);
 /* derived joint state for the Python articulation view: suspension pos/vel [N,4]x2 */
 int wl_derive_suspension(wl_sim* sim, float* d_susp_pos, float* d_susp_vel, void* stream);
+/* step-kernel geometry: 0 = auto (by num_envs), 1 = one thread per env, 4 = four lanes (one per wheel) per env.
+ * Results are bit-identical across variants. */
+int wl_set_kernel_variant(wl_sim* sim, int32_t lanes_per_env);
 /* observation width for the configured task */
 int32_t wl_obs_dim(const wl_sim* sim);
 /* number of kernel launches issued through this handle since creation */

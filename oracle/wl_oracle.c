@@ -81,7 +81,13 @@ static void philox4x32(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, uin
 static inline real u01(uint32_t x) { return (real)(x >> 8) * K(5.9604644775390625e-08); }
 /* (0,1] */
 static inline real u01_open(uint32_t x) { return (real)((x >> 8) + 1u) * K(5.9604644775390625e-08); }
-static inline real uniform(uint32_t x, real lo, real hi) { return lo + (hi - lo) * u01(x); }
+/* fm(a,b,c) = round(a*b + c), one rounding: mirrors __fmaf_rn on the device */
+#ifdef WLO_DOUBLE
+static inline real fm(real a, real b, real c) { return fma(a, b, c); }
+#else
+static inline real fm(real a, real b, real c) { return fmaf(a, b, c); }
+#endif
+static inline real uniform(uint32_t x, real lo, real hi) { return fm(hi - lo, u01(x), lo); }
 
 /* ------------------------------------------------------------------------- */
 /* deterministic elementary functions (cephes single-precision kernels)      */
@@ -89,19 +95,21 @@ static inline real uniform(uint32_t x, real lo, real hi) { return lo + (hi - lo)
 #ifdef WLO_DOUBLE
 static void det_sincos(real x, real* s, real* c) { *s = sin(x); *c = cos(x); }
 static real det_atan(real x) { return atan(x); }
+static real det_atan_ratio(real num, real den) { return atan(num / den); }
 static real det_atan2(real y, real x) { return atan2(y, x); }
 static real det_log(real x) { return log(x); }
 #else
 static void det_sincos(float x, float* s, float* c) {
-    float q = floorf(x * 0.63661977236758134f + 0.5f);
-    float y = x - q * 1.5703125f;
-    y = y - q * 4.837512969970703125e-4f;
-    y = y - q * 7.54978995489188216e-8f;
+    float q = floorf(fm(x, 0.63661977236758134f, 0.5f));
+    float y = fm(-q, 1.5703125f, x);
+    y = fm(-q, 4.837512969970703125e-4f, y);
+    y = fm(-q, 7.54978995489188216e-8f, y);
     int qi = (int)q;
     float z = y * y;
-    float sp = ((-1.9515295891e-4f * z + 8.3321608736e-3f) * z - 1.6666654611e-1f) * z * y + y;
-    float cp = ((2.443315711809948e-5f * z - 1.388731625493765e-3f) * z + 4.166664568298827e-2f) * z * z -
-               0.5f * z + 1.0f;
+    float ps = fm(fm(-1.9515295891e-4f, z, 8.3321608736e-3f), z, -1.6666654611e-1f);
+    float sp = fm(ps * z, y, y);
+    float pc = fm(fm(2.443315711809948e-5f, z, -1.388731625493765e-3f), z, 4.166664568298827e-2f);
+    float cp = fm(pc * z, z, fm(-0.5f, z, 1.0f));
     switch (qi & 3) {
         case 0: *s = sp; *c = cp; break;
         case 1: *s = cp; *c = -sp; break;
@@ -109,15 +117,19 @@ static void det_sincos(float x, float* s, float* c) {
         default: *s = -cp; *c = sp; break;
     }
 }
-static float det_atan(float xx) {
-    float sign = 1.0f, x = xx, y;
-    if (x < 0.0f) { sign = -1.0f; x = -x; }
-    if (x > 2.414213562373095f) { y = 1.5707963267948966f; x = -(1.0f / x); }
-    else if (x > 0.4142135623730950f) { y = 0.7853981633974483f; x = (x - 1.0f) / (x + 1.0f); }
-    else y = 0.0f;
+/* atan(num/den), num >= 0, den > 0, with one division (cephes ranges applied to the ratio) */
+static float det_atan_ratio(float num, float den) {
+    float y0, x;
+    if (num > 2.414213562373095f * den) { y0 = 1.5707963267948966f; x = -(den / num); }
+    else if (num > 0.4142135623730950f * den) { y0 = 0.7853981633974483f; x = (num - den) / (num + den); }
+    else { y0 = 0.0f; x = num / den; }
     float z = x * x;
-    y += (((8.05374449538e-2f * z - 1.38776856032e-1f) * z + 1.99777106478e-1f) * z - 3.33329491539e-1f) * z * x + x;
-    return sign * y;
+    float p = fm(fm(fm(8.05374449538e-2f, z, -1.38776856032e-1f), z, 1.99777106478e-1f), z, -3.33329491539e-1f);
+    return y0 + fm(p * z, x, x);
+}
+static float det_atan(float xx) {
+    float r = det_atan_ratio(fabsf(xx), 1.0f);
+    return (xx < 0.0f) ? -r : r;
 }
 static float det_atan2(float y, float x) {
     if (x == 0.0f) {
@@ -125,9 +137,10 @@ static float det_atan2(float y, float x) {
         if (y < 0.0f) return -1.5707963267948966f;
         return 0.0f;
     }
-    float z = det_atan(y / x);
-    if (x < 0.0f) z = (y >= 0.0f) ? z + 3.14159265358979323846f : z - 3.14159265358979323846f;
-    return z;
+    float r = det_atan_ratio(fabsf(y), fabsf(x));
+    if ((y < 0.0f) != (x < 0.0f)) r = -r;
+    if (x < 0.0f) r = (y >= 0.0f) ? r + 3.14159265358979323846f : r - 3.14159265358979323846f;
+    return r;
 }
 static float det_log(float xin) {
     uint32_t bits; memcpy(&bits, &xin, 4);
@@ -136,15 +149,16 @@ static float det_log(float xin) {
     float x; memcpy(&x, &bits, 4);
     if (x < 0.707106781186547524f) { e -= 1; x = x + x - 1.0f; } else { x = x - 1.0f; }
     float z = x * x;
-    float y = ((((((((7.0376836292e-2f * x - 1.1514610310e-1f) * x + 1.1676998740e-1f) * x - 1.2420140846e-1f) * x +
-                    1.4249322787e-1f) * x - 1.6668057665e-1f) * x + 2.0000714765e-1f) * x - 2.4999993993e-1f) * x +
-               3.3333331174e-1f) * x * z;
+    float p = fm(7.0376836292e-2f, x, -1.1514610310e-1f);
+    p = fm(p, x, 1.1676998740e-1f); p = fm(p, x, -1.2420140846e-1f); p = fm(p, x, 1.4249322787e-1f);
+    p = fm(p, x, -1.6668057665e-1f); p = fm(p, x, 2.0000714765e-1f); p = fm(p, x, -2.4999993993e-1f);
+    p = fm(p, x, 3.3333331174e-1f);
+    float y = p * x * z;
     float fe = (float)e;
-    y += -2.12194440e-4f * fe;
-    y += -0.5f * z;
-    z = x + y;
-    z += 0.693359375f * fe;
-    return z;
+    y = fm(-2.12194440e-4f, fe, y);
+    y = fm(-0.5f, z, y);
+    float r = x + y;
+    return fm(0.693359375f, fe, r);
 }
 #endif
 static real det_tan(real x) { real s, c; det_sincos(x, &s, &c); return s / c; }
@@ -184,29 +198,30 @@ typedef struct wlo_sim {
     float* hf;
 } wlo_sim;
 
+static inline real dot3(real ax, real ay, real az, real bx, real by, real bz) { return fm(ax, bx, fm(ay, by, az * bz)); }
 static void rotmat(const real q[4], real R[9]) {
     real w = q[0], x = q[1], y = q[2], z = q[3];
-    real xx = x * x, yy = y * y, zz = z * z, xy = x * y, xz = x * z, yz = y * z, wx = w * x, wy = w * y, wz = w * z;
-    R[0] = K(1.0) - K(2.0) * (yy + zz); R[1] = K(2.0) * (xy - wz); R[2] = K(2.0) * (xz + wy);
-    R[3] = K(2.0) * (xy + wz); R[4] = K(1.0) - K(2.0) * (xx + zz); R[5] = K(2.0) * (yz - wx);
-    R[6] = K(2.0) * (xz - wy); R[7] = K(2.0) * (yz + wx); R[8] = K(1.0) - K(2.0) * (xx + yy);
+    R[0] = fm(K(-2.0), fm(y, y, z * z), K(1.0)); R[1] = K(2.0) * fm(x, y, -(w * z)); R[2] = K(2.0) * fm(x, z, w * y);
+    R[3] = K(2.0) * fm(x, y, w * z); R[4] = fm(K(-2.0), fm(x, x, z * z), K(1.0)); R[5] = K(2.0) * fm(y, z, -(w * x));
+    R[6] = K(2.0) * fm(x, z, -(w * y)); R[7] = K(2.0) * fm(y, z, w * x); R[8] = fm(K(-2.0), fm(x, x, y * y), K(1.0));
 }
 /* out = R a   /   out = R^T a */
 static void rot(const real R[9], const real a[3], real o[3]) {
-    o[0] = R[0] * a[0] + R[1] * a[1] + R[2] * a[2];
-    o[1] = R[3] * a[0] + R[4] * a[1] + R[5] * a[2];
-    o[2] = R[6] * a[0] + R[7] * a[1] + R[8] * a[2];
+    o[0] = dot3(R[0], R[1], R[2], a[0], a[1], a[2]);
+    o[1] = dot3(R[3], R[4], R[5], a[0], a[1], a[2]);
+    o[2] = dot3(R[6], R[7], R[8], a[0], a[1], a[2]);
 }
 static void rotT(const real R[9], const real a[3], real o[3]) {
-    o[0] = R[0] * a[0] + R[3] * a[1] + R[6] * a[2];
-    o[1] = R[1] * a[0] + R[4] * a[1] + R[7] * a[2];
-    o[2] = R[2] * a[0] + R[5] * a[1] + R[8] * a[2];
+    o[0] = dot3(R[0], R[3], R[6], a[0], a[1], a[2]);
+    o[1] = dot3(R[1], R[4], R[7], a[0], a[1], a[2]);
+    o[2] = dot3(R[2], R[5], R[8], a[0], a[1], a[2]);
 }
 static void cross(const real a[3], const real b[3], real o[3]) {
-    o[0] = a[1] * b[2] - a[2] * b[1];
-    o[1] = a[2] * b[0] - a[0] * b[2];
-    o[2] = a[0] * b[1] - a[1] * b[0];
+    o[0] = fm(a[1], b[2], -(a[2] * b[1]));
+    o[1] = fm(a[2], b[0], -(a[0] * b[2]));
+    o[2] = fm(a[0], b[1], -(a[1] * b[0]));
 }
+static inline real vdot(const real a[3], const real b[3]) { return dot3(a[0], a[1], a[2], b[0], b[1], b[2]); }
 
 /* ------------------------------------------------------------------------- */
 /* terrain: height z and unit normal n at world (x,y)                          */
@@ -228,9 +243,9 @@ static int hf_sample(const wlo_sim* s, real x, real y, real* z, real* gx, real* 
     if (iy > c->hf_ny - 2) iy = c->hf_ny - 2;
     real tx = fx - (real)ix, ty = fy - (real)iy;
     real z00 = hf_at(s, ix, iy), z10 = hf_at(s, ix + 1, iy), z01 = hf_at(s, ix, iy + 1), z11 = hf_at(s, ix + 1, iy + 1);
-    real za = z00 + (z10 - z00) * tx, zb = z01 + (z11 - z01) * tx;
-    *z = za + (zb - za) * ty;
-    *gx = ((z10 - z00) + ((z11 - z01) - (z10 - z00)) * ty) * inv;
+    real za = fm(z10 - z00, tx, z00), zb = fm(z11 - z01, tx, z01);
+    *z = fm(zb - za, ty, za);
+    *gx = fm((z11 - z01) - (z10 - z00), ty, z10 - z00) * inv;
     *gy = (zb - za) * inv;
     return 1;
 }
@@ -238,7 +253,7 @@ static void terrain(const wlo_sim* s, real x, real y, real* z, real n[3]) {
     if (s->cfg.task == WL_TASK_ELEVATION && s->hf) {
         real gx, gy;
         if (hf_sample(s, x, y, z, &gx, &gy)) {
-            real inv = K(1.0) / r_sqrt(gx * gx + gy * gy + K(1.0));
+            real inv = K(1.0) / r_sqrt(fm(gx, gx, fm(gy, gy, K(1.0))));
             n[0] = -gx * inv; n[1] = -gy * inv; n[2] = inv;
             return;
         }
@@ -301,13 +316,16 @@ static real dc_motor(const wl_config* c, real kd, real effort_limit, real target
 /* ------------------------------------------------------------------------- */
 typedef struct { real pc[3]; real q[4]; real v[3]; real wb[3]; } chassis_t;
 /* per-env-step invariants (reciprocals are formed ONCE per env step, in this order) */
-typedef struct { real h, inv_h, sden, inv_Iw, I[3], invI[3]; } step_consts;
+typedef struct { real h, inv_h, sden, inv_Iw, hkp, fxk, fyk, I[3], invI[3]; } step_consts;
 
 static void make_step_consts(const wl_config* c, const wlo_env* e, step_consts* k) {
     k->h = (real)c->sim_dt / (real)c->substeps;
     k->inv_h = K(1.0) / k->h;
-    k->sden = K(1.0) / ((real)c->steer_inertia + k->h * (real)c->steer_kd + k->h * k->h * (real)c->steer_kp);
+    k->hkp = k->h * (real)c->steer_kp;
+    k->sden = K(1.0) / fm(k->h, k->hkp, fm(k->h, (real)c->steer_kd, (real)c->steer_inertia));
     k->inv_Iw = K(1.0) / (real)c->wheel_inertia;
+    k->fxk = (real)c->tire_mx * k->inv_h;
+    k->fyk = (real)c->tire_my * k->inv_h;
     real ms = e->mass / (real)c->mass_nominal;          /* inertia scales with the mass ratio (a14) */
     for (int a = 0; a < 3; ++a) { k->I[a] = (real)c->inertia_nominal[a] * ms; k->invI[a] = K(1.0) / k->I[a]; }
 }
@@ -318,92 +336,91 @@ static void physics_substep(const wlo_sim* s, wlo_env* e, chassis_t* b, const re
     real h = k->h;
     real R[9]; rotmat(b->q, R);
     /* steering: implicit PD on the steer joint (hound.py:5-12) */
-    real J = (real)c->steer_inertia, kp = (real)c->steer_kp;
-    real sden = k->sden;
     real sn[2], cs[2];
     for (int j = 0; j < 2; ++j) {
-        real vel = (J * e->steer_vel[j] + h * kp * (steer_target[j] - e->steer[j])) * sden;
+        real vel = fm(k->hkp, steer_target[j] - e->steer[j], (real)c->steer_inertia * e->steer_vel[j]) * k->sden;
         vel = r_clamp(vel, -(real)c->steer_vel_limit, (real)c->steer_vel_limit);
-        real pos = r_clamp(e->steer[j] + h * vel, -(real)c->steer_pos_limit, (real)c->steer_pos_limit);
+        real pos = r_clamp(fm(h, vel, e->steer[j]), -(real)c->steer_pos_limit, (real)c->steer_pos_limit);
         e->steer_vel[j] = vel; e->steer[j] = pos;
         det_sincos(pos, &sn[j], &cs[j]);
     }
     real vb[3]; rotT(R, b->v, vb);
-    real Fb[3] = {K(0.0), K(0.0), K(0.0)}, Tb[3] = {K(0.0), K(0.0), K(0.0)};
+    real F[4][3], T[4][3];
     real rw = (real)c->wheel_radius, bw = (real)c->wheel_damping;
-    real inv_h = k->inv_h;
     for (int i = 0; i < 4; ++i) {
         real rho[3];
         rho[0] = ((i >= 2) ? (real)c->hub_x_front : (real)c->hub_x_rear) - (real)c->com[0];
         rho[1] = ((i & 1) ? -(real)c->hub_y : (real)c->hub_y) - (real)c->com[1];
         rho[2] = (real)c->hub_z - (real)c->com[2];
-        real hubw[3]; rot(R, rho, hubw);
-        hubw[0] += b->pc[0]; hubw[1] += b->pc[1]; hubw[2] += b->pc[2];
-        real zt, nw[3]; terrain(s, hubw[0], hubw[1], &zt, nw);
-        real comp = rw - (hubw[2] - zt) * nw[2];
-        /* drive torque first, then friction against the resulting slip (implicit stick, DESIGN.md) */
-        real om_star = e->omega[i] + h * ((tau[i] - bw * e->omega[i]) * k->inv_Iw);
-        real Fx = K(0.0);
-        if (comp > K(0.0)) {
-            real nb[3]; rotT(R, nw, nb);
-            real rc[3] = {rho[0] - rw * nb[0], rho[1] - rw * nb[1], rho[2] - rw * nb[2]};
-            real wxr[3]; cross(b->wb, rc, wxr);
-            real vc[3] = {vb[0] + wxr[0], vb[1] + wxr[1], vb[2] + wxr[2]};
-            real sdot = -(nb[0] * vc[0] + nb[1] * vc[1] + nb[2] * vc[2]);
-            real Fz = (real)c->susp_k * comp + (real)c->susp_c * sdot;
-            if (comp > (real)c->susp_travel) Fz += (real)c->bump_k * (comp - (real)c->susp_travel);
-            Fz = r_max(Fz, K(0.0));
-            real hb[3];
-            if (i >= 2) { hb[0] = cs[i - 2]; hb[1] = sn[i - 2]; hb[2] = K(0.0); }
-            else { hb[0] = K(1.0); hb[1] = K(0.0); hb[2] = K(0.0); }
-            real d = hb[0] * nb[0] + hb[1] * nb[1] + hb[2] * nb[2];
-            real ft[3] = {hb[0] - d * nb[0], hb[1] - d * nb[1], hb[2] - d * nb[2]};
-            real finv = K(1.0) / r_sqrt(ft[0] * ft[0] + ft[1] * ft[1] + ft[2] * ft[2]);
-            ft[0] *= finv; ft[1] *= finv; ft[2] *= finv;
-            real lt[3]; cross(nb, ft, lt);
-            real vx = vc[0] * ft[0] + vc[1] * ft[1] + vc[2] * ft[2];
-            real vy = vc[0] * lt[0] + vc[1] * lt[1] + vc[2] * lt[2];
-            real vsx = vx - om_star * rw;
-            real invden = K(1.0) / r_max(r_fabs(vx), (real)c->tire_v0);
-            real kappa = -vsx * invden, ta = -vy * invden;
-            real sigma = r_sqrt(kappa * kappa + ta * ta);
-            real Fy = K(0.0);
-            if (sigma > K(1.0e-9)) {
-                real sm, cm; det_sincos(e->C[i] * det_atan((real)c->tire_B * sigma), &sm, &cm);
-                real Fmag = Fz * (e->D[i] * sm) / sigma;
-                Fx = Fmag * kappa; Fy = Fmag * ta;
-                real fxm = (real)c->tire_mx * r_fabs(vsx) * inv_h, fym = (real)c->tire_my * r_fabs(vy) * inv_h;
-                Fx = r_clamp(Fx, -fxm, fxm); Fy = r_clamp(Fy, -fym, fym);
-            }
-            real F[3] = {Fz * nb[0] + Fx * ft[0] + Fy * lt[0], Fz * nb[1] + Fx * ft[1] + Fy * lt[1],
-                         Fz * nb[2] + Fx * ft[2] + Fy * lt[2]};
-            real T[3]; cross(rc, F, T);
-            Fb[0] += F[0]; Fb[1] += F[1]; Fb[2] += F[2];
-            Tb[0] += T[0]; Tb[1] += T[1]; Tb[2] += T[2];
+        real comp, nb[3];
+        if (c->task == WL_TASK_ELEVATION) {
+            real hubw[3]; rot(R, rho, hubw);
+            hubw[0] += b->pc[0]; hubw[1] += b->pc[1]; hubw[2] += b->pc[2];
+            real zt, nw[3]; terrain(s, hubw[0], hubw[1], &zt, nw);
+            comp = fm(-(hubw[2] - zt), nw[2], rw);
+            rotT(R, nw, nb);
+        } else {                                     /* plane z = 0 */
+            real hz = dot3(R[6], R[7], R[8], rho[0], rho[1], rho[2]) + b->pc[2];
+            comp = rw - hz;
+            nb[0] = R[6]; nb[1] = R[7]; nb[2] = R[8];
         }
-        e->omega[i] = om_star - h * ((rw * Fx) * k->inv_Iw);
+        /* drive torque first, then friction against the resulting slip (implicit stick, DESIGN.md) */
+        real om_star = fm(h, (tau[i] - bw * e->omega[i]) * k->inv_Iw, e->omega[i]);
+        real rc[3] = {fm(-rw, nb[0], rho[0]), fm(-rw, nb[1], rho[1]), fm(-rw, nb[2], rho[2])};
+        real vc[3]; cross(b->wb, rc, vc);
+        vc[0] += vb[0]; vc[1] += vb[1]; vc[2] += vb[2];
+        real sdot = -vdot(nb, vc);
+        real Fz = fm((real)c->susp_k, comp, (real)c->susp_c * sdot);
+        if (comp > (real)c->susp_travel) Fz = fm((real)c->bump_k, comp - (real)c->susp_travel, Fz);
+        Fz = (comp > K(0.0)) ? r_max(Fz, K(0.0)) : K(0.0);
+        real ft[3];
+        if (i >= 2) {
+            real d = fm(cs[i - 2], nb[0], sn[i - 2] * nb[1]);
+            ft[0] = fm(-d, nb[0], cs[i - 2]); ft[1] = fm(-d, nb[1], sn[i - 2]); ft[2] = -(d * nb[2]);
+        } else {
+            real d = nb[0];
+            ft[0] = fm(-d, nb[0], K(1.0)); ft[1] = -(d * nb[1]); ft[2] = -(d * nb[2]);
+        }
+        real finv = K(1.0) / r_sqrt(vdot(ft, ft));
+        ft[0] *= finv; ft[1] *= finv; ft[2] *= finv;
+        real lt[3]; cross(nb, ft, lt);
+        real vx = vdot(vc, ft), vy = vdot(vc, lt);
+        real sx = fm(om_star, rw, -vx), sy = -vy;     /* slip velocity of the tyre surface */
+        real smag = r_sqrt(fm(sx, sx, sy * sy));
+        real den = r_max(r_fabs(vx), (real)c->tire_v0);
+        real sm, cm; det_sincos(e->C[i] * det_atan_ratio((real)c->tire_B * smag, den), &sm, &cm);
+        real Fmag = Fz * (e->D[i] * sm);
+        real inv_s = K(1.0) / r_max(smag, K(1.0e-9));
+        real Fx = (Fmag * sx) * inv_s, Fy = (Fmag * sy) * inv_s;
+        real fxm = k->fxk * r_fabs(sx), fym = k->fyk * r_fabs(sy);
+        Fx = r_clamp(Fx, -fxm, fxm); Fy = r_clamp(Fy, -fym, fym);
+        for (int a = 0; a < 3; ++a) F[i][a] = fm(Fz, nb[a], fm(Fx, ft[a], Fy * lt[a]));
+        cross(rc, F[i], T[i]);
+        e->omega[i] = fm(-h, (rw * Fx) * k->inv_Iw, om_star);
     }
+    real Fb[3], Tb[3];
+    for (int a = 0; a < 3; ++a) { Fb[a] = (F[0][a] + F[1][a]) + (F[2][a] + F[3][a]); Tb[a] = (T[0][a] + T[1][a]) + (T[2][a] + T[3][a]); }
     /* chassis: semi-implicit Euler, Euler's equations in the body frame (gyroscopic term on, mushr.py:28) */
     real Fw[3]; rot(R, Fb, Fw);
-    b->v[0] = b->v[0] + h * (Fw[0] * e->inv_mass);
-    b->v[1] = b->v[1] + h * (Fw[1] * e->inv_mass);
-    b->v[2] = b->v[2] + h * (Fw[2] * e->inv_mass - (real)c->gravity);
+    b->v[0] = fm(h, Fw[0] * e->inv_mass, b->v[0]);
+    b->v[1] = fm(h, Fw[1] * e->inv_mass, b->v[1]);
+    b->v[2] = fm(h, fm(Fw[2], e->inv_mass, -(real)c->gravity), b->v[2]);
     real Iw3[3] = {k->I[0] * b->wb[0], k->I[1] * b->wb[1], k->I[2] * b->wb[2]};
     real g[3]; cross(b->wb, Iw3, g);
-    b->wb[0] = b->wb[0] + h * ((Tb[0] - g[0]) * k->invI[0]);
-    b->wb[1] = b->wb[1] + h * ((Tb[1] - g[1]) * k->invI[1]);
-    b->wb[2] = b->wb[2] + h * ((Tb[2] - g[2]) * k->invI[2]);
-    b->pc[0] = b->pc[0] + h * b->v[0];
-    b->pc[1] = b->pc[1] + h * b->v[1];
-    b->pc[2] = b->pc[2] + h * b->v[2];
+    b->wb[0] = fm(h, (Tb[0] - g[0]) * k->invI[0], b->wb[0]);
+    b->wb[1] = fm(h, (Tb[1] - g[1]) * k->invI[1], b->wb[1]);
+    b->wb[2] = fm(h, (Tb[2] - g[2]) * k->invI[2], b->wb[2]);
+    b->pc[0] = fm(h, b->v[0], b->pc[0]);
+    b->pc[1] = fm(h, b->v[1], b->pc[1]);
+    b->pc[2] = fm(h, b->v[2], b->pc[2]);
     real hh = K(0.5) * h;
     real qw = b->q[0], qx = b->q[1], qy = b->q[2], qz = b->q[3];
     real ox = b->wb[0], oy = b->wb[1], oz = b->wb[2];
-    real nqw = qw - hh * (qx * ox + qy * oy + qz * oz);
-    real nqx = qx + hh * (qw * ox + qy * oz - qz * oy);
-    real nqy = qy + hh * (qw * oy + qz * ox - qx * oz);
-    real nqz = qz + hh * (qw * oz + qx * oy - qy * ox);
-    real qinv = K(1.0) / r_sqrt(nqw * nqw + nqx * nqx + nqy * nqy + nqz * nqz);
+    real nqw = fm(-hh, dot3(qx, qy, qz, ox, oy, oz), qw);
+    real nqx = fm(hh, fm(qw, ox, fm(qy, oz, -(qz * oy))), qx);
+    real nqy = fm(hh, fm(qw, oy, fm(qz, ox, -(qx * oz))), qy);
+    real nqz = fm(hh, fm(qw, oz, fm(qx, oy, -(qy * ox))), qz);
+    real qinv = K(1.0) / r_sqrt(fm(nqw, nqw, fm(nqx, nqx, fm(nqy, nqy, nqz * nqz))));
     b->q[0] = nqw * qinv; b->q[1] = nqx * qinv; b->q[2] = nqy * qinv; b->q[3] = nqz * qinv;
 }
 
@@ -414,9 +431,9 @@ static void physics_substep(const wlo_sim* s, wlo_env* e, chassis_t* b, const re
 static inline real wrap_2pi(real a) { return (a < K(0.0)) ? a + TWO_PI_R : a; }
 static void euler_xyz(const real q[4], real e[3]) {
     real w = q[0], x = q[1], y = q[2], z = q[3];
-    real sin_roll = K(2.0) * (w * x + y * z), cos_roll = K(1.0) - K(2.0) * (x * x + y * y);
-    real sin_pitch = K(2.0) * (w * y - z * x);
-    real sin_yaw = K(2.0) * (w * z + x * y), cos_yaw = K(1.0) - K(2.0) * (y * y + z * z);
+    real sin_roll = K(2.0) * fm(w, x, y * z), cos_roll = fm(K(-2.0), fm(x, x, y * y), K(1.0));
+    real sin_pitch = K(2.0) * fm(w, y, -(z * x));
+    real sin_yaw = K(2.0) * fm(w, z, x * y), cos_yaw = fm(K(-2.0), fm(y, y, z * z), K(1.0));
     real pitch;
     if (r_fabs(sin_pitch) >= K(1.0)) pitch = (sin_pitch < K(0.0)) ? -HALF_PI_R : HALF_PI_R;
     else pitch = det_asin(sin_pitch);

@@ -84,16 +84,18 @@ def test_startup_and_reset_state_bit_exact():
     assert np.array_equal(_bits(_state_groups(sim)), _bits(orc.export_state()))
 
 
+@pytest.mark.parametrize("variant", [1, 4])      # one thread per env / four lanes (one per wheel) per env
 @pytest.mark.parametrize("n,steps,kw", [
     (256, 1000, {}),                               # RSS_DRIFT settings, DR + pushes + noise on
     (333, 300, {"randomize": False}),              # ragged N (not a multiple of the CTA), DR off
     (64, 300, {"drive": "4wd"}),                   # BASELINE config 4: 4WD action map + 4 driven wheels
     (1, 260, {}),                                  # single env (BASELINE config 1 plumbing size)
 ])
-def test_step_trajectory_bit_exact(n, steps, kw):
+def test_step_trajectory_bit_exact(n, steps, kw, variant):
     """1000-step trajectories: obs, reward, done masks, episode log and the full state, every step."""
     _need_gpu()
     spec, sim, orc = _pair(n, seed=42, **kw)
+    sim.set_kernel_variant(variant)
     n_done = 0
     for t in range(steps):
         act = sim.synth_actions(t, dist=t % 2)
@@ -137,6 +139,21 @@ def test_observe_resamples_noise_bit_exact():
     a = sim.observe(0, 0).cpu().numpy(); b = sim.observe(0, 1).cpu().numpy()
     assert np.array_equal(_bits(a), _bits(orc.observe(0, 0))) and np.array_equal(_bits(b), _bits(orc.observe(0, 1)))
     assert not np.array_equal(a[:, :12], b[:, :12]) and np.array_equal(a[:, 12:], b[:, 12:])
+
+
+def test_kernel_variants_agree_at_full_size():
+    """4096 envs (RSS_DRIFT_CONFIG size): thread-per-env and quad-per-env kernels give identical bits."""
+    _need_gpu()
+    import wheeledlab_b200 as wl
+    a = wl.WheeledSim(wl.drift_task(num_envs=4096, seed=42), "cuda:0"); b = wl.WheeledSim(wl.drift_task(num_envs=4096, seed=42), "cuda:0")
+    a.set_kernel_variant(1); b.set_kernel_variant(4)
+    for s in (a, b):
+        s.startup(); s.reset(None, 0)
+    for t in range(400):
+        act = a.synth_actions(t)
+        for x, y in zip(a.step(act, t), b.step(act, t)):
+            assert torch.equal(x, y), f"variant mismatch at step {t}"
+    assert torch.equal(a.groups, b.groups)
 
 
 def test_sharding_invariance_two_shards_equal_one():

@@ -20,7 +20,11 @@ struct wl_sim {
     size_t state_bytes;
     int64_t launches;
     int obs_dim;
+    int variant;            // 0 auto, 1 thread-per-env, 4 quad-per-env
 };
+
+// below this many envs one thread/env cannot fill 148 SMs x 4 schedulers; use 4 lanes per env
+#define WL_QUAD_MAX_ENVS (148 * 4 * 32 * 2)
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
@@ -74,12 +78,12 @@ wl_step_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st, wl_
         b.pc = V3{e.p.x + cw.x, e.p.y + cw.y, e.p.z + cw.z};
         b.v = e.v; b.qw = e.qw; b.qx = e.qx; b.qy = e.qy; b.qz = e.qz;
         b.wb = rotT(R, e.w);
-        StepConsts kc = make_step_consts(c, e);
+        StepConsts kc = make_step_consts(c, e.mass);
         for (int d = 0; d < c.decimation; ++d) {
             float tau[4];
 #pragma unroll
             for (int w = 0; w < 4; ++w) tau[w] = dc_motor(c, e.kd[w], c.dc_effort[w], wheel_target[w], e.omega[w]);
-            for (int j = 0; j < c.substeps; ++j) physics_substep<TASK>(c, T, e, b, tau, steer_target, kc);
+            for (int j = 0; j < c.substeps; ++j) physics_substep<TASK, 1>(c, T, e, b, tau, steer_target, kc);
         }
         R = rotmat(b.qw, b.qx, b.qy, b.qz);
         cw = rot(R, V3{c.com[0], c.com[1], c.com[2]});
@@ -95,7 +99,7 @@ wl_step_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st, wl_
         V3 vb = rotT(R, e.v);
         if (TASK == WL_TASK_DRIFT) {
             terminated = drift_off_track(c, e.p.x, e.p.y);
-            drift_reward_terms(c, e, e.p, vb, b.wb, e.w.z, terminated, time_out, f);
+            drift_reward_terms(c, e.steer[0], e.steer[1], det_atan2(vb.y, vb.x), e.p, vb, b.wb, e.w.z, terminated, time_out, f);
         }
         // E. rewards: value = f*w*dt, skipped when w == 0
         float total = 0.0f;
@@ -141,6 +145,123 @@ wl_step_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st, wl_
         if (TASK == WL_TASK_DRIFT) blind_obs(c, e, gid, t, RNG_OBS, 0u, obs + (size_t)WL_OBS_DIM_BLIND * i);
         store_env(st, n, i, e, TASK == WL_TASK_ELEVATION);
     }
+}
+
+// Four lanes per env (lane = wheel).  Same arithmetic, same results; the per-wheel work runs in parallel and the
+// chassis is integrated redundantly in the 4 lanes.  Used when N is too small to fill the chip with one thread/env.
+template <int TASK>
+__global__ void __launch_bounds__(128)
+wl_step_quad_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st, wl_globals* __restrict__ gl, Terrain T,
+                    const float2* __restrict__ action, float* __restrict__ obs, float* __restrict__ rew,
+                    uint8_t* __restrict__ terminated_o, uint8_t* __restrict__ truncated_o, uint32_t t) {
+    const int n = c.num_envs;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = tid >> 2, w = tid & 3;
+    const int slot = (int)(t & 1u);
+    if (tid == 0) {
+#pragma unroll
+        for (int k = 0; k < WL_MAX_REW_TERMS; ++k) gl->log_sum[slot ^ 1][k] = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) gl->log_term[slot ^ 1][k] = 0.0f;
+        gl->any_reset[slot ^ 1] = 0;
+    }
+    const bool live = i < n;                 // a whole quad is live or not (blockDim is a multiple of 4)
+    const int ii = live ? i : n - 1;         // dead quads shadow the last env (no stores) so shuffles stay convergent
+    const uint32_t gid = (uint32_t)(c.env_id_offset + ii);
+    const unsigned base = (threadIdx.x & 31u) & ~3u;
+    EnvState e;
+    load_env_quad(st, n, ii, w, e, TASK == WL_TASK_ELEVATION);
+    // A. action manager (redundant in the 4 lanes)
+    float2 a = action[ii];
+    e.prev_action[0] = e.action[0]; e.prev_action[1] = e.action[1];
+    e.action[0] = a.x; e.action[1] = a.y;
+    float wheel_target[4], steer_target[2];
+    process_action(c, a.x, a.y, wheel_target, steer_target);
+    const float my_target = (w == 0) ? wheel_target[0] : (w == 1) ? wheel_target[1] : (w == 2) ? wheel_target[2] : wheel_target[3];
+    const float my_effort = (w == 0) ? c.dc_effort[0] : (w == 1) ? c.dc_effort[1] : (w == 2) ? c.dc_effort[2] : c.dc_effort[3];
+    float my_steer_target[2] = {(w == 3) ? steer_target[1] : steer_target[0], 0.0f};
+    // B. decimation x (actuators -> integrator)
+    Chassis b;
+    M3 R = rotmat(e.qw, e.qx, e.qy, e.qz);
+    V3 cw = rot(R, V3{c.com[0], c.com[1], c.com[2]});
+    b.pc = V3{e.p.x + cw.x, e.p.y + cw.y, e.p.z + cw.z};
+    b.v = e.v; b.qw = e.qw; b.qx = e.qx; b.qy = e.qy; b.qz = e.qz;
+    b.wb = rotT(R, e.w);
+    StepConsts kc = make_step_consts(c, e.mass);
+    for (int d = 0; d < c.decimation; ++d) {
+        float tau[4];
+        tau[0] = dc_motor(c, e.kd[0], my_effort, my_target, e.omega[0]);
+        for (int j = 0; j < c.substeps; ++j) physics_substep<TASK, 4>(c, T, e, b, tau, my_steer_target, kc);
+    }
+    R = rotmat(b.qw, b.qx, b.qy, b.qz);
+    cw = rot(R, V3{c.com[0], c.com[1], c.com[2]});
+    e.p = V3{b.pc.x - cw.x, b.pc.y - cw.y, b.pc.z - cw.z};
+    e.v = b.v; e.qw = b.qw; e.qx = b.qx; e.qy = b.qy; e.qz = b.qz;
+    e.w = rot(R, b.wb);
+    // C./D. counters, terminations (redundant)
+    e.ep_len += 1;
+    const bool time_out = e.ep_len >= c.max_episode_length;
+    const float step_dt = c.sim_dt * (float)c.decimation;
+    V3 vb = rotT(R, e.v);
+    bool terminated = false;
+    float f[WL_MAX_REW_TERMS];
+    const float steer_l = __shfl_sync(0xffffffffu, e.steer[0], base + 2), steer_r = __shfl_sync(0xffffffffu, e.steer[0], base + 3);
+    if (TASK == WL_TASK_DRIFT) {
+        terminated = drift_off_track(c, e.p.x, e.p.y);
+        drift_reward_terms(c, steer_l, steer_r, det_atan2(vb.y, vb.x), e.p, vb, b.wb, e.w.z, terminated, time_out, f);
+    }
+    float total = 0.0f;
+#pragma unroll
+    for (int k = 0; k < WL_MAX_REW_TERMS; ++k) {
+        if (k < c.num_rew_terms) {
+            float wgt = __ldg(&gl->rew_weight[k]);
+            if (wgt != 0.0f) { float val = f[k] * wgt * step_dt; total += val; e.sums[k] += val; }
+        }
+    }
+    const bool done = terminated || time_out;
+    if (live && w == 0) { rew[i] = total; terminated_o[i] = terminated ? 1 : 0; truncated_o[i] = time_out ? 1 : 0; }
+    // F. per-step episode log: one contribution per env (lane 0 of each live quad)
+    const bool contrib = done && live && (w == 0);
+    const unsigned any = __ballot_sync(0xffffffffu, contrib);
+    if (any) {
+        float vals[WL_MAX_REW_TERMS + 3];
+#pragma unroll
+        for (int k = 0; k < WL_MAX_REW_TERMS; ++k) vals[k] = contrib ? e.sums[k] : 0.0f;
+        vals[WL_MAX_REW_TERMS + 0] = contrib ? 1.0f : 0.0f;
+        vals[WL_MAX_REW_TERMS + 1] = (contrib && terminated) ? 1.0f : 0.0f;
+        vals[WL_MAX_REW_TERMS + 2] = (contrib && time_out) ? 1.0f : 0.0f;
+#pragma unroll
+        for (int k = 0; k < WL_MAX_REW_TERMS + 3; ++k) vals[k] = warp_sum(vals[k]);
+        if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+            for (int k = 0; k < WL_MAX_REW_TERMS; ++k) atomicAdd(&gl->log_sum[slot][k], vals[k]);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) atomicAdd(&gl->log_term[slot][k], vals[WL_MAX_REW_TERMS + k]);
+            gl->any_reset[slot] = 1;
+        }
+    }
+    if (done) {
+        if (TASK == WL_TASK_DRIFT) drift_reset_env(c, e, gid, t);      // redundant in the 4 lanes; joints untouched (Q3)
+    }
+    interval_pushes(c, e, gid, t, step_dt);
+    // I. observations: the three euler angles are three atan2 calls -> one per lane
+    {
+        float qw = e.qw, qx = e.qx, qy = e.qy, qz = e.qz;
+        float sin_roll = 2.0f * fm(qw, qx, qy * qz), cos_roll = fm(-2.0f, fm(qx, qx, qy * qy), 1.0f);
+        float sin_pitch = 2.0f * fm(qw, qy, -(qz * qx));
+        float sin_yaw = 2.0f * fm(qw, qz, qx * qy), cos_yaw = fm(-2.0f, fm(qy, qy, qz * qz), 1.0f);
+        float ay = (w == 0) ? sin_roll : (w == 1) ? sin_pitch : sin_yaw;
+        float ax = (w == 0) ? cos_roll : (w == 1) ? sqrtf((1.0f - sin_pitch) * (1.0f + sin_pitch)) : cos_yaw;
+        float ang = det_atan2(ay, ax);
+        if (w == 1 && fabsf(sin_pitch) >= 1.0f) ang = (sin_pitch < 0.0f) ? -1.57079632679489661923f : 1.57079632679489661923f;
+        float eu_k = wrap_2pi(ang);
+        if (TASK == WL_TASK_DRIFT) {
+            // blind_obs_quad shuffles: every lane of the warp calls it, dead quads only skip the stores
+            float* o = obs + (size_t)WL_OBS_DIM_BLIND * ii;
+            blind_obs_quad(c, e, w, eu_k, gid, t, RNG_OBS, 0u, o, live);
+        }
+    }
+    if (live) store_env_quad(st, n, i, w, e, TASK == WL_TASK_ELEVATION);
 }
 
 __global__ void wl_startup_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st) {
@@ -299,6 +420,7 @@ int wl_create(const wl_config* cfg, void* d_state, size_t state_bytes, const flo
     s->hf = d_heightfield;
     s->state_bytes = state_bytes;
     s->launches = 0;
+    s->variant = 0;
     s->obs_dim = (cfg->task == WL_TASK_ELEVATION) ? WL_OBS_DIM_ELEV : WL_OBS_DIM_BLIND;
     // live reward weights
     if (int rc = cuda_check(cudaMemcpy(s->globals->rew_weight, cfg->rew_weight, sizeof(float) * WL_MAX_REW_TERMS,
@@ -309,6 +431,12 @@ int wl_create(const wl_config* cfg, void* d_state, size_t state_bytes, const flo
 
 int wl_destroy(wl_sim* sim) { delete sim; return WL_OK; }
 int32_t wl_obs_dim(const wl_sim* sim) { return sim ? sim->obs_dim : 0; }
+int wl_set_kernel_variant(wl_sim* sim, int32_t lanes_per_env) {
+    if (!sim) return fail(WL_EINVAL, "wl_set_kernel_variant: null handle");
+    if (lanes_per_env != 0 && lanes_per_env != 1 && lanes_per_env != 4) return fail(WL_EINVAL, "wl_set_kernel_variant: 0, 1 or 4");
+    sim->variant = lanes_per_env;
+    return WL_OK;
+}
 int64_t wl_launch_count(const wl_sim* sim) { return sim ? sim->launches : 0; }
 
 #define WL_LAUNCH_CHECK(sim, what)                                                     \
@@ -339,11 +467,20 @@ int wl_step(wl_sim* sim, const float* d_action, float* d_obs, float* d_rew, uint
             int64_t step_counter, void* stream) {
     if (!sim || !d_action || !d_obs || !d_rew || !d_terminated || !d_truncated) return fail(WL_EINVAL, "wl_step: null argument");
     if (((uintptr_t)d_action & 7u) || ((uintptr_t)d_obs & 7u)) return fail(WL_EINVAL, "wl_step: action/obs must be 8-byte aligned");
-    const int n = sim->cfg.num_envs, bs = pick_block(n);
+    const int n = sim->cfg.num_envs;
     Terrain T{sim->hf};
-    wl_step_kernel<WL_TASK_DRIFT><<<(n + bs - 1) / bs, bs, 0, (cudaStream_t)stream>>>(
-        sim->cfg, sim->state, sim->globals, T, reinterpret_cast<const float2*>(d_action), d_obs, d_rew, d_terminated,
-        d_truncated, (uint32_t)step_counter);
+    const int variant = sim->variant ? sim->variant : ((n <= WL_QUAD_MAX_ENVS) ? 4 : 1);
+    if (variant == 4) {
+        const int bs = 32, threads = 4 * n;
+        wl_step_quad_kernel<WL_TASK_DRIFT><<<(threads + bs - 1) / bs, bs, 0, (cudaStream_t)stream>>>(
+            sim->cfg, sim->state, sim->globals, T, reinterpret_cast<const float2*>(d_action), d_obs, d_rew, d_terminated,
+            d_truncated, (uint32_t)step_counter);
+    } else {
+        const int bs = pick_block(n);
+        wl_step_kernel<WL_TASK_DRIFT><<<(n + bs - 1) / bs, bs, 0, (cudaStream_t)stream>>>(
+            sim->cfg, sim->state, sim->globals, T, reinterpret_cast<const float2*>(d_action), d_obs, d_rew, d_terminated,
+            d_truncated, (uint32_t)step_counter);
+    }
     WL_LAUNCH_CHECK(sim, "wl_step_kernel");
     return WL_OK;
 }

@@ -60,6 +60,49 @@ __device__ __forceinline__ void store_env(float4* __restrict__ st, int n, int i,
     if (with_cmd) stg4(st, WL_G_CMD, n, i, make_float4(e.cmd[0], e.cmd[1], e.cmd[2], e.cmd[3]));
 }
 
+// ---- quad (4 lanes per env) state access: lane w = wheel [bl,br,fl,fr][w].  Per-wheel scalars live in slot [0]
+// of the lane's EnvState (omega, D, C, kd) and front lanes keep THEIR steer joint in steer[0]/steer_vel[0].
+__device__ __forceinline__ void load_env_quad(const float4* __restrict__ st, int n, int i, int w, EnvState& e, bool with_cmd) {
+    float4 g;
+    g = ldg4(st, WL_G_POS, n, i); e.p = V3{g.x, g.y, g.z}; e.ep_len = __float_as_int(g.w);
+    g = ldg4(st, WL_G_QUAT, n, i); e.qw = g.x; e.qx = g.y; e.qy = g.z; e.qz = g.w;
+    g = ldg4(st, WL_G_LINVEL, n, i); e.v = V3{g.x, g.y, g.z}; e.t_hf = g.w;
+    g = ldg4(st, WL_G_ANGVEL, n, i); e.w = V3{g.x, g.y, g.z}; e.t_lf = g.w;
+    g = ldg4(st, WL_G_ACTION, n, i); e.action[0] = g.x; e.action[1] = g.y; e.prev_action[0] = g.z; e.prev_action[1] = g.w;
+    g = ldg4(st, WL_G_SUM0, n, i); e.sums[0] = g.x; e.sums[1] = g.y; e.sums[2] = g.z; e.sums[3] = g.w;
+    g = ldg4(st, WL_G_SUM1, n, i); e.sums[4] = g.x; e.sums[5] = g.y; e.sums[6] = g.z; e.sums[7] = g.w;
+    g = ldg4(st, WL_G_PMASS, n, i); e.mass = g.x; e.inv_mass = g.y; e.spare0 = g.z; e.spare1 = g.w;
+    const float* f = reinterpret_cast<const float*>(st);
+    const size_t lane_off = (size_t)i * 4 + w;                       // 32 lanes -> 128 contiguous bytes
+    e.omega[0] = f[(size_t)WL_G_WHEEL * n * 4 + lane_off];
+    e.D[0] = f[(size_t)WL_G_PMU_D * n * 4 + lane_off];
+    e.C[0] = f[(size_t)WL_G_PMU_C * n * 4 + lane_off];
+    e.kd[0] = f[(size_t)WL_G_PKD * n * 4 + lane_off];
+    g = ldg4(st, WL_G_STEER, n, i);
+    e.steer[0] = (w == 3) ? g.y : g.x; e.steer_vel[0] = (w == 3) ? g.w : g.z;   // lanes 0-2 see the LEFT joint, lane 3 the right
+    e.steer[1] = g.y; e.steer_vel[1] = g.w;
+    if (with_cmd) { g = ldg4(st, WL_G_CMD, n, i); e.cmd[0] = g.x; e.cmd[1] = g.y; e.cmd[2] = g.z; e.cmd[3] = g.w; }
+}
+__device__ __forceinline__ void store_env_quad(float4* __restrict__ st, int n, int i, int w, const EnvState& e, bool with_cmd) {
+    float* f = reinterpret_cast<float*>(st);
+    f[(size_t)WL_G_WHEEL * n * 4 + (size_t)i * 4 + w] = e.omega[0];
+    if (w >= 2) {                                                      // own steer joint: pos at [w-2], vel at [2 + w-2]
+        f[(size_t)WL_G_STEER * n * 4 + (size_t)i * 4 + (w - 2)] = e.steer[0];
+        f[(size_t)WL_G_STEER * n * 4 + (size_t)i * 4 + w] = e.steer_vel[0];
+    }
+    if (w == 0) {
+        stg4(st, WL_G_POS, n, i, make_float4(e.p.x, e.p.y, e.p.z, __int_as_float(e.ep_len)));
+        stg4(st, WL_G_QUAT, n, i, make_float4(e.qw, e.qx, e.qy, e.qz));
+        stg4(st, WL_G_LINVEL, n, i, make_float4(e.v.x, e.v.y, e.v.z, e.t_hf));
+        stg4(st, WL_G_ANGVEL, n, i, make_float4(e.w.x, e.w.y, e.w.z, e.t_lf));
+    } else if (w == 1) {
+        stg4(st, WL_G_ACTION, n, i, make_float4(e.action[0], e.action[1], e.prev_action[0], e.prev_action[1]));
+        stg4(st, WL_G_SUM0, n, i, make_float4(e.sums[0], e.sums[1], e.sums[2], e.sums[3]));
+        stg4(st, WL_G_SUM1, n, i, make_float4(e.sums[4], e.sums[5], e.sums[6], e.sums[7]));
+        if (with_cmd) stg4(st, WL_G_CMD, n, i, make_float4(e.cmd[0], e.cmd[1], e.cmd[2], e.cmd[3]));
+    }
+}
+
 // ---- A. action term ---------------------------------------------------------------
 __device__ __forceinline__ void process_action(const wl_config& c, float a0, float a1, float wheel_target[4], float steer_target[2]) {
     if (c.bounding == WL_BOUND_CLIP) { a0 = r_clamp(a0, -1.0f, 1.0f); a1 = r_clamp(a1, -1.0f, 1.0f); }
@@ -100,32 +143,28 @@ __device__ __forceinline__ float dc_motor(const wl_config& c, float kd, float ef
 // ---- terrain -----------------------------------------------------------------------
 struct Terrain { const float* __restrict__ hf; };
 
-template <int TASK>
-__device__ __forceinline__ void terrain_at(const wl_config& c, const Terrain& T, float x, float y, float& z, V3& n) {
-    if (TASK == WL_TASK_ELEVATION) {
-        if (T.hf != nullptr) {
-            float inv = 1.0f / c.hf_cell;
-            float fx = (x - c.hf_x0) * inv, fy = (y - c.hf_y0) * inv;
-            if ((fx >= 0.0f) && (fy >= 0.0f) && (fx <= (float)(c.hf_nx - 1)) && (fy <= (float)(c.hf_ny - 1))) {
-                int ix = (int)floorf(fx), iy = (int)floorf(fy);
-                if (ix > c.hf_nx - 2) ix = c.hf_nx - 2;
-                if (iy > c.hf_ny - 2) iy = c.hf_ny - 2;
-                float tx = fx - (float)ix, ty = fy - (float)iy;
-                const float* row0 = T.hf + (size_t)iy * c.hf_nx + ix;
-                const float* row1 = row0 + c.hf_nx;
-                float z00 = __ldg(row0), z10 = __ldg(row0 + 1), z01 = __ldg(row1), z11 = __ldg(row1 + 1);
-                float za = z00 + (z10 - z00) * tx, zb = z01 + (z11 - z01) * tx;
-                z = za + (zb - za) * ty;
-                float gx = ((z10 - z00) + ((z11 - z01) - (z10 - z00)) * ty) * inv;
-                float gy = (zb - za) * inv;
-                float ninv = 1.0f / sqrtf(gx * gx + gy * gy + 1.0f);
-                n = V3{-gx * ninv, -gy * ninv, ninv};
-                return;
-            }
-            z = c.hf_outside_z;
-        } else {
-            z = 0.0f;
+// height z and unit normal n (world) under world point (x, y).  FLAT tasks never call this.
+__device__ __forceinline__ void heightfield_at(const wl_config& c, const Terrain& T, float x, float y, float& z, V3& n) {
+    if (T.hf != nullptr) {
+        float inv = 1.0f / c.hf_cell;
+        float fx = (x - c.hf_x0) * inv, fy = (y - c.hf_y0) * inv;
+        if ((fx >= 0.0f) && (fy >= 0.0f) && (fx <= (float)(c.hf_nx - 1)) && (fy <= (float)(c.hf_ny - 1))) {
+            int ix = (int)floorf(fx), iy = (int)floorf(fy);
+            if (ix > c.hf_nx - 2) ix = c.hf_nx - 2;
+            if (iy > c.hf_ny - 2) iy = c.hf_ny - 2;
+            float tx = fx - (float)ix, ty = fy - (float)iy;
+            const float* row0 = T.hf + (size_t)iy * c.hf_nx + ix;
+            const float* row1 = row0 + c.hf_nx;
+            float z00 = __ldg(row0), z10 = __ldg(row0 + 1), z01 = __ldg(row1), z11 = __ldg(row1 + 1);
+            float za = fm(z10 - z00, tx, z00), zb = fm(z11 - z01, tx, z01);
+            z = fm(zb - za, ty, za);
+            float gx = fm((z11 - z01) - (z10 - z00), ty, z10 - z00) * inv;
+            float gy = (zb - za) * inv;
+            float ninv = 1.0f / sqrtf(fm(gx, gx, fm(gy, gy, 1.0f)));
+            n = V3{-gx * ninv, -gy * ninv, ninv};
+            return;
         }
+        z = c.hf_outside_z;
     } else {
         z = 0.0f;
     }
@@ -134,104 +173,150 @@ __device__ __forceinline__ void terrain_at(const wl_config& c, const Terrain& T,
 
 // ---- a8 integrator sub-step ----------------------------------------------------------
 struct Chassis { V3 pc; float qw, qx, qy, qz; V3 v; V3 wb; };
-struct StepConsts { float h, inv_h, sden, inv_Iw; float I[3], invI[3]; };
+struct StepConsts { float h, inv_h, sden, inv_Iw, hkp, fxk, fyk; float I[3], invI[3]; };
 
-__device__ __forceinline__ StepConsts make_step_consts(const wl_config& c, const EnvState& e) {
+__device__ __forceinline__ StepConsts make_step_consts(const wl_config& c, float mass) {
     StepConsts k;
     k.h = c.sim_dt / (float)c.substeps;
     k.inv_h = 1.0f / k.h;
-    k.sden = 1.0f / (c.steer_inertia + k.h * c.steer_kd + k.h * k.h * c.steer_kp);
+    k.hkp = k.h * c.steer_kp;
+    k.sden = 1.0f / fm(k.h, k.hkp, fm(k.h, c.steer_kd, c.steer_inertia));
     k.inv_Iw = 1.0f / c.wheel_inertia;
-    float ms = e.mass / c.mass_nominal;
+    k.fxk = c.tire_mx * k.inv_h;
+    k.fyk = c.tire_my * k.inv_h;
+    float ms = mass / c.mass_nominal;
 #pragma unroll
     for (int a = 0; a < 3; ++a) { k.I[a] = c.inertia_nominal[a] * ms; k.invI[a] = 1.0f / k.I[a]; }
     return k;
 }
 
+// steer joint j (0 left, 1 right): implicit PD step, returns sin/cos of the new angle
+__device__ __forceinline__ void steer_step(const wl_config& c, const StepConsts& k, float target, float& pos, float& vel,
+                                           float& sn, float& cs) {
+    float v = fm(k.hkp, target - pos, c.steer_inertia * vel) * k.sden;
+    v = r_clamp(v, -c.steer_vel_limit, c.steer_vel_limit);
+    float p = r_clamp(fm(k.h, v, pos), -c.steer_pos_limit, c.steer_pos_limit);
+    vel = v; pos = p;
+    det_sincos(p, sn, cs);
+}
+
+struct WheelOut { V3 F, Tq; float omega; };
+
+// one wheel: contact, Pacejka slip force with the implicit-stick cap, spin update.  `i` = wheel index
+// [bl, br, fl, fr]; (sn, cs) = sin/cos of its steer angle (front wheels only).
 template <int TASK>
-__device__ __forceinline__ void physics_substep(const wl_config& c, const Terrain& T, EnvState& e, Chassis& b,
-                                                const float tau[4], const float steer_target[2], const StepConsts& k) {
-    const float h = k.h;
-    M3 R = rotmat(b.qw, b.qx, b.qy, b.qz);
-    float sn[2], cs[2];
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-        float vel = (c.steer_inertia * e.steer_vel[j] + h * c.steer_kp * (steer_target[j] - e.steer[j])) * k.sden;
-        vel = r_clamp(vel, -c.steer_vel_limit, c.steer_vel_limit);
-        float pos = r_clamp(e.steer[j] + h * vel, -c.steer_pos_limit, c.steer_pos_limit);
-        e.steer_vel[j] = vel; e.steer[j] = pos;
-        det_sincos(pos, sn[j], cs[j]);
-    }
-    V3 vb = rotT(R, b.v);
-    V3 Fb{0.0f, 0.0f, 0.0f}, Tb{0.0f, 0.0f, 0.0f};
-    const float rw = c.wheel_radius, bw = c.wheel_damping;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        V3 rho{((i >= 2) ? c.hub_x_front : c.hub_x_rear) - c.com[0], ((i & 1) ? -c.hub_y : c.hub_y) - c.com[1], c.hub_z - c.com[2]};
+__device__ __forceinline__ WheelOut wheel_force(const wl_config& c, const Terrain& T, const StepConsts& k, const M3& R,
+                                                const Chassis& b, V3 vb, int i, float sn, float cs, float omega, float tau,
+                                                float Dmu, float Cmu) {
+    const float rw = c.wheel_radius;
+    V3 rho{((i >= 2) ? c.hub_x_front : c.hub_x_rear) - c.com[0], ((i & 1) ? -c.hub_y : c.hub_y) - c.com[1], c.hub_z - c.com[2]};
+    float comp; V3 nb;
+    if (TASK == WL_TASK_ELEVATION) {
         V3 hubw = rot(R, rho);
         hubw.x += b.pc.x; hubw.y += b.pc.y; hubw.z += b.pc.z;
-        float zt; V3 nw; terrain_at<TASK>(c, T, hubw.x, hubw.y, zt, nw);
-        float comp = rw - (hubw.z - zt) * nw.z;
-        // drive torque first, then friction against the resulting slip (implicit stick)
-        float om_star = e.omega[i] + h * ((tau[i] - bw * e.omega[i]) * k.inv_Iw);
-        float Fx = 0.0f;
-        if (comp > 0.0f) {
-            V3 nb = rotT(R, nw);
-            V3 rc{rho.x - rw * nb.x, rho.y - rw * nb.y, rho.z - rw * nb.z};
-            V3 wxr = cross(b.wb, rc);
-            V3 vc{vb.x + wxr.x, vb.y + wxr.y, vb.z + wxr.z};
-            float sdot = -(nb.x * vc.x + nb.y * vc.y + nb.z * vc.z);
-            float Fz = c.susp_k * comp + c.susp_c * sdot;
-            if (comp > c.susp_travel) Fz += c.bump_k * (comp - c.susp_travel);
-            Fz = r_max(Fz, 0.0f);
-            V3 hb;
-            if (i >= 2) hb = V3{cs[i - 2], sn[i - 2], 0.0f}; else hb = V3{1.0f, 0.0f, 0.0f};
-            float d = hb.x * nb.x + hb.y * nb.y + hb.z * nb.z;
-            V3 ft{hb.x - d * nb.x, hb.y - d * nb.y, hb.z - d * nb.z};
-            float finv = 1.0f / sqrtf(ft.x * ft.x + ft.y * ft.y + ft.z * ft.z);
-            ft.x *= finv; ft.y *= finv; ft.z *= finv;
-            V3 lt = cross(nb, ft);
-            float vx = vc.x * ft.x + vc.y * ft.y + vc.z * ft.z;
-            float vy = vc.x * lt.x + vc.y * lt.y + vc.z * lt.z;
-            float vsx = vx - om_star * rw;
-            float invden = 1.0f / r_max(fabsf(vx), c.tire_v0);
-            float kappa = -vsx * invden, ta = -vy * invden;
-            float sigma = sqrtf(kappa * kappa + ta * ta);
-            float Fy = 0.0f;
-            if (sigma > 1.0e-9f) {
-                float sm, cm; det_sincos(e.C[i] * det_atan(c.tire_B * sigma), sm, cm);
-                float Fmag = Fz * (e.D[i] * sm) / sigma;
-                Fx = Fmag * kappa; Fy = Fmag * ta;
-                float fxm = c.tire_mx * fabsf(vsx) * k.inv_h, fym = c.tire_my * fabsf(vy) * k.inv_h;
-                Fx = r_clamp(Fx, -fxm, fxm); Fy = r_clamp(Fy, -fym, fym);
-            }
-            V3 F{Fz * nb.x + Fx * ft.x + Fy * lt.x, Fz * nb.y + Fx * ft.y + Fy * lt.y, Fz * nb.z + Fx * ft.z + Fy * lt.z};
-            V3 Tq = cross(rc, F);
-            Fb.x += F.x; Fb.y += F.y; Fb.z += F.z;
-            Tb.x += Tq.x; Tb.y += Tq.y; Tb.z += Tq.z;
-        }
-        e.omega[i] = om_star - h * ((rw * Fx) * k.inv_Iw);
+        float zt; V3 nw; heightfield_at(c, T, hubw.x, hubw.y, zt, nw);
+        comp = fm(-(hubw.z - zt), nw.z, rw);
+        nb = rotT(R, nw);
+    } else {                                     // plane z = 0, normal (0,0,1)
+        float hz = dot3(R.r[6], R.r[7], R.r[8], rho.x, rho.y, rho.z) + b.pc.z;
+        comp = rw - hz;
+        nb = V3{R.r[6], R.r[7], R.r[8]};
     }
+    WheelOut o;
+    float om_star = fm(k.h, (tau - c.wheel_damping * omega) * k.inv_Iw, omega);   // drive torque first
+    V3 rc = axpy(rho, -rw, nb);
+    V3 vc = cross(b.wb, rc);
+    vc.x += vb.x; vc.y += vb.y; vc.z += vb.z;
+    float sdot = -dot(nb, vc);
+    float Fz = fm(c.susp_k, comp, c.susp_c * sdot);
+    if (comp > c.susp_travel) Fz = fm(c.bump_k, comp - c.susp_travel, Fz);
+    Fz = (comp > 0.0f) ? r_max(Fz, 0.0f) : 0.0f;
+    V3 ft;
+    if (i >= 2) { float d = fm(cs, nb.x, sn * nb.y); ft = V3{fm(-d, nb.x, cs), fm(-d, nb.y, sn), -(d * nb.z)}; }
+    else { float d = nb.x; ft = V3{fm(-d, nb.x, 1.0f), -(d * nb.y), -(d * nb.z)}; }
+    float finv = 1.0f / sqrtf(dot(ft, ft));
+    ft.x *= finv; ft.y *= finv; ft.z *= finv;
+    V3 lt = cross(nb, ft);
+    float vx = dot(vc, ft), vy = dot(vc, lt);
+    float sx = fm(om_star, rw, -vx), sy = -vy;               // slip velocity of the tyre surface
+    float smag = sqrtf(fm(sx, sx, sy * sy));
+    float den = r_max(fabsf(vx), c.tire_v0);
+    float sm, cm; det_sincos(Cmu * det_atan_ratio(c.tire_B * smag, den), sm, cm);
+    float Fmag = Fz * (Dmu * sm);
+    float inv_s = 1.0f / r_max(smag, 1.0e-9f);
+    float Fx = (Fmag * sx) * inv_s, Fy = (Fmag * sy) * inv_s;
+    float fxm = k.fxk * fabsf(sx), fym = k.fyk * fabsf(sy);  // implicit-stick cap
+    Fx = r_clamp(Fx, -fxm, fxm); Fy = r_clamp(Fy, -fym, fym);
+    o.F = V3{fm(Fz, nb.x, fm(Fx, ft.x, Fy * lt.x)), fm(Fz, nb.y, fm(Fx, ft.y, Fy * lt.y)), fm(Fz, nb.z, fm(Fx, ft.z, Fy * lt.z))};
+    o.Tq = cross(rc, o.F);
+    o.omega = fm(-k.h, (rw * Fx) * k.inv_Iw, om_star);
+    return o;
+}
+
+// chassis: semi-implicit Euler; Euler's equations in the body frame (gyroscopic term on, mushr.py:28)
+__device__ __forceinline__ void chassis_integrate(const wl_config& c, const StepConsts& k, const M3& R, Chassis& b, V3 Fb, V3 Tb,
+                                                  float inv_mass) {
+    const float h = k.h;
     V3 Fw = rot(R, Fb);
-    b.v.x = b.v.x + h * (Fw.x * e.inv_mass);
-    b.v.y = b.v.y + h * (Fw.y * e.inv_mass);
-    b.v.z = b.v.z + h * (Fw.z * e.inv_mass - c.gravity);
+    b.v.x = fm(h, Fw.x * inv_mass, b.v.x);
+    b.v.y = fm(h, Fw.y * inv_mass, b.v.y);
+    b.v.z = fm(h, fm(Fw.z, inv_mass, -c.gravity), b.v.z);
     V3 Iw3{k.I[0] * b.wb.x, k.I[1] * b.wb.y, k.I[2] * b.wb.z};
     V3 g = cross(b.wb, Iw3);
-    b.wb.x = b.wb.x + h * ((Tb.x - g.x) * k.invI[0]);
-    b.wb.y = b.wb.y + h * ((Tb.y - g.y) * k.invI[1]);
-    b.wb.z = b.wb.z + h * ((Tb.z - g.z) * k.invI[2]);
-    b.pc.x = b.pc.x + h * b.v.x;
-    b.pc.y = b.pc.y + h * b.v.y;
-    b.pc.z = b.pc.z + h * b.v.z;
+    b.wb.x = fm(h, (Tb.x - g.x) * k.invI[0], b.wb.x);
+    b.wb.y = fm(h, (Tb.y - g.y) * k.invI[1], b.wb.y);
+    b.wb.z = fm(h, (Tb.z - g.z) * k.invI[2], b.wb.z);
+    b.pc = axpy(b.pc, h, b.v);
     float hh = 0.5f * h;
     float qw = b.qw, qx = b.qx, qy = b.qy, qz = b.qz, ox = b.wb.x, oy = b.wb.y, oz = b.wb.z;
-    float nqw = qw - hh * (qx * ox + qy * oy + qz * oz);
-    float nqx = qx + hh * (qw * ox + qy * oz - qz * oy);
-    float nqy = qy + hh * (qw * oy + qz * ox - qx * oz);
-    float nqz = qz + hh * (qw * oz + qx * oy - qy * ox);
-    float qinv = 1.0f / sqrtf(nqw * nqw + nqx * nqx + nqy * nqy + nqz * nqz);
+    float nqw = fm(-hh, dot3(qx, qy, qz, ox, oy, oz), qw);
+    float nqx = fm(hh, fm(qw, ox, fm(qy, oz, -(qz * oy))), qx);
+    float nqy = fm(hh, fm(qw, oy, fm(qz, ox, -(qx * oz))), qy);
+    float nqz = fm(hh, fm(qw, oz, fm(qx, oy, -(qy * ox))), qz);
+    float qinv = 1.0f / sqrtf(fm(nqw, nqw, fm(nqx, nqx, fm(nqy, nqy, nqz * nqz))));
     b.qw = nqw * qinv; b.qx = nqx * qinv; b.qy = nqy * qinv; b.qz = nqz * qinv;
+}
+
+// LANES == 1: one thread owns the env and loops over the 4 wheels.
+// LANES == 4: four adjacent lanes own one env; lane (l & 3) owns wheel l & 3, the chassis is integrated
+//             redundantly (bit-identically) in all four, forces are summed with two butterfly shuffles.
+// Both sum as (F0 + F1) + (F2 + F3), the order the oracle uses.
+template <int TASK, int LANES>
+__device__ __forceinline__ void physics_substep(const wl_config& c, const Terrain& T, EnvState& e, Chassis& b,
+                                                const float tau[4], const float steer_target[2], const StepConsts& k) {
+    M3 R = rotmat(b.qw, b.qx, b.qy, b.qz);
+    V3 vb = rotT(R, b.v);
+    V3 Fb, Tb;
+    if (LANES == 1) {
+        float sn[2], cs[2];
+        steer_step(c, k, steer_target[0], e.steer[0], e.steer_vel[0], sn[0], cs[0]);
+        steer_step(c, k, steer_target[1], e.steer[1], e.steer_vel[1], sn[1], cs[1]);
+        WheelOut w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            w[i] = wheel_force<TASK>(c, T, k, R, b, vb, i, (i >= 2) ? sn[i - 2] : 0.0f, (i >= 2) ? cs[i - 2] : 1.0f, e.omega[i],
+                                     tau[i], e.D[i], e.C[i]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) e.omega[i] = w[i].omega;
+        Fb = V3{(w[0].F.x + w[1].F.x) + (w[2].F.x + w[3].F.x), (w[0].F.y + w[1].F.y) + (w[2].F.y + w[3].F.y),
+                (w[0].F.z + w[1].F.z) + (w[2].F.z + w[3].F.z)};
+        Tb = V3{(w[0].Tq.x + w[1].Tq.x) + (w[2].Tq.x + w[3].Tq.x), (w[0].Tq.y + w[1].Tq.y) + (w[2].Tq.y + w[3].Tq.y),
+                (w[0].Tq.z + w[1].Tq.z) + (w[2].Tq.z + w[3].Tq.z)};
+    } else {
+        const int i = threadIdx.x & 3;
+        float sn = 0.0f, cs = 1.0f;
+        if (i >= 2) steer_step(c, k, steer_target[0], e.steer[0], e.steer_vel[0], sn, cs);   // lane-local copy of ITS joint
+        WheelOut w = wheel_force<TASK>(c, T, k, R, b, vb, i, sn, cs, e.omega[0], tau[0], e.D[0], e.C[0]);
+        e.omega[0] = w.omega;
+        float v6[6] = {w.F.x, w.F.y, w.F.z, w.Tq.x, w.Tq.y, w.Tq.z};
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+            v6[q] += __shfl_xor_sync(0xffffffffu, v6[q], 1);
+            v6[q] += __shfl_xor_sync(0xffffffffu, v6[q], 2);
+        }
+        Fb = V3{v6[0], v6[1], v6[2]}; Tb = V3{v6[3], v6[4], v6[5]};
+    }
+    chassis_integrate(c, k, R, b, Fb, Tb, e.inv_mass);
 }
 
 // ---- drift terminations / rewards -----------------------------------------------------
@@ -244,9 +329,11 @@ __device__ __forceinline__ bool drift_off_track(const wl_config& c, float x, flo
     return off || in;
 }
 
-__device__ __forceinline__ void drift_reward_terms(const wl_config& c, const EnvState& e, V3 p, V3 vb, V3 wb, float wz_world,
-                                                   bool out_of_bounds, bool time_out, float f[WL_MAX_REW_TERMS]) {
-    float slip = fabsf(det_atan2(vb.y, vb.x));
+// `slip_atan` = det_atan2(vb.y, vb.x) (computed by the caller so that the quad kernel can batch its atan2 calls)
+__device__ __forceinline__ void drift_reward_terms(const wl_config& c, float steer_l, float steer_r, float slip_atan, V3 p, V3 vb,
+                                                   V3 wb, float wz_world, bool out_of_bounds, bool time_out,
+                                                   float f[WL_MAX_REW_TERMS]) {
+    float slip = fabsf(slip_atan);
     float valid = (fabsf(vb.x) < c.slip_min_vel_x || slip > c.slip_max_thresh) ? 0.0f : slip;
     if (valid < c.slip_min_thresh) valid = 0.0f;
     f[WL_DR_SIDE_SLIP] = valid;
@@ -254,7 +341,7 @@ __device__ __forceinline__ void drift_reward_terms(const wl_config& c, const Env
     float dv = gs - c.vel_speed_target;
     f[WL_DR_VEL] = dv * dv + c.vel_offset;
     f[WL_DR_PROGRESS] = wz_world;
-    float sm = (e.steer[0] + e.steer[1]) / 2.0f;
+    float sm = (steer_l + steer_r) / 2.0f;
     float av = r_clamp(wb.z, -c.tlgr_ang_vel_thresh, c.tlgr_ang_vel_thresh);
     float tl = sm * av * -1.0f;
     f[WL_DR_TLGR] = r_max(tl, 0.0f);
@@ -335,6 +422,35 @@ __device__ __forceinline__ void blind_obs(const wl_config& c, const EnvState& e,
     float2* o2 = reinterpret_cast<float2*>(obs);
 #pragma unroll
     for (int k = 0; k < 7; ++k) o2[k] = make_float2(o[2 * k], o[2 * k + 1]);
+}
+
+// quad version: lane k in {0,1,2} draws Philox block k (4 normals) and writes obs[4k..4k+3]; lane 3 writes the
+// last action.  `eu_k` = this lane's euler angle (lane0 roll, lane1 pitch, lane2 yaw), already wrapped.
+__device__ __forceinline__ void blind_obs_quad(const wl_config& c, const EnvState& e, int w, float eu_k, uint32_t gid, uint32_t t,
+                                               uint32_t stream, uint32_t sub0, float* __restrict__ obs, bool live) {
+    M3 R = rotmat(e.qw, e.qx, e.qy, e.qz);
+    V3 vb = rotT(R, e.v), wb = rotT(R, e.w);
+    float z0 = 0.0f, z1 = 0.0f, z2 = 0.0f, z3 = 0.0f;
+    if (c.enable_corruption) {
+        uint4 r = philox4x32(c.seed, gid, t, stream, sub0 + (uint32_t)(w < 3 ? w : 0));
+        box_muller(r.x, r.y, z0, z1);
+        box_muller(r.z, r.w, z2, z3);
+    }
+    const unsigned base = (threadIdx.x & 31u) & ~3u;
+    float eu1 = __shfl_sync(0xffffffffu, eu_k, base + 1), eu2 = __shfl_sync(0xffffffffu, eu_k, base + 2);
+    float b0, b1, b2, b3, s0, s1, s2, s3;
+    if (w == 0) { b0 = e.p.x; b1 = e.p.y; b2 = e.p.z; b3 = eu_k; s0 = s1 = s2 = c.noise_std[0]; s3 = c.noise_std[1]; }
+    else if (w == 1) { b0 = eu1; b1 = eu2; b2 = vb.x; b3 = vb.y; s0 = s1 = c.noise_std[1]; s2 = s3 = c.noise_std[2]; }
+    else if (w == 2) { b0 = vb.z; b1 = wb.x; b2 = wb.y; b3 = wb.z; s0 = c.noise_std[2]; s1 = s2 = s3 = c.noise_std[3]; }
+    else { b0 = r_clamp(e.action[0], -1.0f, 1.0f); b1 = r_clamp(e.action[1], -1.0f, 1.0f); b2 = b3 = 0.0f; s0 = s1 = s2 = s3 = 0.0f; z0 = z1 = 0.0f; }
+    float2* o2 = reinterpret_cast<float2*>(obs + 4 * w);
+    if (!live) return;
+    if (w < 3) {
+        o2[0] = make_float2(b0 + s0 * z0, b1 + s1 * z1);
+        o2[1] = make_float2(b2 + s2 * z2, b3 + s3 * z3);
+    } else {
+        o2[0] = make_float2(b0, b1);
+    }
 }
 
 }  // namespace wl

@@ -116,6 +116,10 @@ class WheeledSim:
               "wl_synth_actions")
         return act
 
+    def set_kernel_variant(self, lanes_per_env: int):
+        """0 auto, 1 thread-per-env, 4 quad-per-env (bit-identical results)."""
+        check(lib.wl_set_kernel_variant(self._h, lanes_per_env), "wl_set_kernel_variant")
+
     @property
     def launch_count(self) -> int:
         return int(lib.wl_launch_count(self._h))
