@@ -101,6 +101,7 @@ extern "C" {
     XS(int32_t, i32, decimation)                                                                   \
     XS(int32_t, i32, substeps)        /* integrator sub-steps per sim step (TGS-like) */           \
     XS(int32_t, i32, max_episode_length)                                                           \
+    XS(float, f32, episode_length_s)  /* max_episode_length_s, divides the episode log (Appendix B) */ \
     XS(float, f32, gravity)                                                                        \
     /* --- action term (wheeledlab_tasks/common/actions.py) --- */                                 \
     XS(int32_t, i32, action_kind)                                                                  \
@@ -208,7 +209,21 @@ extern "C" {
     XS(float, f32, elev_rollover_cos) /* cos(60 deg), :217-222 */                                  \
     XS(float, f32, elev_goal_dist)                                                                 \
     XS(float, f32, elev_fall_vel)                                                                  \
-    XS(float, f32, elev_plane_z)      /* 0.19 in higher_elevation, :166-173 */
+    XS(float, f32, elev_plane_z)      /* 0.19 in higher_elevation, :166-173 */                     \
+    /* --- derived constants: filled by wl_config_finalize() (wl_create calls it on its copy); fp32,   \
+     *     formed once on the host so the kernels carry no per-step divisions for them --- */        \
+    XS(float, f32, d_h)               /* sim_dt / substeps */                                      \
+    XS(float, f32, d_inv_h)                                                                        \
+    XS(float, f32, d_step_dt)         /* sim_dt * decimation */                                    \
+    XS(float, f32, d_hkp)             /* h * steer_kp */                                           \
+    XS(float, f32, d_sden)            /* 1 / (J + h kd + h^2 kp) */                                \
+    XS(float, f32, d_inv_Iw)                                                                       \
+    XS(float, f32, d_fxk)             /* tire_mx / h */                                            \
+    XS(float, f32, d_fyk)                                                                          \
+    XS(float, f32, d_inv_wheel_radius_cfg)                                                         \
+    XS(float, f32, d_inv_dc_vel_limit)                                                             \
+    XS(float, f32, d_inv_mass_nominal)                                                             \
+    XA(float, f32, d_invI_nominal, 3)
 
 typedef struct wl_config {
 #define WL_XS(type, tag, name) type name;
@@ -242,12 +257,14 @@ typedef struct wl_config {
 
 /* small global (not per-env) device block appended after the groups */
 typedef struct wl_globals {
-    float rew_weight[WL_MAX_REW_TERMS];   /* live reward weights (curriculum mutates)       */
-    float log_sum[2][WL_MAX_REW_TERMS];   /* per-step sum over reset envs of episode sums   */
-    float log_term[2][4];                 /* per-step reset counts: [all, terminated, timeout, spare] */
-    int32_t any_reset[2];                 /* set by step kernel when >=1 env reset          */
+    float rew_weight[WL_MAX_REW_TERMS];   /* live reward weights (curriculum mutates)                      */
+    float acc[12];                        /* this step: [0..7] sum over reset envs of their episode sums,   */
+                                          /* [8] #reset, [9] #terminated, [10] #timed-out                    */
+    uint32_t ticket;                      /* CTAs finished in the current launch (last one finalises)       */
+    int32_t any_reset_last;               /* 1 if the previous step reset >= 1 env (read by wl_curriculum)  */
     int32_t _pad[2];
 } wl_globals;
+#define WL_LOG_FLOATS 16                  /* d_log layout: [0..7] Episode_Reward means, [8..10] counts      */
 
 typedef struct wl_sim wl_sim;   /* opaque handle (host memory) */
 
@@ -255,6 +272,8 @@ typedef struct wl_sim wl_sim;   /* opaque handle (host memory) */
 /* "name:tag:count:offset;..." for every wl_config field, plus "sizeof:<n>". */
 const char* wl_config_describe(void);
 size_t wl_config_sizeof(void);
+/* fill the d_* derived fields from the primary ones (idempotent). */
+int wl_config_finalize(wl_config* cfg);
 
 /* ---- lifetime -------------------------------------------------------------- */
 size_t wl_state_bytes(int32_t num_envs);     /* groups + globals, 256-byte padded */
@@ -278,16 +297,19 @@ int wl_reset(wl_sim* sim, const int64_t* d_env_ids, int32_t n_ids, int64_t step_
 /* one env.step(): action[N,2] f32 -> obs[N,obs_dim] f32, rew[N] f32, terminated[N] u8,
  * truncated[N] u8.  `step_counter` = common_step_counter BEFORE this step.  Auto-resets
  * finished envs (reward belongs to the pre-reset state, obs to the post-reset state). */
+/* d_log: optional float[WL_LOG_FLOATS]: mean over the envs reset in this step of each reward term's episode sum
+ * divided by max_episode_length_s (RewardManager.reset -> extras["log"]), then the reset / terminated / time-out
+ * counts.  Written by the last CTA of the launch: no extra kernel, no host sync. */
 int wl_step(wl_sim* sim, const float* d_action, float* d_obs, float* d_rew, uint8_t* d_terminated,
-            uint8_t* d_truncated, int64_t step_counter, void* stream);
+            uint8_t* d_truncated, float* d_log, int64_t step_counter, void* stream);
 /* observation_manager.compute(): re-samples the noise. call_idx distinguishes
  * repeated calls at the same step_counter. */
 int wl_observe(wl_sim* sim, float* d_obs, int64_t step_counter, int32_t call_idx, void* stream);
 /* curriculum (curriculums.py:10-35) evaluated on device so that no host sync is needed:
  * for each term t in [0,n): if any env reset during the last step, rew_weight[slot[t]] += inc[t]
  * when the host-evaluated counter conditions in fire_mask bit t hold. */
-int wl_curriculum(wl_sim* sim, int64_t step_counter, int32_t n_terms, const int32_t* slots,
-                  const float* increases, uint32_t fire_mask, void* stream);
+int wl_curriculum(wl_sim* sim, int32_t n_terms, const int32_t* slots, const float* increases, uint32_t fire_mask,
+                  void* stream);
 /* synthetic actions: U[-1,1]^2 (dist=0) or clip(N(0,1),-1,1) (dist=1) keyed by
  * (seed, global env id, step_counter); writes d_action[N,2]. */
 int wl_synth_actions(wl_sim* sim, float* d_action, int64_t step_counter, int32_t dist, void* stream);

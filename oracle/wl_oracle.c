@@ -96,6 +96,7 @@ static inline real uniform(uint32_t x, real lo, real hi) { return fm(hi - lo, u0
 static void det_sincos(real x, real* s, real* c) { *s = sin(x); *c = cos(x); }
 static real det_atan(real x) { return atan(x); }
 static real det_atan_ratio(real num, real den) { return atan(num / den); }
+static real det_sin_0_pi(real x) { return sin(x); }
 static real det_atan2(real y, real x) { return atan2(y, x); }
 static real det_log(real x) { return log(x); }
 #else
@@ -116,6 +117,13 @@ static void det_sincos(float x, float* s, float* c) {
         case 2: *s = -sp; *c = -cp; break;
         default: *s = -cp; *c = sp; break;
     }
+}
+/* sin(x), x in [0, pi]: fold to [0, pi/2], degree-9 odd polynomial (|err| <= 1.5e-7) */
+static float det_sin_0_pi(float x) {
+    float xr = (x > 1.57079632679489661923f) ? (3.14159265358979323846f - x) : x;
+    float z = xr * xr;
+    float q = fm(fm(fm(2.590488293208182e-06f, z, -1.9800897280219942e-04f), z, 8.332899771630764e-03f), z, -1.6666647791862488e-01f);
+    return fm(xr * z, q, xr);
 }
 /* atan(num/den), num >= 0, den > 0, with one division (cephes ranges applied to the ratio) */
 static float det_atan_ratio(float num, float den) {
@@ -192,9 +200,9 @@ typedef struct wlo_sim {
     wl_config cfg;
     wlo_env* env;
     real rew_weight[WL_MAX_REW_TERMS];
-    double log_sum[2][WL_MAX_REW_TERMS];
-    double log_term[2][4];
-    int32_t any_reset[2];
+    double log_sum[WL_MAX_REW_TERMS];     /* last step: sum over reset envs of episode sums */
+    double log_term[4];                   /* last step: #reset, #terminated, #timed-out */
+    int32_t any_reset_last;
     float* hf;
 } wlo_sim;
 
@@ -278,7 +286,7 @@ static int process_action(const wl_config* c, const float a_in[2], real wheel_ta
     real tan_d = det_tan(delta);
     real L = (real)c->base_length, W = (real)c->base_width, r = (real)c->wheel_radius_cfg;
     if (c->action_kind == WL_ACT_RWD) {
-        real wt = v / r;
+        real wt = v * (real)c->d_inv_wheel_radius_cfg;
         wheel_target[WL_BL] = wt; wheel_target[WL_BR] = wt; wheel_target[WL_FL] = K(0.0); wheel_target[WL_FR] = K(0.0);
         steer_target[0] = tan_d; steer_target[1] = tan_d;      /* quirk Q1: tan(delta) is the position target */
         return 0;
@@ -287,11 +295,11 @@ static int process_action(const wl_config* c, const float a_in[2], real wheel_ta
     real hw = W / K(2.0);
     real Rl = Rt - hw, Rr = Rt + hw;
     real Rrl = r_sqrt(Rl * Rl + L * L), Rrr = r_sqrt(Rr * Rr + L * L);
-    real den = Rt * r;
-    wheel_target[WL_FL] = v * r_fabs(Rrl / den);
-    wheel_target[WL_FR] = v * r_fabs(Rrr / den);
-    wheel_target[WL_BL] = v * r_fabs(Rl / den);
-    wheel_target[WL_BR] = v * r_fabs(Rr / den);
+    real rden = K(1.0) / (Rt * r);
+    wheel_target[WL_FL] = v * r_fabs(Rrl * rden);
+    wheel_target[WL_FR] = v * r_fabs(Rrr * rden);
+    wheel_target[WL_BL] = v * r_fabs(Rl * rden);
+    wheel_target[WL_BR] = v * r_fabs(Rr * rden);
     if (c->action_kind == WL_ACT_4WD) { steer_target[0] = tan_d; steer_target[1] = tan_d; }
     else { steer_target[0] = det_atan(L / Rl); steer_target[1] = det_atan(L / Rr); }
     return 0;
@@ -303,8 +311,8 @@ static int process_action(const wl_config* c, const float a_in[2], real wheel_ta
 static real dc_motor(const wl_config* c, real kd, real effort_limit, real target, real omega) {
     if (!(effort_limit > K(0.0))) return K(0.0);        /* passive joint, hound.py:44-51 */
     real tau = kd * (target - omega);                    /* stiffness = 0 */
-    real sat = (real)c->dc_saturation, vl = (real)c->dc_vel_limit;
-    real ratio = omega / vl;
+    real sat = (real)c->dc_saturation;
+    real ratio = omega * (real)c->d_inv_dc_vel_limit;
     real max_eff = r_clamp(sat * (K(1.0) - ratio), K(0.0), effort_limit);
     real min_eff = r_clamp(sat * (K(-1.0) - ratio), -effort_limit, K(0.0));
     return r_clamp(tau, min_eff, max_eff);
@@ -315,30 +323,40 @@ static real dc_motor(const wl_config* c, real kd, real effort_limit, real target
 /* body-frame quantities: vb, wb; pc = COM position (world)                     */
 /* ------------------------------------------------------------------------- */
 typedef struct { real pc[3]; real q[4]; real v[3]; real wb[3]; } chassis_t;
-/* per-env-step invariants (reciprocals are formed ONCE per env step, in this order) */
-typedef struct { real h, inv_h, sden, inv_Iw, hkp, fxk, fyk, I[3], invI[3]; } step_consts;
+/* mass-dependent per-env invariants; everything else comes from the d_* derived config fields */
+typedef struct { real I[3], invI[3]; } step_consts;
 
 static void make_step_consts(const wl_config* c, const wlo_env* e, step_consts* k) {
-    k->h = (real)c->sim_dt / (real)c->substeps;
-    k->inv_h = K(1.0) / k->h;
-    k->hkp = k->h * (real)c->steer_kp;
-    k->sden = K(1.0) / fm(k->h, k->hkp, fm(k->h, (real)c->steer_kd, (real)c->steer_inertia));
-    k->inv_Iw = K(1.0) / (real)c->wheel_inertia;
-    k->fxk = (real)c->tire_mx * k->inv_h;
-    k->fyk = (real)c->tire_my * k->inv_h;
-    real ms = e->mass / (real)c->mass_nominal;          /* inertia scales with the mass ratio (a14) */
-    for (int a = 0; a < 3; ++a) { k->I[a] = (real)c->inertia_nominal[a] * ms; k->invI[a] = K(1.0) / k->I[a]; }
+    real ms = e->mass * (real)c->d_inv_mass_nominal;     /* inertia scales with the mass ratio (a14) */
+    real ms_inv = (real)c->mass_nominal * e->inv_mass;
+    for (int a = 0; a < 3; ++a) { k->I[a] = (real)c->inertia_nominal[a] * ms; k->invI[a] = (real)c->d_invI_nominal[a] * ms_inv; }
+}
+
+/* derived constants: same fp32 operations, same order, as wl_config_finalize() in the product library */
+static void config_finalize(wl_config* c) {
+    c->d_h = c->sim_dt / (float)c->substeps;
+    c->d_inv_h = 1.0f / c->d_h;
+    c->d_step_dt = c->sim_dt * (float)c->decimation;
+    c->d_hkp = c->d_h * c->steer_kp;
+    c->d_sden = 1.0f / fmaf(c->d_h, c->d_hkp, fmaf(c->d_h, c->steer_kd, c->steer_inertia));
+    c->d_inv_Iw = 1.0f / c->wheel_inertia;
+    c->d_fxk = c->tire_mx * c->d_inv_h;
+    c->d_fyk = c->tire_my * c->d_inv_h;
+    c->d_inv_wheel_radius_cfg = 1.0f / c->wheel_radius_cfg;
+    c->d_inv_dc_vel_limit = 1.0f / c->dc_vel_limit;
+    c->d_inv_mass_nominal = 1.0f / c->mass_nominal;
+    for (int a = 0; a < 3; ++a) c->d_invI_nominal[a] = 1.0f / c->inertia_nominal[a];
 }
 
 static void physics_substep(const wlo_sim* s, wlo_env* e, chassis_t* b, const real tau[4], const real steer_target[2],
                             const step_consts* k) {
     const wl_config* c = &s->cfg;
-    real h = k->h;
+    real h = (real)c->d_h;
     real R[9]; rotmat(b->q, R);
     /* steering: implicit PD on the steer joint (hound.py:5-12) */
     real sn[2], cs[2];
     for (int j = 0; j < 2; ++j) {
-        real vel = fm(k->hkp, steer_target[j] - e->steer[j], (real)c->steer_inertia * e->steer_vel[j]) * k->sden;
+        real vel = fm((real)c->d_hkp, steer_target[j] - e->steer[j], (real)c->steer_inertia * e->steer_vel[j]) * (real)c->d_sden;
         vel = r_clamp(vel, -(real)c->steer_vel_limit, (real)c->steer_vel_limit);
         real pos = r_clamp(fm(h, vel, e->steer[j]), -(real)c->steer_pos_limit, (real)c->steer_pos_limit);
         e->steer_vel[j] = vel; e->steer[j] = pos;
@@ -365,7 +383,7 @@ static void physics_substep(const wlo_sim* s, wlo_env* e, chassis_t* b, const re
             nb[0] = R[6]; nb[1] = R[7]; nb[2] = R[8];
         }
         /* drive torque first, then friction against the resulting slip (implicit stick) */
-        real om_star = fm(h, (tau[i] - bw * e->omega[i]) * k->inv_Iw, e->omega[i]);
+        real om_star = fm(h, (tau[i] - bw * e->omega[i]) * (real)c->d_inv_Iw, e->omega[i]);
         real rc[3] = {fm(-rw, nb[0], rho[0]), fm(-rw, nb[1], rho[1]), fm(-rw, nb[2], rho[2])};
         real vc[3]; cross(b->wb, rc, vc);
         vc[0] += vb[0]; vc[1] += vb[1]; vc[2] += vb[2];
@@ -381,22 +399,24 @@ static void physics_substep(const wlo_sim* s, wlo_env* e, chassis_t* b, const re
             real d = nb[0];
             ft[0] = fm(-d, nb[0], K(1.0)); ft[1] = -(d * nb[1]); ft[2] = -(d * nb[2]);
         }
-        real finv = K(1.0) / r_sqrt(vdot(ft, ft));
+        /* |ft|^2 = 1 - d^2: binomial series of (1 - e)^(-1/2), e = 1 - |ft|^2 */
+        real en = K(1.0) - vdot(ft, ft);
+        real finv = fm(fm(fm(fm(K(0.2734375), en, K(0.3125)), en, K(0.375)), en, K(0.5)), en, K(1.0));
         ft[0] *= finv; ft[1] *= finv; ft[2] *= finv;
         real lt[3]; cross(nb, ft, lt);
         real vx = vdot(vc, ft), vy = vdot(vc, lt);
         real sx = fm(om_star, rw, -vx), sy = -vy;     /* slip velocity of the tyre surface */
         real smag = r_sqrt(fm(sx, sx, sy * sy));
         real den = r_max(r_fabs(vx), (real)c->tire_v0);
-        real sm, cm; det_sincos(e->C[i] * det_atan_ratio((real)c->tire_B * smag, den), &sm, &cm);
+        real sm = det_sin_0_pi(e->C[i] * det_atan_ratio((real)c->tire_B * smag, den));
         real Fmag = Fz * (e->D[i] * sm);
         real inv_s = K(1.0) / r_max(smag, K(1.0e-9));
         real Fx = (Fmag * sx) * inv_s, Fy = (Fmag * sy) * inv_s;
-        real fxm = k->fxk * r_fabs(sx), fym = k->fyk * r_fabs(sy);
+        real fxm = (real)c->d_fxk * r_fabs(sx), fym = (real)c->d_fyk * r_fabs(sy);
         Fx = r_clamp(Fx, -fxm, fxm); Fy = r_clamp(Fy, -fym, fym);
         for (int a = 0; a < 3; ++a) F[i][a] = fm(Fz, nb[a], fm(Fx, ft[a], Fy * lt[a]));
         cross(rc, F[i], T[i]);
-        e->omega[i] = fm(-h, (rw * Fx) * k->inv_Iw, om_star);
+        e->omega[i] = fm(-h, (rw * Fx) * (real)c->d_inv_Iw, om_star);
     }
     real Fb[3], Tb[3];
     for (int a = 0; a < 3; ++a) { Fb[a] = (F[0][a] + F[1][a]) + (F[2][a] + F[3][a]); Tb[a] = (T[0][a] + T[1][a]) + (T[2][a] + T[3][a]); }
@@ -420,7 +440,9 @@ static void physics_substep(const wlo_sim* s, wlo_env* e, chassis_t* b, const re
     real nqx = fm(hh, fm(qw, ox, fm(qy, oz, -(qz * oy))), qx);
     real nqy = fm(hh, fm(qw, oy, fm(qz, ox, -(qx * oz))), qy);
     real nqz = fm(hh, fm(qw, oz, fm(qx, oy, -(qy * ox))), qz);
-    real qinv = K(1.0) / r_sqrt(fm(nqw, nqw, fm(nqx, nqx, fm(nqy, nqy, nqz * nqz))));
+    /* renormalise with the series of (1 + e)^(-1/2), e = |q|^2 - 1 */
+    real eq = fm(nqw, nqw, fm(nqx, nqx, fm(nqy, nqy, nqz * nqz))) - K(1.0);
+    real qinv = fm(fm(fm(K(-0.3125), eq, K(0.375)), eq, K(-0.5)), eq, K(1.0));
     b->q[0] = nqw * qinv; b->q[1] = nqx * qinv; b->q[2] = nqy * qinv; b->q[3] = nqz * qinv;
 }
 
@@ -612,7 +634,7 @@ static int env_step(wlo_sim* s, int li, const float* a_in, int64_t t, float* obs
     /* D. terminations (time_out first in cfg order, :351-362) */
     int time_out = e->ep_len >= c->max_episode_length;
     int terminated = 0;
-    real step_dt = (real)c->sim_dt * (real)c->decimation;
+    real step_dt = (real)c->d_step_dt;
     real f[WL_MAX_REW_TERMS];
     real vb[3]; rotT(R, e->v, vb);
     if (c->task == WL_TASK_DRIFT) {
@@ -650,6 +672,7 @@ static int env_step(wlo_sim* s, int li, const float* a_in, int64_t t, float* obs
 wlo_sim* wlo_create(const wl_config* cfg, const float* heightfield) {
     wlo_sim* s = (wlo_sim*)calloc(1, sizeof(wlo_sim));
     s->cfg = *cfg;
+    config_finalize(&s->cfg);
     s->env = (wlo_env*)calloc((size_t)cfg->num_envs, sizeof(wlo_env));
     for (int k = 0; k < WL_MAX_REW_TERMS; ++k) s->rew_weight[k] = (real)cfg->rew_weight[k];
     if (heightfield && cfg->hf_nx > 0) {
@@ -711,7 +734,6 @@ int wlo_step(wlo_sim* s, const float* action, float* obs, float* rew, uint8_t* t
              int64_t step_counter, int nthreads) {
     const wl_config* c = &s->cfg;
     int od = (c->task == WL_TASK_ELEVATION) ? WL_OBS_DIM_ELEV : WL_OBS_DIM_BLIND;
-    int slot = (int)(step_counter & 1);
     step_log tot; memset(&tot, 0, sizeof tot);
     int err = 0;
     (void)nthreads;
@@ -736,9 +758,9 @@ int wlo_step(wlo_sim* s, const float* action, float* obs, float* rew, uint8_t* t
             tot.n_reset += lg.n_reset; tot.n_term += lg.n_term; tot.n_timeout += lg.n_timeout; tot.any |= lg.any;
         }
     }
-    for (int k = 0; k < WL_MAX_REW_TERMS; ++k) s->log_sum[slot][k] = tot.sum[k];
-    s->log_term[slot][0] = tot.n_reset; s->log_term[slot][1] = tot.n_term; s->log_term[slot][2] = tot.n_timeout;
-    s->any_reset[slot] = tot.any;
+    for (int k = 0; k < WL_MAX_REW_TERMS; ++k) s->log_sum[k] = tot.sum[k];
+    s->log_term[0] = tot.n_reset; s->log_term[1] = tot.n_term; s->log_term[2] = tot.n_timeout;
+    s->any_reset_last = tot.any;
     return err;
 }
 
@@ -754,10 +776,8 @@ int wlo_observe(wlo_sim* s, float* obs, int64_t step_counter, int32_t call_idx) 
 /* curriculum, wheeledlab/envs/mdp/curriculums.py:10-35 -- the counter conditions are
  * evaluated by the caller (fire_mask); the "called only when >=1 env reset" condition
  *  is applied here from the last step's any_reset flag. */
-int wlo_curriculum(wlo_sim* s, int64_t step_counter, int32_t n_terms, const int32_t* slots, const float* increases,
-                   uint32_t fire_mask) {
-    int slot = (int)((step_counter - 1) & 1);
-    if (!s->any_reset[slot]) return 0;
+int wlo_curriculum(wlo_sim* s, int32_t n_terms, const int32_t* slots, const float* increases, uint32_t fire_mask) {
+    if (!s->any_reset_last) return 0;
     for (int t = 0; t < n_terms; ++t)
         if ((fire_mask >> t) & 1u) s->rew_weight[slots[t]] += (real)increases[t];
     return 0;
@@ -824,11 +844,12 @@ void wlo_import_state(wlo_sim* s, const float* cbuf) {
 }
 void wlo_get_weights(const wlo_sim* s, float* w) { for (int k = 0; k < WL_MAX_REW_TERMS; ++k) w[k] = (float)s->rew_weight[k]; }
 void wlo_set_weights(wlo_sim* s, const float* w) { for (int k = 0; k < WL_MAX_REW_TERMS; ++k) s->rew_weight[k] = (real)w[k]; }
-/* log: [0..7] sum of episode sums over reset envs, [8] n_reset, [9] n_terminated, [10] n_timeout */
-void wlo_get_log(const wlo_sim* s, int64_t step_counter, double* out) {
-    int slot = (int)(step_counter & 1);
-    for (int k = 0; k < WL_MAX_REW_TERMS; ++k) out[k] = s->log_sum[slot][k];
-    out[8] = s->log_term[slot][0]; out[9] = s->log_term[slot][1]; out[10] = s->log_term[slot][2];
+/* the d_log row of the last step (RewardManager.reset, Appendix B): [0..7] mean episode sum over the reset envs /
+ * max_episode_length_s, [8] n_reset, [9] n_terminated, [10] n_timeout */
+void wlo_get_log(const wlo_sim* s, double* out) {
+    double cnt = s->log_term[0] > 1.0 ? s->log_term[0] : 1.0;
+    for (int k = 0; k < WL_MAX_REW_TERMS; ++k) out[k] = s->log_sum[k] / (cnt * (double)s->cfg.episode_length_s);
+    out[8] = s->log_term[0]; out[9] = s->log_term[1]; out[10] = s->log_term[2];
 }
 
 /* ---- unit-level hooks for golden-vector and det-math tests -------------------- */
@@ -853,7 +874,8 @@ int wlo_philox(uint64_t seed, uint32_t c0_base, uint32_t c1, uint32_t c2, uint32
     return 0;
 }
 /* action map only: out wheel targets [n,4] (bl,br,fl,fr) and steer targets [n,2] */
-int wlo_action_map(const wl_config* c, const float* action, float* wheel, float* steer, int32_t n) {
+int wlo_action_map(const wl_config* c_in, const float* action, float* wheel, float* steer, int32_t n) {
+    wl_config cc = *c_in; config_finalize(&cc); const wl_config* c = &cc;
     for (int i = 0; i < n; ++i) {
         real wt[4], st[2];
         int rc = process_action(c, action + 2 * i, wt, st);

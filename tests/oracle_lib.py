@@ -26,13 +26,13 @@ def _load(name):
     lib.wlo_reset.argtypes = [vp, vp, i32, i64]
     lib.wlo_step.argtypes = [vp, vp, vp, vp, vp, vp, i64, i32]
     lib.wlo_observe.argtypes = [vp, vp, i64, i32]
-    lib.wlo_curriculum.argtypes = [vp, i64, i32, vp, vp, u32]
+    lib.wlo_curriculum.argtypes = [vp, i32, vp, vp, u32]
     lib.wlo_synth_actions.argtypes = [vp, vp, i64, i32]
     lib.wlo_export_state.argtypes = [vp, vp]
     lib.wlo_import_state.argtypes = [vp, vp]
     lib.wlo_get_weights.argtypes = [vp, vp]
     lib.wlo_set_weights.argtypes = [vp, vp]
-    lib.wlo_get_log.argtypes = [vp, i64, vp]
+    lib.wlo_get_log.argtypes = [vp, vp]
     lib.wlo_detmath.argtypes = [i32, vp, vp, vp, i32]
     lib.wlo_philox.argtypes = [u64, u32, u32, u32, u32, vp, i32]
     lib.wlo_action_map.argtypes = [vp, vp, vp, vp, i32]
@@ -104,10 +104,10 @@ class Oracle:
         assert self.lib.wlo_observe(self._h, _p(obs), step_counter, call_idx) == 0
         return obs
 
-    def curriculum(self, step_counter, slots, increases, fire_mask):
+    def curriculum(self, slots, increases, fire_mask):
         s = np.asarray(slots, np.int32)
         i = np.asarray(increases, np.float32)
-        assert self.lib.wlo_curriculum(self._h, step_counter, len(s), _p(s), _p(i), fire_mask) == 0
+        assert self.lib.wlo_curriculum(self._h, len(s), _p(s), _p(i), fire_mask) == 0
 
     def synth_actions(self, step_counter, dist=0):
         a = np.empty((self.n, 2), np.float32)
@@ -132,9 +132,9 @@ class Oracle:
         w = np.ascontiguousarray(w, np.float32)
         self.lib.wlo_set_weights(self._h, _p(w))
 
-    def log(self, step_counter):
+    def log(self):
         out = np.zeros(11, np.float64)
-        self.lib.wlo_get_log(self._h, step_counter, _p(out))
+        self.lib.wlo_get_log(self._h, _p(out))
         return out
 
 

@@ -67,14 +67,15 @@ WlConfig = make_config_struct(CONFIG_DESCRIBE)
 class WlGlobals(C.Structure):
     _fields_ = [
         ("rew_weight", C.c_float * 8),
-        ("log_sum", (C.c_float * 8) * 2),
-        ("log_term", (C.c_float * 4) * 2),
-        ("any_reset", C.c_int32 * 2),
+        ("acc", C.c_float * 12),
+        ("ticket", C.c_uint32),
+        ("any_reset_last", C.c_int32),
         ("_pad", C.c_int32 * 2),
     ]
 
 
 _vp, _i32, _i64, _u32, _u64, _sz = C.c_void_p, C.c_int32, C.c_int64, C.c_uint32, C.c_uint64, C.c_size_t
+lib.wl_config_finalize.argtypes = [C.POINTER(WlConfig)]
 lib.wl_state_bytes.restype = _sz
 lib.wl_state_bytes.argtypes = [_i32]
 lib.wl_globals_offset.restype = _sz
@@ -83,9 +84,9 @@ lib.wl_create.argtypes = [C.POINTER(WlConfig), _vp, _sz, _vp, C.POINTER(_vp)]
 lib.wl_destroy.argtypes = [_vp]
 lib.wl_startup.argtypes = [_vp, _vp]
 lib.wl_reset.argtypes = [_vp, _vp, _i32, _i64, _vp]
-lib.wl_step.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]
+lib.wl_step.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]
 lib.wl_observe.argtypes = [_vp, _vp, _i64, _i32, _vp]
-lib.wl_curriculum.argtypes = [_vp, _i64, _i32, C.POINTER(_i32), C.POINTER(C.c_float), _u32, _vp]
+lib.wl_curriculum.argtypes = [_vp, _i32, C.POINTER(_i32), C.POINTER(C.c_float), _u32, _vp]
 lib.wl_synth_actions.argtypes = [_vp, _vp, _i64, _i32, _vp]
 lib.wl_derive_suspension.argtypes = [_vp, _vp, _vp, _vp]
 lib.wl_set_kernel_variant.argtypes = [_vp, _i32]
@@ -97,7 +98,7 @@ lib.wl_test_detmath.argtypes = [_i32, _vp, _vp, _vp, _i32, _vp]
 lib.wl_test_philox.argtypes = [_u64, _u32, _u32, _u32, _u32, _vp, _i32, _vp]
 
 EXPORTED_SYMBOLS = [
-    "wl_config_describe", "wl_config_sizeof", "wl_state_bytes", "wl_globals_offset", "wl_create", "wl_destroy",
+    "wl_config_describe", "wl_config_sizeof", "wl_config_finalize", "wl_state_bytes", "wl_globals_offset", "wl_create", "wl_destroy",
     "wl_last_error", "wl_build_info", "wl_startup", "wl_reset", "wl_step", "wl_observe", "wl_curriculum",
     "wl_synth_actions", "wl_derive_suspension", "wl_set_kernel_variant", "wl_obs_dim", "wl_launch_count", "wl_test_detmath", "wl_test_philox",
 ]

@@ -1,6 +1,7 @@
 // wl_api.cu -- kernels + the extern "C" ABI declared in include/wheeledlab_b200.h.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false -lineinfo -O3 (see build.py).
 #include <cstdio>
+#include <cmath>
 #include <cstring>
 #include <new>
 #include <string>
@@ -45,22 +46,58 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+// Per-step episode log: warp-shuffle reduce over the finished envs, one atomic set per warp.
+__device__ __forceinline__ void log_accumulate(wl_globals* __restrict__ gl, bool contrib, bool terminated, bool time_out,
+                                               const float sums[WL_MAX_REW_TERMS]) {
+    const unsigned any_c = __ballot_sync(0xffffffffu, contrib);
+    if (!any_c) return;
+    float vals[WL_MAX_REW_TERMS + 3];
+#pragma unroll
+    for (int k = 0; k < WL_MAX_REW_TERMS; ++k) vals[k] = contrib ? sums[k] : 0.0f;
+    vals[WL_MAX_REW_TERMS + 0] = contrib ? 1.0f : 0.0f;
+    vals[WL_MAX_REW_TERMS + 1] = (contrib && terminated) ? 1.0f : 0.0f;
+    vals[WL_MAX_REW_TERMS + 2] = (contrib && time_out) ? 1.0f : 0.0f;
+#pragma unroll
+    for (int k = 0; k < WL_MAX_REW_TERMS + 3; ++k) vals[k] = warp_sum(vals[k]);
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < WL_MAX_REW_TERMS + 3; ++k) atomicAdd(&gl->acc[k], vals[k]);
+    }
+}
+// Last CTA of the launch turns the accumulators into the extras["log"] row and re-arms them.
+__device__ __forceinline__ void log_finalize(const wl_config& c, wl_globals* __restrict__ gl, float* __restrict__ d_log) {
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    const unsigned tk = atomicAdd(&gl->ticket, 1u);
+    if (tk != gridDim.x - 1) return;
+    __threadfence();
+    float a[WL_MAX_REW_TERMS + 3];
+#pragma unroll
+    for (int k = 0; k < WL_MAX_REW_TERMS + 3; ++k) a[k] = __ldcg(&gl->acc[k]);
+    const float cnt = a[WL_MAX_REW_TERMS];
+    if (d_log != nullptr) {
+        const float denom = r_max(cnt, 1.0f) * c.episode_length_s;
+#pragma unroll
+        for (int k = 0; k < WL_MAX_REW_TERMS; ++k) d_log[k] = a[k] / denom;
+        d_log[8] = a[8]; d_log[9] = a[9]; d_log[10] = a[10];
+#pragma unroll
+        for (int k = 11; k < WL_LOG_FLOATS; ++k) d_log[k] = 0.0f;
+    }
+    gl->any_reset_last = (cnt > 0.0f) ? 1 : 0;
+#pragma unroll
+    for (int k = 0; k < 12; ++k) gl->acc[k] = 0.0f;
+    gl->ticket = 0u;
+}
+
 // One thread per env.  TASK selects the MDP + terrain at compile time.
 template <int TASK>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)
 wl_step_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st, wl_globals* __restrict__ gl, Terrain T,
                const float2* __restrict__ action, float* __restrict__ obs, float* __restrict__ rew,
-               uint8_t* __restrict__ terminated_o, uint8_t* __restrict__ truncated_o, uint32_t t) {
+               uint8_t* __restrict__ terminated_o, uint8_t* __restrict__ truncated_o, float* __restrict__ d_log, uint32_t t) {
     const int n = c.num_envs;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int slot = (int)(t & 1u);
-    if (i == 0) {   // clear the log slot the NEXT step accumulates into
-#pragma unroll
-        for (int k = 0; k < WL_MAX_REW_TERMS; ++k) gl->log_sum[slot ^ 1][k] = 0.0f;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) gl->log_term[slot ^ 1][k] = 0.0f;
-        gl->any_reset[slot ^ 1] = 0;
-    }
     bool done = false, terminated = false, time_out = false;
     EnvState e;
     if (i < n) {
@@ -78,7 +115,7 @@ wl_step_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st, wl_
         b.pc = V3{e.p.x + cw.x, e.p.y + cw.y, e.p.z + cw.z};
         b.v = e.v; b.qw = e.qw; b.qx = e.qx; b.qy = e.qy; b.qz = e.qz;
         b.wb = rotT(R, e.w);
-        StepConsts kc = make_step_consts(c, e.mass);
+        StepConsts kc = make_step_consts(c, e.mass, e.inv_mass);
         for (int d = 0; d < c.decimation; ++d) {
             float tau[4];
 #pragma unroll
@@ -94,7 +131,7 @@ wl_step_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st, wl_
         e.ep_len += 1;
         // D. terminations
         time_out = e.ep_len >= c.max_episode_length;
-        const float step_dt = c.sim_dt * (float)c.decimation;
+        const float step_dt = c.d_step_dt;
         float f[WL_MAX_REW_TERMS];
         V3 vb = rotT(R, e.v);
         if (TASK == WL_TASK_DRIFT) {
@@ -116,35 +153,19 @@ wl_step_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st, wl_
         done = terminated || time_out;
     }
     // F. auto-reset + per-step episode log (warp-shuffle reduction over the finished envs)
-    const unsigned any = __ballot_sync(0xffffffffu, done);
-    if (any) {
-        float vals[WL_MAX_REW_TERMS + 3];
-#pragma unroll
-        for (int k = 0; k < WL_MAX_REW_TERMS; ++k) vals[k] = done ? e.sums[k] : 0.0f;
-        vals[WL_MAX_REW_TERMS + 0] = done ? 1.0f : 0.0f;
-        vals[WL_MAX_REW_TERMS + 1] = (done && terminated) ? 1.0f : 0.0f;
-        vals[WL_MAX_REW_TERMS + 2] = (done && time_out) ? 1.0f : 0.0f;
-#pragma unroll
-        for (int k = 0; k < WL_MAX_REW_TERMS + 3; ++k) vals[k] = warp_sum(vals[k]);
-        if ((threadIdx.x & 31) == 0) {
-#pragma unroll
-            for (int k = 0; k < WL_MAX_REW_TERMS; ++k) atomicAdd(&gl->log_sum[slot][k], vals[k]);
-#pragma unroll
-            for (int k = 0; k < 3; ++k) atomicAdd(&gl->log_term[slot][k], vals[WL_MAX_REW_TERMS + k]);
-            gl->any_reset[slot] = 1;
-        }
-    }
+    log_accumulate(gl, done, terminated, time_out, e.sums);
     if (i < n) {
         const uint32_t gid = (uint32_t)(c.env_id_offset + i);
         if (done) {
             if (TASK == WL_TASK_DRIFT) drift_reset_env(c, e, gid, t);
         }
         // H. interval events on the post-reset state
-        interval_pushes(c, e, gid, t, c.sim_dt * (float)c.decimation);
+        interval_pushes(c, e, gid, t, c.d_step_dt);
         // I. observations
         if (TASK == WL_TASK_DRIFT) blind_obs(c, e, gid, t, RNG_OBS, 0u, obs + (size_t)WL_OBS_DIM_BLIND * i);
         store_env(st, n, i, e, TASK == WL_TASK_ELEVATION);
     }
+    log_finalize(c, gl, d_log);
 }
 
 // Four lanes per env (lane = wheel).  Same arithmetic, same results; the per-wheel work runs in parallel and the
@@ -153,18 +174,10 @@ template <int TASK>
 __global__ void __launch_bounds__(128)
 wl_step_quad_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st, wl_globals* __restrict__ gl, Terrain T,
                     const float2* __restrict__ action, float* __restrict__ obs, float* __restrict__ rew,
-                    uint8_t* __restrict__ terminated_o, uint8_t* __restrict__ truncated_o, uint32_t t) {
+                    uint8_t* __restrict__ terminated_o, uint8_t* __restrict__ truncated_o, float* __restrict__ d_log, uint32_t t) {
     const int n = c.num_envs;
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int i = tid >> 2, w = tid & 3;
-    const int slot = (int)(t & 1u);
-    if (tid == 0) {
-#pragma unroll
-        for (int k = 0; k < WL_MAX_REW_TERMS; ++k) gl->log_sum[slot ^ 1][k] = 0.0f;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) gl->log_term[slot ^ 1][k] = 0.0f;
-        gl->any_reset[slot ^ 1] = 0;
-    }
     const bool live = i < n;                 // a whole quad is live or not (blockDim is a multiple of 4)
     const int ii = live ? i : n - 1;         // dead quads shadow the last env (no stores) so shuffles stay convergent
     const uint32_t gid = (uint32_t)(c.env_id_offset + ii);
@@ -187,7 +200,7 @@ wl_step_quad_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st
     b.pc = V3{e.p.x + cw.x, e.p.y + cw.y, e.p.z + cw.z};
     b.v = e.v; b.qw = e.qw; b.qx = e.qx; b.qy = e.qy; b.qz = e.qz;
     b.wb = rotT(R, e.w);
-    StepConsts kc = make_step_consts(c, e.mass);
+    StepConsts kc = make_step_consts(c, e.mass, e.inv_mass);
     for (int d = 0; d < c.decimation; ++d) {
         float tau[4];
         tau[0] = dc_motor(c, e.kd[0], my_effort, my_target, e.omega[0]);
@@ -201,7 +214,7 @@ wl_step_quad_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st
     // C./D. counters, terminations (redundant)
     e.ep_len += 1;
     const bool time_out = e.ep_len >= c.max_episode_length;
-    const float step_dt = c.sim_dt * (float)c.decimation;
+    const float step_dt = c.d_step_dt;
     V3 vb = rotT(R, e.v);
     bool terminated = false;
     float f[WL_MAX_REW_TERMS];
@@ -222,24 +235,7 @@ wl_step_quad_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st
     if (live && w == 0) { rew[i] = total; terminated_o[i] = terminated ? 1 : 0; truncated_o[i] = time_out ? 1 : 0; }
     // F. per-step episode log: one contribution per env (lane 0 of each live quad)
     const bool contrib = done && live && (w == 0);
-    const unsigned any = __ballot_sync(0xffffffffu, contrib);
-    if (any) {
-        float vals[WL_MAX_REW_TERMS + 3];
-#pragma unroll
-        for (int k = 0; k < WL_MAX_REW_TERMS; ++k) vals[k] = contrib ? e.sums[k] : 0.0f;
-        vals[WL_MAX_REW_TERMS + 0] = contrib ? 1.0f : 0.0f;
-        vals[WL_MAX_REW_TERMS + 1] = (contrib && terminated) ? 1.0f : 0.0f;
-        vals[WL_MAX_REW_TERMS + 2] = (contrib && time_out) ? 1.0f : 0.0f;
-#pragma unroll
-        for (int k = 0; k < WL_MAX_REW_TERMS + 3; ++k) vals[k] = warp_sum(vals[k]);
-        if ((threadIdx.x & 31) == 0) {
-#pragma unroll
-            for (int k = 0; k < WL_MAX_REW_TERMS; ++k) atomicAdd(&gl->log_sum[slot][k], vals[k]);
-#pragma unroll
-            for (int k = 0; k < 3; ++k) atomicAdd(&gl->log_term[slot][k], vals[WL_MAX_REW_TERMS + k]);
-            gl->any_reset[slot] = 1;
-        }
-    }
+    log_accumulate(gl, contrib, terminated, time_out, e.sums);
     if (done) {
         if (TASK == WL_TASK_DRIFT) drift_reset_env(c, e, gid, t);      // redundant in the 4 lanes; joints untouched (Q3)
     }
@@ -262,6 +258,7 @@ wl_step_quad_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st
         }
     }
     if (live) store_env_quad(st, n, i, w, e, TASK == WL_TASK_ELEVATION);
+    log_finalize(c, gl, d_log);
 }
 
 __global__ void wl_startup_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st) {
@@ -320,10 +317,10 @@ __global__ void wl_observe_kernel(const __grid_constant__ wl_config c, const flo
     blind_obs(c, e, (uint32_t)(c.env_id_offset + i), t, RNG_OBS_EXTRA, 3u * call_idx, obs + (size_t)WL_OBS_DIM_BLIND * i);
 }
 
-struct CurrArgs { int32_t n; int32_t slots[WL_MAX_REW_TERMS]; float inc[WL_MAX_REW_TERMS]; uint32_t fire_mask; int32_t slot; };
+struct CurrArgs { int32_t n; int32_t slots[WL_MAX_REW_TERMS]; float inc[WL_MAX_REW_TERMS]; uint32_t fire_mask; };
 __global__ void wl_curriculum_kernel(wl_globals* __restrict__ gl, CurrArgs a) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    if (!gl->any_reset[a.slot]) return;
+    if (!gl->any_reset_last) return;
     for (int t = 0; t < a.n; ++t)
         if ((a.fire_mask >> t) & 1u) gl->rew_weight[a.slots[t]] += a.inc[t];
 }
@@ -393,6 +390,24 @@ const char* wl_config_describe(void) {
     return s.c_str();
 }
 
+int wl_config_finalize(wl_config* c) {
+    if (!c) return fail(WL_EINVAL, "wl_config_finalize: null");
+    if (c->substeps <= 0 || !(c->sim_dt > 0.0f)) return fail(WL_EINVAL, "wl_config_finalize: bad sim timing");
+    c->d_h = c->sim_dt / (float)c->substeps;
+    c->d_inv_h = 1.0f / c->d_h;
+    c->d_step_dt = c->sim_dt * (float)c->decimation;
+    c->d_hkp = c->d_h * c->steer_kp;
+    c->d_sden = 1.0f / fmaf(c->d_h, c->d_hkp, fmaf(c->d_h, c->steer_kd, c->steer_inertia));
+    c->d_inv_Iw = 1.0f / c->wheel_inertia;
+    c->d_fxk = c->tire_mx * c->d_inv_h;
+    c->d_fyk = c->tire_my * c->d_inv_h;
+    c->d_inv_wheel_radius_cfg = 1.0f / c->wheel_radius_cfg;
+    c->d_inv_dc_vel_limit = 1.0f / c->dc_vel_limit;
+    c->d_inv_mass_nominal = 1.0f / c->mass_nominal;
+    for (int a = 0; a < 3; ++a) c->d_invI_nominal[a] = 1.0f / c->inertia_nominal[a];
+    return WL_OK;
+}
+
 size_t wl_globals_offset(int32_t num_envs) { return align256(groups_bytes(num_envs)); }
 size_t wl_state_bytes(int32_t num_envs) { return wl_globals_offset(num_envs) + align256(sizeof(wl_globals)); }
 
@@ -415,6 +430,7 @@ int wl_create(const wl_config* cfg, void* d_state, size_t state_bytes, const flo
     wl_sim* s = new (std::nothrow) wl_sim();
     if (!s) return fail(WL_EINVAL, "wl_create: out of host memory");
     s->cfg = *cfg;
+    if (int rc = wl_config_finalize(&s->cfg)) { delete s; return rc; }
     s->state = reinterpret_cast<float4*>(d_state);
     s->globals = reinterpret_cast<wl_globals*>(reinterpret_cast<char*>(d_state) + wl_globals_offset(cfg->num_envs));
     s->hf = d_heightfield;
@@ -464,7 +480,7 @@ int wl_reset(wl_sim* sim, const int64_t* d_env_ids, int32_t n_ids, int64_t step_
 }
 
 int wl_step(wl_sim* sim, const float* d_action, float* d_obs, float* d_rew, uint8_t* d_terminated, uint8_t* d_truncated,
-            int64_t step_counter, void* stream) {
+            float* d_log, int64_t step_counter, void* stream) {
     if (!sim || !d_action || !d_obs || !d_rew || !d_terminated || !d_truncated) return fail(WL_EINVAL, "wl_step: null argument");
     if (((uintptr_t)d_action & 7u) || ((uintptr_t)d_obs & 7u)) return fail(WL_EINVAL, "wl_step: action/obs must be 8-byte aligned");
     const int n = sim->cfg.num_envs;
@@ -474,12 +490,12 @@ int wl_step(wl_sim* sim, const float* d_action, float* d_obs, float* d_rew, uint
         const int bs = 32, threads = 4 * n;
         wl_step_quad_kernel<WL_TASK_DRIFT><<<(threads + bs - 1) / bs, bs, 0, (cudaStream_t)stream>>>(
             sim->cfg, sim->state, sim->globals, T, reinterpret_cast<const float2*>(d_action), d_obs, d_rew, d_terminated,
-            d_truncated, (uint32_t)step_counter);
+            d_truncated, d_log, (uint32_t)step_counter);
     } else {
         const int bs = pick_block(n);
         wl_step_kernel<WL_TASK_DRIFT><<<(n + bs - 1) / bs, bs, 0, (cudaStream_t)stream>>>(
             sim->cfg, sim->state, sim->globals, T, reinterpret_cast<const float2*>(d_action), d_obs, d_rew, d_terminated,
-            d_truncated, (uint32_t)step_counter);
+            d_truncated, d_log, (uint32_t)step_counter);
     }
     WL_LAUNCH_CHECK(sim, "wl_step_kernel");
     return WL_OK;
@@ -494,13 +510,13 @@ int wl_observe(wl_sim* sim, float* d_obs, int64_t step_counter, int32_t call_idx
     return WL_OK;
 }
 
-int wl_curriculum(wl_sim* sim, int64_t step_counter, int32_t n_terms, const int32_t* slots, const float* increases,
-                  uint32_t fire_mask, void* stream) {
+int wl_curriculum(wl_sim* sim, int32_t n_terms, const int32_t* slots, const float* increases, uint32_t fire_mask,
+                  void* stream) {
     if (!sim) return fail(WL_EINVAL, "wl_curriculum: null handle");
     if (n_terms < 0 || n_terms > WL_MAX_REW_TERMS) return fail(WL_EINVAL, "wl_curriculum: n_terms");
     if (n_terms == 0 || fire_mask == 0) return WL_OK;
     CurrArgs a; memset(&a, 0, sizeof a);
-    a.n = n_terms; a.fire_mask = fire_mask; a.slot = (int32_t)((step_counter - 1) & 1);
+    a.n = n_terms; a.fire_mask = fire_mask;
     for (int t = 0; t < n_terms; ++t) {
         if (slots[t] < 0 || slots[t] >= WL_MAX_REW_TERMS) return fail(WL_EINVAL, "wl_curriculum: slot out of range");
         a.slots[t] = slots[t]; a.inc[t] = increases[t];

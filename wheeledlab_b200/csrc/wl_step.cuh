@@ -112,7 +112,7 @@ __device__ __forceinline__ void process_action(const wl_config& c, float a0, flo
     float tan_d = det_tan(delta);
     float L = c.base_length, W = c.base_width, r = c.wheel_radius_cfg;
     if (c.action_kind == WL_ACT_RWD) {
-        float wt = v / r;
+        float wt = v * c.d_inv_wheel_radius_cfg;
         wheel_target[WL_BL] = wt; wheel_target[WL_BR] = wt; wheel_target[WL_FL] = 0.0f; wheel_target[WL_FR] = 0.0f;
         steer_target[0] = tan_d; steer_target[1] = tan_d;      // quirk Q1
         return;
@@ -121,11 +121,11 @@ __device__ __forceinline__ void process_action(const wl_config& c, float a0, flo
     float hw = W / 2.0f;
     float Rl = Rt - hw, Rr = Rt + hw;
     float Rrl = sqrtf(Rl * Rl + L * L), Rrr = sqrtf(Rr * Rr + L * L);
-    float den = Rt * r;
-    wheel_target[WL_FL] = v * fabsf(Rrl / den);
-    wheel_target[WL_FR] = v * fabsf(Rrr / den);
-    wheel_target[WL_BL] = v * fabsf(Rl / den);
-    wheel_target[WL_BR] = v * fabsf(Rr / den);
+    float rden = 1.0f / (Rt * r);
+    wheel_target[WL_FL] = v * fabsf(Rrl * rden);
+    wheel_target[WL_FR] = v * fabsf(Rrr * rden);
+    wheel_target[WL_BL] = v * fabsf(Rl * rden);
+    wheel_target[WL_BR] = v * fabsf(Rr * rden);
     if (c.action_kind == WL_ACT_4WD) { steer_target[0] = tan_d; steer_target[1] = tan_d; }
     else { steer_target[0] = det_atan(L / Rl); steer_target[1] = det_atan(L / Rr); }
 }
@@ -134,7 +134,7 @@ __device__ __forceinline__ void process_action(const wl_config& c, float a0, flo
 __device__ __forceinline__ float dc_motor(const wl_config& c, float kd, float effort_limit, float target, float omega) {
     if (!(effort_limit > 0.0f)) return 0.0f;
     float tau = kd * (target - omega);
-    float ratio = omega / c.dc_vel_limit;
+    float ratio = omega * c.d_inv_dc_vel_limit;
     float max_eff = r_clamp(c.dc_saturation * (1.0f - ratio), 0.0f, effort_limit);
     float min_eff = r_clamp(c.dc_saturation * (-1.0f - ratio), -effort_limit, 0.0f);
     return r_clamp(tau, min_eff, max_eff);
@@ -173,29 +173,22 @@ __device__ __forceinline__ void heightfield_at(const wl_config& c, const Terrain
 
 // ---- a8 integrator sub-step ----------------------------------------------------------
 struct Chassis { V3 pc; float qw, qx, qy, qz; V3 v; V3 wb; };
-struct StepConsts { float h, inv_h, sden, inv_Iw, hkp, fxk, fyk; float I[3], invI[3]; };
+struct StepConsts { float I[3], invI[3]; };       // mass-dependent only; everything else is c.d_*
 
-__device__ __forceinline__ StepConsts make_step_consts(const wl_config& c, float mass) {
+__device__ __forceinline__ StepConsts make_step_consts(const wl_config& c, float mass, float inv_mass) {
     StepConsts k;
-    k.h = c.sim_dt / (float)c.substeps;
-    k.inv_h = 1.0f / k.h;
-    k.hkp = k.h * c.steer_kp;
-    k.sden = 1.0f / fm(k.h, k.hkp, fm(k.h, c.steer_kd, c.steer_inertia));
-    k.inv_Iw = 1.0f / c.wheel_inertia;
-    k.fxk = c.tire_mx * k.inv_h;
-    k.fyk = c.tire_my * k.inv_h;
-    float ms = mass / c.mass_nominal;
+    float ms = mass * c.d_inv_mass_nominal;          // inertia scales with the DR mass ratio (a14)
+    float ms_inv = c.mass_nominal * inv_mass;
 #pragma unroll
-    for (int a = 0; a < 3; ++a) { k.I[a] = c.inertia_nominal[a] * ms; k.invI[a] = 1.0f / k.I[a]; }
+    for (int a = 0; a < 3; ++a) { k.I[a] = c.inertia_nominal[a] * ms; k.invI[a] = c.d_invI_nominal[a] * ms_inv; }
     return k;
 }
 
 // steer joint j (0 left, 1 right): implicit PD step, returns sin/cos of the new angle
-__device__ __forceinline__ void steer_step(const wl_config& c, const StepConsts& k, float target, float& pos, float& vel,
-                                           float& sn, float& cs) {
-    float v = fm(k.hkp, target - pos, c.steer_inertia * vel) * k.sden;
+__device__ __forceinline__ void steer_step(const wl_config& c, float target, float& pos, float& vel, float& sn, float& cs) {
+    float v = fm(c.d_hkp, target - pos, c.steer_inertia * vel) * c.d_sden;
     v = r_clamp(v, -c.steer_vel_limit, c.steer_vel_limit);
-    float p = r_clamp(fm(k.h, v, pos), -c.steer_pos_limit, c.steer_pos_limit);
+    float p = r_clamp(fm(c.d_h, v, pos), -c.steer_pos_limit, c.steer_pos_limit);
     vel = v; pos = p;
     det_sincos(p, sn, cs);
 }
@@ -223,7 +216,7 @@ __device__ __forceinline__ WheelOut wheel_force(const wl_config& c, const Terrai
         nb = V3{R.r[6], R.r[7], R.r[8]};
     }
     WheelOut o;
-    float om_star = fm(k.h, (tau - c.wheel_damping * omega) * k.inv_Iw, omega);   // drive torque first
+    float om_star = fm(c.d_h, (tau - c.wheel_damping * omega) * c.d_inv_Iw, omega);   // drive torque first
     V3 rc = axpy(rho, -rw, nb);
     V3 vc = cross(b.wb, rc);
     vc.x += vb.x; vc.y += vb.y; vc.z += vb.z;
@@ -234,29 +227,31 @@ __device__ __forceinline__ WheelOut wheel_force(const wl_config& c, const Terrai
     V3 ft;
     if (i >= 2) { float d = fm(cs, nb.x, sn * nb.y); ft = V3{fm(-d, nb.x, cs), fm(-d, nb.y, sn), -(d * nb.z)}; }
     else { float d = nb.x; ft = V3{fm(-d, nb.x, 1.0f), -(d * nb.y), -(d * nb.z)}; }
-    float finv = 1.0f / sqrtf(dot(ft, ft));
+    // |ft|^2 = 1 - d^2: normalise with the binomial series of (1 - e)^(-1/2), e = 1 - |ft|^2 (no sqrt, no division)
+    float en = 1.0f - dot(ft, ft);
+    float finv = fm(fm(fm(fm(0.2734375f, en, 0.3125f), en, 0.375f), en, 0.5f), en, 1.0f);
     ft.x *= finv; ft.y *= finv; ft.z *= finv;
     V3 lt = cross(nb, ft);
     float vx = dot(vc, ft), vy = dot(vc, lt);
     float sx = fm(om_star, rw, -vx), sy = -vy;               // slip velocity of the tyre surface
     float smag = sqrtf(fm(sx, sx, sy * sy));
     float den = r_max(fabsf(vx), c.tire_v0);
-    float sm, cm; det_sincos(Cmu * det_atan_ratio(c.tire_B * smag, den), sm, cm);
+    float sm = det_sin_0_pi(Cmu * det_atan_ratio(c.tire_B * smag, den));
     float Fmag = Fz * (Dmu * sm);
     float inv_s = 1.0f / r_max(smag, 1.0e-9f);
     float Fx = (Fmag * sx) * inv_s, Fy = (Fmag * sy) * inv_s;
-    float fxm = k.fxk * fabsf(sx), fym = k.fyk * fabsf(sy);  // implicit-stick cap
+    float fxm = c.d_fxk * fabsf(sx), fym = c.d_fyk * fabsf(sy);  // implicit-stick cap
     Fx = r_clamp(Fx, -fxm, fxm); Fy = r_clamp(Fy, -fym, fym);
     o.F = V3{fm(Fz, nb.x, fm(Fx, ft.x, Fy * lt.x)), fm(Fz, nb.y, fm(Fx, ft.y, Fy * lt.y)), fm(Fz, nb.z, fm(Fx, ft.z, Fy * lt.z))};
     o.Tq = cross(rc, o.F);
-    o.omega = fm(-k.h, (rw * Fx) * k.inv_Iw, om_star);
+    o.omega = fm(-c.d_h, (rw * Fx) * c.d_inv_Iw, om_star);
     return o;
 }
 
 // chassis: semi-implicit Euler; Euler's equations in the body frame (gyroscopic term on, mushr.py:28)
 __device__ __forceinline__ void chassis_integrate(const wl_config& c, const StepConsts& k, const M3& R, Chassis& b, V3 Fb, V3 Tb,
                                                   float inv_mass) {
-    const float h = k.h;
+    const float h = c.d_h;
     V3 Fw = rot(R, Fb);
     b.v.x = fm(h, Fw.x * inv_mass, b.v.x);
     b.v.y = fm(h, Fw.y * inv_mass, b.v.y);
@@ -273,7 +268,9 @@ __device__ __forceinline__ void chassis_integrate(const wl_config& c, const Step
     float nqx = fm(hh, fm(qw, ox, fm(qy, oz, -(qz * oy))), qx);
     float nqy = fm(hh, fm(qw, oy, fm(qz, ox, -(qx * oz))), qy);
     float nqz = fm(hh, fm(qw, oz, fm(qx, oy, -(qy * ox))), qz);
-    float qinv = 1.0f / sqrtf(fm(nqw, nqw, fm(nqx, nqx, fm(nqy, nqy, nqz * nqz))));
+    // renormalise with the series of (1 + e)^(-1/2), e = |q|^2 - 1 = O(h^2 |w|^2) (no sqrt, no division)
+    float eq = fm(nqw, nqw, fm(nqx, nqx, fm(nqy, nqy, nqz * nqz))) - 1.0f;
+    float qinv = fm(fm(fm(-0.3125f, eq, 0.375f), eq, -0.5f), eq, 1.0f);
     b.qw = nqw * qinv; b.qx = nqx * qinv; b.qy = nqy * qinv; b.qz = nqz * qinv;
 }
 
@@ -289,8 +286,8 @@ __device__ __forceinline__ void physics_substep(const wl_config& c, const Terrai
     V3 Fb, Tb;
     if (LANES == 1) {
         float sn[2], cs[2];
-        steer_step(c, k, steer_target[0], e.steer[0], e.steer_vel[0], sn[0], cs[0]);
-        steer_step(c, k, steer_target[1], e.steer[1], e.steer_vel[1], sn[1], cs[1]);
+        steer_step(c, steer_target[0], e.steer[0], e.steer_vel[0], sn[0], cs[0]);
+        steer_step(c, steer_target[1], e.steer[1], e.steer_vel[1], sn[1], cs[1]);
         WheelOut w[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
@@ -305,7 +302,7 @@ __device__ __forceinline__ void physics_substep(const wl_config& c, const Terrai
     } else {
         const int i = threadIdx.x & 3;
         float sn = 0.0f, cs = 1.0f;
-        if (i >= 2) steer_step(c, k, steer_target[0], e.steer[0], e.steer_vel[0], sn, cs);   // lane-local copy of ITS joint
+        if (i >= 2) steer_step(c, steer_target[0], e.steer[0], e.steer_vel[0], sn, cs);   // lane-local copy of ITS joint
         WheelOut w = wheel_force<TASK>(c, T, k, R, b, vb, i, sn, cs, e.omega[0], tau[0], e.D[0], e.C[0]);
         e.omega[0] = w.omega;
         float v6[6] = {w.F.x, w.F.y, w.F.z, w.Tq.x, w.Tq.y, w.Tq.z};

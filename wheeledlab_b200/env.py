@@ -276,31 +276,30 @@ class ManagerBasedRLEnv:
         if action.dtype != torch.float32 or not action.is_contiguous() or str(action.device) != self.device:
             action = action.to(self.device, torch.float32).contiguous()
         t = self.common_step_counter
-        obs, rew, term_u8, trunc_u8 = self.sim.step(action, t)
+        log = torch.empty(16, dtype=torch.float32, device=self.device) if self.log_episode_info else None
+        obs, rew, term_u8, trunc_u8 = self.sim.step(action, t, log=log)
         self.common_step_counter = t + 1
         # curriculum (inside _reset_idx upstream: uses the incremented counter and fires only if >=1 env reset;
         # the "any reset" test happens on the device, so there is no host sync)
         mask = self._curriculum_fire_mask()
         if mask:
-            self.sim.curriculum(self.common_step_counter, self._curr_slots, self._curr_inc, mask)
+            self.sim.curriculum(self._curr_slots, self._curr_inc, mask)
         terminated, truncated = term_u8.view(torch.bool), trunc_u8.view(torch.bool)
         tm = self.termination_manager
         tm.terminated, tm.time_outs = terminated, truncated
-        if self.log_episode_info:
-            self.extras["log"] = self._episode_log(t)
+        if log is not None:
+            self.extras["log"] = self._episode_log(log)
         return {"policy": obs}, rew, terminated, truncated, self.extras
 
-    def _episode_log(self, t: int):
-        """extras["log"] (RewardManager/TerminationManager.reset): device tensors, no sync."""
-        sums, terms = self.sim.step_log(t)
-        sums, terms = sums.clone(), terms.clone()
-        denom = torch.clamp(terms[0], min=1.0) * self.max_episode_length_s
-        log = {}
+    def _episode_log(self, log: torch.Tensor):
+        """extras["log"] (RewardManager/TerminationManager.reset): views of the row the step
+        kernel's last CTA wrote -- device tensors, no extra launches, no host sync."""
+        out = {}
         for k, name in enumerate(self.spec.reward_names):
-            log["Episode_Reward/" + name] = sums[k] / denom
+            out["Episode_Reward/" + name] = log[k]
         for name, is_to in self.spec.termination_names:
-            log["Episode_Termination/" + name] = terms[2] if is_to else terms[1]
-        return log
+            out["Episode_Termination/" + name] = log[10] if is_to else log[9]
+        return out
 
 
 def make(task_id: str, cfg=None, render_mode=None, device="cuda:0", **kw) -> ManagerBasedRLEnv:

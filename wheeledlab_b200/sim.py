@@ -51,8 +51,6 @@ class WheeledSim:
         goff = lib.wl_globals_offset(n) // 4
         self._globals = self._buf[goff: goff + C.sizeof(_lib.WlGlobals) // 4]
         self.rew_weight = self._globals[0:8]
-        self._log_sum = self._globals[8:24].view(2, 8)
-        self._log_term = self._globals[24:32].view(2, 4)
         self.obs_dim = int(lib.wl_obs_dim(self._h))
 
     # -- lifetime ------------------------------------------------------------------
@@ -81,8 +79,9 @@ class WheeledSim:
                 check(lib.wl_reset(self._h, C.c_void_p(ids.data_ptr()), ids.numel(), step_counter,
                                    _stream_ptr(self.device)), "wl_reset")
 
-    def step(self, action: torch.Tensor, step_counter: int, out=None):
-        """action [N,2] f32 (device, contiguous) -> (obs [N,D] f32, rew [N] f32, terminated [N] u8, truncated [N] u8)."""
+    def step(self, action: torch.Tensor, step_counter: int, out=None, log: torch.Tensor | None = None):
+        """action [N,2] f32 (device, contiguous) -> (obs [N,D] f32, rew [N] f32, terminated [N] u8, truncated [N] u8).
+        `log`: optional float32[16] device tensor receiving this step's episode log row (see wl_step)."""
         n = self.num_envs
         if out is None:
             obs = torch.empty((n, self.obs_dim), dtype=torch.float32, device=self.device)
@@ -92,7 +91,8 @@ class WheeledSim:
         else:
             obs, rew, term, trunc = out
         check(lib.wl_step(self._h, C.c_void_p(action.data_ptr()), C.c_void_p(obs.data_ptr()), C.c_void_p(rew.data_ptr()),
-                          C.c_void_p(term.data_ptr()), C.c_void_p(trunc.data_ptr()), step_counter,
+                          C.c_void_p(term.data_ptr()), C.c_void_p(trunc.data_ptr()),
+                          C.c_void_p(log.data_ptr()) if log is not None else None, step_counter,
                           _stream_ptr(self.device)), "wl_step")
         return obs, rew, term, trunc
 
@@ -102,13 +102,13 @@ class WheeledSim:
               "wl_observe")
         return obs
 
-    def curriculum(self, step_counter: int, slots, increases, fire_mask: int):
+    def curriculum(self, slots, increases, fire_mask: int):
         n = len(slots)
         if n == 0 or fire_mask == 0:
             return
         a = (C.c_int32 * n)(*slots)
         b = (C.c_float * n)(*increases)
-        check(lib.wl_curriculum(self._h, step_counter, n, a, b, fire_mask, _stream_ptr(self.device)), "wl_curriculum")
+        check(lib.wl_curriculum(self._h, n, a, b, fire_mask, _stream_ptr(self.device)), "wl_curriculum")
 
     def synth_actions(self, step_counter: int, dist: int = 0, out: torch.Tensor | None = None):
         act = out if out is not None else torch.empty((self.num_envs, 2), dtype=torch.float32, device=self.device)
@@ -123,11 +123,6 @@ class WheeledSim:
     @property
     def launch_count(self) -> int:
         return int(lib.wl_launch_count(self._h))
-
-    # -- log of the step with counter value `step_counter` (valid until the step after next) -------
-    def step_log(self, step_counter: int):
-        s = step_counter & 1
-        return self._log_sum[s], self._log_term[s]
 
     # -- zero-copy state views (IsaacLab ArticulationData names) -------------------------------------
     @property

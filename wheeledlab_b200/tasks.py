@@ -177,6 +177,7 @@ def drift_task(num_envs: int = 1024, seed: int = 42, env_id_offset: int = 0, ran
     episode_length_s = 5.0                                             # :396
     # ManagerBasedRLEnv.max_episode_length: ceil in Python doubles (NOT on the fp32 copy of dt) -> 250
     cfg.max_episode_length = math.ceil(episode_length_s / (sim_dt * decimation))
+    cfg.episode_length_s = episode_length_s
     # actions: MushrRWDActionCfg (common/actions.py:5-24), scale re-set at :397
     cfg.action_kind = ACT_RWD if drive == "2wd" else ACT_4WD
     cfg.bounding, cfg.no_reverse = BOUND_CLIP, 1
