@@ -128,6 +128,8 @@ extern "C" {
     XS(float, f32, susp_c)                                                                         \
     XS(float, f32, susp_travel)                                                                    \
     XS(float, f32, bump_k)                                                                         \
+    XS(float, f32, comp_max)          /* compression used for the force is capped (depenetration) */ \
+    XS(float, f32, base_link_z)       /* base_link above the root frame (ray-caster parent), A.1 */ \
     /* --- actuators (wheeledlab_assets/hound.py:4-52) --- */                                      \
     XS(float, f32, dc_saturation)                                                                  \
     XS(float, f32, dc_vel_limit)                                                                   \
@@ -188,6 +190,8 @@ extern "C" {
     /* --- elevation task (elevation/mushr_elevation_env_cfg.py) --- */                            \
     XS(int32_t, i32, hf_nx)           /* height-field raster size */                               \
     XS(int32_t, i32, hf_ny)                                                                        \
+    XS(int32_t, i32, hf_pitch)        /* row pitch in floats (multiple of 4: TMA needs 16-B strides) */ \
+    XS(int32_t, i32, _pad4)                                                                        \
     XS(float, f32, hf_x0)             /* world coord of sample (0,0) */                            \
     XS(float, f32, hf_y0)                                                                          \
     XS(float, f32, hf_cell)                                                                        \
@@ -196,6 +200,7 @@ extern "C" {
     XS(float, f32, scan_plane_init)   /* 0.19,  :79 */                                             \
     XS(float, f32, scan_sensor_dz)    /* +20 m ray start, :135 */                                  \
     XS(float, f32, scan_res)          /* 0.1 */                                                    \
+    XS(float, f32, scan_half)         /* 1.25 = (26-1)*res/2, GridPatternCfg size 2.5 */           \
     XS(float, f32, obs_clip)          /* 10, :61-82 */                                             \
     XA(float, f32, cmd_pos_range, 2)  /* +-19 m, :425-435 */                                       \
     XS(float, f32, cmd_resample_s)                                                                 \
@@ -252,19 +257,24 @@ typedef struct wl_config {
 #define WL_G_PMU_D  10  /* Pacejka peak D per wheel                      (DR param)   */
 #define WL_G_PMU_C  11  /* Pacejka shape C per wheel                     (DR param)   */
 #define WL_G_PKD    12  /* DC-motor damping per wheel                    (DR param)   */
-#define WL_G_CMD    13  /* elevation: goal x,y (world), heading, command time_left    */
-#define WL_NUM_GROUPS 14
+#define WL_G_CMD    13  /* elevation: goal x,y (world), heading_w, command time_left  */
+#define WL_G_CMDB   14  /* elevation: command in the yaw frame x,y, heading_b, spare  */
+#define WL_NUM_GROUPS 15
 
 /* small global (not per-env) device block appended after the groups */
 typedef struct wl_globals {
     float rew_weight[WL_MAX_REW_TERMS];   /* live reward weights (curriculum mutates)                      */
-    float acc[12];                        /* this step: [0..7] sum over reset envs of their episode sums,   */
-                                          /* [8] #reset, [9] #terminated, [10] #timed-out                    */
+    float acc[16];                        /* this step: [0..7] sum over reset envs of their episode sums,   */
+                                          /* [8] #reset, [9+j] #envs whose termination term j fired          */
     uint32_t ticket;                      /* CTAs finished in the current launch (last one finalises)       */
     int32_t any_reset_last;               /* 1 if the previous step reset >= 1 env (read by wl_curriculum)  */
     int32_t _pad[2];
 } wl_globals;
-#define WL_LOG_FLOATS 16                  /* d_log layout: [0..7] Episode_Reward means, [8..10] counts      */
+#define WL_LOG_FLOATS 16                  /* d_log: [0..7] Episode_Reward means, [8] #reset, [9+j] term counts */
+/* termination term order (bit j of the per-env mask; declaration order of the reference cfgs)
+ *   drift     (mushr_drift_env_cfg.py:351-362):     0 time_out, 1 out_of_bounds
+ *   elevation (mushr_elevation_env_cfg.py:349-376): 0 time_out, 1 cart_out_of_bounds, 2 stuck, 3 rollover, 4 at_goal */
+#define WL_MAX_TERM_TERMS 7
 
 typedef struct wl_sim wl_sim;   /* opaque handle (host memory) */
 
@@ -279,7 +289,8 @@ int wl_config_finalize(wl_config* cfg);
 size_t wl_state_bytes(int32_t num_envs);     /* groups + globals, 256-byte padded */
 size_t wl_globals_offset(int32_t num_envs);  /* byte offset of wl_globals in the state buffer */
 /* d_state: zero-initialised device buffer of wl_state_bytes(cfg->num_envs) bytes.
- * d_heightfield: float[hf_ny*hf_nx] on device (row-major, y-major rows) or NULL. */
+ * d_heightfield: float[hf_ny*hf_nx] on device (row-major: index iy*hf_nx + ix, 16-byte aligned, hf_nx % 4 == 0)
+ * or NULL.  For the elevation task a TMA tensor map over it is built here. */
 int wl_create(const wl_config* cfg, void* d_state, size_t state_bytes, const float* d_heightfield,
               wl_sim** out);
 int wl_destroy(wl_sim* sim);
@@ -318,6 +329,8 @@ int wl_derive_suspension(wl_sim* sim, float* d_susp_pos, float* d_susp_vel, void
 /* step-kernel geometry: 0 = auto (by num_envs), 1 = one thread per env, 4 = four lanes (one per wheel) per env.
  * Results are bit-identical across variants. */
 int wl_set_kernel_variant(wl_sim* sim, int32_t lanes_per_env);
+/* height-scan tile staging: 1 = TMA (cp.async.bulk.tensor.2d, default), 0 = plain loads (A/B comparison) */
+int wl_set_scan_tma(wl_sim* sim, int32_t use_tma);
 /* observation width for the configured task */
 int32_t wl_obs_dim(const wl_sim* sim);
 /* number of kernel launches issued through this handle since creation */

@@ -193,7 +193,8 @@ typedef struct {
     real sums[WL_MAX_REW_TERMS];
     real mass, inv_mass, spare0, spare1;
     real D[4], C[4], kd[4];
-    real cmd[4];
+    real cmd[4];      /* elevation: goal x,y (world), heading_w, command time_left */
+    real cmdb[4];     /* elevation: command in the yaw frame x,y, heading_b, spare */
 } wlo_env;
 
 typedef struct wlo_sim {
@@ -201,7 +202,7 @@ typedef struct wlo_sim {
     wlo_env* env;
     real rew_weight[WL_MAX_REW_TERMS];
     double log_sum[WL_MAX_REW_TERMS];     /* last step: sum over reset envs of episode sums */
-    double log_term[4];                   /* last step: #reset, #terminated, #timed-out */
+    double log_term[8];                   /* last step: #reset, then per termination term counts */
     int32_t any_reset_last;
     float* hf;
 } wlo_sim;
@@ -238,7 +239,7 @@ static inline real vdot(const real a[3], const real b[3]) { return dot3(a[0], a[
 /* procedural), ground plane hf_outside_z outside the raster                   */
 /* (elevation/mushr_elevation_env_cfg.py:95-128).                              */
 /* ------------------------------------------------------------------------- */
-static inline real hf_at(const wlo_sim* s, int ix, int iy) { return (real)s->hf[(size_t)iy * s->cfg.hf_nx + ix]; }
+static inline real hf_at(const wlo_sim* s, int ix, int iy) { return (real)s->hf[(size_t)iy * s->cfg.hf_pitch + ix]; }
 
 /* returns 1 when (x,y) is inside the raster */
 static int hf_sample(const wlo_sim* s, real x, real y, real* z, real* gx, real* gy) {
@@ -388,8 +389,9 @@ static void physics_substep(const wlo_sim* s, wlo_env* e, chassis_t* b, const re
         real vc[3]; cross(b->wb, rc, vc);
         vc[0] += vb[0]; vc[1] += vb[1]; vc[2] += vb[2];
         real sdot = -vdot(nb, vc);
-        real Fz = fm((real)c->susp_k, comp, (real)c->susp_c * sdot);
-        if (comp > (real)c->susp_travel) Fz = fm((real)c->bump_k, comp - (real)c->susp_travel, Fz);
+        real ce = r_min(comp, (real)c->comp_max);     /* depenetration cap */
+        real Fz = fm((real)c->susp_k, ce, (real)c->susp_c * sdot);
+        if (ce > (real)c->susp_travel) Fz = fm((real)c->bump_k, ce - (real)c->susp_travel, Fz);
         Fz = (comp > K(0.0)) ? r_max(Fz, K(0.0)) : K(0.0);
         real ft[3];
         if (i >= 2) {
@@ -553,6 +555,104 @@ static void drift_reset_env(const wl_config* c, wlo_env* e, uint32_t gid, int64_
     sample_interval_timers(c, e, r2[0], r2[1]);
 }
 
+/* ------------------------------------------------------------------------- */
+/* elevation task, elevation/mushr_elevation_env_cfg.py                          */
+/* ------------------------------------------------------------------------- */
+/* terminations :339-376 -> mask bits [0 time_out,1 cart_out_of_bounds,2 stuck,3 rollover,4 at_goal]; rewards :283-305 */
+static uint32_t elev_terms(const wl_config* c, const wlo_env* e, const real R[9], const real vb[3], real sum_omega, int time_out,
+                           real f[WL_MAX_REW_TERMS]) {
+    real gx = e->cmdb[0] - e->p[0], gy = e->cmdb[1] - e->p[1];        /* quirk Q5: yaw-frame command minus WORLD position */
+    real gn = r_sqrt(fm(gx, gx, gy * gy));
+    int oob = e->p[2] < (real)c->elev_min_height;                     /* root_height_below_minimum :354-357 */
+    int stuck = (r_min(vb[0], K(1.2)) < (real)c->elev_stuck_min_vel) && (sum_omega > (real)c->elev_stuck_spin); /* :342-347 */
+    int roll = R[8] < (real)c->elev_rollover_cos;                     /* upright_bool :217-222,339-340 */
+    int goal = gn < (real)c->elev_goal_dist;                          /* close_to_goal :268-273 */
+    f[WL_ER_GOAL_RATE] = K(5.0) + fm(e->v[0], gx, e->v[1] * gy) / gn; /* goal_progress_rate :239-249 */
+    real zv = e->p[2] - (real)c->elev_plane_z;                        /* higher_elevation :166-173 */
+    real he = ((zv > K(0.1)) && (vb[0] > K(0.1))) ? zv : K(0.0);
+    f[WL_ER_HEIGHT_Z] = r_clamp(he, K(0.0), K(1.0));
+    f[WL_ER_FALLING] = (vb[2] > (real)c->elev_fall_vel) ? K(1.0) : K(0.0);   /* is_falling_penalty :251-254 (2nd def) */
+    f[WL_ER_TERM_PEN] = (stuck && !time_out) ? K(1.0) : K(0.0);      /* is_terminated_term("stuck") */
+    f[4] = f[5] = f[6] = f[7] = K(0.0);
+    return (time_out ? 1u : 0u) | (oob ? 2u : 0u) | (stuck ? 4u : 0u) | (roll ? 8u : 0u) | (goal ? 16u : 0u);
+}
+/* reset_root_state_uniform :409-419 on default root z 0.25 (:97,147-149) + manager resets + command resample :425-435 */
+static void elev_reset_env(const wl_config* c, wlo_env* e, uint32_t gid, int64_t t) {
+    uint32_t r[4], r2[4];
+    philox4x32(c->seed, gid, (uint32_t)t, RNG_RESET, 0u, r);
+    philox4x32(c->seed, gid, (uint32_t)t, RNG_RESET, 1u, r2);
+    e->p[0] = uniform(r[0], (real)c->elev_reset_xy[0], (real)c->elev_reset_xy[1]);
+    e->p[1] = uniform(r[1], (real)c->elev_reset_xy[0], (real)c->elev_reset_xy[1]);
+    e->p[2] = (real)c->elev_spawn_z;
+    real yaw = uniform(r[2], -(real)c->elev_reset_yaw, (real)c->elev_reset_yaw);
+    real sh, ch; det_sincos(yaw * K(0.5), &sh, &ch);
+    e->q[0] = ch; e->q[1] = K(0.0); e->q[2] = K(0.0); e->q[3] = sh;
+    e->v[0] = uniform(r[3], (real)c->elev_reset_vel[0], (real)c->elev_reset_vel[1]);
+    e->v[1] = uniform(r2[0], (real)c->elev_reset_vel[0], (real)c->elev_reset_vel[1]);
+    e->v[2] = K(0.0);
+    e->w[0] = e->w[1] = e->w[2] = K(0.0);
+    e->ep_len = 0;
+    for (int k = 0; k < WL_MAX_REW_TERMS; ++k) e->sums[k] = K(0.0);
+    e->action[0] = e->action[1] = e->prev_action[0] = e->prev_action[1] = K(0.0);
+    e->cmd[0] = uniform(r2[1], (real)c->cmd_pos_range[0], (real)c->cmd_pos_range[1]);
+    e->cmd[1] = uniform(r2[2], (real)c->cmd_pos_range[0], (real)c->cmd_pos_range[1]);
+    e->cmd[2] = K(0.0);
+    e->cmd[3] = (real)c->cmd_resample_s;
+}
+static void yaw_cs(const wlo_env* e, real* cy, real* sy) {
+    real cr = fm(K(-2.0), fm(e->q[2], e->q[2], e->q[3] * e->q[3]), K(1.0)), sr = K(2.0) * fm(e->q[0], e->q[3], e->q[1] * e->q[2]);
+    real rinv = K(1.0) / r_sqrt(fm(cr, cr, sr * sr));
+    *cy = cr * rinv; *sy = sr * rinv;
+}
+/* CommandManager.compute(dt) [UPSTREAM-RECALL]: timer, resample, yaw-frame command */
+static void elev_command_update(const wl_config* c, wlo_env* e, uint32_t gid, int64_t t, real step_dt) {
+    e->cmd[3] = e->cmd[3] - step_dt;
+    if (e->cmd[3] <= K(0.0)) {
+        uint32_t r[4]; philox4x32(c->seed, gid, (uint32_t)t, RNG_CMD, 0u, r);
+        e->cmd[0] = uniform(r[0], (real)c->cmd_pos_range[0], (real)c->cmd_pos_range[1]);
+        e->cmd[1] = uniform(r[1], (real)c->cmd_pos_range[0], (real)c->cmd_pos_range[1]);
+        e->cmd[3] = (real)c->cmd_resample_s;
+    }
+    real cy, sy; yaw_cs(e, &cy, &sy);
+    real dx = e->cmd[0] - e->p[0], dy = e->cmd[1] - e->p[1];
+    e->cmdb[0] = fm(cy, dx, sy * dy);
+    e->cmdb[1] = fm(cy, dy, -(sy * dx));
+    e->cmdb[2] = K(0.0); e->cmdb[3] = K(0.0);
+}
+static void euler_xyz(const real q[4], real e[3]);
+/* ElevationObsCfg (:50-88): 13 proprioceptive floats + 676-ray height map, all clipped, no noise */
+static void elev_obs(const wlo_sim* s, const wlo_env* e, float* obs) {
+    const wl_config* c = &s->cfg;
+    real R[9]; rotmat(e->q, R);
+    real vb[3], wb[3], eu[3]; rotT(R, e->v, vb); rotT(R, e->w, wb); euler_xyz(e->q, eu);
+    real gx = e->cmdb[0] - e->p[0], gy = e->cmdb[1] - e->p[1];
+    real cl = (real)c->obs_clip;
+    obs[0] = (float)((gx != gx) ? K(0.0) : gx); obs[1] = (float)((gy != gy) ? K(0.0) : gy);
+    for (int k = 0; k < 3; ++k) {
+        obs[2 + k] = (float)eu[k];
+        obs[5 + k] = (float)r_clamp(vb[k], -cl, cl);
+        obs[8 + k] = (float)r_clamp(wb[k], -cl, cl);
+    }
+    obs[11] = (float)r_clamp(e->action[0], K(-1.0), K(1.0));
+    obs[12] = (float)r_clamp(e->action[1], K(-1.0), K(1.0));
+    /* ray-caster :132-142: 26x26 grid on base_link, yaw-only alignment, vertical rays vs the terrain raster */
+    real bx = fm((real)c->base_link_z, R[2], e->p[0]), by = fm((real)c->base_link_z, R[5], e->p[1]), bz = fm((real)c->base_link_z, R[8], e->p[2]);
+    real cy, sy; yaw_cs(e, &cy, &sy);
+    for (int k = 0; k < WL_SCAN_RAYS; ++k) {
+        int rx = k % WL_SCAN_SIDE, ry = k / WL_SCAN_SIDE;
+        real lx = fm((real)rx, (real)c->scan_res, -(real)c->scan_half), ly = fm((real)ry, (real)c->scan_res, -(real)c->scan_half);
+        real wx = fm(cy, lx, fm(-sy, ly, bx)), wy = fm(sy, lx, fm(cy, ly, by));
+        real hit, gxx, gyy, v;
+        if (hf_sample(s, wx, wy, &hit, &gxx, &gyy)) {
+            real hs = bz - hit - (real)c->scan_offset;                              /* mdp.height_scan */
+            v = r_clamp(-hs + (e->p[2] - (real)c->scan_plane_init), -cl, cl);       /* world_height_map :44-48 */
+        } else {
+            v = cl;                                                                 /* miss: +inf, clipped */
+        }
+        obs[13 + k] = (float)v;
+    }
+}
+
 /* interval pushes, mushr_drift_env_cfg.py:121-143; push_by_setting_velocity (+=) [UPSTREAM-RECALL a13] */
 static void interval_pushes(const wl_config* c, wlo_env* e, uint32_t gid, int64_t t, real step_dt) {
     if (!c->push_enable) return;
@@ -598,7 +698,7 @@ static void blind_obs(const wl_config* c, const wlo_env* e, uint32_t gid, uint32
 /* ------------------------------------------------------------------------- */
 /* one env.step() for one env -- ordering per SURVEY 3.3 A..I                  */
 /* ------------------------------------------------------------------------- */
-typedef struct { double sum[WL_MAX_REW_TERMS]; double n_reset, n_term, n_timeout; int any; } step_log;
+typedef struct { double sum[WL_MAX_REW_TERMS]; double n_reset; double n_term[WL_MAX_TERM_TERMS]; int any; } step_log;
 
 static int env_step(wlo_sim* s, int li, const float* a_in, int64_t t, float* obs, float* rew, uint8_t* term_o,
                     uint8_t* trunc_o, step_log* lg) {
@@ -631,15 +731,18 @@ static int env_step(wlo_sim* s, int li, const float* a_in, int64_t t, float* obs
     rot(R, b.wb, e->w);
     /* C. counters */
     e->ep_len += 1;
-    /* D. terminations (time_out first in cfg order, :351-362) */
+    /* D. terminations (time_out first in cfg order) */
     int time_out = e->ep_len >= c->max_episode_length;
-    int terminated = 0;
+    uint32_t tmask;
     real step_dt = (real)c->d_step_dt;
     real f[WL_MAX_REW_TERMS];
     real vb[3]; rotT(R, e->v, vb);
     if (c->task == WL_TASK_DRIFT) {
-        terminated = drift_off_track(c, e->p[0], e->p[1]);
-        drift_reward_terms(c, e, e->p, vb, b.wb, e->w[2], terminated, time_out, f);
+        int oob = drift_off_track(c, e->p[0], e->p[1]);
+        drift_reward_terms(c, e, e->p, vb, b.wb, e->w[2], oob, time_out, f);
+        tmask = (time_out ? 1u : 0u) | (oob ? 2u : 0u);
+    } else if (c->task == WL_TASK_ELEVATION) {
+        tmask = elev_terms(c, e, R, vb, (e->omega[0] + e->omega[1]) + (e->omega[2] + e->omega[3]), time_out, f);
     } else {
         return WL_EUNSUPPORTED;
     }
@@ -652,12 +755,19 @@ static int env_step(wlo_sim* s, int li, const float* a_in, int64_t t, float* obs
         e->sums[k] += val;
     }
     *rew = (float)total;
-    *term_o = (uint8_t)terminated; *trunc_o = (uint8_t)time_out;
+    *term_o = (uint8_t)((tmask & ~1u) ? 1 : 0); *trunc_o = (uint8_t)(tmask & 1u);
     /* F. auto reset */
-    if (terminated || time_out) {
-        lg->any = 1; lg->n_reset += 1.0; lg->n_term += terminated ? 1.0 : 0.0; lg->n_timeout += time_out ? 1.0 : 0.0;
+    if (tmask) {
+        lg->any = 1; lg->n_reset += 1.0;
+        for (int j = 0; j < WL_MAX_TERM_TERMS; ++j) lg->n_term[j] += ((tmask >> j) & 1u) ? 1.0 : 0.0;
         for (int k = 0; k < WL_MAX_REW_TERMS; ++k) lg->sum[k] += (double)e->sums[k];
-        drift_reset_env(c, e, gid, t);
+        if (c->task == WL_TASK_ELEVATION) elev_reset_env(c, e, gid, t); else drift_reset_env(c, e, gid, t);
+    }
+    if (c->task == WL_TASK_ELEVATION) {
+        /* G. commands; I. observations */
+        elev_command_update(c, e, gid, t, step_dt);
+        elev_obs(s, e, obs);
+        return 0;
     }
     /* H. interval events on the post-reset state */
     interval_pushes(c, e, gid, t, step_dt);
@@ -676,7 +786,7 @@ wlo_sim* wlo_create(const wl_config* cfg, const float* heightfield) {
     s->env = (wlo_env*)calloc((size_t)cfg->num_envs, sizeof(wlo_env));
     for (int k = 0; k < WL_MAX_REW_TERMS; ++k) s->rew_weight[k] = (real)cfg->rew_weight[k];
     if (heightfield && cfg->hf_nx > 0) {
-        size_t n = (size_t)cfg->hf_nx * cfg->hf_ny;
+        size_t n = (size_t)cfg->hf_pitch * cfg->hf_ny;
         s->hf = (float*)malloc(n * sizeof(float));
         memcpy(s->hf, heightfield, n * sizeof(float));
     }
@@ -721,11 +831,11 @@ int wlo_startup(wlo_sim* s) {
 
 int wlo_reset(wlo_sim* s, const int64_t* env_ids, int32_t n_ids, int64_t step_counter) {
     const wl_config* c = &s->cfg;
-    if (c->task != WL_TASK_DRIFT) return WL_EUNSUPPORTED;
     int n = env_ids ? n_ids : c->num_envs;
     for (int k = 0; k < n; ++k) {
         int li = env_ids ? (int)env_ids[k] : k;
-        drift_reset_env(c, &s->env[li], (uint32_t)(c->env_id_offset + li), step_counter);
+        if (c->task == WL_TASK_ELEVATION) elev_reset_env(c, &s->env[li], (uint32_t)(c->env_id_offset + li), step_counter);
+        else drift_reset_env(c, &s->env[li], (uint32_t)(c->env_id_offset + li), step_counter);
     }
     return 0;
 }
@@ -755,18 +865,23 @@ int wlo_step(wlo_sim* s, const float* action, float* obs, float* rew, uint8_t* t
 #endif
         {
             for (int k = 0; k < WL_MAX_REW_TERMS; ++k) tot.sum[k] += lg.sum[k];
-            tot.n_reset += lg.n_reset; tot.n_term += lg.n_term; tot.n_timeout += lg.n_timeout; tot.any |= lg.any;
+            tot.n_reset += lg.n_reset; tot.any |= lg.any;
+            for (int j = 0; j < WL_MAX_TERM_TERMS; ++j) tot.n_term[j] += lg.n_term[j];
         }
     }
     for (int k = 0; k < WL_MAX_REW_TERMS; ++k) s->log_sum[k] = tot.sum[k];
-    s->log_term[0] = tot.n_reset; s->log_term[1] = tot.n_term; s->log_term[2] = tot.n_timeout;
+    s->log_term[0] = tot.n_reset;
+    for (int j = 0; j < WL_MAX_TERM_TERMS; ++j) s->log_term[1 + j] = tot.n_term[j];
     s->any_reset_last = tot.any;
     return err;
 }
 
 int wlo_observe(wlo_sim* s, float* obs, int64_t step_counter, int32_t call_idx) {
     const wl_config* c = &s->cfg;
-    if (c->task != WL_TASK_DRIFT) return WL_EUNSUPPORTED;
+    if (c->task == WL_TASK_ELEVATION) {
+        for (int li = 0; li < c->num_envs; ++li) elev_obs(s, &s->env[li], obs + (size_t)WL_OBS_DIM_ELEV * li);
+        return 0;
+    }
     for (int li = 0; li < c->num_envs; ++li)
         blind_obs(c, &s->env[li], (uint32_t)(c->env_id_offset + li), (uint32_t)step_counter, RNG_OBS_EXTRA,
                   3u * (uint32_t)call_idx, obs + (size_t)WL_OBS_DIM_BLIND * li);
@@ -819,6 +934,7 @@ void wlo_export_state(const wlo_sim* s, float* buf) {
         g = grp(buf, WL_G_PMU_C, n, i); for (int k = 0; k < 4; ++k) g[k] = (float)e->C[k];
         g = grp(buf, WL_G_PKD, n, i); for (int k = 0; k < 4; ++k) g[k] = (float)e->kd[k];
         g = grp(buf, WL_G_CMD, n, i); for (int k = 0; k < 4; ++k) g[k] = (float)e->cmd[k];
+        g = grp(buf, WL_G_CMDB, n, i); for (int k = 0; k < 4; ++k) g[k] = (float)e->cmdb[k];
     }
 }
 void wlo_import_state(wlo_sim* s, const float* cbuf) {
@@ -840,6 +956,7 @@ void wlo_import_state(wlo_sim* s, const float* cbuf) {
         g = grp(buf, WL_G_PMU_C, n, i); for (int k = 0; k < 4; ++k) e->C[k] = g[k];
         g = grp(buf, WL_G_PKD, n, i); for (int k = 0; k < 4; ++k) e->kd[k] = g[k];
         g = grp(buf, WL_G_CMD, n, i); for (int k = 0; k < 4; ++k) e->cmd[k] = g[k];
+        g = grp(buf, WL_G_CMDB, n, i); for (int k = 0; k < 4; ++k) e->cmdb[k] = g[k];
     }
 }
 void wlo_get_weights(const wlo_sim* s, float* w) { for (int k = 0; k < WL_MAX_REW_TERMS; ++k) w[k] = (float)s->rew_weight[k]; }
@@ -849,7 +966,7 @@ void wlo_set_weights(wlo_sim* s, const float* w) { for (int k = 0; k < WL_MAX_RE
 void wlo_get_log(const wlo_sim* s, double* out) {
     double cnt = s->log_term[0] > 1.0 ? s->log_term[0] : 1.0;
     for (int k = 0; k < WL_MAX_REW_TERMS; ++k) out[k] = s->log_sum[k] / (cnt * (double)s->cfg.episode_length_s);
-    out[8] = s->log_term[0]; out[9] = s->log_term[1]; out[10] = s->log_term[2];
+    for (int j = 0; j < 8; ++j) out[8 + j] = s->log_term[j];
 }
 
 /* ---- unit-level hooks for golden-vector and det-math tests -------------------- */
@@ -912,6 +1029,33 @@ int wlo_drift_reset_pose(const wl_config* c, const int32_t* idx, const float* u_
         drift_reset_pose(c, &e, (uint32_t)idx[i], (real)u_xy[2 * i], (real)u_xy[2 * i + 1], (real)u_yaw[i]);
         for (int k = 0; k < 3; ++k) pose[7 * i + k] = (float)e.p[k];
         for (int k = 0; k < 4; ++k) pose[7 * i + 3 + k] = (float)e.q[k];
+    }
+    return 0;
+}
+/* elevation MDP terms on given states: root[n,13] = pos3 quat4 linvel_w3 angvel_w3, cmdb[n,2], omega[n,4];
+ * out f[n,8] unweighted reward terms, mask[n] termination bits, proprio[n,13] observation head */
+int wlo_elev_terms(const wl_config* c_in, const float* root, const float* cmdb, const float* omega, const float* action,
+                   const int32_t* ep_len, float* f_out, uint32_t* mask, float* proprio, int32_t n) {
+    wl_config cc = *c_in; config_finalize(&cc); const wl_config* c = &cc;
+    for (int i = 0; i < n; ++i) {
+        wlo_env e; memset(&e, 0, sizeof e);
+        const float* r = root + 13 * i;
+        for (int k = 0; k < 3; ++k) { e.p[k] = r[k]; e.v[k] = r[7 + k]; e.w[k] = r[10 + k]; }
+        for (int k = 0; k < 4; ++k) { e.q[k] = r[3 + k]; e.omega[k] = omega[4 * i + k]; }
+        e.cmdb[0] = cmdb[2 * i]; e.cmdb[1] = cmdb[2 * i + 1];
+        e.action[0] = action[2 * i]; e.action[1] = action[2 * i + 1];
+        real R[9]; rotmat(e.q, R);
+        real vb[3]; rotT(R, e.v, vb);
+        real f[WL_MAX_REW_TERMS];
+        mask[i] = elev_terms(c, &e, R, vb, (e.omega[0] + e.omega[1]) + (e.omega[2] + e.omega[3]), ep_len[i] >= c->max_episode_length, f);
+        for (int k = 0; k < WL_MAX_REW_TERMS; ++k) f_out[WL_MAX_REW_TERMS * i + k] = (float)f[k];
+        /* proprio head only (no height-field needed) */
+        real wb[3], eu[3]; rotT(R, e.w, wb); euler_xyz(e.q, eu);
+        real gx = e.cmdb[0] - e.p[0], gy = e.cmdb[1] - e.p[1], cl = (real)c->obs_clip;
+        float* o = proprio + 13 * i;
+        o[0] = (float)((gx != gx) ? K(0.0) : gx); o[1] = (float)((gy != gy) ? K(0.0) : gy);
+        for (int k = 0; k < 3; ++k) { o[2 + k] = (float)eu[k]; o[5 + k] = (float)r_clamp(vb[k], -cl, cl); o[8 + k] = (float)r_clamp(wb[k], -cl, cl); }
+        o[11] = (float)r_clamp(e.action[0], K(-1.0), K(1.0)); o[12] = (float)r_clamp(e.action[1], K(-1.0), K(1.0));
     }
     return 0;
 }

@@ -113,7 +113,7 @@ def golden_actions():
     term.process_actions(a.clone()); term.apply_actions()
     out["ack_wheel"] = env.scene["robot"].captured["vel"].numpy()
     out["ack_steer"] = env.scene["robot"].captured["pos"].numpy()
-    np.savez(HERE / "actions.npz", **out)
+    np.savez_compressed(HERE / "actions.npz", **out)
 
 
 def golden_drift_terms():
@@ -144,7 +144,7 @@ def golden_drift_terms():
     env.termination_manager.time_outs = (torch.arange(n) % 7 == 0)
     out["time_outs"] = env.termination_manager.time_outs.numpy().astype(np.uint8)
     out["f_term_pens"] = R.term_pens.func(env, **R.term_pens.params).numpy()
-    np.savez(HERE / "drift_terms.npz", **out)
+    np.savez_compressed(HERE / "drift_terms.npz", **out)
 
 
 def golden_reset_along_track():
@@ -168,7 +168,7 @@ def golden_reset_along_track():
     out["pose"] = env.scene["robot"].captured["pose"].numpy()
     out["velocity"] = env.scene["robot"].captured["velocity"].numpy()
     out["pos_noise"], out["yaw_noise"] = np.float32(cfg.params["pos_noise"]), np.float32(cfg.params["yaw_noise"])
-    np.savez(HERE / "reset_along_track.npz", **out)
+    np.savez_compressed(HERE / "reset_along_track.npz", **out)
 
 
 def golden_curriculum():
@@ -184,7 +184,7 @@ def golden_curriculum():
                 t = getattr(C, name)
                 t.func(env, torch.arange(4), **t.params)
             rows.append((c, env.reward_manager.w["side_slip"], env.reward_manager.w["tlgr"], env.reward_manager.w["term_pens"]))
-    np.savez(HERE / "curriculum.npz", rows=np.array(rows, dtype=np.float64))
+    np.savez_compressed(HERE / "curriculum.npz", rows=np.array(rows, dtype=np.float64))
 
 
 def golden_euler():
@@ -195,10 +195,73 @@ def golden_euler():
     env = FakeEnv(q.shape[0])
     env.scene["robot"].data.root_quat_w = q
     e = wmdp.root_euler_xyz(env)
-    np.savez(HERE / "euler.npz", quat=q.numpy(), euler=e.numpy())
+    np.savez_compressed(HERE / "euler.npz", quat=q.numpy(), euler=e.numpy())
+
+
+def golden_elevation():
+    """Elevation task term functions of the reference (mushr_elevation_env_cfg.py) on random states."""
+    from wheeledlab_tasks.elevation import mushr_elevation_env_cfg as E
+    from isaaclab.managers import SceneEntityCfg
+    n = 1024
+    g = torch.Generator().manual_seed(9)
+    pos = torch.cat([torch.rand(n, 2, generator=g) * 38 - 19, torch.rand(n, 1, generator=g) * 0.6 + 0.05], -1)
+    rpy = torch.randn(n, 3, generator=g) * torch.tensor([0.5, 0.5, 2.0])
+    quat = math_utils.quat_from_euler_xyz(rpy[:, 0], rpy[:, 1], rpy[:, 2])
+    vel_w = torch.randn(n, 3, generator=g) * torch.tensor([1.0, 1.0, 0.3])
+    ang_w = torch.randn(n, 3, generator=g)
+    cmd = torch.zeros(n, 4); cmd[:, :2] = torch.rand(n, 2, generator=g) * 8 - 4
+    cmd[:64, :2] = pos[:64, :2] + (torch.rand(64, 2, generator=g) - 0.5) * 0.6          # some envs close to the goal
+    omega = torch.randn(n, 4, generator=g) * 4 + 1.0
+    action = torch.randn(n, 2, generator=g)
+    env = FakeEnv(n)
+    d = env.scene["robot"].data
+    d.root_pos_w, d.root_quat_w, d.root_lin_vel_w = pos, quat, vel_w
+    d.root_lin_vel_b = math_utils.quat_rotate_inverse(quat, vel_w)
+    d.root_ang_vel_b = math_utils.quat_rotate_inverse(quat, ang_w)
+    d.joint_vel = torch.zeros(n, 12); d.joint_vel[:, 0:4] = omega
+    env.command_manager = types.SimpleNamespace(get_command=lambda name: cmd)
+    env.action_manager.action = action
+    out = {"pos": pos.numpy(), "quat": quat.numpy(), "vel_w": vel_w.numpy(), "ang_w": ang_w.numpy(), "cmd": cmd.numpy(),
+           "omega": omega.numpy(), "action": action.numpy()}
+    R, T, O = E.ElevationRewardsCfg(), E.ElevationTerminationsCfg(), E.ElevationObsCfg().policy
+    out["f_goal"] = R.vel_towards_goal.func(env).numpy()
+    out["f_height"] = R.height_z.func(env).numpy()
+    out["f_falling"] = R.falling_penalty.func(env).float().numpy()
+    out["weights"] = np.array([R.vel_towards_goal.weight, R.height_z.weight, R.falling_penalty.weight, R.termination_penalty.weight], np.float32)
+    out["t_oob"] = T.cart_out_of_bounds.func(env, **T.cart_out_of_bounds.params).numpy().astype(np.uint8)
+    stuck_cfg = SceneEntityCfg("robot", joint_names=".*throttle")
+    # the stuck term resolves SceneEntityCfg("robot", joint_names=".*throttle") through the manager; do it by hand here
+    import isaaclab.envs.mdp as imdp
+    orig_joint_vel = imdp.joint_vel
+    imdp.joint_vel = lambda env, asset_cfg=None: env.scene["robot"].data.joint_vel[:, 0:4]
+    E.mdp.joint_vel = imdp.joint_vel
+    out["t_stuck"] = T.stuck.func(env, **T.stuck.params).numpy().astype(np.uint8)
+    imdp.joint_vel = orig_joint_vel; E.mdp.joint_vel = orig_joint_vel
+    out["t_rollover"] = T.rollover.func(env, **T.rollover.params).numpy().astype(np.uint8)
+    out["t_at_goal"] = T.at_goal.func(env, **T.at_goal.params).numpy().astype(np.uint8)
+    out["o_goal"] = O.goal_relative_xyz.func(env).numpy()
+    out["o_euler"] = O.world_euler_xyz.func(env).numpy()
+    clip = O.base_lin_vel.clip
+    out["o_linvel"] = torch.clip(O.base_lin_vel.func(env), clip[0], clip[1]).numpy()
+    out["o_angvel"] = torch.clip(O.base_ang_vel.func(env), clip[0], clip[1]).numpy()
+    out["o_action"] = torch.clip(O.last_action.func(env), -1, 1).numpy()
+    # height map formula/sign/clip on synthetic hits: sensor.data.pos_w = ray-caster parent (base_link), hits = terrain z
+    sens = types.SimpleNamespace(data=types.SimpleNamespace())
+    sens.data.pos_w = pos + torch.tensor([0.0, 0.0, 0.094655])
+    hits = torch.rand(n, 676, 3, generator=g) * 2.0
+    hits[:, ::7, 2] = float("inf")                                        # misses
+    sens.data.ray_hits_w = hits
+    env.scene.sensors = {"height_scanner": sens}
+    p = O.elevation_map.params
+    hm = O.elevation_map.func(env, **p)
+    out["hm_hits_z"] = hits[:64, :, 2].numpy(); out["hm_pos_z"] = pos[:64, 2].numpy()
+    out["hm_out"] = torch.clip(hm, O.elevation_map.clip[0], O.elevation_map.clip[1])[:64].numpy()
+    out["hm_offset"], out["hm_plane"] = np.float32(p["offset"]), np.float32(p["plane_init_value"])
+    np.savez_compressed(HERE / "elevation_terms.npz", **out)
 
 
 if __name__ == "__main__":
+    golden_elevation()
     golden_actions(); golden_drift_terms(); golden_reset_along_track(); golden_curriculum(); golden_euler()
     for f in sorted(HERE.glob("*.npz")):
         print(f.name, f.stat().st_size)

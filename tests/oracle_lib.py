@@ -39,6 +39,7 @@ def _load(name):
     lib.wlo_drift_terms.argtypes = [vp, vp, vp, vp, vp, vp, i32]
     lib.wlo_euler_xyz.argtypes = [vp, vp, i32]
     lib.wlo_drift_reset_pose.argtypes = [vp, vp, vp, vp, vp, i32]
+    lib.wlo_elev_terms.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32]
     lib.wlo_config_describe.restype = C.c_char_p
     return lib
 
@@ -57,7 +58,7 @@ def _p(a):
     return C.c_void_p(a.ctypes.data) if a is not None else None
 
 
-NUM_GROUPS = 14
+NUM_GROUPS = 15
 
 
 class Oracle:
@@ -133,7 +134,7 @@ class Oracle:
         self.lib.wlo_set_weights(self._h, _p(w))
 
     def log(self):
-        out = np.zeros(11, np.float64)
+        out = np.zeros(16, np.float64)
         self.lib.wlo_get_log(self._h, _p(out))
         return out
 
@@ -188,3 +189,13 @@ def drift_reset_pose(cfg, idx, u_xy, u_yaw):
     pose = np.empty((idx.shape[0], 7), np.float32)
     assert get_lib().wlo_drift_reset_pose(C.byref(cfg), _p(idx), _p(u_xy), _p(u_yaw), _p(pose), idx.shape[0]) == 0
     return pose
+
+
+def elev_terms(cfg, root, cmdb, omega, action, ep_len):
+    root = np.ascontiguousarray(root, np.float32); cmdb = np.ascontiguousarray(cmdb, np.float32)
+    omega = np.ascontiguousarray(omega, np.float32); action = np.ascontiguousarray(action, np.float32)
+    ep = np.ascontiguousarray(ep_len, np.int32)
+    n = root.shape[0]
+    f = np.empty((n, 8), np.float32); mask = np.empty(n, np.uint32); prop = np.empty((n, 13), np.float32)
+    assert get_lib().wlo_elev_terms(C.byref(cfg), _p(root), _p(cmdb), _p(omega), _p(action), _p(ep), _p(f), _p(mask), _p(prop), n) == 0
+    return f, mask, prop

@@ -120,3 +120,58 @@ def test_root_euler_xyz_matches_reference():
     sp = 2 * (g["quat"][:, 0] * g["quat"][:, 2] - g["quat"][:, 3] * g["quat"][:, 1])
     ok = np.abs(sp) < 0.999
     assert d[ok].max() < 5e-6 and d.max() < 2e-3
+
+
+def test_elevation_terms_match_reference():
+    """mushr_elevation_env_cfg.py reward / termination / observation term functions (reference outputs)."""
+    import wheeledlab_b200 as wl
+    g = np.load(G / "elevation_terms.npz")
+    cfg = wl.elevation_task(num_envs=4).cfg
+    n = g["pos"].shape[0]
+    root = np.concatenate([g["pos"], g["quat"], g["vel_w"], g["ang_w"]], axis=1).astype(np.float32)
+    f, mask, prop = O.elev_terms(cfg, root, g["cmd"][:, :2], g["omega"], g["action"], np.zeros(n, np.int32))
+    gvec = g["cmd"][:, :2] - g["pos"][:, :2]
+    assert np.allclose(f[:, 0], g["f_goal"], rtol=2e-5, atol=2e-5)
+    # thresholded terms: compare away from float ties of the body-frame velocity (rotation helpers differ by ulps)
+    R = None
+    assert (np.abs(f[:, 1] - g["f_height"]) > 1e-5).mean() < 0.01
+    assert (f[:, 2] != g["f_falling"]).mean() < 0.005
+    assert np.array_equal((mask >> 1) & 1, g["t_oob"])
+    assert (((mask >> 2) & 1) != g["t_stuck"]).mean() < 0.005
+    assert (((mask >> 3) & 1) != g["t_rollover"]).mean() < 0.005
+    assert np.array_equal((mask >> 4) & 1, g["t_at_goal"]) and g["t_at_goal"].sum() > 10
+    assert g["t_stuck"].sum() > 5 and g["t_rollover"].sum() > 50
+    assert np.allclose(list(cfg.rew_weight)[:4], g["weights"])
+    # observation head
+    assert np.allclose(prop[:, 0:2], g["o_goal"], atol=1e-5)
+    d = np.abs(prop[:, 2:5] - g["o_euler"]); d = np.minimum(d, 2 * np.pi - d)
+    sp = 2 * (g["quat"][:, 0] * g["quat"][:, 2] - g["quat"][:, 3] * g["quat"][:, 1])
+    assert d[np.abs(sp) < 0.999].max() < 5e-6
+    assert np.allclose(prop[:, 5:8], g["o_linvel"], atol=2e-6) and np.allclose(prop[:, 8:11], g["o_angvel"], atol=2e-6)
+    assert np.array_equal(prop[:, 11:13], g["o_action"])
+
+
+def test_elevation_height_map_formula_matches_reference():
+    """world_height_map sign / offsets / clipping (mushr_elevation_env_cfg.py:44-48,74-82) on a flat raster: the oracle's
+    ray-cast observation must equal the reference function evaluated on the same hits."""
+    import wheeledlab_b200 as wl
+    g = np.load(G / "elevation_terms.npz")
+    assert g["hm_offset"] == np.float32(0.084) and g["hm_plane"] == np.float32(0.19)
+    hits, pz, ref = g["hm_hits_z"], g["hm_pos_z"], g["hm_out"]
+    # reference: -(pos_w.z - hit - offset) + (root_z - plane), clipped to +-10, miss -> +10
+    bz = pz[:, None] + np.float32(0.094655)
+    mine = np.clip(-(bz - hits - np.float32(0.084)) + (pz[:, None] - np.float32(0.19)), -10, 10)
+    assert np.allclose(mine, ref, atol=1e-6) and (ref[:, ::7] == 10).all()
+    # and the oracle on a constant-height raster reproduces it (upright car, identity yaw)
+    for h0 in (0.2, 1.3):
+        hf = np.full((411, 411), h0, np.float32)
+        spec = wl.elevation_task(num_envs=2, heightfield=hf, hf_origin=(-20.5, -20.5))
+        o = O.Oracle(spec.cfg, heightfield=spec.heightfield); o.startup()
+        st = o.export_state(); st[0, :, 0:3] = (1.0, -2.0, 0.27); st[1, :, 0] = 1.0
+        st[0, 1, 0] = 20.0                                   # env 1 near the +x edge: part of the grid misses
+        o.import_state(st)
+        obs = o.observe(0)
+        exp = np.float32(h0) - (np.float32(0.27) + np.float32(0.094655)) + np.float32(0.084) + (np.float32(0.27) - np.float32(0.19))
+        assert np.allclose(obs[0, 13:], exp, atol=1e-6)
+        scan1 = obs[1, 13:].reshape(26, 26)
+        assert (scan1[:, -7:] == 10).all() and np.allclose(scan1[:, :18], exp, atol=1e-6)

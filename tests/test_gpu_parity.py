@@ -253,3 +253,68 @@ def test_cuda_graph_replay_matches_eager():
         for x, y in zip(outs_a[t], bufs[t]):
             assert torch.equal(x, y)
     assert torch.equal(a.groups, b.groups)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Elevation task (BASELINE config 3): height-field contact, goal command, 26x26 TMA-staged ray-cast observation
+# ---------------------------------------------------------------------------------------------------------------
+def _elev_pair(n, seed=42):
+    import wheeledlab_b200 as wl
+    spec = wl.elevation_task(num_envs=n, seed=seed)
+    sim = wl.WheeledSim(spec, "cuda:0")
+    sim.startup(); sim.reset(None, 0)
+    orc = O.Oracle(spec.cfg, heightfield=spec.heightfield)
+    orc.startup(); orc.reset(None, 0)
+    return spec, sim, orc
+
+
+@pytest.mark.parametrize("variant,tma", [(1, True), (4, True), (4, False)])
+def test_elevation_trajectory_bit_exact(variant, tma):
+    _need_gpu()
+    n, steps = 96, 260
+    spec, sim, orc = _elev_pair(n)
+    sim.set_kernel_variant(variant); sim.set_scan_tma(tma)
+    assert sim.obs_dim == 689
+    a0 = sim.observe(0).cpu().numpy()
+    assert np.array_equal(_bits(a0), _bits(orc.observe(0)))
+    counts = np.zeros(5)
+    for t in range(steps):
+        act = sim.synth_actions(t)
+        log = torch.empty(16, device="cuda")
+        obs, rew, term, trunc = sim.step(act, t, log=log)
+        o_obs, o_rew, o_term, o_trunc = orc.step(act.cpu().numpy(), t)
+        torch.cuda.synchronize()
+        assert np.array_equal(term.cpu().numpy(), o_term) and np.array_equal(trunc.cpu().numpy(), o_trunc), t
+        assert np.array_equal(_bits(rew.cpu().numpy()), _bits(o_rew)), f"reward differs at step {t}"
+        got = obs.cpu().numpy()
+        assert np.array_equal(_bits(got[:, :13]), _bits(o_obs[:, :13])), f"proprio obs differs at step {t}"
+        assert np.array_equal(_bits(got[:, 13:]), _bits(o_obs[:, 13:])), f"height scan differs at step {t}"
+        lg = orc.log(); counts += lg[9:14]
+        assert np.array_equal(log.cpu().numpy()[8:14], lg[8:14].astype(np.float32))
+        if t % 65 == 0 or t == steps - 1:
+            assert np.array_equal(_bits(_state_groups(sim)), _bits(orc.export_state())), f"state differs at step {t}"
+    assert counts[0] > 0 and counts[2] > 0 and counts.sum() >= n        # time-outs, stuck, ... all exercised
+    sc = got[:, 13:]
+    assert sc.max() <= 10 and sc.min() >= -10 and (np.abs(sc) < 9.9).mean() > 0.5
+
+
+def test_elevation_full_size_properties():
+    """RSS_ELEV_CONFIG size (4096 envs): env surface, obs width 689, scan/clip bounds, reset semantics."""
+    _need_gpu()
+    import wheeledlab_b200 as wl
+    env = wl.make("Isaac-MushrElevationRL-v0", num_envs=4096, seed=42)
+    obs, _ = env.reset()
+    assert obs["policy"].shape == (4096, 689) and env.max_episode_length == 200
+    prev = env.episode_length_buf.clone()
+    for t in range(60):
+        obs, rew, term, trunc, extras = env.step(env.sim.synth_actions(t))
+        done = term | trunc
+        ep = env.episode_length_buf
+        assert torch.equal(ep == 0, done) and torch.equal(ep[~done], prev[~done] + 1)
+        o = obs["policy"]
+        assert torch.isfinite(o).all() and o[:, 5:].abs().max() <= 10.0
+        z = env.scene["robot"].data.root_pos_w[:, 2]
+        assert torch.allclose(z[done], torch.full_like(z[done], 0.25))          # respawn at default root z (:147-149)
+        prev = ep.clone()
+    assert "Episode_Termination/stuck" in extras["log"] and env.command_manager.get_command("goal_pose").shape == (4096, 4)
+    env.close()

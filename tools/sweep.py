@@ -14,8 +14,13 @@ import wheeledlab_b200 as wl  # noqa: E402
 from bench import BYTES_PER_ENV_STEP, _peaks  # noqa: E402
 
 
+TASK = "drift"
+BYTES = {"drift": BYTES_PER_ENV_STEP, "elevation": (15 * 16 + 8) + (11 * 16 + 689 * 4 + 4 + 2)}
+
+
 def one(n, steps, warm, flush):
-    sim = wl.WheeledSim(wl.drift_task(num_envs=n, seed=42), "cuda:0")
+    spec = wl.drift_task(num_envs=n, seed=42) if TASK == "drift" else wl.elevation_task(num_envs=n, seed=42)
+    sim = wl.WheeledSim(spec, "cuda:0")
     sim.startup(); sim.reset(None, 0)
     acts = [sim.synth_actions(t) for t in range(4)]
     outs = tuple(torch.empty_like(x) for x in sim.step(acts[0], 0))
@@ -31,7 +36,7 @@ def one(n, steps, warm, flush):
     ms = [a.elapsed_time(b) for a, b in ev]
     med = statistics.median(ms)
     return {"envs": n, "kernel_us_median": med * 1e3, "kernel_us_min": min(ms) * 1e3,
-            "env_steps_per_s": n / (med * 1e-3), "achieved_GBps": BYTES_PER_ENV_STEP * n / (med * 1e-3) / 1e9}
+            "env_steps_per_s": n / (med * 1e-3), "achieved_GBps": BYTES[TASK] * n / (med * 1e-3) / 1e9}
 
 
 def main():
@@ -40,7 +45,10 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warm", type=int, default=5)
     ap.add_argument("--no-flush", action="store_true")
+    ap.add_argument("--task", default="drift", choices=["drift", "elevation"])
     a = ap.parse_args()
+    global TASK
+    TASK = a.task
     peak, src = _peaks()
     flush = None if a.no_flush else torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda:0")
     rows = []
@@ -49,7 +57,8 @@ def main():
         r["frac_of_peak"] = r["achieved_GBps"] / peak
         rows.append(r)
         print(json.dumps(r), file=sys.stderr, flush=True)
-    print(json.dumps({"kernel": "wl_step_kernel<DRIFT>", "bytes_per_env_step": BYTES_PER_ENV_STEP, "peak_GBps": peak,
+    print(json.dumps({"kernel": f"wl_step[_quad]_kernel<{TASK}>" + (" + wl_scan_kernel<TMA>" if TASK == "elevation" else ""),
+                      "bytes_per_env_step": BYTES[TASK], "peak_GBps": peak,
                       "peak_source": src, "l2_flush_between_launches": not a.no_flush, "rows": rows}))
 
 

@@ -6,6 +6,8 @@
 #include <new>
 #include <string>
 
+#include <cuda.h>
+
 #include "wl_step.cuh"
 
 using namespace wl;
@@ -22,6 +24,9 @@ struct wl_sim {
     int64_t launches;
     int obs_dim;
     int variant;            // 0 auto, 1 thread-per-env, 4 quad-per-env
+    CUtensorMap tmap;       // 2-D tensor map over the height-field (elevation task)
+    bool has_tmap;
+    bool scan_tma;          // ray-cast tile staged by TMA (true) or by plain loads (false; A/B + fallback for tests)
 };
 
 // below this many envs one thread/env cannot fill 148 SMs x 4 schedulers; use 4 lanes per env
@@ -47,21 +52,22 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 // Per-step episode log: warp-shuffle reduce over the finished envs, one atomic set per warp.
-__device__ __forceinline__ void log_accumulate(wl_globals* __restrict__ gl, bool contrib, bool terminated, bool time_out,
+// acc layout: [0..7] episode sums, [8] #reset, [9+j] #envs whose termination term j fired (tmask bit j).
+__device__ __forceinline__ void log_accumulate(wl_globals* __restrict__ gl, bool contrib, uint32_t tmask,
                                                const float sums[WL_MAX_REW_TERMS]) {
     const unsigned any_c = __ballot_sync(0xffffffffu, contrib);
     if (!any_c) return;
-    float vals[WL_MAX_REW_TERMS + 3];
+    float vals[16];
 #pragma unroll
     for (int k = 0; k < WL_MAX_REW_TERMS; ++k) vals[k] = contrib ? sums[k] : 0.0f;
-    vals[WL_MAX_REW_TERMS + 0] = contrib ? 1.0f : 0.0f;
-    vals[WL_MAX_REW_TERMS + 1] = (contrib && terminated) ? 1.0f : 0.0f;
-    vals[WL_MAX_REW_TERMS + 2] = (contrib && time_out) ? 1.0f : 0.0f;
+    vals[8] = contrib ? 1.0f : 0.0f;
 #pragma unroll
-    for (int k = 0; k < WL_MAX_REW_TERMS + 3; ++k) vals[k] = warp_sum(vals[k]);
+    for (int j = 0; j < WL_MAX_TERM_TERMS; ++j) vals[9 + j] = (contrib && ((tmask >> j) & 1u)) ? 1.0f : 0.0f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) vals[k] = warp_sum(vals[k]);
     if ((threadIdx.x & 31) == 0) {
 #pragma unroll
-        for (int k = 0; k < WL_MAX_REW_TERMS + 3; ++k) atomicAdd(&gl->acc[k], vals[k]);
+        for (int k = 0; k < 16; ++k) if (vals[k] != 0.0f) atomicAdd(&gl->acc[k], vals[k]);
     }
 }
 // Last CTA of the launch turns the accumulators into the extras["log"] row and re-arms them.
@@ -72,21 +78,20 @@ __device__ __forceinline__ void log_finalize(const wl_config& c, wl_globals* __r
     const unsigned tk = atomicAdd(&gl->ticket, 1u);
     if (tk != gridDim.x - 1) return;
     __threadfence();
-    float a[WL_MAX_REW_TERMS + 3];
+    float a[16];
 #pragma unroll
-    for (int k = 0; k < WL_MAX_REW_TERMS + 3; ++k) a[k] = __ldcg(&gl->acc[k]);
-    const float cnt = a[WL_MAX_REW_TERMS];
+    for (int k = 0; k < 16; ++k) a[k] = __ldcg(&gl->acc[k]);
+    const float cnt = a[8];
     if (d_log != nullptr) {
         const float denom = r_max(cnt, 1.0f) * c.episode_length_s;
 #pragma unroll
         for (int k = 0; k < WL_MAX_REW_TERMS; ++k) d_log[k] = a[k] / denom;
-        d_log[8] = a[8]; d_log[9] = a[9]; d_log[10] = a[10];
 #pragma unroll
-        for (int k = 11; k < WL_LOG_FLOATS; ++k) d_log[k] = 0.0f;
+        for (int k = 8; k < 16; ++k) d_log[k] = a[k];
     }
     gl->any_reset_last = (cnt > 0.0f) ? 1 : 0;
 #pragma unroll
-    for (int k = 0; k < 12; ++k) gl->acc[k] = 0.0f;
+    for (int k = 0; k < 16; ++k) gl->acc[k] = 0.0f;
     gl->ticket = 0u;
 }
 
@@ -96,12 +101,14 @@ __global__ void __launch_bounds__(128, 4)
 wl_step_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st, wl_globals* __restrict__ gl, Terrain T,
                const float2* __restrict__ action, float* __restrict__ obs, float* __restrict__ rew,
                uint8_t* __restrict__ terminated_o, uint8_t* __restrict__ truncated_o, float* __restrict__ d_log, uint32_t t) {
+    constexpr bool ELEV = (TASK == WL_TASK_ELEVATION);
     const int n = c.num_envs;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    bool done = false, terminated = false, time_out = false;
+    bool done = false;
+    uint32_t tmask = 0u;
     EnvState e;
     if (i < n) {
-        load_env(st, n, i, e, TASK == WL_TASK_ELEVATION);
+        load_env(st, n, i, e, ELEV);
         // A. action manager
         float2 a = action[i];
         e.prev_action[0] = e.action[0]; e.prev_action[1] = e.action[1];
@@ -127,43 +134,50 @@ wl_step_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st, wl_
         e.p = V3{b.pc.x - cw.x, b.pc.y - cw.y, b.pc.z - cw.z};
         e.v = b.v; e.qw = b.qw; e.qx = b.qx; e.qy = b.qy; e.qz = b.qz;
         e.w = rot(R, b.wb);
-        // C. counters
+        // C. counters   D. terminations   E. rewards (value = f*w*dt, skipped when w == 0)
         e.ep_len += 1;
-        // D. terminations
-        time_out = e.ep_len >= c.max_episode_length;
-        const float step_dt = c.d_step_dt;
+        const bool time_out = e.ep_len >= c.max_episode_length;
         float f[WL_MAX_REW_TERMS];
         V3 vb = rotT(R, e.v);
-        if (TASK == WL_TASK_DRIFT) {
-            terminated = drift_off_track(c, e.p.x, e.p.y);
-            drift_reward_terms(c, e.steer[0], e.steer[1], det_atan2(vb.y, vb.x), e.p, vb, b.wb, e.w.z, terminated, time_out, f);
+        if (ELEV) {
+            tmask = elev_terms(c, e, R, vb, (e.omega[0] + e.omega[1]) + (e.omega[2] + e.omega[3]), time_out, f);
+        } else {
+            const bool oob = drift_off_track(c, e.p.x, e.p.y);
+            drift_reward_terms(c, e.steer[0], e.steer[1], det_atan2(vb.y, vb.x), e.p, vb, b.wb, e.w.z, oob, time_out, f);
+            tmask = (time_out ? 1u : 0u) | (oob ? 2u : 0u);
         }
-        // E. rewards: value = f*w*dt, skipped when w == 0
         float total = 0.0f;
 #pragma unroll
         for (int k = 0; k < WL_MAX_REW_TERMS; ++k) {
             if (k < c.num_rew_terms) {
                 float w = __ldg(&gl->rew_weight[k]);
-                if (w != 0.0f) { float val = f[k] * w * step_dt; total += val; e.sums[k] += val; }
+                if (w != 0.0f) { float val = f[k] * w * c.d_step_dt; total += val; e.sums[k] += val; }
             }
         }
         rew[i] = total;
-        terminated_o[i] = terminated ? 1 : 0;
-        truncated_o[i] = time_out ? 1 : 0;
-        done = terminated || time_out;
+        terminated_o[i] = (tmask & ~1u) ? 1 : 0;
+        truncated_o[i] = (tmask & 1u) ? 1 : 0;
+        done = tmask != 0u;
     }
     // F. auto-reset + per-step episode log (warp-shuffle reduction over the finished envs)
-    log_accumulate(gl, done, terminated, time_out, e.sums);
+    log_accumulate(gl, done, tmask, e.sums);
     if (i < n) {
         const uint32_t gid = (uint32_t)(c.env_id_offset + i);
         if (done) {
-            if (TASK == WL_TASK_DRIFT) drift_reset_env(c, e, gid, t);
+            if (ELEV) elev_reset_env(c, e, gid, t); else drift_reset_env(c, e, gid, t);
         }
-        // H. interval events on the post-reset state
-        interval_pushes(c, e, gid, t, c.d_step_dt);
-        // I. observations
-        if (TASK == WL_TASK_DRIFT) blind_obs(c, e, gid, t, RNG_OBS, 0u, obs + (size_t)WL_OBS_DIM_BLIND * i);
-        store_env(st, n, i, e, TASK == WL_TASK_ELEVATION);
+        // G. commands   H. interval events (post-reset state)   I. observations
+        if (ELEV) {
+            elev_command_update(c, e, gid, t, c.d_step_dt);
+            float o[13]; elev_proprio(c, e, euler_xyz(e.qw, e.qx, e.qy, e.qz), o);
+            float* row = obs + (size_t)WL_OBS_DIM_ELEV * i;
+#pragma unroll
+            for (int k = 0; k < 13; ++k) row[k] = o[k];
+        } else {
+            interval_pushes(c, e, gid, t, c.d_step_dt);
+            blind_obs(c, e, gid, t, RNG_OBS, 0u, obs + (size_t)WL_OBS_DIM_BLIND * i);
+        }
+        store_env(st, n, i, e, ELEV);
     }
     log_finalize(c, gl, d_log);
 }
@@ -175,6 +189,7 @@ __global__ void __launch_bounds__(128)
 wl_step_quad_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st, wl_globals* __restrict__ gl, Terrain T,
                     const float2* __restrict__ action, float* __restrict__ obs, float* __restrict__ rew,
                     uint8_t* __restrict__ terminated_o, uint8_t* __restrict__ truncated_o, float* __restrict__ d_log, uint32_t t) {
+    constexpr bool ELEV = (TASK == WL_TASK_ELEVATION);
     const int n = c.num_envs;
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int i = tid >> 2, w = tid & 3;
@@ -183,7 +198,7 @@ wl_step_quad_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st
     const uint32_t gid = (uint32_t)(c.env_id_offset + ii);
     const unsigned base = (threadIdx.x & 31u) & ~3u;
     EnvState e;
-    load_env_quad(st, n, ii, w, e, TASK == WL_TASK_ELEVATION);
+    load_env_quad(st, n, ii, w, e, ELEV);
     // A. action manager (redundant in the 4 lanes)
     float2 a = action[ii];
     e.prev_action[0] = e.action[0]; e.prev_action[1] = e.action[1];
@@ -211,35 +226,38 @@ wl_step_quad_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st
     e.p = V3{b.pc.x - cw.x, b.pc.y - cw.y, b.pc.z - cw.z};
     e.v = b.v; e.qw = b.qw; e.qx = b.qx; e.qy = b.qy; e.qz = b.qz;
     e.w = rot(R, b.wb);
-    // C./D. counters, terminations (redundant)
+    // C./D./E. counters, terminations, rewards (redundant in the 4 lanes)
     e.ep_len += 1;
     const bool time_out = e.ep_len >= c.max_episode_length;
-    const float step_dt = c.d_step_dt;
     V3 vb = rotT(R, e.v);
-    bool terminated = false;
+    uint32_t tmask;
     float f[WL_MAX_REW_TERMS];
-    const float steer_l = __shfl_sync(0xffffffffu, e.steer[0], base + 2), steer_r = __shfl_sync(0xffffffffu, e.steer[0], base + 3);
-    if (TASK == WL_TASK_DRIFT) {
-        terminated = drift_off_track(c, e.p.x, e.p.y);
-        drift_reward_terms(c, steer_l, steer_r, det_atan2(vb.y, vb.x), e.p, vb, b.wb, e.w.z, terminated, time_out, f);
+    if (ELEV) {
+        float o01 = e.omega[0] + __shfl_xor_sync(0xffffffffu, e.omega[0], 1);      // (w0+w1), (w2+w3)
+        float osum = o01 + __shfl_xor_sync(0xffffffffu, o01, 2);                   // (w0+w1)+(w2+w3)
+        tmask = elev_terms(c, e, R, vb, osum, time_out, f);
+    } else {
+        const float steer_l = __shfl_sync(0xffffffffu, e.steer[0], base + 2), steer_r = __shfl_sync(0xffffffffu, e.steer[0], base + 3);
+        const bool oob = drift_off_track(c, e.p.x, e.p.y);
+        drift_reward_terms(c, steer_l, steer_r, det_atan2(vb.y, vb.x), e.p, vb, b.wb, e.w.z, oob, time_out, f);
+        tmask = (time_out ? 1u : 0u) | (oob ? 2u : 0u);
     }
     float total = 0.0f;
 #pragma unroll
     for (int k = 0; k < WL_MAX_REW_TERMS; ++k) {
         if (k < c.num_rew_terms) {
             float wgt = __ldg(&gl->rew_weight[k]);
-            if (wgt != 0.0f) { float val = f[k] * wgt * step_dt; total += val; e.sums[k] += val; }
+            if (wgt != 0.0f) { float val = f[k] * wgt * c.d_step_dt; total += val; e.sums[k] += val; }
         }
     }
-    const bool done = terminated || time_out;
-    if (live && w == 0) { rew[i] = total; terminated_o[i] = terminated ? 1 : 0; truncated_o[i] = time_out ? 1 : 0; }
-    // F. per-step episode log: one contribution per env (lane 0 of each live quad)
-    const bool contrib = done && live && (w == 0);
-    log_accumulate(gl, contrib, terminated, time_out, e.sums);
+    const bool done = tmask != 0u;
+    if (live && w == 0) { rew[i] = total; terminated_o[i] = (tmask & ~1u) ? 1 : 0; truncated_o[i] = (tmask & 1u) ? 1 : 0; }
+    // F. per-step episode log: one contribution per env (lane 0 of each live quad), then auto-reset
+    log_accumulate(gl, done && live && (w == 0), tmask, e.sums);
     if (done) {
-        if (TASK == WL_TASK_DRIFT) drift_reset_env(c, e, gid, t);      // redundant in the 4 lanes; joints untouched (Q3)
+        if (ELEV) elev_reset_env(c, e, gid, t); else drift_reset_env(c, e, gid, t);   // redundant; joints untouched (Q3)
     }
-    interval_pushes(c, e, gid, t, step_dt);
+    if (ELEV) elev_command_update(c, e, gid, t, c.d_step_dt); else interval_pushes(c, e, gid, t, c.d_step_dt);
     // I. observations: the three euler angles are three atan2 calls -> one per lane
     {
         float qw = e.qw, qx = e.qx, qy = e.qy, qz = e.qz;
@@ -251,14 +269,108 @@ wl_step_quad_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st
         float ang = det_atan2(ay, ax);
         if (w == 1 && fabsf(sin_pitch) >= 1.0f) ang = (sin_pitch < 0.0f) ? -1.57079632679489661923f : 1.57079632679489661923f;
         float eu_k = wrap_2pi(ang);
-        if (TASK == WL_TASK_DRIFT) {
+        if (ELEV) {
+            V3 eu{__shfl_sync(0xffffffffu, eu_k, base + 0), __shfl_sync(0xffffffffu, eu_k, base + 1), __shfl_sync(0xffffffffu, eu_k, base + 2)};
+            float o[13]; elev_proprio(c, e, eu, o);
+            if (live) {
+                float* row = obs + (size_t)WL_OBS_DIM_ELEV * i;
+                // lane w writes o[w], o[w+4], o[w+8] (and lane 0 also o[12]): 4-byte rows, scalar stores
+                const float v0 = (w == 0) ? o[0] : (w == 1) ? o[1] : (w == 2) ? o[2] : o[3];
+                const float v1 = (w == 0) ? o[4] : (w == 1) ? o[5] : (w == 2) ? o[6] : o[7];
+                const float v2 = (w == 0) ? o[8] : (w == 1) ? o[9] : (w == 2) ? o[10] : o[11];
+                row[w] = v0; row[w + 4] = v1; row[w + 8] = v2;
+                if (w == 0) row[12] = o[12];
+            }
+        } else {
             // blind_obs_quad shuffles: every lane of the warp calls it, dead quads only skip the stores
-            float* o = obs + (size_t)WL_OBS_DIM_BLIND * ii;
-            blind_obs_quad(c, e, w, eu_k, gid, t, RNG_OBS, 0u, o, live);
+            blind_obs_quad(c, e, w, eu_k, gid, t, RNG_OBS, 0u, obs + (size_t)WL_OBS_DIM_BLIND * ii, live);
         }
     }
-    if (live) store_env_quad(st, n, i, w, e, TASK == WL_TASK_ELEVATION);
+    if (live) store_env_quad(st, n, i, w, e, ELEV);
     log_finalize(c, gl, d_log);
+}
+
+// ---------------------------------------------------------------------------------------
+// height-scan observation (ray-caster sensor, elevation/mushr_elevation_env_cfg.py:44-48,74-82,132-142):
+// one CTA per env.  The yaw-rotated 2.5 m x 2.5 m footprint fits a WL_TILE x WL_TILE window of the height-field;
+// one elected thread pulls that window into shared memory with a single TMA (cp.async.bulk.tensor.2d, completion on
+// an mbarrier; out-of-raster elements are zero-filled by the hardware and never read), then 128 threads take the
+// 676 vertical rays as bilinear samples from shared memory and write obs[13:689] coalesced.
+// ---------------------------------------------------------------------------------------
+#define WL_TILE 40
+#define WL_SCAN_THREADS 128
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <bool USE_TMA>
+__global__ void __launch_bounds__(WL_SCAN_THREADS)
+wl_scan_kernel(const __grid_constant__ wl_config c, const __grid_constant__ CUtensorMap tmap, const float4* __restrict__ st,
+               const float* __restrict__ hf, float* __restrict__ obs) {
+    __shared__ __align__(128) float tile[WL_TILE * WL_TILE];
+    __shared__ __align__(8) unsigned long long mbar;
+    const int n = c.num_envs;
+    const int i = blockIdx.x;
+    float4 g0 = ldg4(st, WL_G_POS, n, i), g1 = ldg4(st, WL_G_QUAT, n, i);
+    EnvState e; e.p = V3{g0.x, g0.y, g0.z}; e.qw = g1.x; e.qx = g1.y; e.qy = g1.z; e.qz = g1.w;
+    M3 R = rotmat(e.qw, e.qx, e.qy, e.qz);
+    // ray-caster parent = base_link (root + R (0,0,base_link_z)); rays are yaw-aligned (attach_yaw_only)
+    const float bx = fm(c.base_link_z, R.r[2], e.p.x), by = fm(c.base_link_z, R.r[5], e.p.y), bz = fm(c.base_link_z, R.r[8], e.p.z);
+    float cy, sy; yaw_cs(e, cy, sy);
+    const float inv = 1.0f / c.hf_cell;
+    // window origin (in samples): covers base +- (half*sqrt2 + 1 cell)
+    const float reach = c.scan_half * 1.41421356237f + c.hf_cell;
+    const int ox = (int)floorf((bx - reach - c.hf_x0) * inv), oy = (int)floorf((by - reach - c.hf_y0) * inv);
+    if (USE_TMA) {
+        if (threadIdx.x == 0) {
+            const uint32_t mb = smem_u32(&mbar);
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const uint32_t mb = smem_u32(&mbar), dst = smem_u32(tile);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"((uint32_t)(WL_TILE * WL_TILE * 4)) : "memory");
+            asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                         ::"r"(dst), "l"(&tmap), "r"(ox), "r"(oy), "r"(mb) : "memory");
+        }
+        {   // all threads wait for the bytes (phase 0)
+            const uint32_t mb = smem_u32(&mbar);
+            uint32_t ok = 0;
+            while (!ok) {
+                asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                             : "=r"(ok) : "r"(mb), "r"(0u) : "memory");
+            }
+        }
+    } else {
+        for (int k = threadIdx.x; k < WL_TILE * WL_TILE; k += WL_SCAN_THREADS) {
+            int tx = k % WL_TILE, ty = k / WL_TILE, gx = ox + tx, gy = oy + ty;
+            tile[k] = (gx >= 0 && gy >= 0 && gx < c.hf_nx && gy < c.hf_ny) ? __ldg(hf + (size_t)gy * c.hf_pitch + gx) : 0.0f;
+        }
+        __syncthreads();
+    }
+    float* row = obs + (size_t)WL_OBS_DIM_ELEV * i + 13;
+    for (int k = threadIdx.x; k < WL_SCAN_RAYS; k += WL_SCAN_THREADS) {
+        const int rx = k % WL_SCAN_SIDE, ry = k / WL_SCAN_SIDE;                  // "xy" ordering: x fastest
+        const float lx = fm((float)rx, c.scan_res, -c.scan_half), ly = fm((float)ry, c.scan_res, -c.scan_half);
+        const float wx = fm(cy, lx, fm(-sy, ly, bx)), wy = fm(sy, lx, fm(cy, ly, by));
+        const float fx = (wx - c.hf_x0) * inv, fy = (wy - c.hf_y0) * inv;
+        float v;
+        if ((fx >= 0.0f) && (fy >= 0.0f) && (fx <= (float)(c.hf_nx - 1)) && (fy <= (float)(c.hf_ny - 1))) {
+            int ix = (int)floorf(fx), iy = (int)floorf(fy);
+            if (ix > c.hf_nx - 2) ix = c.hf_nx - 2;
+            if (iy > c.hf_ny - 2) iy = c.hf_ny - 2;
+            const float tx = fx - (float)ix, ty = fy - (float)iy;
+            const float* t0 = tile + (iy - oy) * WL_TILE + (ix - ox);
+            const float z00 = t0[0], z10 = t0[1], z01 = t0[WL_TILE], z11 = t0[WL_TILE + 1];
+            const float za = fm(z10 - z00, tx, z00), zb = fm(z11 - z01, tx, z01);
+            const float hit = fm(zb - za, ty, za);
+            const float hs = bz - hit - c.scan_offset;                           // mdp.height_scan
+            v = r_clamp(-hs + (e.p.z - c.scan_plane_init), -c.obs_clip, c.obs_clip);   // world_height_map, clip
+        } else {
+            v = c.obs_clip;                                                      // miss: +inf clipped
+        }
+        row[k] = v;
+    }
 }
 
 __global__ void wl_startup_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st) {
@@ -302,9 +414,11 @@ __global__ void wl_reset_kernel(const __grid_constant__ wl_config c, float4* __r
     const int i = ids ? (int)ids[k] : k;
     if (i < 0 || i >= n) return;
     EnvState e;
-    load_env(st, n, i, e, true);
-    drift_reset_env(c, e, (uint32_t)(c.env_id_offset + i), t);
-    store_env(st, n, i, e, false);
+    const bool elev = c.task == WL_TASK_ELEVATION;
+    load_env(st, n, i, e, elev);
+    if (elev) elev_reset_env(c, e, (uint32_t)(c.env_id_offset + i), t);      // command b-frame vector is NOT refreshed by reset()
+    else drift_reset_env(c, e, (uint32_t)(c.env_id_offset + i), t);
+    store_env(st, n, i, e, elev);
 }
 
 __global__ void wl_observe_kernel(const __grid_constant__ wl_config c, const float4* __restrict__ st, float* __restrict__ obs,
@@ -313,6 +427,14 @@ __global__ void wl_observe_kernel(const __grid_constant__ wl_config c, const flo
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     EnvState e;
+    if (c.task == WL_TASK_ELEVATION) {
+        load_env(st, n, i, e, true);
+        float o[13]; elev_proprio(c, e, euler_xyz(e.qw, e.qx, e.qy, e.qz), o);
+        float* row = obs + (size_t)WL_OBS_DIM_ELEV * i;
+#pragma unroll
+        for (int k = 0; k < 13; ++k) row[k] = o[k];
+        return;
+    }
     load_env(st, n, i, e, false);
     blind_obs(c, e, (uint32_t)(c.env_id_offset + i), t, RNG_OBS_EXTRA, 3u * call_idx, obs + (size_t)WL_OBS_DIM_BLIND * i);
 }
@@ -363,6 +485,16 @@ static inline int pick_block(int n) {
     if (n >= 148 * 128 * 4) return 128;
     if (n >= 148 * 64 * 2) return 64;
     return 32;
+}
+
+static int launch_scan(wl_sim* sim, float* d_obs, cudaStream_t cs) {
+    const int n = sim->cfg.num_envs;
+    if (sim->scan_tma && sim->has_tmap)
+        wl_scan_kernel<true><<<n, WL_SCAN_THREADS, 0, cs>>>(sim->cfg, sim->tmap, sim->state, sim->hf, d_obs);
+    else
+        wl_scan_kernel<false><<<n, WL_SCAN_THREADS, 0, cs>>>(sim->cfg, sim->tmap, sim->state, sim->hf, d_obs);
+    sim->launches++;
+    return cuda_check(cudaGetLastError(), "wl_scan_kernel");
 }
 
 // ---------------------------------------------------------------------------------------
@@ -417,7 +549,14 @@ int wl_create(const wl_config* cfg, void* d_state, size_t state_bytes, const flo
     if (cfg->num_envs <= 0) return fail(WL_EINVAL, "wl_create: num_envs must be > 0");
     if (state_bytes < wl_state_bytes(cfg->num_envs)) return fail(WL_EINVAL, "wl_create: state buffer too small");
     if (((uintptr_t)d_state & 255u) != 0) return fail(WL_EINVAL, "wl_create: state buffer must be 256-byte aligned");
-    if (cfg->task != WL_TASK_DRIFT) return fail(WL_EUNSUPPORTED, "wl_create: task not implemented in this build");
+    if (cfg->task != WL_TASK_DRIFT && cfg->task != WL_TASK_ELEVATION)
+        return fail(WL_EUNSUPPORTED, "wl_create: task not implemented in this build (drift, elevation)");
+    if (cfg->task == WL_TASK_ELEVATION) {
+        if (!d_heightfield) return fail(WL_EINVAL, "wl_create: the elevation task needs a height-field");
+        if (cfg->hf_nx < 2 || cfg->hf_ny < 2 || cfg->hf_pitch < cfg->hf_nx || (cfg->hf_pitch & 3) || !(cfg->hf_cell > 0.0f))
+            return fail(WL_EINVAL, "wl_create: bad height-field geometry (hf_pitch must be >= hf_nx and a multiple of 4)");
+        if (((uintptr_t)d_heightfield & 15u) != 0) return fail(WL_EINVAL, "wl_create: height-field must be 16-byte aligned");
+    }
     if (cfg->bounding != WL_BOUND_CLIP && cfg->bounding != WL_BOUND_NONE)
         return fail(WL_EUNSUPPORTED, "wl_create: bounding_strategy 'tanh' is not implemented");
     if (cfg->decimation <= 0 || cfg->substeps <= 0 || !(cfg->sim_dt > 0.0f)) return fail(WL_EINVAL, "wl_create: bad sim timing");
@@ -437,6 +576,26 @@ int wl_create(const wl_config* cfg, void* d_state, size_t state_bytes, const flo
     s->state_bytes = state_bytes;
     s->launches = 0;
     s->variant = 0;
+    s->has_tmap = false;
+    s->scan_tma = true;
+    if (cfg->task == WL_TASK_ELEVATION) {
+        typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (int rc = cuda_check(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres),
+                                "cudaGetDriverEntryPoint(cuTensorMapEncodeTiled)")) { delete s; return rc; }
+        if (!fn || qres != cudaDriverEntryPointSuccess) { delete s; return fail(WL_ECUDA, "cuTensorMapEncodeTiled not available"); }
+        cuuint64_t gdim[2] = {(cuuint64_t)cfg->hf_nx, (cuuint64_t)cfg->hf_ny};
+        cuuint64_t gstride[1] = {(cuuint64_t)cfg->hf_pitch * sizeof(float)};
+        cuuint32_t box[2] = {WL_TILE, WL_TILE}, estr[2] = {1, 1};
+        CUresult cr = ((encode_fn)fn)(&s->tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)d_heightfield, gdim, gstride, box, estr,
+                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr != CUDA_SUCCESS) { delete s; return fail(WL_ECUDA, "cuTensorMapEncodeTiled failed (code " + std::to_string((int)cr) + ")"); }
+        s->has_tmap = true;
+    }
     s->obs_dim = (cfg->task == WL_TASK_ELEVATION) ? WL_OBS_DIM_ELEV : WL_OBS_DIM_BLIND;
     // live reward weights
     if (int rc = cuda_check(cudaMemcpy(s->globals->rew_weight, cfg->rew_weight, sizeof(float) * WL_MAX_REW_TERMS,
@@ -447,6 +606,11 @@ int wl_create(const wl_config* cfg, void* d_state, size_t state_bytes, const flo
 
 int wl_destroy(wl_sim* sim) { delete sim; return WL_OK; }
 int32_t wl_obs_dim(const wl_sim* sim) { return sim ? sim->obs_dim : 0; }
+int wl_set_scan_tma(wl_sim* sim, int32_t use_tma) {
+    if (!sim) return fail(WL_EINVAL, "wl_set_scan_tma: null handle");
+    sim->scan_tma = use_tma != 0;
+    return WL_OK;
+}
 int wl_set_kernel_variant(wl_sim* sim, int32_t lanes_per_env) {
     if (!sim) return fail(WL_EINVAL, "wl_set_kernel_variant: null handle");
     if (lanes_per_env != 0 && lanes_per_env != 1 && lanes_per_env != 4) return fail(WL_EINVAL, "wl_set_kernel_variant: 0, 1 or 4");
@@ -486,16 +650,23 @@ int wl_step(wl_sim* sim, const float* d_action, float* d_obs, float* d_rew, uint
     const int n = sim->cfg.num_envs;
     Terrain T{sim->hf};
     const int variant = sim->variant ? sim->variant : ((n <= WL_QUAD_MAX_ENVS) ? 4 : 1);
+    const float2* act = reinterpret_cast<const float2*>(d_action);
+    cudaStream_t cs = (cudaStream_t)stream;
+    const uint32_t t = (uint32_t)step_counter;
+    const bool elev = sim->cfg.task == WL_TASK_ELEVATION;
     if (variant == 4) {
-        const int bs = 32, threads = 4 * n;
-        wl_step_quad_kernel<WL_TASK_DRIFT><<<(threads + bs - 1) / bs, bs, 0, (cudaStream_t)stream>>>(
-            sim->cfg, sim->state, sim->globals, T, reinterpret_cast<const float2*>(d_action), d_obs, d_rew, d_terminated,
-            d_truncated, d_log, (uint32_t)step_counter);
+        const int bs = 32, threads = 4 * n, grid = (threads + bs - 1) / bs;
+        if (elev) wl_step_quad_kernel<WL_TASK_ELEVATION><<<grid, bs, 0, cs>>>(sim->cfg, sim->state, sim->globals, T, act, d_obs, d_rew, d_terminated, d_truncated, d_log, t);
+        else wl_step_quad_kernel<WL_TASK_DRIFT><<<grid, bs, 0, cs>>>(sim->cfg, sim->state, sim->globals, T, act, d_obs, d_rew, d_terminated, d_truncated, d_log, t);
     } else {
-        const int bs = pick_block(n);
-        wl_step_kernel<WL_TASK_DRIFT><<<(n + bs - 1) / bs, bs, 0, (cudaStream_t)stream>>>(
-            sim->cfg, sim->state, sim->globals, T, reinterpret_cast<const float2*>(d_action), d_obs, d_rew, d_terminated,
-            d_truncated, d_log, (uint32_t)step_counter);
+        const int bs = pick_block(n), grid = (n + bs - 1) / bs;
+        if (elev) wl_step_kernel<WL_TASK_ELEVATION><<<grid, bs, 0, cs>>>(sim->cfg, sim->state, sim->globals, T, act, d_obs, d_rew, d_terminated, d_truncated, d_log, t);
+        else wl_step_kernel<WL_TASK_DRIFT><<<grid, bs, 0, cs>>>(sim->cfg, sim->state, sim->globals, T, act, d_obs, d_rew, d_terminated, d_truncated, d_log, t);
+    }
+    if (elev) {
+        WL_LAUNCH_CHECK(sim, "wl_step_kernel");
+        if (int rc = launch_scan(sim, d_obs, cs)) return rc;
+        return WL_OK;
     }
     WL_LAUNCH_CHECK(sim, "wl_step_kernel");
     return WL_OK;
@@ -507,6 +678,7 @@ int wl_observe(wl_sim* sim, float* d_obs, int64_t step_counter, int32_t call_idx
     wl_observe_kernel<<<(n + bs - 1) / bs, bs, 0, (cudaStream_t)stream>>>(sim->cfg, sim->state, d_obs, (uint32_t)step_counter,
                                                                          (uint32_t)call_idx);
     WL_LAUNCH_CHECK(sim, "wl_observe_kernel");
+    if (sim->cfg.task == WL_TASK_ELEVATION) return launch_scan(sim, d_obs, (cudaStream_t)stream);
     return WL_OK;
 }
 

@@ -26,7 +26,8 @@ struct EnvState {
     float sums[WL_MAX_REW_TERMS];
     float mass, inv_mass, spare0, spare1;
     float D[4], C[4], kd[4];
-    float cmd[4];
+    float cmd[4];     // elevation: goal x,y (world), heading_w, command time_left
+    float cmdb[4];    // elevation: command in the yaw frame x,y, heading_b, spare
 };
 
 __device__ __forceinline__ void load_env(const float4* __restrict__ st, int n, int i, EnvState& e, bool with_cmd) {
@@ -44,7 +45,10 @@ __device__ __forceinline__ void load_env(const float4* __restrict__ st, int n, i
     g = ldg4(st, WL_G_PMU_D, n, i); e.D[0] = g.x; e.D[1] = g.y; e.D[2] = g.z; e.D[3] = g.w;
     g = ldg4(st, WL_G_PMU_C, n, i); e.C[0] = g.x; e.C[1] = g.y; e.C[2] = g.z; e.C[3] = g.w;
     g = ldg4(st, WL_G_PKD, n, i); e.kd[0] = g.x; e.kd[1] = g.y; e.kd[2] = g.z; e.kd[3] = g.w;
-    if (with_cmd) { g = ldg4(st, WL_G_CMD, n, i); e.cmd[0] = g.x; e.cmd[1] = g.y; e.cmd[2] = g.z; e.cmd[3] = g.w; }
+    if (with_cmd) {
+        g = ldg4(st, WL_G_CMD, n, i); e.cmd[0] = g.x; e.cmd[1] = g.y; e.cmd[2] = g.z; e.cmd[3] = g.w;
+        g = ldg4(st, WL_G_CMDB, n, i); e.cmdb[0] = g.x; e.cmdb[1] = g.y; e.cmdb[2] = g.z; e.cmdb[3] = g.w;
+    }
 }
 // dynamic state only (params are read-only in the step)
 __device__ __forceinline__ void store_env(float4* __restrict__ st, int n, int i, const EnvState& e, bool with_cmd) {
@@ -57,7 +61,10 @@ __device__ __forceinline__ void store_env(float4* __restrict__ st, int n, int i,
     stg4(st, WL_G_ACTION, n, i, make_float4(e.action[0], e.action[1], e.prev_action[0], e.prev_action[1]));
     stg4(st, WL_G_SUM0, n, i, make_float4(e.sums[0], e.sums[1], e.sums[2], e.sums[3]));
     stg4(st, WL_G_SUM1, n, i, make_float4(e.sums[4], e.sums[5], e.sums[6], e.sums[7]));
-    if (with_cmd) stg4(st, WL_G_CMD, n, i, make_float4(e.cmd[0], e.cmd[1], e.cmd[2], e.cmd[3]));
+    if (with_cmd) {
+        stg4(st, WL_G_CMD, n, i, make_float4(e.cmd[0], e.cmd[1], e.cmd[2], e.cmd[3]));
+        stg4(st, WL_G_CMDB, n, i, make_float4(e.cmdb[0], e.cmdb[1], e.cmdb[2], e.cmdb[3]));
+    }
 }
 
 // ---- quad (4 lanes per env) state access: lane w = wheel [bl,br,fl,fr][w].  Per-wheel scalars live in slot [0]
@@ -81,7 +88,10 @@ __device__ __forceinline__ void load_env_quad(const float4* __restrict__ st, int
     g = ldg4(st, WL_G_STEER, n, i);
     e.steer[0] = (w == 3) ? g.y : g.x; e.steer_vel[0] = (w == 3) ? g.w : g.z;   // lanes 0-2 see the LEFT joint, lane 3 the right
     e.steer[1] = g.y; e.steer_vel[1] = g.w;
-    if (with_cmd) { g = ldg4(st, WL_G_CMD, n, i); e.cmd[0] = g.x; e.cmd[1] = g.y; e.cmd[2] = g.z; e.cmd[3] = g.w; }
+    if (with_cmd) {
+        g = ldg4(st, WL_G_CMD, n, i); e.cmd[0] = g.x; e.cmd[1] = g.y; e.cmd[2] = g.z; e.cmd[3] = g.w;
+        g = ldg4(st, WL_G_CMDB, n, i); e.cmdb[0] = g.x; e.cmdb[1] = g.y; e.cmdb[2] = g.z; e.cmdb[3] = g.w;
+    }
 }
 __device__ __forceinline__ void store_env_quad(float4* __restrict__ st, int n, int i, int w, const EnvState& e, bool with_cmd) {
     float* f = reinterpret_cast<float*>(st);
@@ -99,7 +109,10 @@ __device__ __forceinline__ void store_env_quad(float4* __restrict__ st, int n, i
         stg4(st, WL_G_ACTION, n, i, make_float4(e.action[0], e.action[1], e.prev_action[0], e.prev_action[1]));
         stg4(st, WL_G_SUM0, n, i, make_float4(e.sums[0], e.sums[1], e.sums[2], e.sums[3]));
         stg4(st, WL_G_SUM1, n, i, make_float4(e.sums[4], e.sums[5], e.sums[6], e.sums[7]));
-        if (with_cmd) stg4(st, WL_G_CMD, n, i, make_float4(e.cmd[0], e.cmd[1], e.cmd[2], e.cmd[3]));
+        if (with_cmd) {
+            stg4(st, WL_G_CMD, n, i, make_float4(e.cmd[0], e.cmd[1], e.cmd[2], e.cmd[3]));
+            stg4(st, WL_G_CMDB, n, i, make_float4(e.cmdb[0], e.cmdb[1], e.cmdb[2], e.cmdb[3]));
+        }
     }
 }
 
@@ -143,31 +156,35 @@ __device__ __forceinline__ float dc_motor(const wl_config& c, float kd, float ef
 // ---- terrain -----------------------------------------------------------------------
 struct Terrain { const float* __restrict__ hf; };
 
+// bilinear height-field sample at world (x, y): returns false outside the raster (a "miss" for the ray-caster,
+// the z = hf_outside_z ground plane for the wheels).  gx, gy = d z / d x, d z / d y.
+__device__ __forceinline__ bool hf_sample(const wl_config& c, const float* __restrict__ hf, float x, float y, float& z, float& gx,
+                                          float& gy) {
+    float inv = 1.0f / c.hf_cell;
+    float fx = (x - c.hf_x0) * inv, fy = (y - c.hf_y0) * inv;
+    if (!((fx >= 0.0f) && (fy >= 0.0f) && (fx <= (float)(c.hf_nx - 1)) && (fy <= (float)(c.hf_ny - 1)))) return false;
+    int ix = (int)floorf(fx), iy = (int)floorf(fy);
+    if (ix > c.hf_nx - 2) ix = c.hf_nx - 2;
+    if (iy > c.hf_ny - 2) iy = c.hf_ny - 2;
+    float tx = fx - (float)ix, ty = fy - (float)iy;
+    const float* row0 = hf + (size_t)iy * c.hf_pitch + ix;
+    const float* row1 = row0 + c.hf_pitch;
+    float z00 = __ldg(row0), z10 = __ldg(row0 + 1), z01 = __ldg(row1), z11 = __ldg(row1 + 1);
+    float za = fm(z10 - z00, tx, z00), zb = fm(z11 - z01, tx, z01);
+    z = fm(zb - za, ty, za);
+    gx = fm((z11 - z01) - (z10 - z00), ty, z10 - z00) * inv;
+    gy = (zb - za) * inv;
+    return true;
+}
 // height z and unit normal n (world) under world point (x, y).  FLAT tasks never call this.
 __device__ __forceinline__ void heightfield_at(const wl_config& c, const Terrain& T, float x, float y, float& z, V3& n) {
-    if (T.hf != nullptr) {
-        float inv = 1.0f / c.hf_cell;
-        float fx = (x - c.hf_x0) * inv, fy = (y - c.hf_y0) * inv;
-        if ((fx >= 0.0f) && (fy >= 0.0f) && (fx <= (float)(c.hf_nx - 1)) && (fy <= (float)(c.hf_ny - 1))) {
-            int ix = (int)floorf(fx), iy = (int)floorf(fy);
-            if (ix > c.hf_nx - 2) ix = c.hf_nx - 2;
-            if (iy > c.hf_ny - 2) iy = c.hf_ny - 2;
-            float tx = fx - (float)ix, ty = fy - (float)iy;
-            const float* row0 = T.hf + (size_t)iy * c.hf_nx + ix;
-            const float* row1 = row0 + c.hf_nx;
-            float z00 = __ldg(row0), z10 = __ldg(row0 + 1), z01 = __ldg(row1), z11 = __ldg(row1 + 1);
-            float za = fm(z10 - z00, tx, z00), zb = fm(z11 - z01, tx, z01);
-            z = fm(zb - za, ty, za);
-            float gx = fm((z11 - z01) - (z10 - z00), ty, z10 - z00) * inv;
-            float gy = (zb - za) * inv;
-            float ninv = 1.0f / sqrtf(fm(gx, gx, fm(gy, gy, 1.0f)));
-            n = V3{-gx * ninv, -gy * ninv, ninv};
-            return;
-        }
-        z = c.hf_outside_z;
-    } else {
-        z = 0.0f;
+    float gx, gy;
+    if (T.hf != nullptr && hf_sample(c, T.hf, x, y, z, gx, gy)) {
+        float ninv = 1.0f / sqrtf(fm(gx, gx, fm(gy, gy, 1.0f)));
+        n = V3{-gx * ninv, -gy * ninv, ninv};
+        return;
     }
+    z = (T.hf != nullptr) ? c.hf_outside_z : 0.0f;
     n = V3{0.0f, 0.0f, 1.0f};
 }
 
@@ -221,8 +238,9 @@ __device__ __forceinline__ WheelOut wheel_force(const wl_config& c, const Terrai
     V3 vc = cross(b.wb, rc);
     vc.x += vb.x; vc.y += vb.y; vc.z += vb.z;
     float sdot = -dot(nb, vc);
-    float Fz = fm(c.susp_k, comp, c.susp_c * sdot);
-    if (comp > c.susp_travel) Fz = fm(c.bump_k, comp - c.susp_travel, Fz);
+    float ce = r_min(comp, c.comp_max);                       // depenetration cap (spawn inside a ramp, hard landings)
+    float Fz = fm(c.susp_k, ce, c.susp_c * sdot);
+    if (ce > c.susp_travel) Fz = fm(c.bump_k, ce - c.susp_travel, Fz);
     Fz = (comp > 0.0f) ? r_max(Fz, 0.0f) : 0.0f;
     V3 ft;
     if (i >= 2) { float d = fm(cs, nb.x, sn * nb.y); ft = V3{fm(-d, nb.x, cs), fm(-d, nb.y, sn), -(d * nb.z)}; }
@@ -350,6 +368,82 @@ __device__ __forceinline__ void drift_reward_terms(const wl_config& c, float ste
     f[WL_DR_CROSS_TRACK] = sqrtf(sq) + c.ctd_offset;
     f[WL_DR_TERM_PENS] = (out_of_bounds && !time_out) ? 1.0f : 0.0f;
     f[7] = 0.0f;
+}
+
+// ---- elevation task (elevation/mushr_elevation_env_cfg.py) -------------------------------------------------
+// terminations :339-376 -> mask bits [0 time_out, 1 cart_out_of_bounds, 2 stuck, 3 rollover, 4 at_goal]; rewards :155-305
+// (active terms :283-305).  The command is the yaw-frame vector stored at the previous command update (quirk Q5:
+// the reference subtracts the WORLD position from it).
+__device__ __forceinline__ uint32_t elev_terms(const wl_config& c, const EnvState& e, const M3& R, V3 vb, float sum_omega,
+                                               bool time_out, float f[WL_MAX_REW_TERMS]) {
+    float gx = e.cmdb[0] - e.p.x, gy = e.cmdb[1] - e.p.y;
+    float gn = sqrtf(fm(gx, gx, gy * gy));
+    bool oob = e.p.z < c.elev_min_height;                                   // root_height_below_minimum :354-357
+    bool stuck = (r_min(vb.x, 1.2f) < c.elev_stuck_min_vel) && (sum_omega > c.elev_stuck_spin);   // :342-347 (2nd def wins, Q6)
+    bool roll = R.r[8] < c.elev_rollover_cos;                               // upright_bool :217-222,339-340
+    bool goal = gn < c.elev_goal_dist;                                      // close_to_goal :268-273
+    f[WL_ER_GOAL_RATE] = 5.0f + fm(e.v.x, gx, e.v.y * gy) / gn;             // goal_progress_rate :239-249
+    float zv = e.p.z - c.elev_plane_z;                                      // higher_elevation :166-173
+    float he = ((zv > 0.1f) && (vb.x > 0.1f)) ? zv : 0.0f;
+    f[WL_ER_HEIGHT_Z] = r_clamp(he, 0.0f, 1.0f);
+    f[WL_ER_FALLING] = (vb.z > c.elev_fall_vel) ? 1.0f : 0.0f;              // is_falling_penalty :251-254 (2nd def, Q6)
+    f[WL_ER_TERM_PEN] = (stuck && !time_out) ? 1.0f : 0.0f;                 // is_terminated_term("stuck")
+    f[4] = f[5] = f[6] = f[7] = 0.0f;
+    return (time_out ? 1u : 0u) | (oob ? 2u : 0u) | (stuck ? 4u : 0u) | (roll ? 8u : 0u) | (goal ? 16u : 0u);
+}
+// reset_root_state_uniform (:409-419) on the default root state (z = 0.25, :97,147-149) + manager resets +
+// command reset (UniformPose2dCommand resample, :425-435)
+__device__ __forceinline__ void elev_reset_env(const wl_config& c, EnvState& e, uint32_t gid, uint32_t t) {
+    uint4 r = philox4x32(c.seed, gid, t, RNG_RESET, 0u);
+    uint4 r2 = philox4x32(c.seed, gid, t, RNG_RESET, 1u);
+    e.p.x = uniform(r.x, c.elev_reset_xy[0], c.elev_reset_xy[1]);
+    e.p.y = uniform(r.y, c.elev_reset_xy[0], c.elev_reset_xy[1]);
+    e.p.z = c.elev_spawn_z;
+    float yaw = uniform(r.z, -c.elev_reset_yaw, c.elev_reset_yaw);
+    float sh, ch; det_sincos(yaw * 0.5f, sh, ch);
+    e.qw = ch; e.qx = 0.0f; e.qy = 0.0f; e.qz = sh;
+    e.v = V3{uniform(r.w, c.elev_reset_vel[0], c.elev_reset_vel[1]), uniform(r2.x, c.elev_reset_vel[0], c.elev_reset_vel[1]), 0.0f};
+    e.w = V3{0.0f, 0.0f, 0.0f};
+    e.ep_len = 0;
+#pragma unroll
+    for (int k = 0; k < WL_MAX_REW_TERMS; ++k) e.sums[k] = 0.0f;
+    e.action[0] = e.action[1] = e.prev_action[0] = e.prev_action[1] = 0.0f;
+    e.cmd[0] = uniform(r2.y, c.cmd_pos_range[0], c.cmd_pos_range[1]);
+    e.cmd[1] = uniform(r2.z, c.cmd_pos_range[0], c.cmd_pos_range[1]);
+    e.cmd[2] = 0.0f;
+    e.cmd[3] = c.cmd_resample_s;
+}
+// cos/sin of the root yaw (quat_apply_yaw): normalised (1-2(y^2+z^2), 2(wz+xy))
+__device__ __forceinline__ void yaw_cs(const EnvState& e, float& cy, float& sy) {
+    float cr = fm(-2.0f, fm(e.qy, e.qy, e.qz * e.qz), 1.0f), sr = 2.0f * fm(e.qw, e.qz, e.qx * e.qy);
+    float rinv = 1.0f / sqrtf(fm(cr, cr, sr * sr));
+    cy = cr * rinv; sy = sr * rinv;
+}
+// CommandManager.compute(dt): timer, resample, then the yaw-frame command (UniformPose2dCommand._update_command)
+__device__ __forceinline__ void elev_command_update(const wl_config& c, EnvState& e, uint32_t gid, uint32_t t, float step_dt) {
+    e.cmd[3] = e.cmd[3] - step_dt;
+    if (e.cmd[3] <= 0.0f) {
+        uint4 r = philox4x32(c.seed, gid, t, RNG_CMD, 0u);
+        e.cmd[0] = uniform(r.x, c.cmd_pos_range[0], c.cmd_pos_range[1]);
+        e.cmd[1] = uniform(r.y, c.cmd_pos_range[0], c.cmd_pos_range[1]);
+        e.cmd[3] = c.cmd_resample_s;
+    }
+    float cy, sy; yaw_cs(e, cy, sy);
+    float dx = e.cmd[0] - e.p.x, dy = e.cmd[1] - e.p.y;
+    e.cmdb[0] = fm(cy, dx, sy * dy);             // rotate by -yaw
+    e.cmdb[1] = fm(cy, dy, -(sy * dx));
+    e.cmdb[2] = 0.0f; e.cmdb[3] = 0.0f;
+}
+// proprioceptive head of the elevation observation (:57-72): 13 floats, no noise (:85); `eu` = euler_xyz
+__device__ __forceinline__ void elev_proprio(const wl_config& c, const EnvState& e, V3 eu, float o[13]) {
+    M3 R = rotmat(e.qw, e.qx, e.qy, e.qz);
+    V3 vb = rotT(R, e.v), wb = rotT(R, e.w);
+    float gx = e.cmdb[0] - e.p.x, gy = e.cmdb[1] - e.p.y;
+    o[0] = (gx != gx) ? 0.0f : gx; o[1] = (gy != gy) ? 0.0f : gy;          // nan_to_num(nan=0)
+    o[2] = eu.x; o[3] = eu.y; o[4] = eu.z;
+    o[5] = r_clamp(vb.x, -c.obs_clip, c.obs_clip); o[6] = r_clamp(vb.y, -c.obs_clip, c.obs_clip); o[7] = r_clamp(vb.z, -c.obs_clip, c.obs_clip);
+    o[8] = r_clamp(wb.x, -c.obs_clip, c.obs_clip); o[9] = r_clamp(wb.y, -c.obs_clip, c.obs_clip); o[10] = r_clamp(wb.z, -c.obs_clip, c.obs_clip);
+    o[11] = r_clamp(e.action[0], -1.0f, 1.0f); o[12] = r_clamp(e.action[1], -1.0f, 1.0f);
 }
 
 // ---- reset / pushes / observations -----------------------------------------------------

@@ -57,6 +57,21 @@ class RewardManager:
         return self._env.sim.rew_weight[: len(self.active_terms)]
 
 
+class CommandManager:
+    """command_manager.get_command("goal_pose") -> [N,4] (pos_b xyz, heading_b), UniformPose2dCommand layout."""
+
+    def __init__(self, env):
+        self._env = env
+
+    def get_command(self, name):
+        from .sim import G_CMDB
+        g = self._env.sim.groups[G_CMDB]
+        out = torch.zeros((self._env.num_envs, 4), device=self._env.device)
+        out[:, 0:2] = g[:, 0:2]
+        out[:, 3] = g[:, 2]
+        return out
+
+
 class TerminationManager:
     def __init__(self, env):
         self._env = env
@@ -197,7 +212,7 @@ class ManagerBasedRLEnv:
         self.cfg = SimpleNamespace(is_finite_horizon=False, seed=int(self.spec.cfg.seed), spec=self.spec)
         self.render_mode = render_mode
         self.device = str(torch.device(device))
-        self.sim = WheeledSim(self.spec, device)
+        self.sim = WheeledSim(self.spec, device)     # (the elevation height-field travels in spec.heightfield)
         self.num_envs = self.sim.num_envs
         self.step_dt = self.spec.step_dt
         self.physics_dt = float(self.spec.cfg.sim_dt)
@@ -210,6 +225,7 @@ class ManagerBasedRLEnv:
         self.observation_manager = ObservationManager(self)
         self.reward_manager = RewardManager(self)
         self.termination_manager = TerminationManager(self)
+        self.command_manager = CommandManager(self)
         self.single_action_space = _Box(-math.inf, math.inf, (self.spec.action_dim,))
         self.action_space = _Box(-math.inf, math.inf, (self.num_envs, self.spec.action_dim))
         self.single_observation_space = {"policy": _Box(-math.inf, math.inf, (self.spec.obs_dim,))}
@@ -297,8 +313,8 @@ class ManagerBasedRLEnv:
         out = {}
         for k, name in enumerate(self.spec.reward_names):
             out["Episode_Reward/" + name] = log[k]
-        for name, is_to in self.spec.termination_names:
-            out["Episode_Termination/" + name] = log[10] if is_to else log[9]
+        for j, (name, _) in enumerate(self.spec.termination_names):
+            out["Episode_Termination/" + name] = log[9 + j]
         return out
 
 

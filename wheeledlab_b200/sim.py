@@ -15,8 +15,8 @@ from .tasks import TaskSpec
 
 # state groups (include/wheeledlab_b200.h)
 G_POS, G_QUAT, G_LINVEL, G_ANGVEL, G_WHEEL, G_STEER, G_ACTION, G_SUM0, G_SUM1 = range(9)
-G_PMASS, G_PMU_D, G_PMU_C, G_PKD, G_CMD = 9, 10, 11, 12, 13
-NUM_GROUPS = 14
+G_PMASS, G_PMU_D, G_PMU_C, G_PKD, G_CMD, G_CMDB = 9, 10, 11, 12, 13, 14
+NUM_GROUPS = 15
 
 
 def _stream_ptr(device) -> C.c_void_p:
@@ -39,6 +39,8 @@ class WheeledSim:
             assert self._buf.data_ptr() % 256 == 0
             self._hf = None
             hf_ptr = None
+            if heightfield is None and getattr(spec, "heightfield", None) is not None:
+                heightfield = torch.from_numpy(spec.heightfield)
             if heightfield is not None:
                 self._hf = heightfield.to(self.device, torch.float32).contiguous()
                 hf_ptr = C.c_void_p(self._hf.data_ptr())
@@ -115,6 +117,9 @@ class WheeledSim:
         check(lib.wl_synth_actions(self._h, C.c_void_p(act.data_ptr()), step_counter, dist, _stream_ptr(self.device)),
               "wl_synth_actions")
         return act
+
+    def set_scan_tma(self, use_tma: bool):
+        check(lib.wl_set_scan_tma(self._h, 1 if use_tma else 0), "wl_set_scan_tma")
 
     def set_kernel_variant(self, lanes_per_env: int):
         """0 auto, 1 thread-per-env, 4 quad-per-env (bit-identical results)."""

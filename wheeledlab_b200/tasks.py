@@ -59,6 +59,7 @@ class TaskSpec:
     action_dim: int = 2
     episode_length_s: float = 5.0
     joint_names: list = field(default_factory=list)
+    heightfield: object = None                                  # float32 [ny, pitch] (elevation)
 
     @property
     def step_dt(self) -> float:
@@ -143,6 +144,8 @@ def _mushr_vehicle(cfg: WlConfig) -> None:
     cfg.susp_c = 2 * 0.7 * math.sqrt(cfg.susp_k * m / 4)
     cfg.susp_travel = 0.01                       # prismatic limits +-0.01 m
     cfg.bump_k = 10 * cfg.susp_k
+    cfg.comp_max = 0.03                          # force uses min(compression, 3 cm): bounded depenetration
+    cfg.base_link_z = 0.094655                   # base_link above base_footprint (Appendix A.1)
     cfg.steer_inertia = 1.0e-4
     cfg.tire_B = 10.0
     cfg.tire_v0 = 0.5
@@ -234,10 +237,86 @@ def drift_task(num_envs: int = 1024, seed: int = 42, env_id_offset: int = 0, ran
     )
 
 
+def elevation_task(num_envs: int = 1024, seed: int = 42, env_id_offset: int = 0, heightfield=None, hf_origin=None,
+                   hf_cell: float = 0.1) -> TaskSpec:
+    """MushrElevationRLEnvCfg (elevation/mushr_elevation_env_cfg.py:437-469).  ``heightfield``: float32 [ny, nx]
+    raster of the terrain top surface (default: terrain.procedural_heightfield(seed))."""
+    from .terrain import pad_pitch, procedural_heightfield
+    cfg = WlConfig()
+    cfg.abi_version = WL_ABI_VERSION
+    cfg.task = TASK_ELEVATION
+    cfg.num_envs, cfg.env_id_offset, cfg.seed = num_envs, env_id_offset, seed
+    sim_dt, decimation = 0.01, 10                                      # :461-462
+    cfg.sim_dt, cfg.decimation, cfg.substeps = sim_dt, decimation, 2   # integrator sub-step 5 ms
+    episode_length_s = 20.0                                            # :465
+    cfg.max_episode_length = math.ceil(episode_length_s / (sim_dt * decimation))
+    cfg.episode_length_s = episode_length_s
+    cfg.action_kind, cfg.bounding, cfg.no_reverse = ACT_4WD, BOUND_CLIP, 1      # Mushr4WDActionCfg, common/actions.py:27-48
+    _set(cfg.act_scale, (3.0, 0.488))                                  # :463
+    _set(cfg.act_offset, (0.0, 0.0))
+    cfg.base_length, cfg.base_width, cfg.wheel_radius_cfg = 0.325, 0.2, 0.05
+    _mushr_vehicle(cfg)
+    _hound_actuators(cfg, "4wd")                                       # MUSHR_SUS_CFG -> HOUND_SUS_ACTUATOR_CFG
+    cfg.ground_mu_s, cfg.ground_mu_d = 1.0, 1.0                        # :95-108 (combine = multiply)
+    cfg.dr_enable, cfg.dr_num_buckets = 1, 5                           # :387-398: mu_s 2.0, mu_d 1.0, 5 identical buckets
+    D, Cs = material_buckets(5, (2.0, 2.0), (1.0, 1.0), False, cfg.ground_mu_s, cfg.ground_mu_d, seed)
+    _set(cfg.dr_bucket_D, D)
+    _set(cfg.dr_bucket_C, Cs)
+    _set(cfg.dr_kd_range, (10.0, 50.0))
+    cfg.dr_kd_mask = 0                                                 # no randomize_actuator_gains event in this task
+    _set(cfg.dr_mass_add, (0.2, 0.5))                                  # :400-407
+    cfg.enable_corruption, cfg.push_enable = 0, 0                      # :85; no interval events
+    _set(cfg.noise_std, (0.0, 0.0, 0.0, 0.0))
+    cfg.num_ref_poses = 1
+    # height-field
+    if heightfield is None:
+        heightfield, x0, y0, hf_cell = procedural_heightfield(seed)
+    else:
+        x0, y0 = hf_origin
+    heightfield = np.ascontiguousarray(heightfield, dtype=np.float32)
+    cfg.hf_ny, cfg.hf_nx = heightfield.shape
+    padded = pad_pitch(heightfield)
+    cfg.hf_pitch = padded.shape[1]
+    cfg.hf_x0, cfg.hf_y0, cfg.hf_cell = x0, y0, hf_cell
+    cfg.hf_outside_z = 0.0                                             # ground plane z = 0 outside the mesh (:120-128)
+    cfg.scan_offset, cfg.scan_plane_init, cfg.scan_sensor_dz = 0.084, 0.19, 20.0   # :74-82,135
+    cfg.scan_res, cfg.scan_half, cfg.obs_clip = 0.1, 1.25, 10.0        # :139 GridPatternCfg(size=[2.5,2.5], resolution=0.1)
+    _set(cfg.cmd_pos_range, (-19.0, 19.0))                             # :425-435
+    cfg.cmd_resample_s = 10.0
+    _set(cfg.elev_reset_xy, (-19.0, 19.0))                             # :409-419
+    cfg.elev_reset_yaw = 3.14
+    _set(cfg.elev_reset_vel, (0.1, 0.2))
+    cfg.elev_spawn_z = 0.25                                            # :97,147-149
+    cfg.elev_min_height = 0.15                                         # :354-357
+    cfg.elev_stuck_min_vel, cfg.elev_stuck_spin = 0.02, 5.0            # :358-364
+    cfg.elev_rollover_cos = math.cos(math.radians(60.0))               # :366-369: rad2deg(acos(R22)) > 60
+    cfg.elev_goal_dist = 0.5                                           # :371-374
+    cfg.elev_fall_vel = 0.10                                           # :251
+    cfg.elev_plane_z = 0.19                                            # :168
+    reward_names = ["vel_towards_goal", "height_z", "falling_penalty", "termination_penalty"]   # :283-305
+    cfg.num_rew_terms = len(reward_names)
+    _set(cfg.rew_weight, (200.0, 5000.0, 0.0, -200.0))
+    curriculum = [                                                     # :311-333
+        CurriculumTerm("more_goal", "vel_towards_goal", 5.0, 50, 5),
+        CurriculumTerm("more_falling_pen", "falling_penalty", 1.0, 50, 10),
+    ]
+    spec = TaskSpec(
+        name="elevation", cfg=cfg, reward_names=reward_names,
+        termination_names=[("time_out", True), ("cart_out_of_bounds", False), ("stuck", False), ("rollover", False),
+                           ("at_goal", False)],
+        curriculum=curriculum, obs_dim=689, action_dim=2, episode_length_s=episode_length_s,
+        joint_names=list(MUSHR_JOINT_NAMES),
+    )
+    spec.heightfield = padded
+    return spec
+
+
 def make_task(name_or_id: str, **kw) -> TaskSpec:
     name = GYM_IDS.get(name_or_id, name_or_id)
     if name == "drift":
         return drift_task(**kw)
     if name in ("drift_4wd", "hound_4wd"):
         return drift_task(drive="4wd", **kw)
+    if name == "elevation":
+        return elevation_task(**kw)
     raise NotImplementedError(f"task {name_or_id!r} is not implemented in this build")
