@@ -191,9 +191,12 @@ def run_ours(args):
     spec = wl.drift_task(num_envs=E, seed=args.seed, env_id_offset=rank * E)
     sim = wl.WheeledSim(spec, dev)
     sim.startup(); sim.reset(None, 0)
+    from wheeledlab_b200.distributed import RolloutSlab
+    T_ROLL = 128                                                                  # rsl_rl num_steps_per_env (rsl_rl_ppo_cfg.py:6)
     acts = torch.stack([sim.synth_actions(t) for t in range(W + K)])           # resident in HBM
-    outs = tuple(torch.empty_like(x) for x in sim.step(acts[0], 0))
-    sim.load_state(sim.state_snapshot())                                          # (no-op; keeps API exercised)
+    slab = RolloutSlab(T_ROLL, E, sim.obs_dim, 2, dev)                            # the step writes straight into the send buffer
+    outs = slab.step_outputs(0)
+    sim.step(acts[0], 0, out=outs)
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # 256 MiB > 126 MB L2
     peak, peak_src = _peaks()
 
@@ -213,15 +216,21 @@ def run_ours(args):
     l0 = sim.launch_count
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     barrier()
+    gev, gathered = [], None
     for k in range(K):
+        row = k % T_ROLL
         ev[k][0].record()
-        sim.step(acts[(W + k) % (W + K)], t, out=outs); t += 1
+        sim.step(acts[(W + k) % (W + K)], t, out=slab.step_outputs(row)); t += 1
         ev[k][1].record()
         flush.fill_(0.0)
+        if world > 1 and row == T_ROLL - 1:            # one all-gather of the rollout slab per PPO iteration
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record(); gathered = slab.all_gather(); g1.record(); gev.append((g0, g1))
     barrier()
     launches = sim.launch_count - l0
     step_ms = [a.elapsed_time(b) for a, b in ev]
-    tot_ms = sum(step_ms)
+    gather_ms = sum(a.elapsed_time(b) for a, b in gev)
+    tot_ms = sum(step_ms) + gather_ms
     # ---- warm-L2, CUDA-graph replay of K steps (supplementary: how the loop is meant to be driven) ----
     g = torch.cuda.CUDAGraph()
     s = torch.cuda.Stream()
@@ -269,6 +278,7 @@ def run_ours(args):
         return float(tt.item())
 
     tot_ms, graph_ms, e2e_ms = max_over_ranks(tot_ms), max_over_ranks(graph_ms), max_over_ranks(e2e_ms)
+    gather_ms = max_over_ranks(gather_ms)
     if rank == 0:
         total_envs = E * world
         value = total_envs * K / (tot_ms * 1e-3)
@@ -292,6 +302,8 @@ def run_ours(args):
                          "kernel_variant": "quad (4 lanes/env)" if E <= 148 * 4 * 32 * 2 else "thread-per-env",
                          "note": "N=4096 moves 1.7 MB/launch: launch-latency bound, see profiles/ for the N sweep"},
             "cpu_baseline": cpu,
+            "collective": {"kind": "all_gather_into_tensor(rollout slab)", "per_iteration_steps": T_ROLL,
+                           "bytes_per_rank": slab.nbytes, "count": len(gev), "ms_total": gather_ms} if world > 1 else None,
             "warm_l2_graph": {"value": total_envs * K / (graph_ms * 1e-3), "unit": UNIT, "ms_per_step": graph_ms / K,
                               "note": "K steps captured in one CUDA graph, state L2-resident (supplementary)"},
         }

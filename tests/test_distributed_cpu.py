@@ -1,0 +1,71 @@
+"""world_size-2 gloo test of the multi-GPU host logic: shard offsets, slab layout, the single
+all-gather, and shard invariance (2 x N/2 shards == one N run) using the CPU oracle as the stepper."""
+import os
+import socket
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = Path(__file__).resolve().parent.parent
+N_LOCAL, T = 24, 12
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker(rank, world, port, outdir):
+    sys.path[:0] = [str(ROOT), str(ROOT / "tests")]
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import wheeledlab_b200 as wl
+    from wheeledlab_b200.distributed import RolloutSlab, shard_offset
+    from oracle_lib import Oracle
+    spec = wl.drift_task(num_envs=N_LOCAL, seed=5, env_id_offset=shard_offset(rank, N_LOCAL))
+    orc = Oracle(spec.cfg); orc.startup(); orc.reset(None, 0)
+    slab = RolloutSlab(T, N_LOCAL, 14, 2, "cpu")
+    for t in range(T):
+        a = orc.synth_actions(t)
+        obs, rew, term, trunc = orc.step(a, t)
+        slab.actions[t] = torch.from_numpy(a); slab.obs[t] = torch.from_numpy(obs); slab.rewards[t] = torch.from_numpy(rew)
+        slab.terminated[t] = torch.from_numpy(term); slab.truncated[t] = torch.from_numpy(trunc)
+    g = slab.all_gather()
+    if rank == 0:
+        np.savez(Path(outdir) / "gathered.npz", obs=g.cat("obs").numpy(), rewards=g.cat("rewards").numpy(),
+                 actions=g.cat("actions").numpy(), terminated=g.cat("terminated").numpy(), truncated=g.cat("truncated").numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gather_equals_single_run(tmp_path):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    got = np.load(tmp_path / "gathered.npz")
+    sys.path[:0] = [str(ROOT / "tests")]
+    import wheeledlab_b200 as wl
+    from oracle_lib import Oracle
+    spec = wl.drift_task(num_envs=world * N_LOCAL, seed=5)
+    orc = Oracle(spec.cfg); orc.startup(); orc.reset(None, 0)
+    for t in range(T):
+        a = orc.synth_actions(t)
+        obs, rew, term, trunc = orc.step(a, t)
+        assert np.array_equal(got["actions"][t].view(np.uint32), a.view(np.uint32))
+        assert np.array_equal(got["obs"][t].view(np.uint32), obs.view(np.uint32)), f"shard/gather mismatch at t={t}"
+        assert np.array_equal(got["rewards"][t].view(np.uint32), rew.view(np.uint32))
+        assert np.array_equal(got["terminated"][t], term) and np.array_equal(got["truncated"][t], trunc)
+
+
+def test_slab_layout_single_process():
+    from wheeledlab_b200.distributed import RolloutSlab
+    s = RolloutSlab(4, 8, 14, 2, "cpu")
+    s.obs[2, 3, 5] = 7.0; s.rewards[1, 2] = -1.5; s.terminated[3, 7] = 1
+    g = s.all_gather()
+    assert g.cat("obs").shape == (4, 8, 14) and g.cat("obs")[2, 3, 5] == 7.0
+    assert g.cat("rewards")[1, 2] == -1.5 and g.cat("terminated")[3, 7] == 1
+    assert s.nbytes % 256 == 0
+    obs, rew, term, trunc = s.step_outputs(1)
+    assert obs.is_contiguous() and obs.data_ptr() == s.obs[1].data_ptr() and rew.shape == (8,)

@@ -1,0 +1,186 @@
+"""Lowering of the REFERENCE's own env-cfg objects onto the fused kernels' POD config.
+
+``gym.make("Isaac-MushrDriftRL-v0", cfg=env_cfg)`` hands the unmodified ``MushrDriftRLEnvCfg`` /
+``MushrElevationRLEnvCfg`` / ``F1TenthDriftRLEnvCfg`` instance (built against IsaacLab, or against the stand-in in
+``shims/isaaclab``) to the entry point.  This module reads that object -- terms are recognised by the NAME of the
+function they reference, values are taken from the cfg (weights, params, dt, decimation, scales, noise, DR ranges) --
+and fills a ``TaskSpec``.  A term the kernels do not implement raises ``NotImplementedError`` (no silent fallback).
+
+Reference files: wheeledlab_tasks/drifting/mushr_drift_env_cfg.py, f1tenth_drift_env_cfg.py,
+elevation/mushr_elevation_env_cfg.py, common/{actions,observations}.py.
+"""
+from __future__ import annotations
+
+import math
+
+from . import tasks as T
+
+_DRIFT_REWARDS = {"side_slip": 0, "vel_dist": 1, "track_progress_rate": 2, "turn_left_go_right": 3, "energy_through_turn": 4,
+                  "cross_track_dist": 5, "is_terminated_term": 6}
+_ALIASES = {"turn_left_go_right_f1": "turn_left_go_right"}    # f1tenth_drift_env_cfg.py:90-104: same math, other joint names
+_ELEV_REWARDS = {"goal_progress_rate": 0, "higher_elevation": 1, "is_falling_penalty": 2, "is_terminated_term": 3}
+_ACTION_KINDS = {"RCCarRWDAction": T.ACT_RWD, "RCCar4WDAction": T.ACT_4WD, "AckermannAction": T.ACT_ACKERMANN}
+_BOUND = {None: T.BOUND_NONE, "clip": T.BOUND_CLIP, "tanh": T.BOUND_TANH}
+
+
+def _fields(obj):
+    if obj is None:
+        return []
+    names = getattr(obj, "_cfg_fields", None) or [k for k in vars(obj) if not k.startswith("_")]
+    return [(k, getattr(obj, k)) for k in names if getattr(obj, k) is not None]
+
+
+def _fname(term):
+    f = term.func
+    return getattr(f, "__name__", type(f).__name__)
+
+
+def _lower_common(cfg, spec: T.TaskSpec):
+    c = spec.cfg
+    sim_dt, dec = float(cfg.sim.dt), int(cfg.decimation)
+    c.sim_dt, c.decimation = sim_dt, dec
+    c.substeps = max(1, math.ceil(sim_dt / 0.005 - 1e-9))
+    spec.episode_length_s = float(cfg.episode_length_s)
+    c.episode_length_s = spec.episode_length_s
+    c.max_episode_length = math.ceil(spec.episode_length_s / (sim_dt * dec))
+    # action term (exactly one in every registered task: actions.throttle_steer)
+    terms = _fields(cfg.actions)
+    if len(terms) != 1:
+        raise NotImplementedError(f"expected one action term, got {[k for k, _ in terms]}")
+    a = terms[0][1]
+    kind = a.class_type.__name__
+    if kind not in _ACTION_KINDS:
+        raise NotImplementedError(f"action term {kind} is not implemented by the fused step")
+    c.action_kind = _ACTION_KINDS[kind]
+    if a.bounding_strategy not in _BOUND:
+        raise NotImplementedError(f"bounding_strategy {a.bounding_strategy!r}")
+    c.bounding = _BOUND[a.bounding_strategy]
+    c.no_reverse = 1 if a.no_reverse else 0
+    c.act_scale[0], c.act_scale[1] = a.scale
+    c.act_offset[0], c.act_offset[1] = a.offset
+    c.base_length, c.base_width, c.wheel_radius_cfg = a.base_length, a.base_width, a.wheel_radius
+    # observation noise (BlindObsCfg) -- term order is fixed by the kernel; stds are read from the cfg
+    pol = cfg.observations.policy
+    c.enable_corruption = 1 if getattr(pol, "enable_corruption", False) else 0
+    # curriculum
+    spec.curriculum = []
+    for name, term in _fields(getattr(cfg, "curriculum", None)):
+        if _fname(term) != "increase_reward_weight_over_time":
+            raise NotImplementedError(f"curriculum term {name}: {_fname(term)}")
+        p = term.params
+        spec.curriculum.append(T.CurriculumTerm(name, p["reward_term_name"], float(p["increase"]),
+                                                int(p.get("episodes_per_increase", 1)), p.get("max_increases", math.inf)))
+
+
+def _lower_rewards(cfg, spec, table, handlers):
+    c = spec.cfg
+    names = [None] * len(table)
+    for k in range(T_MAX := 8):
+        c.rew_weight[k] = 0.0
+    for name, term in _fields(cfg.rewards):
+        fn = _ALIASES.get(_fname(term), _fname(term))
+        if fn not in table:
+            raise NotImplementedError(f"reward term {name} -> {fn} is not implemented by the fused step")
+        slot = table[fn]
+        names[slot] = name
+        c.rew_weight[slot] = float(term.weight)
+        handlers.get(fn, lambda p: None)(term.params or {})
+    if any(n is None for n in names):
+        missing = [f for f, s in table.items() if names[s] is None]
+        # absent terms keep weight 0 (skipped by the reward manager); give them placeholder names
+        for f in missing:
+            names[table[f]] = f
+    spec.reward_names = names
+    c.num_rew_terms = len(names)
+
+
+def spec_from_reference_cfg(cfg, env_id_offset: int = 0) -> T.TaskSpec:
+    """Build the TaskSpec for a reference env-cfg instance (Drift / F1Tenth drift / Elevation)."""
+    num_envs = int(cfg.scene.num_envs)
+    seed = int(cfg.seed) if getattr(cfg, "seed", None) is not None else 42
+    reward_funcs = {_ALIASES.get(_fname(t), _fname(t)) for _, t in _fields(cfg.rewards)}
+    if "side_slip" in reward_funcs or "cross_track_dist" in reward_funcs:
+        events = dict(_fields(cfg.events))
+        randomize = "change_wheel_friction" in events
+        drive = "4wd" if cfg.actions.throttle_steer.class_type.__name__ != "RCCarRWDAction" else "2wd"
+        usd = str(getattr(getattr(cfg.scene.robot, "spawn", None), "usd_path", "")).lower()
+        spec = T.drift_task(num_envs=num_envs, seed=seed, env_id_offset=env_id_offset, randomize=randomize, drive=drive,
+                            vehicle="f1tenth" if "f1tenth" in usd else "mushr")
+        c = spec.cfg
+        _lower_common(cfg, spec)
+
+        def h_slip(p):
+            c.slip_min_thresh, c.slip_max_thresh = p["min_thresh"], p["max_thresh"]
+            c.slip_min_vel_x = p.get("min_vel_x", 0.5)
+
+        def h_vel(p):
+            c.vel_speed_target = p.get("speed_target", T.MAX_SPEED)
+            c.vel_offset = p.get("offset", -T.MAX_SPEED ** 2)
+
+        def h_ctd(p):
+            c.trk_straight = p["straight"]
+            c.ctd_track_radius = p.get("track_radius", (T.CORNER_IN_RADIUS + T.CORNER_OUT_RADIUS) / 2)
+            c.ctd_offset = p.get("offset", -1.0)
+            if p.get("p", 1.0) != 1:
+                raise NotImplementedError("cross_track_dist with p != 1")
+
+        _lower_rewards(cfg, spec, _DRIFT_REWARDS, {
+            "side_slip": h_slip, "vel_dist": h_vel, "cross_track_dist": h_ctd,
+            "turn_left_go_right": lambda p: setattr(c, "tlgr_ang_vel_thresh", p.get("ang_vel_thresh", math.pi / 4)),
+            "energy_through_turn": lambda p: setattr(c, "energy_straight", p["straight"]),
+        })
+        for name, term in _fields(cfg.terminations):
+            fn = _fname(term)
+            if fn == "cart_off_track":
+                p = term.params
+                c.trk_straight, c.trk_corner_in, c.trk_corner_out = p["straight"], p["corner_in_radius"], p["corner_out_radius"]
+            elif fn != "time_out":
+                raise NotImplementedError(f"termination term {name} -> {fn}")
+        for name, term in events.items():
+            fn, p = _fname(term), term.params
+            if fn == "reset_root_state_along_track":
+                c.num_ref_poses = int(p.get("num_points", 20))
+                c.reset_pos_noise, c.reset_yaw_noise = p.get("pos_noise", 0.0), p.get("yaw_noise", 0.0)
+                poses = T.generate_reference_poses(c.num_ref_poses, p.get("track_radius", 0.8), p.get("track_straight_dist", 0.8), seed)
+                for k, v in enumerate(poses.reshape(-1)):
+                    c.ref_poses[k] = v
+            elif fn == "randomize_rigid_body_material":
+                c.dr_num_buckets = int(p["num_buckets"])
+                D, Cs = T.material_buckets(c.dr_num_buckets, p["static_friction_range"], p["dynamic_friction_range"],
+                                           p.get("make_consistent", False), c.ground_mu_s, c.ground_mu_d, seed)
+                for k in range(c.dr_num_buckets):
+                    c.dr_bucket_D[k], c.dr_bucket_C[k] = D[k], Cs[k]
+            elif fn == "randomize_actuator_gains":
+                c.dr_kd_range[0], c.dr_kd_range[1] = p["damping_distribution_params"]
+            elif fn == "randomize_rigid_body_mass":
+                c.dr_mass_add[0], c.dr_mass_add[1] = p["mass_distribution_params"]
+            elif fn == "push_by_setting_velocity":
+                vr = p["velocity_range"]
+                if "x" in vr:                                   # high-frequency push
+                    c.push_hf_interval[0], c.push_hf_interval[1] = term.interval_range_s
+                    c.push_hf_range[0], c.push_hf_range[1], c.push_hf_range[2] = vr["x"][1], vr.get("y", (0, 0))[1], vr["yaw"][1]
+                else:
+                    c.push_lf_interval[0], c.push_lf_interval[1] = term.interval_range_s
+                    c.push_lf_yaw = vr["yaw"][1]
+            elif fn == "disable_all_lidars":
+                pass                                            # no-op without omni.isaac.sensor (quirk Q15)
+            else:
+                raise NotImplementedError(f"event term {name} -> {fn}")
+        return spec
+    if "goal_progress_rate" in reward_funcs:
+        spec = T.elevation_task(num_envs=num_envs, seed=seed, env_id_offset=env_id_offset)
+        _lower_common(cfg, spec)
+        _lower_rewards(cfg, spec, _ELEV_REWARDS, {})
+        return spec
+    raise NotImplementedError(f"env cfg {type(cfg).__name__} is not one of the registered Drift / Elevation tasks")
+
+
+def env_from_reference_cfg(cfg, render_mode=None, device=None, **kwargs):
+    """Entry point used by ``shims/isaaclab/envs:ManagerBasedRLEnv`` (gym kwargs: cfg=<env cfg>)."""
+    from .env import ManagerBasedRLEnv
+    dev = device or getattr(getattr(cfg, "sim", None), "device", None) or "cuda:0"
+    env = ManagerBasedRLEnv(spec_from_reference_cfg(cfg), render_mode=render_mode, device=dev)
+    env.cfg = cfg                                   # writer.log_config(self.env.cfg, ...) (modified_rsl_rl_runner.py:42-44)
+    if not hasattr(cfg, "is_finite_horizon"):
+        cfg.is_finite_horizon = False
+    return env

@@ -297,7 +297,10 @@ wl_step_quad_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st
 // an mbarrier; out-of-raster elements are zero-filled by the hardware and never read), then 128 threads take the
 // 676 vertical rays as bilinear samples from shared memory and write obs[13:689] coalesced.
 // ---------------------------------------------------------------------------------------
-#define WL_TILE 40
+// window = WL_TILE_W x WL_TILE_H samples.  The footprint needs <= 38 samples per axis; TMA wants the innermost box
+// coordinate 16-byte aligned (ox % 4 == 0), so the window starts up to 3 samples early and is 44 wide.
+#define WL_TILE_W 44
+#define WL_TILE_H 40
 #define WL_SCAN_THREADS 128
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -306,7 +309,7 @@ template <bool USE_TMA>
 __global__ void __launch_bounds__(WL_SCAN_THREADS)
 wl_scan_kernel(const __grid_constant__ wl_config c, const __grid_constant__ CUtensorMap tmap, const float4* __restrict__ st,
                const float* __restrict__ hf, float* __restrict__ obs) {
-    __shared__ __align__(128) float tile[WL_TILE * WL_TILE];
+    __shared__ __align__(128) float tile[WL_TILE_W * WL_TILE_H];
     __shared__ __align__(8) unsigned long long mbar;
     const int n = c.num_envs;
     const int i = blockIdx.x;
@@ -319,7 +322,8 @@ wl_scan_kernel(const __grid_constant__ wl_config c, const __grid_constant__ CUte
     const float inv = 1.0f / c.hf_cell;
     // window origin (in samples): covers base +- (half*sqrt2 + 1 cell)
     const float reach = c.scan_half * 1.41421356237f + c.hf_cell;
-    const int ox = (int)floorf((bx - reach - c.hf_x0) * inv), oy = (int)floorf((by - reach - c.hf_y0) * inv);
+    const int ox = ((int)floorf((bx - reach - c.hf_x0) * inv)) & ~3;      // two's complement: rounds toward -inf
+    const int oy = (int)floorf((by - reach - c.hf_y0) * inv);
     if (USE_TMA) {
         if (threadIdx.x == 0) {
             const uint32_t mb = smem_u32(&mbar);
@@ -329,7 +333,7 @@ wl_scan_kernel(const __grid_constant__ wl_config c, const __grid_constant__ CUte
         __syncthreads();
         if (threadIdx.x == 0) {
             const uint32_t mb = smem_u32(&mbar), dst = smem_u32(tile);
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"((uint32_t)(WL_TILE * WL_TILE * 4)) : "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"((uint32_t)(WL_TILE_W * WL_TILE_H * 4)) : "memory");
             asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                          ::"r"(dst), "l"(&tmap), "r"(ox), "r"(oy), "r"(mb) : "memory");
         }
@@ -342,8 +346,8 @@ wl_scan_kernel(const __grid_constant__ wl_config c, const __grid_constant__ CUte
             }
         }
     } else {
-        for (int k = threadIdx.x; k < WL_TILE * WL_TILE; k += WL_SCAN_THREADS) {
-            int tx = k % WL_TILE, ty = k / WL_TILE, gx = ox + tx, gy = oy + ty;
+        for (int k = threadIdx.x; k < WL_TILE_W * WL_TILE_H; k += WL_SCAN_THREADS) {
+            int tx = k % WL_TILE_W, ty = k / WL_TILE_W, gx = ox + tx, gy = oy + ty;
             tile[k] = (gx >= 0 && gy >= 0 && gx < c.hf_nx && gy < c.hf_ny) ? __ldg(hf + (size_t)gy * c.hf_pitch + gx) : 0.0f;
         }
         __syncthreads();
@@ -360,8 +364,8 @@ wl_scan_kernel(const __grid_constant__ wl_config c, const __grid_constant__ CUte
             if (ix > c.hf_nx - 2) ix = c.hf_nx - 2;
             if (iy > c.hf_ny - 2) iy = c.hf_ny - 2;
             const float tx = fx - (float)ix, ty = fy - (float)iy;
-            const float* t0 = tile + (iy - oy) * WL_TILE + (ix - ox);
-            const float z00 = t0[0], z10 = t0[1], z01 = t0[WL_TILE], z11 = t0[WL_TILE + 1];
+            const float* t0 = tile + (iy - oy) * WL_TILE_W + (ix - ox);
+            const float z00 = t0[0], z10 = t0[1], z01 = t0[WL_TILE_W], z11 = t0[WL_TILE_W + 1];
             const float za = fm(z10 - z00, tx, z00), zb = fm(z11 - z01, tx, z01);
             const float hit = fm(zb - za, ty, za);
             const float hs = bz - hit - c.scan_offset;                           // mdp.height_scan
@@ -589,7 +593,7 @@ int wl_create(const wl_config* cfg, void* d_state, size_t state_bytes, const flo
         if (!fn || qres != cudaDriverEntryPointSuccess) { delete s; return fail(WL_ECUDA, "cuTensorMapEncodeTiled not available"); }
         cuuint64_t gdim[2] = {(cuuint64_t)cfg->hf_nx, (cuuint64_t)cfg->hf_ny};
         cuuint64_t gstride[1] = {(cuuint64_t)cfg->hf_pitch * sizeof(float)};
-        cuuint32_t box[2] = {WL_TILE, WL_TILE}, estr[2] = {1, 1};
+        cuuint32_t box[2] = {WL_TILE_W, WL_TILE_H}, estr[2] = {1, 1};
         CUresult cr = ((encode_fn)fn)(&s->tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)d_heightfield, gdim, gstride, box, estr,
                                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

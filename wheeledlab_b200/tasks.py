@@ -154,6 +154,33 @@ def _mushr_vehicle(cfg: WlConfig) -> None:
     cfg.gravity = 9.81
 
 
+def _f1tenth_vehicle(cfg: WlConfig) -> None:
+    """F1Tenth (Robots/F1TENTH/f1tenth.usd) + F1TENTH_4WD_ACTUATOR_CFG (wheeledlab_assets/f1tenth.py:9-27)."""
+    m = 4.1565 + 4 * 1.8001 + 2 * 0.0915 + 0.368            # base_link + wheels (1.8 kg each!) + rotators + hokuyo
+    cfg.mass_nominal = m
+    a, b, c = 0.50, 0.30, 0.12
+    _set(cfg.inertia_nominal, (m / 12 * (b * b + c * c), m / 12 * (a * a + c * c), m / 12 * (a * a + b * b)))
+    _set(cfg.com, (-0.0100, 0.0, 0.03))
+    cfg.hub_x_front, cfg.hub_x_rear, cfg.hub_y, cfg.hub_z = 0.194799, -0.170156, 0.142, 0.0205 - (-0.0343)
+    cfg.wheel_radius = 0.055
+    cfg.wheel_inertia = 0.5 * 1.8001 * 0.055 ** 2
+    cfg.wheel_damping = 0.0
+    cfg.hub_z = cfg.wheel_radius - 0.003                    # 3 mm static deflection at spawn
+    cfg.susp_k = m * 9.81 / (4 * 0.003)
+    cfg.susp_c = 2 * 0.7 * math.sqrt(cfg.susp_k * m / 4)
+    cfg.susp_travel, cfg.bump_k, cfg.comp_max, cfg.base_link_z = 0.01, 10 * cfg.susp_k, 0.03, 0.0
+    cfg.steer_inertia = 2.0e-3
+    cfg.tire_B, cfg.tire_v0 = 10.0, 0.5
+    cfg.tire_mx = 1.0 / (cfg.wheel_radius ** 2 / cfg.wheel_inertia + 4.0 / m)
+    cfg.tire_my = m / 4.0
+    cfg.gravity = 9.81
+    cfg.dc_saturation, cfg.dc_vel_limit = 1.0, 400.0
+    _set(cfg.dc_effort, (0.25,) * 4)
+    _set(cfg.dc_damping, (1100.0,) * 4)
+    cfg.steer_kp, cfg.steer_kd, cfg.steer_vel_limit = 120.0, 8.0, 10.0
+    cfg.steer_pos_limit = math.radians(45.0)
+
+
 def _hound_actuators(cfg: WlConfig, drive: str) -> None:
     """HOUND_SUS_2WD_ACTUATOR_CFG / HOUND_SUS_ACTUATOR_CFG (wheeledlab_assets/hound.py:4-52)."""
     cfg.dc_saturation, cfg.dc_vel_limit = 1.05, 450.0
@@ -169,7 +196,7 @@ def _hound_actuators(cfg: WlConfig, drive: str) -> None:
 
 
 def drift_task(num_envs: int = 1024, seed: int = 42, env_id_offset: int = 0, randomize: bool = True,
-               drive: str = "2wd") -> TaskSpec:
+               drive: str = "2wd", vehicle: str = "mushr") -> TaskSpec:
     """MushrDriftRLEnvCfg (drifting/mushr_drift_env_cfg.py:368-404); drive='4wd' gives the BASELINE 'HOUND 4WD' variant."""
     cfg = WlConfig()
     cfg.abi_version = WL_ABI_VERSION
@@ -187,8 +214,11 @@ def drift_task(num_envs: int = 1024, seed: int = 42, env_id_offset: int = 0, ran
     _set(cfg.act_scale, (MAX_SPEED, 0.488))
     _set(cfg.act_offset, (0.0, 0.0))
     cfg.base_length, cfg.base_width, cfg.wheel_radius_cfg = 0.325, 0.2, 0.05
-    _mushr_vehicle(cfg)
-    _hound_actuators(cfg, drive)
+    if vehicle == "f1tenth":
+        _f1tenth_vehicle(cfg)
+    else:
+        _mushr_vehicle(cfg)
+        _hound_actuators(cfg, drive)
     cfg.ground_mu_s, cfg.ground_mu_d = 1.1, 1.0                       # :45-49
     # startup DR (DriftEventsRandomCfg :95-154)
     cfg.dr_enable = 1 if randomize else 0
@@ -317,6 +347,11 @@ def make_task(name_or_id: str, **kw) -> TaskSpec:
         return drift_task(**kw)
     if name in ("drift_4wd", "hound_4wd"):
         return drift_task(drive="4wd", **kw)
+    if name == "f1tenth_drift":
+        spec = drift_task(drive="4wd", vehicle="f1tenth", **kw)
+        spec.cfg.base_length, spec.cfg.base_width = 0.365, 0.284          # F1Tenth4WDActionCfg, common/actions.py:64-66
+        spec.name = "f1tenth_drift"
+        return spec
     if name == "elevation":
         return elevation_task(**kw)
     raise NotImplementedError(f"task {name_or_id!r} is not implemented in this build")
