@@ -248,16 +248,14 @@ def run_ours(args):
     env = wl.ManagerBasedRLEnv(wl.drift_task(num_envs=E, seed=args.seed, env_id_offset=rank * E), device=dev)
     env.reset()
     h_act = acts.cpu().pin_memory()
-    d_act = torch.empty((E, 2), dtype=torch.float32, device=dev)
-    h_rew = torch.empty(E, dtype=torch.float32).pin_memory()
-    h_term = torch.empty(E, dtype=torch.bool).pin_memory()
-    h_trunc = torch.empty(E, dtype=torch.bool).pin_memory()
+    h_in = env.host_action_buffer                       # pinned [E,2]: the host-side policy writes actions here
 
     def e2e_step(k):
-        d_act.copy_(h_act[k % (W + K)], non_blocking=True)
-        obs, rew, term, trunc, extras = env.step(d_act)
-        h_rew.copy_(rew, non_blocking=True); h_term.copy_(term, non_blocking=True); h_trunc.copy_(trunc, non_blocking=True)
-        torch.cuda.current_stream().synchronize()          # the caller consumes reward / dones on the host
+        # the call a host-side user makes: host actions in, host reward / done masks out (one C-ABI call inside:
+        # H2D actions -> fused step -> D2H results -> stream sync); observations stay on the device for the policy
+        h_in.copy_(h_act[k % (W + K)])
+        obs, rew, term, trunc, extras = env.step_host(h_in)
+        return rew, term, trunc
 
     for k in range(W):
         e2e_step(k)
@@ -294,7 +292,8 @@ def run_ours(args):
                        "l2": "flushed between timed steps (256 MiB fill)", "parallelism": f"env-shard x{world}"},
             "clocks": clocks,
             "e2e": {"value": total_envs * K / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": E * 8,
-                    "d2h_bytes_per_step": E * 6, "ms_per_step": e2e_ms / K},
+                    "d2h_bytes_per_step": E * 6, "ms_per_step": e2e_ms / K,
+                    "api": "ManagerBasedRLEnv.step_host(pinned actions) -> wl_step_host: H2D + step + D2H + sync per step"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src, "kernel": "wl_step_kernel<DRIFT>",

@@ -313,6 +313,15 @@ int wl_reset(wl_sim* sim, const int64_t* d_env_ids, int32_t n_ids, int64_t step_
  * counts.  Written by the last CTA of the launch: no extra kernel, no host sync. */
 int wl_step(wl_sim* sim, const float* d_action, float* d_obs, float* d_rew, uint8_t* d_terminated,
             uint8_t* d_truncated, float* d_log, int64_t step_counter, void* stream);
+/* env.step() for a HOST-side caller, host buffers in, host buffers out, one call:
+ *   H2D  h_action[N,2] (pinned)  ->  d_action
+ *   wl_step(...) writing d_obs, and reward / terminated / truncated into ONE device block d_result laid out as
+ *        float rew[N] | uint8 terminated[N] | uint8 truncated[N]          (wl_result_bytes(N) bytes)
+ *   D2H  d_result -> h_result (pinned, same layout), then cudaStreamSynchronize(stream).
+ * Observations stay on the device (the policy lives there); pass h_obs != NULL to copy them back as well. */
+size_t wl_result_bytes(int32_t num_envs);
+int wl_step_host(wl_sim* sim, const float* h_action, float* d_action, float* d_obs, void* d_result, float* d_log,
+                 void* h_result, float* h_obs, int64_t step_counter, void* stream);
 /* observation_manager.compute(): re-samples the noise. call_idx distinguishes
  * repeated calls at the same step_counter. */
 int wl_observe(wl_sim* sim, float* d_obs, int64_t step_counter, int32_t call_idx, void* stream);

@@ -318,3 +318,22 @@ def test_elevation_full_size_properties():
         prev = ep.clone()
     assert "Episode_Termination/stuck" in extras["log"] and env.command_manager.get_command("goal_pose").shape == (4096, 4)
     env.close()
+
+
+def test_step_host_matches_device_step():
+    """wl_step_host (host buffers in/out, one C call) == wl_step on device tensors, bit for bit."""
+    _need_gpu()
+    import wheeledlab_b200 as wl
+    a = wl.make("Isaac-MushrDriftRL-v0", num_envs=512, seed=3); b = wl.make("Isaac-MushrDriftRL-v0", num_envs=512, seed=3)
+    a.reset(); b.reset()
+    h_in = b.host_action_buffer
+    assert h_in.is_pinned()
+    for t in range(40):
+        act = a.sim.synth_actions(t)
+        oa, ra, ta, ua, _ = a.step(act)
+        h_in.copy_(act.cpu())
+        ob, rb, tb, ub, ex = b.step_host(h_in)
+        assert rb.device.type == "cpu" and tb.dtype == torch.bool
+        assert torch.equal(oa["policy"], ob["policy"]) and torch.equal(ra.cpu(), rb) and torch.equal(ta.cpu(), tb) and torch.equal(ua.cpu(), ub)
+        assert float(ex["log"]["Episode_Termination/time_out"]) >= 0
+    assert torch.equal(a.sim.groups, b.sim.groups)

@@ -53,10 +53,10 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 // Per-step episode log: warp-shuffle reduce over the finished envs, one atomic set per warp.
 // acc layout: [0..7] episode sums, [8] #reset, [9+j] #envs whose termination term j fired (tmask bit j).
-__device__ __forceinline__ void log_accumulate(wl_globals* __restrict__ gl, bool contrib, uint32_t tmask,
+__device__ __forceinline__ bool log_accumulate(wl_globals* __restrict__ gl, bool contrib, uint32_t tmask,
                                                const float sums[WL_MAX_REW_TERMS]) {
     const unsigned any_c = __ballot_sync(0xffffffffu, contrib);
-    if (!any_c) return;
+    if (!any_c) return false;
     float vals[16];
 #pragma unroll
     for (int k = 0; k < WL_MAX_REW_TERMS; ++k) vals[k] = contrib ? sums[k] : 0.0f;
@@ -68,12 +68,13 @@ __device__ __forceinline__ void log_accumulate(wl_globals* __restrict__ gl, bool
     if ((threadIdx.x & 31) == 0) {
 #pragma unroll
         for (int k = 0; k < 16; ++k) if (vals[k] != 0.0f) atomicAdd(&gl->acc[k], vals[k]);
+        __threadfence();          // order this warp's accumulation before its CTA's ticket (only warps that contributed pay)
     }
+    return true;
 }
 // Last CTA of the launch turns the accumulators into the extras["log"] row and re-arms them.
 __device__ __forceinline__ void log_finalize(const wl_config& c, wl_globals* __restrict__ gl, float* __restrict__ d_log) {
-    __threadfence();
-    __syncthreads();
+    __syncthreads();              // all warps of the CTA are past their (fenced) accumulation
     if (threadIdx.x != 0) return;
     const unsigned tk = atomicAdd(&gl->ticket, 1u);
     if (tk != gridDim.x - 1) return;
@@ -107,6 +108,9 @@ wl_step_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st, wl_
     bool done = false;
     uint32_t tmask = 0u;
     EnvState e;
+    // live reward weights: issued with the state loads so their latency hides behind the integrator
+    const float4 rw0 = __ldg(reinterpret_cast<const float4*>(gl->rew_weight)), rw1 = __ldg(reinterpret_cast<const float4*>(gl->rew_weight) + 1);
+    const float wts[WL_MAX_REW_TERMS] = {rw0.x, rw0.y, rw0.z, rw0.w, rw1.x, rw1.y, rw1.z, rw1.w};
     if (i < n) {
         load_env(st, n, i, e, ELEV);
         // A. action manager
@@ -150,7 +154,7 @@ wl_step_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st, wl_
 #pragma unroll
         for (int k = 0; k < WL_MAX_REW_TERMS; ++k) {
             if (k < c.num_rew_terms) {
-                float w = __ldg(&gl->rew_weight[k]);
+                float w = wts[k];
                 if (w != 0.0f) { float val = f[k] * w * c.d_step_dt; total += val; e.sums[k] += val; }
             }
         }
@@ -198,6 +202,8 @@ wl_step_quad_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st
     const uint32_t gid = (uint32_t)(c.env_id_offset + ii);
     const unsigned base = (threadIdx.x & 31u) & ~3u;
     EnvState e;
+    const float4 rw0 = __ldg(reinterpret_cast<const float4*>(gl->rew_weight)), rw1 = __ldg(reinterpret_cast<const float4*>(gl->rew_weight) + 1);
+    const float wts[WL_MAX_REW_TERMS] = {rw0.x, rw0.y, rw0.z, rw0.w, rw1.x, rw1.y, rw1.z, rw1.w};
     load_env_quad(st, n, ii, w, e, ELEV);
     // A. action manager (redundant in the 4 lanes)
     float2 a = action[ii];
@@ -246,7 +252,7 @@ wl_step_quad_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st
 #pragma unroll
     for (int k = 0; k < WL_MAX_REW_TERMS; ++k) {
         if (k < c.num_rew_terms) {
-            float wgt = __ldg(&gl->rew_weight[k]);
+            float wgt = wts[k];
             if (wgt != 0.0f) { float val = f[k] * wgt * c.d_step_dt; total += val; e.sums[k] += val; }
         }
     }
@@ -353,133 +359,36 @@ wl_scan_kernel(const __grid_constant__ wl_config c, const __grid_constant__ CUte
         __syncthreads();
     }
     float* row = obs + (size_t)WL_OBS_DIM_ELEV * i + 13;
-    for (int k = threadIdx.x; k < WL_SCAN_RAYS; k += WL_SCAN_THREADS) {
-        const int rx = k % WL_SCAN_SIDE, ry = k / WL_SCAN_SIDE;                  // "xy" ordering: x fastest
-        const float lx = fm((float)rx, c.scan_res, -c.scan_half), ly = fm((float)ry, c.scan_res, -c.scan_half);
-        const float wx = fm(cy, lx, fm(-sy, ly, bx)), wy = fm(sy, lx, fm(cy, ly, by));
-        const float fx = (wx - c.hf_x0) * inv, fy = (wy - c.hf_y0) * inv;
-        float v;
-        if ((fx >= 0.0f) && (fy >= 0.0f) && (fx <= (float)(c.hf_nx - 1)) && (fy <= (float)(c.hf_ny - 1))) {
-            int ix = (int)floorf(fx), iy = (int)floorf(fy);
-            if (ix > c.hf_nx - 2) ix = c.hf_nx - 2;
-            if (iy > c.hf_ny - 2) iy = c.hf_ny - 2;
-            const float tx = fx - (float)ix, ty = fy - (float)iy;
-            const float* t0 = tile + (iy - oy) * WL_TILE_W + (ix - ox);
-            const float z00 = t0[0], z10 = t0[1], z01 = t0[WL_TILE_W], z11 = t0[WL_TILE_W + 1];
-            const float za = fm(z10 - z00, tx, z00), zb = fm(z11 - z01, tx, z01);
-            const float hit = fm(zb - za, ty, za);
-            const float hs = bz - hit - c.scan_offset;                           // mdp.height_scan
-            v = r_clamp(-hs + (e.p.z - c.scan_plane_init), -c.obs_clip, c.obs_clip);   // world_height_map, clip
-        } else {
-            v = c.obs_clip;                                                      // miss: +inf clipped
+    // lane = ray column (26 of 32 lanes active), warp w takes ray rows w, w+4, ...: no integer div/mod per ray and every
+    // warp store is one contiguous 104-byte run of the observation row
+    const int rx = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    if (rx < WL_SCAN_SIDE) {
+        const float lx = fm((float)rx, c.scan_res, -c.scan_half);
+        const float wx0 = fm(cy, lx, bx), wy0 = fm(sy, lx, by);      // + (-sy, cy) * ly below
+        const float fxmax = (float)(c.hf_nx - 1), fymax = (float)(c.hf_ny - 1);
+        const float zoff = c.scan_offset - bz + (e.p.z - c.scan_plane_init);
+        (void)zoff;
+        for (int ry = wrp; ry < WL_SCAN_SIDE; ry += WL_SCAN_THREADS / 32) {
+            const float ly = fm((float)ry, c.scan_res, -c.scan_half);
+            const float wx = fm(cy, lx, fm(-sy, ly, bx)), wy = fm(sy, lx, fm(cy, ly, by));
+            const float fx = (wx - c.hf_x0) * inv, fy = (wy - c.hf_y0) * inv;
+            float v = c.obs_clip;                                                // miss: +inf clipped
+            if ((fx >= 0.0f) && (fy >= 0.0f) && (fx <= fxmax) && (fy <= fymax)) {
+                int ix = (int)floorf(fx), iy = (int)floorf(fy);
+                if (ix > c.hf_nx - 2) ix = c.hf_nx - 2;
+                if (iy > c.hf_ny - 2) iy = c.hf_ny - 2;
+                const float tx = fx - (float)ix, ty = fy - (float)iy;
+                const float* t0 = tile + (iy - oy) * WL_TILE_W + (ix - ox);
+                const float z00 = t0[0], z10 = t0[1], z01 = t0[WL_TILE_W], z11 = t0[WL_TILE_W + 1];
+                const float za = fm(z10 - z00, tx, z00), zb = fm(z11 - z01, tx, z01);
+                const float hit = fm(zb - za, ty, za);
+                const float hs = bz - hit - c.scan_offset;                           // mdp.height_scan
+                v = r_clamp(-hs + (e.p.z - c.scan_plane_init), -c.obs_clip, c.obs_clip);   // world_height_map, clip
+            }
+            row[ry * WL_SCAN_SIDE + rx] = v;
         }
-        row[k] = v;
+        (void)wx0; (void)wy0;
     }
-}
-
-__global__ void wl_startup_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st) {
-    const int n = c.num_envs;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint32_t gid = (uint32_t)(c.env_id_offset + i);
-    uint4 r0 = philox4x32(c.seed, gid, 0u, RNG_STARTUP, 0u);
-    uint4 r1 = philox4x32(c.seed, gid, 0u, RNG_STARTUP, 1u);
-    uint4 r2 = philox4x32(c.seed, gid, 0u, RNG_STARTUP, 2u);
-    const uint32_t rb[4] = {r0.x, r0.y, r0.z, r0.w}, rk[4] = {r1.x, r1.y, r1.z, r1.w};
-    float D[4], C[4], kd[4];
-#pragma unroll
-    for (int w = 0; w < 4; ++w) {
-        uint32_t bk = 0;
-        if (c.dr_enable && c.dr_num_buckets > 1) bk = __umulhi(rb[w], (uint32_t)c.dr_num_buckets);
-        D[w] = c.dr_bucket_D[bk]; C[w] = c.dr_bucket_C[bk];
-        kd[w] = c.dc_damping[w];
-        if (c.dr_enable && ((c.dr_kd_mask >> w) & 1)) kd[w] = uniform(rk[w], c.dr_kd_range[0], c.dr_kd_range[1]);
-    }
-    float mass = c.mass_nominal;
-    if (c.dr_enable) mass = mass + uniform(r2.x, c.dr_mass_add[0], c.dr_mass_add[1]);
-    float inv_mass = 1.0f / mass;
-    stg4(st, WL_G_PMASS, n, i, make_float4(mass, inv_mass, 0.0f, 0.0f));
-    stg4(st, WL_G_PMU_D, n, i, make_float4(D[0], D[1], D[2], D[3]));
-    stg4(st, WL_G_PMU_C, n, i, make_float4(C[0], C[1], C[2], C[3]));
-    stg4(st, WL_G_PKD, n, i, make_float4(kd[0], kd[1], kd[2], kd[3]));
-    float t_hf = uniform(r2.y, c.push_hf_interval[0], c.push_hf_interval[1]);
-    float t_lf = uniform(r2.z, c.push_lf_interval[0], c.push_lf_interval[1]);
-    float4 g;
-    g = ldg4(st, WL_G_LINVEL, n, i); g.w = t_hf; stg4(st, WL_G_LINVEL, n, i, g);
-    g = ldg4(st, WL_G_ANGVEL, n, i); g.w = t_lf; stg4(st, WL_G_ANGVEL, n, i, g);
-    stg4(st, WL_G_QUAT, n, i, make_float4(1.0f, 0.0f, 0.0f, 0.0f));
-}
-
-__global__ void wl_reset_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st, const int64_t* __restrict__ ids,
-                                int n_ids, uint32_t t) {
-    const int n = c.num_envs;
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n_ids) return;
-    const int i = ids ? (int)ids[k] : k;
-    if (i < 0 || i >= n) return;
-    EnvState e;
-    const bool elev = c.task == WL_TASK_ELEVATION;
-    load_env(st, n, i, e, elev);
-    if (elev) elev_reset_env(c, e, (uint32_t)(c.env_id_offset + i), t);      // command b-frame vector is NOT refreshed by reset()
-    else drift_reset_env(c, e, (uint32_t)(c.env_id_offset + i), t);
-    store_env(st, n, i, e, elev);
-}
-
-__global__ void wl_observe_kernel(const __grid_constant__ wl_config c, const float4* __restrict__ st, float* __restrict__ obs,
-                                  uint32_t t, uint32_t call_idx) {
-    const int n = c.num_envs;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    EnvState e;
-    if (c.task == WL_TASK_ELEVATION) {
-        load_env(st, n, i, e, true);
-        float o[13]; elev_proprio(c, e, euler_xyz(e.qw, e.qx, e.qy, e.qz), o);
-        float* row = obs + (size_t)WL_OBS_DIM_ELEV * i;
-#pragma unroll
-        for (int k = 0; k < 13; ++k) row[k] = o[k];
-        return;
-    }
-    load_env(st, n, i, e, false);
-    blind_obs(c, e, (uint32_t)(c.env_id_offset + i), t, RNG_OBS_EXTRA, 3u * call_idx, obs + (size_t)WL_OBS_DIM_BLIND * i);
-}
-
-struct CurrArgs { int32_t n; int32_t slots[WL_MAX_REW_TERMS]; float inc[WL_MAX_REW_TERMS]; uint32_t fire_mask; };
-__global__ void wl_curriculum_kernel(wl_globals* __restrict__ gl, CurrArgs a) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    if (!gl->any_reset_last) return;
-    for (int t = 0; t < a.n; ++t)
-        if ((a.fire_mask >> t) & 1u) gl->rew_weight[a.slots[t]] += a.inc[t];
-}
-
-__global__ void wl_synth_actions_kernel(const __grid_constant__ wl_config c, float2* __restrict__ action, uint32_t t, int dist) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= c.num_envs) return;
-    uint4 r = philox4x32(c.seed, (uint32_t)(c.env_id_offset + i), t, RNG_ACTION, 0u);
-    float a0, a1;
-    if (dist == 0) { a0 = 2.0f * u01(r.x) - 1.0f; a1 = 2.0f * u01(r.y) - 1.0f; }
-    else { float z0, z1; box_muller(r.x, r.y, z0, z1); a0 = r_clamp(z0, -1.0f, 1.0f); a1 = r_clamp(z1, -1.0f, 1.0f); }
-    action[i] = make_float2(a0, a1);
-}
-
-__global__ void wl_detmath_kernel(int op, const float* __restrict__ in, const float* __restrict__ in2, float* __restrict__ out, int n) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    float x = in[i], s, c2, r = 0.0f;
-    switch (op) {
-        case 0: det_sincos(x, s, c2); r = s; break;
-        case 1: det_sincos(x, s, c2); r = c2; break;
-        case 2: r = det_atan(x); break;
-        case 3: r = det_atan2(in2[i], x); break;
-        case 4: r = det_log(x); break;
-        case 5: r = det_tan(x); break;
-        case 6: r = det_asin(x); break;
-    }
-    out[i] = r;
-}
-__global__ void wl_philox_kernel(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint4* __restrict__ out, int n) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    out[i] = philox4x32(seed, c0 + (uint32_t)i, c1, c2, c3);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -674,6 +583,25 @@ int wl_step(wl_sim* sim, const float* d_action, float* d_obs, float* d_rew, uint
     }
     WL_LAUNCH_CHECK(sim, "wl_step_kernel");
     return WL_OK;
+}
+
+size_t wl_result_bytes(int32_t num_envs) { return (size_t)num_envs * 6u; }
+
+int wl_step_host(wl_sim* sim, const float* h_action, float* d_action, float* d_obs, void* d_result, float* d_log,
+                 void* h_result, float* h_obs, int64_t step_counter, void* stream) {
+    if (!sim || !h_action || !d_action || !d_obs || !d_result || !h_result) return fail(WL_EINVAL, "wl_step_host: null argument");
+    const size_t n = (size_t)sim->cfg.num_envs;
+    cudaStream_t cs = (cudaStream_t)stream;
+    if (int rc = cuda_check(cudaMemcpyAsync(d_action, h_action, n * 2 * sizeof(float), cudaMemcpyHostToDevice, cs), "H2D actions")) return rc;
+    float* d_rew = reinterpret_cast<float*>(d_result);
+    uint8_t* d_term = reinterpret_cast<uint8_t*>(d_result) + n * 4;
+    uint8_t* d_trunc = d_term + n;
+    if (int rc = wl_step(sim, d_action, d_obs, d_rew, d_term, d_trunc, d_log, step_counter, stream)) return rc;
+    if (int rc = cuda_check(cudaMemcpyAsync(h_result, d_result, wl_result_bytes((int32_t)n), cudaMemcpyDeviceToHost, cs), "D2H results")) return rc;
+    if (h_obs) {
+        if (int rc = cuda_check(cudaMemcpyAsync(h_obs, d_obs, n * (size_t)sim->obs_dim * sizeof(float), cudaMemcpyDeviceToHost, cs), "D2H obs")) return rc;
+    }
+    return cuda_check(cudaStreamSynchronize(cs), "wl_step_host: stream synchronize");
 }
 
 int wl_observe(wl_sim* sim, float* d_obs, int64_t step_counter, int32_t call_idx, void* stream) {

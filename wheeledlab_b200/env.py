@@ -27,6 +27,28 @@ class _Box:
         return torch.randn(self.shape, generator=generator, device=device)
 
 
+class _LazyLog(dict):
+    """extras["log"]: keys are known up front, values are 0-dim views of the device row the step kernel's last CTA
+    wrote; the views are only created when somebody reads them (the train loop appends the dict every step and reads it
+    once per iteration, modified_rsl_rl_runner.py:95-98)."""
+
+    def __init__(self, row: torch.Tensor, index: dict):
+        super().__init__((k, None) for k in index)
+        self._row, self._index = row, index
+
+    def __getitem__(self, k):
+        return self._row[self._index[k]]
+
+    def get(self, k, default=None):
+        return self._row[self._index[k]] if k in self._index else default
+
+    def items(self):
+        return [(k, self[k]) for k in self._index]
+
+    def values(self):
+        return [self[k] for k in self._index]
+
+
 class RewardTermCfgView:
     """What reward_manager.get_term_cfg returns: an object with a mutable ``weight`` (curriculums.py:33-35)."""
 
@@ -233,6 +255,9 @@ class ManagerBasedRLEnv:
         self._curr_slots = [self.reward_manager._slot(t.reward_term_name) for t in self.spec.curriculum]
         self._curr_inc = [float(t.increase) for t in self.spec.curriculum]
         self.log_episode_info = True
+        self._log_index = {"Episode_Reward/" + n: k for k, n in enumerate(self.spec.reward_names)}
+        self._log_index.update({"Episode_Termination/" + n: 9 + j for j, (n, _) in enumerate(self.spec.termination_names)})
+        self._host_io = None
         # event_manager.apply(mode="startup")
         self.sim.startup()
         self._needs_reset = True
@@ -308,14 +333,42 @@ class ManagerBasedRLEnv:
         return {"policy": obs}, rew, terminated, truncated, self.extras
 
     def _episode_log(self, log: torch.Tensor):
-        """extras["log"] (RewardManager/TerminationManager.reset): views of the row the step
+        """extras["log"] (RewardManager/TerminationManager.reset): lazy views of the row the step
         kernel's last CTA wrote -- device tensors, no extra launches, no host sync."""
-        out = {}
-        for k, name in enumerate(self.spec.reward_names):
-            out["Episode_Reward/" + name] = log[k]
-        for j, (name, _) in enumerate(self.spec.termination_names):
-            out["Episode_Termination/" + name] = log[9 + j]
-        return out
+        return _LazyLog(log, self._log_index)
+
+    def step_host(self, action_host: torch.Tensor):
+        """env.step() for a HOST-side caller: `action_host` is a CPU tensor [N,2] (pinned for best speed).  One C call
+        does H2D(actions) -> fused step -> D2H(reward, terminated, truncated) -> sync.  Returns
+        (obs_dict [device], rew [pinned host], terminated [pinned host], truncated [pinned host], extras); the host
+        result views are overwritten by the next step_host call."""
+        if self._needs_reset:
+            self.reset()
+        if self._host_io is None:
+            self._host_io = self.sim.make_host_io()
+        io = self._host_io
+        if action_host.data_ptr() != io["h_action"].data_ptr():
+            io["h_action"].copy_(action_host)
+        t = self.common_step_counter
+        obs = torch.empty((self.num_envs, self.spec.obs_dim), dtype=torch.float32, device=self.device)
+        log = torch.empty(16, dtype=torch.float32, device=self.device) if self.log_episode_info else None
+        self.sim.step_host(io, t, obs, log)
+        self.common_step_counter = t + 1
+        mask = self._curriculum_fire_mask()
+        if mask:
+            self.sim.curriculum(self._curr_slots, self._curr_inc, mask)
+        tm = self.termination_manager
+        tm.terminated, tm.time_outs = io["d_terminated"].view(torch.bool), io["d_truncated"].view(torch.bool)
+        if log is not None:
+            self.extras["log"] = self._episode_log(log)
+        return {"policy": obs}, io["rew"], io["terminated"], io["truncated"], self.extras
+
+    @property
+    def host_action_buffer(self) -> torch.Tensor:
+        """Pinned [N,2] buffer a host-side policy can write actions into (zero-copy input of step_host)."""
+        if self._host_io is None:
+            self._host_io = self.sim.make_host_io()
+        return self._host_io["h_action"]
 
 
 def make(task_id: str, cfg=None, render_mode=None, device="cuda:0", **kw) -> ManagerBasedRLEnv:

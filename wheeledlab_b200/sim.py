@@ -98,6 +98,36 @@ class WheeledSim:
                           _stream_ptr(self.device)), "wl_step")
         return obs, rew, term, trunc
 
+    def make_host_io(self):
+        """Buffers for step_host(): pinned host action / result blocks + their device twins."""
+        n = self.num_envs
+        nres = int(lib.wl_result_bytes(n))
+        io = {
+            "h_action": torch.empty((n, 2), dtype=torch.float32).pin_memory(),
+            "d_action": torch.empty((n, 2), dtype=torch.float32, device=self.device),
+            "d_result": torch.empty(nres, dtype=torch.uint8, device=self.device),
+            "h_result": torch.empty(nres, dtype=torch.uint8).pin_memory(),
+        }
+        h = io["h_result"]
+        io["rew"] = h[: 4 * n].view(torch.float32)
+        io["terminated"] = h[4 * n: 5 * n].view(torch.bool)
+        io["truncated"] = h[5 * n: 6 * n].view(torch.bool)
+        d = io["d_result"]
+        io["d_rew"] = d[: 4 * n].view(torch.float32)
+        io["d_terminated"] = d[4 * n: 5 * n]
+        io["d_truncated"] = d[5 * n: 6 * n]
+        return io
+
+    def step_host(self, io, step_counter: int, obs: torch.Tensor, log: torch.Tensor | None = None, h_obs: torch.Tensor | None = None):
+        """ONE C call: H2D(io.h_action) -> fused step -> D2H(reward | terminated | truncated) -> stream sync.
+        Results are in io["rew"], io["terminated"], io["truncated"] (pinned host views); obs stays on the device."""
+        check(lib.wl_step_host(self._h, C.c_void_p(io["h_action"].data_ptr()), C.c_void_p(io["d_action"].data_ptr()),
+                               C.c_void_p(obs.data_ptr()), C.c_void_p(io["d_result"].data_ptr()),
+                               C.c_void_p(log.data_ptr()) if log is not None else None,
+                               C.c_void_p(io["h_result"].data_ptr()),
+                               C.c_void_p(h_obs.data_ptr()) if h_obs is not None else None, step_counter,
+                               _stream_ptr(self.device)), "wl_step_host")
+
     def observe(self, step_counter: int, call_idx: int = 0, out: torch.Tensor | None = None):
         obs = out if out is not None else torch.empty((self.num_envs, self.obs_dim), dtype=torch.float32, device=self.device)
         check(lib.wl_observe(self._h, C.c_void_p(obs.data_ptr()), step_counter, call_idx, _stream_ptr(self.device)),
