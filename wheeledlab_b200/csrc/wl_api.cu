@@ -391,6 +391,111 @@ wl_scan_kernel(const __grid_constant__ wl_config c, const __grid_constant__ CUte
     }
 }
 
+__global__ void wl_startup_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st) {
+    const int n = c.num_envs;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t gid = (uint32_t)(c.env_id_offset + i);
+    uint4 r0 = philox4x32(c.seed, gid, 0u, RNG_STARTUP, 0u);
+    uint4 r1 = philox4x32(c.seed, gid, 0u, RNG_STARTUP, 1u);
+    uint4 r2 = philox4x32(c.seed, gid, 0u, RNG_STARTUP, 2u);
+    const uint32_t rb[4] = {r0.x, r0.y, r0.z, r0.w}, rk[4] = {r1.x, r1.y, r1.z, r1.w};
+    float D[4], C[4], kd[4];
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+        uint32_t bk = 0;
+        if (c.dr_enable && c.dr_num_buckets > 1) bk = __umulhi(rb[w], (uint32_t)c.dr_num_buckets);
+        D[w] = c.dr_bucket_D[bk]; C[w] = c.dr_bucket_C[bk];
+        kd[w] = c.dc_damping[w];
+        if (c.dr_enable && ((c.dr_kd_mask >> w) & 1)) kd[w] = uniform(rk[w], c.dr_kd_range[0], c.dr_kd_range[1]);
+    }
+    float mass = c.mass_nominal;
+    if (c.dr_enable) mass = mass + uniform(r2.x, c.dr_mass_add[0], c.dr_mass_add[1]);
+    float inv_mass = 1.0f / mass;
+    stg4(st, WL_G_PMASS, n, i, make_float4(mass, inv_mass, 0.0f, 0.0f));
+    stg4(st, WL_G_PMU_D, n, i, make_float4(D[0], D[1], D[2], D[3]));
+    stg4(st, WL_G_PMU_C, n, i, make_float4(C[0], C[1], C[2], C[3]));
+    stg4(st, WL_G_PKD, n, i, make_float4(kd[0], kd[1], kd[2], kd[3]));
+    float t_hf = uniform(r2.y, c.push_hf_interval[0], c.push_hf_interval[1]);
+    float t_lf = uniform(r2.z, c.push_lf_interval[0], c.push_lf_interval[1]);
+    float4 g;
+    g = ldg4(st, WL_G_LINVEL, n, i); g.w = t_hf; stg4(st, WL_G_LINVEL, n, i, g);
+    g = ldg4(st, WL_G_ANGVEL, n, i); g.w = t_lf; stg4(st, WL_G_ANGVEL, n, i, g);
+    stg4(st, WL_G_QUAT, n, i, make_float4(1.0f, 0.0f, 0.0f, 0.0f));
+}
+
+__global__ void wl_reset_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st, const int64_t* __restrict__ ids,
+                                int n_ids, uint32_t t) {
+    const int n = c.num_envs;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_ids) return;
+    const int i = ids ? (int)ids[k] : k;
+    if (i < 0 || i >= n) return;
+    EnvState e;
+    const bool elev = c.task == WL_TASK_ELEVATION;
+    load_env(st, n, i, e, elev);
+    if (elev) elev_reset_env(c, e, (uint32_t)(c.env_id_offset + i), t);      // command b-frame vector is NOT refreshed by reset()
+    else drift_reset_env(c, e, (uint32_t)(c.env_id_offset + i), t);
+    store_env(st, n, i, e, elev);
+}
+
+__global__ void wl_observe_kernel(const __grid_constant__ wl_config c, const float4* __restrict__ st, float* __restrict__ obs,
+                                  uint32_t t, uint32_t call_idx) {
+    const int n = c.num_envs;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    EnvState e;
+    if (c.task == WL_TASK_ELEVATION) {
+        load_env(st, n, i, e, true);
+        float o[13]; elev_proprio(c, e, euler_xyz(e.qw, e.qx, e.qy, e.qz), o);
+        float* row = obs + (size_t)WL_OBS_DIM_ELEV * i;
+#pragma unroll
+        for (int k = 0; k < 13; ++k) row[k] = o[k];
+        return;
+    }
+    load_env(st, n, i, e, false);
+    blind_obs(c, e, (uint32_t)(c.env_id_offset + i), t, RNG_OBS_EXTRA, 3u * call_idx, obs + (size_t)WL_OBS_DIM_BLIND * i);
+}
+
+struct CurrArgs { int32_t n; int32_t slots[WL_MAX_REW_TERMS]; float inc[WL_MAX_REW_TERMS]; uint32_t fire_mask; };
+__global__ void wl_curriculum_kernel(wl_globals* __restrict__ gl, CurrArgs a) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (!gl->any_reset_last) return;
+    for (int t = 0; t < a.n; ++t)
+        if ((a.fire_mask >> t) & 1u) gl->rew_weight[a.slots[t]] += a.inc[t];
+}
+
+__global__ void wl_synth_actions_kernel(const __grid_constant__ wl_config c, float2* __restrict__ action, uint32_t t, int dist) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c.num_envs) return;
+    uint4 r = philox4x32(c.seed, (uint32_t)(c.env_id_offset + i), t, RNG_ACTION, 0u);
+    float a0, a1;
+    if (dist == 0) { a0 = 2.0f * u01(r.x) - 1.0f; a1 = 2.0f * u01(r.y) - 1.0f; }
+    else { float z0, z1; box_muller(r.x, r.y, z0, z1); a0 = r_clamp(z0, -1.0f, 1.0f); a1 = r_clamp(z1, -1.0f, 1.0f); }
+    action[i] = make_float2(a0, a1);
+}
+
+__global__ void wl_detmath_kernel(int op, const float* __restrict__ in, const float* __restrict__ in2, float* __restrict__ out, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float x = in[i], s, c2, r = 0.0f;
+    switch (op) {
+        case 0: det_sincos(x, s, c2); r = s; break;
+        case 1: det_sincos(x, s, c2); r = c2; break;
+        case 2: r = det_atan(x); break;
+        case 3: r = det_atan2(in2[i], x); break;
+        case 4: r = det_log(x); break;
+        case 5: r = det_tan(x); break;
+        case 6: r = det_asin(x); break;
+    }
+    out[i] = r;
+}
+__global__ void wl_philox_kernel(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint4* __restrict__ out, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = philox4x32(seed, c0 + (uint32_t)i, c1, c2, c3);
+}
+
 // ---------------------------------------------------------------------------------------
 // launch geometry: spread small N over all 148 SMs, use fatter CTAs once the chip is full
 // ---------------------------------------------------------------------------------------
