@@ -322,6 +322,12 @@ int wl_step(wl_sim* sim, const float* d_action, float* d_obs, float* d_rew, uint
 size_t wl_result_bytes(int32_t num_envs);
 int wl_step_host(wl_sim* sim, const float* h_action, float* d_action, float* d_obs, void* d_result, float* d_log,
                  void* h_result, float* h_obs, int64_t step_counter, void* stream);
+/* Same contract, zero-copy transport: h_action / h_result must be PINNED host memory (cudaHostAlloc / torch
+ * pin_memory: device-addressable under unified addressing).  The step kernel reads the actions from and writes
+ * reward / terminated / truncated to host memory directly over PCIe -- no staging copies, no extra launches -- then
+ * the stream is synchronised.  Bytes crossing the bus per step are identical to wl_step_host. */
+int wl_step_host_zero_copy(wl_sim* sim, const float* h_action, float* d_obs, float* d_log, void* h_result,
+                           int64_t step_counter, void* stream);
 /* observation_manager.compute(): re-samples the noise. call_idx distinguishes
  * repeated calls at the same step_counter. */
 int wl_observe(wl_sim* sim, float* d_obs, int64_t step_counter, int32_t call_idx, void* stream);

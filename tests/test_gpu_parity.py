@@ -329,6 +329,7 @@ def test_step_host_matches_device_step():
     h_in = b.host_action_buffer
     assert h_in.is_pinned()
     for t in range(40):
+        b.host_transport = "zero_copy" if t % 2 else "copy"
         act = a.sim.synth_actions(t)
         oa, ra, ta, ua, _ = a.step(act)
         h_in.copy_(act.cpu())

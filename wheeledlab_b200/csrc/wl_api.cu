@@ -709,6 +709,22 @@ int wl_step_host(wl_sim* sim, const float* h_action, float* d_action, float* d_o
     return cuda_check(cudaStreamSynchronize(cs), "wl_step_host: stream synchronize");
 }
 
+int wl_step_host_zero_copy(wl_sim* sim, const float* h_action, float* d_obs, float* d_log, void* h_result,
+                           int64_t step_counter, void* stream) {
+    if (!sim || !h_action || !d_obs || !h_result) return fail(WL_EINVAL, "wl_step_host_zero_copy: null argument");
+    const size_t n = (size_t)sim->cfg.num_envs;
+    const float* da = nullptr; void* dr = nullptr;
+    if (cudaHostGetDevicePointer((void**)&da, (void*)h_action, 0) != cudaSuccess || cudaHostGetDevicePointer(&dr, h_result, 0) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(WL_EINVAL, "wl_step_host_zero_copy: h_action / h_result must be pinned (device-mapped) host memory");
+    }
+    float* d_rew = reinterpret_cast<float*>(dr);
+    uint8_t* d_term = reinterpret_cast<uint8_t*>(dr) + n * 4;
+    uint8_t* d_trunc = d_term + n;
+    if (int rc = wl_step(sim, da, d_obs, d_rew, d_term, d_trunc, d_log, step_counter, stream)) return rc;
+    return cuda_check(cudaStreamSynchronize((cudaStream_t)stream), "wl_step_host_zero_copy: stream synchronize");
+}
+
 int wl_observe(wl_sim* sim, float* d_obs, int64_t step_counter, int32_t call_idx, void* stream) {
     if (!sim || !d_obs) return fail(WL_EINVAL, "wl_observe: null argument");
     const int n = sim->cfg.num_envs, bs = 128;

@@ -227,6 +227,8 @@ class _Scene:
 class ManagerBasedRLEnv:
     """Drop-in for ``isaaclab.envs.ManagerBasedRLEnv`` on the Drift/Elevation/Visual gym ids."""
 
+    _RING = 512      # step_host() output buffers are reused after this many steps
+
     metadata = {"render_modes": [None, "human", "rgb_array"], "isaac_sim_version": "b200-native"}
 
     def __init__(self, cfg: TaskSpec | str = "Isaac-MushrDriftRL-v0", render_mode=None, device="cuda:0", **task_kw):
@@ -258,6 +260,8 @@ class ManagerBasedRLEnv:
         self._log_index = {"Episode_Reward/" + n: k for k, n in enumerate(self.spec.reward_names)}
         self._log_index.update({"Episode_Termination/" + n: 9 + j for j, (n, _) in enumerate(self.spec.termination_names)})
         self._host_io = None
+        self._ring = None
+        self.host_transport = "zero_copy"        # or "copy": staged H2D / D2H copies (wl_step_host)
         # event_manager.apply(mode="startup")
         self.sim.startup()
         self._needs_reset = True
@@ -350,17 +354,26 @@ class ManagerBasedRLEnv:
         if action_host.data_ptr() != io["h_action"].data_ptr():
             io["h_action"].copy_(action_host)
         t = self.common_step_counter
-        obs = torch.empty((self.num_envs, self.spec.obs_dim), dtype=torch.float32, device=self.device)
-        log = torch.empty(16, dtype=torch.float32, device=self.device) if self.log_episode_info else None
-        self.sim.step_host(io, t, obs, log)
+        # outputs come from a ring of preallocated device buffers (valid for _RING steps, like IsaacLab's own reuse)
+        k = t % self._RING
+        if self._ring is None:
+            self._ring = [(torch.empty((self.num_envs, self.spec.obs_dim), dtype=torch.float32, device=self.device),
+                           torch.empty(16, dtype=torch.float32, device=self.device)) for _ in range(self._RING)]
+        obs, log = self._ring[k]
+        if not self.log_episode_info:
+            log = None
+        if self.host_transport == "zero_copy":
+            self.sim.step_host_zero_copy(io, t, obs, log)
+        else:
+            self.sim.step_host(io, t, obs, log)
         self.common_step_counter = t + 1
         mask = self._curriculum_fire_mask()
         if mask:
             self.sim.curriculum(self._curr_slots, self._curr_inc, mask)
         tm = self.termination_manager
-        tm.terminated, tm.time_outs = io["d_terminated"].view(torch.bool), io["d_truncated"].view(torch.bool)
+        tm.terminated, tm.time_outs = io["terminated"], io["truncated"]
         if log is not None:
-            self.extras["log"] = self._episode_log(log)
+            self.extras["log"] = _LazyLog(log, self._log_index)
         return {"policy": obs}, io["rew"], io["terminated"], io["truncated"], self.extras
 
     @property

@@ -116,7 +116,15 @@ class WheeledSim:
         io["d_rew"] = d[: 4 * n].view(torch.float32)
         io["d_terminated"] = d[4 * n: 5 * n]
         io["d_truncated"] = d[5 * n: 6 * n]
+        io["_p_h_action"] = C.c_void_p(io["h_action"].data_ptr())
+        io["_p_h_result"] = C.c_void_p(io["h_result"].data_ptr())
         return io
+
+    def step_host_zero_copy(self, io, step_counter: int, obs: torch.Tensor, log: torch.Tensor | None = None):
+        """Zero-copy transport of the same contract: the kernel reads io.h_action / writes io.h_result over PCIe."""
+        check(lib.wl_step_host_zero_copy(self._h, io["_p_h_action"], C.c_void_p(obs.data_ptr()),
+                                         C.c_void_p(log.data_ptr()) if log is not None else None, io["_p_h_result"],
+                                         step_counter, _stream_ptr(self.device)), "wl_step_host_zero_copy")
 
     def step_host(self, io, step_counter: int, obs: torch.Tensor, log: torch.Tensor | None = None, h_obs: torch.Tensor | None = None):
         """ONE C call: H2D(io.h_action) -> fused step -> D2H(reward | terminated | truncated) -> stream sync.
