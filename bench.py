@@ -185,6 +185,8 @@ def run_ours(args):
     dev = f"cuda:{local}"
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"           # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device(dev))
 
     E, K, W = args.envs, args.steps, args.warmup
@@ -209,6 +211,9 @@ def run_ours(args):
     t = 1
     for _ in range(W):
         sim.step(acts[t % (W + K)], t, out=outs); flush.fill_(0.0); t += 1
+    if world > 1:                                       # untimed: NCCL communicator / channel set-up
+        for _ in range(3):
+            slab.all_gather()
     sampler = ClockSampler(local)
     barrier()
     if rank == 0:
