@@ -77,6 +77,10 @@ extern "C" {
 #define WL_ER_HEIGHT_Z    1
 #define WL_ER_FALLING     2
 #define WL_ER_TERM_PEN    3
+/* visual reward term slots (visual/mushr_visual_env_cfg.py:376-387) */
+#define WL_VR_TRAVERSABLE 0
+#define WL_VR_FORWARD_VEL 1
+#define WL_OBS_DIM_VISUAL 8    /* base_lin_vel(3) base_ang_vel(3) last_action(2); the camera term is out of scope */
 
 /* error codes */
 #define WL_OK          0
@@ -215,6 +219,16 @@ extern "C" {
     XS(float, f32, elev_goal_dist)                                                                 \
     XS(float, f32, elev_fall_vel)                                                                  \
     XS(float, f32, elev_plane_z)      /* 0.19 in higher_elevation, :166-173 */                     \
+    /* --- visual task, physics side (visual/mushr_visual_env_cfg.py; camera out of scope) --- */    \
+    XS(int32_t, i32, vis_rows)        /* traversability map [rows(y), cols(x)], :73-75 */          \
+    XS(int32_t, i32, vis_cols)                                                                     \
+    XS(int32_t, i32, vis_n_trav)      /* number of traversable cells (spawn candidates) */         \
+    XS(int32_t, i32, _pad5)                                                                        \
+    XS(float, f32, vis_row_spacing)   /* 0.5, :68-70 */                                            \
+    XS(float, f32, vis_col_spacing)                                                                \
+    XS(float, f32, vis_width)         /* num_rows*row_spacing = 250, :113-114 */                   \
+    XS(float, f32, vis_height)                                                                     \
+    XS(float, f32, vis_spawn_z)       /* 0.1, utils/__init__.py:188-202 + InitialPoseCfg */        \
     /* --- derived constants: filled by wl_config_finalize() (wl_create calls it on its copy); fp32,   \
      *     formed once on the host so the kernels carry no per-step divisions for them --- */        \
     XS(float, f32, d_h)               /* sim_dt / substeps */                                      \
@@ -273,7 +287,8 @@ typedef struct wl_globals {
 #define WL_LOG_FLOATS 16                  /* d_log: [0..7] Episode_Reward means, [8] #reset, [9+j] term counts */
 /* termination term order (bit j of the per-env mask; declaration order of the reference cfgs)
  *   drift     (mushr_drift_env_cfg.py:351-362):     0 time_out, 1 out_of_bounds
- *   elevation (mushr_elevation_env_cfg.py:349-376): 0 time_out, 1 cart_out_of_bounds, 2 stuck, 3 rollover, 4 at_goal */
+ *   elevation (mushr_elevation_env_cfg.py:349-376): 0 time_out, 1 cart_out_of_bounds, 2 stuck, 3 rollover, 4 at_goal
+ *   visual    (mushr_visual_env_cfg.py:404-409):    0 time_out, 1 out_range */
 #define WL_MAX_TERM_TERMS 7
 
 typedef struct wl_sim wl_sim;   /* opaque handle (host memory) */
@@ -290,7 +305,10 @@ size_t wl_state_bytes(int32_t num_envs);     /* groups + globals, 256-byte padde
 size_t wl_globals_offset(int32_t num_envs);  /* byte offset of wl_globals in the state buffer */
 /* d_state: zero-initialised device buffer of wl_state_bytes(cfg->num_envs) bytes.
  * d_heightfield: float[hf_ny*hf_nx] on device (row-major: index iy*hf_nx + ix, 16-byte aligned, hf_nx % 4 == 0)
- * or NULL.  For the elevation task a TMA tensor map over it is built here. */
+ * or NULL.  For the elevation task a TMA tensor map over it is built here.
+ * Visual task: the same pointer carries the traversability data instead: int32 trav_cells[vis_n_trav] (cell id =
+ * row*vis_cols + col, the spawn candidates) followed, at byte offset ((4*vis_n_trav + 15) & ~15), by
+ * uint8 map[vis_rows*vis_cols] (1 = traversable). */
 int wl_create(const wl_config* cfg, void* d_state, size_t state_bytes, const float* d_heightfield,
               wl_sim** out);
 int wl_destroy(wl_sim* sim);

@@ -102,9 +102,10 @@ __global__ void __launch_bounds__(128, 4)
 wl_step_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st, wl_globals* __restrict__ gl, Terrain T,
                const float2* __restrict__ action, float* __restrict__ obs, float* __restrict__ rew,
                uint8_t* __restrict__ terminated_o, uint8_t* __restrict__ truncated_o, float* __restrict__ d_log, uint32_t t) {
-    constexpr bool ELEV = (TASK == WL_TASK_ELEVATION);
+    constexpr bool ELEV = (TASK == WL_TASK_ELEVATION), VIS = (TASK == WL_TASK_VISUAL);
     const int n = c.num_envs;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const VisualMap vm = VIS ? visual_map(c, T.hf) : VisualMap{nullptr, nullptr};
     bool done = false;
     uint32_t tmask = 0u;
     EnvState e;
@@ -145,6 +146,8 @@ wl_step_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st, wl_
         V3 vb = rotT(R, e.v);
         if (ELEV) {
             tmask = elev_terms(c, e, R, vb, (e.omega[0] + e.omega[1]) + (e.omega[2] + e.omega[3]), time_out, f);
+        } else if (VIS) {
+            tmask = visual_terms(c, vm, e, vb, time_out, f);
         } else {
             const bool oob = drift_off_track(c, e.p.x, e.p.y);
             drift_reward_terms(c, e.steer[0], e.steer[1], det_atan2(vb.y, vb.x), e.p, vb, b.wb, e.w.z, oob, time_out, f);
@@ -168,10 +171,14 @@ wl_step_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st, wl_
     if (i < n) {
         const uint32_t gid = (uint32_t)(c.env_id_offset + i);
         if (done) {
-            if (ELEV) elev_reset_env(c, e, gid, t); else drift_reset_env(c, e, gid, t);
+            if (ELEV) elev_reset_env(c, e, gid, t); else if (VIS) visual_reset_env(c, vm, e, gid, t); else drift_reset_env(c, e, gid, t);
         }
         // G. commands   H. interval events (post-reset state)   I. observations
-        if (ELEV) {
+        if (VIS) {
+            float o[8]; visual_proprio(c, e, o);
+            float4* row = reinterpret_cast<float4*>(obs + (size_t)WL_OBS_DIM_VISUAL * i);
+            row[0] = make_float4(o[0], o[1], o[2], o[3]); row[1] = make_float4(o[4], o[5], o[6], o[7]);
+        } else if (ELEV) {
             elev_command_update(c, e, gid, t, c.d_step_dt);
             float o[13]; elev_proprio(c, e, euler_xyz(e.qw, e.qx, e.qy, e.qz), o);
             float* row = obs + (size_t)WL_OBS_DIM_ELEV * i;
@@ -193,7 +200,8 @@ __global__ void __launch_bounds__(128)
 wl_step_quad_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st, wl_globals* __restrict__ gl, Terrain T,
                     const float2* __restrict__ action, float* __restrict__ obs, float* __restrict__ rew,
                     uint8_t* __restrict__ terminated_o, uint8_t* __restrict__ truncated_o, float* __restrict__ d_log, uint32_t t) {
-    constexpr bool ELEV = (TASK == WL_TASK_ELEVATION);
+    constexpr bool ELEV = (TASK == WL_TASK_ELEVATION), VIS = (TASK == WL_TASK_VISUAL);
+    const VisualMap vm = VIS ? visual_map(c, T.hf) : VisualMap{nullptr, nullptr};
     const int n = c.num_envs;
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int i = tid >> 2, w = tid & 3;
@@ -242,6 +250,8 @@ wl_step_quad_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st
         float o01 = e.omega[0] + __shfl_xor_sync(0xffffffffu, e.omega[0], 1);      // (w0+w1), (w2+w3)
         float osum = o01 + __shfl_xor_sync(0xffffffffu, o01, 2);                   // (w0+w1)+(w2+w3)
         tmask = elev_terms(c, e, R, vb, osum, time_out, f);
+    } else if (VIS) {
+        tmask = visual_terms(c, vm, e, vb, time_out, f);
     } else {
         const float steer_l = __shfl_sync(0xffffffffu, e.steer[0], base + 2), steer_r = __shfl_sync(0xffffffffu, e.steer[0], base + 3);
         const bool oob = drift_off_track(c, e.p.x, e.p.y);
@@ -261,9 +271,16 @@ wl_step_quad_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st
     // F. per-step episode log: one contribution per env (lane 0 of each live quad), then auto-reset
     log_accumulate(gl, done && live && (w == 0), tmask, e.sums);
     if (done) {
-        if (ELEV) elev_reset_env(c, e, gid, t); else drift_reset_env(c, e, gid, t);   // redundant; joints untouched (Q3)
+        if (ELEV) elev_reset_env(c, e, gid, t); else if (VIS) visual_reset_env(c, vm, e, gid, t); else drift_reset_env(c, e, gid, t);
     }
-    if (ELEV) elev_command_update(c, e, gid, t, c.d_step_dt); else interval_pushes(c, e, gid, t, c.d_step_dt);
+    if (ELEV) elev_command_update(c, e, gid, t, c.d_step_dt); else if (!VIS) interval_pushes(c, e, gid, t, c.d_step_dt);
+    if (VIS) {      // 8 proprioceptive floats, no noise, no euler: lanes 0 and 1 write one float4 each
+        float o[8]; visual_proprio(c, e, o);
+        if (live && w < 2) {
+            float4* row = reinterpret_cast<float4*>(obs + (size_t)WL_OBS_DIM_VISUAL * i);
+            row[w] = (w == 0) ? make_float4(o[0], o[1], o[2], o[3]) : make_float4(o[4], o[5], o[6], o[7]);
+        }
+    } else
     // I. observations: the three euler angles are three atan2 calls -> one per lane
     {
         float qw = e.qw, qx = e.qx, qy = e.qy, qz = e.qz;
@@ -424,8 +441,8 @@ __global__ void wl_startup_kernel(const __grid_constant__ wl_config c, float4* _
     stg4(st, WL_G_QUAT, n, i, make_float4(1.0f, 0.0f, 0.0f, 0.0f));
 }
 
-__global__ void wl_reset_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st, const int64_t* __restrict__ ids,
-                                int n_ids, uint32_t t) {
+__global__ void wl_reset_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st, const float* __restrict__ aux,
+                                const int64_t* __restrict__ ids, int n_ids, uint32_t t) {
     const int n = c.num_envs;
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n_ids) return;
@@ -435,6 +452,7 @@ __global__ void wl_reset_kernel(const __grid_constant__ wl_config c, float4* __r
     const bool elev = c.task == WL_TASK_ELEVATION;
     load_env(st, n, i, e, elev);
     if (elev) elev_reset_env(c, e, (uint32_t)(c.env_id_offset + i), t);      // command b-frame vector is NOT refreshed by reset()
+    else if (c.task == WL_TASK_VISUAL) visual_reset_env(c, visual_map(c, aux), e, (uint32_t)(c.env_id_offset + i), t);
     else drift_reset_env(c, e, (uint32_t)(c.env_id_offset + i), t);
     store_env(st, n, i, e, elev);
 }
@@ -445,6 +463,14 @@ __global__ void wl_observe_kernel(const __grid_constant__ wl_config c, const flo
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     EnvState e;
+    if (c.task == WL_TASK_VISUAL) {
+        load_env(st, n, i, e, false);
+        float o[8]; visual_proprio(c, e, o);
+        float* row = obs + (size_t)WL_OBS_DIM_VISUAL * i;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) row[k] = o[k];
+        return;
+    }
     if (c.task == WL_TASK_ELEVATION) {
         load_env(st, n, i, e, true);
         float o[13]; elev_proprio(c, e, euler_xyz(e.qw, e.qx, e.qy, e.qz), o);
@@ -567,8 +593,13 @@ int wl_create(const wl_config* cfg, void* d_state, size_t state_bytes, const flo
     if (cfg->num_envs <= 0) return fail(WL_EINVAL, "wl_create: num_envs must be > 0");
     if (state_bytes < wl_state_bytes(cfg->num_envs)) return fail(WL_EINVAL, "wl_create: state buffer too small");
     if (((uintptr_t)d_state & 255u) != 0) return fail(WL_EINVAL, "wl_create: state buffer must be 256-byte aligned");
-    if (cfg->task != WL_TASK_DRIFT && cfg->task != WL_TASK_ELEVATION)
-        return fail(WL_EUNSUPPORTED, "wl_create: task not implemented in this build (drift, elevation)");
+    if (cfg->task != WL_TASK_DRIFT && cfg->task != WL_TASK_ELEVATION && cfg->task != WL_TASK_VISUAL)
+        return fail(WL_EUNSUPPORTED, "wl_create: unknown task");
+    if (cfg->task == WL_TASK_VISUAL) {
+        if (!d_heightfield) return fail(WL_EINVAL, "wl_create: the visual task needs the traversability data (see header)");
+        if (cfg->vis_rows < 1 || cfg->vis_cols < 1 || cfg->vis_n_trav < 1) return fail(WL_EINVAL, "wl_create: bad traversability map geometry");
+        if (((uintptr_t)d_heightfield & 15u) != 0) return fail(WL_EINVAL, "wl_create: traversability data must be 16-byte aligned");
+    }
     if (cfg->task == WL_TASK_ELEVATION) {
         if (!d_heightfield) return fail(WL_EINVAL, "wl_create: the elevation task needs a height-field");
         if (cfg->hf_nx < 2 || cfg->hf_ny < 2 || cfg->hf_pitch < cfg->hf_nx || (cfg->hf_pitch & 3) || !(cfg->hf_cell > 0.0f))
@@ -614,7 +645,7 @@ int wl_create(const wl_config* cfg, void* d_state, size_t state_bytes, const flo
         if (cr != CUDA_SUCCESS) { delete s; return fail(WL_ECUDA, "cuTensorMapEncodeTiled failed (code " + std::to_string((int)cr) + ")"); }
         s->has_tmap = true;
     }
-    s->obs_dim = (cfg->task == WL_TASK_ELEVATION) ? WL_OBS_DIM_ELEV : WL_OBS_DIM_BLIND;
+    s->obs_dim = (cfg->task == WL_TASK_ELEVATION) ? WL_OBS_DIM_ELEV : (cfg->task == WL_TASK_VISUAL) ? WL_OBS_DIM_VISUAL : WL_OBS_DIM_BLIND;
     // live reward weights
     if (int rc = cuda_check(cudaMemcpy(s->globals->rew_weight, cfg->rew_weight, sizeof(float) * WL_MAX_REW_TERMS,
                                        cudaMemcpyHostToDevice), "upload reward weights")) { delete s; return rc; }
@@ -656,7 +687,7 @@ int wl_reset(wl_sim* sim, const int64_t* d_env_ids, int32_t n_ids, int64_t step_
     const int n = d_env_ids ? n_ids : sim->cfg.num_envs;
     if (n <= 0) return WL_OK;
     const int bs = 128;
-    wl_reset_kernel<<<(n + bs - 1) / bs, bs, 0, (cudaStream_t)stream>>>(sim->cfg, sim->state, d_env_ids, n, (uint32_t)step_counter);
+    wl_reset_kernel<<<(n + bs - 1) / bs, bs, 0, (cudaStream_t)stream>>>(sim->cfg, sim->state, sim->hf, d_env_ids, n, (uint32_t)step_counter);
     WL_LAUNCH_CHECK(sim, "wl_reset_kernel");
     return WL_OK;
 }
@@ -671,14 +702,16 @@ int wl_step(wl_sim* sim, const float* d_action, float* d_obs, float* d_rew, uint
     const float2* act = reinterpret_cast<const float2*>(d_action);
     cudaStream_t cs = (cudaStream_t)stream;
     const uint32_t t = (uint32_t)step_counter;
-    const bool elev = sim->cfg.task == WL_TASK_ELEVATION;
+    const bool elev = sim->cfg.task == WL_TASK_ELEVATION, vis = sim->cfg.task == WL_TASK_VISUAL;
     if (variant == 4) {
         const int bs = 32, threads = 4 * n, grid = (threads + bs - 1) / bs;
         if (elev) wl_step_quad_kernel<WL_TASK_ELEVATION><<<grid, bs, 0, cs>>>(sim->cfg, sim->state, sim->globals, T, act, d_obs, d_rew, d_terminated, d_truncated, d_log, t);
+        else if (vis) wl_step_quad_kernel<WL_TASK_VISUAL><<<grid, bs, 0, cs>>>(sim->cfg, sim->state, sim->globals, T, act, d_obs, d_rew, d_terminated, d_truncated, d_log, t);
         else wl_step_quad_kernel<WL_TASK_DRIFT><<<grid, bs, 0, cs>>>(sim->cfg, sim->state, sim->globals, T, act, d_obs, d_rew, d_terminated, d_truncated, d_log, t);
     } else {
         const int bs = pick_block(n), grid = (n + bs - 1) / bs;
         if (elev) wl_step_kernel<WL_TASK_ELEVATION><<<grid, bs, 0, cs>>>(sim->cfg, sim->state, sim->globals, T, act, d_obs, d_rew, d_terminated, d_truncated, d_log, t);
+        else if (vis) wl_step_kernel<WL_TASK_VISUAL><<<grid, bs, 0, cs>>>(sim->cfg, sim->state, sim->globals, T, act, d_obs, d_rew, d_terminated, d_truncated, d_log, t);
         else wl_step_kernel<WL_TASK_DRIFT><<<grid, bs, 0, cs>>>(sim->cfg, sim->state, sim->globals, T, act, d_obs, d_rew, d_terminated, d_truncated, d_log, t);
     }
     if (elev) {

@@ -446,6 +446,55 @@ __device__ __forceinline__ void elev_proprio(const wl_config& c, const EnvState&
     o[11] = r_clamp(e.action[0], -1.0f, 1.0f); o[12] = r_clamp(e.action[1], -1.0f, 1.0f);
 }
 
+// ---- visual task, physics side (visual/mushr_visual_env_cfg.py; the RTX camera observation is out of scope) -------
+struct VisualMap { const int32_t* __restrict__ cells; const uint8_t* __restrict__ map; };
+__device__ __forceinline__ VisualMap visual_map(const wl_config& c, const float* aux) {
+    const char* b = reinterpret_cast<const char*>(aux);
+    return VisualMap{reinterpret_cast<const int32_t*>(b), reinterpret_cast<const uint8_t*>(b + (((size_t)c.vis_n_trav * 4 + 15) & ~(size_t)15))};
+}
+// rewards :304-387 (traversable_reward, forward_vel), terminations :392-409 (time_out, out_of_map);
+// map lookup = TraversabilityHashmapUtil.get_map_id (utils/traversability_utils.py:83-88: +spacing/2, truncation,
+// clamp, indexed [y_idx, x_idx]; quirk Q14)
+__device__ __forceinline__ uint32_t visual_terms(const wl_config& c, const VisualMap& vm, const EnvState& e, V3 vb, bool time_out,
+                                                 float f[WL_MAX_REW_TERMS]) {
+    int xi = (int)((e.p.x + c.vis_width / 2.0f + c.vis_row_spacing / 2.0f) / c.vis_row_spacing);
+    int yi = (int)((e.p.y + c.vis_height / 2.0f + c.vis_col_spacing / 2.0f) / c.vis_col_spacing);
+    xi = xi < 0 ? 0 : (xi > c.vis_rows - 1 ? c.vis_rows - 1 : xi);
+    yi = yi < 0 ? 0 : (yi > c.vis_cols - 1 ? c.vis_cols - 1 : yi);
+    const bool trav = __ldg(vm.map + (size_t)yi * c.vis_cols + xi) != 0;
+    f[WL_VR_TRAVERSABLE] = trav ? 1.0f : -1.0f;
+    f[WL_VR_FORWARD_VEL] = vb.x;
+    f[2] = f[3] = f[4] = f[5] = f[6] = f[7] = 0.0f;
+    const bool out = (e.p.x > c.vis_width / 2.0f) || (e.p.x < -c.vis_width / 2.0f) || (e.p.y > c.vis_height / 2.0f) ||
+                     (e.p.y < -c.vis_height / 2.0f);
+    return (time_out ? 1u : 0u) | (out ? 2u : 0u);
+}
+// reset_root_state (visual/mdp/events.py:11-42) with generate_random_poses (utils/__init__.py:188-202): a uniformly
+// random traversable cell, yaw U(0,360) deg, z = 0.1, zero velocity
+__device__ __forceinline__ void visual_reset_env(const wl_config& c, const VisualMap& vm, EnvState& e, uint32_t gid, uint32_t t) {
+    uint4 r = philox4x32(c.seed, gid, t, RNG_RESET, 0u);
+    const int cell = __ldg(vm.cells + __umulhi(r.x, (uint32_t)c.vis_n_trav));
+    const int ys = cell / c.vis_cols, xs = cell - ys * c.vis_cols;
+    e.p.x = ((float)xs - (float)(c.vis_cols / 2)) * c.vis_row_spacing;
+    e.p.y = ((float)ys - (float)(c.vis_rows / 2)) * c.vis_col_spacing;
+    e.p.z = c.vis_spawn_z;
+    float yaw = (360.0f * u01(r.y)) * 0.017453292519943295f;
+    float sh, ch; det_sincos(yaw * 0.5f, sh, ch);
+    e.qw = ch; e.qx = 0.0f; e.qy = 0.0f; e.qz = sh;
+    e.v = V3{0.0f, 0.0f, 0.0f}; e.w = V3{0.0f, 0.0f, 0.0f};
+    e.ep_len = 0;
+#pragma unroll
+    for (int k = 0; k < WL_MAX_REW_TERMS; ++k) e.sums[k] = 0.0f;
+    e.action[0] = e.action[1] = e.prev_action[0] = e.prev_action[1] = 0.0f;
+}
+// VisualObsCfg.PolicyCfg minus the camera term (:43-57; enable_corruption False): 8 floats
+__device__ __forceinline__ void visual_proprio(const wl_config& c, const EnvState& e, float o[8]) {
+    M3 R = rotmat(e.qw, e.qx, e.qy, e.qz);
+    V3 vb = rotT(R, e.v), wb = rotT(R, e.w);
+    o[0] = vb.x; o[1] = vb.y; o[2] = vb.z; o[3] = wb.x; o[4] = wb.y; o[5] = wb.z;
+    o[6] = r_clamp(e.action[0], -1.0f, 1.0f); o[7] = r_clamp(e.action[1], -1.0f, 1.0f);
+}
+
 // ---- reset / pushes / observations -----------------------------------------------------
 __device__ __forceinline__ void sample_interval_timers(const wl_config& c, EnvState& e, uint32_t a, uint32_t b) {
     e.t_hf = uniform(a, c.push_hf_interval[0], c.push_hf_interval[1]);
