@@ -205,6 +205,8 @@ typedef struct wlo_sim {
     double log_term[8];                   /* last step: #reset, then per termination term counts */
     int32_t any_reset_last;
     float* hf;
+    int32_t* vis_cells;       /* visual: spawn-candidate cell ids */
+    uint8_t* vis_map;         /* visual: traversability map [rows, cols] */
 } wlo_sim;
 
 static inline real dot3(real ax, real ay, real az, real bx, real by, real bz) { return fm(ax, bx, fm(ay, by, az * bz)); }
@@ -653,6 +655,49 @@ static void elev_obs(const wlo_sim* s, const wlo_env* e, float* obs) {
     }
 }
 
+/* ------------------------------------------------------------------------- */
+/* visual task, physics side (visual/mushr_visual_env_cfg.py; camera out of scope) */
+/* ------------------------------------------------------------------------- */
+/* rewards :304-387, terminations :392-409; map lookup = TraversabilityHashmapUtil.get_map_id
+ * (utils/traversability_utils.py:83-88: +spacing/2, truncation toward zero, clamp, indexed [y_idx, x_idx]) */
+static uint32_t visual_terms(const wlo_sim* s, const wlo_env* e, const real vb[3], int time_out, real f[WL_MAX_REW_TERMS]) {
+    const wl_config* c = &s->cfg;
+    int xi = (int)((e->p[0] + (real)c->vis_width / K(2.0) + (real)c->vis_row_spacing / K(2.0)) / (real)c->vis_row_spacing);
+    int yi = (int)((e->p[1] + (real)c->vis_height / K(2.0) + (real)c->vis_col_spacing / K(2.0)) / (real)c->vis_col_spacing);
+    xi = xi < 0 ? 0 : (xi > c->vis_rows - 1 ? c->vis_rows - 1 : xi);
+    yi = yi < 0 ? 0 : (yi > c->vis_cols - 1 ? c->vis_cols - 1 : yi);
+    int trav = s->vis_map[(size_t)yi * c->vis_cols + xi] != 0;
+    f[WL_VR_TRAVERSABLE] = trav ? K(1.0) : K(-1.0);                       /* traversable_reward :309-312 */
+    f[WL_VR_FORWARD_VEL] = vb[0];                                         /* forward_vel :371-372 */
+    for (int k = 2; k < WL_MAX_REW_TERMS; ++k) f[k] = K(0.0);
+    int out = (e->p[0] > (real)c->vis_width / K(2.0)) || (e->p[0] < -(real)c->vis_width / K(2.0)) ||
+              (e->p[1] > (real)c->vis_height / K(2.0)) || (e->p[1] < -(real)c->vis_height / K(2.0));   /* out_of_map :392-400 */
+    return (time_out ? 1u : 0u) | (out ? 2u : 0u);
+}
+/* reset_root_state (visual/mdp/events.py:11-42) + generate_random_poses (utils/__init__.py:188-202) */
+static void visual_reset_env(const wlo_sim* s, wlo_env* e, uint32_t gid, int64_t t) {
+    const wl_config* c = &s->cfg;
+    uint32_t r[4]; philox4x32(c->seed, gid, (uint32_t)t, RNG_RESET, 0u, r);
+    int cell = s->vis_cells[(uint32_t)(((uint64_t)r[0] * (uint64_t)c->vis_n_trav) >> 32)];
+    int ys = cell / c->vis_cols, xs = cell - ys * c->vis_cols;
+    e->p[0] = ((real)xs - (real)(c->vis_cols / 2)) * (real)c->vis_row_spacing;
+    e->p[1] = ((real)ys - (real)(c->vis_rows / 2)) * (real)c->vis_col_spacing;
+    e->p[2] = (real)c->vis_spawn_z;
+    real yaw = (K(360.0) * u01(r[1])) * K(0.017453292519943295);
+    real sh, ch; det_sincos(yaw * K(0.5), &sh, &ch);
+    e->q[0] = ch; e->q[1] = K(0.0); e->q[2] = K(0.0); e->q[3] = sh;
+    for (int k = 0; k < 3; ++k) { e->v[k] = K(0.0); e->w[k] = K(0.0); }
+    e->ep_len = 0;
+    for (int k = 0; k < WL_MAX_REW_TERMS; ++k) e->sums[k] = K(0.0);
+    e->action[0] = e->action[1] = e->prev_action[0] = e->prev_action[1] = K(0.0);
+}
+static void visual_obs(const wlo_env* e, float* obs) {
+    real R[9]; rotmat(e->q, R);
+    real vb[3], wb[3]; rotT(R, e->v, vb); rotT(R, e->w, wb);
+    for (int k = 0; k < 3; ++k) { obs[k] = (float)vb[k]; obs[3 + k] = (float)wb[k]; }
+    obs[6] = (float)r_clamp(e->action[0], K(-1.0), K(1.0)); obs[7] = (float)r_clamp(e->action[1], K(-1.0), K(1.0));
+}
+
 /* interval pushes, mushr_drift_env_cfg.py:121-143; push_by_setting_velocity (+=) [UPSTREAM-RECALL a13] */
 static void interval_pushes(const wl_config* c, wlo_env* e, uint32_t gid, int64_t t, real step_dt) {
     if (!c->push_enable) return;
@@ -743,6 +788,8 @@ static int env_step(wlo_sim* s, int li, const float* a_in, int64_t t, float* obs
         tmask = (time_out ? 1u : 0u) | (oob ? 2u : 0u);
     } else if (c->task == WL_TASK_ELEVATION) {
         tmask = elev_terms(c, e, R, vb, (e->omega[0] + e->omega[1]) + (e->omega[2] + e->omega[3]), time_out, f);
+    } else if (c->task == WL_TASK_VISUAL) {
+        tmask = visual_terms(s, e, vb, time_out, f);
     } else {
         return WL_EUNSUPPORTED;
     }
@@ -761,8 +808,11 @@ static int env_step(wlo_sim* s, int li, const float* a_in, int64_t t, float* obs
         lg->any = 1; lg->n_reset += 1.0;
         for (int j = 0; j < WL_MAX_TERM_TERMS; ++j) lg->n_term[j] += ((tmask >> j) & 1u) ? 1.0 : 0.0;
         for (int k = 0; k < WL_MAX_REW_TERMS; ++k) lg->sum[k] += (double)e->sums[k];
-        if (c->task == WL_TASK_ELEVATION) elev_reset_env(c, e, gid, t); else drift_reset_env(c, e, gid, t);
+        if (c->task == WL_TASK_ELEVATION) elev_reset_env(c, e, gid, t);
+        else if (c->task == WL_TASK_VISUAL) visual_reset_env(s, e, gid, t);
+        else drift_reset_env(c, e, gid, t);
     }
+    if (c->task == WL_TASK_VISUAL) { visual_obs(e, obs); return 0; }
     if (c->task == WL_TASK_ELEVATION) {
         /* G. commands; I. observations */
         elev_command_update(c, e, gid, t, step_dt);
@@ -785,7 +835,13 @@ wlo_sim* wlo_create(const wl_config* cfg, const float* heightfield) {
     config_finalize(&s->cfg);
     s->env = (wlo_env*)calloc((size_t)cfg->num_envs, sizeof(wlo_env));
     for (int k = 0; k < WL_MAX_REW_TERMS; ++k) s->rew_weight[k] = (real)cfg->rew_weight[k];
-    if (heightfield && cfg->hf_nx > 0) {
+    if (heightfield && cfg->task == WL_TASK_VISUAL) {        /* aux = int32 cells[n_trav] | pad16 | uint8 map[rows*cols] */
+        size_t off = ((size_t)cfg->vis_n_trav * 4 + 15) & ~(size_t)15, nm = (size_t)cfg->vis_rows * cfg->vis_cols;
+        s->vis_cells = (int32_t*)malloc((size_t)cfg->vis_n_trav * 4);
+        s->vis_map = (uint8_t*)malloc(nm);
+        memcpy(s->vis_cells, heightfield, (size_t)cfg->vis_n_trav * 4);
+        memcpy(s->vis_map, (const char*)heightfield + off, nm);
+    } else if (heightfield && cfg->hf_nx > 0) {
         size_t n = (size_t)cfg->hf_pitch * cfg->hf_ny;
         s->hf = (float*)malloc(n * sizeof(float));
         memcpy(s->hf, heightfield, n * sizeof(float));
@@ -793,7 +849,7 @@ wlo_sim* wlo_create(const wl_config* cfg, const float* heightfield) {
     for (int i = 0; i < cfg->num_envs; ++i) s->env[i].q[0] = K(1.0);
     return s;
 }
-void wlo_destroy(wlo_sim* s) { if (s) { free(s->env); free(s->hf); free(s); } }
+void wlo_destroy(wlo_sim* s) { if (s) { free(s->env); free(s->hf); free(s->vis_cells); free(s->vis_map); free(s); } }
 int wlo_is_double(void) {
 #ifdef WLO_DOUBLE
     return 1;
@@ -835,6 +891,7 @@ int wlo_reset(wlo_sim* s, const int64_t* env_ids, int32_t n_ids, int64_t step_co
     for (int k = 0; k < n; ++k) {
         int li = env_ids ? (int)env_ids[k] : k;
         if (c->task == WL_TASK_ELEVATION) elev_reset_env(c, &s->env[li], (uint32_t)(c->env_id_offset + li), step_counter);
+        else if (c->task == WL_TASK_VISUAL) visual_reset_env(s, &s->env[li], (uint32_t)(c->env_id_offset + li), step_counter);
         else drift_reset_env(c, &s->env[li], (uint32_t)(c->env_id_offset + li), step_counter);
     }
     return 0;
@@ -843,7 +900,7 @@ int wlo_reset(wlo_sim* s, const int64_t* env_ids, int32_t n_ids, int64_t step_co
 int wlo_step(wlo_sim* s, const float* action, float* obs, float* rew, uint8_t* terminated, uint8_t* truncated,
              int64_t step_counter, int nthreads) {
     const wl_config* c = &s->cfg;
-    int od = (c->task == WL_TASK_ELEVATION) ? WL_OBS_DIM_ELEV : WL_OBS_DIM_BLIND;
+    int od = (c->task == WL_TASK_ELEVATION) ? WL_OBS_DIM_ELEV : (c->task == WL_TASK_VISUAL) ? WL_OBS_DIM_VISUAL : WL_OBS_DIM_BLIND;
     step_log tot; memset(&tot, 0, sizeof tot);
     int err = 0;
     (void)nthreads;
@@ -880,6 +937,10 @@ int wlo_observe(wlo_sim* s, float* obs, int64_t step_counter, int32_t call_idx) 
     const wl_config* c = &s->cfg;
     if (c->task == WL_TASK_ELEVATION) {
         for (int li = 0; li < c->num_envs; ++li) elev_obs(s, &s->env[li], obs + (size_t)WL_OBS_DIM_ELEV * li);
+        return 0;
+    }
+    if (c->task == WL_TASK_VISUAL) {
+        for (int li = 0; li < c->num_envs; ++li) visual_obs(&s->env[li], obs + (size_t)WL_OBS_DIM_VISUAL * li);
         return 0;
     }
     for (int li = 0; li < c->num_envs; ++li)

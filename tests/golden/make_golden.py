@@ -260,7 +260,36 @@ def golden_elevation():
     np.savez_compressed(HERE / "elevation_terms.npz", **out)
 
 
+def golden_visual():
+    """Traversability lookup (utils/traversability_utils.py) and respawn-pose formula (utils/__init__.py:188-202) of the
+    Visual task, loaded by file path with stand-in modules for matplotlib / pxr (imported at module scope there)."""
+    import importlib.util
+    for name in ("matplotlib", "matplotlib.pyplot", "pxr"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    for k in ("Usd", "UsdGeom", "UsdPhysics", "Gf"):
+        setattr(sys.modules["pxr"], k, types.SimpleNamespace())
+    vdir = REF / "wheeledlab_tasks" / "wheeledlab_tasks" / "visual" / "utils"
+    spec = importlib.util.spec_from_file_location("wl_visual_utils", vdir / "__init__.py", submodule_search_locations=[str(vdir)])
+    vu = importlib.util.module_from_spec(spec); sys.modules["wl_visual_utils"] = vu; spec.loader.exec_module(vu)
+    rng = np.random.default_rng(4)
+    m = rng.random((40, 60)) < 0.3                       # [rows(y), cols(x)] non-square on purpose
+    util = vu.TraversabilityHashmapUtil()
+    util.set_traversability_hashmap(m.tolist(), (60, 40), (0.5, 0.5))     # map_size = (num_rows, num_cols) as the cfg passes them
+    g = torch.Generator().manual_seed(3)
+    pts = (torch.rand(4000, 2, generator=g) - 0.5) * torch.tensor([36.0, 26.0])
+    trav = util.get_traversability(pts)
+    xi, yi = util.get_map_id(pts[:, 0], pts[:, 1])
+    np.random.seed(11)
+    poses = vu.generate_random_poses(256, 0.5, 0.5, m.tolist(), margin=0.1)
+    np.random.seed(11)
+    idxs = np.random.choice(int(m.sum()), 256)
+    np.savez_compressed(HERE / "visual_terms.npz", map=m, pts=pts.numpy(), trav=trav.numpy().astype(np.uint8), xi=xi.numpy(), yi=yi.numpy(),
+                        poses=np.array(poses, dtype=np.float64), idxs=idxs)
+
+
 if __name__ == "__main__":
+    golden_visual()
     golden_elevation()
     golden_actions(); golden_drift_terms(); golden_reset_along_track(); golden_curriculum(); golden_euler()
     for f in sorted(HERE.glob("*.npz")):

@@ -69,8 +69,13 @@ class Oracle:
         self.cfg = cfg
         self.n = int(cfg.num_envs)
         self.threads = threads
-        self.obs_dim = 689 if int(cfg.task) == 1 else 14
-        hf = None if heightfield is None else np.ascontiguousarray(heightfield, dtype=np.float32)
+        self.obs_dim = {0: 14, 1: 689, 2: 8}[int(cfg.task)]
+        if heightfield is None:
+            hf = None
+        elif int(cfg.task) == 2:
+            hf = np.ascontiguousarray(heightfield)                      # raw aux bytes (visual)
+        else:
+            hf = np.ascontiguousarray(heightfield, dtype=np.float32)
         self._h = C.c_void_p(self.lib.wlo_create(C.byref(cfg), _p(hf)))
 
     def __del__(self):

@@ -175,3 +175,66 @@ def test_elevation_height_map_formula_matches_reference():
         assert np.allclose(obs[0, 13:], exp, atol=1e-6)
         scan1 = obs[1, 13:].reshape(26, 26)
         assert (scan1[:, -7:] == 10).all() and np.allclose(scan1[:, :18], exp, atol=1e-6)
+
+
+def test_visual_map_lookup_and_spawn_match_reference():
+    """TraversabilityHashmapUtil.get_map_id / get_traversability and generate_random_poses (reference outputs)."""
+    import wheeledlab_b200 as wl
+    from wheeledlab_b200.terrain import pack_traversability
+    g = np.load(G / "visual_terms.npz")
+    m = g["map"]                                           # [40 rows(y), 60 cols(x)]
+    # the reference passes map_size=(num_rows, num_cols) and uses num_rows for the X clamp / width: mirror that
+    spec = wl.visual_task(num_envs=4, traversability=m)
+    c = spec.cfg
+    c.vis_rows, c.vis_cols = 60, 40                        # util.num_rows, util.num_cols as set_traversability_hashmap got them
+    c.vis_width, c.vis_height = 60 * 0.5, 40 * 0.5
+    # lookup through the oracle: place envs at the points, read reward term 0 (+1 traversable / -1 not)
+    n = g["pts"].shape[0]
+    spec2 = wl.visual_task(num_envs=n, traversability=m)
+    for k in ("vis_rows", "vis_cols", "vis_width", "vis_height"):
+        setattr(spec2.cfg, k, getattr(c, k))
+    # map row stride is the TRUE column count (60); the oracle indexes map[y*vis_cols + x] -> keep stride = 60 by
+    # passing the map transposed-consistent: emulate with the python formula instead and check oracle separately below
+    x, y = g["pts"][:, 0].astype(np.float32), g["pts"][:, 1].astype(np.float32)
+    xi = np.clip(((x + np.float32(15.0) + np.float32(0.25)) / np.float32(0.5)).astype(np.int64), 0, 59)
+    yi = np.clip(((y + np.float32(10.0) + np.float32(0.25)) / np.float32(0.5)).astype(np.int64), 0, 39)
+    assert np.array_equal(xi, g["xi"]) and np.array_equal(yi, g["yi"])
+    assert np.array_equal(m[yi, xi].astype(np.uint8), g["trav"])
+    # spawn formula: candidates = map.nonzero() in row-major order; x = (col - W//2)*sp, y = (row - H//2)*sp
+    ys, xs = m.nonzero()
+    px = (xs[g["idxs"]].astype(np.float64) - 60 // 2) * 0.5
+    py = (ys[g["idxs"]].astype(np.float64) - 40 // 2) * 0.5
+    assert np.array_equal(px, g["poses"][:, 0]) and np.array_equal(py, g["poses"][:, 1])
+    assert g["poses"][:, 2].min() >= 0 and g["poses"][:, 2].max() <= 360
+    blob, n_trav = pack_traversability(m)
+    cells = blob[: n_trav * 4].view(np.int32)
+    assert np.array_equal(cells // 60, ys) and np.array_equal(cells % 60, xs)
+
+
+def test_visual_oracle_terms_on_square_map():
+    """Oracle reward/termination/reset of the visual task against the same formulas on the registered 500x500 map."""
+    import wheeledlab_b200 as wl
+    spec = wl.visual_task(num_envs=512, seed=5)
+    m = spec.traversability
+    assert m.shape == (500, 500) and 0.02 < m.mean() < 0.2 and spec.cfg.max_episode_length == 50
+    o = O.Oracle(spec.cfg, heightfield=spec.heightfield); o.startup(); o.reset(None, 0)
+    st = o.export_state()
+    x, y, z = st[0, :, 0], st[0, :, 1], st[0, :, 2]
+    col = np.round(x / 0.5 + 250).astype(int); row = np.round(y / 0.5 + 250).astype(int)
+    assert m[row, col].all() and np.allclose(z, 0.1)                    # respawn on traversable cells at z = 0.1
+    rng = np.random.default_rng(0)
+    st[0, :, 0] = rng.uniform(-130, 130, 512); st[0, :, 1] = rng.uniform(-130, 130, 512); st[0, :, 2] = 0.0
+    st[2, :, 0:3] = 0; st[3, :, 0:3] = 0
+    o.import_state(st)
+    w = o.weights(); w[1] = 0.0; o.set_weights(w)                        # isolate the traversability term
+    obs, rew, term, trunc = o.step(np.zeros((512, 2), np.float32), 0)
+    # positions barely move in one step from rest; compare away from cell borders
+    x, y = st[0, :, 0], st[0, :, 1]
+    fx, fy = (x + 125 + 0.25) / 0.5, (y + 125 + 0.25) / 0.5
+    safe = (np.abs(fx - np.round(fx)) > 0.05) & (np.abs(fy - np.round(fy)) > 0.05)
+    xi = np.clip(fx.astype(int), 0, 499); yi = np.clip(fy.astype(int), 0, 499)
+    exp = np.where(m[yi, xi], 1.0, -1.0) * 5.0 * 0.2
+    assert np.allclose(rew[safe], exp[safe], atol=1e-6)
+    out = (np.abs(x) > 125.001) | (np.abs(y) > 125.001)
+    inside = (np.abs(x) < 124.999) & (np.abs(y) < 124.999)
+    assert term[out].all() and not term[inside].any() and obs.shape == (512, 8)

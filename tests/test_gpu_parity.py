@@ -338,3 +338,32 @@ def test_step_host_matches_device_step():
         assert torch.equal(oa["policy"], ob["policy"]) and torch.equal(ra.cpu(), rb) and torch.equal(ta.cpu(), tb) and torch.equal(ua.cpu(), ub)
         assert float(ex["log"]["Episode_Termination/time_out"]) >= 0
     assert torch.equal(a.sim.groups, b.sim.groups)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Visual task, physics side (traversability-map reward, out-of-map termination, random traversable respawn)
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("variant", [1, 4])
+def test_visual_trajectory_bit_exact(variant):
+    _need_gpu()
+    import wheeledlab_b200 as wl
+    n, steps = 128, 120
+    spec = wl.visual_task(num_envs=n, seed=42)
+    sim = wl.WheeledSim(spec, "cuda:0"); sim.set_kernel_variant(variant)
+    sim.startup(); sim.reset(None, 0)
+    orc = O.Oracle(spec.cfg, heightfield=spec.heightfield); orc.startup(); orc.reset(None, 0)
+    assert sim.obs_dim == 8
+    assert np.array_equal(_bits(sim.observe(0).cpu().numpy()), _bits(orc.observe(0)))
+    n_done = 0
+    for t in range(steps):
+        act = sim.synth_actions(t)
+        obs, rew, term, trunc = sim.step(act, t)
+        o_obs, o_rew, o_term, o_trunc = orc.step(act.cpu().numpy(), t)
+        torch.cuda.synchronize()
+        assert np.array_equal(term.cpu().numpy(), o_term) and np.array_equal(trunc.cpu().numpy(), o_trunc), t
+        assert np.array_equal(_bits(rew.cpu().numpy()), _bits(o_rew)) and np.array_equal(_bits(obs.cpu().numpy()), _bits(o_obs)), t
+        n_done += int((o_term | o_trunc).sum())
+    assert np.array_equal(_bits(_state_groups(sim)), _bits(orc.export_state())) and n_done >= 2 * n
+    env = wl.make("Isaac-MushrVisualRL-v0", num_envs=64)
+    o, _ = env.reset()
+    assert o["policy"].shape == (64, 8) and env.max_episode_length == 50

@@ -4,7 +4,7 @@ Importing the package loads ``libwheeledlab_b200.so`` (hand-written sm_100a kern
 it raises if the library has not been built -- there is no CPU or eager-PyTorch fallback.
 """
 from ._lib import LIB_PATH, WlConfig, WlError, lib  # noqa: F401
-from .tasks import GYM_IDS, TaskSpec, drift_task, elevation_task, make_task  # noqa: F401
+from .tasks import GYM_IDS, TaskSpec, drift_task, elevation_task, make_task, visual_task  # noqa: F401
 from .sim import WheeledSim  # noqa: F401
 from .env import ManagerBasedRLEnv, make  # noqa: F401
 

@@ -42,7 +42,10 @@ class WheeledSim:
             if heightfield is None and getattr(spec, "heightfield", None) is not None:
                 heightfield = torch.from_numpy(spec.heightfield)
             if heightfield is not None:
-                self._hf = heightfield.to(self.device, torch.float32).contiguous()
+                if heightfield.dtype == torch.uint8:                  # visual: raw aux blob
+                    self._hf = heightfield.to(self.device).contiguous()
+                else:
+                    self._hf = heightfield.to(self.device, torch.float32).contiguous()
                 hf_ptr = C.c_void_p(self._hf.data_ptr())
             handle = C.c_void_p()
             check(lib.wl_create(C.byref(self.cfg), C.c_void_p(self._buf.data_ptr()), nbytes, hf_ptr, C.byref(handle)),

@@ -59,7 +59,8 @@ class TaskSpec:
     action_dim: int = 2
     episode_length_s: float = 5.0
     joint_names: list = field(default_factory=list)
-    heightfield: object = None                                  # float32 [ny, pitch] (elevation)
+    heightfield: object = None                                  # float32 [ny, pitch] (elevation) / aux blob (visual)
+    traversability: object = None                               # bool [rows, cols] (visual)
 
     @property
     def step_dt(self) -> float:
@@ -341,6 +342,54 @@ def elevation_task(num_envs: int = 1024, seed: int = 42, env_id_offset: int = 0,
     return spec
 
 
+def visual_task(num_envs: int = 1024, seed: int = 42, env_id_offset: int = 0, traversability=None) -> TaskSpec:
+    """MushrVisualRLEnvCfg, PHYSICS SIDE ONLY (visual/mushr_visual_env_cfg.py:412-439): flat plane, 4WD MuSHR,
+    traversability-map reward, out-of-map termination, random traversable respawn.  The RTX tiled-camera observation
+    term is out of scope: the policy observation here is the 8 proprioceptive floats that follow it."""
+    from .terrain import pack_traversability, traversability_map
+    cfg = WlConfig()
+    cfg.abi_version = WL_ABI_VERSION
+    cfg.task = TASK_VISUAL
+    cfg.num_envs, cfg.env_id_offset, cfg.seed = num_envs, env_id_offset, seed
+    sim_dt, decimation = 0.02, 10                                      # :435-436
+    cfg.sim_dt, cfg.decimation, cfg.substeps = sim_dt, decimation, 4   # integrator sub-step 5 ms
+    episode_length_s = 10.0                                            # :439
+    cfg.max_episode_length = math.ceil(episode_length_s / (sim_dt * decimation))
+    cfg.episode_length_s = episode_length_s
+    cfg.action_kind, cfg.bounding, cfg.no_reverse = ACT_4WD, BOUND_CLIP, 1
+    _set(cfg.act_scale, (3.0, 0.488))                                  # Mushr4WDActionCfg defaults (common/actions.py:44)
+    _set(cfg.act_offset, (0.0, 0.0))
+    cfg.base_length, cfg.base_width, cfg.wheel_radius_cfg = 0.325, 0.2, 0.05
+    _mushr_vehicle(cfg)
+    _hound_actuators(cfg, "4wd")
+    cfg.ground_mu_s, cfg.ground_mu_d = 2.0, 2.0                        # :126-135 (combine = multiply)
+    cfg.dr_enable, cfg.dr_num_buckets = 0, 1                           # VisualEventsCfg: reset only (DR variant not registered)
+    D, Cs = material_buckets(1, (1.0, 1.0), (1.0, 1.0), True, cfg.ground_mu_s, cfg.ground_mu_d, seed)   # USD wheel material 1.0/1.0
+    _set(cfg.dr_bucket_D, D)
+    _set(cfg.dr_bucket_C, Cs)
+    _set(cfg.dr_kd_range, (10.0, 50.0))
+    cfg.dr_kd_mask = 0
+    _set(cfg.dr_mass_add, (0.0, 0.0))
+    cfg.enable_corruption, cfg.push_enable, cfg.num_ref_poses = 0, 0, 1
+    if traversability is None:
+        traversability = traversability_map(seed)
+    blob, n_trav = pack_traversability(traversability)
+    cfg.vis_rows, cfg.vis_cols = traversability.shape
+    cfg.vis_n_trav = n_trav
+    cfg.vis_row_spacing = cfg.vis_col_spacing = 0.5                    # :68-70
+    cfg.vis_width, cfg.vis_height = cfg.vis_rows * 0.5, cfg.vis_cols * 0.5   # :113-114
+    cfg.vis_spawn_z = 0.1
+    reward_names = ["traversablility", "vel_rew"]                     # :376-387 (sic)
+    cfg.num_rew_terms = len(reward_names)
+    _set(cfg.rew_weight, (5.0, 7.0))
+    spec = TaskSpec(name="visual", cfg=cfg, reward_names=reward_names,
+                    termination_names=[("time_out", True), ("out_range", False)], curriculum=[], obs_dim=8, action_dim=2,
+                    episode_length_s=episode_length_s, joint_names=list(MUSHR_JOINT_NAMES))
+    spec.heightfield = blob                                            # aux device blob (see header)
+    spec.traversability = traversability
+    return spec
+
+
 def make_task(name_or_id: str, **kw) -> TaskSpec:
     name = GYM_IDS.get(name_or_id, name_or_id)
     if name == "drift":
@@ -354,4 +403,6 @@ def make_task(name_or_id: str, **kw) -> TaskSpec:
         return spec
     if name == "elevation":
         return elevation_task(**kw)
+    if name == "visual":
+        return visual_task(**kw)
     raise NotImplementedError(f"task {name_or_id!r} is not implemented in this build")

@@ -55,3 +55,48 @@ def procedural_heightfield(seed: int = 0, half_extent: float = 20.5, cell: float
         h = np.maximum(h, base + np.clip(d + top, 0.0, top))
     h = np.clip(h, 0.0, z_max)
     return h.astype(np.float32), -half_extent, -half_extent, cell
+
+
+def traversability_map(seed: int = 0, map_size=(500, 500), env_size=(100, 100), sub_group_size=(50, 50), num_walkers: int = 1):
+    """Black/white traversability map of the Visual task: restates generated_colored_plane / generate_env_map /
+    generate_path (visual/utils/__init__.py:8-139; parameters visual/mushr_visual_env_cfg.py:66-90): per 100x100 block,
+    one start point per 50x50 sub-group, `num_walkers` random monotone lattice paths to random free cells, then a
+    one-step dilation with the asymmetric structure [[0,1,0],[0,1,1],[0,0,0]].  Returns bool [rows, cols]."""
+    rng = np.random.default_rng(seed + 0x51A1)
+    rows, cols = map_size
+    er, ec = env_size
+    gr, gc = sub_group_size
+    if rows % er or cols % ec:
+        raise ValueError("Map size must be a multiple of the sub environment size.")
+    m = np.zeros((rows, cols), dtype=bool)
+    for bi in range(rows // er):
+        for bj in range(cols // ec):
+            blk = np.zeros((er, ec), dtype=bool)
+            starts = [(int(rng.integers(0, gr)) + i * gr, int(rng.integers(0, gc)) + j * gc)
+                      for i in range(er // gr) for j in range(ec // gc)]
+            for sr, sc in starts:
+                for _ in range(num_walkers):
+                    tr, tc = int(rng.integers(0, er)), int(rng.integers(0, ec))
+                    while blk[tr, tc]:
+                        tr, tc = int(rng.integers(0, er)), int(rng.integers(0, ec))
+                    moves = [(-1 if tr < sr else 1, 0)] * abs(tr - sr) + [(0, -1 if tc < sc else 1)] * abs(tc - sc)
+                    r, c = sr, sc
+                    blk[r, c] = True
+                    for k in rng.permutation(len(moves)):
+                        r, c = r + moves[k][0], c + moves[k][1]
+                        blk[r, c] = True
+            m[bi * er:(bi + 1) * er, bj * ec:(bj + 1) * ec] = blk
+    from scipy.ndimage import binary_dilation
+    return binary_dilation(m, structure=np.array([[0, 1, 0], [0, 1, 1], [0, 0, 0]], dtype=bool), iterations=1)
+
+
+def pack_traversability(m: np.ndarray) -> np.ndarray:
+    """Device blob for the visual task (include/wheeledlab_b200.h): int32 trav_cells[n] | pad to 16 B | uint8 map."""
+    m = np.ascontiguousarray(m, dtype=bool)
+    ys, xs = m.nonzero()                                   # generate_random_poses: candidates = map.nonzero()
+    cells = (ys.astype(np.int64) * m.shape[1] + xs).astype(np.int32)
+    off = (cells.size * 4 + 15) & ~15
+    blob = np.zeros(off + m.size, dtype=np.uint8)
+    blob[: cells.size * 4] = cells.view(np.uint8)
+    blob[off:] = m.reshape(-1).astype(np.uint8)
+    return blob, int(cells.size)
