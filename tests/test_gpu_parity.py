@@ -367,3 +367,26 @@ def test_visual_trajectory_bit_exact(variant):
     env = wl.make("Isaac-MushrVisualRL-v0", num_envs=64)
     o, _ = env.reset()
     assert o["policy"].shape == (64, 8) and env.max_episode_length == 50
+
+
+def test_articulation_views_and_suspension():
+    """env.scene["robot"].data.* (IsaacLab names): zero-copy root state, derived joint state incl. suspension."""
+    _need_gpu()
+    import wheeledlab_b200 as wl
+    env = wl.make("Isaac-MushrDriftRL-v0", num_envs=256, seed=1)
+    env.reset()
+    for t in range(30):
+        env.step(env.sim.synth_actions(t))
+    d = env.scene["robot"].data
+    jp, jv = d.joint_pos, d.joint_vel
+    assert jp.shape == (256, 10) and jv.shape == (256, 10)
+    susp = jp[:, 6:10]
+    assert susp.abs().max() <= 0.01 + 1e-6 and (susp > 0.001).float().mean() > 0.9      # ~3.7 mm static deflection, +-10 mm travel
+    ids, names = env.scene["robot"].find_joints(".*_steer")
+    assert names == ["front_left_wheel_steer", "front_right_wheel_steer"] and torch.equal(jp[:, ids], env.sim.steer_pos)
+    # write_root_pose_to_sim goes through the zero-copy views (events.py:132-133)
+    pose = torch.tensor([[0.8, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0]], device="cuda").repeat(4, 1)
+    env.scene["robot"].write_root_pose_to_sim(pose, env_ids=torch.tensor([0, 5, 7, 9], device="cuda"))
+    assert torch.equal(d.root_pos_w[[0, 5, 7, 9]], pose[:, :3]) and torch.equal(d.root_quat_w[5], pose[0, 3:])
+    vb = d.root_lin_vel_b
+    assert vb.shape == (256, 3) and torch.isfinite(vb).all()

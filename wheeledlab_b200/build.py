@@ -29,7 +29,8 @@ def build_native(force: bool = False, verbose: bool = False) -> Path:
     srcs = [CSRC / "wl_api.cu"]
     deps = srcs + list(CSRC.glob("*.cuh")) + [ROOT / "include" / "wheeledlab_b200.h"]
     if force or _stale(LIB, deps):
-        cmd = [NVCC, *NVCC_FLAGS, *(["-Xptxas", "-v"] if verbose else []), "-o", str(LIB), *map(str, srcs)]
+        extra = [f"-DWL_STEP_MIN_BLOCKS={os.environ['WL_STEP_MIN_BLOCKS']}"] if os.environ.get("WL_STEP_MIN_BLOCKS") else []
+        cmd = [NVCC, *NVCC_FLAGS, *extra, *(["-Xptxas", "-v"] if verbose else []), "-o", str(LIB), *map(str, srcs)]
         subprocess.run(cmd, check=True, cwd=str(ROOT))
     return LIB
 

@@ -97,8 +97,11 @@ __device__ __forceinline__ void log_finalize(const wl_config& c, wl_globals* __r
 }
 
 // One thread per env.  TASK selects the MDP + terrain at compile time.
+#ifndef WL_STEP_MIN_BLOCKS
+#define WL_STEP_MIN_BLOCKS 4      // 4 CTAs x 128 threads / SM (<= 128 registers); see profiles/ for the occupancy A/B
+#endif
 template <int TASK>
-__global__ void __launch_bounds__(128, 4)
+__global__ void __launch_bounds__(128, WL_STEP_MIN_BLOCKS)
 wl_step_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st, wl_globals* __restrict__ gl, Terrain T,
                const float2* __restrict__ action, float* __restrict__ obs, float* __restrict__ rew,
                uint8_t* __restrict__ terminated_o, uint8_t* __restrict__ truncated_o, float* __restrict__ d_log, uint32_t t) {
@@ -483,6 +486,40 @@ __global__ void wl_observe_kernel(const __grid_constant__ wl_config c, const flo
     blind_obs(c, e, (uint32_t)(c.env_id_offset + i), t, RNG_OBS_EXTRA, 3u * call_idx, obs + (size_t)WL_OBS_DIM_BLIND * i);
 }
 
+// suspension joint pos / vel are not part of the stored state: derive them for the articulation view.
+// pos = clamp(compression, +-travel) of the wheel's contact spring, vel = compression rate, wheel order [bl,br,fl,fr].
+template <int TASK>
+__global__ void wl_suspension_kernel(const __grid_constant__ wl_config c, const float4* __restrict__ st, Terrain T,
+                                     float4* __restrict__ pos_o, float4* __restrict__ vel_o) {
+    const int n = c.num_envs;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    EnvState e;
+    load_env(st, n, i, e, false);
+    M3 R = rotmat(e.qw, e.qx, e.qy, e.qz);
+    V3 cw = rot(R, V3{c.com[0], c.com[1], c.com[2]});
+    V3 pc{e.p.x + cw.x, e.p.y + cw.y, e.p.z + cw.z};
+    V3 vb = rotT(R, e.v), wb = rotT(R, e.w);
+    float sp[4], sv[4];
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+        V3 rho{((w >= 2) ? c.hub_x_front : c.hub_x_rear) - c.com[0], ((w & 1) ? -c.hub_y : c.hub_y) - c.com[1], c.hub_z - c.com[2]};
+        V3 hubw = rot(R, rho);
+        hubw.x += pc.x; hubw.y += pc.y; hubw.z += pc.z;
+        float zt = 0.0f; V3 nw{0.0f, 0.0f, 1.0f};
+        if (TASK == WL_TASK_ELEVATION) heightfield_at(c, T, hubw.x, hubw.y, zt, nw);
+        float comp = fm(-(hubw.z - zt), nw.z, c.wheel_radius);
+        V3 nb = rotT(R, nw);
+        V3 rc = axpy(rho, -c.wheel_radius, nb);
+        V3 vc = cross(wb, rc);
+        vc.x += vb.x; vc.y += vb.y; vc.z += vb.z;
+        sp[w] = r_clamp(comp, -c.susp_travel, c.susp_travel);
+        sv[w] = (comp > 0.0f) ? -dot(nb, vc) : 0.0f;
+    }
+    pos_o[i] = make_float4(sp[0], sp[1], sp[2], sp[3]);
+    vel_o[i] = make_float4(sv[0], sv[1], sv[2], sv[3]);
+}
+
 struct CurrArgs { int32_t n; int32_t slots[WL_MAX_REW_TERMS]; float inc[WL_MAX_REW_TERMS]; uint32_t fire_mask; };
 __global__ void wl_curriculum_kernel(wl_globals* __restrict__ gl, CurrArgs a) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
@@ -794,8 +831,16 @@ int wl_synth_actions(wl_sim* sim, float* d_action, int64_t step_counter, int32_t
 }
 
 int wl_derive_suspension(wl_sim* sim, float* d_susp_pos, float* d_susp_vel, void* stream) {
-    (void)sim; (void)d_susp_pos; (void)d_susp_vel; (void)stream;
-    return fail(WL_EUNSUPPORTED, "wl_derive_suspension: not implemented yet");
+    if (!sim || !d_susp_pos || !d_susp_vel) return fail(WL_EINVAL, "wl_derive_suspension: null argument");
+    if (((uintptr_t)d_susp_pos & 15u) || ((uintptr_t)d_susp_vel & 15u)) return fail(WL_EINVAL, "wl_derive_suspension: outputs must be 16-byte aligned");
+    const int n = sim->cfg.num_envs, bs = 128;
+    Terrain T{sim->hf};
+    if (sim->cfg.task == WL_TASK_ELEVATION)
+        wl_suspension_kernel<WL_TASK_ELEVATION><<<(n + bs - 1) / bs, bs, 0, (cudaStream_t)stream>>>(sim->cfg, sim->state, T, (float4*)d_susp_pos, (float4*)d_susp_vel);
+    else
+        wl_suspension_kernel<WL_TASK_DRIFT><<<(n + bs - 1) / bs, bs, 0, (cudaStream_t)stream>>>(sim->cfg, sim->state, T, (float4*)d_susp_pos, (float4*)d_susp_vel);
+    WL_LAUNCH_CHECK(sim, "wl_suspension_kernel");
+    return WL_OK;
 }
 
 int wl_test_detmath(int32_t op, const float* d_in, const float* d_in2, float* d_out, int32_t n, void* stream) {

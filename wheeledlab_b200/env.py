@@ -170,13 +170,15 @@ class _RobotData:
         out = torch.zeros((n, 10), device=self._sim.device)
         out[:, 0:4] = self._sim.wheel_vel
         out[:, 4:6] = self._sim.steer_vel
+        out[:, 6:10] = self._sim.suspension_state()[1]
         return out
 
     @property
     def joint_pos(self):
         n = self._sim.num_envs
-        out = torch.zeros((n, 10), device=self._sim.device)
+        out = torch.zeros((n, 10), device=self._sim.device)     # wheel angles are not tracked (not needed by any term)
         out[:, 4:6] = self._sim.steer_pos
+        out[:, 6:10] = self._sim.suspension_state()[0]
         return out
 
 

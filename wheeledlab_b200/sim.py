@@ -159,6 +159,14 @@ class WheeledSim:
               "wl_synth_actions")
         return act
 
+    def suspension_state(self):
+        """Derived suspension joint (pos [N,4], vel [N,4]) in wheel order [bl, br, fl, fr]."""
+        pos = torch.empty((self.num_envs, 4), dtype=torch.float32, device=self.device)
+        vel = torch.empty((self.num_envs, 4), dtype=torch.float32, device=self.device)
+        check(lib.wl_derive_suspension(self._h, C.c_void_p(pos.data_ptr()), C.c_void_p(vel.data_ptr()), _stream_ptr(self.device)),
+              "wl_derive_suspension")
+        return pos, vel
+
     def set_scan_tma(self, use_tma: bool):
         check(lib.wl_set_scan_tma(self._h, 1 if use_tma else 0), "wl_set_scan_tma")
 
