@@ -308,7 +308,10 @@ def run_ours(args):
                            "actions from / writes reward+dones to pinned host memory over PCIe, then stream sync, every step"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "wl_step_kernel<DRIFT>",
+                         # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of
+                         # this kernel at this size (profiles/r01_ncu_v3_step_4096.txt: 931 072 B read, 0 B written -- the
+                         # 1.7 MB working set is written back from L2 later, so DRAM traffic < algorithmic bytes)
+                         "traffic": 931072 if E == 4096 else None, "traffic_unit": "bytes/launch", "peak_source": peak_src, "kernel": "wl_step_kernel<DRIFT>",
                          "bytes_per_env_step": BYTES_PER_ENV_STEP, "avg_kernel_us": kern_s * 1e6,
                          "kernel_variant": "quad (4 lanes/env)" if E <= 148 * 4 * 32 * 2 else "thread-per-env",
                          "note": "N=4096 moves 1.7 MB/launch: launch-latency bound, see profiles/ for the N sweep"},
