@@ -15,12 +15,15 @@ from bench import BYTES_PER_ENV_STEP, _peaks  # noqa: E402
 
 
 TASK = "drift"
+VARIANT = 0
 BYTES = {"drift": BYTES_PER_ENV_STEP, "elevation": (15 * 16 + 8) + (11 * 16 + 689 * 4 + 4 + 2)}
 
 
 def one(n, steps, warm, flush):
     spec = wl.drift_task(num_envs=n, seed=42) if TASK == "drift" else wl.elevation_task(num_envs=n, seed=42)
     sim = wl.WheeledSim(spec, "cuda:0")
+    if VARIANT:
+        sim.set_kernel_variant(VARIANT)
     sim.startup(); sim.reset(None, 0)
     acts = [sim.synth_actions(t) for t in range(4)]
     outs = tuple(torch.empty_like(x) for x in sim.step(acts[0], 0))
@@ -46,9 +49,11 @@ def main():
     ap.add_argument("--warm", type=int, default=5)
     ap.add_argument("--no-flush", action="store_true")
     ap.add_argument("--task", default="drift", choices=["drift", "elevation"])
+    ap.add_argument("--variant", type=int, default=0, help="0 auto, 1 thread/env, 4 quad/env")
     a = ap.parse_args()
-    global TASK
+    global TASK, VARIANT
     TASK = a.task
+    VARIANT = a.variant
     peak, src = _peaks()
     flush = None if a.no_flush else torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda:0")
     rows = []
