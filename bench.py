@@ -206,6 +206,13 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        tt = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
     # ---- device-resident timing: per-step events around the step launch, L2 flushed between steps ----
     t = 1
     for _ in range(W):
@@ -275,14 +282,30 @@ def run_ours(args):
 
     e2e_copy_ms = time_e2e("copy")
     e2e_ms = time_e2e("zero_copy")
+    # ---- policy in the loop: 128 x (64x64 ELU MLP -> step -> slab row) captured as ONE CUDA graph (supplementary) ----
+    pil = None
+    try:
+        from wheeledlab_b200.rollout import GraphedRollout
+        torch.manual_seed(0)
+        mlp = torch.nn.Sequential(torch.nn.Linear(sim.obs_dim, 64), torch.nn.ELU(), torch.nn.Linear(64, 64), torch.nn.ELU(),
+                                  torch.nn.Linear(64, 2)).to(dev)
+        sim_p = wl.WheeledSim(wl.drift_task(num_envs=E, seed=args.seed, env_id_offset=rank * E), dev)
+        sim_p.startup(); sim_p.reset(None, 0)
+        with torch.no_grad():
+            roll = GraphedRollout(sim_p, lambda o: mlp(o), T_ROLL).capture(0)
+            roll.run(); barrier()
+            R = 4
+            p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            p0.record()
+            for _ in range(R):
+                roll.run()
+            p1.record(); barrier()
+        pil_ms = max_over_ranks(p0.elapsed_time(p1)) if world > 1 else p0.elapsed_time(p1)
+        pil = {"value": E * world * T_ROLL * R / (pil_ms * 1e-3), "unit": UNIT, "ms_per_step": pil_ms / (T_ROLL * R),
+               "note": "rsl_rl-sized actor (14-64-64-2 ELU, torch/cuBLAS) + fused env step, 128 steps per CUDA-graph launch"}
+    except Exception as ex:                                      # supplementary figure only
+        pil = {"error": repr(ex)[:200]}
     clocks = sampler.stop() if rank == 0 else None
-
-    def max_over_ranks(x):
-        if world == 1:
-            return x
-        tt = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        return float(tt.item())
 
     tot_ms, graph_ms, e2e_ms = max_over_ranks(tot_ms), max_over_ranks(graph_ms), max_over_ranks(e2e_ms)
     e2e_copy_ms = max_over_ranks(e2e_copy_ms)
@@ -318,6 +341,7 @@ def run_ours(args):
             "cpu_baseline": cpu,
             "collective": {"kind": "all_gather_into_tensor(rollout slab)", "per_iteration_steps": T_ROLL,
                            "bytes_per_rank": slab.nbytes, "count": len(gev), "ms_total": gather_ms} if world > 1 else None,
+            "policy_in_loop_graph": pil,
             "warm_l2_graph": {"value": total_envs * K / (graph_ms * 1e-3), "unit": UNIT, "ms_per_step": graph_ms / K,
                               "note": "K steps captured in one CUDA graph, state L2-resident (supplementary)"},
         }

@@ -191,6 +191,14 @@ extern "C" {
     XS(float, f32, energy_straight)                                                                \
     XS(int32_t, i32, num_rew_terms)                                                                \
     XA(float, f32, rew_weight, WL_MAX_REW_TERMS)  /* initial weights; live copy is on device */    \
+    /* --- curriculum: increase_reward_weight_over_time terms (curriculums.py:10-35), evaluated ON DEVICE by the  \
+     *     last CTA of every step (no host logic => the step is CUDA-graph replayable) --- */        \
+    XS(int32_t, i32, curr_n)                                                                       \
+    XS(int32_t, i32, _pad6)                                                                        \
+    XA(int32_t, i32, curr_slot, 4)    /* reward slot of term k */                                  \
+    XA(int32_t, i32, curr_every, 4)   /* episodes_per_increase */                                  \
+    XA(int32_t, i32, curr_max, 4)     /* max_increases (INT32_MAX = inf) */                        \
+    XA(float, f32, curr_inc, 4)       /* increase */                                               \
     /* --- elevation task (elevation/mushr_elevation_env_cfg.py) --- */                            \
     XS(int32_t, i32, hf_nx)           /* height-field raster size */                               \
     XS(int32_t, i32, hf_ny)                                                                        \
@@ -282,7 +290,8 @@ typedef struct wl_globals {
                                           /* [8] #reset, [9+j] #envs whose termination term j fired          */
     uint32_t ticket;                      /* CTAs finished in the current launch (last one finalises)       */
     int32_t any_reset_last;               /* 1 if the previous step reset >= 1 env (read by wl_curriculum)  */
-    int32_t _pad[2];
+    uint32_t step_counter;                /* common_step_counter on the device (= last step's counter + 1)  */
+    int32_t _pad[1];
 } wl_globals;
 #define WL_LOG_FLOATS 16                  /* d_log: [0..7] Episode_Reward means, [8] #reset, [9+j] term counts */
 /* termination term order (bit j of the per-env mask; declaration order of the reference cfgs)
@@ -297,6 +306,8 @@ typedef struct wl_sim wl_sim;   /* opaque handle (host memory) */
 /* "name:tag:count:offset;..." for every wl_config field, plus "sizeof:<n>". */
 const char* wl_config_describe(void);
 size_t wl_config_sizeof(void);
+/* set the device-resident step counter (wl_create zeroes it; wl_step advances it) */
+int wl_set_step_counter(wl_sim* sim, int64_t value, void* stream);
 /* fill the d_* derived fields from the primary ones (idempotent). */
 int wl_config_finalize(wl_config* cfg);
 
@@ -324,8 +335,11 @@ int wl_startup(wl_sim* sim, void* stream);
  * IsaacLab passes them (_reset_idx).  `step_counter` keys the counter-based RNG. */
 int wl_reset(wl_sim* sim, const int64_t* d_env_ids, int32_t n_ids, int64_t step_counter, void* stream);
 /* one env.step(): action[N,2] f32 -> obs[N,obs_dim] f32, rew[N] f32, terminated[N] u8,
- * truncated[N] u8.  `step_counter` = common_step_counter BEFORE this step.  Auto-resets
- * finished envs (reward belongs to the pre-reset state, obs to the post-reset state). */
+ * truncated[N] u8.  `step_counter` = common_step_counter BEFORE this step, or WL_DEVICE_COUNTER to use (and
+ * advance) the counter kept in device memory -- then the call carries no per-step host value and a captured CUDA
+ * graph of it can be replayed.  Auto-resets finished envs (reward belongs to the pre-reset state, obs to the
+ * post-reset state).  The cfg's curriculum terms are applied by the last CTA (reference: inside _reset_idx). */
+#define WL_DEVICE_COUNTER (-1)
 /* d_log: optional float[WL_LOG_FLOATS]: mean over the envs reset in this step of each reward term's episode sum
  * divided by max_episode_length_s (RewardManager.reset -> extras["log"]), then the reset / terminated / time-out
  * counts.  Written by the last CTA of the launch: no extra kernel, no host sync. */

@@ -930,6 +930,17 @@ int wlo_step(wlo_sim* s, const float* action, float* obs, float* rew, uint8_t* t
     s->log_term[0] = tot.n_reset;
     for (int j = 0; j < WL_MAX_TERM_TERMS; ++j) s->log_term[1 + j] = tot.n_term[j];
     s->any_reset_last = tot.any;
+    /* common_step_counter += 1, then the curriculum terms (curriculums.py:23-35), only if >= 1 env reset this step */
+    {
+        int64_t cn = step_counter + 1;
+        if (c->curr_n > 0 && tot.any && (cn % c->max_episode_length) == 0) {
+            int E = (int)(cn / c->max_episode_length);
+            for (int k = 0; k < c->curr_n; ++k) {
+                if (E / c->curr_every[k] > c->curr_max[k]) continue;
+                if ((E + 1) % c->curr_every[k] == 0) s->rew_weight[c->curr_slot[k]] += (real)c->curr_inc[k];
+            }
+        }
+    }
     return err;
 }
 

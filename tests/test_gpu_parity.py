@@ -176,25 +176,56 @@ def test_sharding_invariance_two_shards_equal_one():
 
 
 def test_curriculum_on_device_matches_oracle():
+    """increase_reward_weight_over_time evaluated by the step kernel's last CTA: fires only at episode boundaries of the
+    global counter AND only if some env reset in that step; weights and subsequent rewards match the oracle."""
     _need_gpu()
-    spec, sim, orc = _pair(64, seed=2)
+    import wheeledlab_b200 as wl
+    spec = wl.drift_task(num_envs=64, seed=2)
+    spec.cfg.curr_every[0] = 1                       # term 0 (side_slip += 20) every episode, term 2 every 2nd
+    spec.cfg.curr_every[2] = 2
+    sim = wl.WheeledSim(spec, "cuda:0"); sim.startup(); sim.reset(None, 0)
+    orc = O.Oracle(spec.cfg); orc.startup(); orc.reset(None, 0)
     w0 = sim.rew_weight.cpu().numpy().copy()
-    act = sim.synth_actions(0)
-    sim.step(act, 0); orc.step(act.cpu().numpy(), 0)
-    # no env reset at step 0 -> curriculum call is a no-op even with every fire bit set
-    sim.curriculum([0, 3, 6], [20.0, 10.0, -1000.0], 0b111); orc.curriculum([0, 3, 6], [20.0, 10.0, -1000.0], 0b111)
-    assert np.array_equal(sim.rew_weight.cpu().numpy(), w0)
-    for t in range(1, 250):
+    for t in range(0, 502):
         act = sim.synth_actions(t)
-        sim.step(act, t); orc.step(act.cpu().numpy(), t)
-    # step 249 times out every surviving env -> any_reset set -> weights move
-    sim.curriculum([0, 3, 6], [20.0, 10.0, -1000.0], 0b101); orc.curriculum([0, 3, 6], [20.0, 10.0, -1000.0], 0b101)
-    w = sim.rew_weight.cpu().numpy()
-    assert w[0] == w0[0] + 20 and w[3] == w0[3] and w[6] == w0[6] - 1000
-    assert np.array_equal(w, orc.weights())
-    act = sim.synth_actions(250)
-    _, rew, _, _ = sim.step(act, 250); _, o_rew, _, _ = orc.step(act.cpu().numpy(), 250)
-    assert np.array_equal(_bits(rew.cpu().numpy()), _bits(o_rew))
+        _, rew, _, _ = sim.step(act, t); _, o_rew, _, _ = orc.step(act.cpu().numpy(), t)
+        assert np.array_equal(_bits(rew.cpu().numpy()), _bits(o_rew)), t
+        if t in (248, 249, 498, 499):
+            w = sim.rew_weight.cpu().numpy()
+            assert np.array_equal(w, orc.weights()), t
+            if t == 248:
+                assert np.array_equal(w, w0)
+            if t == 249:                             # counter 250: E = 1 -> term0 fires ((E+1) % 1 == 0), term2 fires ((1+1) % 2 == 0)
+                assert w[0] == w0[0] + 20 and w[6] == w0[6] - 1000 and w[3] == w0[3]
+            if t == 499:                             # counter 500: E = 2 -> term0 fires again, term2 not ((2+1) % 2 != 0)
+                assert w[0] == w0[0] + 40 and w[6] == w0[6] - 1000
+
+
+def test_device_counter_graph_replay_equals_host_counter():
+    """wl_step(WL_DEVICE_COUNTER) captured ONCE in a CUDA graph and replayed T times == T host-counter steps."""
+    _need_gpu()
+    import wheeledlab_b200 as wl
+    n, T = 512, 300
+    a = wl.WheeledSim(wl.drift_task(num_envs=n, seed=6), "cuda:0"); b = wl.WheeledSim(wl.drift_task(num_envs=n, seed=6), "cuda:0")
+    for s_ in (a, b):
+        s_.startup(); s_.reset(None, 0)
+    act = torch.empty((n, 2), device="cuda"); out = tuple(torch.empty_like(x) for x in a.step(a.synth_actions(0), 0))
+    b.step(b.synth_actions(0), 0)                    # both are at counter 1 now
+    b.set_step_counter(1)
+    stream = torch.cuda.Stream(); stream.wait_stream(torch.cuda.current_stream())
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(stream):
+        with torch.cuda.graph(g, stream=stream):
+            b.synth_actions(wl.WheeledSim.DEVICE_COUNTER, out=act)
+            b.step(act, wl.WheeledSim.DEVICE_COUNTER, out=out)
+    torch.cuda.current_stream().wait_stream(stream)
+    for t in range(1, T):
+        ref = a.step(a.synth_actions(t), t)
+        g.replay()
+        torch.cuda.synchronize()
+        for x, y in zip(ref, out):
+            assert torch.equal(x, y), f"graph replay differs at step {t}"
+    assert torch.equal(a.groups, b.groups) and torch.equal(a.rew_weight, b.rew_weight)
 
 
 def test_env_api_surface_and_full_size_properties():
@@ -390,3 +421,29 @@ def test_articulation_views_and_suspension():
     assert torch.equal(d.root_pos_w[[0, 5, 7, 9]], pose[:, :3]) and torch.equal(d.root_quat_w[5], pose[0, 3:])
     vb = d.root_lin_vel_b
     assert vb.shape == (256, 3) and torch.isfinite(vb).all()
+
+
+def test_graphed_policy_rollout_equals_eager_loop():
+    """T x (MLP policy -> env.step) captured in one CUDA graph == the same loop run eagerly with host counters."""
+    _need_gpu()
+    import wheeledlab_b200 as wl
+    from wheeledlab_b200.rollout import GraphedRollout
+    n, T = 1024, 64
+    torch.manual_seed(0)
+    mlp = torch.nn.Sequential(torch.nn.Linear(14, 64), torch.nn.ELU(), torch.nn.Linear(64, 64), torch.nn.ELU(), torch.nn.Linear(64, 2)).cuda()
+    policy = lambda obs: mlp(obs)
+    a = wl.WheeledSim(wl.drift_task(num_envs=n, seed=9), "cuda:0"); b = wl.WheeledSim(wl.drift_task(num_envs=n, seed=9), "cuda:0")
+    for s_ in (a, b):
+        s_.startup(); s_.reset(None, 0)
+    with torch.no_grad():
+        roll = GraphedRollout(b, policy, T).capture(step_counter=0)
+        for it in range(3):
+            slab = roll.run()
+            torch.cuda.synchronize()
+            obs = a.observe(0, 0) if it == 0 else obs
+            for k in range(T):
+                act = policy(obs).contiguous()
+                obs, rew, term, trunc = a.step(act, it * T + k)
+                assert torch.equal(slab.obs[k], obs) and torch.equal(slab.rewards[k], rew), (it, k)
+                assert torch.equal(slab.terminated[k], term) and torch.equal(slab.truncated[k], trunc)
+    assert torch.equal(a.groups, b.groups)

@@ -70,12 +70,14 @@ class WlGlobals(C.Structure):
         ("acc", C.c_float * 12),
         ("ticket", C.c_uint32),
         ("any_reset_last", C.c_int32),
-        ("_pad", C.c_int32 * 2),
+        ("step_counter", C.c_uint32),
+        ("_pad", C.c_int32 * 1),
     ]
 
 
 _vp, _i32, _i64, _u32, _u64, _sz = C.c_void_p, C.c_int32, C.c_int64, C.c_uint32, C.c_uint64, C.c_size_t
 lib.wl_config_finalize.argtypes = [C.POINTER(WlConfig)]
+lib.wl_set_step_counter.argtypes = [_vp, _i64, _vp]
 lib.wl_state_bytes.restype = _sz
 lib.wl_state_bytes.argtypes = [_i32]
 lib.wl_globals_offset.restype = _sz
@@ -103,7 +105,7 @@ lib.wl_test_detmath.argtypes = [_i32, _vp, _vp, _vp, _i32, _vp]
 lib.wl_test_philox.argtypes = [_u64, _u32, _u32, _u32, _u32, _vp, _i32, _vp]
 
 EXPORTED_SYMBOLS = [
-    "wl_config_describe", "wl_config_sizeof", "wl_config_finalize", "wl_state_bytes", "wl_globals_offset", "wl_create", "wl_destroy",
+    "wl_config_describe", "wl_config_sizeof", "wl_config_finalize", "wl_set_step_counter", "wl_state_bytes", "wl_globals_offset", "wl_create", "wl_destroy",
     "wl_last_error", "wl_build_info", "wl_startup", "wl_reset", "wl_step", "wl_step_host", "wl_step_host_zero_copy", "wl_result_bytes", "wl_observe", "wl_curriculum",
     "wl_synth_actions", "wl_derive_suspension", "wl_set_kernel_variant", "wl_set_scan_tma", "wl_obs_dim", "wl_launch_count", "wl_test_detmath", "wl_test_philox",
 ]

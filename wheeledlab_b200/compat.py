@@ -70,6 +70,7 @@ def _lower_common(cfg, spec: T.TaskSpec):
         p = term.params
         spec.curriculum.append(T.CurriculumTerm(name, p["reward_term_name"], float(p["increase"]),
                                                 int(p.get("episodes_per_increase", 1)), p.get("max_increases", math.inf)))
+    spec._curriculum_dirty = True
 
 
 def _lower_rewards(cfg, spec, table, handlers):
@@ -92,6 +93,7 @@ def _lower_rewards(cfg, spec, table, handlers):
             names[table[f]] = f
     spec.reward_names = names
     c.num_rew_terms = len(names)
+    T.set_curriculum(c, names, spec.curriculum)     # reward slots are known now
 
 
 def spec_from_reference_cfg(cfg, env_id_offset: int = 0) -> T.TaskSpec:

@@ -73,7 +73,7 @@ __device__ __forceinline__ bool log_accumulate(wl_globals* __restrict__ gl, bool
     return true;
 }
 // Last CTA of the launch turns the accumulators into the extras["log"] row and re-arms them.
-__device__ __forceinline__ void log_finalize(const wl_config& c, wl_globals* __restrict__ gl, float* __restrict__ d_log) {
+__device__ __forceinline__ void log_finalize(const wl_config& c, wl_globals* __restrict__ gl, float* __restrict__ d_log, uint32_t t) {
     __syncthreads();              // all warps of the CTA are past their (fenced) accumulation
     if (threadIdx.x != 0) return;
     const unsigned tk = atomicAdd(&gl->ticket, 1u);
@@ -94,6 +94,17 @@ __device__ __forceinline__ void log_finalize(const wl_config& c, wl_globals* __r
 #pragma unroll
     for (int k = 0; k < 16; ++k) gl->acc[k] = 0.0f;
     gl->ticket = 0u;
+    // common_step_counter += 1, then the curriculum (increase_reward_weight_over_time, curriculums.py:23-35; the
+    // reference calls it from _reset_idx, i.e. only on steps where >= 1 env reset)
+    const uint32_t cn = t + 1u;
+    gl->step_counter = cn;
+    if (c.curr_n > 0 && cnt > 0.0f && (cn % (uint32_t)c.max_episode_length) == 0u) {
+        const int E = (int)(cn / (uint32_t)c.max_episode_length);
+        for (int k = 0; k < c.curr_n; ++k) {
+            if (E / c.curr_every[k] > c.curr_max[k]) continue;
+            if ((E + 1) % c.curr_every[k] == 0) gl->rew_weight[c.curr_slot[k]] += c.curr_inc[k];
+        }
+    }
 }
 
 // One thread per env.  TASK selects the MDP + terrain at compile time.
@@ -104,10 +115,11 @@ template <int TASK>
 __global__ void __launch_bounds__(128, WL_STEP_MIN_BLOCKS)
 wl_step_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st, wl_globals* __restrict__ gl, Terrain T,
                const float2* __restrict__ action, float* __restrict__ obs, float* __restrict__ rew,
-               uint8_t* __restrict__ terminated_o, uint8_t* __restrict__ truncated_o, float* __restrict__ d_log, uint32_t t) {
+               uint8_t* __restrict__ terminated_o, uint8_t* __restrict__ truncated_o, float* __restrict__ d_log, uint32_t t_arg) {
     constexpr bool ELEV = (TASK == WL_TASK_ELEVATION), VIS = (TASK == WL_TASK_VISUAL);
     const int n = c.num_envs;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t t = (t_arg == 0xFFFFFFFFu) ? __ldcg(&gl->step_counter) : t_arg;   // device-resident counter (graph replay)
     const VisualMap vm = VIS ? visual_map(c, T.hf) : VisualMap{nullptr, nullptr};
     bool done = false;
     uint32_t tmask = 0u;
@@ -193,7 +205,7 @@ wl_step_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st, wl_
         }
         store_env(st, n, i, e, ELEV);
     }
-    log_finalize(c, gl, d_log);
+    log_finalize(c, gl, d_log, t);
 }
 
 // Four lanes per env (lane = wheel).  Same arithmetic, same results; the per-wheel work runs in parallel and the
@@ -202,8 +214,9 @@ template <int TASK>
 __global__ void __launch_bounds__(128)
 wl_step_quad_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st, wl_globals* __restrict__ gl, Terrain T,
                     const float2* __restrict__ action, float* __restrict__ obs, float* __restrict__ rew,
-                    uint8_t* __restrict__ terminated_o, uint8_t* __restrict__ truncated_o, float* __restrict__ d_log, uint32_t t) {
+                    uint8_t* __restrict__ terminated_o, uint8_t* __restrict__ truncated_o, float* __restrict__ d_log, uint32_t t_arg) {
     constexpr bool ELEV = (TASK == WL_TASK_ELEVATION), VIS = (TASK == WL_TASK_VISUAL);
+    const uint32_t t = (t_arg == 0xFFFFFFFFu) ? __ldcg(&gl->step_counter) : t_arg;
     const VisualMap vm = VIS ? visual_map(c, T.hf) : VisualMap{nullptr, nullptr};
     const int n = c.num_envs;
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -313,7 +326,7 @@ wl_step_quad_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st
         }
     }
     if (live) store_env_quad(st, n, i, w, e, ELEV);
-    log_finalize(c, gl, d_log);
+    log_finalize(c, gl, d_log, t);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -528,9 +541,11 @@ __global__ void wl_curriculum_kernel(wl_globals* __restrict__ gl, CurrArgs a) {
         if ((a.fire_mask >> t) & 1u) gl->rew_weight[a.slots[t]] += a.inc[t];
 }
 
-__global__ void wl_synth_actions_kernel(const __grid_constant__ wl_config c, float2* __restrict__ action, uint32_t t, int dist) {
+__global__ void wl_synth_actions_kernel(const __grid_constant__ wl_config c, const wl_globals* __restrict__ gl,
+                                        float2* __restrict__ action, uint32_t t_arg, int dist) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= c.num_envs) return;
+    const uint32_t t = (t_arg == 0xFFFFFFFFu) ? __ldcg(&gl->step_counter) : t_arg;
     uint4 r = philox4x32(c.seed, (uint32_t)(c.env_id_offset + i), t, RNG_ACTION, 0u);
     float a0, a1;
     if (dist == 0) { a0 = 2.0f * u01(r.x) - 1.0f; a1 = 2.0f * u01(r.y) - 1.0f; }
@@ -603,6 +618,13 @@ const char* wl_config_describe(void) {
     return s.c_str();
 }
 
+int wl_set_step_counter(wl_sim* sim, int64_t value, void* stream) {
+    if (!sim) return fail(WL_EINVAL, "wl_set_step_counter: null handle");
+    const uint32_t v = (uint32_t)value;
+    return cuda_check(cudaMemcpyAsync(&sim->globals->step_counter, &v, sizeof v, cudaMemcpyHostToDevice, (cudaStream_t)stream),
+                      "wl_set_step_counter");
+}
+
 int wl_config_finalize(wl_config* c) {
     if (!c) return fail(WL_EINVAL, "wl_config_finalize: null");
     if (c->substeps <= 0 || !(c->sim_dt > 0.0f)) return fail(WL_EINVAL, "wl_config_finalize: bad sim timing");
@@ -647,6 +669,10 @@ int wl_create(const wl_config* cfg, void* d_state, size_t state_bytes, const flo
         return fail(WL_EUNSUPPORTED, "wl_create: bounding_strategy 'tanh' is not implemented");
     if (cfg->decimation <= 0 || cfg->substeps <= 0 || !(cfg->sim_dt > 0.0f)) return fail(WL_EINVAL, "wl_create: bad sim timing");
     if (cfg->num_rew_terms < 0 || cfg->num_rew_terms > WL_MAX_REW_TERMS) return fail(WL_EINVAL, "wl_create: num_rew_terms");
+    if (cfg->curr_n < 0 || cfg->curr_n > 4) return fail(WL_EINVAL, "wl_create: curr_n must be in [0,4]");
+    for (int k = 0; k < cfg->curr_n; ++k)
+        if (cfg->curr_every[k] < 1 || cfg->curr_slot[k] < 0 || cfg->curr_slot[k] >= WL_MAX_REW_TERMS)
+            return fail(WL_EINVAL, "wl_create: bad curriculum term");
     if (cfg->num_ref_poses <= 0 || cfg->num_ref_poses > WL_MAX_REF_POSES) return fail(WL_EINVAL, "wl_create: num_ref_poses");
     if (cfg->dr_num_buckets < 1 || cfg->dr_num_buckets > WL_MAX_BUCKETS) return fail(WL_EINVAL, "wl_create: dr_num_buckets");
     int dev_count = 0;
@@ -824,7 +850,7 @@ int wl_curriculum(wl_sim* sim, int32_t n_terms, const int32_t* slots, const floa
 int wl_synth_actions(wl_sim* sim, float* d_action, int64_t step_counter, int32_t dist, void* stream) {
     if (!sim || !d_action) return fail(WL_EINVAL, "wl_synth_actions: null argument");
     const int n = sim->cfg.num_envs, bs = 128;
-    wl_synth_actions_kernel<<<(n + bs - 1) / bs, bs, 0, (cudaStream_t)stream>>>(sim->cfg, reinterpret_cast<float2*>(d_action),
+    wl_synth_actions_kernel<<<(n + bs - 1) / bs, bs, 0, (cudaStream_t)stream>>>(sim->cfg, sim->globals, reinterpret_cast<float2*>(d_action),
                                                                                (uint32_t)step_counter, dist);
     WL_LAUNCH_CHECK(sim, "wl_synth_actions_kernel");
     return WL_OK;

@@ -303,7 +303,8 @@ class ManagerBasedRLEnv:
         return obs["policy"], {"observations": obs}
 
     def _curriculum_fire_mask(self) -> int:
-        """Counter conditions of increase_reward_weight_over_time (curriculums.py:23-35)."""
+        """Counter conditions of increase_reward_weight_over_time (curriculums.py:23-35) -- the host-side restatement the
+        golden-vector test checks; at run time the same conditions are evaluated on the device (log_finalize)."""
         c, L = self.common_step_counter, self.max_episode_length
         if c % L != 0:
             return 0
@@ -326,11 +327,8 @@ class ManagerBasedRLEnv:
         log = torch.empty(16, dtype=torch.float32, device=self.device) if self.log_episode_info else None
         obs, rew, term_u8, trunc_u8 = self.sim.step(action, t, log=log)
         self.common_step_counter = t + 1
-        # curriculum (inside _reset_idx upstream: uses the incremented counter and fires only if >=1 env reset;
-        # the "any reset" test happens on the device, so there is no host sync)
-        mask = self._curriculum_fire_mask()
-        if mask:
-            self.sim.curriculum(self._curr_slots, self._curr_inc, mask)
+        # curriculum: applied by the step kernel's last CTA (uses the incremented counter and fires only if >= 1 env
+        # reset, like the reference's call from _reset_idx) -- no host logic, no sync
         terminated, truncated = term_u8.view(torch.bool), trunc_u8.view(torch.bool)
         tm = self.termination_manager
         tm.terminated, tm.time_outs = terminated, truncated
@@ -369,9 +367,6 @@ class ManagerBasedRLEnv:
         else:
             self.sim.step_host(io, t, obs, log)
         self.common_step_counter = t + 1
-        mask = self._curriculum_fire_mask()
-        if mask:
-            self.sim.curriculum(self._curr_slots, self._curr_inc, mask)
         tm = self.termination_manager
         tm.terminated, tm.time_outs = io["terminated"], io["truncated"]
         if log is not None:

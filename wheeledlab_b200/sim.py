@@ -84,9 +84,15 @@ class WheeledSim:
                 check(lib.wl_reset(self._h, C.c_void_p(ids.data_ptr()), ids.numel(), step_counter,
                                    _stream_ptr(self.device)), "wl_reset")
 
-    def step(self, action: torch.Tensor, step_counter: int, out=None, log: torch.Tensor | None = None):
+    DEVICE_COUNTER = -1
+
+    def set_step_counter(self, value: int):
+        check(lib.wl_set_step_counter(self._h, value, _stream_ptr(self.device)), "wl_set_step_counter")
+
+    def step(self, action: torch.Tensor, step_counter: int = -1, out=None, log: torch.Tensor | None = None):
         """action [N,2] f32 (device, contiguous) -> (obs [N,D] f32, rew [N] f32, terminated [N] u8, truncated [N] u8).
-        `log`: optional float32[16] device tensor receiving this step's episode log row (see wl_step)."""
+        `step_counter` = common_step_counter before the step, or DEVICE_COUNTER (-1): use and advance the counter kept on
+        the device (CUDA-graph replayable).  `log`: optional float32[16] device tensor receiving the episode log row."""
         n = self.num_envs
         if out is None:
             obs = torch.empty((n, self.obs_dim), dtype=torch.float32, device=self.device)

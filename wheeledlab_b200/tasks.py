@@ -124,6 +124,18 @@ def material_buckets(num_buckets, static_range, dynamic_range, make_consistent, 
     return D.astype(np.float32), Cshape.astype(np.float32)
 
 
+def set_curriculum(cfg: WlConfig, reward_names, curriculum) -> None:
+    """Lower CurriculumTerm list onto the cfg's on-device curriculum table."""
+    if len(curriculum) > 4:
+        raise NotImplementedError("at most 4 curriculum terms")
+    cfg.curr_n = len(curriculum)
+    for k, t in enumerate(curriculum):
+        cfg.curr_slot[k] = list(reward_names).index(t.reward_term_name)
+        cfg.curr_every[k] = int(t.episodes_per_increase)
+        cfg.curr_max[k] = 2**31 - 1 if t.max_increases == math.inf else int(t.max_increases)
+        cfg.curr_inc[k] = float(t.increase)
+
+
 def _set(arr, values):
     for k, v in enumerate(values):
         arr[k] = v
@@ -261,6 +273,7 @@ def drift_task(num_envs: int = 1024, seed: int = 42, env_id_offset: int = 0, ran
         CurriculumTerm("more_tlgr", "tlgr", 10.0, 20, 5),
         CurriculumTerm("more_term_pens", "term_pens", -1000.0, 50, 5),
     ]
+    set_curriculum(cfg, reward_names, curriculum)
     return TaskSpec(
         name="drift" if drive == "2wd" else "drift_4wd", cfg=cfg, reward_names=reward_names,
         termination_names=[("time_out", True), ("out_of_bounds", False)], curriculum=curriculum, obs_dim=14,
@@ -331,6 +344,7 @@ def elevation_task(num_envs: int = 1024, seed: int = 42, env_id_offset: int = 0,
         CurriculumTerm("more_goal", "vel_towards_goal", 5.0, 50, 5),
         CurriculumTerm("more_falling_pen", "falling_penalty", 1.0, 50, 10),
     ]
+    set_curriculum(cfg, reward_names, curriculum)
     spec = TaskSpec(
         name="elevation", cfg=cfg, reward_names=reward_names,
         termination_names=[("time_out", True), ("cart_out_of_bounds", False), ("stuck", False), ("rollover", False),
