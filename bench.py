@@ -171,7 +171,21 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+class _StdoutGuard:
+    """Everything any library prints to fd 1 (e.g. NCCL's version banner) goes to stderr; emit() writes the ONE JSON line
+    to the real stdout."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self._real = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, text: str):
+        os.write(self._real, (text + "\n").encode())
+
+
 def run_ours(args):
+    guard = _StdoutGuard()
     import torch
     import torch.distributed as dist
     import wheeledlab_b200 as wl
@@ -235,12 +249,17 @@ def run_ours(args):
         ev[k][1].record()
         flush.fill_(0.0)
         if world > 1 and row == T_ROLL - 1:            # one all-gather of the rollout slab per PPO iteration
+            barrier()                                  # untimed: the L2-flush fills between steps de-synchronise the ranks'
+            #                                            host loops; without this the gather would be charged that artefact
             g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             g0.record(); gathered = slab.all_gather(); g1.record(); gev.append((g0, g1))
     barrier()
     launches = sim.launch_count - l0
     step_ms = [a.elapsed_time(b) for a, b in ev]
-    gather_ms = sum(a.elapsed_time(b) for a, b in gev)
+    gather_each = [a.elapsed_time(b) for a, b in gev]
+    gather_ms = sum(gather_each)
+    if gev and rank == 0:
+        print(f"[bench] all-gather ms per call: {[round(x, 3) for x in gather_each]}", file=sys.stderr)
     tot_ms = sum(step_ms) + gather_ms
     # ---- warm-L2, CUDA-graph replay of K steps (supplementary: how the loop is meant to be driven) ----
     g = torch.cuda.CUDAGraph()
@@ -345,7 +364,7 @@ def run_ours(args):
             "warm_l2_graph": {"value": total_envs * K / (graph_ms * 1e-3), "unit": UNIT, "ms_per_step": graph_ms / K,
                               "note": "K steps captured in one CUDA graph, state L2-resident (supplementary)"},
         }
-        print(json.dumps(line), flush=True)
+        guard.emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
