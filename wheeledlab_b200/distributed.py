@@ -48,9 +48,13 @@ class RolloutSlab:
         return self.obs[t], self.rewards[t], self.terminated[t], self.truncated[t]
 
     def all_gather(self, group=None) -> "GatheredRollout":
-        """ONE collective: every rank receives every rank's slab (NCCL over NVLink on GPUs, gloo in CPU tests)."""
+        """ONE collective: every rank receives every rank's slab (NCCL over NVLink on GPUs, gloo in CPU tests).
+        The receive buffer is allocated once and reused: the returned views are overwritten by the next gather (a fresh
+        cudaMalloc of world x slab bytes per iteration costs tens of ms)."""
         world = dist.get_world_size(group) if dist.is_initialized() else 1
-        out = torch.empty(world * self.flat.numel(), dtype=torch.uint8, device=self.device)
+        if getattr(self, "_recv", None) is None or self._recv.numel() != world * self.flat.numel():
+            self._recv = torch.empty(world * self.flat.numel(), dtype=torch.uint8, device=self.device)
+        out = self._recv
         if world == 1:
             out.copy_(self.flat)
         else:
