@@ -357,13 +357,17 @@ class ManagerBasedRLEnv:
         # outputs come from a ring of preallocated device buffers (valid for _RING steps, like IsaacLab's own reuse)
         k = t % self._RING
         if self._ring is None:
-            self._ring = [(torch.empty((self.num_envs, self.spec.obs_dim), dtype=torch.float32, device=self.device),
-                           torch.empty(16, dtype=torch.float32, device=self.device)) for _ in range(self._RING)]
-        obs, log = self._ring[k]
+            import ctypes as C
+            self._ring = []
+            for _ in range(self._RING):
+                o = torch.empty((self.num_envs, self.spec.obs_dim), dtype=torch.float32, device=self.device)
+                lg = torch.empty(16, dtype=torch.float32, device=self.device)
+                self._ring.append((o, lg, C.c_void_p(o.data_ptr()), C.c_void_p(lg.data_ptr())))
+        obs, log, p_obs, p_log = self._ring[k]
         if not self.log_episode_info:
-            log = None
+            log, p_log = None, None
         if self.host_transport == "zero_copy":
-            self.sim.step_host_zero_copy(io, t, obs, log)
+            self.sim.step_host_zero_copy(io, t, obs, log, p_obs, p_log)
         else:
             self.sim.step_host(io, t, obs, log)
         self.common_step_counter = t + 1
