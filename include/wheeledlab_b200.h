@@ -345,6 +345,14 @@ int wl_reset(wl_sim* sim, const int64_t* d_env_ids, int32_t n_ids, int64_t step_
  * counts.  Written by the last CTA of the launch: no extra kernel, no host sync. */
 int wl_step(wl_sim* sim, const float* d_action, float* d_obs, float* d_rew, uint8_t* d_terminated,
             uint8_t* d_truncated, float* d_log, int64_t step_counter, void* stream);
+/* K consecutive env.step()s in ONE launch with the state held in registers (synthetic / scripted-action rollouts:
+ * wheeledlab_tasks/test/create_and_step_env.py:34-41 without the per-step host round trip).  d_actions: [K,N,2] or NULL
+ * (then U[-1,1]^2 is drawn in-kernel from the counter-based generator; d_actions_out, if not NULL, receives them).
+ * Outputs are [K,N,...] slabs; d_log is [K, WL_LOG_FLOATS].  Bit-identical to K wl_step calls.  With curriculum terms
+ * configured, [step_counter, step_counter+K) must end at or before the next episode boundary of the global counter
+ * (the boundary's weight update happens between launches).  Drift / Visual only (Elevation needs its scan kernel). */
+int wl_rollout(wl_sim* sim, int32_t K, const float* d_actions, float* d_actions_out, float* d_obs, float* d_rew,
+               uint8_t* d_terminated, uint8_t* d_truncated, float* d_log, int64_t step_counter, void* stream);
 /* env.step() for a HOST-side caller, host buffers in, host buffers out, one call:
  *   H2D  h_action[N,2] (pinned)  ->  d_action
  *   wl_step(...) writing d_obs, and reward / terminated / truncated into ONE device block d_result laid out as

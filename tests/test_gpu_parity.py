@@ -452,3 +452,34 @@ def test_graphed_policy_rollout_equals_eager_loop():
                 assert torch.equal(slab.obs[k], obs) and torch.equal(slab.rewards[k], rew), (it, k)
                 assert torch.equal(slab.terminated[k], term) and torch.equal(slab.truncated[k], trunc)
     assert torch.equal(a.groups, b.groups)
+
+
+def test_fused_k_step_rollout_equals_k_single_steps():
+    """wl_rollout (K env.steps in one launch, state in registers, in-kernel actions) == K x (synth_actions + wl_step)."""
+    _need_gpu()
+    import wheeledlab_b200 as wl
+    from wheeledlab_b200.distributed import RolloutSlab
+    n, K = 700, 100
+    a = wl.WheeledSim(wl.drift_task(num_envs=n, seed=13), "cuda:0"); b = wl.WheeledSim(wl.drift_task(num_envs=n, seed=13), "cuda:0")
+    for s_ in (a, b):
+        s_.startup(); s_.reset(None, 0)
+    slab = RolloutSlab(K, n, 14, 2, "cuda:0"); logs = torch.empty((K, 16), device="cuda")
+    for it, t0 in enumerate((0, 100, 200)):          # 200..299 crosses counter 250 -> must be split
+        if t0 == 200:
+            with pytest.raises(wl.WlError):
+                b.rollout(K, t0, slab, logs)
+            b.rollout(50, 200, slab, logs); first = [x[:50].clone() for x in (slab.obs, slab.rewards, slab.terminated, slab.truncated, slab.actions)]
+            b.rollout(50, 250, slab, logs)
+            got = [torch.cat([f, x[:50]]) for f, x in zip(first, (slab.obs, slab.rewards, slab.terminated, slab.truncated, slab.actions))]
+        else:
+            b.rollout(K, t0, slab, logs)
+            got = [x.clone() for x in (slab.obs, slab.rewards, slab.terminated, slab.truncated, slab.actions)]
+        for k in range(K):
+            act = a.synth_actions(t0 + k)
+            log = torch.empty(16, device="cuda")
+            obs, rew, term, trunc = a.step(act, t0 + k, log=log)
+            assert torch.equal(got[4][k], act) and torch.equal(got[0][k], obs) and torch.equal(got[1][k], rew), (t0, k)
+            assert torch.equal(got[2][k], term) and torch.equal(got[3][k], trunc)
+            if t0 != 200:
+                assert torch.allclose(logs[k], log, rtol=1e-5, atol=1e-4) and torch.equal(logs[k, 8:], log[8:])
+        assert torch.equal(a.groups, b.groups) and torch.equal(a.rew_weight, b.rew_weight)

@@ -88,6 +88,7 @@ lib.wl_startup.argtypes = [_vp, _vp]
 lib.wl_reset.argtypes = [_vp, _vp, _i32, _i64, _vp]
 lib.wl_step.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]
 lib.wl_observe.argtypes = [_vp, _vp, _i64, _i32, _vp]
+lib.wl_rollout.argtypes = [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]
 lib.wl_result_bytes.restype = _sz
 lib.wl_result_bytes.argtypes = [_i32]
 lib.wl_step_host.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]
@@ -106,7 +107,7 @@ lib.wl_test_philox.argtypes = [_u64, _u32, _u32, _u32, _u32, _vp, _i32, _vp]
 
 EXPORTED_SYMBOLS = [
     "wl_config_describe", "wl_config_sizeof", "wl_config_finalize", "wl_set_step_counter", "wl_state_bytes", "wl_globals_offset", "wl_create", "wl_destroy",
-    "wl_last_error", "wl_build_info", "wl_startup", "wl_reset", "wl_step", "wl_step_host", "wl_step_host_zero_copy", "wl_result_bytes", "wl_observe", "wl_curriculum",
+    "wl_last_error", "wl_build_info", "wl_startup", "wl_reset", "wl_step", "wl_step_host", "wl_step_host_zero_copy", "wl_rollout", "wl_result_bytes", "wl_observe", "wl_curriculum",
     "wl_synth_actions", "wl_derive_suspension", "wl_set_kernel_variant", "wl_set_scan_tma", "wl_obs_dim", "wl_launch_count", "wl_test_detmath", "wl_test_philox",
 ]
 

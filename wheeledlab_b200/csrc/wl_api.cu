@@ -53,7 +53,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 // Per-step episode log: warp-shuffle reduce over the finished envs, one atomic set per warp.
 // acc layout: [0..7] episode sums, [8] #reset, [9+j] #envs whose termination term j fired (tmask bit j).
-__device__ __forceinline__ bool log_accumulate(wl_globals* __restrict__ gl, bool contrib, uint32_t tmask,
+__device__ __forceinline__ bool log_accumulate(float* __restrict__ acc, bool contrib, uint32_t tmask,
                                                const float sums[WL_MAX_REW_TERMS]) {
     const unsigned any_c = __ballot_sync(0xffffffffu, contrib);
     if (!any_c) return false;
@@ -67,10 +67,20 @@ __device__ __forceinline__ bool log_accumulate(wl_globals* __restrict__ gl, bool
     for (int k = 0; k < 16; ++k) vals[k] = warp_sum(vals[k]);
     if ((threadIdx.x & 31) == 0) {
 #pragma unroll
-        for (int k = 0; k < 16; ++k) if (vals[k] != 0.0f) atomicAdd(&gl->acc[k], vals[k]);
+        for (int k = 0; k < 16; ++k) if (vals[k] != 0.0f) atomicAdd(&acc[k], vals[k]);
         __threadfence();          // order this warp's accumulation before its CTA's ticket (only warps that contributed pay)
     }
     return true;
+}
+// increase_reward_weight_over_time (curriculums.py:23-35) for the counter value `cn` reached by the step that just ended;
+// the reference calls it from _reset_idx, i.e. only on steps where >= 1 env reset.
+__device__ __forceinline__ void apply_curriculum(const wl_config& c, wl_globals* __restrict__ gl, uint32_t cn, bool any_reset) {
+    if (c.curr_n <= 0 || !any_reset || (cn % (uint32_t)c.max_episode_length) != 0u) return;
+    const int E = (int)(cn / (uint32_t)c.max_episode_length);
+    for (int k = 0; k < c.curr_n; ++k) {
+        if (E / c.curr_every[k] > c.curr_max[k]) continue;
+        if ((E + 1) % c.curr_every[k] == 0) gl->rew_weight[c.curr_slot[k]] += c.curr_inc[k];
+    }
 }
 // Last CTA of the launch turns the accumulators into the extras["log"] row and re-arms them.
 __device__ __forceinline__ void log_finalize(const wl_config& c, wl_globals* __restrict__ gl, float* __restrict__ d_log, uint32_t t) {
@@ -98,13 +108,7 @@ __device__ __forceinline__ void log_finalize(const wl_config& c, wl_globals* __r
     // reference calls it from _reset_idx, i.e. only on steps where >= 1 env reset)
     const uint32_t cn = t + 1u;
     gl->step_counter = cn;
-    if (c.curr_n > 0 && cnt > 0.0f && (cn % (uint32_t)c.max_episode_length) == 0u) {
-        const int E = (int)(cn / (uint32_t)c.max_episode_length);
-        for (int k = 0; k < c.curr_n; ++k) {
-            if (E / c.curr_every[k] > c.curr_max[k]) continue;
-            if ((E + 1) % c.curr_every[k] == 0) gl->rew_weight[c.curr_slot[k]] += c.curr_inc[k];
-        }
-    }
+    apply_curriculum(c, gl, cn, cnt > 0.0f);
 }
 
 // One thread per env.  TASK selects the MDP + terrain at compile time.
@@ -182,7 +186,7 @@ wl_step_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st, wl_
         done = tmask != 0u;
     }
     // F. auto-reset + per-step episode log (warp-shuffle reduction over the finished envs)
-    log_accumulate(gl, done, tmask, e.sums);
+    log_accumulate(gl->acc, done, tmask, e.sums);
     if (i < n) {
         const uint32_t gid = (uint32_t)(c.env_id_offset + i);
         if (done) {
@@ -210,27 +214,15 @@ wl_step_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st, wl_
 
 // Four lanes per env (lane = wheel).  Same arithmetic, same results; the per-wheel work runs in parallel and the
 // chassis is integrated redundantly in the 4 lanes.  Used when N is too small to fill the chip with one thread/env.
+// quad_env_step = sections A..I of ONE env.step() on register-resident state `e` (lane-local view, see load_env_quad).
 template <int TASK>
-__global__ void __launch_bounds__(128)
-wl_step_quad_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st, wl_globals* __restrict__ gl, Terrain T,
-                    const float2* __restrict__ action, float* __restrict__ obs, float* __restrict__ rew,
-                    uint8_t* __restrict__ terminated_o, uint8_t* __restrict__ truncated_o, float* __restrict__ d_log, uint32_t t_arg) {
+__device__ __forceinline__ void quad_env_step(const wl_config& c, const Terrain& T, const VisualMap& vm, float* __restrict__ acc_row,
+                                              const float wts[WL_MAX_REW_TERMS], EnvState& e, int i, int w, bool live, uint32_t gid,
+                                              unsigned base, uint32_t t, float2 a, float* __restrict__ obs_row,
+                                              float* __restrict__ rew, uint8_t* __restrict__ terminated_o,
+                                              uint8_t* __restrict__ truncated_o) {
     constexpr bool ELEV = (TASK == WL_TASK_ELEVATION), VIS = (TASK == WL_TASK_VISUAL);
-    const uint32_t t = (t_arg == 0xFFFFFFFFu) ? __ldcg(&gl->step_counter) : t_arg;
-    const VisualMap vm = VIS ? visual_map(c, T.hf) : VisualMap{nullptr, nullptr};
-    const int n = c.num_envs;
-    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
-    const int i = tid >> 2, w = tid & 3;
-    const bool live = i < n;                 // a whole quad is live or not (blockDim is a multiple of 4)
-    const int ii = live ? i : n - 1;         // dead quads shadow the last env (no stores) so shuffles stay convergent
-    const uint32_t gid = (uint32_t)(c.env_id_offset + ii);
-    const unsigned base = (threadIdx.x & 31u) & ~3u;
-    EnvState e;
-    const float4 rw0 = __ldg(reinterpret_cast<const float4*>(gl->rew_weight)), rw1 = __ldg(reinterpret_cast<const float4*>(gl->rew_weight) + 1);
-    const float wts[WL_MAX_REW_TERMS] = {rw0.x, rw0.y, rw0.z, rw0.w, rw1.x, rw1.y, rw1.z, rw1.w};
-    load_env_quad(st, n, ii, w, e, ELEV);
     // A. action manager (redundant in the 4 lanes)
-    float2 a = action[ii];
     e.prev_action[0] = e.action[0]; e.prev_action[1] = e.action[1];
     e.action[0] = a.x; e.action[1] = a.y;
     float wheel_target[4], steer_target[2];
@@ -285,7 +277,7 @@ wl_step_quad_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st
     const bool done = tmask != 0u;
     if (live && w == 0) { rew[i] = total; terminated_o[i] = (tmask & ~1u) ? 1 : 0; truncated_o[i] = (tmask & 1u) ? 1 : 0; }
     // F. per-step episode log: one contribution per env (lane 0 of each live quad), then auto-reset
-    log_accumulate(gl, done && live && (w == 0), tmask, e.sums);
+    log_accumulate(acc_row, done && live && (w == 0), tmask, e.sums);
     if (done) {
         if (ELEV) elev_reset_env(c, e, gid, t); else if (VIS) visual_reset_env(c, vm, e, gid, t); else drift_reset_env(c, e, gid, t);
     }
@@ -293,7 +285,7 @@ wl_step_quad_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st
     if (VIS) {      // 8 proprioceptive floats, no noise, no euler: lanes 0 and 1 write one float4 each
         float o[8]; visual_proprio(c, e, o);
         if (live && w < 2) {
-            float4* row = reinterpret_cast<float4*>(obs + (size_t)WL_OBS_DIM_VISUAL * i);
+            float4* row = reinterpret_cast<float4*>(obs_row);
             row[w] = (w == 0) ? make_float4(o[0], o[1], o[2], o[3]) : make_float4(o[4], o[5], o[6], o[7]);
         }
     } else
@@ -312,21 +304,103 @@ wl_step_quad_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st
             V3 eu{__shfl_sync(0xffffffffu, eu_k, base + 0), __shfl_sync(0xffffffffu, eu_k, base + 1), __shfl_sync(0xffffffffu, eu_k, base + 2)};
             float o[13]; elev_proprio(c, e, eu, o);
             if (live) {
-                float* row = obs + (size_t)WL_OBS_DIM_ELEV * i;
                 // lane w writes o[w], o[w+4], o[w+8] (and lane 0 also o[12]): 4-byte rows, scalar stores
                 const float v0 = (w == 0) ? o[0] : (w == 1) ? o[1] : (w == 2) ? o[2] : o[3];
                 const float v1 = (w == 0) ? o[4] : (w == 1) ? o[5] : (w == 2) ? o[6] : o[7];
                 const float v2 = (w == 0) ? o[8] : (w == 1) ? o[9] : (w == 2) ? o[10] : o[11];
-                row[w] = v0; row[w + 4] = v1; row[w + 8] = v2;
-                if (w == 0) row[12] = o[12];
+                obs_row[w] = v0; obs_row[w + 4] = v1; obs_row[w + 8] = v2;
+                if (w == 0) obs_row[12] = o[12];
             }
         } else {
             // blind_obs_quad shuffles: every lane of the warp calls it, dead quads only skip the stores
-            blind_obs_quad(c, e, w, eu_k, gid, t, RNG_OBS, 0u, obs + (size_t)WL_OBS_DIM_BLIND * ii, live);
+            blind_obs_quad(c, e, w, eu_k, gid, t, RNG_OBS, 0u, obs_row, live);
         }
     }
+}
+
+template <int TASK>
+__global__ void __launch_bounds__(128)
+wl_step_quad_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st, wl_globals* __restrict__ gl, Terrain T,
+                    const float2* __restrict__ action, float* __restrict__ obs, float* __restrict__ rew,
+                    uint8_t* __restrict__ terminated_o, uint8_t* __restrict__ truncated_o, float* __restrict__ d_log, uint32_t t_arg) {
+    constexpr bool ELEV = (TASK == WL_TASK_ELEVATION), VIS = (TASK == WL_TASK_VISUAL);
+    const uint32_t t = (t_arg == 0xFFFFFFFFu) ? __ldcg(&gl->step_counter) : t_arg;
+    const VisualMap vm = VIS ? visual_map(c, T.hf) : VisualMap{nullptr, nullptr};
+    const int n = c.num_envs;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = tid >> 2, w = tid & 3;
+    const bool live = i < n;                 // a whole quad is live or not (blockDim is a multiple of 4)
+    const int ii = live ? i : n - 1;         // dead quads shadow the last env (no stores) so shuffles stay convergent
+    const uint32_t gid = (uint32_t)(c.env_id_offset + ii);
+    const unsigned base = (threadIdx.x & 31u) & ~3u;
+    EnvState e;
+    const float4 rw0 = __ldg(reinterpret_cast<const float4*>(gl->rew_weight)), rw1 = __ldg(reinterpret_cast<const float4*>(gl->rew_weight) + 1);
+    const float wts[WL_MAX_REW_TERMS] = {rw0.x, rw0.y, rw0.z, rw0.w, rw1.x, rw1.y, rw1.z, rw1.w};
+    load_env_quad(st, n, ii, w, e, ELEV);
+    const int od = ELEV ? WL_OBS_DIM_ELEV : VIS ? WL_OBS_DIM_VISUAL : WL_OBS_DIM_BLIND;
+    quad_env_step<TASK>(c, T, vm, gl->acc, wts, e, i, w, live, gid, base, t, action[ii], obs + (size_t)od * ii, rew, terminated_o, truncated_o);
     if (live) store_env_quad(st, n, i, w, e, ELEV);
     log_finalize(c, gl, d_log, t);
+}
+
+// K consecutive env.step()s in ONE launch (synthetic / scripted-action rollouts): the state stays in registers
+// for the whole rollout, every step still writes its observation / reward / done rows ([K,N,...] slab) and its episode-log
+// row.  actions == nullptr => U[-1,1]^2 drawn in-kernel from the counter-based generator (and stored to act_out).
+// Bit-identical to K calls of wl_step.  The curriculum is applied by the host-side splitter: [t, t+K) never crosses an
+// episode boundary of the global counter when curr_n > 0.
+template <int TASK>
+__global__ void __launch_bounds__(128)
+wl_rollout_quad_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st, wl_globals* __restrict__ gl, Terrain T,
+                       const float2* __restrict__ action, float2* __restrict__ act_out, float* __restrict__ obs,
+                       float* __restrict__ rew, uint8_t* __restrict__ terminated_o, uint8_t* __restrict__ truncated_o,
+                       float* __restrict__ d_log, uint32_t t_arg, int K) {
+    constexpr bool ELEV = (TASK == WL_TASK_ELEVATION), VIS = (TASK == WL_TASK_VISUAL);
+    const uint32_t t0 = (t_arg == 0xFFFFFFFFu) ? __ldcg(&gl->step_counter) : t_arg;
+    const VisualMap vm = VIS ? visual_map(c, T.hf) : VisualMap{nullptr, nullptr};
+    const int n = c.num_envs;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = tid >> 2, w = tid & 3;
+    const bool live = i < n;
+    const int ii = live ? i : n - 1;
+    const uint32_t gid = (uint32_t)(c.env_id_offset + ii);
+    const unsigned base = (threadIdx.x & 31u) & ~3u;
+    EnvState e;
+    const float4 rw0 = __ldg(reinterpret_cast<const float4*>(gl->rew_weight)), rw1 = __ldg(reinterpret_cast<const float4*>(gl->rew_weight) + 1);
+    const float wts[WL_MAX_REW_TERMS] = {rw0.x, rw0.y, rw0.z, rw0.w, rw1.x, rw1.y, rw1.z, rw1.w};
+    load_env_quad(st, n, ii, w, e, ELEV);
+    const int od = ELEV ? WL_OBS_DIM_ELEV : VIS ? WL_OBS_DIM_VISUAL : WL_OBS_DIM_BLIND;
+    for (int k = 0; k < K; ++k) {
+        const uint32_t t = t0 + (uint32_t)k;
+        float2 a;
+        if (action != nullptr) a = action[(size_t)k * n + ii];
+        else {
+            uint4 r = philox4x32(c.seed, gid, t, RNG_ACTION, 0u);
+            a = make_float2(2.0f * u01(r.x) - 1.0f, 2.0f * u01(r.y) - 1.0f);
+        }
+        if (act_out != nullptr && live && w == 0) act_out[(size_t)k * n + i] = a;
+        quad_env_step<TASK>(c, T, vm, d_log + (size_t)k * WL_LOG_FLOATS, wts, e, i, w, live, gid, base, t, a,
+                            obs + ((size_t)k * n + ii) * od, rew + (size_t)k * n, terminated_o + (size_t)k * n,
+                            truncated_o + (size_t)k * n);
+    }
+    if (live) store_env_quad(st, n, i, w, e, ELEV);
+    // last CTA: turn the K accumulator rows into means, publish the counter / any-reset flag
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    const unsigned tk = atomicAdd(&gl->ticket, 1u);
+    if (tk != gridDim.x - 1) return;
+    __threadfence();
+    float last_cnt = 0.0f;
+    for (int k = 0; k < K; ++k) {
+        float* row = d_log + (size_t)k * WL_LOG_FLOATS;
+        const float cnt = __ldcg(&row[8]);
+        const float denom = r_max(cnt, 1.0f) * c.episode_length_s;
+        for (int q = 0; q < WL_MAX_REW_TERMS; ++q) row[q] = __ldcg(&row[q]) / denom;
+        last_cnt = cnt;
+    }
+    gl->any_reset_last = (last_cnt > 0.0f) ? 1 : 0;
+    gl->step_counter = t0 + (uint32_t)K;
+    gl->ticket = 0u;
+    apply_curriculum(c, gl, t0 + (uint32_t)K, last_cnt > 0.0f);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -783,6 +857,33 @@ int wl_step(wl_sim* sim, const float* d_action, float* d_obs, float* d_rew, uint
         return WL_OK;
     }
     WL_LAUNCH_CHECK(sim, "wl_step_kernel");
+    return WL_OK;
+}
+
+int wl_rollout(wl_sim* sim, int32_t K, const float* d_actions, float* d_actions_out, float* d_obs, float* d_rew,
+               uint8_t* d_terminated, uint8_t* d_truncated, float* d_log, int64_t step_counter, void* stream) {
+    if (!sim || !d_obs || !d_rew || !d_terminated || !d_truncated || !d_log) return fail(WL_EINVAL, "wl_rollout: null argument");
+    if (K < 1) return fail(WL_EINVAL, "wl_rollout: K must be >= 1");
+    if (sim->cfg.task == WL_TASK_ELEVATION) return fail(WL_EUNSUPPORTED, "wl_rollout: the elevation step is two kernels (use wl_step)");
+    if (sim->cfg.curr_n > 0) {
+        if (step_counter < 0) return fail(WL_EINVAL, "wl_rollout: with curriculum terms the host must pass the step counter");
+        const int64_t L = sim->cfg.max_episode_length;
+        // counters after steps 0..K-2 are t+1..t+K-1: none may be an episode boundary (only the last step may end on one)
+        if ((step_counter + K - 1) / L != step_counter / L)
+            return fail(WL_EINVAL, "wl_rollout: [t, t+K) must end at or before the next episode boundary of the global counter");
+    }
+    const int n = sim->cfg.num_envs;
+    Terrain T{sim->hf};
+    const int bs = 32, threads = 4 * n, grid = (threads + bs - 1) / bs;
+    cudaStream_t cs = (cudaStream_t)stream;
+    if (int rc = cuda_check(cudaMemsetAsync(d_log, 0, (size_t)K * WL_LOG_FLOATS * sizeof(float), cs), "wl_rollout: clear log rows")) return rc;
+    const float2* act = reinterpret_cast<const float2*>(d_actions);
+    float2* aout = reinterpret_cast<float2*>(d_actions_out);
+    if (sim->cfg.task == WL_TASK_VISUAL)
+        wl_rollout_quad_kernel<WL_TASK_VISUAL><<<grid, bs, 0, cs>>>(sim->cfg, sim->state, sim->globals, T, act, aout, d_obs, d_rew, d_terminated, d_truncated, d_log, (uint32_t)step_counter, K);
+    else
+        wl_rollout_quad_kernel<WL_TASK_DRIFT><<<grid, bs, 0, cs>>>(sim->cfg, sim->state, sim->globals, T, act, aout, d_obs, d_rew, d_terminated, d_truncated, d_log, (uint32_t)step_counter, K);
+    WL_LAUNCH_CHECK(sim, "wl_rollout_quad_kernel");
     return WL_OK;
 }
 

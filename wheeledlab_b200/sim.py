@@ -150,6 +150,16 @@ class WheeledSim:
                                C.c_void_p(h_obs.data_ptr()) if h_obs is not None else None, step_counter,
                                _stream_ptr(self.device)), "wl_step_host")
 
+    def rollout(self, K: int, step_counter: int, slab, logs: torch.Tensor, actions: torch.Tensor | None = None):
+        """K fused steps in ONE launch (wl_rollout): writes slab.obs/rewards/terminated/truncated[0:K] and logs[0:K];
+        `actions` [K,N,2] or None (in-kernel U[-1,1]^2, stored to slab.actions).  With curriculum terms the window must end
+        at or before the next episode boundary: use rollout_split() to cut a longer window."""
+        check(lib.wl_rollout(self._h, K, C.c_void_p(actions.data_ptr()) if actions is not None else None,
+                             C.c_void_p(slab.actions.data_ptr()) if actions is None else None,
+                             C.c_void_p(slab.obs.data_ptr()), C.c_void_p(slab.rewards.data_ptr()),
+                             C.c_void_p(slab.terminated.data_ptr()), C.c_void_p(slab.truncated.data_ptr()),
+                             C.c_void_p(logs.data_ptr()), step_counter, _stream_ptr(self.device)), "wl_rollout")
+
     def observe(self, step_counter: int, call_idx: int = 0, out: torch.Tensor | None = None):
         obs = out if out is not None else torch.empty((self.num_envs, self.obs_dim), dtype=torch.float32, device=self.device)
         check(lib.wl_observe(self._h, C.c_void_p(obs.data_ptr()), step_counter, call_idx, _stream_ptr(self.device)),
