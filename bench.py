@@ -324,6 +324,27 @@ def run_ours(args):
                "note": "rsl_rl-sized actor (14-64-64-2 ELU, torch/cuBLAS) + fused env step, 128 steps per CUDA-graph launch"}
     except Exception as ex:                                      # supplementary figure only
         pil = {"error": repr(ex)[:200]}
+    # ---- fused K-step synthetic rollout: K env.steps per launch, state in registers, in-kernel actions (supplementary) ----
+    fused = None
+    try:
+        KF = 125                                                  # divides the 250-step episode: windows end on curriculum boundaries
+        sim_f = wl.WheeledSim(wl.drift_task(num_envs=E, seed=args.seed, env_id_offset=rank * E), dev)
+        sim_f.startup(); sim_f.reset(None, 0)
+        slab_f = RolloutSlab(KF, E, sim_f.obs_dim, 2, dev)
+        logs_f = torch.empty((KF, 16), dtype=torch.float32, device=dev)
+        sim_f.rollout(KF, 0, slab_f, logs_f); barrier()
+        RF = 8
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for r in range(RF):
+            sim_f.rollout(KF, KF * (1 + r), slab_f, logs_f)
+        f1.record(); barrier()
+        f_ms = max_over_ranks(f0.elapsed_time(f1))
+        fused = {"value": E * world * KF * RF / (f_ms * 1e-3), "unit": UNIT, "ms_per_step": f_ms / (KF * RF), "K": KF,
+                 "note": "wl_rollout: K env.steps per launch, state in registers, in-kernel U[-1,1]^2 actions; every step still "
+                         "writes its obs/action/reward/done slab rows and episode-log row; bit-identical to K wl_step calls"}
+    except Exception as ex:
+        fused = {"error": repr(ex)[:200]}
     clocks = sampler.stop() if rank == 0 else None
 
     tot_ms, graph_ms, e2e_ms = max_over_ranks(tot_ms), max_over_ranks(graph_ms), max_over_ranks(e2e_ms)
@@ -361,6 +382,7 @@ def run_ours(args):
             "collective": {"kind": "all_gather_into_tensor(rollout slab)", "per_iteration_steps": T_ROLL,
                            "bytes_per_rank": slab.nbytes, "count": len(gev), "ms_total": gather_ms} if world > 1 else None,
             "policy_in_loop_graph": pil,
+            "rollout_fused": fused,
             "warm_l2_graph": {"value": total_envs * K / (graph_ms * 1e-3), "unit": UNIT, "ms_per_step": graph_ms / K,
                               "note": "K steps captured in one CUDA graph, state L2-resident (supplementary)"},
         }
