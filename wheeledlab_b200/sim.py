@@ -166,6 +166,21 @@ class WheeledSim:
               "wl_observe")
         return obs
 
+    def bind_step(self, action: torch.Tensor, out, log: torch.Tensor | None = None):
+        """Pre-resolve the pointers of one (action, outputs) set; returns f(step_counter) that enqueues the step with a
+        single ctypes call (used by tight host loops that reuse the same buffers, e.g. rollout slabs)."""
+        obs, rew, term, trunc = out
+        args = (self._h, C.c_void_p(action.data_ptr()), C.c_void_p(obs.data_ptr()), C.c_void_p(rew.data_ptr()),
+                C.c_void_p(term.data_ptr()), C.c_void_p(trunc.data_ptr()), C.c_void_p(log.data_ptr()) if log is not None else None)
+        keep = (action, obs, rew, term, trunc, log)
+        fn, dev = lib.wl_step, self.device
+
+        def run(step_counter: int, _keep=keep):
+            rc = fn(*args, step_counter, _stream_ptr(dev))
+            if rc:
+                check(rc, "wl_step")
+        return run
+
     def curriculum(self, slots, increases, fire_mask: int):
         n = len(slots)
         if n == 0 or fire_mask == 0:
