@@ -367,10 +367,10 @@ def run_ours(args):
                        "l2": "flushed between timed steps (256 MiB fill)", "parallelism": f"env-shard x{world}"},
             "clocks": clocks,
             "e2e": {"value": total_envs * K / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": E * 8,
-                    "d2h_bytes_per_step": E * 6 + 4, "ms_per_step": e2e_ms / K,
+                    "d2h_bytes_per_step": E * 6, "ms_per_step": e2e_ms / K,
                     "staged_copy_transport_ms_per_step": e2e_copy_ms / K,
                     "api": "ManagerBasedRLEnv.step_host(pinned actions) -> wl_step_host_zero_copy: the kernel reads the "
-                           "actions from / writes reward+dones+completion word to pinned host memory over PCIe; the host spins on that word, every step"},
+                           "actions from / writes reward+dones to pinned host memory over PCIe, then stream sync, every step"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of

@@ -356,8 +356,7 @@ int wl_rollout(wl_sim* sim, int32_t K, const float* d_actions, float* d_actions_
 /* env.step() for a HOST-side caller, host buffers in, host buffers out, one call:
  *   H2D  h_action[N,2] (pinned)  ->  d_action
  *   wl_step(...) writing d_obs, and reward / terminated / truncated into ONE device block d_result laid out as
- *        float rew[N] | uint8 terminated[N] | uint8 truncated[N] | pad to 16 B | uint32 completion word (+12 B)
- *        = wl_result_bytes(N) bytes
+ *        float rew[N] | uint8 terminated[N] | uint8 truncated[N]          (wl_result_bytes(N) bytes)
  *   D2H  d_result -> h_result (pinned, same layout), then cudaStreamSynchronize(stream).
  * Observations stay on the device (the policy lives there); pass h_obs != NULL to copy them back as well. */
 size_t wl_result_bytes(int32_t num_envs);
@@ -366,8 +365,7 @@ int wl_step_host(wl_sim* sim, const float* h_action, float* d_action, float* d_o
 /* Same contract, zero-copy transport: h_action / h_result must be PINNED host memory (cudaHostAlloc / torch
  * pin_memory: device-addressable under unified addressing).  The step kernel reads the actions from and writes
  * reward / terminated / truncated to host memory directly over PCIe -- no staging copies, no extra launches -- then
- * the last CTA publishes step_counter+1 in the block's completion word after a system-scope fence and the host spins on
- * it (no cudaStreamSynchronize round trip).  Bytes crossing the bus per step: wl_step_host's + 4. */
+ * the stream is synchronised.  Bytes crossing the bus per step are identical to wl_step_host. */
 int wl_step_host_zero_copy(wl_sim* sim, const float* h_action, float* d_obs, float* d_log, void* h_result,
                            int64_t step_counter, void* stream);
 /* observation_manager.compute(): re-samples the noise. call_idx distinguishes

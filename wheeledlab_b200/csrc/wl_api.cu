@@ -83,12 +83,7 @@ __device__ __forceinline__ void apply_curriculum(const wl_config& c, wl_globals*
     }
 }
 // Last CTA of the launch turns the accumulators into the extras["log"] row and re-arms them.
-// h_done (optional): pinned-host sequence word.  When the outputs live in host memory (zero-copy transport) every thread
-// fences its PCIe writes system-wide, and the last CTA publishes t+1 there: the host spins on that word instead of
-// paying a cudaStreamSynchronize round trip.
-__device__ __forceinline__ void log_finalize(const wl_config& c, wl_globals* __restrict__ gl, float* __restrict__ d_log, uint32_t t,
-                                             uint32_t* __restrict__ h_done) {
-    if (h_done != nullptr) __threadfence_system();
+__device__ __forceinline__ void log_finalize(const wl_config& c, wl_globals* __restrict__ gl, float* __restrict__ d_log, uint32_t t) {
     __syncthreads();              // all warps of the CTA are past their (fenced) accumulation
     if (threadIdx.x != 0) return;
     const unsigned tk = atomicAdd(&gl->ticket, 1u);
@@ -114,7 +109,6 @@ __device__ __forceinline__ void log_finalize(const wl_config& c, wl_globals* __r
     const uint32_t cn = t + 1u;
     gl->step_counter = cn;
     apply_curriculum(c, gl, cn, cnt > 0.0f);
-    if (h_done != nullptr) { __threadfence_system(); *reinterpret_cast<volatile uint32_t*>(h_done) = cn; }
 }
 
 // One thread per env.  TASK selects the MDP + terrain at compile time.
@@ -125,8 +119,7 @@ template <int TASK>
 __global__ void __launch_bounds__(128, WL_STEP_MIN_BLOCKS)
 wl_step_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st, wl_globals* __restrict__ gl, Terrain T,
                const float2* __restrict__ action, float* __restrict__ obs, float* __restrict__ rew,
-               uint8_t* __restrict__ terminated_o, uint8_t* __restrict__ truncated_o, float* __restrict__ d_log, uint32_t t_arg,
-               uint32_t* __restrict__ h_done) {
+               uint8_t* __restrict__ terminated_o, uint8_t* __restrict__ truncated_o, float* __restrict__ d_log, uint32_t t_arg) {
     constexpr bool ELEV = (TASK == WL_TASK_ELEVATION), VIS = (TASK == WL_TASK_VISUAL);
     const int n = c.num_envs;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -216,7 +209,7 @@ wl_step_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st, wl_
         }
         store_env(st, n, i, e, ELEV);
     }
-    log_finalize(c, gl, d_log, t, h_done);
+    log_finalize(c, gl, d_log, t);
 }
 
 // Four lanes per env (lane = wheel).  Same arithmetic, same results; the per-wheel work runs in parallel and the
@@ -329,8 +322,7 @@ template <int TASK>
 __global__ void __launch_bounds__(128)
 wl_step_quad_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st, wl_globals* __restrict__ gl, Terrain T,
                     const float2* __restrict__ action, float* __restrict__ obs, float* __restrict__ rew,
-                    uint8_t* __restrict__ terminated_o, uint8_t* __restrict__ truncated_o, float* __restrict__ d_log, uint32_t t_arg,
-                    uint32_t* __restrict__ h_done) {
+                    uint8_t* __restrict__ terminated_o, uint8_t* __restrict__ truncated_o, float* __restrict__ d_log, uint32_t t_arg) {
     constexpr bool ELEV = (TASK == WL_TASK_ELEVATION), VIS = (TASK == WL_TASK_VISUAL);
     const uint32_t t = (t_arg == 0xFFFFFFFFu) ? __ldcg(&gl->step_counter) : t_arg;
     const VisualMap vm = VIS ? visual_map(c, T.hf) : VisualMap{nullptr, nullptr};
@@ -348,7 +340,7 @@ wl_step_quad_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st
     const int od = ELEV ? WL_OBS_DIM_ELEV : VIS ? WL_OBS_DIM_VISUAL : WL_OBS_DIM_BLIND;
     quad_env_step<TASK>(c, T, vm, gl->acc, wts, e, i, w, live, gid, base, t, action[ii], obs + (size_t)od * ii, rew, terminated_o, truncated_o);
     if (live) store_env_quad(st, n, i, w, e, ELEV);
-    log_finalize(c, gl, d_log, t, h_done);
+    log_finalize(c, gl, d_log, t);
 }
 
 // K consecutive env.step()s in ONE launch (synthetic / scripted-action rollouts): the state stays in registers
@@ -837,18 +829,8 @@ int wl_reset(wl_sim* sim, const int64_t* d_env_ids, int32_t n_ids, int64_t step_
     return WL_OK;
 }
 
-static int step_impl(wl_sim* sim, const float* d_action, float* d_obs, float* d_rew, uint8_t* d_terminated, uint8_t* d_truncated,
-                     float* d_log, int64_t step_counter, void* stream, uint32_t* h_done);
-
 int wl_step(wl_sim* sim, const float* d_action, float* d_obs, float* d_rew, uint8_t* d_terminated, uint8_t* d_truncated,
             float* d_log, int64_t step_counter, void* stream) {
-    return step_impl(sim, d_action, d_obs, d_rew, d_terminated, d_truncated, d_log, step_counter, stream, nullptr);
-}
-
-}  // extern "C"
-
-static int step_impl(wl_sim* sim, const float* d_action, float* d_obs, float* d_rew, uint8_t* d_terminated, uint8_t* d_truncated,
-                     float* d_log, int64_t step_counter, void* stream, uint32_t* h_done) {
     if (!sim || !d_action || !d_obs || !d_rew || !d_terminated || !d_truncated) return fail(WL_EINVAL, "wl_step: null argument");
     if (((uintptr_t)d_action & 7u) || ((uintptr_t)d_obs & 7u)) return fail(WL_EINVAL, "wl_step: action/obs must be 8-byte aligned");
     const int n = sim->cfg.num_envs;
@@ -860,14 +842,14 @@ static int step_impl(wl_sim* sim, const float* d_action, float* d_obs, float* d_
     const bool elev = sim->cfg.task == WL_TASK_ELEVATION, vis = sim->cfg.task == WL_TASK_VISUAL;
     if (variant == 4) {
         const int bs = 32, threads = 4 * n, grid = (threads + bs - 1) / bs;
-        if (elev) wl_step_quad_kernel<WL_TASK_ELEVATION><<<grid, bs, 0, cs>>>(sim->cfg, sim->state, sim->globals, T, act, d_obs, d_rew, d_terminated, d_truncated, d_log, t, h_done);
-        else if (vis) wl_step_quad_kernel<WL_TASK_VISUAL><<<grid, bs, 0, cs>>>(sim->cfg, sim->state, sim->globals, T, act, d_obs, d_rew, d_terminated, d_truncated, d_log, t, h_done);
-        else wl_step_quad_kernel<WL_TASK_DRIFT><<<grid, bs, 0, cs>>>(sim->cfg, sim->state, sim->globals, T, act, d_obs, d_rew, d_terminated, d_truncated, d_log, t, h_done);
+        if (elev) wl_step_quad_kernel<WL_TASK_ELEVATION><<<grid, bs, 0, cs>>>(sim->cfg, sim->state, sim->globals, T, act, d_obs, d_rew, d_terminated, d_truncated, d_log, t);
+        else if (vis) wl_step_quad_kernel<WL_TASK_VISUAL><<<grid, bs, 0, cs>>>(sim->cfg, sim->state, sim->globals, T, act, d_obs, d_rew, d_terminated, d_truncated, d_log, t);
+        else wl_step_quad_kernel<WL_TASK_DRIFT><<<grid, bs, 0, cs>>>(sim->cfg, sim->state, sim->globals, T, act, d_obs, d_rew, d_terminated, d_truncated, d_log, t);
     } else {
         const int bs = pick_block(n), grid = (n + bs - 1) / bs;
-        if (elev) wl_step_kernel<WL_TASK_ELEVATION><<<grid, bs, 0, cs>>>(sim->cfg, sim->state, sim->globals, T, act, d_obs, d_rew, d_terminated, d_truncated, d_log, t, h_done);
-        else if (vis) wl_step_kernel<WL_TASK_VISUAL><<<grid, bs, 0, cs>>>(sim->cfg, sim->state, sim->globals, T, act, d_obs, d_rew, d_terminated, d_truncated, d_log, t, h_done);
-        else wl_step_kernel<WL_TASK_DRIFT><<<grid, bs, 0, cs>>>(sim->cfg, sim->state, sim->globals, T, act, d_obs, d_rew, d_terminated, d_truncated, d_log, t, h_done);
+        if (elev) wl_step_kernel<WL_TASK_ELEVATION><<<grid, bs, 0, cs>>>(sim->cfg, sim->state, sim->globals, T, act, d_obs, d_rew, d_terminated, d_truncated, d_log, t);
+        else if (vis) wl_step_kernel<WL_TASK_VISUAL><<<grid, bs, 0, cs>>>(sim->cfg, sim->state, sim->globals, T, act, d_obs, d_rew, d_terminated, d_truncated, d_log, t);
+        else wl_step_kernel<WL_TASK_DRIFT><<<grid, bs, 0, cs>>>(sim->cfg, sim->state, sim->globals, T, act, d_obs, d_rew, d_terminated, d_truncated, d_log, t);
     }
     if (elev) {
         WL_LAUNCH_CHECK(sim, "wl_step_kernel");
@@ -877,8 +859,6 @@ static int step_impl(wl_sim* sim, const float* d_action, float* d_obs, float* d_
     WL_LAUNCH_CHECK(sim, "wl_step_kernel");
     return WL_OK;
 }
-
-extern "C" {
 
 int wl_rollout(wl_sim* sim, int32_t K, const float* d_actions, float* d_actions_out, float* d_obs, float* d_rew,
                uint8_t* d_terminated, uint8_t* d_truncated, float* d_log, int64_t step_counter, void* stream) {
@@ -907,7 +887,7 @@ int wl_rollout(wl_sim* sim, int32_t K, const float* d_actions, float* d_actions_
     return WL_OK;
 }
 
-size_t wl_result_bytes(int32_t num_envs) { return (((size_t)num_envs * 6u + 15u) & ~(size_t)15u) + 16u; }
+size_t wl_result_bytes(int32_t num_envs) { return (size_t)num_envs * 6u; }
 
 int wl_step_host(wl_sim* sim, const float* h_action, float* d_action, float* d_obs, void* d_result, float* d_log,
                  void* h_result, float* h_obs, int64_t step_counter, void* stream) {
@@ -929,7 +909,6 @@ int wl_step_host(wl_sim* sim, const float* h_action, float* d_action, float* d_o
 int wl_step_host_zero_copy(wl_sim* sim, const float* h_action, float* d_obs, float* d_log, void* h_result,
                            int64_t step_counter, void* stream) {
     if (!sim || !h_action || !d_obs || !h_result) return fail(WL_EINVAL, "wl_step_host_zero_copy: null argument");
-    if (step_counter < 0) return fail(WL_EINVAL, "wl_step_host_zero_copy: needs the host step counter (completion sequence word)");
     const size_t n = (size_t)sim->cfg.num_envs;
     const float* da = nullptr; void* dr = nullptr;
     if (cudaHostGetDevicePointer((void**)&da, (void*)h_action, 0) != cudaSuccess || cudaHostGetDevicePointer(&dr, h_result, 0) != cudaSuccess) {
@@ -939,29 +918,8 @@ int wl_step_host_zero_copy(wl_sim* sim, const float* h_action, float* d_obs, flo
     float* d_rew = reinterpret_cast<float*>(dr);
     uint8_t* d_term = reinterpret_cast<uint8_t*>(dr) + n * 4;
     uint8_t* d_trunc = d_term + n;
-    const size_t flag_off = (n * 6u + 15u) & ~(size_t)15u;       // completion word after the result block
-    uint32_t* d_done = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(dr) + flag_off);
-    volatile uint32_t* h_done = reinterpret_cast<volatile uint32_t*>(reinterpret_cast<char*>(h_result) + flag_off);
-    const uint32_t expect = (uint32_t)step_counter + 1u;
-    *h_done = expect - 1u;
-    if (sim->cfg.task == WL_TASK_ELEVATION) {                     // two kernels: the scan is last -> plain stream sync
-        if (int rc = step_impl(sim, da, d_obs, d_rew, d_term, d_trunc, d_log, step_counter, stream, nullptr)) return rc;
-        return cuda_check(cudaStreamSynchronize((cudaStream_t)stream), "wl_step_host_zero_copy: stream synchronize");
-    }
-    if (int rc = step_impl(sim, da, d_obs, d_rew, d_term, d_trunc, d_log, step_counter, stream, d_done)) return rc;
-    // the kernel's last CTA publishes `expect` after a system-scope fence: spin on the host word (no driver round trip)
-    for (uint64_t spins = 0;; ++spins) {
-        if (*h_done == expect) break;
-        if ((spins & 0xFFFFu) == 0xFFFFu) {                       // every 65k polls: make sure the stream is still healthy
-            cudaError_t q = cudaStreamQuery((cudaStream_t)stream);
-            if (q == cudaSuccess) { if (*h_done == expect) break; return fail(WL_ECUDA, "wl_step_host_zero_copy: kernel finished without publishing completion"); }
-            if (q != cudaErrorNotReady) return cuda_check(q, "wl_step_host_zero_copy");
-        }
-#if defined(__x86_64__)
-        __builtin_ia32_pause();
-#endif
-    }
-    return WL_OK;
+    if (int rc = wl_step(sim, da, d_obs, d_rew, d_term, d_trunc, d_log, step_counter, stream)) return rc;
+    return cuda_check(cudaStreamSynchronize((cudaStream_t)stream), "wl_step_host_zero_copy: stream synchronize");
 }
 
 int wl_observe(wl_sim* sim, float* d_obs, int64_t step_counter, int32_t call_idx, void* stream) {
