@@ -471,10 +471,7 @@ wl_scan_kernel(const __grid_constant__ wl_config c, const __grid_constant__ CUte
     const int rx = threadIdx.x & 31, wrp = threadIdx.x >> 5;
     if (rx < WL_SCAN_SIDE) {
         const float lx = fm((float)rx, c.scan_res, -c.scan_half);
-        const float wx0 = fm(cy, lx, bx), wy0 = fm(sy, lx, by);      // + (-sy, cy) * ly below
         const float fxmax = (float)(c.hf_nx - 1), fymax = (float)(c.hf_ny - 1);
-        const float zoff = c.scan_offset - bz + (e.p.z - c.scan_plane_init);
-        (void)zoff;
         for (int ry = wrp; ry < WL_SCAN_SIDE; ry += WL_SCAN_THREADS / 32) {
             const float ly = fm((float)ry, c.scan_res, -c.scan_half);
             const float wx = fm(cy, lx, fm(-sy, ly, bx)), wy = fm(sy, lx, fm(cy, ly, by));
@@ -494,7 +491,6 @@ wl_scan_kernel(const __grid_constant__ wl_config c, const __grid_constant__ CUte
             }
             row[ry * WL_SCAN_SIDE + rx] = v;
         }
-        (void)wx0; (void)wy0;
     }
 }
 

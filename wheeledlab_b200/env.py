@@ -256,8 +256,6 @@ class ManagerBasedRLEnv:
         self.action_space = _Box(-math.inf, math.inf, (self.num_envs, self.spec.action_dim))
         self.single_observation_space = {"policy": _Box(-math.inf, math.inf, (self.spec.obs_dim,))}
         self.observation_space = {"policy": _Box(-math.inf, math.inf, (self.num_envs, self.spec.obs_dim))}
-        self._curr_slots = [self.reward_manager._slot(t.reward_term_name) for t in self.spec.curriculum]
-        self._curr_inc = [float(t.increase) for t in self.spec.curriculum]
         self.log_episode_info = True
         self._log_index = {"Episode_Reward/" + n: k for k, n in enumerate(self.spec.reward_names)}
         self._log_index.update({"Episode_Termination/" + n: 9 + j for j, (n, _) in enumerate(self.spec.termination_names)})
