@@ -210,3 +210,24 @@ def test_curriculum_counter_semantics():
     assert 20 not in fired and 1 not in fired
     # max_increases: term1 (5) stops once E//20 > 5 i.e. E >= 120 -> E=119: 119//20=5 not > 5 -> still fires
     assert fired[119] & 0b010
+
+
+def test_reference_terrain_raster_spot_heights():
+    """The shipped raster of Terrains/huge_compact.usd reproduces the top-surface heights SURVEY 8c decoded independently."""
+    from wheeledlab_b200.terrain import reference_heightfield
+    H, x0, y0, cell = reference_heightfield()
+    assert H.shape == (411, 411) and (x0, y0) == (-20.5, -20.5) and abs(cell - 0.1) < 1e-9
+    at = lambda x, y: H[int(round((y - y0) / cell)), int(round((x - x0) / cell))]
+    for x, y, z in [(0, 0, 0.2), (-2, 1, 0.2), (5.3, -7.7, 0.38109), (-12.2, 3.3, 0.47669), (19.9, 19.9, 0.2)]:
+        assert abs(at(x, y) - z) < 1e-5, (x, y, at(x, y))
+    assert H.max() == np.float32(2.0) and H[H > 0].min() == np.float32(0.2) and (H == 0).sum() == 100
+
+
+def test_elevation_oracle_on_reference_terrain():
+    import wheeledlab_b200 as wl
+    spec = wl.elevation_task(num_envs=48, seed=3)
+    o = O.Oracle(spec.cfg, heightfield=spec.heightfield); o.startup(); o.reset(None, 0)
+    for t in range(150):
+        obs, rew, term, trunc = o.step(o.synth_actions(t), t)
+        assert np.isfinite(obs).all() and np.isfinite(rew).all() and obs[:, 13:].max() <= 10 and obs[:, 13:].min() >= -10
+    assert obs.shape == (48, 689)

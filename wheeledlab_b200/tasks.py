@@ -282,10 +282,11 @@ def drift_task(num_envs: int = 1024, seed: int = 42, env_id_offset: int = 0, ran
 
 
 def elevation_task(num_envs: int = 1024, seed: int = 42, env_id_offset: int = 0, heightfield=None, hf_origin=None,
-                   hf_cell: float = 0.1) -> TaskSpec:
+                   hf_cell: float = 0.1, terrain: str = "reference") -> TaskSpec:
     """MushrElevationRLEnvCfg (elevation/mushr_elevation_env_cfg.py:437-469).  ``heightfield``: float32 [ny, nx]
-    raster of the terrain top surface (default: terrain.procedural_heightfield(seed))."""
-    from .terrain import pad_pitch, procedural_heightfield
+    raster of the terrain top surface; default = the raster of the reference's own Terrains/huge_compact.usd
+    (terrain="reference"), or a synthetic terrain with the same envelope (terrain="procedural")."""
+    from .terrain import pad_pitch, procedural_heightfield, reference_heightfield
     cfg = WlConfig()
     cfg.abi_version = WL_ABI_VERSION
     cfg.task = TASK_ELEVATION
@@ -314,7 +315,7 @@ def elevation_task(num_envs: int = 1024, seed: int = 42, env_id_offset: int = 0,
     cfg.num_ref_poses = 1
     # height-field
     if heightfield is None:
-        heightfield, x0, y0, hf_cell = procedural_heightfield(seed)
+        heightfield, x0, y0, hf_cell = reference_heightfield() if terrain == "reference" else procedural_heightfield(seed)
     else:
         x0, y0 = hf_origin
     heightfield = np.ascontiguousarray(heightfield, dtype=np.float32)

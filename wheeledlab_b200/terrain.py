@@ -16,6 +16,16 @@ import math
 import numpy as np
 
 
+def reference_heightfield():
+    """Raster of the reference's own terrain mesh (Terrains/huge_compact.usd, top surface, 0.1 m, 411x411), produced by
+    tools/rasterize_terrain.py from the binary USD (pure-Python USDC reader in tools/usdc_read.py) and shipped as a 58 KB
+    data file.  Returns (heights [ny, nx] float32, x0, y0, cell).  Spot heights match SURVEY 8c:
+    z(0,0)=0.2, z(5.3,-7.7)=0.38109, z(-12.2,3.3)=0.47669; the four 0.5 m corners are outside the mesh (0 = ground plane)."""
+    from pathlib import Path
+    d = np.load(Path(__file__).resolve().parent / "data" / "terrain_huge_compact_0p1m.npz")
+    return d["heights"].astype(np.float32), float(d["x0"]), float(d["y0"]), float(d["cell"])
+
+
 def pad_pitch(h: np.ndarray) -> np.ndarray:
     ny, nx = h.shape
     pitch = (nx + 3) & ~3
