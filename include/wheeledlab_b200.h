@@ -391,6 +391,16 @@ int32_t wl_obs_dim(const wl_sim* sim);
 /* number of kernel launches issued through this handle since creation */
 int64_t wl_launch_count(const wl_sim* sim);
 
+/* ---- the step after the rollout: returns / advantages over the [T, N] slab ---------------------------
+ * rsl_rl RolloutStorage.compute_returns as called at modified_rsl_rl_runner.py:116 [UPSTREAM-RECALL], with the time-out
+ * bootstrap of PPO.process_env_step (rewards += gamma * values * time_outs) folded in when d_time_outs != NULL:
+ *   delta_t = r_t + (1 - done_t) * gamma * V_{t+1} - V_t ;  A_t = delta_t + (1 - done_t) * gamma * lam * A_{t+1}
+ *   returns_t = A_t + V_t ; advantages_t = A_t          (V_T = d_last_values; no normalisation here)
+ * All arrays are [T, N] row-major (env fastest), exactly the rollout-slab layout; one thread per env walks t = T-1..0. */
+int wl_gae(const float* d_rewards, const float* d_values, const float* d_last_values, const uint8_t* d_dones,
+           const uint8_t* d_time_outs, float gamma, float lam, float* d_returns, float* d_advantages, int32_t T,
+           int32_t N, void* stream);
+
 /* ---- test hooks (bit-exactness of the deterministic math vs the oracle) ------ */
 /* op: 0 sin,1 cos,2 atan,3 atan2(x=in,y=in2),4 log,5 tan,6 asin ; out[n] */
 int wl_test_detmath(int32_t op, const float* d_in, const float* d_in2, float* d_out, int32_t n,

@@ -483,3 +483,25 @@ def test_fused_k_step_rollout_equals_k_single_steps():
             if t0 != 200:
                 assert torch.allclose(logs[k], log, rtol=1e-5, atol=1e-4) and torch.equal(logs[k, 8:], log[8:])
         assert torch.equal(a.groups, b.groups) and torch.equal(a.rew_weight, b.rew_weight)
+
+
+def test_gae_matches_rsl_rl_formula():
+    """wl_gae vs a torch fp32 restatement of rsl_rl's compute_returns (+ time-out bootstrap), tolerance 1e-5."""
+    _need_gpu()
+    from wheeledlab_b200.learner import compute_returns
+    torch.manual_seed(0)
+    for T, N in ((128, 4096), (5, 33), (1, 1)):
+        rew = torch.randn(T, N, device="cuda"); val = torch.randn(T, N, device="cuda"); last = torch.randn(N, device="cuda")
+        done = torch.rand(T, N, device="cuda") < 0.05
+        tout = done & (torch.rand(T, N, device="cuda") < 0.5)
+        gamma, lam = 0.99, 0.95
+        ret, adv = compute_returns(rew, val, last, done, gamma, lam, time_outs=tout)
+        r2 = rew + gamma * val * tout.float()
+        a = torch.zeros(N, device="cuda"); exp_ret = torch.empty_like(rew)
+        for t in reversed(range(T)):
+            nv = last if t == T - 1 else val[t + 1]
+            nt = 1.0 - done[t].float()
+            delta = r2[t] + nt * gamma * nv - val[t]
+            a = delta + nt * gamma * lam * a
+            exp_ret[t] = a + val[t]
+        assert torch.allclose(ret, exp_ret, rtol=1e-5, atol=1e-5) and torch.allclose(adv, exp_ret - val, rtol=1e-5, atol=1e-5)

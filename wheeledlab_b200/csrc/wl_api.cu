@@ -623,6 +623,43 @@ __global__ void wl_synth_actions_kernel(const __grid_constant__ wl_config c, con
     action[i] = make_float2(a0, a1);
 }
 
+// GAE(lambda) over the rollout slab: one thread per env, t = T-1 .. 0; loads are issued WL_GAE_CHUNK steps ahead so the
+// reverse scan is bandwidth- rather than latency-bound (17 B read + 8 B written per (t, env)).
+#define WL_GAE_CHUNK 8
+__global__ void __launch_bounds__(128)
+wl_gae_kernel(const float* __restrict__ rew, const float* __restrict__ val, const float* __restrict__ last_val,
+              const uint8_t* __restrict__ done, const uint8_t* __restrict__ tout, float gamma, float lam,
+              float* __restrict__ ret, float* __restrict__ adv, int T, int N) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    float next_v = last_val[i], a = 0.0f;
+    for (int t1 = T; t1 > 0; t1 -= WL_GAE_CHUNK) {
+        const int t0 = (t1 - WL_GAE_CHUNK > 0) ? t1 - WL_GAE_CHUNK : 0;
+        float r[WL_GAE_CHUNK], v[WL_GAE_CHUNK]; uint8_t d[WL_GAE_CHUNK], to[WL_GAE_CHUNK];
+#pragma unroll
+        for (int k = 0; k < WL_GAE_CHUNK; ++k) {
+            const int t = t1 - 1 - k;
+            if (t >= t0) {
+                const size_t o = (size_t)t * N + i;
+                r[k] = rew[o]; v[k] = val[o]; d[k] = done[o]; to[k] = tout ? tout[o] : (uint8_t)0;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < WL_GAE_CHUNK; ++k) {
+            const int t = t1 - 1 - k;
+            if (t >= t0) {
+                const float nt = d[k] ? 0.0f : 1.0f;
+                const float rr = to[k] ? r[k] + gamma * v[k] : r[k];           // time-out bootstrap
+                const float delta = rr + nt * gamma * next_v - v[k];
+                a = delta + nt * gamma * lam * a;
+                const size_t o = (size_t)t * N + i;
+                ret[o] = a + v[k]; adv[o] = a;
+                next_v = v[k];
+            }
+        }
+    }
+}
+
 __global__ void wl_detmath_kernel(int op, const float* __restrict__ in, const float* __restrict__ in2, float* __restrict__ out, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -964,6 +1001,16 @@ int wl_derive_suspension(wl_sim* sim, float* d_susp_pos, float* d_susp_vel, void
         wl_suspension_kernel<WL_TASK_DRIFT><<<(n + bs - 1) / bs, bs, 0, (cudaStream_t)stream>>>(sim->cfg, sim->state, T, (float4*)d_susp_pos, (float4*)d_susp_vel);
     WL_LAUNCH_CHECK(sim, "wl_suspension_kernel");
     return WL_OK;
+}
+
+int wl_gae(const float* d_rewards, const float* d_values, const float* d_last_values, const uint8_t* d_dones,
+           const uint8_t* d_time_outs, float gamma, float lam, float* d_returns, float* d_advantages, int32_t T, int32_t N,
+           void* stream) {
+    if (!d_rewards || !d_values || !d_last_values || !d_dones || !d_returns || !d_advantages) return fail(WL_EINVAL, "wl_gae: null argument");
+    if (T < 1 || N < 1) return fail(WL_EINVAL, "wl_gae: T and N must be >= 1");
+    wl_gae_kernel<<<(N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(d_rewards, d_values, d_last_values, d_dones, d_time_outs, gamma,
+                                                                     lam, d_returns, d_advantages, T, N);
+    return cuda_check(cudaGetLastError(), "wl_gae_kernel");
 }
 
 int wl_test_detmath(int32_t op, const float* d_in, const float* d_in2, float* d_out, int32_t n, void* stream) {
