@@ -326,6 +326,30 @@ def run_ours(args):
                "note": "rsl_rl-sized actor (14-64-64-2 ELU, torch/cuBLAS) + fused env step, 128 steps per CUDA-graph launch"}
     except Exception as ex:                                      # supplementary figure only
         pil = {"error": repr(ex)[:200]}
+    # ---- actor + critic + Gaussian sampling FUSED into the step kernel (wl_act_step), 128 launches per graph (supplementary) ----
+    pfu = None
+    try:
+        from wheeledlab_b200.policy import FusedPolicyRollout, pack_actor_critic
+        torch.manual_seed(0)
+        mk = lambda out: torch.nn.Sequential(torch.nn.Linear(sim.obs_dim, 64), torch.nn.ELU(), torch.nn.Linear(64, 64), torch.nn.ELU(),
+                                             torch.nn.Linear(64, out)).to(dev)
+        blob = pack_actor_critic(mk(2), mk(1), torch.ones(2), sim.obs_dim, dev)
+        sim_q = wl.WheeledSim(wl.drift_task(num_envs=E, seed=args.seed, env_id_offset=rank * E), dev)
+        sim_q.startup(); sim_q.reset(None, 0)
+        froll = FusedPolicyRollout(sim_q, blob, T_ROLL).capture(0)
+        froll.run(); barrier()
+        R = 4
+        q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        q0.record()
+        for _ in range(R):
+            froll.run()
+        q1.record(); barrier()
+        pfu_ms = max_over_ranks(q0.elapsed_time(q1)) if world > 1 else q0.elapsed_time(q1)
+        pfu = {"value": E * world * T_ROLL * R / (pfu_ms * 1e-3), "unit": UNIT, "ms_per_step": pfu_ms / (T_ROLL * R),
+               "note": "rsl_rl actor AND critic (14-64-64-2/1 ELU), Gaussian sample + log-prob, and the env step in ONE kernel; "
+                       "128 launches per CUDA graph"}
+    except Exception as ex:                                      # supplementary figure only
+        pfu = {"error": repr(ex)[:200]}
     # ---- fused K-step synthetic rollout: K env.steps per launch, state in registers, in-kernel actions (supplementary) ----
     fused = None
     try:
@@ -384,6 +408,7 @@ def run_ours(args):
             "collective": {"kind": "all_gather_into_tensor(rollout slab)", "per_iteration_steps": T_ROLL,
                            "bytes_per_rank": slab.nbytes, "count": len(gev), "ms_total": gather_ms} if world > 1 else None,
             "policy_in_loop_graph": pil,
+            "policy_fused_in_step": pfu,
             "rollout_fused": fused,
             "warm_l2_graph": {"value": total_envs * K / (graph_ms * 1e-3), "unit": UNIT, "ms_per_step": graph_ms / K,
                               "note": "K steps captured in one CUDA graph, state L2-resident (supplementary)"},

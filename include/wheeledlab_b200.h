@@ -391,6 +391,25 @@ int32_t wl_obs_dim(const wl_sim* sim);
 /* number of kernel launches issued through this handle since creation */
 int64_t wl_launch_count(const wl_sim* sim);
 
+/* ---- the step before env.step(): the policy ---------------------------------------------------------
+ * alg.act(obs) of the rollout loop (modified_rsl_rl_runner.py:72; rsl_rl ActorCritic with the reference's sizes,
+ * drifting/config/agents/mushr/rsl_rl_ppo_cfg.py:12-17: actor and critic 64x64 ELU MLPs, Gaussian head with a learned
+ * std) FUSED in front of the env step: one launch = value + action mean + sampled action + log-prob + the whole step.
+ * Weights are a caller-owned device blob of fp32 in INPUT-MAJOR (transposed) layout, per net:
+ *     W1t[obs_dim][64] b1[64]  W2t[64][64] b2[64]  W3t[64][out] b3[out]        (actor: out = 2, critic: out = 1)
+ * blob = actor net | critic net | std[2]; every block starts 16-byte aligned (wl_policy_blob_floats gives offsets).
+ * a = mean + std * z, z ~ N(0,1) from the counter-based generator (stream 9, keyed by global env id and step). */
+typedef struct wl_policy_out {
+    float* actions;      /* [N,2] sampled actions (also what the env step consumes) */
+    float* mean;         /* [N,2] */
+    float* log_prob;     /* [N]   sum over action dims */
+    float* value;        /* [N]   */
+} wl_policy_out;
+/* offsets (in floats) of the 13 arrays inside the blob for observation width obs_dim; returns the total float count */
+int32_t wl_policy_blob_floats(int32_t obs_dim, int32_t offsets[13]);
+int wl_act_step(wl_sim* sim, const float* d_obs_in, const float* d_policy_blob, wl_policy_out out, float* d_obs,
+                float* d_rew, uint8_t* d_terminated, uint8_t* d_truncated, float* d_log, int64_t step_counter, void* stream);
+
 /* ---- the step after the rollout: returns / advantages over the [T, N] slab ---------------------------
  * rsl_rl RolloutStorage.compute_returns as called at modified_rsl_rl_runner.py:116 [UPSTREAM-RECALL], with the time-out
  * bootstrap of PPO.process_env_step (rewards += gamma * values * time_outs) folded in when d_time_outs != NULL:

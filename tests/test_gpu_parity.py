@@ -505,3 +505,73 @@ def test_gae_matches_rsl_rl_formula():
             a = delta + nt * gamma * lam * a
             exp_ret[t] = a + val[t]
         assert torch.allclose(ret, exp_ret, rtol=1e-5, atol=1e-5) and torch.allclose(adv, exp_ret - val, rtol=1e-5, atol=1e-5)
+
+
+def _actor_critic(seed=0):
+    torch.manual_seed(seed)
+    mk = lambda out: torch.nn.Sequential(torch.nn.Linear(14, 64), torch.nn.ELU(), torch.nn.Linear(64, 64), torch.nn.ELU(), torch.nn.Linear(64, out)).cuda()
+    return mk(2), mk(1), torch.tensor([0.7, 1.3], device="cuda")
+
+
+def test_fused_actor_critic_step_matches_torch_policy_and_plain_step():
+    """wl_act_step = rsl_rl ActorCritic.act/evaluate (64x64 ELU MLPs, Gaussian head) + env.step in ONE launch.
+    Policy outputs vs a torch fp32 restatement (tolerance: fp32 accumulation order, 2e-5); the env side must be
+    BIT-identical to wl_step fed the same sampled actions."""
+    _need_gpu()
+    import wheeledlab_b200 as wl
+    from wheeledlab_b200.policy import act_step, pack_actor_critic
+    n = 1531
+    actor, critic, std = _actor_critic()
+    a = wl.WheeledSim(wl.drift_task(num_envs=n, seed=21), "cuda:0"); b = wl.WheeledSim(wl.drift_task(num_envs=n, seed=21), "cuda:0")
+    for s_ in (a, b):
+        s_.startup(); s_.reset(None, 0)
+    blob = pack_actor_critic(actor, critic, std, 14, "cuda:0")
+    obs = a.observe(0, 0)
+    dev = "cuda"
+    act = torch.empty((n, 2), device=dev); mean = torch.empty((n, 2), device=dev); lp = torch.empty(n, device=dev); val = torch.empty(n, device=dev)
+    zs = []
+    with torch.no_grad():
+        for t in range(40):
+            out = tuple(torch.empty_like(x) for x in (obs, lp, torch.empty(n, dtype=torch.uint8, device=dev), torch.empty(n, dtype=torch.uint8, device=dev)))
+            act_step(b, obs, blob, act, mean, lp, val, out, None, t)
+            m_ref, v_ref = actor(obs), critic(obs).squeeze(-1)
+            assert torch.allclose(mean, m_ref, rtol=2e-5, atol=2e-5), (t, (mean - m_ref).abs().max())
+            assert torch.allclose(val, v_ref, rtol=2e-5, atol=2e-5), (t, (val - v_ref).abs().max())
+            lp_ref = torch.distributions.Normal(mean, std).log_prob(act).sum(-1)
+            assert torch.allclose(lp, lp_ref, rtol=1e-4, atol=1e-4), (t, (lp - lp_ref).abs().max())
+            zs.append(((act - mean) / std).flatten())
+            ref = a.step(act.clone(), t)
+            for x, y in zip(out, ref):
+                assert torch.equal(x, y), t
+            obs = ref[0]
+    assert torch.equal(a.groups, b.groups)
+    z = torch.cat(zs)
+    assert abs(z.mean().item()) < 0.02 and abs(z.var().item() - 1.0) < 0.03          # N(0,1) samples, 122k draws
+
+
+def test_fused_policy_rollout_graph_equals_eager_act_steps():
+    _need_gpu()
+    import wheeledlab_b200 as wl
+    from wheeledlab_b200.policy import FusedPolicyRollout, act_step, pack_actor_critic
+    n, T = 777, 32
+    actor, critic, std = _actor_critic(3)
+    a = wl.WheeledSim(wl.drift_task(num_envs=n, seed=5), "cuda:0"); b = wl.WheeledSim(wl.drift_task(num_envs=n, seed=5), "cuda:0")
+    for s_ in (a, b):
+        s_.startup(); s_.reset(None, 0)
+    blob = pack_actor_critic(actor, critic, std, 14, "cuda:0")
+    roll = FusedPolicyRollout(b, blob, T).capture(0)
+    dev = "cuda"
+    obs = a.observe(0, 0)
+    act = torch.empty((n, 2), device=dev); mean = torch.empty((n, 2), device=dev); lp = torch.empty(n, device=dev); val = torch.empty(n, device=dev)
+    for it in range(3):
+        slab = roll.run(); torch.cuda.synchronize()
+        for k in range(T):
+            out = (torch.empty((n, 14), device=dev), torch.empty(n, device=dev), torch.empty(n, dtype=torch.uint8, device=dev), torch.empty(n, dtype=torch.uint8, device=dev))
+            act_step(a, obs, blob, act, mean, lp, val, out, None, it * T + k)
+            assert torch.equal(slab.actions[k], act) and torch.equal(roll.pol.values[k], val) and torch.equal(roll.pol.log_prob[k], lp), (it, k)
+            assert torch.equal(slab.obs[k], out[0]) and torch.equal(slab.rewards[k], out[1])
+            obs = out[0]
+    assert torch.equal(a.groups, b.groups)
+    with pytest.raises(wl.WlError):                      # 689-wide elevation observations are not supported by the fused policy
+        e = wl.WheeledSim(wl.elevation_task(num_envs=8, seed=1, terrain="procedural"), "cuda:0")
+        act_step(e, torch.zeros((8, 689), device=dev), blob, act, mean, lp, val, out, None, 0)

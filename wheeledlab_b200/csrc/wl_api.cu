@@ -343,6 +343,115 @@ wl_step_quad_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st
     log_finalize(c, gl, d_log, t);
 }
 
+// ---------------------------------------------------------------------------------------
+// fused policy: actor + critic 64x64 ELU MLPs in front of the quad step (one warp = 8 envs; lane w of a quad owns hidden
+// units [16w, 16w+16) of BOTH nets; layer outputs are exchanged through 4 KB of shared memory per warp)
+// ---------------------------------------------------------------------------------------
+#define WL_HID 64
+struct PolicyView { const float *w1a, *b1a, *w2a, *b2a, *w3a, *b3a, *w1c, *b1c, *w2c, *b2c, *w3c, *b3c, *std; };
+
+static int policy_offsets(int obs_dim, int32_t off[13]) {
+    auto al = [](int x) { return (x + 3) & ~3; };
+    int p = 0;
+    for (int net = 0; net < 2; ++net) {
+        const int out = net == 0 ? 2 : 1;
+        off[net * 6 + 0] = p; p = al(p + obs_dim * WL_HID);
+        off[net * 6 + 1] = p; p = al(p + WL_HID);
+        off[net * 6 + 2] = p; p = al(p + WL_HID * WL_HID);
+        off[net * 6 + 3] = p; p = al(p + WL_HID);
+        off[net * 6 + 4] = p; p = al(p + WL_HID * out);
+        off[net * 6 + 5] = p; p = al(p + out);
+    }
+    off[12] = p; p = al(p + 2);
+    return p;
+}
+
+__device__ __forceinline__ float elu(float x) { return x > 0.0f ? x : __expf(x) - 1.0f; }
+
+// one hidden layer slice: 16 units of this lane, `nin` inputs read from xin (shared memory or registers via pointer)
+template <int NIN_MAX>
+__device__ __forceinline__ void mlp_layer16(const float* __restrict__ wt, const float* __restrict__ bias, const float* xin, int nin,
+                                            int unit0, float acc[16]) {
+    const float4* b4 = reinterpret_cast<const float4*>(bias + unit0);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { float4 b = __ldg(b4 + q); acc[4 * q] = b.x; acc[4 * q + 1] = b.y; acc[4 * q + 2] = b.z; acc[4 * q + 3] = b.w; }
+#pragma unroll 4
+    for (int j = 0; j < nin; ++j) {
+        const float x = xin[j];
+        const float4* w4 = reinterpret_cast<const float4*>(wt + (size_t)j * WL_HID + unit0);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float4 wv = __ldg(w4 + q);
+            acc[4 * q] = fmaf(wv.x, x, acc[4 * q]); acc[4 * q + 1] = fmaf(wv.y, x, acc[4 * q + 1]);
+            acc[4 * q + 2] = fmaf(wv.z, x, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(wv.w, x, acc[4 * q + 3]);
+        }
+    }
+}
+
+template <int TASK>
+__global__ void __launch_bounds__(32)
+wl_act_step_quad_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st, wl_globals* __restrict__ gl, Terrain T,
+                        const float* __restrict__ obs_in, PolicyView pv, wl_policy_out po, float* __restrict__ obs,
+                        float* __restrict__ rew, uint8_t* __restrict__ terminated_o, uint8_t* __restrict__ truncated_o,
+                        float* __restrict__ d_log, uint32_t t_arg, int obs_dim) {
+    constexpr bool ELEV = (TASK == WL_TASK_ELEVATION), VIS = (TASK == WL_TASK_VISUAL);
+    __shared__ float sx[8][16];                  // observation rows of the warp's 8 envs
+    __shared__ float sh[8][2][WL_HID];           // hidden activations, [env][actor|critic][unit]
+    const uint32_t t = (t_arg == 0xFFFFFFFFu) ? __ldcg(&gl->step_counter) : t_arg;
+    const VisualMap vm = VIS ? visual_map(c, T.hf) : VisualMap{nullptr, nullptr};
+    const int n = c.num_envs;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = tid >> 2, w = tid & 3, q = (threadIdx.x & 31) >> 2;
+    const bool live = i < n;
+    const int ii = live ? i : n - 1;
+    const uint32_t gid = (uint32_t)(c.env_id_offset + ii);
+    const unsigned base = (threadIdx.x & 31u) & ~3u;
+    EnvState e;
+    const float4 rw0 = __ldg(reinterpret_cast<const float4*>(gl->rew_weight)), rw1 = __ldg(reinterpret_cast<const float4*>(gl->rew_weight) + 1);
+    const float wts[WL_MAX_REW_TERMS] = {rw0.x, rw0.y, rw0.z, rw0.w, rw1.x, rw1.y, rw1.z, rw1.w};
+    load_env_quad(st, n, ii, w, e, ELEV);        // state loads fly while the policy runs
+    // ---- policy: obs row -> shared
+    for (int j = w; j < obs_dim; j += 4) sx[q][j] = obs_in[(size_t)ii * obs_dim + j];
+    __syncwarp();
+    float ha[16], hc[16];
+    mlp_layer16<16>(pv.w1a, pv.b1a, sx[q], obs_dim, 16 * w, ha);
+    mlp_layer16<16>(pv.w1c, pv.b1c, sx[q], obs_dim, 16 * w, hc);
+#pragma unroll
+    for (int u = 0; u < 16; ++u) { sh[q][0][16 * w + u] = elu(ha[u]); sh[q][1][16 * w + u] = elu(hc[u]); }
+    __syncwarp();
+    mlp_layer16<64>(pv.w2a, pv.b2a, sh[q][0], WL_HID, 16 * w, ha);
+    mlp_layer16<64>(pv.w2c, pv.b2c, sh[q][1], WL_HID, 16 * w, hc);
+    // output heads: partial dots over this lane's 16 hidden units, then a quad butterfly
+    float m0 = 0.0f, m1 = 0.0f, vv = 0.0f;
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+        const float xa = elu(ha[u]), xc = elu(hc[u]);
+        const int j = 16 * w + u;
+        m0 = fmaf(__ldg(pv.w3a + 2 * j), xa, m0); m1 = fmaf(__ldg(pv.w3a + 2 * j + 1), xa, m1);
+        vv = fmaf(__ldg(pv.w3c + j), xc, vv);
+    }
+    m0 += __shfl_xor_sync(0xffffffffu, m0, 1); m0 += __shfl_xor_sync(0xffffffffu, m0, 2);
+    m1 += __shfl_xor_sync(0xffffffffu, m1, 1); m1 += __shfl_xor_sync(0xffffffffu, m1, 2);
+    vv += __shfl_xor_sync(0xffffffffu, vv, 1); vv += __shfl_xor_sync(0xffffffffu, vv, 2);
+    m0 += __ldg(pv.b3a); m1 += __ldg(pv.b3a + 1); vv += __ldg(pv.b3c);
+    // Gaussian head: a = mean + std * z (rsl_rl ActorCritic.act), log-prob summed over the action dims
+    const float s0 = __ldg(pv.std), s1 = __ldg(pv.std + 1);
+    uint4 r = philox4x32(c.seed, gid, t, RNG_POLICY, 0u);
+    float z0, z1; box_muller(r.x, r.y, z0, z1);
+    const float2 a = make_float2(fmaf(s0, z0, m0), fmaf(s1, z1, m1));
+    if (live && w == 0) {
+        reinterpret_cast<float2*>(po.actions)[i] = a;
+        reinterpret_cast<float2*>(po.mean)[i] = make_float2(m0, m1);
+        po.log_prob[i] = -0.5f * (z0 * z0 + z1 * z1) - __logf(s0) - __logf(s1) - 1.8378770664093453f;   // 2 * 0.5 log(2 pi)
+        po.value[i] = vv;
+    }
+    // ---- the env step on the sampled action
+    const int od = ELEV ? WL_OBS_DIM_ELEV : VIS ? WL_OBS_DIM_VISUAL : WL_OBS_DIM_BLIND;
+    quad_env_step<TASK>(c, T, vm, gl->acc, wts, e, i, w, live, gid, base, t, a, obs + (size_t)od * ii, rew, terminated_o, truncated_o);
+    if (live) store_env_quad(st, n, i, w, e, ELEV);
+    log_finalize(c, gl, d_log, t);
+}
+
 // K consecutive env.step()s in ONE launch (synthetic / scripted-action rollouts): the state stays in registers
 // for the whole rollout, every step still writes its observation / reward / done rows ([K,N,...] slab) and its episode-log
 // row.  actions == nullptr => U[-1,1]^2 drawn in-kernel from the counter-based generator (and stored to act_out).
@@ -1000,6 +1109,35 @@ int wl_derive_suspension(wl_sim* sim, float* d_susp_pos, float* d_susp_vel, void
     else
         wl_suspension_kernel<WL_TASK_DRIFT><<<(n + bs - 1) / bs, bs, 0, (cudaStream_t)stream>>>(sim->cfg, sim->state, T, (float4*)d_susp_pos, (float4*)d_susp_vel);
     WL_LAUNCH_CHECK(sim, "wl_suspension_kernel");
+    return WL_OK;
+}
+
+int32_t wl_policy_blob_floats(int32_t obs_dim, int32_t offsets[13]) {
+    int32_t tmp[13];
+    return policy_offsets(obs_dim, offsets ? offsets : tmp);
+}
+
+int wl_act_step(wl_sim* sim, const float* d_obs_in, const float* d_policy_blob, wl_policy_out out, float* d_obs, float* d_rew,
+                uint8_t* d_terminated, uint8_t* d_truncated, float* d_log, int64_t step_counter, void* stream) {
+    if (!sim || !d_obs_in || !d_policy_blob || !out.actions || !out.mean || !out.log_prob || !out.value || !d_obs || !d_rew ||
+        !d_terminated || !d_truncated)
+        return fail(WL_EINVAL, "wl_act_step: null argument");
+    if (sim->cfg.task == WL_TASK_ELEVATION) return fail(WL_EUNSUPPORTED, "wl_act_step: blind-observation tasks only (obs_dim <= 16)");
+    if (sim->obs_dim > 16) return fail(WL_EUNSUPPORTED, "wl_act_step: obs_dim > 16");
+    if (((uintptr_t)d_policy_blob & 15u) || ((uintptr_t)out.actions & 7u) || ((uintptr_t)out.mean & 7u))
+        return fail(WL_EINVAL, "wl_act_step: policy blob must be 16-byte aligned, actions/mean 8-byte aligned");
+    int32_t o[13];
+    policy_offsets(sim->obs_dim, o);
+    const float* B = d_policy_blob;
+    PolicyView pv{B + o[0], B + o[1], B + o[2], B + o[3], B + o[4], B + o[5], B + o[6], B + o[7], B + o[8], B + o[9], B + o[10], B + o[11], B + o[12]};
+    const int n = sim->cfg.num_envs, threads = 4 * n, grid = (threads + 31) / 32;
+    Terrain T{sim->hf};
+    cudaStream_t cs = (cudaStream_t)stream;
+    if (sim->cfg.task == WL_TASK_VISUAL)
+        wl_act_step_quad_kernel<WL_TASK_VISUAL><<<grid, 32, 0, cs>>>(sim->cfg, sim->state, sim->globals, T, d_obs_in, pv, out, d_obs, d_rew, d_terminated, d_truncated, d_log, (uint32_t)step_counter, sim->obs_dim);
+    else
+        wl_act_step_quad_kernel<WL_TASK_DRIFT><<<grid, 32, 0, cs>>>(sim->cfg, sim->state, sim->globals, T, d_obs_in, pv, out, d_obs, d_rew, d_terminated, d_truncated, d_log, (uint32_t)step_counter, sim->obs_dim);
+    WL_LAUNCH_CHECK(sim, "wl_act_step_quad_kernel");
     return WL_OK;
 }
 
