@@ -396,7 +396,8 @@ int64_t wl_launch_count(const wl_sim* sim);
  * drifting/config/agents/mushr/rsl_rl_ppo_cfg.py:12-17: actor and critic 64x64 ELU MLPs, Gaussian head with a learned
  * std) FUSED in front of the env step: one launch = value + action mean + sampled action + log-prob + the whole step.
  * Weights are a caller-owned device blob of fp32 in INPUT-MAJOR (transposed) layout, per net:
- *     W1t[obs_dim][64] b1[64]  W2t[64][64] b2[64]  W3t[64][out] b3[out]        (actor: out = 2, critic: out = 1)
+ *     W1t[ceil4(obs_dim)][64] b1[64]  W2t[64][64] b2[64]  W3t[64][out] b3[out]   (actor: out = 2, critic: out = 1;
+ *     rows obs_dim.. of W1t are zero padding)
  * blob = actor net | critic net | std[2]; every block starts 16-byte aligned (wl_policy_blob_floats gives offsets).
  * a = mean + std * z, z ~ N(0,1) from the counter-based generator (stream 9, keyed by global env id and step). */
 typedef struct wl_policy_out {

@@ -10,7 +10,7 @@ import os
 from pathlib import Path
 
 _PKG_DIR = Path(__file__).resolve().parent
-LIB_PATH = _PKG_DIR / "libwheeledlab_b200.so"
+LIB_PATH = Path(os.environ["WHEELEDLAB_B200_LIB"]) if os.environ.get("WHEELEDLAB_B200_LIB") else _PKG_DIR / "libwheeledlab_b200.so"   # (override: kernel A/B builds)
 
 _TAGS = {"i32": C.c_int32, "u64": C.c_uint64, "f32": C.c_float}
 

@@ -348,14 +348,15 @@ wl_step_quad_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st
 // units [16w, 16w+16) of BOTH nets; layer outputs are exchanged through 4 KB of shared memory per warp)
 // ---------------------------------------------------------------------------------------
 #define WL_HID 64
-struct PolicyView { const float *w1a, *b1a, *w2a, *b2a, *w3a, *b3a, *w1c, *b1c, *w2c, *b2c, *w3c, *b3c, *std; };
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+struct PolicyOffsets { int32_t o[13]; };
 
 static int policy_offsets(int obs_dim, int32_t off[13]) {
     auto al = [](int x) { return (x + 3) & ~3; };
     int p = 0;
     for (int net = 0; net < 2; ++net) {
         const int out = net == 0 ? 2 : 1;
-        off[net * 6 + 0] = p; p = al(p + obs_dim * WL_HID);
+        off[net * 6 + 0] = p; p = al(p + al(obs_dim) * WL_HID);      // rows padded to a multiple of 4 (zeros)
         off[net * 6 + 1] = p; p = al(p + WL_HID);
         off[net * 6 + 2] = p; p = al(p + WL_HID * WL_HID);
         off[net * 6 + 3] = p; p = al(p + WL_HID);
@@ -366,89 +367,166 @@ static int policy_offsets(int obs_dim, int32_t off[13]) {
     return p;
 }
 
+__device__ __forceinline__ void mbar_init(uint64_t* b) { asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(b))); }
+__device__ __forceinline__ void mbar_expect(uint64_t* b, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* b) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* b) {       // phase 0 (each barrier is used once per launch)
+    const uint32_t mb = smem_u32(b);
+    uint32_t ok = 0;
+    while (!ok)
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(mb), "r"(0u) : "memory");
+}
 __device__ __forceinline__ float elu(float x) { return x > 0.0f ? x : __expf(x) - 1.0f; }
 
-// one hidden layer slice: 16 units of this lane, `nin` inputs read from xin (shared memory or registers via pointer)
-template <int NIN_MAX>
-__device__ __forceinline__ void mlp_layer16(const float* __restrict__ wt, const float* __restrict__ bias, const float* xin, int nin,
-                                            int unit0, float acc[16]) {
-    const float4* b4 = reinterpret_cast<const float4*>(bias + unit0);
+// one hidden layer for a register tile of 4 units x 4 envs: per 4 inputs, 4 LDS.128 of activations (one per env, a pure
+// broadcast: the whole warp shares the env tile) and 4 LDS.128 of input-major weights (conflict-free: the 16 lanes of a
+// net read 256 contiguous bytes) feed 64 FMAs; accumulation order per output = bias, then inputs ascending
+__device__ __forceinline__ void mlp_tile_layer(const float* W, const float* bias, const float* x0, int xstride, int nin, float acc[4][4]) {
+    const float4 b0 = *reinterpret_cast<const float4*>(bias);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) { float4 b = __ldg(b4 + q); acc[4 * q] = b.x; acc[4 * q + 1] = b.y; acc[4 * q + 2] = b.z; acc[4 * q + 3] = b.w; }
+    for (int e = 0; e < 4; ++e) { acc[e][0] = b0.x; acc[e][1] = b0.y; acc[e][2] = b0.z; acc[e][3] = b0.w; }
 #pragma unroll 4
-    for (int j = 0; j < nin; ++j) {
-        const float x = xin[j];
-        const float4* w4 = reinterpret_cast<const float4*>(wt + (size_t)j * WL_HID + unit0);
+    for (int j = 0; j < nin; j += 4) {
+        float xs[4][4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            float4 wv = __ldg(w4 + q);
-            acc[4 * q] = fmaf(wv.x, x, acc[4 * q]); acc[4 * q + 1] = fmaf(wv.y, x, acc[4 * q + 1]);
-            acc[4 * q + 2] = fmaf(wv.z, x, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(wv.w, x, acc[4 * q + 3]);
+        for (int e = 0; e < 4; ++e) {
+            const float4 v = *reinterpret_cast<const float4*>(x0 + e * xstride + j);
+            xs[e][0] = v.x; xs[e][1] = v.y; xs[e][2] = v.z; xs[e][3] = v.w;
+        }
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+            const float4 w0 = *reinterpret_cast<const float4*>(W + (j + jj) * WL_HID);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float x = xs[e][jj];
+                acc[e][0] = fmaf(w0.x, x, acc[e][0]); acc[e][1] = fmaf(w0.y, x, acc[e][1]);
+                acc[e][2] = fmaf(w0.z, x, acc[e][2]); acc[e][3] = fmaf(w0.w, x, acc[e][3]);
+            }
         }
     }
 }
 
+__device__ __forceinline__ void mlp_tile_store_elu(float* h0, int hstride, const float acc[4][4]) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+        *reinterpret_cast<float4*>(h0 + e * hstride) = make_float4(elu(acc[e][0]), elu(acc[e][1]), elu(acc[e][2]), elu(acc[e][3]));
+}
+
+#define WL_ACT_ENVS 32                           // envs per CTA: 4096 envs -> 128 CTAs, one per SM
+#define WL_ACT_THREADS 256                       // 8 lanes per env for the MLPs (2 warps per scheduler); threads 0..127 = the env quads
+#define WL_ACT_XS 20                             // padded observation row
+#define WL_ACT_HS (2 * WL_HID + 4)               // padded hidden row, [actor 64 | critic 64 | pad]
+
 template <int TASK>
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(WL_ACT_THREADS)
 wl_act_step_quad_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st, wl_globals* __restrict__ gl, Terrain T,
-                        const float* __restrict__ obs_in, PolicyView pv, wl_policy_out po, float* __restrict__ obs,
-                        float* __restrict__ rew, uint8_t* __restrict__ terminated_o, uint8_t* __restrict__ truncated_o,
-                        float* __restrict__ d_log, uint32_t t_arg, int obs_dim) {
+                        const float* __restrict__ obs_in, const float* __restrict__ blob, int blob_floats, PolicyOffsets po_off,
+                        wl_policy_out po, float* __restrict__ obs, float* __restrict__ rew, uint8_t* __restrict__ terminated_o,
+                        uint8_t* __restrict__ truncated_o, float* __restrict__ d_log, uint32_t t_arg, int obs_dim) {
     constexpr bool ELEV = (TASK == WL_TASK_ELEVATION), VIS = (TASK == WL_TASK_VISUAL);
-    __shared__ float sx[8][16];                  // observation rows of the warp's 8 envs
-    __shared__ float sh[8][2][WL_HID];           // hidden activations, [env][actor|critic][unit]
+    extern __shared__ __align__(128) float smem[];
+    __shared__ __align__(8) uint64_t mbar[2];
+    float* sw = smem;                                        // the whole weight blob (~42 KB)
+    float* sx = smem + blob_floats;                          // [32][WL_ACT_XS]
+    float* sh = sx + WL_ACT_ENVS * WL_ACT_XS;                // [32][WL_ACT_HS]
+    // ---- bulk async copies (TMA, 1-D) bring the blob from L2 into shared memory while the env state loads fly: the two
+    // first-layer blocks (7.5 KB) complete on mbar[0], everything else (34 KB) on mbar[1] and lands during layer 1
+    if (threadIdx.x == 0) {
+        mbar_init(&mbar[0]); mbar_init(&mbar[1]);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const int a0 = po_off.o[0], a1 = po_off.o[2], c0 = po_off.o[6], c1 = po_off.o[8];
+        mbar_expect(&mbar[0], (uint32_t)((a1 - a0) + (c1 - c0)) * 4u);
+        bulk_g2s(sw + a0, blob + a0, (uint32_t)(a1 - a0) * 4u, &mbar[0]);
+        bulk_g2s(sw + c0, blob + c0, (uint32_t)(c1 - c0) * 4u, &mbar[0]);
+        mbar_expect(&mbar[1], (uint32_t)((c0 - a1) + (blob_floats - c1)) * 4u);
+        bulk_g2s(sw + a1, blob + a1, (uint32_t)(c0 - a1) * 4u, &mbar[1]);
+        bulk_g2s(sw + c1, blob + c1, (uint32_t)(blob_floats - c1) * 4u, &mbar[1]);
+    }
     const uint32_t t = (t_arg == 0xFFFFFFFFu) ? __ldcg(&gl->step_counter) : t_arg;
     const VisualMap vm = VIS ? visual_map(c, T.hf) : VisualMap{nullptr, nullptr};
     const int n = c.num_envs;
-    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
-    const int i = tid >> 2, w = tid & 3, q = (threadIdx.x & 31) >> 2;
+    const bool stepper = threadIdx.x < 4 * WL_ACT_ENVS;      // warps 0..3 own the env quads; warps 4..7 only help with the MLPs
+    const int q = (threadIdx.x >> 2) & (WL_ACT_ENVS - 1), w = threadIdx.x & 3;
+    const int i = blockIdx.x * WL_ACT_ENVS + q;
     const bool live = i < n;
     const int ii = live ? i : n - 1;
     const uint32_t gid = (uint32_t)(c.env_id_offset + ii);
     const unsigned base = (threadIdx.x & 31u) & ~3u;
     EnvState e;
-    const float4 rw0 = __ldg(reinterpret_cast<const float4*>(gl->rew_weight)), rw1 = __ldg(reinterpret_cast<const float4*>(gl->rew_weight) + 1);
-    const float wts[WL_MAX_REW_TERMS] = {rw0.x, rw0.y, rw0.z, rw0.w, rw1.x, rw1.y, rw1.z, rw1.w};
-    load_env_quad(st, n, ii, w, e, ELEV);        // state loads fly while the policy runs
-    // ---- policy: obs row -> shared
-    for (int j = w; j < obs_dim; j += 4) sx[q][j] = obs_in[(size_t)ii * obs_dim + j];
-    __syncwarp();
-    float ha[16], hc[16];
-    mlp_layer16<16>(pv.w1a, pv.b1a, sx[q], obs_dim, 16 * w, ha);
-    mlp_layer16<16>(pv.w1c, pv.b1c, sx[q], obs_dim, 16 * w, hc);
-#pragma unroll
-    for (int u = 0; u < 16; ++u) { sh[q][0][16 * w + u] = elu(ha[u]); sh[q][1][16 * w + u] = elu(hc[u]); }
-    __syncwarp();
-    mlp_layer16<64>(pv.w2a, pv.b2a, sh[q][0], WL_HID, 16 * w, ha);
-    mlp_layer16<64>(pv.w2c, pv.b2c, sh[q][1], WL_HID, 16 * w, hc);
-    // output heads: partial dots over this lane's 16 hidden units, then a quad butterfly
-    float m0 = 0.0f, m1 = 0.0f, vv = 0.0f;
-#pragma unroll
-    for (int u = 0; u < 16; ++u) {
-        const float xa = elu(ha[u]), xc = elu(hc[u]);
-        const int j = 16 * w + u;
-        m0 = fmaf(__ldg(pv.w3a + 2 * j), xa, m0); m1 = fmaf(__ldg(pv.w3a + 2 * j + 1), xa, m1);
-        vv = fmaf(__ldg(pv.w3c + j), xc, vv);
+    float wts[WL_MAX_REW_TERMS];
+    if (stepper) {
+        const float4 rw0 = __ldg(reinterpret_cast<const float4*>(gl->rew_weight)), rw1 = __ldg(reinterpret_cast<const float4*>(gl->rew_weight) + 1);
+        wts[0] = rw0.x; wts[1] = rw0.y; wts[2] = rw0.z; wts[3] = rw0.w; wts[4] = rw1.x; wts[5] = rw1.y; wts[6] = rw1.z; wts[7] = rw1.w;
+        load_env_quad(st, n, ii, w, e, ELEV);
     }
-    m0 += __shfl_xor_sync(0xffffffffu, m0, 1); m0 += __shfl_xor_sync(0xffffffffu, m0, 2);
-    m1 += __shfl_xor_sync(0xffffffffu, m1, 1); m1 += __shfl_xor_sync(0xffffffffu, m1, 2);
-    vv += __shfl_xor_sync(0xffffffffu, vv, 1); vv += __shfl_xor_sync(0xffffffffu, vv, 2);
-    m0 += __ldg(pv.b3a); m1 += __ldg(pv.b3a + 1); vv += __ldg(pv.b3c);
-    // Gaussian head: a = mean + std * z (rsl_rl ActorCritic.act), log-prob summed over the action dims
-    const float s0 = __ldg(pv.std), s1 = __ldg(pv.std + 1);
-    uint4 r = philox4x32(c.seed, gid, t, RNG_POLICY, 0u);
-    float z0, z1; box_muller(r.x, r.y, z0, z1);
-    const float2 a = make_float2(fmaf(s0, z0, m0), fmaf(s1, z1, m1));
-    if (live && w == 0) {
-        reinterpret_cast<float2*>(po.actions)[i] = a;
-        reinterpret_cast<float2*>(po.mean)[i] = make_float2(m0, m1);
-        po.log_prob[i] = -0.5f * (z0 * z0 + z1 * z1) - __logf(s0) - __logf(s1) - 1.8378770664093453f;   // 2 * 0.5 log(2 pi)
-        po.value[i] = vv;
+    for (int k = threadIdx.x; k < WL_ACT_ENVS * 16; k += WL_ACT_THREADS) {
+        const int eq = k >> 4, j = k & 15, ei = min(blockIdx.x * WL_ACT_ENVS + eq, n - 1);
+        sx[eq * WL_ACT_XS + j] = j < obs_dim ? obs_in[(size_t)ei * obs_dim + j] : 0.0f;
     }
-    // ---- the env step on the sampled action
-    const int od = ELEV ? WL_OBS_DIM_ELEV : VIS ? WL_OBS_DIM_VISUAL : WL_OBS_DIM_BLIND;
-    quad_env_step<TASK>(c, T, vm, gl->acc, wts, e, i, w, live, gid, base, t, a, obs + (size_t)od * ii, rew, terminated_o, truncated_o);
-    if (live) store_env_quad(st, n, i, w, e, ELEV);
+    // the policy noise does not depend on the weights: draw it while the copies are in flight
+    float z0 = 0.0f, z1 = 0.0f;
+    if (stepper) {
+        const uint4 r = philox4x32(c.seed, gid, t, RNG_POLICY, 0u);
+        box_muller(r.x, r.y, z0, z1);
+    }
+    __syncthreads();                                         // mbarrier init visible to every waiter; obs rows written
+    mbar_wait(&mbar[0]);
+    // ---- MLPs: warp k takes envs 4k..4k+3 of the CTA; its 32 lanes tile the 128 (actor | critic) hidden columns 4 at a
+    // time, so a lane holds 4 units x 4 envs in registers.  Layer exchanges stay warp-local (__syncwarp).  W1t has obs_dim
+    // rows; rows obs_dim..nin1-1 read whatever follows in the blob and meet the zero padding of x.
+    {
+        const int lane = threadIdx.x & 31, net = lane >> 4, ucol = (lane & 15) * 4;
+        const int env0 = (threadIdx.x >> 5) * 4;
+        const int nin1 = (obs_dim + 3) & ~3;
+        const int oW1 = net ? po_off.o[6] : po_off.o[0], oB1 = net ? po_off.o[7] : po_off.o[1];     // (no dynamic indexing of kernel params)
+        const int oW2 = net ? po_off.o[8] : po_off.o[2], oB2 = net ? po_off.o[9] : po_off.o[3];
+        float acc[4][4];
+        float* h0 = sh + env0 * WL_ACT_HS + net * WL_HID;
+        mlp_tile_layer(sw + oW1 + ucol, sw + oB1 + ucol, sx + env0 * WL_ACT_XS, WL_ACT_XS, nin1, acc);
+        mlp_tile_store_elu(h0 + ucol, WL_ACT_HS, acc);
+        __syncwarp();
+        mbar_wait(&mbar[1]);                                 // layer-2 / head weights have landed (copy overlapped layer 1)
+        mlp_tile_layer(sw + oW2 + ucol, sw + oB2 + ucol, h0, WL_ACT_HS, WL_HID, acc);
+        __syncwarp();                                        // every lane has finished reading layer-1 activations
+        mlp_tile_store_elu(h0 + ucol, WL_ACT_HS, acc);
+    }
+    __syncthreads();                                         // layer-2 activations of all 32 envs are in shared memory
+    if (stepper) {
+        // output heads: lane w of the env's quad takes hidden units [16w, 16w+16) of both nets, then a quad butterfly
+        const float* hrow = sh + q * WL_ACT_HS;
+        const float* w3a = sw + po_off.o[4]; const float* w3c = sw + po_off.o[10];
+        float m0 = 0.0f, m1 = 0.0f, vv = 0.0f;
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            const int j = 16 * w + u;
+            const float xa = hrow[j], xc = hrow[WL_HID + j];
+            m0 = fmaf(w3a[2 * j], xa, m0); m1 = fmaf(w3a[2 * j + 1], xa, m1);
+            vv = fmaf(w3c[j], xc, vv);
+        }
+        m0 += __shfl_xor_sync(0xffffffffu, m0, 1); m0 += __shfl_xor_sync(0xffffffffu, m0, 2);
+        m1 += __shfl_xor_sync(0xffffffffu, m1, 1); m1 += __shfl_xor_sync(0xffffffffu, m1, 2);
+        vv += __shfl_xor_sync(0xffffffffu, vv, 1); vv += __shfl_xor_sync(0xffffffffu, vv, 2);
+        m0 += sw[po_off.o[5]]; m1 += sw[po_off.o[5] + 1]; vv += sw[po_off.o[11]];
+        // Gaussian head: a = mean + std * z (rsl_rl ActorCritic.act), log-prob summed over the action dims
+        const float s0 = sw[po_off.o[12]], s1 = sw[po_off.o[12] + 1];
+        const float2 a = make_float2(fmaf(s0, z0, m0), fmaf(s1, z1, m1));
+        if (live && w == 0) {
+            reinterpret_cast<float2*>(po.actions)[i] = a;
+            reinterpret_cast<float2*>(po.mean)[i] = make_float2(m0, m1);
+            po.log_prob[i] = -0.5f * (z0 * z0 + z1 * z1) - __logf(s0) - __logf(s1) - 1.8378770664093453f;   // 2 * 0.5 log(2 pi)
+            po.value[i] = vv;
+        }
+        // ---- the env step on the sampled action
+        const int od = ELEV ? WL_OBS_DIM_ELEV : VIS ? WL_OBS_DIM_VISUAL : WL_OBS_DIM_BLIND;
+        quad_env_step<TASK>(c, T, vm, gl->acc, wts, e, i, w, live, gid, base, t, a, obs + (size_t)od * ii, rew, terminated_o, truncated_o);
+        if (live) store_env_quad(st, n, i, w, e, ELEV);
+    }
     log_finalize(c, gl, d_log, t);
 }
 
@@ -525,7 +603,6 @@ wl_rollout_quad_kernel(const __grid_constant__ wl_config c, float4* __restrict__
 #define WL_TILE_H 40
 #define WL_SCAN_THREADS 128
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 template <bool USE_TMA>
 __global__ void __launch_bounds__(WL_SCAN_THREADS)
@@ -1126,17 +1203,22 @@ int wl_act_step(wl_sim* sim, const float* d_obs_in, const float* d_policy_blob, 
     if (sim->obs_dim > 16) return fail(WL_EUNSUPPORTED, "wl_act_step: obs_dim > 16");
     if (((uintptr_t)d_policy_blob & 15u) || ((uintptr_t)out.actions & 7u) || ((uintptr_t)out.mean & 7u))
         return fail(WL_EINVAL, "wl_act_step: policy blob must be 16-byte aligned, actions/mean 8-byte aligned");
-    int32_t o[13];
-    policy_offsets(sim->obs_dim, o);
-    const float* B = d_policy_blob;
-    PolicyView pv{B + o[0], B + o[1], B + o[2], B + o[3], B + o[4], B + o[5], B + o[6], B + o[7], B + o[8], B + o[9], B + o[10], B + o[11], B + o[12]};
-    const int n = sim->cfg.num_envs, threads = 4 * n, grid = (threads + 31) / 32;
+    PolicyOffsets po;
+    const int blob_floats = policy_offsets(sim->obs_dim, po.o);
+    const int n = sim->cfg.num_envs, grid = (n + WL_ACT_ENVS - 1) / WL_ACT_ENVS;
+    const size_t smem = sizeof(float) * ((size_t)blob_floats + WL_ACT_ENVS * (WL_ACT_XS + WL_ACT_HS));
     Terrain T{sim->hf};
     cudaStream_t cs = (cudaStream_t)stream;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(wl_act_step_quad_kernel<WL_TASK_VISUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        cudaFuncSetAttribute(wl_act_step_quad_kernel<WL_TASK_DRIFT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        attr_set = true;
+    }
     if (sim->cfg.task == WL_TASK_VISUAL)
-        wl_act_step_quad_kernel<WL_TASK_VISUAL><<<grid, 32, 0, cs>>>(sim->cfg, sim->state, sim->globals, T, d_obs_in, pv, out, d_obs, d_rew, d_terminated, d_truncated, d_log, (uint32_t)step_counter, sim->obs_dim);
+        wl_act_step_quad_kernel<WL_TASK_VISUAL><<<grid, WL_ACT_THREADS, smem, cs>>>(sim->cfg, sim->state, sim->globals, T, d_obs_in, d_policy_blob, blob_floats, po, out, d_obs, d_rew, d_terminated, d_truncated, d_log, (uint32_t)step_counter, sim->obs_dim);
     else
-        wl_act_step_quad_kernel<WL_TASK_DRIFT><<<grid, 32, 0, cs>>>(sim->cfg, sim->state, sim->globals, T, d_obs_in, pv, out, d_obs, d_rew, d_terminated, d_truncated, d_log, (uint32_t)step_counter, sim->obs_dim);
+        wl_act_step_quad_kernel<WL_TASK_DRIFT><<<grid, WL_ACT_THREADS, smem, cs>>>(sim->cfg, sim->state, sim->globals, T, d_obs_in, d_policy_blob, blob_floats, po, out, d_obs, d_rew, d_terminated, d_truncated, d_log, (uint32_t)step_counter, sim->obs_dim);
     WL_LAUNCH_CHECK(sim, "wl_act_step_quad_kernel");
     return WL_OK;
 }
