@@ -55,13 +55,14 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index: int):
-        self.gpu, self.rows, self.proc = gpu_index, [], None
+    def __init__(self, gpu_indices):
+        self.gpu = ",".join(str(g) for g in (gpu_indices if isinstance(gpu_indices, (list, tuple, range)) else [gpu_indices]))
+        self.rows, self.proc = [], None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                          "-lms", "100", "-i", self.gpu], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -80,17 +81,21 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             pass
-        sm, mx, reasons = [], [], set()
+        sm, mx, reasons, per = [], [], set(), {}
         for r in self.rows:
             try:
                 sm.append(float(r[1])); mx.append(float(r[2]))
+                per.setdefault(int(r[0]), []).append(float(r[1]))
             except Exception:
                 continue
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        out = {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+               "reasons": sorted(reasons), "samples": len(sm)}
+        if len(per) > 1:                                      # one median per GPU of the job
+            out["per_gpu_sm_mhz"] = [statistics.median(per[g]) for g in sorted(per)]
+        return out
 
 
 def _oracle(spec, native=True, threads=1):
@@ -209,8 +214,9 @@ def run_ours(args):
     from wheeledlab_b200.distributed import RolloutSlab
     T_ROLL = 128                                                                  # rsl_rl num_steps_per_env (rsl_rl_ppo_cfg.py:6)
     acts = torch.stack([sim.synth_actions(t) for t in range(W + K)])           # resident in HBM
-    slab = RolloutSlab(T_ROLL, E, sim.obs_dim, 2, dev)                            # the step writes straight into the send buffer
-    outs = slab.step_outputs(0)
+    slabs = [RolloutSlab(T_ROLL, E, sim.obs_dim, 2, dev) for _ in range(2 if world > 1 else 1)]   # the step writes straight into
+    slab = slabs[0]                                                               # the send buffer; two of them so that the
+    outs = slab.step_outputs(0)                                                   # gather of iteration i overlaps rollout i+1
     sim.step(acts[0], 0, out=outs)
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # 256 MiB > 126 MB L2
     peak, peak_src = _peaks()
@@ -231,38 +237,58 @@ def run_ours(args):
     t = 1
     for _ in range(W):
         sim.step(acts[t % (W + K)], t, out=outs); flush.fill_(0.0); t += 1
-    if world > 1:                                       # untimed: NCCL communicator / channel set-up
-        for _ in range(3):
-            slab.all_gather()
-    sampler = ClockSampler(local)
+    if world > 1:                                       # untimed: NCCL communicator / channel set-up, receive buffers
+        for _ in range(2):
+            for sl in slabs:
+                sl.all_gather()
+    sampler = ClockSampler(list(range(world)) if world > 1 else local)
     barrier()
     if rank == 0:
         sampler.start()
     l0 = sim.launch_count
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     barrier()
-    gev, gathered = [], None
+    gev, wev, gathered = [], [], None
+    gstream = torch.cuda.Stream(device=dev) if world > 1 else None
+    gdone = [None] * len(slabs)                         # per slab: event after which its rows may be overwritten again
+    main = torch.cuda.current_stream()
     # pointers resolved once per (action row, slab row): the timed loop is event / one ctypes call / event / flush
-    bound = [sim.bind_step(acts[(W + k) % (W + K)], slab.step_outputs(k % T_ROLL)) for k in range(K)]
+    n_it = (K + T_ROLL - 1) // T_ROLL
+    bound = [sim.bind_step(acts[(W + k) % (W + K)], slabs[(k // T_ROLL) % len(slabs)].step_outputs(k % T_ROLL)) for k in range(K)]
     for k in range(K):
-        row = k % T_ROLL
+        row, cur = k % T_ROLL, (k // T_ROLL) % len(slabs)
+        if world > 1 and row == 0 and gdone[cur] is not None:
+            # the slab about to be refilled must have been gathered: any time the step stream has to WAIT for that is the
+            # exposed (non-overlapped) cost of the collective and is added to the step times
+            w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            w0.record(); main.wait_event(gdone[cur]); w1.record(); wev.append((w0, w1))
         ev[k][0].record()
         bound[k](t); t += 1
         ev[k][1].record()
         flush.fill_(0.0)
-        if world > 1 and row == T_ROLL - 1:            # one all-gather of the rollout slab per PPO iteration
-            barrier()                                  # untimed: the L2-flush fills between steps de-synchronise the ranks'
-            #                                            host loops; without this the gather would be charged that artefact
-            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            g0.record(); gathered = slab.all_gather(); g1.record(); gev.append((g0, g1))
+        if world > 1 and row == T_ROLL - 1:            # one all-gather of the rollout slab per PPO iteration, on its own
+            filled = torch.cuda.Event(); filled.record()       # stream: it overlaps the next iteration's steps
+            with torch.cuda.stream(gstream):
+                gstream.wait_event(filled)
+                g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                g0.record(); gathered = slabs[cur].all_gather(); g1.record(); gev.append((g0, g1))
+                gdone[cur] = g1
+    if world > 1:                                       # the last gathers must be finished before the clock stops
+        w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0.record()
+        for g in gdone:
+            if g is not None:
+                main.wait_event(g)
+        w1.record(); wev.append((w0, w1))
     barrier()
     launches = sim.launch_count - l0
     step_ms = [a.elapsed_time(b) for a, b in ev]
     gather_each = [a.elapsed_time(b) for a, b in gev]
-    gather_ms = sum(gather_each)
+    gather_ms = sum(gather_each)                        # duration of the collectives on their own stream (mostly hidden)
+    exposed_ms = sum(a.elapsed_time(b) for a, b in wev) # what the step stream actually waited for them
     if gev and rank == 0:
-        print(f"[bench] all-gather ms per call: {[round(x, 3) for x in gather_each]}", file=sys.stderr)
-    tot_ms = sum(step_ms) + gather_ms
+        print(f"[bench] all-gather ms per call: {[round(x, 3) for x in gather_each]}, exposed {exposed_ms:.3f} ms", file=sys.stderr)
+    tot_ms = sum(step_ms) + exposed_ms
     # ---- warm-L2, CUDA-graph replay of K steps (supplementary: how the loop is meant to be driven) ----
     g = torch.cuda.CUDAGraph()
     s = torch.cuda.Stream()
@@ -306,6 +332,8 @@ def run_ours(args):
     # ---- policy in the loop: 128 x (64x64 ELU MLP -> step -> slab row) captured as ONE CUDA graph (supplementary) ----
     pil = None
     try:
+        if args.no_extras:
+            raise RuntimeError('skipped (--no-extras)')
         from wheeledlab_b200.rollout import GraphedRollout
         torch.manual_seed(0)
         mlp = torch.nn.Sequential(torch.nn.Linear(sim.obs_dim, 64), torch.nn.ELU(), torch.nn.Linear(64, 64), torch.nn.ELU(),
@@ -329,6 +357,8 @@ def run_ours(args):
     # ---- actor + critic + Gaussian sampling FUSED into the step kernel (wl_act_step), 128 launches per graph (supplementary) ----
     pfu = None
     try:
+        if args.no_extras:
+            raise RuntimeError('skipped (--no-extras)')
         from wheeledlab_b200.policy import FusedPolicyRollout, pack_actor_critic
         torch.manual_seed(0)
         mk = lambda out: torch.nn.Sequential(torch.nn.Linear(sim.obs_dim, 64), torch.nn.ELU(), torch.nn.Linear(64, 64), torch.nn.ELU(),
@@ -353,6 +383,8 @@ def run_ours(args):
     # ---- fused K-step synthetic rollout: K env.steps per launch, state in registers, in-kernel actions (supplementary) ----
     fused = None
     try:
+        if args.no_extras:
+            raise RuntimeError('skipped (--no-extras)')
         KF = 125                                                  # divides the 250-step episode: windows end on curriculum boundaries
         sim_f = wl.WheeledSim(wl.drift_task(num_envs=E, seed=args.seed, env_id_offset=rank * E), dev)
         sim_f.startup(); sim_f.reset(None, 0)
@@ -376,6 +408,15 @@ def run_ours(args):
     tot_ms, graph_ms, e2e_ms = max_over_ranks(tot_ms), max_over_ranks(graph_ms), max_over_ranks(e2e_ms)
     e2e_copy_ms = max_over_ranks(e2e_copy_ms)
     gather_ms = max_over_ranks(gather_ms)
+    exposed_ms = max_over_ranks(exposed_ms)
+    per_rank = None
+    if world > 1:                                       # diagnostics: which rank sets the max
+        st = torch.tensor([statistics.mean(step_ms), statistics.median(step_ms), max(step_ms)], dtype=torch.float64, device=dev)
+        allst = [torch.zeros_like(st) for _ in range(world)]
+        dist.all_gather(allst, st)
+        per_rank = {"step_us_mean": [round(float(x[0]) * 1e3, 3) for x in allst],
+                    "step_us_median": [round(float(x[1]) * 1e3, 3) for x in allst],
+                    "step_us_max": [round(float(x[2]) * 1e3, 3) for x in allst]}
     if rank == 0:
         total_envs = E * world
         value = total_envs * K / (tot_ms * 1e-3)
@@ -406,7 +447,12 @@ def run_ours(args):
                          "note": "N=4096 moves 1.7 MB/launch: launch-latency bound, see profiles/ for the N sweep"},
             "cpu_baseline": cpu,
             "collective": {"kind": "all_gather_into_tensor(rollout slab)", "per_iteration_steps": T_ROLL,
-                           "bytes_per_rank": slab.nbytes, "count": len(gev), "ms_total": gather_ms} if world > 1 else None,
+                           "bytes_per_rank": slab.nbytes, "count": len(gev), "ms_total": gather_ms,
+                           "overlapped_with_next_iteration": True, "exposed_ms_total": exposed_ms,
+                           "note": "double-buffered slabs; the gather of iteration i runs on its own stream under the steps of "
+                                   "iteration i+1; `value` charges the time the step stream waited for it (exposed_ms_total)"}
+            if world > 1 else None,
+            "per_rank": per_rank,
             "policy_in_loop_graph": pil,
             "policy_fused_in_step": pfu,
             "rollout_fused": fused,
@@ -427,6 +473,7 @@ def main():
     ap.add_argument("--seed", type=int, default=42)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-budget", type=float, default=12.0)
+    ap.add_argument("--no-extras", action="store_true", help="skip the supplementary figures (policy-in-loop, fused rollout)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
