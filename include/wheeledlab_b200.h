@@ -391,6 +391,18 @@ int32_t wl_obs_dim(const wl_sim* sim);
 /* number of kernel launches issued through this handle since creation */
 int64_t wl_launch_count(const wl_sim* sim);
 
+/* ---- env.step() cut in two, for HOST-SIDE (Python) reward / termination terms ----------------------------
+ * IsaacLab's managers call user terms between "physics + built-in terms" and "reset" (ManagerBasedRLEnv.step: reward and
+ * termination managers run on the post-physics, pre-reset state).  Stage a = sections A-E of wl_step (action, integrator,
+ * counters, built-in terminations and rewards): writes the built-in reward [N] and one byte of termination bits per env
+ * (bit j = built-in term j, order as listed above) and leaves the pre-reset state in the state buffer.  The caller may now
+ * read the state, ADD its own reward terms to d_rew and raise its own termination flags.  Stage b = sections F-I (episode
+ * log, auto-reset, commands / interval pushes, observations, last-CTA epilogue) for done = any built-in bit | extras.
+ * wl_step_stage_a + wl_step_stage_b with null extras == wl_step, bit for bit. */
+int wl_step_stage_a(wl_sim* sim, const float* d_action, float* d_rew, uint8_t* d_term_bits, int64_t step_counter, void* stream);
+int wl_step_stage_b(wl_sim* sim, const uint8_t* d_term_bits, const uint8_t* d_extra_terminated, const uint8_t* d_extra_truncated,
+                    float* d_obs, uint8_t* d_terminated, uint8_t* d_truncated, float* d_log, int64_t step_counter, void* stream);
+
 /* ---- the step before env.step(): the policy ---------------------------------------------------------
  * alg.act(obs) of the rollout loop (modified_rsl_rl_runner.py:72; rsl_rl ActorCritic with the reference's sizes,
  * drifting/config/agents/mushr/rsl_rl_ppo_cfg.py:12-17: actor and critic 64x64 ELU MLPs, Gaussian head with a learned

@@ -70,3 +70,23 @@ def test_unknown_term_fails_loudly(ref_cfgs):
     cfg.rewards.side_slip = RewardTermCfg(func=lambda env: 0, weight=1.0)
     with pytest.raises(NotImplementedError):
         spec_from_reference_cfg(cfg)
+
+
+def test_unknown_term_becomes_host_side_term_when_allowed(ref_cfgs):
+    """allow_python_terms: the cfg's own function is kept and registered as a Python term of the staged step."""
+    D, _, _ = ref_cfgs
+    from wheeledlab_b200.compat import spec_from_reference_cfg
+    from isaaclab.managers import RewardTermCfg, TerminationTermCfg
+    cfg = D.MushrDriftRLEnvCfg()
+    f = lambda env, k=1.0: 0
+    g = lambda env: 0
+    cfg.rewards.my_bonus = RewardTermCfg(func=f, weight=3.0, params={"k": 2.0})
+    cfg.terminations.my_stop = TerminationTermCfg(func=g)
+    cfg.rewards._cfg_fields = list(getattr(cfg.rewards, "_cfg_fields", [])) + ["my_bonus"] if hasattr(cfg.rewards, "_cfg_fields") else None
+    cfg.terminations._cfg_fields = list(getattr(cfg.terminations, "_cfg_fields", [])) + ["my_stop"] if hasattr(cfg.terminations, "_cfg_fields") else None
+    with pytest.raises(NotImplementedError):
+        spec_from_reference_cfg(cfg)
+    s = spec_from_reference_cfg(cfg, allow_python_terms=True)
+    assert s.python_reward_terms == [("my_bonus", f, 3.0, {"k": 2.0})]
+    assert s.python_termination_terms == [("my_stop", g, False, {})]
+    assert "my_bonus" not in s.reward_names and len(s.reward_names) == 7      # built-in slots untouched

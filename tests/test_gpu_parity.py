@@ -575,3 +575,80 @@ def test_fused_policy_rollout_graph_equals_eager_act_steps():
     with pytest.raises(wl.WlError):                      # 689-wide elevation observations are not supported by the fused policy
         e = wl.WheeledSim(wl.elevation_task(num_envs=8, seed=1, terrain="procedural"), "cuda:0")
         act_step(e, torch.zeros((8, 689), device=dev), blob, act, mean, lp, val, out, None, 0)
+
+
+@pytest.mark.parametrize("task", ["drift", "elevation", "visual"])
+def test_staged_step_equals_fused_step(task):
+    """wl_step_stage_a + wl_step_stage_b (the cut for host-side Python terms) == wl_step, bit for bit, incl. resets,
+    episode log, curriculum and the device counter."""
+    _need_gpu()
+    import wheeledlab_b200 as wl
+    n = 333
+    mk = {"drift": lambda: wl.drift_task(num_envs=n, seed=17), "elevation": lambda: wl.elevation_task(num_envs=n, seed=17),
+          "visual": lambda: wl.visual_task(num_envs=n, seed=17)}[task]
+    a, b = wl.WheeledSim(mk(), "cuda:0"), wl.WheeledSim(mk(), "cuda:0")
+    for s_ in (a, b):
+        s_.startup(); s_.reset(None, 0)
+    a.set_kernel_variant(1)                                # same thread-per-env code path as the staged kernels (variants are bit-identical anyway)
+    la, lb = torch.zeros(16, device="cuda"), torch.zeros(16, device="cuda")
+    steps = 520 if task == "drift" else 230                # crosses episode ends (250 / 200 steps) -> time-out resets + curriculum
+    for t in range(steps):
+        act = a.synth_actions(t)
+        obs, rew, term, trunc = a.step(act, t, log=la)
+        rew_b, bits = b.step_stage_a(act, t)
+        obs_b, term_b, trunc_b = b.step_stage_b(bits, t, log=lb)
+        assert torch.equal(rew, rew_b) and torch.equal(obs, obs_b), (task, t)
+        assert torch.equal(term, term_b) and torch.equal(trunc, trunc_b), (task, t)
+        assert torch.allclose(la, lb, rtol=1e-4, atol=1e-6), (task, t)    # float atomics across warps: order is not fixed
+    assert torch.equal(a.groups, b.groups) and torch.equal(a.rew_weight, b.rew_weight)
+
+
+def test_python_terms_run_between_rewards_and_reset():
+    """env.add_reward_term / add_termination_term / add_observation_term: IsaacLab term semantics on the staged step."""
+    _need_gpu()
+    import wheeledlab_b200 as wl
+    n = 257
+    plain = wl.ManagerBasedRLEnv(wl.drift_task(num_envs=n, seed=23), device="cuda:0")
+    env = wl.ManagerBasedRLEnv(wl.drift_task(num_envs=n, seed=23), device="cuda:0")
+    seen = []
+
+    def forward_speed(e, scale=1.0):
+        v = e.scene["robot"].data.root_lin_vel_b[:, 0] * scale
+        seen.append(v.clone())
+        return v
+
+    env.add_reward_term("forward_speed", forward_speed, weight=2.0, params={"scale": 0.5})
+    env.add_observation_term("speed_obs", lambda e: e.scene["robot"].data.root_lin_vel_w)
+    o0, _ = env.reset(); p0, _ = plain.reset()
+    assert o0["policy"].shape == (n, 17) and torch.equal(o0["policy"][:, :14], p0["policy"])
+    g = torch.Generator(device="cuda").manual_seed(0)
+    sums, n_done = torch.zeros(n, device="cuda"), 0
+    for t in range(300):                                   # crosses the 250-step time-out: episode log of the Python term
+        act = torch.rand((n, 2), device="cuda", generator=g) * 2 - 1
+        o, r, te, tr, ex = env.step(act)
+        po, pr, pte, ptr, pex = plain.step(act)
+        assert torch.equal(o["policy"][:, :14], po["policy"]) and torch.equal(te, pte) and torch.equal(tr, ptr)
+        assert torch.equal(r, pr + seen[-1] * (2.0 * env.step_dt)), t           # built-in total + func * weight * dt
+        assert torch.equal(o["policy"][:, 14:], env.scene["robot"].data.root_lin_vel_w)
+        for k in pex["log"]:
+            assert torch.allclose(ex["log"][k], pex["log"][k], rtol=1e-4, atol=1e-6), (t, k)    # float atomics: summation order
+        sums += seen[-1] * (2.0 * env.step_dt)
+        done = te | tr
+        expect = (sums * done).sum() / done.sum().clamp(min=1) / env.max_episode_length_s       # RewardManager.reset logging
+        assert torch.allclose(ex["log"]["Episode_Reward/forward_speed"], expect, rtol=1e-5, atol=1e-7), t
+        sums[done] = 0.0
+        n_done += int(done.sum())
+    assert n_done >= n                                     # every env finished at least one episode (250-step time-out)
+    # a Python termination term resets the env in the same step, before the observation is taken
+    env3 = wl.ManagerBasedRLEnv(wl.drift_task(num_envs=n, seed=23), device="cuda:0")
+    env3.add_termination_term("short_episode", lambda e: e.episode_length_buf >= 7)
+    env3.reset()
+    for t in range(7):
+        pre = env3.episode_length_buf.clone()
+        o, r, te, tr, ex = env3.step(torch.zeros((n, 2), device="cuda"))
+    fire = pre + 1 >= 7                                    # (an env a built-in term reset earlier is younger)
+    assert int(fire.sum()) >= n - 8 and bool(te[fire].all()) and not bool(tr.any())
+    assert bool((env3.episode_length_buf[fire] == 0).all())
+    assert int(ex["log"]["Episode_Termination/short_episode"]) == int(fire.sum())
+    with pytest.raises(NotImplementedError):
+        env3.step_host(torch.zeros((n, 2)).pin_memory())

@@ -73,7 +73,7 @@ def _lower_common(cfg, spec: T.TaskSpec):
     spec._curriculum_dirty = True
 
 
-def _lower_rewards(cfg, spec, table, handlers):
+def _lower_rewards(cfg, spec, table, handlers, allow_python_terms=False):
     c = spec.cfg
     names = [None] * len(table)
     for k in range(T_MAX := 8):
@@ -81,7 +81,11 @@ def _lower_rewards(cfg, spec, table, handlers):
     for name, term in _fields(cfg.rewards):
         fn = _ALIASES.get(_fname(term), _fname(term))
         if fn not in table:
-            raise NotImplementedError(f"reward term {name} -> {fn} is not implemented by the fused step")
+            if allow_python_terms:      # the reference's own Python function, evaluated between the two halves of the staged step
+                spec.python_reward_terms.append((name, term.func, float(term.weight), dict(term.params or {})))
+                continue
+            raise NotImplementedError(f"reward term {name} -> {fn} is not implemented by the fused step "
+                                      f"(pass allow_python_terms=True to run it as a host-side term)")
         slot = table[fn]
         names[slot] = name
         c.rew_weight[slot] = float(term.weight)
@@ -96,8 +100,10 @@ def _lower_rewards(cfg, spec, table, handlers):
     T.set_curriculum(c, names, spec.curriculum)     # reward slots are known now
 
 
-def spec_from_reference_cfg(cfg, env_id_offset: int = 0) -> T.TaskSpec:
-    """Build the TaskSpec for a reference env-cfg instance (Drift / F1Tenth drift / Elevation)."""
+def spec_from_reference_cfg(cfg, env_id_offset: int = 0, allow_python_terms: bool = False) -> T.TaskSpec:
+    """Build the TaskSpec for a reference env-cfg instance (Drift / F1Tenth drift / Elevation).  With
+    ``allow_python_terms`` reward / termination terms the kernels do not implement are kept as host-side terms that call
+    the cfg's own function (staged step, env.add_reward_term); otherwise they raise."""
     num_envs = int(cfg.scene.num_envs)
     seed = int(cfg.seed) if getattr(cfg, "seed", None) is not None else 42
     reward_funcs = {_ALIASES.get(_fname(t), _fname(t)) for _, t in _fields(cfg.rewards)}
@@ -130,14 +136,16 @@ def spec_from_reference_cfg(cfg, env_id_offset: int = 0) -> T.TaskSpec:
             "side_slip": h_slip, "vel_dist": h_vel, "cross_track_dist": h_ctd,
             "turn_left_go_right": lambda p: setattr(c, "tlgr_ang_vel_thresh", p.get("ang_vel_thresh", math.pi / 4)),
             "energy_through_turn": lambda p: setattr(c, "energy_straight", p["straight"]),
-        })
+        }, allow_python_terms)
         for name, term in _fields(cfg.terminations):
             fn = _fname(term)
             if fn == "cart_off_track":
                 p = term.params
                 c.trk_straight, c.trk_corner_in, c.trk_corner_out = p["straight"], p["corner_in_radius"], p["corner_out_radius"]
             elif fn != "time_out":
-                raise NotImplementedError(f"termination term {name} -> {fn}")
+                if not allow_python_terms:
+                    raise NotImplementedError(f"termination term {name} -> {fn} (pass allow_python_terms=True to run it host-side)")
+                spec.python_termination_terms.append((name, term.func, bool(getattr(term, "time_out", False)), dict(term.params or {})))
         for name, term in events.items():
             fn, p = _fname(term), term.params
             if fn == "reset_root_state_along_track":
@@ -172,16 +180,16 @@ def spec_from_reference_cfg(cfg, env_id_offset: int = 0) -> T.TaskSpec:
     if "goal_progress_rate" in reward_funcs:
         spec = T.elevation_task(num_envs=num_envs, seed=seed, env_id_offset=env_id_offset)
         _lower_common(cfg, spec)
-        _lower_rewards(cfg, spec, _ELEV_REWARDS, {})
+        _lower_rewards(cfg, spec, _ELEV_REWARDS, {}, allow_python_terms)
         return spec
     raise NotImplementedError(f"env cfg {type(cfg).__name__} is not one of the registered Drift / Elevation tasks")
 
 
-def env_from_reference_cfg(cfg, render_mode=None, device=None, **kwargs):
+def env_from_reference_cfg(cfg, render_mode=None, device=None, allow_python_terms: bool = False, **kwargs):
     """Entry point used by ``shims/isaaclab/envs:ManagerBasedRLEnv`` (gym kwargs: cfg=<env cfg>)."""
     from .env import ManagerBasedRLEnv
     dev = device or getattr(getattr(cfg, "sim", None), "device", None) or "cuda:0"
-    env = ManagerBasedRLEnv(spec_from_reference_cfg(cfg), render_mode=render_mode, device=dev)
+    env = ManagerBasedRLEnv(spec_from_reference_cfg(cfg, allow_python_terms=allow_python_terms), render_mode=render_mode, device=dev)
     env.cfg = cfg                                   # writer.log_config(self.env.cfg, ...) (modified_rsl_rl_runner.py:42-44)
     if not hasattr(cfg, "is_finite_horizon"):
         cfg.is_finite_horizon = False

@@ -115,11 +115,16 @@ __device__ __forceinline__ void log_finalize(const wl_config& c, wl_globals* __r
 #ifndef WL_STEP_MIN_BLOCKS
 #define WL_STEP_MIN_BLOCKS 4      // 4 CTAs x 128 threads / SM (<= 128 registers); see profiles/ for the occupancy A/B
 #endif
-template <int TASK>
+// STAGE 0: the whole env.step.  STAGE 1 / 2: the same code cut after section E (wl_step_stage_a / wl_step_stage_b), so that
+// host-side (Python) reward and termination terms can run between "rewards" and "reset" exactly where the reference's
+// managers would call them; the state round-trips through HBM losslessly, so 1 + 2 == 0 bit for bit.
+struct StageIO { uint8_t* tmask; const uint8_t* extra_terminated; const uint8_t* extra_truncated; };
+template <int TASK, int STAGE = 0>
 __global__ void __launch_bounds__(128, WL_STEP_MIN_BLOCKS)
 wl_step_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st, wl_globals* __restrict__ gl, Terrain T,
                const float2* __restrict__ action, float* __restrict__ obs, float* __restrict__ rew,
-               uint8_t* __restrict__ terminated_o, uint8_t* __restrict__ truncated_o, float* __restrict__ d_log, uint32_t t_arg) {
+               uint8_t* __restrict__ terminated_o, uint8_t* __restrict__ truncated_o, float* __restrict__ d_log, uint32_t t_arg,
+               StageIO sio = StageIO{nullptr, nullptr, nullptr}) {
     constexpr bool ELEV = (TASK == WL_TASK_ELEVATION), VIS = (TASK == WL_TASK_VISUAL);
     const int n = c.num_envs;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -131,7 +136,17 @@ wl_step_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st, wl_
     // live reward weights: issued with the state loads so their latency hides behind the integrator
     const float4 rw0 = __ldg(reinterpret_cast<const float4*>(gl->rew_weight)), rw1 = __ldg(reinterpret_cast<const float4*>(gl->rew_weight) + 1);
     const float wts[WL_MAX_REW_TERMS] = {rw0.x, rw0.y, rw0.z, rw0.w, rw1.x, rw1.y, rw1.z, rw1.w};
-    if (i < n) {
+    if (STAGE == 2) {
+        if (i < n) {
+            load_env(st, n, i, e, ELEV);
+            tmask = sio.tmask[i];
+            if (sio.extra_truncated && sio.extra_truncated[i]) tmask |= 1u;            // host-side time-out style term
+            if (sio.extra_terminated && sio.extra_terminated[i]) tmask |= 0x80u;       // host-side termination term
+            terminated_o[i] = (tmask & ~1u) ? 1 : 0;
+            truncated_o[i] = (tmask & 1u) ? 1 : 0;
+            done = tmask != 0u;
+        }
+    } else if (i < n) {
         load_env(st, n, i, e, ELEV);
         // A. action manager
         float2 a = action[i];
@@ -181,10 +196,16 @@ wl_step_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st, wl_
             }
         }
         rew[i] = total;
+        if (STAGE == 1) {                    // cut: state (with this step's episode sums) back to HBM, term bits for stage 2
+            sio.tmask[i] = (uint8_t)tmask;
+            store_env(st, n, i, e, ELEV);
+            return;
+        }
         terminated_o[i] = (tmask & ~1u) ? 1 : 0;
         truncated_o[i] = (tmask & 1u) ? 1 : 0;
         done = tmask != 0u;
     }
+    if (STAGE == 1) return;
     // F. auto-reset + per-step episode log (warp-shuffle reduction over the finished envs)
     log_accumulate(gl->acc, done, tmask, e.sums);
     if (i < n) {
@@ -1076,6 +1097,47 @@ int wl_step(wl_sim* sim, const float* d_action, float* d_obs, float* d_rew, uint
         return WL_OK;
     }
     WL_LAUNCH_CHECK(sim, "wl_step_kernel");
+    return WL_OK;
+}
+
+// ---- env.step cut in two (host-side reward / termination terms run in between) ----------------------------------------
+}   // extern "C" (templates have C++ linkage)
+template <int STAGE>
+static int launch_stage(wl_sim* sim, const float2* act, float* d_obs, float* d_rew, uint8_t* d_terminated, uint8_t* d_truncated,
+                        float* d_log, uint32_t t, StageIO sio, cudaStream_t cs) {
+    const int n = sim->cfg.num_envs, bs = pick_block(n), grid = (n + bs - 1) / bs;
+    Terrain T{sim->hf};
+    switch (sim->cfg.task) {
+    case WL_TASK_ELEVATION:
+        wl_step_kernel<WL_TASK_ELEVATION, STAGE><<<grid, bs, 0, cs>>>(sim->cfg, sim->state, sim->globals, T, act, d_obs, d_rew, d_terminated, d_truncated, d_log, t, sio);
+        break;
+    case WL_TASK_VISUAL:
+        wl_step_kernel<WL_TASK_VISUAL, STAGE><<<grid, bs, 0, cs>>>(sim->cfg, sim->state, sim->globals, T, act, d_obs, d_rew, d_terminated, d_truncated, d_log, t, sio);
+        break;
+    default:
+        wl_step_kernel<WL_TASK_DRIFT, STAGE><<<grid, bs, 0, cs>>>(sim->cfg, sim->state, sim->globals, T, act, d_obs, d_rew, d_terminated, d_truncated, d_log, t, sio);
+    }
+    WL_LAUNCH_CHECK(sim, STAGE == 1 ? "wl_step_kernel<stage a>" : "wl_step_kernel<stage b>");
+    return WL_OK;
+}
+extern "C" {
+
+int wl_step_stage_a(wl_sim* sim, const float* d_action, float* d_rew, uint8_t* d_term_bits, int64_t step_counter, void* stream) {
+    if (!sim || !d_action || !d_rew || !d_term_bits) return fail(WL_EINVAL, "wl_step_stage_a: null argument");
+    if ((uintptr_t)d_action & 7u) return fail(WL_EINVAL, "wl_step_stage_a: action must be 8-byte aligned");
+    if (step_counter < 0) return fail(WL_EINVAL, "wl_step_stage_a: the staged step takes the host's step counter");
+    return launch_stage<1>(sim, reinterpret_cast<const float2*>(d_action), nullptr, d_rew, nullptr, nullptr, nullptr, (uint32_t)step_counter,
+                           StageIO{d_term_bits, nullptr, nullptr}, (cudaStream_t)stream);
+}
+
+int wl_step_stage_b(wl_sim* sim, const uint8_t* d_term_bits, const uint8_t* d_extra_terminated, const uint8_t* d_extra_truncated,
+                    float* d_obs, uint8_t* d_terminated, uint8_t* d_truncated, float* d_log, int64_t step_counter, void* stream) {
+    if (!sim || !d_term_bits || !d_obs || !d_terminated || !d_truncated) return fail(WL_EINVAL, "wl_step_stage_b: null argument");
+    if (step_counter < 0) return fail(WL_EINVAL, "wl_step_stage_b: the staged step takes the host's step counter");
+    if (int rc = launch_stage<2>(sim, nullptr, d_obs, nullptr, d_terminated, d_truncated, d_log, (uint32_t)step_counter,
+                                 StageIO{const_cast<uint8_t*>(d_term_bits), d_extra_terminated, d_extra_truncated}, (cudaStream_t)stream))
+        return rc;
+    if (sim->cfg.task == WL_TASK_ELEVATION) return launch_scan(sim, d_obs, (cudaStream_t)stream);
     return WL_OK;
 }
 

@@ -32,21 +32,28 @@ class _LazyLog(dict):
     wrote; the views are only created when somebody reads them (the train loop appends the dict every step and reads it
     once per iteration, modified_rsl_rl_runner.py:95-98)."""
 
-    def __init__(self, row: torch.Tensor, index: dict):
+    def __init__(self, row: torch.Tensor, index: dict, extra: dict | None = None):
         super().__init__((k, None) for k in index)
         self._row, self._index = row, index
+        self._extra = extra or {}                # entries of host-side (Python) terms: already 0-dim device tensors
+        for k in self._extra:
+            dict.__setitem__(self, k, None)
 
     def __getitem__(self, k):
+        if k in self._extra:
+            return self._extra[k]
         return self._row[self._index[k]]
 
     def get(self, k, default=None):
+        if k in self._extra:
+            return self._extra[k]
         return self._row[self._index[k]] if k in self._index else default
 
     def items(self):
-        return [(k, self[k]) for k in self._index]
+        return [(k, self[k]) for k in list(self._index) + list(self._extra)]
 
     def values(self):
-        return [self[k] for k in self._index]
+        return [self[k] for k in list(self._index) + list(self._extra)]
 
 
 class RewardTermCfgView:
@@ -137,7 +144,7 @@ class ObservationManager:
         env = self._env
         obs = env.sim.observe(env.common_step_counter, self._calls)
         self._calls += 1
-        return {"policy": obs}
+        return {"policy": env._append_py_obs(obs)}
 
 
 class _RobotData:
@@ -262,6 +269,13 @@ class ManagerBasedRLEnv:
         self._host_io = None
         self._ring = None
         self.host_transport = "zero_copy"        # or "copy": staged H2D / D2H copies (wl_step_host)
+        # host-side (Python) MDP terms: evaluated between the two halves of the staged step (see add_reward_term)
+        self._py_rewards, self._py_terms, self._py_obs = [], [], []
+        self._py_sums = {}
+        for name, func, weight, params in self.spec.python_reward_terms:
+            self.add_reward_term(name, func, weight, params)
+        for name, func, time_out, params in self.spec.python_termination_terms:
+            self.add_termination_term(name, func, time_out, params)
         # event_manager.apply(mode="startup")
         self.sim.startup()
         self._needs_reset = True
@@ -316,11 +330,87 @@ class ManagerBasedRLEnv:
                 mask |= 1 << k
         return mask
 
+    # -- host-side (Python) MDP terms: the reference's extension mechanism -----------------------------------------
+    def add_reward_term(self, name: str, func, weight: float, params: dict | None = None):
+        """Register ``func(env, **params) -> [N]`` as a reward term (IsaacLab RewardTermCfg semantics: contributes
+        func * weight * step_dt, accumulated per episode and logged as Episode_Reward/<name>).  It runs on the
+        post-physics, PRE-reset state, exactly where ManagerBasedRLEnv.step calls the reward manager: the env switches
+        to the staged step (wl_step_stage_a -> Python terms -> wl_step_stage_b)."""
+        self._py_rewards.append(SimpleNamespace(name=name, func=func, weight=float(weight), params=dict(params or {})))
+        self._py_sums[name] = torch.zeros(self.num_envs, dtype=torch.float32, device=self.device)
+        self.reward_manager.python_terms = [t.name for t in self._py_rewards]
+
+    def add_termination_term(self, name: str, func, time_out: bool = False, params: dict | None = None):
+        """Register ``func(env, **params) -> [N] bool`` as a termination term (TerminationTermCfg semantics; evaluated
+        before the rewards, OR-ed into terminated / time_outs, resets the env in the same step)."""
+        self._py_terms.append(SimpleNamespace(name=name, func=func, time_out=bool(time_out), params=dict(params or {})))
+        self.termination_manager.python_terms = [t.name for t in self._py_terms]
+
+    def add_observation_term(self, name: str, func, params: dict | None = None):
+        """Register ``func(env, **params) -> [N, k]``; appended to the policy observation (after the built-in terms)."""
+        term = SimpleNamespace(name=name, func=func, params=dict(params or {}))
+        k = int(func(self, **term.params).reshape(self.num_envs, -1).shape[1])
+        self._py_obs.append(term)
+        d = self.observation_manager.group_obs_dim["policy"][0] + k
+        self.observation_manager.group_obs_dim["policy"] = (d,)
+        self.single_observation_space = {"policy": _Box(-math.inf, math.inf, (d,))}
+        self.observation_space = {"policy": _Box(-math.inf, math.inf, (self.num_envs, d))}
+
+    def _append_py_obs(self, obs: torch.Tensor) -> torch.Tensor:
+        if not self._py_obs:
+            return obs
+        return torch.cat([obs] + [t.func(self, **t.params).reshape(self.num_envs, -1).to(torch.float32) for t in self._py_obs], dim=1)
+
+    def _step_staged(self, action: torch.Tensor):
+        """env.step with Python terms in the loop: stage a (A-E) -> terminations -> rewards -> stage b (F-I)."""
+        t = self.common_step_counter
+        sim, tm = self.sim, self.termination_manager
+        rew, bits = sim.step_stage_a(action, t)
+        built_in_to = (bits & 1).bool()
+        built_in_term = (bits & 0xFE).bool()
+        extra_term = extra_to = None
+        fired = {}
+        for term in self._py_terms:
+            v = term.func(self, **term.params).to(torch.bool)
+            fired[term.name] = v
+            if term.time_out:
+                extra_to = v if extra_to is None else (extra_to | v)
+            else:
+                extra_term = v if extra_term is None else (extra_term | v)
+        # what reward terms such as is_terminated_term see (TerminationManager.compute runs before RewardManager.compute)
+        tm.terminated = built_in_term if extra_term is None else (built_in_term | extra_term)
+        tm.time_outs = built_in_to if extra_to is None else (built_in_to | extra_to)
+        for term in self._py_rewards:
+            if term.weight == 0.0:
+                continue
+            val = term.func(self, **term.params).to(torch.float32) * (term.weight * self.step_dt)
+            rew += val
+            self._py_sums[term.name] += val
+        log = torch.empty(16, dtype=torch.float32, device=self.device) if self.log_episode_info else None
+        obs, term_u8, trunc_u8 = sim.step_stage_b(bits, t, extra_term, extra_to, log=log)
+        self.common_step_counter = t + 1
+        terminated, truncated = term_u8.view(torch.bool), trunc_u8.view(torch.bool)
+        tm.terminated, tm.time_outs = terminated, truncated
+        if log is not None:
+            done = terminated | truncated
+            cnt = done.sum().clamp(min=1).to(torch.float32)
+            extra = {}
+            for term in self._py_rewards:                        # RewardManager.reset: mean episodic sum / max_episode_length_s
+                sums = self._py_sums[term.name]
+                extra["Episode_Reward/" + term.name] = (sums * done).sum() / cnt / self.max_episode_length_s
+                sums.masked_fill_(done, 0.0)
+            for term in self._py_terms:
+                extra["Episode_Termination/" + term.name] = (fired[term.name] & done).sum()
+            self.extras["log"] = _LazyLog(log, self._log_index, extra)
+        return {"policy": self._append_py_obs(obs)}, rew, terminated, truncated, self.extras
+
     def step(self, action: torch.Tensor):
         if self._needs_reset:
             self.reset()
         if action.dtype != torch.float32 or not action.is_contiguous() or str(action.device) != self.device:
             action = action.to(self.device, torch.float32).contiguous()
+        if self._py_rewards or self._py_terms:
+            return self._step_staged(action)
         t = self.common_step_counter
         log = torch.empty(16, dtype=torch.float32, device=self.device) if self.log_episode_info else None
         obs, rew, term_u8, trunc_u8 = self.sim.step(action, t, log=log)
@@ -332,7 +422,7 @@ class ManagerBasedRLEnv:
         tm.terminated, tm.time_outs = terminated, truncated
         if log is not None:
             self.extras["log"] = self._episode_log(log)
-        return {"policy": obs}, rew, terminated, truncated, self.extras
+        return {"policy": self._append_py_obs(obs)}, rew, terminated, truncated, self.extras
 
     def _episode_log(self, log: torch.Tensor):
         """extras["log"] (RewardManager/TerminationManager.reset): lazy views of the row the step
@@ -344,6 +434,8 @@ class ManagerBasedRLEnv:
         does H2D(actions) -> fused step -> D2H(reward, terminated, truncated) -> sync.  Returns
         (obs_dict [device], rew [pinned host], terminated [pinned host], truncated [pinned host], extras); the host
         result views are overwritten by the next step_host call."""
+        if self._py_rewards or self._py_terms:
+            raise NotImplementedError("step_host: host-side Python terms need the staged step (use env.step)")
         if self._needs_reset:
             self.reset()
         if self._host_io is None:

@@ -160,6 +160,32 @@ class WheeledSim:
                              C.c_void_p(slab.terminated.data_ptr()), C.c_void_p(slab.truncated.data_ptr()),
                              C.c_void_p(logs.data_ptr()), step_counter, _stream_ptr(self.device)), "wl_rollout")
 
+    def step_stage_a(self, action: torch.Tensor, step_counter: int, rew: torch.Tensor | None = None, term_bits: torch.Tensor | None = None):
+        """Sections A-E of env.step (wl_step_stage_a): integrator + built-in terms; leaves the PRE-RESET state in the buffer.
+        Returns (built-in reward [N] f32, termination bits [N] u8: bit j = built-in term j)."""
+        n, dev = self.num_envs, self.device
+        rew = rew if rew is not None else torch.empty(n, dtype=torch.float32, device=dev)
+        term_bits = term_bits if term_bits is not None else torch.empty(n, dtype=torch.uint8, device=dev)
+        check(lib.wl_step_stage_a(self._h, C.c_void_p(action.data_ptr()), C.c_void_p(rew.data_ptr()), C.c_void_p(term_bits.data_ptr()),
+                                  step_counter, _stream_ptr(dev)), "wl_step_stage_a")
+        return rew, term_bits
+
+    def step_stage_b(self, term_bits: torch.Tensor, step_counter: int, extra_terminated: torch.Tensor | None = None,
+                     extra_truncated: torch.Tensor | None = None, out=None, log: torch.Tensor | None = None):
+        """Sections F-I (wl_step_stage_b): episode log, auto-reset of done envs (built-in bits | extras), commands /
+        pushes, observations.  extras: [N] u8/bool or None.  Returns (obs, terminated u8, truncated u8)."""
+        n, dev = self.num_envs, self.device
+        if out is None:
+            out = (torch.empty((n, self.obs_dim), dtype=torch.float32, device=dev), torch.empty(n, dtype=torch.uint8, device=dev),
+                   torch.empty(n, dtype=torch.uint8, device=dev))
+        obs, term, trunc = out
+        u8 = lambda x: None if x is None else C.c_void_p((x.view(torch.uint8) if x.dtype == torch.bool else x).data_ptr())
+        check(lib.wl_step_stage_b(self._h, C.c_void_p(term_bits.data_ptr()), u8(extra_terminated), u8(extra_truncated),
+                                  C.c_void_p(obs.data_ptr()), C.c_void_p(term.data_ptr()), C.c_void_p(trunc.data_ptr()),
+                                  C.c_void_p(log.data_ptr()) if log is not None else None, step_counter, _stream_ptr(dev)),
+              "wl_step_stage_b")
+        return obs, term, trunc
+
     def observe(self, step_counter: int, call_idx: int = 0, out: torch.Tensor | None = None):
         obs = out if out is not None else torch.empty((self.num_envs, self.obs_dim), dtype=torch.float32, device=self.device)
         check(lib.wl_observe(self._h, C.c_void_p(obs.data_ptr()), step_counter, call_idx, _stream_ptr(self.device)),

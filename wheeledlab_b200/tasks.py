@@ -61,6 +61,9 @@ class TaskSpec:
     joint_names: list = field(default_factory=list)
     heightfield: object = None                                  # float32 [ny, pitch] (elevation) / aux blob (visual)
     traversability: object = None                               # bool [rows, cols] (visual)
+    # host-side (Python) MDP terms evaluated between the two halves of the staged step (env.add_*_term):
+    python_reward_terms: list = field(default_factory=list)     # [(name, func, weight, params)]
+    python_termination_terms: list = field(default_factory=list)  # [(name, func, time_out, params)]
 
     @property
     def step_dt(self) -> float:
