@@ -80,7 +80,9 @@ extern "C" {
 /* visual reward term slots (visual/mushr_visual_env_cfg.py:376-387) */
 #define WL_VR_TRAVERSABLE 0
 #define WL_VR_FORWARD_VEL 1
-#define WL_OBS_DIM_VISUAL 8    /* base_lin_vel(3) base_ang_vel(3) last_action(2); the camera term is out of scope */
+#define WL_OBS_DIM_VISUAL 8    /* base_lin_vel(3) base_ang_vel(3) last_action(2); preceded by vis_cam_w*(vis_cam_h-vis_cam_row0)
+                                * camera floats when vis_cam != 0 (PolicyCfg order, mushr_visual_env_cfg.py:45-52) */
+#define WL_CAM_MAX_PIXELS 4096 /* kept pixels per env (80 x 40 = 3200 in the reference cfg) */
 
 /* error codes */
 #define WL_OK          0
@@ -237,6 +239,26 @@ extern "C" {
     XS(float, f32, vis_width)         /* num_rows*row_spacing = 250, :113-114 */                   \
     XS(float, f32, vis_height)                                                                     \
     XS(float, f32, vis_spawn_z)       /* 0.1, utils/__init__.py:188-202 + InitialPoseCfg */        \
+    /* --- visual task, camera term (software pinhole camera over the 2-colour plane) --- */ \
+    XS(int32_t, i32, vis_cam)         /* 0 off, 1 camera_data_rgb_flattened, 2 ..._aug (mdp_sensors/observations.py:64-87) */ \
+    XS(int32_t, i32, vis_cam_w)       /* 80, :234 */                                                \
+    XS(int32_t, i32, vis_cam_h)       /* 60, :233 */                                                \
+    XS(int32_t, i32, vis_cam_row0)    /* H // 3: rows [row0, H) are kept, observations.py:67,78 */  \
+    XS(float, f32, vis_cam_fx)        /* focal_length * W / horizontal_aperture (pixels), :236-239 */ \
+    XS(float, f32, vis_cam_fy)        /* focal_length * H / vertical_aperture */                    \
+    XS(float, f32, vis_cam_cx)        /* W / 2 */                                                   \
+    XS(float, f32, vis_cam_cy)        /* H / 2 */                                                   \
+    XA(float, f32, vis_cam_pos, 3)    /* optical centre in the root frame: camera_link + offset (0.08,0,0), :242 */ \
+    XS(float, f32, vis_cam_bg)        /* colour of what is not the plane mesh (sky, black base plane): 0 */ \
+    XS(float, f32, vis_mesh_x0)       /* first mesh vertex: -width/2 - row_spacing/2, utils/__init__.py:26-28 */ \
+    XS(float, f32, vis_mesh_y0)                                                                    \
+    XS(float, f32, vis_mesh_dx)       /* vertex pitch: width / (num_rows - 1) (np.linspace), quirk: != row_spacing */ \
+    XS(float, f32, vis_mesh_dy)                                                                    \
+    XS(float, f32, vis_aug_brightness) /* ColorJitter(brightness=0.8, contrast=0.2, saturation=0.8, hue=0.5), observations.py:21 */ \
+    XS(float, f32, vis_aug_contrast)                                                               \
+    XS(float, f32, vis_aug_saturation)                                                             \
+    XS(float, f32, vis_aug_hue)                                                                    \
+    XA(float, f32, vis_aug_sigma, 2)  /* GaussianBlur(5, sigma=(0.1, 5.0)), observations.py:23 */  \
     /* --- derived constants: filled by wl_config_finalize() (wl_create calls it on its copy); fp32,   \
      *     formed once on the host so the kernels carry no per-step divisions for them --- */        \
     XS(float, f32, d_h)               /* sim_dt / substeps */                                      \
@@ -390,6 +412,12 @@ int wl_set_scan_tma(wl_sim* sim, int32_t use_tma);
 int32_t wl_obs_dim(const wl_sim* sim);
 /* number of kernel launches issued through this handle since creation */
 int64_t wl_launch_count(const wl_sim* sim);
+
+/* Visual task camera term alone (wl_step / wl_observe launch it themselves when cfg.vis_cam != 0): fills the first
+ * vis_cam_w * (vis_cam_h - vis_cam_row0) floats of every observation row from the current state.  d_aug = NULL draws the
+ * ColorJitter / GaussianBlur parameters from the generator (one draw per call, like torchvision on a batch); otherwise
+ * 9 floats on the device: brightness, contrast, saturation, hue, sigma, order[4] (fn_idx of ColorJitter.get_params). */
+int wl_camera(wl_sim* sim, float* d_obs, int64_t step_counter, const float* d_aug, void* stream);
 
 /* ---- env.step() cut in two, for HOST-SIDE (Python) reward / termination terms ----------------------------
  * IsaacLab's managers call user terms between "physics + built-in terms" and "reset" (ManagerBasedRLEnv.step: reward and

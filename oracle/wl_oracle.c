@@ -63,6 +63,8 @@ static inline real r_clamp(real x, real lo, real hi) { return r_min(r_max(x, lo)
 #define RNG_STARTUP 6u
 #define RNG_OBS_EXTRA 7u
 #define RNG_CMD 8u
+#define RNG_CAM 10u
+#define RNG_CAM_EXTRA 11u
 
 static void philox4x32(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t out[4]) {
     uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
@@ -99,6 +101,7 @@ static real det_atan_ratio(real num, real den) { return atan(num / den); }
 static real det_sin_0_pi(real x) { return sin(x); }
 static real det_atan2(real y, real x) { return atan2(y, x); }
 static real det_log(real x) { return log(x); }
+static real det_exp(real x) { return exp(x); }
 #else
 static void det_sincos(float x, float* s, float* c) {
     float q = floorf(fm(x, 0.63661977236758134f, 0.5f));
@@ -167,6 +170,20 @@ static float det_log(float xin) {
     y = fm(-0.5f, z, y);
     float r = x + y;
     return fm(0.693359375f, fe, r);
+}
+/* exp(x), x <= 0 (cephes expf) */
+static float det_exp(float x) {
+    if (x < -87.0f) return 0.0f;
+    float n = floorf(fm(x, 1.44269504088896341f, 0.5f));
+    float r = fm(-n, 0.693359375f, x);
+    r = fm(n, 2.12194440e-4f, r);
+    float z = r * r;
+    float p = fm(1.9875691500e-4f, r, 1.3981999507e-3f);
+    p = fm(p, r, 8.3334519073e-3f); p = fm(p, r, 4.1665795894e-2f); p = fm(p, r, 1.6666665459e-1f); p = fm(p, r, 5.0000001201e-1f);
+    float y = fm(p, z, r) + 1.0f;
+    uint32_t bits = (uint32_t)((int)n + 127) << 23;
+    float sc; memcpy(&sc, &bits, 4);
+    return y * sc;
 }
 #endif
 static real det_tan(real x) { real s, c; det_sincos(x, &s, &c); return s / c; }
@@ -698,6 +715,110 @@ static void visual_obs(const wlo_env* e, float* obs) {
     obs[6] = (float)r_clamp(e->action[0], K(-1.0), K(1.0)); obs[7] = (float)r_clamp(e->action[1], K(-1.0), K(1.0));
 }
 
+/* ---- visual task, camera term: software pinhole camera over the 2-colour plane mesh ----------------------------------
+ * Follows camera_data_rgb_flattened[_aug] (visual/mdp_sensors/observations.py:64-87): keep rows [H//3, H), (ColorJitter,
+ * GaussianBlur(5),) Grayscale, Normalize(0.5, 0.5), flatten.  The RTX renderer is replaced by a ray / plane intersection
+ * against the coloured mesh of utils/__init__.py:8-89 (unlit albedo; background = vis_cam_bg) -- the rendering model is
+ * builder-defined (parity unpinned); the post-processing is pinned to the reference function by tests/golden. */
+static int vis_cam_floats(const wl_config* c) { return c->vis_cam ? c->vis_cam_w * (c->vis_cam_h - c->vis_cam_row0) : 0; }
+static real cam_gray(real v) { return fm(K(0.114), v, fm(K(0.587), v, K(0.2989) * v)); }
+static real cam_clamp01(real v) { return r_min(r_max(v, K(0.0)), K(1.0)); }
+typedef struct { real v0, v1, w0, w1, w2; } cam_aug_t;
+static cam_aug_t cam_aug_params(const wl_config* c, uint32_t t, uint32_t stream, uint32_t sub, const float* aug, real p) {
+    cam_aug_t A; A.v0 = K(0.0); A.v1 = K(1.0); A.w0 = K(1.0); A.w1 = K(0.0); A.w2 = K(0.0);
+    if (c->vis_cam != 2) return A;
+    real b, ct, sa, sigma; int order[4] = {0, 1, 2, 3};
+    if (aug) {
+        b = (real)aug[0]; ct = (real)aug[1]; sa = (real)aug[2]; sigma = (real)aug[4];
+        for (int k = 0; k < 4; ++k) order[k] = (int)aug[5 + k];
+    } else {
+        uint32_t r[4], q[4];
+        philox4x32(c->seed, 0u, t, stream, 2u * sub, r); philox4x32(c->seed, 0u, t, stream, 2u * sub + 1u, q);
+        b = uniform(r[0], r_max(K(0.0), K(1.0) - (real)c->vis_aug_brightness), K(1.0) + (real)c->vis_aug_brightness);
+        ct = uniform(r[1], r_max(K(0.0), K(1.0) - (real)c->vis_aug_contrast), K(1.0) + (real)c->vis_aug_contrast);
+        sa = uniform(r[2], r_max(K(0.0), K(1.0) - (real)c->vis_aug_saturation), K(1.0) + (real)c->vis_aug_saturation);
+        sigma = uniform(r[3], (real)c->vis_aug_sigma[0], (real)c->vis_aug_sigma[1]);
+        for (int i = 3; i >= 1; --i) {
+            int j = (int)(((uint64_t)q[3 - i] * (uint64_t)(i + 1)) >> 32);
+            int tmp = order[i]; order[i] = order[j]; order[j] = tmp;
+        }
+    }
+    for (int k = 0; k < 4; ++k) {
+        int op = order[k];
+        if (op == 0) { A.v0 = cam_clamp01(b * A.v0); A.v1 = cam_clamp01(b * A.v1); }
+        else if (op == 1) {
+            real m = fm(p, cam_gray(A.v1), (K(1.0) - p) * cam_gray(A.v0));
+            A.v0 = cam_clamp01(fm(ct, A.v0, (K(1.0) - ct) * m)); A.v1 = cam_clamp01(fm(ct, A.v1, (K(1.0) - ct) * m));
+        } else if (op == 2) {
+            A.v0 = cam_clamp01(fm(sa, A.v0, (K(1.0) - sa) * cam_gray(A.v0))); A.v1 = cam_clamp01(fm(sa, A.v1, (K(1.0) - sa) * cam_gray(A.v1)));
+        }
+    }
+    real e1 = det_exp(K(-0.5) / (sigma * sigma)), e2 = (e1 * e1) * (e1 * e1);
+    real S = fm(K(2.0), e1 + e2, K(1.0));
+    A.w0 = K(1.0) / S; A.w1 = e1 / S; A.w2 = e2 / S;
+    return A;
+}
+static int cam_pixel_white(const wl_config* c, const uint8_t* map, const real R[9], const real pc[3], int u, int v) {
+    real xo = ((real)u + K(0.5) - (real)c->vis_cam_cx) / (real)c->vis_cam_fx;
+    real yo = ((real)v + K(0.5) - (real)c->vis_cam_cy) / (real)c->vis_cam_fy;
+    real dx = fm(-R[2], yo, fm(-R[1], xo, R[0]));
+    real dy = fm(-R[5], yo, fm(-R[4], xo, R[3]));
+    real dz = fm(-R[8], yo, fm(-R[7], xo, R[6]));
+    int bg = c->vis_cam_bg >= 0.5f;
+    if (!(dz < K(0.0)) || !(pc[2] > K(0.0))) return bg;
+    real tt = pc[2] / (-dz);
+    if (tt > K(100.0)) return bg;
+    real hx = fm(tt, dx, pc[0]), hy = fm(tt, dy, pc[1]);
+    real fx = r_floor((hx - (real)c->vis_mesh_x0) / (real)c->vis_mesh_dx), fy = r_floor((hy - (real)c->vis_mesh_y0) / (real)c->vis_mesh_dy);
+    if (!(fx >= K(0.0)) || !(fy >= K(0.0)) || !(fx < (real)(c->vis_cols - 1)) || !(fy < (real)(c->vis_rows - 1))) return 0;
+    return map[(size_t)(int)fy * c->vis_cols + (int)fx] != 0;
+}
+/* post-processing of one frame given its white mask [rows*W]: jitter on the class values, separable blur, gray, normalise */
+static void camera_post(const wl_config* c, const uint8_t* white, uint32_t t, uint32_t stream, uint32_t sub, const float* aug, float* out) {
+    const int W = c->vis_cam_w, rows = c->vis_cam_h - c->vis_cam_row0, npix = W * rows;
+    int nw = 0;
+    for (int k = 0; k < npix; ++k) nw += white[k] ? 1 : 0;
+    cam_aug_t A = cam_aug_params(c, t, stream, sub, aug, (real)nw / (real)npix);
+    if (c->vis_cam != 2) {
+        for (int k = 0; k < npix; ++k) out[k] = (float)fm(K(2.0), cam_gray(white[k] ? K(1.0) : K(0.0)), K(-1.0));
+        return;
+    }
+    real* Hb = (real*)malloc(sizeof(real) * (size_t)npix);
+    for (int r = 0; r < rows; ++r)
+        for (int u = 0; u < W; ++u) {
+#define WLO_JV(x_) (white[r * W + ((x_) < 0 ? -(x_) : ((x_) >= W ? 2 * W - 2 - (x_) : (x_)))] ? A.v1 : A.v0)
+            real acc = A.w0 * WLO_JV(u);
+            acc = fm(A.w1, WLO_JV(u - 1) + WLO_JV(u + 1), acc);
+            acc = fm(A.w2, WLO_JV(u - 2) + WLO_JV(u + 2), acc);
+            Hb[r * W + u] = acc;
+#undef WLO_JV
+        }
+    for (int r = 0; r < rows; ++r)
+        for (int u = 0; u < W; ++u) {
+#define WLO_HR(y_) Hb[((y_) < 0 ? -(y_) : ((y_) >= rows ? 2 * rows - 2 - (y_) : (y_))) * W + u]
+            real acc = A.w0 * WLO_HR(r);
+            acc = fm(A.w1, WLO_HR(r - 1) + WLO_HR(r + 1), acc);
+            acc = fm(A.w2, WLO_HR(r - 2) + WLO_HR(r + 2), acc);
+            out[r * W + u] = (float)fm(K(2.0), cam_gray(acc), K(-1.0));
+#undef WLO_HR
+        }
+    free(Hb);
+}
+static void camera_render(const wl_config* c, const uint8_t* map, const wlo_env* e, uint8_t* white) {
+    const int W = c->vis_cam_w, rows = c->vis_cam_h - c->vis_cam_row0;
+    real R[9]; rotmat(e->q, R);
+    real cp[3] = {(real)c->vis_cam_pos[0], (real)c->vis_cam_pos[1], (real)c->vis_cam_pos[2]}, off[3];
+    rot(R, cp, off);
+    real pc[3] = {e->p[0] + off[0], e->p[1] + off[1], e->p[2] + off[2]};
+    for (int r = 0; r < rows; ++r)
+        for (int u = 0; u < W; ++u) white[r * W + u] = (uint8_t)cam_pixel_white(c, map, R, pc, u, c->vis_cam_row0 + r);
+}
+static void camera_obs(const wlo_sim* s, const wlo_env* e, uint32_t t, uint32_t stream, uint32_t sub, const float* aug, float* out) {
+    uint8_t white[WL_CAM_MAX_PIXELS];
+    camera_render(&s->cfg, s->vis_map, e, white);
+    camera_post(&s->cfg, white, t, stream, sub, aug, out);
+}
+
 /* interval pushes, mushr_drift_env_cfg.py:121-143; push_by_setting_velocity (+=) [UPSTREAM-RECALL a13] */
 static void interval_pushes(const wl_config* c, wlo_env* e, uint32_t gid, int64_t t, real step_dt) {
     if (!c->push_enable) return;
@@ -812,7 +933,11 @@ static int env_step(wlo_sim* s, int li, const float* a_in, int64_t t, float* obs
         else if (c->task == WL_TASK_VISUAL) visual_reset_env(s, e, gid, t);
         else drift_reset_env(c, e, gid, t);
     }
-    if (c->task == WL_TASK_VISUAL) { visual_obs(e, obs); return 0; }
+    if (c->task == WL_TASK_VISUAL) {      /* PolicyCfg order: camera, base_lin_vel, base_ang_vel, last_action (:45-52) */
+        if (c->vis_cam) camera_obs(s, e, (uint32_t)t, RNG_CAM, 0u, NULL, obs);
+        visual_obs(e, obs + vis_cam_floats(c));
+        return 0;
+    }
     if (c->task == WL_TASK_ELEVATION) {
         /* G. commands; I. observations */
         elev_command_update(c, e, gid, t, step_dt);
@@ -900,7 +1025,7 @@ int wlo_reset(wlo_sim* s, const int64_t* env_ids, int32_t n_ids, int64_t step_co
 int wlo_step(wlo_sim* s, const float* action, float* obs, float* rew, uint8_t* terminated, uint8_t* truncated,
              int64_t step_counter, int nthreads) {
     const wl_config* c = &s->cfg;
-    int od = (c->task == WL_TASK_ELEVATION) ? WL_OBS_DIM_ELEV : (c->task == WL_TASK_VISUAL) ? WL_OBS_DIM_VISUAL : WL_OBS_DIM_BLIND;
+    int od = (c->task == WL_TASK_ELEVATION) ? WL_OBS_DIM_ELEV : (c->task == WL_TASK_VISUAL) ? WL_OBS_DIM_VISUAL + vis_cam_floats(c) : WL_OBS_DIM_BLIND;
     step_log tot; memset(&tot, 0, sizeof tot);
     int err = 0;
     (void)nthreads;
@@ -951,7 +1076,12 @@ int wlo_observe(wlo_sim* s, float* obs, int64_t step_counter, int32_t call_idx) 
         return 0;
     }
     if (c->task == WL_TASK_VISUAL) {
-        for (int li = 0; li < c->num_envs; ++li) visual_obs(&s->env[li], obs + (size_t)WL_OBS_DIM_VISUAL * li);
+        const int camf = vis_cam_floats(c);
+        for (int li = 0; li < c->num_envs; ++li) {
+            float* row = obs + (size_t)(WL_OBS_DIM_VISUAL + camf) * li;
+            if (camf) camera_obs(s, &s->env[li], (uint32_t)step_counter, RNG_CAM_EXTRA, (uint32_t)call_idx, NULL, row);
+            visual_obs(&s->env[li], row + camf);
+        }
         return 0;
     }
     for (int li = 0; li < c->num_envs; ++li)
@@ -1053,9 +1183,33 @@ int wlo_detmath(int32_t op, const float* in, const float* in2, float* out, int32
             case 4: out[i] = (float)det_log(x); break;
             case 5: out[i] = (float)det_tan(x); break;
             case 6: out[i] = (float)det_asin(x); break;
+            case 7: out[i] = (float)det_exp(x); break;
             default: return WL_EINVAL;
         }
     }
+    return 0;
+}
+/* camera term alone: aug = NULL draws the parameters; obs rows have the full visual stride */
+int wlo_camera(wlo_sim* s, float* obs, int64_t step_counter, const float* aug) {
+    const wl_config* c = &s->cfg;
+    if (c->task != WL_TASK_VISUAL || !c->vis_cam) return WL_EUNSUPPORTED;
+    const int camf = vis_cam_floats(c);
+    for (int li = 0; li < c->num_envs; ++li)
+        camera_obs(s, &s->env[li], (uint32_t)step_counter, RNG_CAM, 0u, aug, obs + (size_t)(WL_OBS_DIM_VISUAL + camf) * li);
+    return 0;
+}
+/* post-processing only (golden vectors of camera_data_rgb_flattened[_aug]): white [n, rows*W] u8, aug 9 floats, out [n, rows*W] */
+int wlo_camera_post(const wl_config* c_in, const uint8_t* white, const float* aug, float* out, int32_t n) {
+    wl_config cc = *c_in; config_finalize(&cc);
+    const int npix = vis_cam_floats(&cc);
+    if (npix <= 0 || npix > WL_CAM_MAX_PIXELS) return WL_EINVAL;
+    for (int i = 0; i < n; ++i) camera_post(&cc, white + (size_t)i * npix, 0u, RNG_CAM, 0u, aug, out + (size_t)i * npix);
+    return 0;
+}
+/* raw render of env li: white mask [rows*W] */
+int wlo_camera_render(wlo_sim* s, int32_t li, uint8_t* white) {
+    if (s->cfg.task != WL_TASK_VISUAL || !s->cfg.vis_cam || li < 0 || li >= s->cfg.num_envs) return WL_EINVAL;
+    camera_render(&s->cfg, s->vis_map, &s->env[li], white);
     return 0;
 }
 int wlo_philox(uint64_t seed, uint32_t c0_base, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t* out, int32_t n) {

@@ -288,7 +288,51 @@ def golden_visual():
                         poses=np.array(poses, dtype=np.float64), idxs=idxs)
 
 
+def golden_camera():
+    """camera_data_rgb_flattened / camera_data_rgb_flattened_aug (visual/mdp_sensors/observations.py:64-87), the reference's
+    own functions run on synthetic 2-colour frames.  torchvision draws the ColorJitter / GaussianBlur parameters inside
+    forward(); the two get_params hooks are pinned to known values so that the restatement can be fed the same ones."""
+    import importlib.util
+    import torchvision.transforms as T
+    path = REF / "wheeledlab_tasks" / "wheeledlab_tasks" / "visual" / "mdp_sensors" / "observations.py"
+    spec = importlib.util.spec_from_file_location("wl_visual_sensors_obs", path)
+    mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
+    rng = np.random.default_rng(21)
+    B, H, W = 6, 60, 80
+    white = np.zeros((B, H, W), dtype=bool)
+    for b in range(B):                                   # blobs + stripes + one all-black and one all-white-below-horizon frame
+        if b == 0:
+            continue
+        if b == 1:
+            white[b, 25:, :] = True
+            continue
+        for _ in range(6):
+            r0, c0 = rng.integers(0, H), rng.integers(0, W)
+            white[b, r0:r0 + rng.integers(2, 25), c0:c0 + rng.integers(2, 30)] = True
+        white[b, :, ::7] ^= (b % 2 == 0)
+    rgb = torch.from_numpy(np.repeat((white * 255).astype(np.uint8)[..., None], 3, axis=-1))
+    env = types.SimpleNamespace(scene=types.SimpleNamespace(sensors={"camera": types.SimpleNamespace(data=types.SimpleNamespace(output={"rgb": rgb}))}))
+    cfgp = types.SimpleNamespace(name="camera")
+    raw = mod.camera_data_rgb_flattened(env, cfgp).numpy()
+    augs, outs = [], []
+    orders = [[0, 1, 2, 3], [1, 0, 3, 2], [3, 2, 1, 0], [2, 0, 1, 3], [1, 2, 3, 0]]
+    orig_cj, orig_gb = T.ColorJitter.get_params, T.GaussianBlur.get_params
+    try:
+        for k, order in enumerate(orders):
+            b_, c_, s_, h_ = rng.uniform(0.2, 1.8), rng.uniform(0.8, 1.2), rng.uniform(0.2, 1.8), rng.uniform(-0.5, 0.5)
+            sigma = float([0.1, 0.7, 1.5, 3.3, 5.0][k])
+            T.ColorJitter.get_params = staticmethod(lambda *a, _o=order, _v=(b_, c_, s_, h_): (torch.tensor(_o), *_v))
+            T.GaussianBlur.get_params = staticmethod(lambda *a, _s=sigma: _s)
+            out = mod.camera_data_rgb_flattened_aug(env, cfgp).numpy()
+            augs.append([b_, c_, s_, h_, sigma] + order); outs.append(out)
+    finally:
+        T.ColorJitter.get_params, T.GaussianBlur.get_params = orig_cj, orig_gb
+    np.savez_compressed(HERE / "camera_post.npz", white=white[:, H // 3:, :].reshape(B, -1).astype(np.uint8), raw=raw,
+                        aug=np.array(augs, dtype=np.float32), out=np.stack(outs).astype(np.float32))
+
+
 if __name__ == "__main__":
+    golden_camera()
     golden_visual()
     golden_elevation()
     golden_actions(); golden_drift_terms(); golden_reset_along_track(); golden_curriculum(); golden_euler()

@@ -40,6 +40,9 @@ def _load(name):
     lib.wlo_euler_xyz.argtypes = [vp, vp, i32]
     lib.wlo_drift_reset_pose.argtypes = [vp, vp, vp, vp, vp, i32]
     lib.wlo_elev_terms.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32]
+    lib.wlo_camera.argtypes = [vp, vp, i64, vp]
+    lib.wlo_camera_post.argtypes = [vp, vp, vp, vp, i32]
+    lib.wlo_camera_render.argtypes = [vp, i32, vp]
     lib.wlo_config_describe.restype = C.c_char_p
     return lib
 
@@ -70,6 +73,8 @@ class Oracle:
         self.n = int(cfg.num_envs)
         self.threads = threads
         self.obs_dim = {0: 14, 1: 689, 2: 8}[int(cfg.task)]
+        if int(cfg.task) == 2 and int(cfg.vis_cam):
+            self.obs_dim += int(cfg.vis_cam_w) * (int(cfg.vis_cam_h) - int(cfg.vis_cam_row0))
         if heightfield is None:
             hf = None
         elif int(cfg.task) == 2:
@@ -138,6 +143,19 @@ class Oracle:
         w = np.ascontiguousarray(w, np.float32)
         self.lib.wlo_set_weights(self._h, _p(w))
 
+    def camera(self, step_counter, aug=None):
+        """Camera term alone into a fresh [n, obs_dim] buffer (only the camera floats are written)."""
+        obs = np.zeros((self.n, self.obs_dim), np.float32)
+        a = None if aug is None else np.ascontiguousarray(aug, np.float32)
+        assert self.lib.wlo_camera(self._h, _p(obs), step_counter, _p(a)) == 0
+        return obs
+
+    def camera_render(self, li):
+        npix = self.obs_dim - 8
+        out = np.zeros(npix, np.uint8)
+        assert self.lib.wlo_camera_render(self._h, li, _p(out)) == 0
+        return out
+
     def log(self):
         out = np.zeros(16, np.float64)
         self.lib.wlo_get_log(self._h, _p(out))
@@ -150,6 +168,15 @@ def detmath(op, x, x2=None, kind="f32"):
     x2 = x if x2 is None else np.ascontiguousarray(x2, np.float32)
     out = np.empty_like(x)
     assert lib.wlo_detmath(op, _p(x), _p(x2), _p(out), x.size) == 0
+    return out
+
+
+def camera_post(cfg, white, aug, kind="f32"):
+    """camera_data_rgb_flattened[_aug] on white masks [n, rows*W] with explicit ColorJitter / blur parameters (9 floats)."""
+    white = np.ascontiguousarray(white, np.uint8)
+    out = np.empty(white.shape, np.float32)
+    a = None if aug is None else np.ascontiguousarray(aug, np.float32)
+    assert get_lib(kind).wlo_camera_post(C.byref(cfg), _p(white), _p(a), _p(out), white.shape[0]) == 0
     return out
 
 

@@ -238,3 +238,25 @@ def test_visual_oracle_terms_on_square_map():
     out = (np.abs(x) > 125.001) | (np.abs(y) > 125.001)
     inside = (np.abs(x) < 124.999) & (np.abs(y) < 124.999)
     assert term[out].all() and not term[inside].any() and obs.shape == (512, 8)
+
+
+def test_camera_post_processing_matches_reference_functions():
+    """Oracle restatement of camera_data_rgb_flattened / camera_data_rgb_flattened_aug (crop H//3:, ColorJitter in the
+    drawn order, GaussianBlur(5), Grayscale, Normalize(0.5, 0.5)) vs the reference's own functions (torchvision) run on
+    2-colour frames with pinned ColorJitter / blur parameters (tests/golden/make_golden.py::golden_camera).
+    Tolerance 2e-6 (measured 6e-7): torchvision blurs with a 25-tap conv2d and averages the frame for the contrast op in another order."""
+    import wheeledlab_b200 as wl
+    d = np.load(G / "camera_post.npz")
+    white, aug, out, raw = d["white"], d["aug"], d["out"], d["raw"]
+    small = np.ones((4, 4), dtype=bool)
+    spec_raw = wl.visual_task(num_envs=1, traversability=small, camera="raw")
+    got = O.camera_post(spec_raw.cfg, white, None)
+    assert np.abs(got - raw).max() <= 1e-6
+    spec = wl.visual_task(num_envs=1, traversability=small, camera="aug")
+    for k in range(aug.shape[0]):
+        got = O.camera_post(spec.cfg, white, aug[k])
+        err = np.abs(got - out[k]).max()
+        assert err <= 2e-6, (k, err)
+    # f64 build of the same restatement (libm exp, double accumulation) agrees too: the model, not the rounding, is what matches
+    for k in range(aug.shape[0]):
+        assert np.abs(O.camera_post(spec.cfg, white, aug[k], kind="f64") - out[k]).max() <= 2e-6

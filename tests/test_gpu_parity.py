@@ -47,7 +47,8 @@ def test_detmath_bit_exact():
     import wheeledlab_b200 as wl
     rng = np.random.default_rng(0)
     cases = {0: rng.uniform(-8, 8, 100000), 1: rng.uniform(-8, 8, 100000), 2: rng.normal(0, 10, 100000),
-             4: rng.uniform(1e-7, 1, 100000), 5: rng.uniform(-0.6, 0.6, 100000), 6: rng.uniform(-1, 1, 100000)}
+             4: rng.uniform(1e-7, 1, 100000), 5: rng.uniform(-0.6, 0.6, 100000), 6: rng.uniform(-1, 1, 100000),
+             7: -rng.uniform(0, 90, 100000)}
     for op, x in cases.items():
         x = x.astype(np.float32)
         d_in = torch.from_numpy(x).cuda(); d_out = torch.empty_like(d_in)
@@ -402,7 +403,9 @@ def test_visual_trajectory_bit_exact(variant):
     assert np.array_equal(_bits(_state_groups(sim)), _bits(orc.export_state())) and n_done >= 2 * n
     env = wl.make("Isaac-MushrVisualRL-v0", num_envs=64)
     o, _ = env.reset()
-    assert o["policy"].shape == (64, 8) and env.max_episode_length == 50
+    assert o["policy"].shape == (64, 3208) and env.max_episode_length == 50      # registered task: camera + 8 proprio floats
+    env = wl.ManagerBasedRLEnv(wl.visual_task(num_envs=64), device="cuda:0")
+    assert env.reset()[0]["policy"].shape == (64, 8)
 
 
 def test_articulation_views_and_suspension():
@@ -652,3 +655,45 @@ def test_python_terms_run_between_rewards_and_reset():
     assert int(ex["log"]["Episode_Termination/short_episode"]) == int(fire.sum())
     with pytest.raises(NotImplementedError):
         env3.step_host(torch.zeros((n, 2)).pin_memory())
+
+
+@pytest.mark.parametrize("mode", ["aug", "raw"])
+def test_visual_camera_observation_bit_exact(mode):
+    """Visual task WITH the camera term (obs = 3200 camera floats + 8 proprio = 3208, PolicyCfg order): the CUDA camera
+    kernel (render -> ColorJitter -> 5x5 Gaussian blur -> Grayscale -> Normalize) == the oracle bit for bit, for drawn
+    and for explicit augmentation parameters, through wl_step / wl_observe / the staged step, over resets."""
+    _need_gpu()
+    import wheeledlab_b200 as wl
+    n, steps = 96, 60
+    spec = wl.visual_task(num_envs=n, seed=7, camera=mode)
+    sim = wl.WheeledSim(spec, "cuda:0"); sim.startup(); sim.reset(None, 0)
+    orc = O.Oracle(spec.cfg, heightfield=spec.heightfield); orc.startup(); orc.reset(None, 0)
+    assert sim.obs_dim == 3208 and orc.obs_dim == 3208
+    assert np.array_equal(_bits(sim.observe(0, 2).cpu().numpy()), _bits(orc.observe(0, 2)))
+    seen_white = 0.0
+    for t in range(steps):
+        act = sim.synth_actions(t)
+        if t % 3 == 2:                                   # the staged step launches the camera too
+            rew, bits = sim.step_stage_a(act, t)
+            obs, term, trunc = sim.step_stage_b(bits, t)
+        else:
+            sim.set_kernel_variant(1 if t % 2 else 4)
+            obs, rew, term, trunc = sim.step(act, t)
+        o_obs, o_rew, o_term, o_trunc = orc.step(act.cpu().numpy(), t)
+        assert np.array_equal(term.cpu().numpy(), o_term) and np.array_equal(trunc.cpu().numpy(), o_trunc), t
+        assert np.array_equal(_bits(rew.cpu().numpy()), _bits(o_rew)), t
+        got = obs.cpu().numpy()
+        assert np.array_equal(_bits(got[:, 3200:]), _bits(o_obs[:, 3200:])), t
+        assert np.array_equal(_bits(got[:, :3200]), _bits(o_obs[:, :3200])), (t, np.abs(got[:, :3200] - o_obs[:, :3200]).max())
+        seen_white += float((got[:, :3200] > 0).mean())
+    assert 0.02 < seen_white / steps < 0.9               # the frames are not blank
+    if mode == "aug":                                    # explicit parameters (the golden-vector path), every op order
+        buf = torch.zeros((n, 3208), device="cuda")
+        for k, order in enumerate(([0, 1, 2, 3], [3, 1, 0, 2], [2, 3, 1, 0])):
+            aug = np.array([0.4 + 0.5 * k, 0.85 + 0.1 * k, 1.5 - 0.5 * k, 0.1, [0.1, 1.3, 5.0][k]] + order, dtype=np.float32)
+            sim.camera(5, buf, torch.from_numpy(aug).cuda())
+            exp = orc.camera(5, aug)
+            assert np.array_equal(_bits(buf.cpu().numpy()[:, :3200]), _bits(exp[:, :3200])), k
+    with pytest.raises(wl.WlError):                      # single-launch rollout cannot host the second kernel
+        from wheeledlab_b200.distributed import RolloutSlab
+        sim.rollout(4, 100, RolloutSlab(4, n, 3208, 2, "cuda:0"), torch.empty((4, 16), device="cuda"))

@@ -36,6 +36,7 @@ def test_uniform_and_normal_statistics():
 @pytest.mark.parametrize("op,fn,lo,hi,tol", [
     (0, np.sin, -8.0, 8.0, 2.5e-7), (1, np.cos, -8.0, 8.0, 2.5e-7), (2, np.arctan, -50.0, 50.0, 3e-7),
     (4, np.log, 1e-7, 1.0, 5e-7), (5, np.tan, -0.6, 0.6, 3e-7), (6, np.arcsin, -0.999, 0.999, 4e-7),
+    (7, np.exp, -60.0, 0.0, 2e-7),
 ])
 def test_detmath_accuracy_vs_libm(op, fn, lo, hi, tol):
     x = np.linspace(lo, hi, 200001).astype(np.float32)
@@ -231,3 +232,52 @@ def test_elevation_oracle_on_reference_terrain():
         obs, rew, term, trunc = o.step(o.synth_actions(t), t)
         assert np.isfinite(obs).all() and np.isfinite(rew).all() and obs[:, 13:].max() <= 10 and obs[:, 13:].min() >= -10
     assert obs.shape == (48, 689)
+
+
+def test_camera_render_matches_closed_form_geometry():
+    """Software pinhole camera of the Visual task: the oracle's white mask vs an independent float64 ray / plane
+    intersection (camera 0.162 m above the ground, hfov 90.6 deg, vfov 64.9 deg), car yawed and slightly pitched."""
+    import wheeledlab_b200 as wl
+    rng = np.random.default_rng(5)
+    m = rng.random((500, 500)) < 0.5
+    spec = wl.visual_task(num_envs=3, seed=1, traversability=m, camera="raw")
+    c = spec.cfg
+    orc = O.Oracle(c, heightfield=spec.heightfield)
+    orc.startup(); orc.reset(None, 0)
+    st = orc.export_state()                              # [15, n, 4]
+    yaw, pitch = np.array([0.3, -2.0, 1.1]), np.array([0.0, 0.05, -0.04])
+    pos = np.array([[1.0, -2.0, 0.0], [-30.3, 40.7, 0.01], [124.0, -124.2, 0.0]])
+    for i in range(3):
+        cy, sy, cp, sp = np.cos(yaw[i] / 2), np.sin(yaw[i] / 2), np.cos(pitch[i] / 2), np.sin(pitch[i] / 2)
+        q = np.array([cy * cp, -sy * sp, cy * sp, sy * cp])                 # q_yaw(z) * q_pitch(y), (w, x, y, z)
+        st[0, i, :3] = pos[i]; st[1, i] = q
+    orc.import_state(st)
+    W, H, r0 = int(c.vis_cam_w), int(c.vis_cam_h), int(c.vis_cam_row0)
+    assert (W, H, r0) == (80, 60, 20) and orc.obs_dim == 3208
+    hf, vf = 2 * np.degrees(np.arctan(W / 2 / c.vis_cam_fx)), 2 * np.degrees(np.arctan(H / 2 / c.vis_cam_fy))
+    assert abs(hf - 90.56) < 0.05 and abs(vf - 64.85) < 0.05
+    for i in range(3):
+        got = orc.camera_render(i).reshape(H - r0, W).astype(bool)
+        w, x, y, z = st[1, i].astype(np.float64)
+        R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+                      [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+                      [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
+        pc = pos[i] + R @ np.array(list(c.vis_cam_pos), dtype=np.float64)
+        u, v = np.meshgrid(np.arange(W), np.arange(r0, H))
+        d = np.stack([np.ones_like(u, dtype=np.float64), -(u + 0.5 - c.vis_cam_cx) / c.vis_cam_fx, -(v + 0.5 - c.vis_cam_cy) / c.vis_cam_fy], -1) @ R.T
+        with np.errstate(divide="ignore", invalid="ignore"):
+            tt = pc[2] / -d[..., 2]
+        hit = (d[..., 2] < 0) & (tt <= 100.0)
+        hx, hy = pc[0] + tt * d[..., 0], pc[1] + tt * d[..., 1]
+        ci = np.floor((hx - c.vis_mesh_x0) / c.vis_mesh_dx); ri = np.floor((hy - c.vis_mesh_y0) / c.vis_mesh_dy)
+        ok = hit & (ci >= 0) & (ri >= 0) & (ci < 499) & (ri < 499)
+        exp = np.zeros_like(got)
+        exp[ok] = m[ri[ok].astype(int), ci[ok].astype(int)]
+        assert (got != exp).mean() < 0.004, (i, (got != exp).mean())          # only pixels whose hit point sits on a cell edge
+        assert 0.05 < got[20:].mean() < 0.95                                   # the ground fills the lower rows; ~half the cells are white
+        if i == 0:
+            assert not got[:9].any()                                           # level camera: rows above the horizon see the black sky
+    # the policy observation carries the camera first, then the 8 proprioceptive floats (PolicyCfg order)
+    obs = orc.observe(0)
+    cam = obs[:, :3200]
+    assert obs.shape == (3, 3208) and np.all((np.abs(cam + 1.0) < 1e-6) | (np.abs(cam - 0.9998) < 1e-6))

@@ -216,7 +216,8 @@ wl_step_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st, wl_
         // G. commands   H. interval events (post-reset state)   I. observations
         if (VIS) {
             float o[8]; visual_proprio(c, e, o);
-            float4* row = reinterpret_cast<float4*>(obs + (size_t)WL_OBS_DIM_VISUAL * i);
+            const int camf = vis_cam_floats(c);              // the camera floats come first (wl_camera_kernel fills them)
+            float4* row = reinterpret_cast<float4*>(obs + (size_t)(WL_OBS_DIM_VISUAL + camf) * i + camf);
             row[0] = make_float4(o[0], o[1], o[2], o[3]); row[1] = make_float4(o[4], o[5], o[6], o[7]);
         } else if (ELEV) {
             elev_command_update(c, e, gid, t, c.d_step_dt);
@@ -306,7 +307,7 @@ __device__ __forceinline__ void quad_env_step(const wl_config& c, const Terrain&
     if (VIS) {      // 8 proprioceptive floats, no noise, no euler: lanes 0 and 1 write one float4 each
         float o[8]; visual_proprio(c, e, o);
         if (live && w < 2) {
-            float4* row = reinterpret_cast<float4*>(obs_row);
+            float4* row = reinterpret_cast<float4*>(obs_row + vis_cam_floats(c));
             row[w] = (w == 0) ? make_float4(o[0], o[1], o[2], o[3]) : make_float4(o[4], o[5], o[6], o[7]);
         }
     } else
@@ -358,7 +359,7 @@ wl_step_quad_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st
     const float4 rw0 = __ldg(reinterpret_cast<const float4*>(gl->rew_weight)), rw1 = __ldg(reinterpret_cast<const float4*>(gl->rew_weight) + 1);
     const float wts[WL_MAX_REW_TERMS] = {rw0.x, rw0.y, rw0.z, rw0.w, rw1.x, rw1.y, rw1.z, rw1.w};
     load_env_quad(st, n, ii, w, e, ELEV);
-    const int od = ELEV ? WL_OBS_DIM_ELEV : VIS ? WL_OBS_DIM_VISUAL : WL_OBS_DIM_BLIND;
+    const int od = ELEV ? WL_OBS_DIM_ELEV : VIS ? WL_OBS_DIM_VISUAL + vis_cam_floats(c) : WL_OBS_DIM_BLIND;
     quad_env_step<TASK>(c, T, vm, gl->acc, wts, e, i, w, live, gid, base, t, action[ii], obs + (size_t)od * ii, rew, terminated_o, truncated_o);
     if (live) store_env_quad(st, n, i, w, e, ELEV);
     log_finalize(c, gl, d_log, t);
@@ -544,7 +545,7 @@ wl_act_step_quad_kernel(const __grid_constant__ wl_config c, float4* __restrict_
             po.value[i] = vv;
         }
         // ---- the env step on the sampled action
-        const int od = ELEV ? WL_OBS_DIM_ELEV : VIS ? WL_OBS_DIM_VISUAL : WL_OBS_DIM_BLIND;
+        const int od = ELEV ? WL_OBS_DIM_ELEV : VIS ? WL_OBS_DIM_VISUAL + vis_cam_floats(c) : WL_OBS_DIM_BLIND;
         quad_env_step<TASK>(c, T, vm, gl->acc, wts, e, i, w, live, gid, base, t, a, obs + (size_t)od * ii, rew, terminated_o, truncated_o);
         if (live) store_env_quad(st, n, i, w, e, ELEV);
     }
@@ -576,7 +577,7 @@ wl_rollout_quad_kernel(const __grid_constant__ wl_config c, float4* __restrict__
     const float4 rw0 = __ldg(reinterpret_cast<const float4*>(gl->rew_weight)), rw1 = __ldg(reinterpret_cast<const float4*>(gl->rew_weight) + 1);
     const float wts[WL_MAX_REW_TERMS] = {rw0.x, rw0.y, rw0.z, rw0.w, rw1.x, rw1.y, rw1.z, rw1.w};
     load_env_quad(st, n, ii, w, e, ELEV);
-    const int od = ELEV ? WL_OBS_DIM_ELEV : VIS ? WL_OBS_DIM_VISUAL : WL_OBS_DIM_BLIND;
+    const int od = ELEV ? WL_OBS_DIM_ELEV : VIS ? WL_OBS_DIM_VISUAL + vis_cam_floats(c) : WL_OBS_DIM_BLIND;
     for (int k = 0; k < K; ++k) {
         const uint32_t t = t0 + (uint32_t)k;
         float2 a;
@@ -759,7 +760,8 @@ __global__ void wl_observe_kernel(const __grid_constant__ wl_config c, const flo
     if (c.task == WL_TASK_VISUAL) {
         load_env(st, n, i, e, false);
         float o[8]; visual_proprio(c, e, o);
-        float* row = obs + (size_t)WL_OBS_DIM_VISUAL * i;
+        const int camf = vis_cam_floats(c);
+        float* row = obs + (size_t)(WL_OBS_DIM_VISUAL + camf) * i + camf;
 #pragma unroll
         for (int k = 0; k < 8; ++k) row[k] = o[k];
         return;
@@ -879,6 +881,7 @@ __global__ void wl_detmath_kernel(int op, const float* __restrict__ in, const fl
         case 4: r = det_log(x); break;
         case 5: r = det_tan(x); break;
         case 6: r = det_asin(x); break;
+        case 7: r = det_exp(x); break;
     }
     out[i] = r;
 }
@@ -886,6 +889,81 @@ __global__ void wl_philox_kernel(uint64_t seed, uint32_t c0, uint32_t c1, uint32
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     out[i] = philox4x32(seed, c0 + (uint32_t)i, c1, c2, c3);
+}
+
+// ---------------------------------------------------------------------------------------
+// Visual task camera term (mdp_sensors/observations.py:64-87 on a software pinhole camera): one CTA per env renders the
+// kept rows of the 80 x 60 frame against the 2-colour plane mesh, applies ColorJitter on the two class values, the 5 x 5
+// Gaussian blur (separable, reflect padding) through shared memory, Grayscale + Normalize(0.5, 0.5), and streams the
+// 3200 floats out as float4.  HBM: 12.8 KB written per env, the 250 KB map stays in L2.
+// ---------------------------------------------------------------------------------------
+#define WL_CAM_THREADS 128
+__global__ void __launch_bounds__(WL_CAM_THREADS)
+wl_camera_kernel(const __grid_constant__ wl_config c, const float4* __restrict__ st, const wl_globals* __restrict__ gl,
+                 const float* __restrict__ aux, float* __restrict__ obs, uint32_t t_arg, uint32_t stream, uint32_t sub,
+                 const float* __restrict__ aug) {
+    __shared__ float J[WL_CAM_MAX_PIXELS];       // class bits, then jittered values
+    __shared__ float Hb[WL_CAM_MAX_PIXELS];      // after the horizontal pass
+    __shared__ int n_white;
+    const int i = blockIdx.x, n = c.num_envs;
+    const int W = c.vis_cam_w, rows = c.vis_cam_h - c.vis_cam_row0, npix = W * rows;
+    const uint32_t t = (t_arg == 0xFFFFFFFFu) ? __ldcg(&gl->step_counter) - 1u : t_arg;    // the step's epilogue already advanced it
+    const VisualMap vm = visual_map(c, aux);
+    if (threadIdx.x == 0) n_white = 0;
+    const float4 gp = ldg4(st, WL_G_POS, n, i), gq = ldg4(st, WL_G_QUAT, n, i);
+    const M3 R = rotmat(gq.x, gq.y, gq.z, gq.w);
+    const V3 off = rot(R, V3{c.vis_cam_pos[0], c.vis_cam_pos[1], c.vis_cam_pos[2]});
+    const V3 pc{gp.x + off.x, gp.y + off.y, gp.z + off.z};
+    __syncthreads();
+    int mine = 0;
+    for (int k = threadIdx.x; k < npix; k += WL_CAM_THREADS) {
+        const int r = k / W, u = k - r * W;
+        const bool wh = cam_pixel_white(c, vm.map, R, pc, u, c.vis_cam_row0 + r);
+        J[k] = wh ? 1.0f : 0.0f;
+        mine += wh ? 1 : 0;
+    }
+    mine = (int)warp_sum((float)mine);           // <= 25 * 32: exact in fp32
+    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&n_white, mine);
+    __syncthreads();
+    const CamAug A = cam_aug_params(c, t, stream, sub, aug, (float)n_white / (float)npix);
+    float* row = obs + (size_t)(WL_OBS_DIM_VISUAL + npix) * i;
+    if (c.vis_cam != 2) {                        // camera_data_rgb_flattened: grayscale + normalize only
+        for (int k = threadIdx.x * 4; k < npix; k += WL_CAM_THREADS * 4) {
+            float4 o;
+            o.x = fm(2.0f, cam_gray(J[k]), -1.0f); o.y = fm(2.0f, cam_gray(J[k + 1]), -1.0f);
+            o.z = fm(2.0f, cam_gray(J[k + 2]), -1.0f); o.w = fm(2.0f, cam_gray(J[k + 3]), -1.0f);
+            *reinterpret_cast<float4*>(row + k) = o;
+        }
+        return;
+    }
+    // horizontal pass (reflect: -1 -> 1, -2 -> 2, W -> W-2, W+1 -> W-3) on the jittered class values
+    for (int k = threadIdx.x; k < npix; k += WL_CAM_THREADS) {
+        const int r = k / W, u = k - r * W;
+        const float* Jr = J + r * W;
+        auto val = [&](int x) { x = x < 0 ? -x : (x >= W ? 2 * W - 2 - x : x); return Jr[x] != 0.0f ? A.v1 : A.v0; };
+        float acc = A.w0 * val(u);
+        acc = fm(A.w1, val(u - 1) + val(u + 1), acc);
+        acc = fm(A.w2, val(u - 2) + val(u + 2), acc);
+        Hb[k] = acc;
+    }
+    __syncthreads();
+    // vertical pass + Grayscale + Normalize((x - 0.5) / 0.5), four pixels of one row per thread -> one STG.128
+    for (int k = threadIdx.x * 4; k < npix; k += WL_CAM_THREADS * 4) {
+        const int r = k / W, u = k - r * W;
+        auto rr = [&](int y) { return y < 0 ? -y : (y >= rows ? 2 * rows - 2 - y : y); };
+        const float* h0 = Hb + rr(r) * W + u;
+        const float* hm1 = Hb + rr(r - 1) * W + u; const float* hp1 = Hb + rr(r + 1) * W + u;
+        const float* hm2 = Hb + rr(r - 2) * W + u; const float* hp2 = Hb + rr(r + 2) * W + u;
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float acc = A.w0 * h0[j];
+            acc = fm(A.w1, hm1[j] + hp1[j], acc);
+            acc = fm(A.w2, hm2[j] + hp2[j], acc);
+            o[j] = fm(2.0f, cam_gray(acc), -1.0f);
+        }
+        *reinterpret_cast<float4*>(row + k) = make_float4(o[0], o[1], o[2], o[3]);
+    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -910,6 +988,12 @@ static int launch_scan(wl_sim* sim, float* d_obs, cudaStream_t cs) {
 // ---------------------------------------------------------------------------------------
 // C ABI
 // ---------------------------------------------------------------------------------------
+static int launch_camera(wl_sim* sim, float* d_obs, uint32_t t, uint32_t stream_id, uint32_t sub, const float* d_aug, cudaStream_t cs) {
+    wl_camera_kernel<<<sim->cfg.num_envs, WL_CAM_THREADS, 0, cs>>>(sim->cfg, sim->state, sim->globals, sim->hf, d_obs, t, stream_id, sub, d_aug);
+    sim->launches++;
+    return cuda_check(cudaGetLastError(), "wl_camera_kernel");
+}
+
 extern "C" {
 
 const char* wl_last_error(void) { return g_err.c_str(); }
@@ -972,6 +1056,13 @@ int wl_create(const wl_config* cfg, void* d_state, size_t state_bytes, const flo
         if (!d_heightfield) return fail(WL_EINVAL, "wl_create: the visual task needs the traversability data (see header)");
         if (cfg->vis_rows < 1 || cfg->vis_cols < 1 || cfg->vis_n_trav < 1) return fail(WL_EINVAL, "wl_create: bad traversability map geometry");
         if (((uintptr_t)d_heightfield & 15u) != 0) return fail(WL_EINVAL, "wl_create: traversability data must be 16-byte aligned");
+        if (cfg->vis_cam) {
+            const int rows = cfg->vis_cam_h - cfg->vis_cam_row0;
+            if (cfg->vis_cam < 0 || cfg->vis_cam > 2 || cfg->vis_cam_w < 4 || (cfg->vis_cam_w & 3) || rows < 3 || cfg->vis_cam_row0 < 0 ||
+                cfg->vis_cam_w * rows > WL_CAM_MAX_PIXELS || !(cfg->vis_cam_fx > 0.0f) || !(cfg->vis_cam_fy > 0.0f) ||
+                !(cfg->vis_mesh_dx > 0.0f) || !(cfg->vis_mesh_dy > 0.0f) || (cfg->vis_cam == 2 && !(cfg->vis_aug_sigma[0] > 0.0f)))
+                return fail(WL_EINVAL, "wl_create: bad camera geometry (width % 4 == 0, >= 3 kept rows, <= WL_CAM_MAX_PIXELS pixels)");
+        }
     }
     if (cfg->task == WL_TASK_ELEVATION) {
         if (!d_heightfield) return fail(WL_EINVAL, "wl_create: the elevation task needs a height-field");
@@ -1022,7 +1113,7 @@ int wl_create(const wl_config* cfg, void* d_state, size_t state_bytes, const flo
         if (cr != CUDA_SUCCESS) { delete s; return fail(WL_ECUDA, "cuTensorMapEncodeTiled failed (code " + std::to_string((int)cr) + ")"); }
         s->has_tmap = true;
     }
-    s->obs_dim = (cfg->task == WL_TASK_ELEVATION) ? WL_OBS_DIM_ELEV : (cfg->task == WL_TASK_VISUAL) ? WL_OBS_DIM_VISUAL : WL_OBS_DIM_BLIND;
+    s->obs_dim = (cfg->task == WL_TASK_ELEVATION) ? WL_OBS_DIM_ELEV : (cfg->task == WL_TASK_VISUAL) ? WL_OBS_DIM_VISUAL + (cfg->vis_cam ? cfg->vis_cam_w * (cfg->vis_cam_h - cfg->vis_cam_row0) : 0) : WL_OBS_DIM_BLIND;
     // live reward weights
     if (int rc = cuda_check(cudaMemcpy(s->globals->rew_weight, cfg->rew_weight, sizeof(float) * WL_MAX_REW_TERMS,
                                        cudaMemcpyHostToDevice), "upload reward weights")) { delete s; return rc; }
@@ -1097,6 +1188,7 @@ int wl_step(wl_sim* sim, const float* d_action, float* d_obs, float* d_rew, uint
         return WL_OK;
     }
     WL_LAUNCH_CHECK(sim, "wl_step_kernel");
+    if (vis && sim->cfg.vis_cam) return launch_camera(sim, d_obs, t, RNG_CAM, 0u, nullptr, cs);   // t may be WL_DEVICE_COUNTER
     return WL_OK;
 }
 
@@ -1138,6 +1230,8 @@ int wl_step_stage_b(wl_sim* sim, const uint8_t* d_term_bits, const uint8_t* d_ex
                                  StageIO{const_cast<uint8_t*>(d_term_bits), d_extra_terminated, d_extra_truncated}, (cudaStream_t)stream))
         return rc;
     if (sim->cfg.task == WL_TASK_ELEVATION) return launch_scan(sim, d_obs, (cudaStream_t)stream);
+    if (sim->cfg.task == WL_TASK_VISUAL && sim->cfg.vis_cam)
+        return launch_camera(sim, d_obs, (uint32_t)step_counter, RNG_CAM, 0u, nullptr, (cudaStream_t)stream);
     return WL_OK;
 }
 
@@ -1146,6 +1240,7 @@ int wl_rollout(wl_sim* sim, int32_t K, const float* d_actions, float* d_actions_
     if (!sim || !d_obs || !d_rew || !d_terminated || !d_truncated || !d_log) return fail(WL_EINVAL, "wl_rollout: null argument");
     if (K < 1) return fail(WL_EINVAL, "wl_rollout: K must be >= 1");
     if (sim->cfg.task == WL_TASK_ELEVATION) return fail(WL_EUNSUPPORTED, "wl_rollout: the elevation step is two kernels (use wl_step)");
+    if (sim->cfg.task == WL_TASK_VISUAL && sim->cfg.vis_cam) return fail(WL_EUNSUPPORTED, "wl_rollout: the camera term is a second kernel (use wl_step)");
     if (sim->cfg.curr_n > 0) {
         if (step_counter < 0) return fail(WL_EINVAL, "wl_rollout: with curriculum terms the host must pass the step counter");
         const int64_t L = sim->cfg.max_episode_length;
@@ -1210,7 +1305,15 @@ int wl_observe(wl_sim* sim, float* d_obs, int64_t step_counter, int32_t call_idx
                                                                          (uint32_t)call_idx);
     WL_LAUNCH_CHECK(sim, "wl_observe_kernel");
     if (sim->cfg.task == WL_TASK_ELEVATION) return launch_scan(sim, d_obs, (cudaStream_t)stream);
+    if (sim->cfg.task == WL_TASK_VISUAL && sim->cfg.vis_cam)
+        return launch_camera(sim, d_obs, (uint32_t)step_counter, RNG_CAM_EXTRA, (uint32_t)call_idx, nullptr, (cudaStream_t)stream);
     return WL_OK;
+}
+
+int wl_camera(wl_sim* sim, float* d_obs, int64_t step_counter, const float* d_aug, void* stream) {
+    if (!sim || !d_obs) return fail(WL_EINVAL, "wl_camera: null argument");
+    if (sim->cfg.task != WL_TASK_VISUAL || !sim->cfg.vis_cam) return fail(WL_EUNSUPPORTED, "wl_camera: the handle has no camera term");
+    return launch_camera(sim, d_obs, (uint32_t)step_counter, RNG_CAM, 0u, d_aug, (cudaStream_t)stream);
 }
 
 int wl_curriculum(wl_sim* sim, int32_t n_terms, const int32_t* slots, const float* increases, uint32_t fire_mask,

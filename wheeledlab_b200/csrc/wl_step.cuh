@@ -455,6 +455,67 @@ __device__ __forceinline__ VisualMap visual_map(const wl_config& c, const float*
 // rewards :304-387 (traversable_reward, forward_vel), terminations :392-409 (time_out, out_of_map);
 // map lookup = TraversabilityHashmapUtil.get_map_id (utils/traversability_utils.py:83-88: +spacing/2, truncation,
 // clamp, indexed [y_idx, x_idx]; quirk Q14)
+// ---- visual task, camera term (software pinhole camera over the 2-colour plane mesh; restated in oracle/wl_oracle.c) ----
+__device__ __forceinline__ int vis_cam_floats(const wl_config& c) { return c.vis_cam ? c.vis_cam_w * (c.vis_cam_h - c.vis_cam_row0) : 0; }
+// torchvision rgb_to_grayscale of a grey pixel (r = g = b = v): the weights sum to 0.9999, not 1
+__device__ __forceinline__ float cam_gray(float v) { return fm(0.114f, v, fm(0.587f, v, 0.2989f * v)); }
+__device__ __forceinline__ float cam_clamp01(float v) { return r_min(r_max(v, 0.0f), 1.0f); }
+struct CamAug { float v0, v1, w0, w1, w2; };      // values of the black / white class after ColorJitter; 5-tap Gaussian weights
+// ColorJitter + GaussianBlur parameters of one camera frame (one draw per call for the WHOLE batch, like torchvision's
+// transforms on a [B,3,H,W] tensor); `aug` != null overrides the draw (golden-vector tests).  A 2-valued grey image stays
+// 2-valued under the point operations, so the jitter is tracked on the two class values; p = fraction of white pixels.
+__device__ __forceinline__ CamAug cam_aug_params(const wl_config& c, uint32_t t, uint32_t stream, uint32_t sub, const float* aug, float p) {
+    CamAug A; A.v0 = 0.0f; A.v1 = 1.0f; A.w0 = 1.0f; A.w1 = 0.0f; A.w2 = 0.0f;
+    if (c.vis_cam != 2) return A;
+    float b, ct, sa, sigma; int order[4] = {0, 1, 2, 3};
+    if (aug != nullptr) {
+        b = aug[0]; ct = aug[1]; sa = aug[2]; sigma = aug[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) order[k] = (int)aug[5 + k];
+    } else {
+        const uint4 r = philox4x32(c.seed, 0u, t, stream, 2u * sub), q = philox4x32(c.seed, 0u, t, stream, 2u * sub + 1u);
+        b = uniform(r.x, r_max(0.0f, 1.0f - c.vis_aug_brightness), 1.0f + c.vis_aug_brightness);
+        ct = uniform(r.y, r_max(0.0f, 1.0f - c.vis_aug_contrast), 1.0f + c.vis_aug_contrast);
+        sa = uniform(r.z, r_max(0.0f, 1.0f - c.vis_aug_saturation), 1.0f + c.vis_aug_saturation);
+        sigma = uniform(r.w, c.vis_aug_sigma[0], c.vis_aug_sigma[1]);
+        const uint32_t rq[3] = {q.x, q.y, q.z};            // Fisher-Yates (torch.randperm(4) stand-in)
+#pragma unroll
+        for (int i = 3; i >= 1; --i) { const int j = (int)__umulhi(rq[3 - i], (uint32_t)(i + 1)); const int tmp = order[i]; order[i] = order[j]; order[j] = tmp; }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int op = order[k];
+        if (op == 0) { A.v0 = cam_clamp01(b * A.v0); A.v1 = cam_clamp01(b * A.v1); }
+        else if (op == 1) {
+            const float m = fm(p, cam_gray(A.v1), (1.0f - p) * cam_gray(A.v0));          // mean of the grey-scale image
+            A.v0 = cam_clamp01(fm(ct, A.v0, (1.0f - ct) * m)); A.v1 = cam_clamp01(fm(ct, A.v1, (1.0f - ct) * m));
+        } else if (op == 2) {
+            A.v0 = cam_clamp01(fm(sa, A.v0, (1.0f - sa) * cam_gray(A.v0))); A.v1 = cam_clamp01(fm(sa, A.v1, (1.0f - sa) * cam_gray(A.v1)));
+        }                                                  // op 3 = hue: the identity on grey pixels
+    }
+    const float e1 = det_exp(-0.5f / (sigma * sigma)), e2 = (e1 * e1) * (e1 * e1);       // exp(-x^2 / 2 sigma^2), x = 1, 2
+    const float S = fm(2.0f, e1 + e2, 1.0f);
+    A.w0 = 1.0f / S; A.w1 = e1 / S; A.w2 = e2 / S;
+    return A;
+}
+// is pixel (u, v) white?  ray through the pixel centre -> plane z = 0 -> face of the coloured mesh (utils/__init__.py:8-89)
+__device__ __forceinline__ bool cam_pixel_white(const wl_config& c, const uint8_t* __restrict__ map, const M3& R, const V3& pc, int u, int v) {
+    const float xo = ((float)u + 0.5f - c.vis_cam_cx) / c.vis_cam_fx;       // optical frame: x right, y down, z forward
+    const float yo = ((float)v + 0.5f - c.vis_cam_cy) / c.vis_cam_fy;
+    // link frame (x forward, y left, z up): d = (1, -xo, -yo); world: R d
+    const float dx = fm(-R.r[2], yo, fm(-R.r[1], xo, R.r[0]));
+    const float dy = fm(-R.r[5], yo, fm(-R.r[4], xo, R.r[3]));
+    const float dz = fm(-R.r[8], yo, fm(-R.r[7], xo, R.r[6]));
+    const bool bg = c.vis_cam_bg >= 0.5f;
+    if (!(dz < 0.0f) || !(pc.z > 0.0f)) return bg;
+    const float tt = pc.z / (-dz);                                          // depth along the optical axis
+    if (tt > 100.0f) return bg;                                             // clipping_range = (0.01, 1e2)
+    const float hx = fm(tt, dx, pc.x), hy = fm(tt, dy, pc.y);
+    const float fx = floorf((hx - c.vis_mesh_x0) / c.vis_mesh_dx), fy = floorf((hy - c.vis_mesh_y0) / c.vis_mesh_dy);
+    if (!(fx >= 0.0f) || !(fy >= 0.0f) || !(fx < (float)(c.vis_cols - 1)) || !(fy < (float)(c.vis_rows - 1))) return false;   // black base plane / void
+    return __ldg(map + (size_t)(int)fy * c.vis_cols + (int)fx) != 0;
+}
+
 __device__ __forceinline__ uint32_t visual_terms(const wl_config& c, const VisualMap& vm, const EnvState& e, V3 vb, bool time_out,
                                                  float f[WL_MAX_REW_TERMS]) {
     int xi = (int)((e.p.x + c.vis_width / 2.0f + c.vis_row_spacing / 2.0f) / c.vis_row_spacing);

@@ -160,6 +160,13 @@ class WheeledSim:
                              C.c_void_p(slab.terminated.data_ptr()), C.c_void_p(slab.truncated.data_ptr()),
                              C.c_void_p(logs.data_ptr()), step_counter, _stream_ptr(self.device)), "wl_rollout")
 
+    def camera(self, step_counter: int, obs: torch.Tensor, aug: torch.Tensor | None = None):
+        """Visual task camera term alone (wl_camera): fills the first obs_dim - 8 floats of every row of `obs` [N, obs_dim].
+        aug: None (drawn) or 9 floats on the device: brightness, contrast, saturation, hue, sigma, order[4]."""
+        check(lib.wl_camera(self._h, C.c_void_p(obs.data_ptr()), step_counter, C.c_void_p(aug.data_ptr()) if aug is not None else None,
+                            _stream_ptr(self.device)), "wl_camera")
+        return obs
+
     def step_stage_a(self, action: torch.Tensor, step_counter: int, rew: torch.Tensor | None = None, term_bits: torch.Tensor | None = None):
         """Sections A-E of env.step (wl_step_stage_a): integrator + built-in terms; leaves the PRE-RESET state in the buffer.
         Returns (built-in reward [N] f32, termination bits [N] u8: bit j = built-in term j)."""

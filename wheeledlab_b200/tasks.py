@@ -360,10 +360,15 @@ def elevation_task(num_envs: int = 1024, seed: int = 42, env_id_offset: int = 0,
     return spec
 
 
-def visual_task(num_envs: int = 1024, seed: int = 42, env_id_offset: int = 0, traversability=None) -> TaskSpec:
-    """MushrVisualRLEnvCfg, PHYSICS SIDE ONLY (visual/mushr_visual_env_cfg.py:412-439): flat plane, 4WD MuSHR,
-    traversability-map reward, out-of-map termination, random traversable respawn.  The RTX tiled-camera observation
-    term is out of scope: the policy observation here is the 8 proprioceptive floats that follow it."""
+CAMERA_MODES = {None: 0, "off": 0, "raw": 1, "aug": 2}
+
+
+def visual_task(num_envs: int = 1024, seed: int = 42, env_id_offset: int = 0, traversability=None, camera: str | None = None) -> TaskSpec:
+    """MushrVisualRLEnvCfg (visual/mushr_visual_env_cfg.py:412-439): flat plane, 4WD MuSHR, traversability-map reward,
+    out-of-map termination, random traversable respawn.  ``camera``: None -> the policy observation is the 8
+    proprioceptive floats only (physics-side task); "aug" -> the registered PolicyCfg (camera_data_rgb_flattened_aug, 3200
+    floats, then the 8 proprio floats = 3208, :45-52) on the software pinhole camera (rendering model
+    builder-defined, RTX is not available); "raw" -> camera_data_rgb_flattened (no ColorJitter / GaussianBlur)."""
     from .terrain import pack_traversability, traversability_map
     cfg = WlConfig()
     cfg.abi_version = WL_ABI_VERSION
@@ -397,11 +402,30 @@ def visual_task(num_envs: int = 1024, seed: int = 42, env_id_offset: int = 0, tr
     cfg.vis_row_spacing = cfg.vis_col_spacing = 0.5                    # :68-70
     cfg.vis_width, cfg.vis_height = cfg.vis_rows * 0.5, cfg.vis_cols * 0.5   # :113-114
     cfg.vis_spawn_z = 0.1
+    if camera not in CAMERA_MODES:
+        raise ValueError(f"camera must be one of {list(CAMERA_MODES)}")
+    cfg.vis_cam = CAMERA_MODES[camera]
+    # TiledCameraCfg, :230-246: 80 x 60, focal 1.93, apertures 3.896 x 2.453 (pinhole, square-ish pixels), ROS convention,
+    # mounted at camera_link + (0.08, 0, 0) looking along the car's +x; camera_link in the root frame: SURVEY Appendix A
+    cfg.vis_cam_w, cfg.vis_cam_h = 80, 60
+    cfg.vis_cam_row0 = cfg.vis_cam_h // 3                              # images[:, H//3:], observations.py:67,78
+    focal, h_ap, v_ap = 1.9299999475479126, 3.8959999084472656, 2.453000068664551
+    cfg.vis_cam_fx, cfg.vis_cam_fy = focal * cfg.vis_cam_w / h_ap, focal * cfg.vis_cam_h / v_ap
+    cfg.vis_cam_cx, cfg.vis_cam_cy = cfg.vis_cam_w / 2.0, cfg.vis_cam_h / 2.0
+    _set(cfg.vis_cam_pos, (0.022995 + 0.08, 0.0175, 0.162178))         # camera_link (root frame, Appendix A.1) + OffsetCfg.pos, :242
+    cfg.vis_cam_bg = 0.0                                               # no light / dome in the cfg: sky and base plane black
+    cfg.vis_mesh_x0 = -cfg.vis_width / 2 - cfg.vis_row_spacing / 2     # np.linspace(-w/2, w/2, num_rows) - spacing/2, utils/__init__.py:26-28
+    cfg.vis_mesh_y0 = -cfg.vis_height / 2 - cfg.vis_col_spacing / 2
+    cfg.vis_mesh_dx = cfg.vis_width / (cfg.vis_rows - 1)               # (quirk: the mesh pitch is 500/499 of the reward's cell size)
+    cfg.vis_mesh_dy = cfg.vis_height / (cfg.vis_cols - 1)
+    cfg.vis_aug_brightness, cfg.vis_aug_contrast, cfg.vis_aug_saturation, cfg.vis_aug_hue = 0.8, 0.2, 0.8, 0.5   # observations.py:21
+    _set(cfg.vis_aug_sigma, (0.1, 5.0))                                # GaussianBlur(5, sigma=(0.1, 5.0)), observations.py:23
+    cam_floats = cfg.vis_cam_w * (cfg.vis_cam_h - cfg.vis_cam_row0) if cfg.vis_cam else 0
     reward_names = ["traversablility", "vel_rew"]                     # :376-387 (sic)
     cfg.num_rew_terms = len(reward_names)
     _set(cfg.rew_weight, (5.0, 7.0))
     spec = TaskSpec(name="visual", cfg=cfg, reward_names=reward_names,
-                    termination_names=[("time_out", True), ("out_range", False)], curriculum=[], obs_dim=8, action_dim=2,
+                    termination_names=[("time_out", True), ("out_range", False)], curriculum=[], obs_dim=8 + cam_floats, action_dim=2,
                     episode_length_s=episode_length_s, joint_names=list(MUSHR_JOINT_NAMES))
     spec.heightfield = blob                                            # aux device blob (see header)
     spec.traversability = traversability
@@ -422,5 +446,7 @@ def make_task(name_or_id: str, **kw) -> TaskSpec:
     if name == "elevation":
         return elevation_task(**kw)
     if name == "visual":
+        if name_or_id in GYM_IDS:                 # the registered task observes through the camera (PolicyCfg, :45-52)
+            kw.setdefault("camera", "aug")
         return visual_task(**kw)
     raise NotImplementedError(f"task {name_or_id!r} is not implemented in this build")
