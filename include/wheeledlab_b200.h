@@ -272,7 +272,9 @@ extern "C" {
     XS(float, f32, d_inv_wheel_radius_cfg)                                                         \
     XS(float, f32, d_inv_dc_vel_limit)                                                             \
     XS(float, f32, d_inv_mass_nominal)                                                             \
-    XA(float, f32, d_invI_nominal, 3)
+    XA(float, f32, d_invI_nominal, 3)                                                            \
+    XS(float, f32, d_vis_mesh_inv_dx) /* 1 / vis_mesh_dx (0 when the camera is off) */             \
+    XS(float, f32, d_vis_mesh_inv_dy)
 
 typedef struct wl_config {
 #define WL_XS(type, tag, name) type name;

@@ -366,6 +366,8 @@ static void config_finalize(wl_config* c) {
     c->d_inv_dc_vel_limit = 1.0f / c->dc_vel_limit;
     c->d_inv_mass_nominal = 1.0f / c->mass_nominal;
     for (int a = 0; a < 3; ++a) c->d_invI_nominal[a] = 1.0f / c->inertia_nominal[a];
+    c->d_vis_mesh_inv_dx = c->vis_mesh_dx > 0.0f ? 1.0f / c->vis_mesh_dx : 0.0f;
+    c->d_vis_mesh_inv_dy = c->vis_mesh_dy > 0.0f ? 1.0f / c->vis_mesh_dy : 0.0f;
 }
 
 static void physics_substep(const wlo_sim* s, wlo_env* e, chassis_t* b, const real tau[4], const real steer_target[2],
@@ -769,7 +771,7 @@ static int cam_pixel_white(const wl_config* c, const uint8_t* map, const real R[
     real tt = pc[2] / (-dz);
     if (tt > K(100.0)) return bg;
     real hx = fm(tt, dx, pc[0]), hy = fm(tt, dy, pc[1]);
-    real fx = r_floor((hx - (real)c->vis_mesh_x0) / (real)c->vis_mesh_dx), fy = r_floor((hy - (real)c->vis_mesh_y0) / (real)c->vis_mesh_dy);
+    real fx = r_floor((hx - (real)c->vis_mesh_x0) * (real)c->d_vis_mesh_inv_dx), fy = r_floor((hy - (real)c->vis_mesh_y0) * (real)c->d_vis_mesh_inv_dy);
     if (!(fx >= K(0.0)) || !(fy >= K(0.0)) || !(fx < (real)(c->vis_cols - 1)) || !(fy < (real)(c->vis_rows - 1))) return 0;
     return map[(size_t)(int)fy * c->vis_cols + (int)fx] != 0;
 }
@@ -783,23 +785,26 @@ static void camera_post(const wl_config* c, const uint8_t* white, uint32_t t, ui
         for (int k = 0; k < npix; ++k) out[k] = (float)fm(K(2.0), cam_gray(white[k] ? K(1.0) : K(0.0)), K(-1.0));
         return;
     }
+    /* blur the MASK (separable 5 taps, reflect padding), then map through the jittered class values: the blur is affine
+     * in the mask, J = v0 + (v1 - v0) w */
     real* Hb = (real*)malloc(sizeof(real) * (size_t)npix);
     for (int r = 0; r < rows; ++r)
         for (int u = 0; u < W; ++u) {
-#define WLO_JV(x_) (white[r * W + ((x_) < 0 ? -(x_) : ((x_) >= W ? 2 * W - 2 - (x_) : (x_)))] ? A.v1 : A.v0)
+#define WLO_JV(x_) (white[r * W + ((x_) < 0 ? -(x_) : ((x_) >= W ? 2 * W - 2 - (x_) : (x_)))] ? K(1.0) : K(0.0))
             real acc = A.w0 * WLO_JV(u);
             acc = fm(A.w1, WLO_JV(u - 1) + WLO_JV(u + 1), acc);
             acc = fm(A.w2, WLO_JV(u - 2) + WLO_JV(u + 2), acc);
             Hb[r * W + u] = acc;
 #undef WLO_JV
         }
+    const real dv = A.v1 - A.v0;
     for (int r = 0; r < rows; ++r)
         for (int u = 0; u < W; ++u) {
 #define WLO_HR(y_) Hb[((y_) < 0 ? -(y_) : ((y_) >= rows ? 2 * rows - 2 - (y_) : (y_))) * W + u]
             real acc = A.w0 * WLO_HR(r);
             acc = fm(A.w1, WLO_HR(r - 1) + WLO_HR(r + 1), acc);
             acc = fm(A.w2, WLO_HR(r - 2) + WLO_HR(r + 2), acc);
-            out[r * W + u] = (float)fm(K(2.0), cam_gray(acc), K(-1.0));
+            out[r * W + u] = (float)fm(K(2.0), cam_gray(fm(dv, acc, A.v0)), K(-1.0));
 #undef WLO_HR
         }
     free(Hb);

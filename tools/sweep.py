@@ -16,11 +16,15 @@ from bench import BYTES_PER_ENV_STEP, _peaks  # noqa: E402
 
 TASK = "drift"
 VARIANT = 0
-BYTES = {"drift": BYTES_PER_ENV_STEP, "elevation": (15 * 16 + 8) + (11 * 16 + 689 * 4 + 4 + 2)}
+BYTES = {"drift": BYTES_PER_ENV_STEP, "elevation": (15 * 16 + 8) + (11 * 16 + 689 * 4 + 4 + 2),
+         "visual_cam": BYTES_PER_ENV_STEP - 14 * 4 + 3208 * 4 + 32,    # step state r/w + obs row written (camera 3200 + 8) + pose re-read
+         "camera": 3200 * 4 + 32}                                      # wl_camera_kernel alone: 12.8 KB written + pose (pos, quat) read
 
 
 def one(n, steps, warm, flush):
-    spec = wl.drift_task(num_envs=n, seed=42) if TASK == "drift" else wl.elevation_task(num_envs=n, seed=42)
+    spec = {"drift": lambda: wl.drift_task(num_envs=n, seed=42), "elevation": lambda: wl.elevation_task(num_envs=n, seed=42),
+            "visual_cam": lambda: wl.visual_task(num_envs=n, seed=42, camera="aug"),
+            "camera": lambda: wl.visual_task(num_envs=n, seed=42, camera="aug")}[TASK]()
     sim = wl.WheeledSim(spec, "cuda:0")
     if VARIANT:
         sim.set_kernel_variant(VARIANT)
@@ -34,7 +38,10 @@ def one(n, steps, warm, flush):
     for k in range(steps):
         if flush is not None:
             flush.fill_(0.0)
-        ev[k][0].record(); sim.step(acts[k % 4], warm + 1 + k, out=outs); ev[k][1].record()
+        if TASK == "camera":                             # the camera kernel alone (state left by the warm-up steps)
+            ev[k][0].record(); sim.camera(warm + 1 + k, outs[0]); ev[k][1].record()
+        else:
+            ev[k][0].record(); sim.step(acts[k % 4], warm + 1 + k, out=outs); ev[k][1].record()
     torch.cuda.synchronize()
     ms = [a.elapsed_time(b) for a, b in ev]
     med = statistics.median(ms)
@@ -48,7 +55,7 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warm", type=int, default=5)
     ap.add_argument("--no-flush", action="store_true")
-    ap.add_argument("--task", default="drift", choices=["drift", "elevation"])
+    ap.add_argument("--task", default="drift", choices=["drift", "elevation", "visual_cam", "camera"])
     ap.add_argument("--variant", type=int, default=0, help="0 auto, 1 thread/env, 4 quad/env")
     a = ap.parse_args()
     global TASK, VARIANT
@@ -62,7 +69,9 @@ def main():
         r["frac_of_peak"] = r["achieved_GBps"] / peak
         rows.append(r)
         print(json.dumps(r), file=sys.stderr, flush=True)
-    print(json.dumps({"kernel": f"wl_step[_quad]_kernel<{TASK}>" + (" + wl_scan_kernel<TMA>" if TASK == "elevation" else ""),
+    kname = {"camera": "wl_camera_kernel", "visual_cam": "wl_step[_quad]_kernel<visual> + wl_camera_kernel"}.get(
+        TASK, f"wl_step[_quad]_kernel<{TASK}>" + (" + wl_scan_kernel<TMA>" if TASK == "elevation" else ""))
+    print(json.dumps({"kernel": kname,
                       "bytes_per_env_step": BYTES[TASK], "peak_GBps": peak,
                       "peak_source": src, "l2_flush_between_launches": not a.no_flush, "rows": rows}))
 

@@ -898,71 +898,121 @@ __global__ void wl_philox_kernel(uint64_t seed, uint32_t c0, uint32_t c1, uint32
 // 3200 floats out as float4.  HBM: 12.8 KB written per env, the 250 KB map stays in L2.
 // ---------------------------------------------------------------------------------------
 #define WL_CAM_THREADS 128
+#define WL_CAM_MAX_W 128
+#define WL_CAM_MAX_ROWS 64
 __global__ void __launch_bounds__(WL_CAM_THREADS)
 wl_camera_kernel(const __grid_constant__ wl_config c, const float4* __restrict__ st, const wl_globals* __restrict__ gl,
                  const float* __restrict__ aux, float* __restrict__ obs, uint32_t t_arg, uint32_t stream, uint32_t sub,
                  const float* __restrict__ aug) {
-    __shared__ float J[WL_CAM_MAX_PIXELS];       // class bits, then jittered values
-    __shared__ float Hb[WL_CAM_MAX_PIXELS];      // after the horizontal pass
+    // Thread (u4, rg) owns 4 consecutive columns 4*u4 .. 4*u4+3 of rows rg, rg + RG, ...: row terms are shared by 4 pixels
+    // and every shared-memory access is a vector one.  Jp: white mask (bytes) with 4 pad columns on either side
+    // (only the inner 2 are used: reflected border); Hp: horizontal pass, with 2 reflected rows above and below.
+    __shared__ __align__(16) uint8_t Jp[WL_CAM_MAX_PIXELS + 8 * WL_CAM_MAX_ROWS];     // the mask is kept as bytes: 9 CTAs per SM
+    __shared__ CamAug A_s;
+    __shared__ __align__(16) float Hp[WL_CAM_MAX_PIXELS + 4 * WL_CAM_MAX_W];
+    __shared__ __align__(16) float CX[WL_CAM_MAX_W], CY[WL_CAM_MAX_W], CZ[WL_CAM_MAX_W];   // per-column part of the ray direction
+    __shared__ float yo_s[WL_CAM_MAX_ROWS];
     __shared__ int n_white;
-    const int i = blockIdx.x, n = c.num_envs;
-    const int W = c.vis_cam_w, rows = c.vis_cam_h - c.vis_cam_row0, npix = W * rows;
+    const int i = blockIdx.x, n = c.num_envs, tid = threadIdx.x;
+    const int W = c.vis_cam_w, rows = c.vis_cam_h - c.vis_cam_row0, npix = W * rows, WP = W + 8, W4 = W >> 2;
+    const int RG = WL_CAM_THREADS / W4;                      // row groups (threads >= RG * W4 idle in the 2-D phases)
+    const int rg = tid / W4, u4 = tid - rg * W4;
+    const bool act = rg < RG;
     const uint32_t t = (t_arg == 0xFFFFFFFFu) ? __ldcg(&gl->step_counter) - 1u : t_arg;    // the step's epilogue already advanced it
     const VisualMap vm = visual_map(c, aux);
-    if (threadIdx.x == 0) n_white = 0;
     const float4 gp = ldg4(st, WL_G_POS, n, i), gq = ldg4(st, WL_G_QUAT, n, i);
     const M3 R = rotmat(gq.x, gq.y, gq.z, gq.w);
     const V3 off = rot(R, V3{c.vis_cam_pos[0], c.vis_cam_pos[1], c.vis_cam_pos[2]});
     const V3 pc{gp.x + off.x, gp.y + off.y, gp.z + off.z};
-    __syncthreads();
-    int mine = 0;
-    for (int k = threadIdx.x; k < npix; k += WL_CAM_THREADS) {
-        const int r = k / W, u = k - r * W;
-        const bool wh = cam_pixel_white(c, vm.map, R, pc, u, c.vis_cam_row0 + r);
-        J[k] = wh ? 1.0f : 0.0f;
-        mine += wh ? 1 : 0;
+    if (tid == 0) n_white = 0;
+    // pixel-centre coordinates of the optical frame (x right, y down, z forward) and the column part of R (1, -xo, -yo)
+    if (tid < W) {
+        const float xo = ((float)tid + 0.5f - c.vis_cam_cx) / c.vis_cam_fx;
+        CX[tid] = fm(-R.r[1], xo, R.r[0]); CY[tid] = fm(-R.r[4], xo, R.r[3]); CZ[tid] = fm(-R.r[7], xo, R.r[6]);
     }
-    mine = (int)warp_sum((float)mine);           // <= 25 * 32: exact in fp32
-    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&n_white, mine);
+    if (tid < rows) yo_s[tid] = ((float)(c.vis_cam_row0 + tid) + 0.5f - c.vis_cam_cy) / c.vis_cam_fy;
+    const bool bg = c.vis_cam_bg >= 0.5f, above = pc.z > 0.0f;
+    const float cmax = (float)(c.vis_cols - 1), rmax = (float)(c.vis_rows - 1);
     __syncthreads();
-    const CamAug A = cam_aug_params(c, t, stream, sub, aug, (float)n_white / (float)npix);
-    float* row = obs + (size_t)(WL_OBS_DIM_VISUAL + npix) * i;
-    if (c.vis_cam != 2) {                        // camera_data_rgb_flattened: grayscale + normalize only
-        for (int k = threadIdx.x * 4; k < npix; k += WL_CAM_THREADS * 4) {
-            float4 o;
-            o.x = fm(2.0f, cam_gray(J[k]), -1.0f); o.y = fm(2.0f, cam_gray(J[k + 1]), -1.0f);
-            o.z = fm(2.0f, cam_gray(J[k + 2]), -1.0f); o.w = fm(2.0f, cam_gray(J[k + 3]), -1.0f);
-            *reinterpret_cast<float4*>(row + k) = o;
+    // ---- render: ray through the pixel centre -> plane z = 0 -> face of the coloured mesh (utils/__init__.py:8-89)
+    int mine = 0;
+    if (act) {
+        const float4 cx = reinterpret_cast<const float4*>(CX)[u4], cy = reinterpret_cast<const float4*>(CY)[u4], cz = reinterpret_cast<const float4*>(CZ)[u4];
+        const float cxs[4] = {cx.x, cx.y, cx.z, cx.w}, cys[4] = {cy.x, cy.y, cy.z, cy.w}, czs[4] = {cz.x, cz.y, cz.z, cz.w};
+        for (int r = rg; r < rows; r += RG) {
+            const float yo = yo_s[r];
+            uint8_t wv[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float dz = fm(-R.r[8], yo, czs[j]);
+                bool wh = bg;
+                if (dz < 0.0f && above) {
+                    const float tt = pc.z / (-dz);                                  // depth along the optical axis
+                    if (!(tt > 100.0f)) {                                           // clipping_range = (0.01, 1e2)
+                        const float hx = fm(tt, fm(-R.r[2], yo, cxs[j]), pc.x), hy = fm(tt, fm(-R.r[5], yo, cys[j]), pc.y);
+                        const float fx = floorf((hx - c.vis_mesh_x0) * c.d_vis_mesh_inv_dx), fy = floorf((hy - c.vis_mesh_y0) * c.d_vis_mesh_inv_dy);
+                        wh = (fx >= 0.0f) && (fy >= 0.0f) && (fx < cmax) && (fy < rmax) && (__ldg(vm.map + (size_t)(int)fy * c.vis_cols + (int)fx) != 0);
+                    }
+                }
+                wv[j] = wh ? 1 : 0;
+                mine += wh ? 1 : 0;
+            }
+            *reinterpret_cast<uchar4*>(Jp + r * WP + 4 + 4 * u4) = make_uchar4(wv[0], wv[1], wv[2], wv[3]);
         }
+    }
+    mine = (int)warp_sum((float)mine);           // <= 32 * 64: exact in fp32
+    if ((tid & 31) == 0 && mine) atomicAdd(&n_white, mine);
+    __syncthreads();
+    if (tid == WL_CAM_THREADS - 1)                // one thread draws the frame's ColorJitter / blur parameters for the CTA
+        A_s = cam_aug_params(c, t, stream, sub, aug, (float)n_white / (float)npix);
+    float4* row4 = reinterpret_cast<float4*>(obs + (size_t)(WL_OBS_DIM_VISUAL + npix) * i);
+    if (c.vis_cam != 2) {                        // camera_data_rgb_flattened: grayscale + normalize only
+        const float g0 = fm(2.0f, cam_gray(0.0f), -1.0f), g1 = fm(2.0f, cam_gray(1.0f), -1.0f);
+        if (act)
+            for (int r = rg; r < rows; r += RG) {
+                const uchar4 m = *reinterpret_cast<const uchar4*>(Jp + r * WP + 4 + 4 * u4);
+                row4[r * W4 + u4] = make_float4(m.x ? g1 : g0, m.y ? g1 : g0, m.z ? g1 : g0, m.w ? g1 : g0);
+            }
         return;
     }
-    // horizontal pass (reflect: -1 -> 1, -2 -> 2, W -> W-2, W+1 -> W-3) on the jittered class values
-    for (int k = threadIdx.x; k < npix; k += WL_CAM_THREADS) {
-        const int r = k / W, u = k - r * W;
-        const float* Jr = J + r * W;
-        auto val = [&](int x) { x = x < 0 ? -x : (x >= W ? 2 * W - 2 - x : x); return Jr[x] != 0.0f ? A.v1 : A.v0; };
-        float acc = A.w0 * val(u);
-        acc = fm(A.w1, val(u - 1) + val(u + 1), acc);
-        acc = fm(A.w2, val(u - 2) + val(u + 2), acc);
-        Hb[k] = acc;
+    // reflected border columns: -1 -> 1, -2 -> 2, W -> W-2, W+1 -> W-3
+    if (tid < rows) {
+        uint8_t* jr = Jp + tid * WP + 4;
+        jr[-1] = jr[1]; jr[-2] = jr[2]; jr[W] = jr[W - 2]; jr[W + 1] = jr[W - 3];
     }
     __syncthreads();
-    // vertical pass + Grayscale + Normalize((x - 0.5) / 0.5), four pixels of one row per thread -> one STG.128
-    for (int k = threadIdx.x * 4; k < npix; k += WL_CAM_THREADS * 4) {
-        const int r = k / W, u = k - r * W;
-        auto rr = [&](int y) { return y < 0 ? -y : (y >= rows ? 2 * rows - 2 - y : y); };
-        const float* h0 = Hb + rr(r) * W + u;
-        const float* hm1 = Hb + rr(r - 1) * W + u; const float* hp1 = Hb + rr(r + 1) * W + u;
-        const float* hm2 = Hb + rr(r - 2) * W + u; const float* hp2 = Hb + rr(r + 2) * W + u;
-        float o[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            float acc = A.w0 * h0[j];
-            acc = fm(A.w1, hm1[j] + hp1[j], acc);
-            acc = fm(A.w2, hm2[j] + hp2[j], acc);
-            o[j] = fm(2.0f, cam_gray(acc), -1.0f);
+    const CamAug A = A_s;
+    // ---- horizontal 5-tap pass on the mask; padded row rp holds source row reflect(rp - 2)
+    if (act)
+        for (int rp = rg; rp < rows + 4; rp += RG) {
+            int r = rp - 2;
+            r = r < 0 ? -r : (r >= rows ? 2 * rows - 2 - r : r);
+            const uchar4* j4 = reinterpret_cast<const uchar4*>(Jp + r * WP) + u4;
+            const uchar4 Lb = j4[0], Mb = j4[1], Qb = j4[2];
+            const float4 L = make_float4(0.0f, 0.0f, (float)Lb.z, (float)Lb.w), M = make_float4((float)Mb.x, (float)Mb.y, (float)Mb.z, (float)Mb.w);
+            const float4 Q = make_float4((float)Qb.x, (float)Qb.y, 0.0f, 0.0f);
+            float4 o;
+            o.x = fm(A.w2, L.z + M.z, fm(A.w1, L.w + M.y, A.w0 * M.x));
+            o.y = fm(A.w2, L.w + M.w, fm(A.w1, M.x + M.z, A.w0 * M.y));
+            o.z = fm(A.w2, M.x + Q.x, fm(A.w1, M.y + M.w, A.w0 * M.z));
+            o.w = fm(A.w2, M.y + Q.y, fm(A.w1, M.z + Q.x, A.w0 * M.w));
+            reinterpret_cast<float4*>(Hp + rp * W)[u4] = o;
         }
-        *reinterpret_cast<float4*>(row + k) = make_float4(o[0], o[1], o[2], o[3]);
+    __syncthreads();
+    // ---- vertical pass, then the ColorJitter class values (blur is affine in the mask: J = v0 + (v1 - v0) w),
+    // Grayscale and Normalize((x - 0.5) / 0.5); one STG.128 per thread and row
+    if (act) {
+        const float dv = A.v1 - A.v0;
+        for (int r = rg; r < rows; r += RG) {
+            const float4* h = reinterpret_cast<const float4*>(Hp + r * W) + u4;      // padded rows r .. r+4 = source rows r-2 .. r+2
+            const float4 a = h[0], b = h[W4], m = h[2 * W4], d = h[3 * W4], e = h[4 * W4];
+            float4 o;
+            o.x = fm(2.0f, cam_gray(fm(dv, fm(A.w2, a.x + e.x, fm(A.w1, b.x + d.x, A.w0 * m.x)), A.v0)), -1.0f);
+            o.y = fm(2.0f, cam_gray(fm(dv, fm(A.w2, a.y + e.y, fm(A.w1, b.y + d.y, A.w0 * m.y)), A.v0)), -1.0f);
+            o.z = fm(2.0f, cam_gray(fm(dv, fm(A.w2, a.z + e.z, fm(A.w1, b.z + d.z, A.w0 * m.z)), A.v0)), -1.0f);
+            o.w = fm(2.0f, cam_gray(fm(dv, fm(A.w2, a.w + e.w, fm(A.w1, b.w + d.w, A.w0 * m.w)), A.v0)), -1.0f);
+            row4[r * W4 + u4] = o;
+        }
     }
 }
 
@@ -1038,6 +1088,8 @@ int wl_config_finalize(wl_config* c) {
     c->d_inv_dc_vel_limit = 1.0f / c->dc_vel_limit;
     c->d_inv_mass_nominal = 1.0f / c->mass_nominal;
     for (int a = 0; a < 3; ++a) c->d_invI_nominal[a] = 1.0f / c->inertia_nominal[a];
+    c->d_vis_mesh_inv_dx = c->vis_mesh_dx > 0.0f ? 1.0f / c->vis_mesh_dx : 0.0f;
+    c->d_vis_mesh_inv_dy = c->vis_mesh_dy > 0.0f ? 1.0f / c->vis_mesh_dy : 0.0f;
     return WL_OK;
 }
 
@@ -1059,9 +1111,9 @@ int wl_create(const wl_config* cfg, void* d_state, size_t state_bytes, const flo
         if (cfg->vis_cam) {
             const int rows = cfg->vis_cam_h - cfg->vis_cam_row0;
             if (cfg->vis_cam < 0 || cfg->vis_cam > 2 || cfg->vis_cam_w < 4 || (cfg->vis_cam_w & 3) || rows < 3 || cfg->vis_cam_row0 < 0 ||
-                cfg->vis_cam_w * rows > WL_CAM_MAX_PIXELS || !(cfg->vis_cam_fx > 0.0f) || !(cfg->vis_cam_fy > 0.0f) ||
+                cfg->vis_cam_w * rows > WL_CAM_MAX_PIXELS || cfg->vis_cam_w > 128 || rows > 64 || !(cfg->vis_cam_fx > 0.0f) || !(cfg->vis_cam_fy > 0.0f) ||
                 !(cfg->vis_mesh_dx > 0.0f) || !(cfg->vis_mesh_dy > 0.0f) || (cfg->vis_cam == 2 && !(cfg->vis_aug_sigma[0] > 0.0f)))
-                return fail(WL_EINVAL, "wl_create: bad camera geometry (width % 4 == 0, >= 3 kept rows, <= WL_CAM_MAX_PIXELS pixels)");
+                return fail(WL_EINVAL, "wl_create: bad camera geometry (width % 4 == 0 and <= 128, 3..64 kept rows, <= WL_CAM_MAX_PIXELS pixels)");
         }
     }
     if (cfg->task == WL_TASK_ELEVATION) {

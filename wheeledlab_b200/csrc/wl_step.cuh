@@ -511,7 +511,7 @@ __device__ __forceinline__ bool cam_pixel_white(const wl_config& c, const uint8_
     const float tt = pc.z / (-dz);                                          // depth along the optical axis
     if (tt > 100.0f) return bg;                                             // clipping_range = (0.01, 1e2)
     const float hx = fm(tt, dx, pc.x), hy = fm(tt, dy, pc.y);
-    const float fx = floorf((hx - c.vis_mesh_x0) / c.vis_mesh_dx), fy = floorf((hy - c.vis_mesh_y0) / c.vis_mesh_dy);
+    const float fx = floorf((hx - c.vis_mesh_x0) * c.d_vis_mesh_inv_dx), fy = floorf((hy - c.vis_mesh_y0) * c.d_vis_mesh_inv_dy);
     if (!(fx >= 0.0f) || !(fy >= 0.0f) || !(fx < (float)(c.vis_cols - 1)) || !(fy < (float)(c.vis_rows - 1))) return false;   // black base plane / void
     return __ldg(map + (size_t)(int)fy * c.vis_cols + (int)fx) != 0;
 }
