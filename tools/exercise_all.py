@@ -59,6 +59,10 @@ def main():
     es, _ = drive(wl.elevation_task(num_envs=70, seed=5), steps=2)
     es.set_scan_tma(False); es.step(es.synth_actions(99), 99)
     drive(wl.visual_task(num_envs=70, seed=6), steps=2)
+    vs, _ = drive(wl.visual_task(num_envs=33, seed=6, camera="aug"), steps=2)          # camera kernel (drawn parameters)
+    drive(wl.visual_task(num_envs=9, seed=6, camera="raw"), steps=1)
+    buf = torch.zeros((33, vs.obs_dim), device=dev)
+    vs.camera(3, buf, torch.tensor([1.1, 0.9, 1.2, 0.1, 1.5, 2, 0, 3, 1], dtype=torch.float32, device=dev))
     torch.cuda.synchronize()
     print("exercise_all ok")
 
