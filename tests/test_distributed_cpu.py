@@ -27,8 +27,10 @@ def _worker(rank, world, port, outdir):
     from oracle_lib import Oracle
     spec = wl.drift_task(num_envs=N_LOCAL, seed=5, env_id_offset=shard_offset(rank, N_LOCAL))
     orc = Oracle(spec.cfg); orc.startup(); orc.reset(None, 0)
-    slab = RolloutSlab(T, N_LOCAL, 14, 2, "cpu")
+    slab = RolloutSlab(T, N_LOCAL, 14, 2, "cpu", policy_fields=True)      # + values / log_prob / mean (written by wl_act_step on GPUs)
+    gid = torch.arange(N_LOCAL, dtype=torch.float32) + rank * N_LOCAL
     for t in range(T):
+        slab.values[t] = gid + 1000.0 * t; slab.log_prob[t] = -gid; slab.mean[t] = torch.stack([gid, gid + 0.5], dim=1)
         a = orc.synth_actions(t)
         obs, rew, term, trunc = orc.step(a, t)
         slab.actions[t] = torch.from_numpy(a); slab.obs[t] = torch.from_numpy(obs); slab.rewards[t] = torch.from_numpy(rew)
@@ -36,7 +38,8 @@ def _worker(rank, world, port, outdir):
     g = slab.all_gather()
     if rank == 0:
         np.savez(Path(outdir) / "gathered.npz", obs=g.cat("obs").numpy(), rewards=g.cat("rewards").numpy(),
-                 actions=g.cat("actions").numpy(), terminated=g.cat("terminated").numpy(), truncated=g.cat("truncated").numpy())
+                 actions=g.cat("actions").numpy(), terminated=g.cat("terminated").numpy(), truncated=g.cat("truncated").numpy(),
+                 values=g.cat("values").numpy(), log_prob=g.cat("log_prob").numpy(), mean=g.cat("mean").numpy())
     dist.barrier()
     dist.destroy_process_group()
 
@@ -57,6 +60,9 @@ def test_two_rank_gather_equals_single_run(tmp_path):
         assert np.array_equal(got["obs"][t].view(np.uint32), obs.view(np.uint32)), f"shard/gather mismatch at t={t}"
         assert np.array_equal(got["rewards"][t].view(np.uint32), rew.view(np.uint32))
         assert np.array_equal(got["terminated"][t], term) and np.array_equal(got["truncated"][t], trunc)
+    gid = np.arange(world * N_LOCAL, dtype=np.float32)          # policy fields: global env id = rank * N_local + local id
+    assert np.array_equal(got["values"], gid[None, :] + 1000.0 * np.arange(T, dtype=np.float32)[:, None])
+    assert np.array_equal(got["log_prob"][3], -gid) and np.array_equal(got["mean"][5], np.stack([gid, gid + 0.5], 1))
 
 
 def test_slab_layout_single_process():
@@ -69,3 +75,17 @@ def test_slab_layout_single_process():
     assert s.nbytes % 256 == 0
     obs, rew, term, trunc = s.step_outputs(1)
     assert obs.is_contiguous() and obs.data_ptr() == s.obs[1].data_ptr() and rew.shape == (8,)
+
+
+def test_rollout_recording_uses_the_reference_playback_format(tmp_path):
+    """play_policy.py:131-165: {'observations': [steps, N, D], 'actions': [steps, N, A]} torch-saved as <name>-rollouts.pt."""
+    import torch
+    from wheeledlab_b200.distributed import RolloutSlab
+    from wheeledlab_b200.recording import load_rollouts, save_slab
+    slab = RolloutSlab(6, 5, 14, 2, "cpu")
+    slab.obs.copy_(torch.arange(6 * 5 * 14, dtype=torch.float32).view(6, 5, 14)); slab.actions.fill_(0.25)
+    p = save_slab(str(tmp_path / "playback"), "demo", slab, steps=4)
+    assert p.endswith("demo-rollouts.pt")
+    d = load_rollouts(p)
+    assert d["observations"].shape == (4, 5, 14) and d["actions"].shape == (4, 5, 2)
+    assert torch.equal(d["observations"], slab.obs[:4]) and float(d["actions"].mean()) == 0.25

@@ -19,25 +19,33 @@ def shard_offset(rank: int, envs_per_rank: int) -> int:
 
 class RolloutSlab:
     """Per-rank rollout buffer in the layout the learner consumes: obs [T,N,D] f32, actions [T,N,A] f32,
-    rewards [T,N] f32, dones [T,N] u8 (terminated | truncated << 1).  One contiguous allocation per field so a single
-    all_gather_into_tensor per field moves it; fields are views of ONE flat byte buffer => one collective total."""
+    rewards [T,N] f32, terminated / truncated [T,N] u8 and -- with ``policy_fields`` -- what alg.act() records per step
+    (rsl_rl RolloutStorage: values [T,N], actions_log_prob [T,N], action_mean [T,N,A]; written by wl_act_step).  Fields are
+    views of ONE flat byte buffer, so ONE all_gather_into_tensor moves the whole slab."""
 
-    def __init__(self, T: int, n_local: int, obs_dim: int, act_dim: int, device):
+    def __init__(self, T: int, n_local: int, obs_dim: int, act_dim: int, device, policy_fields: bool = False):
         self.T, self.n, self.obs_dim, self.act_dim = T, n_local, obs_dim, act_dim
         self.device = torch.device(device)
+        # name -> (dtype, trailing shape)
+        self._fields = {"obs": (torch.float32, (obs_dim,)), "actions": (torch.float32, (act_dim,)), "rewards": (torch.float32, ()),
+                        "terminated": (torch.uint8, ()), "truncated": (torch.uint8, ())}
+        if policy_fields:
+            self._fields.update({"values": (torch.float32, ()), "log_prob": (torch.float32, ()), "mean": (torch.float32, (act_dim,))})
         f = T * n_local
-        self._sizes = {"obs": f * obs_dim * 4, "actions": f * act_dim * 4, "rewards": f * 4, "terminated": f, "truncated": f}
+        self._sizes = {}
+        for k, (dt, tail) in self._fields.items():
+            n_el = f
+            for d in tail:
+                n_el *= d
+            self._sizes[k] = n_el * (4 if dt == torch.float32 else 1)
         total = sum((v + 255) // 256 * 256 for v in self._sizes.values())
         self.flat = torch.zeros(total, dtype=torch.uint8, device=self.device)
-        off, v = 0, {}
+        off = 0
         for k, nbytes in self._sizes.items():
-            v[k] = self.flat[off: off + nbytes]
+            dt, tail = self._fields[k]
+            raw = self.flat[off: off + nbytes]
+            setattr(self, k, (raw.view(torch.float32) if dt == torch.float32 else raw).view(T, n_local, *tail))
             off += (nbytes + 255) // 256 * 256
-        self.obs = v["obs"].view(torch.float32).view(T, n_local, obs_dim)
-        self.actions = v["actions"].view(torch.float32).view(T, n_local, act_dim)
-        self.rewards = v["rewards"].view(torch.float32).view(T, n_local)
-        self.terminated = v["terminated"].view(T, n_local)
-        self.truncated = v["truncated"].view(T, n_local)
 
     @property
     def nbytes(self) -> int:
@@ -79,14 +87,8 @@ class GatheredRollout:
             off += (nbytes + 255) // 256 * 256
         else:
             raise KeyError(name)
-        w = self.buf.shape[0]
-        if name == "obs":
-            return raw.view(torch.float32).view(w, p.T, p.n, p.obs_dim)
-        if name == "actions":
-            return raw.view(torch.float32).view(w, p.T, p.n, p.act_dim)
-        if name == "rewards":
-            return raw.view(torch.float32).view(w, p.T, p.n)
-        return raw.view(w, p.T, p.n)
+        dt, tail = p._fields[name]
+        return (raw.view(torch.float32) if dt == torch.float32 else raw).view(self.buf.shape[0], p.T, p.n, *tail)
 
     def cat(self, name: str) -> torch.Tensor:
         f = self.field(name)                       # [W, T, N, ...] -> [T, W*N, ...]

@@ -9,6 +9,7 @@ rollout built on it.
 from __future__ import annotations
 
 import ctypes as C
+from types import SimpleNamespace
 
 import torch
 
@@ -79,8 +80,10 @@ class FusedPolicyRollout:
 
     def __init__(self, sim: WheeledSim, blob: torch.Tensor, T: int = 128, slab: RolloutSlab | None = None):
         self.sim, self.blob, self.T = sim, blob, T
-        self.slab = slab or RolloutSlab(T, sim.num_envs, sim.obs_dim, 2, sim.device)
-        self.pol = PolicyBuffers(T, sim.num_envs, sim.device)
+        self.slab = slab or RolloutSlab(T, sim.num_envs, sim.obs_dim, 2, sim.device, policy_fields=True)
+        # values / log-prob / mean go straight into the slab (= the all-gather send buffer) when it has those fields
+        self.pol = (SimpleNamespace(values=self.slab.values, log_prob=self.slab.log_prob, mean=self.slab.mean)
+                    if hasattr(self.slab, "values") else PolicyBuffers(T, sim.num_envs, sim.device))
         self.logs = torch.zeros((T, 16), dtype=torch.float32, device=sim.device)
         self.obs0 = torch.empty((sim.num_envs, sim.obs_dim), dtype=torch.float32, device=sim.device)
         self.graph = None
