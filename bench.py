@@ -306,13 +306,13 @@ def run_ours(args):
     env = wl.ManagerBasedRLEnv(wl.drift_task(num_envs=E, seed=args.seed, env_id_offset=rank * E), device=dev)
     env.reset()
     h_act = acts.cpu().pin_memory()
-    h_in = env.host_action_buffer                       # pinned [E,2]: the host-side policy writes actions here
+    h_rows = [h_act[k] for k in range(W + K)]           # row views of the pinned block (what a host-side policy hands over)
 
     def e2e_step(k):
         # the call a host-side user makes: host actions in, host reward / done masks out (one C-ABI call inside:
         # H2D actions -> fused step -> D2H results -> stream sync); observations stay on the device for the policy
-        h_in.copy_(h_act[k % (W + K)])
-        obs, rew, term, trunc, extras = env.step_host(h_in)
+        # h_rows[k]: this step's actions in PINNED host memory (a different block every step), read in place
+        obs, rew, term, trunc, extras = env.step_host(h_rows[k % (W + K)])
         return rew, term, trunc
 
     def time_e2e(transport):

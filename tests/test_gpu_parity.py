@@ -365,12 +365,20 @@ def test_step_host_matches_device_step():
     a.reset(); b.reset()
     h_in = b.host_action_buffer
     assert h_in.is_pinned()
+    pinned_block = torch.empty((40, 512, 2)).pin_memory()
+    pinned_rows = [pinned_block[t] for t in range(40)]
     for t in range(40):
-        b.host_transport = "zero_copy" if t % 2 else "copy"
+        b.host_transport = "zero_copy" if (t // 4) % 2 else "copy"      # every input kind under both transports
         act = a.sim.synth_actions(t)
+        pinned_rows[t].copy_(act.cpu())
         oa, ra, ta, ua, _ = a.step(act)
-        h_in.copy_(act.cpu())
-        ob, rb, tb, ub, ex = b.step_host(h_in)
+        if t % 4 < 2:
+            h_in.copy_(act.cpu())
+            ob, rb, tb, ub, ex = b.step_host(h_in)                       # the env's own pinned buffer
+        elif t % 4 == 2:
+            ob, rb, tb, ub, ex = b.step_host(pinned_rows[t])             # a pinned block of the caller: read in place
+        else:
+            ob, rb, tb, ub, ex = b.step_host(act.cpu())                  # pageable memory: staged through the env's buffer
         assert rb.device.type == "cpu" and tb.dtype == torch.bool
         assert torch.equal(oa["policy"], ob["policy"]) and torch.equal(ra.cpu(), rb) and torch.equal(ta.cpu(), tb) and torch.equal(ua.cpu(), ub)
         assert float(ex["log"]["Episode_Termination/time_out"]) >= 0

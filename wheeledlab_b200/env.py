@@ -267,6 +267,7 @@ class ManagerBasedRLEnv:
         self._log_index = {"Episode_Reward/" + n: k for k, n in enumerate(self.spec.reward_names)}
         self._log_index.update({"Episode_Termination/" + n: 9 + j for j, (n, _) in enumerate(self.spec.termination_names)})
         self._host_io = None
+        self._pinned_ptrs = {}                   # data_ptr -> c_void_p of caller buffers known to be pinned [N,2] f32
         self._ring = None
         self.host_transport = "zero_copy"        # or "copy": staged H2D / D2H copies (wl_step_host)
         # host-side (Python) MDP terms: evaluated between the two halves of the staged step (see add_reward_term)
@@ -441,7 +442,21 @@ class ManagerBasedRLEnv:
         if self._host_io is None:
             self._host_io = self.sim.make_host_io()
         io = self._host_io
-        if action_host.data_ptr() != io["h_action"].data_ptr():
+        # a pinned, contiguous f32 block of the caller is read in place (DMA / PCIe reads straight from it); anything else is
+        # staged through the env's own pinned buffer
+        ptr = action_host.data_ptr()
+        if ptr == io["h_action"].data_ptr():
+            p_action = None
+        elif (action_host.dtype == torch.float32 and action_host.is_contiguous() and action_host.shape == (self.num_envs, 2)
+              and action_host.is_pinned()):                  # (queried every call: an address may be reused by pageable memory)
+            p_action = self._pinned_ptrs.get(ptr)
+            if p_action is None:
+                import ctypes as C
+                if len(self._pinned_ptrs) > 65536:
+                    self._pinned_ptrs.clear()
+                p_action = self._pinned_ptrs[ptr] = C.c_void_p(ptr)
+        else:
+            p_action = None
             io["h_action"].copy_(action_host)
         t = self.common_step_counter
         # outputs come from a ring of preallocated device buffers (valid for _RING steps, like IsaacLab's own reuse)
@@ -457,9 +472,9 @@ class ManagerBasedRLEnv:
         if not self.log_episode_info:
             log, p_log = None, None
         if self.host_transport == "zero_copy":
-            self.sim.step_host_zero_copy(io, t, obs, log, p_obs, p_log)
+            self.sim.step_host_zero_copy(io, t, obs, log, p_obs, p_log, p_action)
         else:
-            self.sim.step_host(io, t, obs, log)
+            self.sim.step_host(io, t, obs, log, p_action=p_action)
         self.common_step_counter = t + 1
         tm = self.termination_manager
         tm.terminated, tm.time_outs = io["terminated"], io["truncated"]

@@ -129,21 +129,24 @@ class WheeledSim:
         io["_p_h_result"] = C.c_void_p(io["h_result"].data_ptr())
         return io
 
-    def step_host_zero_copy(self, io, step_counter: int, obs: torch.Tensor, log: torch.Tensor | None = None, p_obs=None, p_log=None):
+    def step_host_zero_copy(self, io, step_counter: int, obs: torch.Tensor, log: torch.Tensor | None = None, p_obs=None, p_log=None,
+                            p_action=None):
         """Zero-copy transport of the same contract: the kernel reads io.h_action / writes io.h_result over PCIe.
-        p_obs / p_log: optional pre-built c_void_p of obs / log (saves two ctypes conversions per step)."""
+        p_obs / p_log: optional pre-built c_void_p of obs / log (saves two ctypes conversions per step); p_action: pointer
+        of the CALLER's pinned [N,2] f32 action block, read in place instead of io.h_action."""
         if p_obs is None:
             p_obs = C.c_void_p(obs.data_ptr())
             p_log = C.c_void_p(log.data_ptr()) if log is not None else None
-        rc = lib.wl_step_host_zero_copy(self._h, io["_p_h_action"], p_obs, p_log, io["_p_h_result"], step_counter,
-                                        _stream_ptr(self.device))
+        rc = lib.wl_step_host_zero_copy(self._h, p_action if p_action is not None else io["_p_h_action"], p_obs, p_log,
+                                        io["_p_h_result"], step_counter, _stream_ptr(self.device))
         if rc:
             check(rc, "wl_step_host_zero_copy")
 
-    def step_host(self, io, step_counter: int, obs: torch.Tensor, log: torch.Tensor | None = None, h_obs: torch.Tensor | None = None):
+    def step_host(self, io, step_counter: int, obs: torch.Tensor, log: torch.Tensor | None = None, h_obs: torch.Tensor | None = None,
+                  p_action=None):
         """ONE C call: H2D(io.h_action) -> fused step -> D2H(reward | terminated | truncated) -> stream sync.
         Results are in io["rew"], io["terminated"], io["truncated"] (pinned host views); obs stays on the device."""
-        check(lib.wl_step_host(self._h, C.c_void_p(io["h_action"].data_ptr()), C.c_void_p(io["d_action"].data_ptr()),
+        check(lib.wl_step_host(self._h, p_action if p_action is not None else io["_p_h_action"], C.c_void_p(io["d_action"].data_ptr()),
                                C.c_void_p(obs.data_ptr()), C.c_void_p(io["d_result"].data_ptr()),
                                C.c_void_p(log.data_ptr()) if log is not None else None,
                                C.c_void_p(io["h_result"].data_ptr()),
