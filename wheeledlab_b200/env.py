@@ -467,8 +467,8 @@ class ManagerBasedRLEnv:
             for _ in range(self._RING):
                 o = torch.empty((self.num_envs, self.spec.obs_dim), dtype=torch.float32, device=self.device)
                 lg = torch.empty(16, dtype=torch.float32, device=self.device)
-                self._ring.append((o, lg, C.c_void_p(o.data_ptr()), C.c_void_p(lg.data_ptr())))
-        obs, log, p_obs, p_log = self._ring[k]
+                self._ring.append((o, lg, C.c_void_p(o.data_ptr()), C.c_void_p(lg.data_ptr()), _LazyLog(lg, self._log_index)))
+        obs, log, p_obs, p_log, lazy = self._ring[k]
         if not self.log_episode_info:
             log, p_log = None, None
         if self.host_transport == "zero_copy":
@@ -479,7 +479,7 @@ class ManagerBasedRLEnv:
         tm = self.termination_manager
         tm.terminated, tm.time_outs = io["terminated"], io["truncated"]
         if log is not None:
-            self.extras["log"] = _LazyLog(log, self._log_index)
+            self.extras["log"] = lazy                    # one lazy view per ring slot (its row tensor never changes)
         return {"policy": obs}, io["rew"], io["terminated"], io["truncated"], self.extras
 
     @property
