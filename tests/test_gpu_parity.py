@@ -705,3 +705,53 @@ def test_visual_camera_observation_bit_exact(mode):
     with pytest.raises(wl.WlError):                      # single-launch rollout cannot host the second kernel
         from wheeledlab_b200.distributed import RolloutSlab
         sim.rollout(4, 100, RolloutSlab(4, n, 3208, 2, "cuda:0"), torch.empty((4, 16), device="cuda"))
+
+
+def test_edge_sizes_and_error_paths():
+    """N = 1 and ragged N through every entry point added late (staged step, fused policy, camera, GAE, fused rollout),
+    empty reset list, and the loud failures of the C-ABI (null / misaligned pointers, wrong task)."""
+    _need_gpu()
+    import ctypes as C
+    import wheeledlab_b200 as wl
+    from wheeledlab_b200.distributed import RolloutSlab
+    from wheeledlab_b200.learner import compute_returns
+    from wheeledlab_b200.policy import act_step, pack_actor_critic
+    dev = "cuda"
+    actor, critic, std = _actor_critic(1)
+    for n in (1, 3, 33):
+        a = wl.WheeledSim(wl.drift_task(num_envs=n, seed=2), "cuda:0"); b = wl.WheeledSim(wl.drift_task(num_envs=n, seed=2), "cuda:0")
+        orc = O.Oracle(a.spec.cfg); orc.startup(); orc.reset(None, 0)
+        for s_ in (a, b):
+            s_.startup(); s_.reset(None, 0)
+            s_.reset(torch.empty(0, dtype=torch.int64, device=dev), 0)          # empty id list: a no-op
+        for t in range(6):
+            act = a.synth_actions(t)
+            obs, rew, term, trunc = a.step(act, t)
+            rew_b, bits = b.step_stage_a(act, t); obs_b, term_b, trunc_b = b.step_stage_b(bits, t)
+            o_obs, o_rew, _, _ = orc.step(act.cpu().numpy(), t)
+            assert torch.equal(obs, obs_b) and torch.equal(rew, rew_b) and np.array_equal(_bits(obs.cpu().numpy()), _bits(o_obs))
+        blob = pack_actor_critic(actor, critic, std, 14, "cuda:0")
+        pa = torch.empty((n, 2), device=dev); pm = torch.empty((n, 2), device=dev); lp = torch.empty(n, device=dev); val = torch.empty(n, device=dev)
+        out = (torch.empty((n, 14), device=dev), torch.empty(n, device=dev), torch.empty(n, dtype=torch.uint8, device=dev), torch.empty(n, dtype=torch.uint8, device=dev))
+        act_step(a, obs, blob, pa, pm, lp, val, out, None, 6)
+        ref = b.step(pa.clone(), 6)
+        assert all(torch.equal(x, y) for x, y in zip(out, ref)) and torch.allclose(pm, actor(obs), rtol=2e-5, atol=2e-5)
+        slab = RolloutSlab(5, n, 14, 2, "cuda:0"); logs = torch.empty((5, 16), device=dev)
+        a.rollout(5, 7, slab, logs)
+        assert torch.isfinite(slab.obs).all()
+        ret, adv = compute_returns(slab.rewards, torch.zeros_like(slab.rewards), torch.zeros(n, device=dev), slab.terminated | slab.truncated, 0.99, 0.95)
+        assert torch.isfinite(ret).all() and ret.shape == (5, n)
+    cam = wl.WheeledSim(wl.visual_task(num_envs=1, seed=3, camera="aug"), "cuda:0"); cam.startup(); cam.reset(None, 0)
+    oc = O.Oracle(cam.spec.cfg, heightfield=cam.spec.heightfield); oc.startup(); oc.reset(None, 0)
+    assert np.array_equal(_bits(cam.observe(0).cpu().numpy()), _bits(oc.observe(0)))
+    # loud failures
+    sim = wl.WheeledSim(wl.drift_task(num_envs=4, seed=1), "cuda:0")
+    buf = torch.zeros(64, device=dev)
+    assert wl.lib.wl_step(sim._h, None, None, None, None, None, None, 0, None) < 0               # null pointers
+    assert wl.lib.wl_step(sim._h, C.c_void_p(buf.data_ptr() + 4), C.c_void_p(buf.data_ptr()), C.c_void_p(buf.data_ptr()), C.c_void_p(buf.data_ptr()),
+                          C.c_void_p(buf.data_ptr()), None, 0, None) < 0                      # action not 8-byte aligned
+    assert b"aligned" in wl.lib.wl_last_error()
+    with pytest.raises(wl.WlError):
+        sim.camera(0, torch.zeros((4, 14), device=dev))                                       # no camera term on a drift handle
+    with pytest.raises(wl.WlError):
+        sim.step_stage_a(sim.synth_actions(0), -1)                                            # the staged step needs the host counter
