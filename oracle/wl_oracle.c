@@ -14,6 +14,9 @@
  *   - The rigid-body / tyre / actuator integrator stands in for PhysX-5 (closed
  *     binary, absent from /root/reference and from this image): PARITY UNPINNED at
  *     the PhysX boundary.  The model is builder-defined (DESIGN.md "Physics model").
+ *   - Visual task camera: the post-processing (crop, ColorJitter, GaussianBlur, Grayscale, Normalize) is PINNED by
+ *     golden vectors from the reference's own torchvision functions; the renderer that feeds it stands in for the RTX
+ *     tiled camera (not available): PARITY UNPINNED at the pixel level.
  *
  * Arithmetic contract shared with the CUDA path (so results are bit-identical):
  * IEEE fp32, no FMA contraction (-ffp-contract=off here, -fmad=false there),
