@@ -498,24 +498,6 @@ __device__ __forceinline__ CamAug cam_aug_params(const wl_config& c, uint32_t t,
     A.w0 = 1.0f / S; A.w1 = e1 / S; A.w2 = e2 / S;
     return A;
 }
-// is pixel (u, v) white?  ray through the pixel centre -> plane z = 0 -> face of the coloured mesh (utils/__init__.py:8-89)
-__device__ __forceinline__ bool cam_pixel_white(const wl_config& c, const uint8_t* __restrict__ map, const M3& R, const V3& pc, int u, int v) {
-    const float xo = ((float)u + 0.5f - c.vis_cam_cx) / c.vis_cam_fx;       // optical frame: x right, y down, z forward
-    const float yo = ((float)v + 0.5f - c.vis_cam_cy) / c.vis_cam_fy;
-    // link frame (x forward, y left, z up): d = (1, -xo, -yo); world: R d
-    const float dx = fm(-R.r[2], yo, fm(-R.r[1], xo, R.r[0]));
-    const float dy = fm(-R.r[5], yo, fm(-R.r[4], xo, R.r[3]));
-    const float dz = fm(-R.r[8], yo, fm(-R.r[7], xo, R.r[6]));
-    const bool bg = c.vis_cam_bg >= 0.5f;
-    if (!(dz < 0.0f) || !(pc.z > 0.0f)) return bg;
-    const float tt = pc.z / (-dz);                                          // depth along the optical axis
-    if (tt > 100.0f) return bg;                                             // clipping_range = (0.01, 1e2)
-    const float hx = fm(tt, dx, pc.x), hy = fm(tt, dy, pc.y);
-    const float fx = floorf((hx - c.vis_mesh_x0) * c.d_vis_mesh_inv_dx), fy = floorf((hy - c.vis_mesh_y0) * c.d_vis_mesh_inv_dy);
-    if (!(fx >= 0.0f) || !(fy >= 0.0f) || !(fx < (float)(c.vis_cols - 1)) || !(fy < (float)(c.vis_rows - 1))) return false;   // black base plane / void
-    return __ldg(map + (size_t)(int)fy * c.vis_cols + (int)fx) != 0;
-}
-
 __device__ __forceinline__ uint32_t visual_terms(const wl_config& c, const VisualMap& vm, const EnvState& e, V3 vb, bool time_out,
                                                  float f[WL_MAX_REW_TERMS]) {
     int xi = (int)((e.p.x + c.vis_width / 2.0f + c.vis_row_spacing / 2.0f) / c.vis_row_spacing);
