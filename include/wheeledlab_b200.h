@@ -37,7 +37,7 @@ extern "C" {
 /* tasks (gym ids, wheeledlab_tasks/__init__.py:14-63) */
 #define WL_TASK_DRIFT     0  /* Isaac-MushrDriftRL-v0, Isaac-F1TenthDriftRL-v0 */
 #define WL_TASK_ELEVATION 1  /* Isaac-MushrElevationRL-v0 */
-#define WL_TASK_VISUAL    2  /* Isaac-MushrVisualRL-v0 (physics/reward side; camera out of scope) */
+#define WL_TASK_VISUAL    2  /* Isaac-MushrVisualRL-v0 (physics/reward side + the software camera term, vis_cam) */
 
 /* action term kinds (wheeledlab/envs/mdp/actions/ *.py) */
 #define WL_ACT_ACKERMANN 0   /* ackermann_actions.py:150-201 */
@@ -229,7 +229,7 @@ extern "C" {
     XS(float, f32, elev_goal_dist)                                                                 \
     XS(float, f32, elev_fall_vel)                                                                  \
     XS(float, f32, elev_plane_z)      /* 0.19 in higher_elevation, :166-173 */                     \
-    /* --- visual task, physics side (visual/mushr_visual_env_cfg.py; camera out of scope) --- */    \
+    /* --- visual task, physics side (visual/mushr_visual_env_cfg.py); the camera term follows --- */ \
     XS(int32_t, i32, vis_rows)        /* traversability map [rows(y), cols(x)], :73-75 */          \
     XS(int32_t, i32, vis_cols)                                                                     \
     XS(int32_t, i32, vis_n_trav)      /* number of traversable cells (spawn candidates) */         \
