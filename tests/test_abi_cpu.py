@@ -61,3 +61,21 @@ def test_product_never_imports_oracle():
     for f in list(pkg.rglob("*.py")) + list(pkg.rglob("*.cu")) + list(pkg.rglob("*.cuh")):
         txt = f.read_text()
         assert "oracle" not in txt.replace("the oracle", "").replace("CPU oracle", "").replace("oracle/wl_oracle.c", "").replace("build_oracle", "").replace('"oracle"', "").replace("oracle's", "") or f.name == "build.py", f
+
+
+def test_plain_c_host_example_builds_against_the_abi(tmp_path):
+    """examples/c_host: a gcc program that includes only include/wheeledlab_b200.h and links the in-tree .so + libcudart
+    (no compute here: it needs a GPU to run; tests/test_gpu_parity.py runs it)."""
+    import shutil
+    import subprocess
+    root = Path(__file__).resolve().parent.parent
+    if not Path("/usr/local/cuda/include/cuda_runtime_api.h").exists():
+        pytest.skip("CUDA toolkit headers not present")
+    ex = root / "examples" / "c_host"
+    subprocess.run(["make", "-C", str(ex), "clean"], check=True, stdout=subprocess.DEVNULL)
+    subprocess.run(["make", "-C", str(ex), "CC=" + (shutil.which("gcc", path="/usr/bin") or "gcc")], check=True, stdout=subprocess.DEVNULL)
+    assert (ex / "wl_c_host").exists()
+    from wheeledlab_b200.dump_config import dump
+    from wheeledlab_b200._lib import WlConfig
+    import ctypes as C
+    assert dump("drift", 64, str(tmp_path / "cfg.bin")) == C.sizeof(WlConfig)

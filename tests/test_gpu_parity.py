@@ -755,3 +755,30 @@ def test_edge_sizes_and_error_paths():
         sim.camera(0, torch.zeros((4, 14), device=dev))                                       # no camera term on a drift handle
     with pytest.raises(wl.WlError):
         sim.step_stage_a(sim.synth_actions(0), -1)                                            # the staged step needs the host counter
+
+
+def test_c_host_example_matches_python_path(tmp_path):
+    """examples/c_host/wl_c_host (plain C on the C-ABI: cudaMalloc'd buffers, a config blob, no Python/torch in the process)
+    returns bit-for-bit what the Python host gets for the same task: order-independent sums of the output bit patterns."""
+    _need_gpu()
+    import json
+    import shutil
+    import subprocess
+    import wheeledlab_b200 as wl
+    from wheeledlab_b200.dump_config import dump
+    root = Path(__file__).resolve().parent.parent
+    ex = root / "examples" / "c_host"
+    subprocess.run(["make", "-C", str(ex), "CC=" + (shutil.which("gcc", path="/usr/bin") or "gcc")], check=True, stdout=subprocess.DEVNULL)
+    n, steps = 1000, 300
+    dump("drift", n, str(tmp_path / "cfg.bin"), seed=9)
+    r = subprocess.run([str(ex / "wl_c_host"), str(tmp_path / "cfg.bin"), str(steps)], check=True, capture_output=True, text=True, timeout=120)
+    got = json.loads(r.stdout.strip().splitlines()[-1])
+    sim = wl.WheeledSim(wl.drift_task(num_envs=n, seed=9), "cuda:0"); sim.startup(); sim.reset(None, 0)
+    obs_sum = rew_sum = n_term = n_trunc = 0
+    for t in range(steps):
+        obs, rew, term, trunc = sim.step(sim.synth_actions(t), t)
+        obs_sum += int(obs.cpu().numpy().view(np.uint32).astype(np.uint64).sum()); rew_sum += int(rew.cpu().numpy().view(np.uint32).astype(np.uint64).sum())
+        n_term += int(term.sum()); n_trunc += int(trunc.sum())
+    assert got["envs"] == n and got["steps"] == steps and "sm_100a" in got["build"]
+    assert (got["obs_bits_sum"], got["rew_bits_sum"], got["terminated"], got["truncated"]) == (obs_sum, rew_sum, n_term, n_trunc)
+    assert n_trunc >= n                                            # the 250-step time-out was crossed
