@@ -2,6 +2,7 @@
 Bit-exact for every output (the arithmetic contract makes fp32 results identical), including done masks
 and reset indices, over trajectories long enough to contain many auto-resets."""
 import ctypes as C
+from pathlib import Path
 
 import numpy as np
 import pytest
