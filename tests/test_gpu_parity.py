@@ -782,4 +782,4 @@ def test_c_host_example_matches_python_path(tmp_path):
         n_term += int(term.sum()); n_trunc += int(trunc.sum())
     assert got["envs"] == n and got["steps"] == steps and "sm_100a" in got["build"]
     assert (got["obs_bits_sum"], got["rew_bits_sum"], got["terminated"], got["truncated"]) == (obs_sum, rew_sum, n_term, n_trunc)
-    assert n_trunc >= n                                            # the 250-step time-out was crossed
+    assert n_trunc > 0 and n_term > 0                              # the run crossed the 250-step time-out and saw off-track resets
