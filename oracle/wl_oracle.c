@@ -1197,6 +1197,12 @@ int wlo_detmath(int32_t op, const float* in, const float* in2, float* out, int32
     }
     return 0;
 }
+/* DCMotor torque (a7) for given gains / targets / joint speeds: out[i] = clip(kd (target - omega), speed-dependent limits) */
+int wlo_dc_motor(const wl_config* c_in, float kd, float effort_limit, const float* target, const float* omega, float* out, int32_t n) {
+    wl_config cc = *c_in; config_finalize(&cc);
+    for (int i = 0; i < n; ++i) out[i] = (float)dc_motor(&cc, (real)kd, (real)effort_limit, (real)target[i], (real)omega[i]);
+    return 0;
+}
 /* camera term alone: aug = NULL draws the parameters; obs rows have the full visual stride */
 int wlo_camera(wlo_sim* s, float* obs, int64_t step_counter, const float* aug) {
     const wl_config* c = &s->cfg;

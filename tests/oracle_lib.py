@@ -40,6 +40,7 @@ def _load(name):
     lib.wlo_euler_xyz.argtypes = [vp, vp, i32]
     lib.wlo_drift_reset_pose.argtypes = [vp, vp, vp, vp, vp, i32]
     lib.wlo_elev_terms.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32]
+    lib.wlo_dc_motor.argtypes = [vp, C.c_float, C.c_float, vp, vp, vp, i32]
     lib.wlo_camera.argtypes = [vp, vp, i64, vp]
     lib.wlo_camera_post.argtypes = [vp, vp, vp, vp, i32]
     lib.wlo_camera_render.argtypes = [vp, i32, vp]
@@ -168,6 +169,13 @@ def detmath(op, x, x2=None, kind="f32"):
     x2 = x if x2 is None else np.ascontiguousarray(x2, np.float32)
     out = np.empty_like(x)
     assert lib.wlo_detmath(op, _p(x), _p(x2), _p(out), x.size) == 0
+    return out
+
+
+def dc_motor(cfg, kd, effort_limit, target, omega):
+    t = np.ascontiguousarray(target, np.float32); w = np.ascontiguousarray(omega, np.float32)
+    out = np.empty_like(t)
+    assert get_lib().wlo_dc_motor(C.byref(cfg), kd, effort_limit, _p(t), _p(w), _p(out), t.size) == 0
     return out
 
 

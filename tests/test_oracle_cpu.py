@@ -281,3 +281,22 @@ def test_camera_render_matches_closed_form_geometry():
     obs = orc.observe(0)
     cam = obs[:, :3200]
     assert obs.shape == (3, 3208) and np.all((np.abs(cam + 1.0) < 1e-6) | (np.abs(cam - 0.9998) < 1e-6))
+
+
+def test_dc_motor_speed_dependent_clip():
+    """DCMotor (IsaacLab actuator_pd.py semantics with the HOUND parameters, hound.py:13-21,40-43): tau = kd (w_t - w)
+    clipped to [max(-eff, sat (-1 - w/w_lim)), min(eff, sat (1 - w/w_lim))], sat = 1.05, w_lim = 450 rad/s."""
+    c = _cfg(num_envs=1).cfg
+    assert abs(c.dc_saturation - 1.05) < 1e-6 and abs(c.dc_vel_limit - 450.0) < 1e-3
+    big = np.array([1e6, -1e6], np.float32)
+    # at rest the clip is +- effort (0.5 N m rear-drive, 0.25 4WD): saturation torque 1.05 exceeds both
+    assert np.allclose(O.dc_motor(c, 1000.0, 0.5, big, np.zeros(2)), [0.5, -0.5])
+    assert np.allclose(O.dc_motor(c, 1000.0, 0.25, big, np.zeros(2)), [0.25, -0.25])
+    # at the velocity limit no forward torque is left; braking torque is still available
+    assert np.allclose(O.dc_motor(c, 1000.0, 0.5, big, np.full(2, 450.0)), [0.0, -0.5])
+    # above w_lim (1 - 0.5/1.05) the available forward torque falls below the effort limit: linear taper
+    w = np.float32(450.0 * (1 - 0.3 / 1.05))
+    assert np.allclose(O.dc_motor(c, 1000.0, 0.5, big[:1], np.array([w])), [0.3], atol=1e-5)
+    # inside the limits the law is the plain damper; a passive joint (effort 0, 2WD front wheels) gives nothing
+    assert np.allclose(O.dc_motor(c, 20.0, 0.5, np.array([10.0]), np.array([9.99])), [0.2], atol=1e-4)
+    assert np.allclose(O.dc_motor(c, 20.0, 0.0, np.array([10.0]), np.array([0.0])), [0.0])
