@@ -374,7 +374,8 @@ int wl_step(wl_sim* sim, const float* d_action, float* d_obs, float* d_rew, uint
  * (then U[-1,1]^2 is drawn in-kernel from the counter-based generator; d_actions_out, if not NULL, receives them).
  * Outputs are [K,N,...] slabs; d_log is [K, WL_LOG_FLOATS].  Bit-identical to K wl_step calls.  With curriculum terms
  * configured, [step_counter, step_counter+K) must end at or before the next episode boundary of the global counter
- * (the boundary's weight update happens between launches).  Drift / Visual only (Elevation needs its scan kernel). */
+ * (the boundary's weight update happens between launches).  Drift / Visual without the camera term only (the Elevation
+ * scan and the Visual camera are second kernels). */
 int wl_rollout(wl_sim* sim, int32_t K, const float* d_actions, float* d_actions_out, float* d_obs, float* d_rew,
                uint8_t* d_terminated, uint8_t* d_truncated, float* d_log, int64_t step_counter, void* stream);
 /* env.step() for a HOST-side caller, host buffers in, host buffers out, one call:
@@ -390,6 +391,7 @@ int wl_step_host(wl_sim* sim, const float* h_action, float* d_action, float* d_o
  * pin_memory: device-addressable under unified addressing).  The step kernel reads the actions from and writes
  * reward / terminated / truncated to host memory directly over PCIe -- no staging copies, no extra launches -- then
  * the stream is synchronised.  Bytes crossing the bus per step are identical to wl_step_host. */
+ /* (h_action may be any pinned [N,2] f32 block of the caller -- it is read in place.) */
 int wl_step_host_zero_copy(wl_sim* sim, const float* h_action, float* d_obs, float* d_log, void* h_result,
                            int64_t step_counter, void* stream);
 /* observation_manager.compute(): re-samples the noise. call_idx distinguishes
@@ -464,7 +466,7 @@ int wl_gae(const float* d_rewards, const float* d_values, const float* d_last_va
            int32_t N, void* stream);
 
 /* ---- test hooks (bit-exactness of the deterministic math vs the oracle) ------ */
-/* op: 0 sin,1 cos,2 atan,3 atan2(x=in,y=in2),4 log,5 tan,6 asin ; out[n] */
+/* op: 0 sin,1 cos,2 atan,3 atan2(x=in,y=in2),4 log,5 tan,6 asin,7 exp (x <= 0) ; out[n] */
 int wl_test_detmath(int32_t op, const float* d_in, const float* d_in2, float* d_out, int32_t n,
                     void* stream);
 /* philox4x32-10: out[4*n] for counters (c0_base + i, c1, c2, c3), key from seed */
