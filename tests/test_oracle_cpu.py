@@ -300,3 +300,86 @@ def test_dc_motor_speed_dependent_clip():
     # inside the limits the law is the plain damper; a passive joint (effort 0, 2WD front wheels) gives nothing
     assert np.allclose(O.dc_motor(c, 20.0, 0.5, np.array([10.0]), np.array([9.99])), [0.2], atol=1e-4)
     assert np.allclose(O.dc_motor(c, 20.0, 0.0, np.array([10.0]), np.array([0.0])), [0.0])
+
+
+# ---- behaviour of the builder-defined vehicle model (parity unpinned vs PhysX: these are the self-consistency checks) ----
+def _open_plane(n=1):
+    """Visual-task physics: flat 250 m plane, 4WD MuSHR, no DR / pushes / noise, 0.2 s per env.step, 10 s episodes."""
+    import wheeledlab_b200 as wl
+    spec = wl.visual_task(num_envs=n, seed=3, traversability=np.ones((500, 500), dtype=bool))
+    o = O.Oracle(spec.cfg, heightfield=spec.heightfield)
+    o.startup(); o.reset(None, 0)
+    st = o.export_state()
+    st[0, :, 0:2] = 0.0                                   # at the origin, heading +x, at rest
+    st[1, :, :] = [1.0, 0.0, 0.0, 0.0]
+    st[2, :, 0:3] = 0.0; st[3, :, 0:3] = 0.0; st[4] = 0.0
+    o.import_state(st)
+    return spec, o
+
+
+def _run(o, action, steps, t0=0):
+    rows = []
+    a = np.tile(np.asarray(action, np.float32), (o.n, 1))
+    for t in range(steps):
+        o.step(a, t0 + t)
+        st = o.export_state()
+        rows.append((st[0, 0, :3].copy(), st[1, 0].copy(), st[2, 0, :3].copy(), st[3, 0, :3].copy(), st[4, 0].copy()))
+    return rows
+
+
+def test_vehicle_settles_at_rest_under_zero_action():
+    """At rest the model keeps a small limit cycle instead of sleeping (KNOWN ARTEFACT, DESIGN.md 3 / docs/next_round_notes.md 6):
+    the explicit DCMotor damper (kd = 1000 N m s/rad against a 1.4e-4 kg m^2 wheel, torque held over the 4 sub-steps of a
+    physics step) chatters between its +-0.25 N m clips; sampled at step ends it shows as +-0.45 rad/s of wheel spin, a
+    0.25 rad/s pitch-rate ripple and a creep of a few cm/s.  The test bounds the artefact so that it cannot grow unnoticed."""
+    spec, o = _open_plane()
+    rows = _run(o, (0.0, 0.0), 10)                        # 2 s
+    p, q, v, w, om = rows[-1]
+    assert np.abs(v).max() < 2e-3 and np.abs(om).max() < 0.6 and np.abs(w).max() < 0.3
+    assert abs(rows[-1][0][2] - rows[-2][0][2]) < 1e-5 and abs(p[2]) < 0.02          # ride height constant, root near the wheel-bottom plane
+    creep = np.hypot(*(rows[-1][0][:2] - rows[-6][0][:2])) / 1.0                     # m/s over the last second
+    assert creep < 0.06 and abs(q[0]) > 0.99999 and abs(p[1]) < 1e-4                  # bounded creep, no tilt, no lateral motion
+
+
+def test_vehicle_accelerates_straight_to_the_commanded_wheel_speed():
+    """throttle 1 -> v_target = 3 m/s at r_cfg = 0.05 (common/actions.py:19) = 60 rad/s; the collider radius is 0.0525
+    (Appendix A), so the free-rolling ground speed is 3.15 m/s: the reference's own mismatch, kept."""
+    spec, o = _open_plane()
+    _run(o, (0.0, 0.0), 5)
+    rows = _run(o, (1.0, 0.0), 40, t0=5)                  # 8 s
+    vx = np.array([r[2][0] for r in rows])
+    assert (np.diff(vx) > -5e-3).all() and vx[3] > 0.3    # monotone (DC-motor limited) acceleration
+    assert 2.9 < vx[-1] < 3.25, vx[-1]                    # (0.03 m/s above free rolling: residual drive slip)
+    assert abs(rows[-1][4].mean() - 60.0) < 1.5           # wheels at the commanded 60 rad/s
+    assert abs(rows[-1][0][1]) < 5e-3 and abs(rows[-1][3][2]) < 5e-3                  # no lateral drift, no yaw
+
+
+def test_vehicle_turns_on_the_kinematic_circle_at_low_speed():
+    """steer 0.5 -> delta = 0.244 rad commanded, joint target tan(delta) = 0.249 rad (quirk Q1); at 1.2 m/s the lateral
+    acceleration (~1.3 m/s^2) is far below the friction limit, so yaw rate ~ v / R with R = wheelbase / tan(steer)."""
+    spec, o = _open_plane()
+    _run(o, (0.0, 0.0), 5)
+    rows = _run(o, (0.4, 0.5), 30, t0=5)                  # 6 s
+    p, q, v, w, om = rows[-1]
+    speed, yaw_rate = float(np.hypot(v[0], v[1])), float(w[2])
+    wheelbase = float(spec.cfg.hub_x_front - spec.cfg.hub_x_rear)
+    R_kin = wheelbase / math.tan(math.tan(0.5 * 0.488))
+    assert 1.0 < speed < 1.35 and yaw_rate > 0            # left turn for positive steer
+    assert 0.8 < yaw_rate * R_kin / speed < 1.25, (yaw_rate, speed, R_kin)
+    # and the path is a circle: the last second of positions is equidistant from its centre
+    pts = np.array([r[0][:2] for r in rows[-6:]])
+    A = np.c_[2 * pts, np.ones(len(pts))]
+    cx, cy, c0 = np.linalg.lstsq(A, (pts ** 2).sum(1), rcond=None)[0]
+    radii = np.hypot(pts[:, 0] - cx, pts[:, 1] - cy)
+    assert radii.std() / radii.mean() < 0.02 and 0.8 < radii.mean() / R_kin < 1.3
+
+
+def test_vehicle_brakes_to_rest_when_the_throttle_is_released():
+    """no_reverse + throttle 0 -> wheel speed target 0: the DC motors brake the car within ~0.6 s; what remains is the
+    rest-state creep bounded in test_vehicle_settles_at_rest_under_zero_action."""
+    spec, o = _open_plane()
+    _run(o, (0.0, 0.0), 5)
+    _run(o, (1.0, 0.0), 20, t0=5)
+    rows = _run(o, (0.0, 0.0), 20, t0=25)
+    vx = np.array([r[2][0] for r in rows])
+    assert vx[0] > 1.0 and (np.diff(vx[:4]) < 0).all() and np.abs(vx[4:]).max() < 0.1
