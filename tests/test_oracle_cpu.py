@@ -383,3 +383,36 @@ def test_vehicle_brakes_to_rest_when_the_throttle_is_released():
     rows = _run(o, (0.0, 0.0), 20, t0=25)
     vx = np.array([r[2][0] for r in rows])
     assert vx[0] > 1.0 and (np.diff(vx[:4]) < 0).all() and np.abs(vx[4:]).max() < 0.1
+
+
+@pytest.mark.parametrize("drive", ["2wd", "4wd"])
+def test_drift_vehicle_acceleration_and_friction_circle(drive):
+    """Drift configuration (5 ms x 4 per env.step) on an unbounded plane, DR off (mu = 1.1 x 1.0): the effort-limited
+    launch (2 x 0.5 N m or 4 x 0.25 N m at r = 0.0525 -> 19 N on 4.1 kg = 4.6 m/s^2) reaches the commanded speed within
+    ~0.8 s, and in a full-lock turn the lateral acceleration stays inside the friction circle mu g."""
+    spec = _cfg(num_envs=1, seed=3, randomize=False, drive=drive)
+    c = spec.cfg
+    c.trk_corner_out, c.trk_corner_in, c.trk_straight, c.max_episode_length = 1e4, 0.0, 0.0, 100000       # no track, no time-out
+    o = O.Oracle(c, kind="f64"); o.startup(); o.reset(None, 0)
+    st = o.export_state()
+    st[0, :, 0:2] = [50.0, 0.0]; st[1, :, :] = [1, 0, 0, 0]; st[2, :, 0:3] = 0; st[3, :, 0:3] = 0; st[4] = 0
+    o.import_state(st)
+
+    def run(a, n, t0):
+        rows = []
+        for t in range(n):
+            _, _, term, trunc = o.step(np.array([a], np.float32), t0 + t)
+            assert not (term[0] or trunc[0])
+            s = o.export_state()
+            rows.append((float(np.hypot(*s[2, 0, :2])), float(s[3, 0, 2]), s[10, 0].copy()))
+        return rows
+
+    run((0, 0), 25, 0)
+    acc = run((1, 0), 100, 25)                              # 2 s of full throttle
+    v = np.array([r[0] for r in acc])
+    assert 3.7 < (v[20] - v[5]) / (15 * 0.02) < 4.9         # ~4.6 m/s^2 while the motors are effort-limited
+    assert v[40] > 2.9 and 3.05 < v[-1] < 3.2               # at speed after 0.8 s; free rolling = 60 rad/s x 0.0525 m = 3.15 m/s
+    turn = run((1, 1), 150, 125)                            # 3 s at full lock
+    speed, yaw_rate, D = turn[-1]
+    a_lat = speed * yaw_rate
+    assert yaw_rate > 1.0 and 0.4 * D.mean() * 9.81 < a_lat < 1.02 * D.mean() * 9.81, (a_lat, D.mean() * 9.81)
