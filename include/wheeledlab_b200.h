@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define WL_ABI_VERSION 1
+#define WL_ABI_VERSION 2
 
 /* tasks (gym ids, wheeledlab_tasks/__init__.py:14-63) */
 #define WL_TASK_DRIFT     0  /* Isaac-MushrDriftRL-v0, Isaac-F1TenthDriftRL-v0 */
@@ -151,6 +151,7 @@ extern "C" {
     XS(float, f32, tire_v0)                                                                        \
     XS(float, f32, tire_mx)           /* effective mass for the longitudinal stick clamp */        \
     XS(float, f32, tire_my)                                                                        \
+    XS(float, f32, tire_mx_rest)      /* 1/tire_mx - r_w^2/I_w (chassis part; the wheel part follows the wheel-mass DR) */ \
     XS(float, f32, ground_mu_s)       /* mushr_drift_env_cfg.py:45-49 (combine=multiply) */        \
     XS(float, f32, ground_mu_d)                                                                    \
     /* --- startup domain randomisation (mushr_drift_env_cfg.py:95-154) --- */                     \
@@ -161,7 +162,12 @@ extern "C" {
     XA(float, f32, dr_kd_range, 2)                                                                 \
     XS(int32_t, i32, dr_kd_mask)      /* bit i => wheel i gets randomised damping */               \
     XS(int32_t, i32, _pad1)                                                                        \
-    XA(float, f32, dr_mass_add, 2)                                                                 \
+    XA(float, f32, dr_mass_add, 2)    /* base-mass range: += U (mode 0) or base_link mass := U (mode 1) */ \
+    XS(int32_t, i32, dr_mass_mode)    /* randomize_rigid_body_mass operation: 0 "add" (drift :145-154, elevation :400-407), 1 "abs" on base_link (visual :280-288) */ \
+    XS(int32_t, i32, dr_wheel_mass_enable) /* visual :290-299: wheel link masses := U(dr_wheel_mass), inertia rescaled by the mass ratio */ \
+    XS(float, f32, dr_base_mass_nominal)   /* base_link mass in the USD (1.0), replaced in mode 1 */       \
+    XS(float, f32, wheel_mass_nominal)     /* wheel link mass in the USD (0.1) */                          \
+    XA(float, f32, dr_wheel_mass, 2)                                                               \
     /* --- observation noise (common/observations.py:27-45) --- */                                 \
     XS(int32_t, i32, enable_corruption)                                                            \
     XS(int32_t, i32, _pad2)                                                                        \
@@ -267,6 +273,7 @@ extern "C" {
     XS(float, f32, d_hkp)             /* h * steer_kp */                                           \
     XS(float, f32, d_sden)            /* 1 / (J + h kd + h^2 kp) */                                \
     XS(float, f32, d_inv_Iw)                                                                       \
+    XS(float, f32, d_hI)              /* h / wheel_inertia */                                      \
     XS(float, f32, d_fxk)             /* tire_mx / h */                                            \
     XS(float, f32, d_fyk)                                                                          \
     XS(float, f32, d_inv_wheel_radius_cfg)                                                         \
@@ -299,13 +306,14 @@ typedef struct wl_config {
 #define WL_G_ACTION  6  /* action_manager.action (2) ; prev_action (2)                */
 #define WL_G_SUM0    7  /* reward episode sums, terms 0-3                             */
 #define WL_G_SUM1    8  /* reward episode sums, terms 4-7                             */
-#define WL_G_PMASS   9  /* mass, 1/mass, spare, spare                    (DR param)   */
+#define WL_G_PMASS   9  /* total mass, 1/mass, spare, spare              (DR param)   */
 #define WL_G_PMU_D  10  /* Pacejka peak D per wheel                      (DR param)   */
 #define WL_G_PMU_C  11  /* Pacejka shape C per wheel                     (DR param)   */
 #define WL_G_PKD    12  /* DC-motor damping per wheel                    (DR param)   */
 #define WL_G_CMD    13  /* elevation: goal x,y (world), heading_w, command time_left  */
 #define WL_G_CMDB   14  /* elevation: command in the yaw frame x,y, heading_b, spare  */
-#define WL_NUM_GROUPS 15
+#define WL_G_PIW    15  /* 1 / wheel spin inertia per wheel (DR param; read only when dr_wheel_mass_enable) */
+#define WL_NUM_GROUPS 16
 
 /* small global (not per-env) device block appended after the groups */
 typedef struct wl_globals {
@@ -466,7 +474,7 @@ int wl_gae(const float* d_rewards, const float* d_values, const float* d_last_va
            int32_t N, void* stream);
 
 /* ---- test hooks (bit-exactness of the deterministic math vs the oracle) ------ */
-/* op: 0 sin,1 cos,2 atan,3 atan2(x=in,y=in2),4 log,5 tan,6 asin,7 exp (x <= 0) ; out[n] */
+/* op: 0 sin,1 cos,2 atan,3 atan2(x=in,y=in2),4 log,5 tan,6 asin,7 exp,8 tanh ; out[n] */
 int wl_test_detmath(int32_t op, const float* d_in, const float* d_in2, float* d_out, int32_t n,
                     void* stream);
 /* philox4x32-10: out[4*n] for counters (c0_base + i, c1, c2, c3), key from seed */

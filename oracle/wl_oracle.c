@@ -191,6 +191,22 @@ static float det_exp(float x) {
 #endif
 static real det_tan(real x) { real s, c; det_sincos(x, &s, &c); return s / c; }
 static real det_asin(real x) { return det_atan2(x, r_sqrt((K(1.0) - x) * (K(1.0) + x))); }
+/* tanh (cephes tanhf): odd polynomial below 0.625, 1 - 2 / (exp(2|x|) + 1) above, +-1 beyond 9 */
+#ifdef WLO_DOUBLE
+static real det_tanh(real x) { return tanh(x); }
+#else
+static float det_tanh(float x) {
+    float a = fabsf(x), r;
+    if (a > 9.0f) r = 1.0f;
+    else if (a >= 0.625f) { float e = det_exp(a + a); r = 1.0f - 2.0f / (e + 1.0f); }
+    else {
+        float z = a * a;
+        float p = fm(fm(fm(fm(-5.70498872745e-3f, z, 2.06390887954e-2f), z, -5.37397155531e-2f), z, 1.33314422036e-1f), z, -3.33332819422e-1f);
+        r = fm(p * z, a, a);
+    }
+    return (x < 0.0f) ? -r : r;
+}
+#endif
 
 /* two standard normals from two u32 (Box-Muller) */
 static void box_muller(uint32_t a, uint32_t b, real* z0, real* z1) {
@@ -213,6 +229,7 @@ typedef struct {
     real sums[WL_MAX_REW_TERMS];
     real mass, inv_mass, spare0, spare1;
     real D[4], C[4], kd[4];
+    real inv_Iw[4];   /* 1 / wheel spin inertia (wheel-mass DR, visual :290-299) */
     real cmd[4];      /* elevation: goal x,y (world), heading_w, command time_left */
     real cmdb[4];     /* elevation: command in the yaw frame x,y, heading_b, spare */
 } wlo_env;
@@ -302,6 +319,7 @@ static void terrain(const wlo_sim* s, real x, real y, real* z, real n[3]) {
 static int process_action(const wl_config* c, const float a_in[2], real wheel_target[4], real steer_target[2]) {
     real a0 = (real)a_in[0], a1 = (real)a_in[1];
     if (c->bounding == WL_BOUND_CLIP) { a0 = r_clamp(a0, K(-1.0), K(1.0)); a1 = r_clamp(a1, K(-1.0), K(1.0)); }
+    else if (c->bounding == WL_BOUND_TANH) { a0 = det_tanh(a0); a1 = det_tanh(a1); }      /* ackermann_actions.py:126-127 */
     else if (c->bounding != WL_BOUND_NONE) return WL_EUNSUPPORTED;
     real v = a0 * (real)c->act_scale[0] + (real)c->act_offset[0];
     real delta = a1 * (real)c->act_scale[1] + (real)c->act_offset[1];
@@ -347,12 +365,29 @@ static real dc_motor(const wl_config* c, real kd, real effort_limit, real target
 /* ------------------------------------------------------------------------- */
 typedef struct { real pc[3]; real q[4]; real v[3]; real wb[3]; } chassis_t;
 /* mass-dependent per-env invariants; everything else comes from the d_* derived config fields */
-typedef struct { real I[3], invI[3]; } step_consts;
+typedef struct { real I[3], invI[3]; real hI[4], idk[4], fxk[4]; } step_consts;
 
 static void make_step_consts(const wl_config* c, const wlo_env* e, step_consts* k) {
     real ms = e->mass * (real)c->d_inv_mass_nominal;     /* inertia scales with the mass ratio (a14) */
     real ms_inv = (real)c->mass_nominal * e->inv_mass;
     for (int a = 0; a < 3; ++a) { k->I[a] = (real)c->inertia_nominal[a] * ms; k->invI[a] = (real)c->d_invI_nominal[a] * ms_inv; }
+    /* implicit DC-motor damper: h / I_w per wheel and 1 / (1 + h kd / I_w), constant over the env step */
+    for (int i = 0; i < 4; ++i) {
+        k->hI[i] = c->dr_wheel_mass_enable ? (real)c->d_h * e->inv_Iw[i] : (real)c->d_hI;
+        k->idk[i] = K(1.0) / fm(k->hI[i], e->kd[i], K(1.0));
+        /* longitudinal stick cap (tire_mx / h) with this wheel's own spin inertia */
+        k->fxk[i] = c->dr_wheel_mass_enable
+                        ? (real)c->d_inv_h / fm((real)c->wheel_radius * (real)c->wheel_radius, e->inv_Iw[i], (real)c->tire_mx_rest)
+                        : (real)c->d_fxk;
+    }
+}
+/* DCMotor speed-dependent effort limits (same clip as dc_motor), evaluated once per physics step like IsaacLab does */
+static void dc_limits(const wl_config* c, real effort_limit, real omega, real* lo, real* hi) {
+    if (!(effort_limit > K(0.0))) { *lo = K(0.0); *hi = K(0.0); return; }
+    real sat = (real)c->dc_saturation;
+    real ratio = omega * (real)c->d_inv_dc_vel_limit;
+    *hi = r_clamp(sat * (K(1.0) - ratio), K(0.0), effort_limit);
+    *lo = r_clamp(sat * (K(-1.0) - ratio), -effort_limit, K(0.0));
 }
 
 /* derived constants: same fp32 operations, same order, as wl_config_finalize() in the product library */
@@ -363,6 +398,7 @@ static void config_finalize(wl_config* c) {
     c->d_hkp = c->d_h * c->steer_kp;
     c->d_sden = 1.0f / fmaf(c->d_h, c->d_hkp, fmaf(c->d_h, c->steer_kd, c->steer_inertia));
     c->d_inv_Iw = 1.0f / c->wheel_inertia;
+    c->d_hI = c->d_h * c->d_inv_Iw;
     c->d_fxk = c->tire_mx * c->d_inv_h;
     c->d_fyk = c->tire_my * c->d_inv_h;
     c->d_inv_wheel_radius_cfg = 1.0f / c->wheel_radius_cfg;
@@ -373,8 +409,8 @@ static void config_finalize(wl_config* c) {
     c->d_vis_mesh_inv_dy = c->vis_mesh_dy > 0.0f ? 1.0f / c->vis_mesh_dy : 0.0f;
 }
 
-static void physics_substep(const wlo_sim* s, wlo_env* e, chassis_t* b, const real tau[4], const real steer_target[2],
-                            const step_consts* k) {
+static void physics_substep(const wlo_sim* s, wlo_env* e, chassis_t* b, const real wheel_target[4], const real eff_lo[4],
+                            const real eff_hi[4], const real steer_target[2], const step_consts* k) {
     const wl_config* c = &s->cfg;
     real h = (real)c->d_h;
     real R[9]; rotmat(b->q, R);
@@ -407,8 +443,13 @@ static void physics_substep(const wlo_sim* s, wlo_env* e, chassis_t* b, const re
             comp = rw - hz;
             nb[0] = R[6]; nb[1] = R[7]; nb[2] = R[8];
         }
-        /* drive torque first, then friction against the resulting slip (implicit stick) */
-        real om_star = fm(h, (tau[i] - bw * e->omega[i]) * (real)c->d_inv_Iw, e->omega[i]);
+        /* drive torque first, then friction against the resulting slip (implicit stick).  The DCMotor damper
+         * tau = kd (w_t - w) is stiff (kd h / I_w >> 1), so it is integrated implicitly in the new wheel speed; when the
+         * resulting torque leaves the motor's effort limits the clipped torque is applied explicitly instead. */
+        real os = fm(k->hI[i], fm(e->kd[i], wheel_target[i], -(bw * e->omega[i])), e->omega[i]) * k->idk[i];
+        real t_imp = e->kd[i] * (wheel_target[i] - os);
+        real tc = r_clamp(t_imp, eff_lo[i], eff_hi[i]);
+        real om_star = (tc == t_imp) ? os : fm(k->hI[i], tc - bw * e->omega[i], e->omega[i]);
         real rc[3] = {fm(-rw, nb[0], rho[0]), fm(-rw, nb[1], rho[1]), fm(-rw, nb[2], rho[2])};
         real vc[3]; cross(b->wb, rc, vc);
         vc[0] += vb[0]; vc[1] += vb[1]; vc[2] += vb[2];
@@ -438,11 +479,11 @@ static void physics_substep(const wlo_sim* s, wlo_env* e, chassis_t* b, const re
         real Fmag = Fz * (e->D[i] * sm);
         real inv_s = K(1.0) / r_max(smag, K(1.0e-9));
         real Fx = (Fmag * sx) * inv_s, Fy = (Fmag * sy) * inv_s;
-        real fxm = (real)c->d_fxk * r_fabs(sx), fym = (real)c->d_fyk * r_fabs(sy);
+        real fxm = k->fxk[i] * r_fabs(sx), fym = (real)c->d_fyk * r_fabs(sy);
         Fx = r_clamp(Fx, -fxm, fxm); Fy = r_clamp(Fy, -fym, fym);
         for (int a = 0; a < 3; ++a) F[i][a] = fm(Fz, nb[a], fm(Fx, ft[a], Fy * lt[a]));
         cross(rc, F[i], T[i]);
-        e->omega[i] = fm(-h, (rw * Fx) * (real)c->d_inv_Iw, om_star);
+        e->omega[i] = fm(-k->hI[i], rw * Fx, om_star);
     }
     real Fb[3], Tb[3];
     for (int a = 0; a < 3; ++a) { Fb[a] = (F[0][a] + F[1][a]) + (F[2][a] + F[3][a]); Tb[a] = (T[0][a] + T[1][a]) + (T[2][a] + T[3][a]); }
@@ -894,9 +935,9 @@ static int env_step(wlo_sim* s, int li, const float* a_in, int64_t t, float* obs
     rotT(R, e->w, b.wb);
     step_consts kc; make_step_consts(c, e, &kc);
     for (int d = 0; d < c->decimation; ++d) {
-        real tau[4];
-        for (int i = 0; i < 4; ++i) tau[i] = dc_motor(c, e->kd[i], (real)c->dc_effort[i], wheel_target[i], e->omega[i]);
-        for (int j = 0; j < c->substeps; ++j) physics_substep(s, e, &b, tau, steer_target, &kc);
+        real lo[4], hi[4];
+        for (int i = 0; i < 4; ++i) dc_limits(c, (real)c->dc_effort[i], e->omega[i], &lo[i], &hi[i]);
+        for (int j = 0; j < c->substeps; ++j) physics_substep(s, e, &b, wheel_target, lo, hi, steer_target, &kc);
     }
     rotmat(b.q, R);
     { real cc[3] = {(real)c->com[0], (real)c->com[1], (real)c->com[2]}; rot(R, cc, cw); }
@@ -997,10 +1038,11 @@ int wlo_startup(wlo_sim* s) {
     for (int li = 0; li < c->num_envs; ++li) {
         wlo_env* e = &s->env[li];
         uint32_t gid = (uint32_t)(c->env_id_offset + li);
-        uint32_t r0[4], r1[4], r2[4];
+        uint32_t r0[4], r1[4], r2[4], r3[4];
         philox4x32(c->seed, gid, 0u, RNG_STARTUP, 0u, r0);
         philox4x32(c->seed, gid, 0u, RNG_STARTUP, 1u, r1);
         philox4x32(c->seed, gid, 0u, RNG_STARTUP, 2u, r2);
+        philox4x32(c->seed, gid, 0u, RNG_STARTUP, 3u, r3);
         for (int i = 0; i < 4; ++i) {
             uint32_t bk = 0;
             if (c->dr_enable && c->dr_num_buckets > 1) bk = (uint32_t)(((uint64_t)r0[i] * (uint64_t)c->dr_num_buckets) >> 32);
@@ -1009,8 +1051,21 @@ int wlo_startup(wlo_sim* s) {
             e->kd[i] = (real)c->dc_damping[i];
             if (c->dr_enable && ((c->dr_kd_mask >> i) & 1)) e->kd[i] = uniform(r1[i], (real)c->dr_kd_range[0], (real)c->dr_kd_range[1]);
         }
+        /* randomize_rigid_body_mass [UPSTREAM-RECALL]: "add" -> base_link mass += U; "abs" -> base_link mass := U
+         * (mushr_visual_env_cfg.py:280-288); wheel links := U (:290-299), their inertia rescaled by the mass ratio */
         e->mass = (real)c->mass_nominal;
-        if (c->dr_enable) e->mass = e->mass + uniform(r2[0], (real)c->dr_mass_add[0], (real)c->dr_mass_add[1]);
+        for (int i = 0; i < 4; ++i) e->inv_Iw[i] = (real)c->d_inv_Iw;
+        if (c->dr_enable) {
+            real u = uniform(r2[0], (real)c->dr_mass_add[0], (real)c->dr_mass_add[1]);
+            if (c->dr_mass_mode == 0) e->mass = e->mass + u;
+            else e->mass = (e->mass - (real)c->dr_base_mass_nominal) + u;
+            if (c->dr_wheel_mass_enable)
+                for (int i = 0; i < 4; ++i) {
+                    real mw = uniform(r3[i], (real)c->dr_wheel_mass[0], (real)c->dr_wheel_mass[1]);
+                    e->mass = e->mass + (mw - (real)c->wheel_mass_nominal);
+                    e->inv_Iw[i] = (real)c->d_inv_Iw * ((real)c->wheel_mass_nominal / mw);
+                }
+        }
         e->inv_mass = K(1.0) / e->mass;
         sample_interval_timers(c, e, r2[1], r2[2]);
         e->q[0] = K(1.0); e->q[1] = e->q[2] = e->q[3] = K(0.0);
@@ -1145,6 +1200,7 @@ void wlo_export_state(const wlo_sim* s, float* buf) {
         g = grp(buf, WL_G_PKD, n, i); for (int k = 0; k < 4; ++k) g[k] = (float)e->kd[k];
         g = grp(buf, WL_G_CMD, n, i); for (int k = 0; k < 4; ++k) g[k] = (float)e->cmd[k];
         g = grp(buf, WL_G_CMDB, n, i); for (int k = 0; k < 4; ++k) g[k] = (float)e->cmdb[k];
+        g = grp(buf, WL_G_PIW, n, i); for (int k = 0; k < 4; ++k) g[k] = (float)e->inv_Iw[k];
     }
 }
 void wlo_import_state(wlo_sim* s, const float* cbuf) {
@@ -1167,6 +1223,7 @@ void wlo_import_state(wlo_sim* s, const float* cbuf) {
         g = grp(buf, WL_G_PKD, n, i); for (int k = 0; k < 4; ++k) e->kd[k] = g[k];
         g = grp(buf, WL_G_CMD, n, i); for (int k = 0; k < 4; ++k) e->cmd[k] = g[k];
         g = grp(buf, WL_G_CMDB, n, i); for (int k = 0; k < 4; ++k) e->cmdb[k] = g[k];
+        g = grp(buf, WL_G_PIW, n, i); for (int k = 0; k < 4; ++k) e->inv_Iw[k] = g[k];
     }
 }
 void wlo_get_weights(const wlo_sim* s, float* w) { for (int k = 0; k < WL_MAX_REW_TERMS; ++k) w[k] = (float)s->rew_weight[k]; }
@@ -1192,6 +1249,7 @@ int wlo_detmath(int32_t op, const float* in, const float* in2, float* out, int32
             case 5: out[i] = (float)det_tan(x); break;
             case 6: out[i] = (float)det_asin(x); break;
             case 7: out[i] = (float)det_exp(x); break;
+            case 8: out[i] = (float)det_tanh(x); break;
             default: return WL_EINVAL;
         }
     }

@@ -113,6 +113,17 @@ def golden_actions():
     term.process_actions(a.clone()); term.apply_actions()
     out["ack_wheel"] = env.scene["robot"].captured["vel"].numpy()
     out["ack_steer"] = env.scene["robot"].captured["pos"].numpy()
+    # the other two bounding strategies of process_actions (ackermann_actions.py:126-130): 'tanh' and None (linear)
+    for tag, strategy in (("tanh", "tanh"), ("none", None)):
+        for name, cfgcls in (("rwd", MushrRWDActionCfg), ("fwd", Mushr4WDActionCfg)):
+            cfg = cfgcls().throttle_steer
+            cfg.bounding_strategy = strategy
+            env = FakeEnv(a.shape[0])
+            term = cfg.class_type(cfg, env)
+            term.process_actions(a.clone()); term.apply_actions()
+            out[f"{name}_{tag}_processed"] = term.processed_actions.numpy().copy()
+            out[f"{name}_{tag}_wheel"] = env.scene["robot"].captured["vel"].numpy()
+            out[f"{name}_{tag}_steer"] = env.scene["robot"].captured["pos"].numpy()
     np.savez_compressed(HERE / "actions.npz", **out)
 
 

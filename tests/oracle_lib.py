@@ -62,7 +62,7 @@ def _p(a):
     return C.c_void_p(a.ctypes.data) if a is not None else None
 
 
-NUM_GROUPS = 15
+NUM_GROUPS = 16
 
 
 class Oracle:

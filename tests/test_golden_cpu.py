@@ -40,6 +40,18 @@ def test_action_terms_match_reference():
     f1.base_length, f1.base_width = 0.365, 0.284                            # F1Tenth4WDActionCfg, common/actions.py:64-66
     wheel, steer = O.action_map(f1, a)
     assert np.allclose(wheel, g["f1_wheel"], rtol=2e-5, atol=ATOL)
+    # bounding_strategy 'tanh' / None (ackermann_actions.py:126-130) through the same maps
+    for tag, bound in (("tanh", 2), ("none", 0)):
+        for name, kw in (("rwd", {}), ("fwd", {"drive": "4wd"})):
+            cfg = _task(**kw).cfg
+            cfg.bounding = bound
+            wheel, steer = O.action_map(cfg, a)
+            nw = 2 if name == "rwd" else 4
+            # tan() near the poles of the un-clipped steering angle amplifies 1 ulp: compare where |delta| < 1.2 rad
+            ok = np.abs(g[f"{name}_{tag}_processed"][:, 1]) < 1.2
+            assert ok.mean() > 0.9
+            assert np.allclose(wheel[ok, :nw], g[f"{name}_{tag}_wheel"][ok], rtol=5e-5, atol=ATOL), (tag, name)
+            assert np.allclose(steer[ok], g[f"{name}_{tag}_steer"][ok], rtol=5e-5, atol=ATOL), (tag, name)
     # processed actions: clip*scale, no_reverse
     assert np.allclose(g["rwd_processed"][:, 0], np.maximum(np.clip(a[:, 0], -1, 1) * 3.0, 0.0))
     assert list(g["fwd_wheel_ids"]) == [0, 1, 2, 3] and list(g["rwd_wheel_ids"]) == [0, 1]

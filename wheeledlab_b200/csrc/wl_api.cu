@@ -138,7 +138,7 @@ wl_step_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st, wl_
     const float wts[WL_MAX_REW_TERMS] = {rw0.x, rw0.y, rw0.z, rw0.w, rw1.x, rw1.y, rw1.z, rw1.w};
     if (STAGE == 2) {
         if (i < n) {
-            load_env(st, n, i, e, ELEV);
+            load_env(st, n, i, e, ELEV, c.dr_wheel_mass_enable != 0, c.d_inv_Iw);
             tmask = sio.tmask[i];
             if (sio.extra_truncated && sio.extra_truncated[i]) tmask |= 1u;            // host-side time-out style term
             if (sio.extra_terminated && sio.extra_terminated[i]) tmask |= 0x80u;       // host-side termination term
@@ -147,7 +147,7 @@ wl_step_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st, wl_
             done = tmask != 0u;
         }
     } else if (i < n) {
-        load_env(st, n, i, e, ELEV);
+        load_env(st, n, i, e, ELEV, c.dr_wheel_mass_enable != 0, c.d_inv_Iw);
         // A. action manager
         float2 a = action[i];
         e.prev_action[0] = e.action[0]; e.prev_action[1] = e.action[1];
@@ -161,12 +161,12 @@ wl_step_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st, wl_
         b.pc = V3{e.p.x + cw.x, e.p.y + cw.y, e.p.z + cw.z};
         b.v = e.v; b.qw = e.qw; b.qx = e.qx; b.qy = e.qy; b.qz = e.qz;
         b.wb = rotT(R, e.w);
-        StepConsts kc = make_step_consts(c, e.mass, e.inv_mass);
+        StepConsts kc = make_step_consts<4>(c, e);
         for (int d = 0; d < c.decimation; ++d) {
-            float tau[4];
+            float lo[4], hi[4];
 #pragma unroll
-            for (int w = 0; w < 4; ++w) tau[w] = dc_motor(c, e.kd[w], c.dc_effort[w], wheel_target[w], e.omega[w]);
-            for (int j = 0; j < c.substeps; ++j) physics_substep<TASK, 1>(c, T, e, b, tau, steer_target, kc);
+            for (int w = 0; w < 4; ++w) dc_limits(c, c.dc_effort[w], e.omega[w], lo[w], hi[w]);
+            for (int j = 0; j < c.substeps; ++j) physics_substep<TASK, 1>(c, T, e, b, wheel_target, lo, hi, steer_target, kc);
         }
         R = rotmat(b.qw, b.qx, b.qy, b.qz);
         cw = rot(R, V3{c.com[0], c.com[1], c.com[2]});
@@ -259,11 +259,12 @@ __device__ __forceinline__ void quad_env_step(const wl_config& c, const Terrain&
     b.pc = V3{e.p.x + cw.x, e.p.y + cw.y, e.p.z + cw.z};
     b.v = e.v; b.qw = e.qw; b.qx = e.qx; b.qy = e.qy; b.qz = e.qz;
     b.wb = rotT(R, e.w);
-    StepConsts kc = make_step_consts(c, e.mass, e.inv_mass);
+    StepConsts kc = make_step_consts<1>(c, e);
+    const float my_targets[4] = {my_target, 0.0f, 0.0f, 0.0f};
     for (int d = 0; d < c.decimation; ++d) {
-        float tau[4];
-        tau[0] = dc_motor(c, e.kd[0], my_effort, my_target, e.omega[0]);
-        for (int j = 0; j < c.substeps; ++j) physics_substep<TASK, 4>(c, T, e, b, tau, my_steer_target, kc);
+        float lo[4], hi[4];
+        dc_limits(c, my_effort, e.omega[0], lo[0], hi[0]);
+        for (int j = 0; j < c.substeps; ++j) physics_substep<TASK, 4>(c, T, e, b, my_targets, lo, hi, my_steer_target, kc);
     }
     R = rotmat(b.qw, b.qx, b.qy, b.qz);
     cw = rot(R, V3{c.com[0], c.com[1], c.com[2]});
@@ -358,7 +359,7 @@ wl_step_quad_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st
     EnvState e;
     const float4 rw0 = __ldg(reinterpret_cast<const float4*>(gl->rew_weight)), rw1 = __ldg(reinterpret_cast<const float4*>(gl->rew_weight) + 1);
     const float wts[WL_MAX_REW_TERMS] = {rw0.x, rw0.y, rw0.z, rw0.w, rw1.x, rw1.y, rw1.z, rw1.w};
-    load_env_quad(st, n, ii, w, e, ELEV);
+    load_env_quad(st, n, ii, w, e, ELEV, c.dr_wheel_mass_enable != 0, c.d_inv_Iw);
     const int od = ELEV ? WL_OBS_DIM_ELEV : VIS ? WL_OBS_DIM_VISUAL + vis_cam_floats(c) : WL_OBS_DIM_BLIND;
     quad_env_step<TASK>(c, T, vm, gl->acc, wts, e, i, w, live, gid, base, t, action[ii], obs + (size_t)od * ii, rew, terminated_o, truncated_o);
     if (live) store_env_quad(st, n, i, w, e, ELEV);
@@ -485,7 +486,7 @@ wl_act_step_quad_kernel(const __grid_constant__ wl_config c, float4* __restrict_
     if (stepper) {
         const float4 rw0 = __ldg(reinterpret_cast<const float4*>(gl->rew_weight)), rw1 = __ldg(reinterpret_cast<const float4*>(gl->rew_weight) + 1);
         wts[0] = rw0.x; wts[1] = rw0.y; wts[2] = rw0.z; wts[3] = rw0.w; wts[4] = rw1.x; wts[5] = rw1.y; wts[6] = rw1.z; wts[7] = rw1.w;
-        load_env_quad(st, n, ii, w, e, ELEV);
+        load_env_quad(st, n, ii, w, e, ELEV, c.dr_wheel_mass_enable != 0, c.d_inv_Iw);
     }
     for (int k = threadIdx.x; k < WL_ACT_ENVS * 16; k += WL_ACT_THREADS) {
         const int eq = k >> 4, j = k & 15, ei = min(blockIdx.x * WL_ACT_ENVS + eq, n - 1);
@@ -576,7 +577,7 @@ wl_rollout_quad_kernel(const __grid_constant__ wl_config c, float4* __restrict__
     EnvState e;
     const float4 rw0 = __ldg(reinterpret_cast<const float4*>(gl->rew_weight)), rw1 = __ldg(reinterpret_cast<const float4*>(gl->rew_weight) + 1);
     const float wts[WL_MAX_REW_TERMS] = {rw0.x, rw0.y, rw0.z, rw0.w, rw1.x, rw1.y, rw1.z, rw1.w};
-    load_env_quad(st, n, ii, w, e, ELEV);
+    load_env_quad(st, n, ii, w, e, ELEV, c.dr_wheel_mass_enable != 0, c.d_inv_Iw);
     const int od = ELEV ? WL_OBS_DIM_ELEV : VIS ? WL_OBS_DIM_VISUAL + vis_cam_floats(c) : WL_OBS_DIM_BLIND;
     for (int k = 0; k < K; ++k) {
         const uint32_t t = t0 + (uint32_t)k;
@@ -710,7 +711,8 @@ __global__ void wl_startup_kernel(const __grid_constant__ wl_config c, float4* _
     uint4 r0 = philox4x32(c.seed, gid, 0u, RNG_STARTUP, 0u);
     uint4 r1 = philox4x32(c.seed, gid, 0u, RNG_STARTUP, 1u);
     uint4 r2 = philox4x32(c.seed, gid, 0u, RNG_STARTUP, 2u);
-    const uint32_t rb[4] = {r0.x, r0.y, r0.z, r0.w}, rk[4] = {r1.x, r1.y, r1.z, r1.w};
+    uint4 r3 = philox4x32(c.seed, gid, 0u, RNG_STARTUP, 3u);
+    const uint32_t rb[4] = {r0.x, r0.y, r0.z, r0.w}, rk[4] = {r1.x, r1.y, r1.z, r1.w}, rm[4] = {r3.x, r3.y, r3.z, r3.w};
     float D[4], C[4], kd[4];
 #pragma unroll
     for (int w = 0; w < 4; ++w) {
@@ -720,9 +722,25 @@ __global__ void wl_startup_kernel(const __grid_constant__ wl_config c, float4* _
         kd[w] = c.dc_damping[w];
         if (c.dr_enable && ((c.dr_kd_mask >> w) & 1)) kd[w] = uniform(rk[w], c.dr_kd_range[0], c.dr_kd_range[1]);
     }
+    // randomize_rigid_body_mass: "add" -> base_link mass += U; "abs" -> base_link mass := U (mushr_visual_env_cfg.py:280-288);
+    // wheel links := U (:290-299), their spin inertia rescaled by the mass ratio
     float mass = c.mass_nominal;
-    if (c.dr_enable) mass = mass + uniform(r2.x, c.dr_mass_add[0], c.dr_mass_add[1]);
+    float inv_Iw[4] = {c.d_inv_Iw, c.d_inv_Iw, c.d_inv_Iw, c.d_inv_Iw};
+    if (c.dr_enable) {
+        const float u = uniform(r2.x, c.dr_mass_add[0], c.dr_mass_add[1]);
+        if (c.dr_mass_mode == 0) mass = mass + u;
+        else mass = (mass - c.dr_base_mass_nominal) + u;
+        if (c.dr_wheel_mass_enable) {
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                const float mw = uniform(rm[w], c.dr_wheel_mass[0], c.dr_wheel_mass[1]);
+                mass = mass + (mw - c.wheel_mass_nominal);
+                inv_Iw[w] = c.d_inv_Iw * (c.wheel_mass_nominal / mw);
+            }
+        }
+    }
     float inv_mass = 1.0f / mass;
+    stg4(st, WL_G_PIW, n, i, make_float4(inv_Iw[0], inv_Iw[1], inv_Iw[2], inv_Iw[3]));
     stg4(st, WL_G_PMASS, n, i, make_float4(mass, inv_mass, 0.0f, 0.0f));
     stg4(st, WL_G_PMU_D, n, i, make_float4(D[0], D[1], D[2], D[3]));
     stg4(st, WL_G_PMU_C, n, i, make_float4(C[0], C[1], C[2], C[3]));
@@ -882,6 +900,7 @@ __global__ void wl_detmath_kernel(int op, const float* __restrict__ in, const fl
         case 5: r = det_tan(x); break;
         case 6: r = det_asin(x); break;
         case 7: r = det_exp(x); break;
+        case 8: r = det_tanh(x); break;
     }
     out[i] = r;
 }
@@ -1047,7 +1066,7 @@ static int launch_camera(wl_sim* sim, float* d_obs, uint32_t t, uint32_t stream_
 extern "C" {
 
 const char* wl_last_error(void) { return g_err.c_str(); }
-const char* wl_build_info(void) { return "wheeledlab_b200 abi=1 arch=sm_100a fmad=false"; }
+const char* wl_build_info(void) { return "wheeledlab_b200 abi=2 arch=sm_100a fmad=false"; }
 size_t wl_config_sizeof(void) { return sizeof(wl_config); }
 
 const char* wl_config_describe(void) {
@@ -1082,6 +1101,7 @@ int wl_config_finalize(wl_config* c) {
     c->d_hkp = c->d_h * c->steer_kp;
     c->d_sden = 1.0f / fmaf(c->d_h, c->d_hkp, fmaf(c->d_h, c->steer_kd, c->steer_inertia));
     c->d_inv_Iw = 1.0f / c->wheel_inertia;
+    c->d_hI = c->d_h * c->d_inv_Iw;
     c->d_fxk = c->tire_mx * c->d_inv_h;
     c->d_fyk = c->tire_my * c->d_inv_h;
     c->d_inv_wheel_radius_cfg = 1.0f / c->wheel_radius_cfg;
@@ -1122,8 +1142,12 @@ int wl_create(const wl_config* cfg, void* d_state, size_t state_bytes, const flo
             return fail(WL_EINVAL, "wl_create: bad height-field geometry (hf_pitch must be >= hf_nx and a multiple of 4)");
         if (((uintptr_t)d_heightfield & 15u) != 0) return fail(WL_EINVAL, "wl_create: height-field must be 16-byte aligned");
     }
-    if (cfg->bounding != WL_BOUND_CLIP && cfg->bounding != WL_BOUND_NONE)
-        return fail(WL_EUNSUPPORTED, "wl_create: bounding_strategy 'tanh' is not implemented");
+    if (cfg->bounding != WL_BOUND_CLIP && cfg->bounding != WL_BOUND_NONE && cfg->bounding != WL_BOUND_TANH)
+        return fail(WL_EUNSUPPORTED, "wl_create: unknown bounding strategy");
+    if (cfg->action_kind != WL_ACT_ACKERMANN && cfg->action_kind != WL_ACT_RWD && cfg->action_kind != WL_ACT_4WD)
+        return fail(WL_EUNSUPPORTED, "wl_create: unknown action term kind");
+    if (cfg->dr_wheel_mass_enable && !(cfg->dr_wheel_mass[0] > 0.0f && cfg->wheel_mass_nominal > 0.0f))
+        return fail(WL_EINVAL, "wl_create: wheel-mass DR needs positive masses");
     if (cfg->decimation <= 0 || cfg->substeps <= 0 || !(cfg->sim_dt > 0.0f)) return fail(WL_EINVAL, "wl_create: bad sim timing");
     if (cfg->num_rew_terms < 0 || cfg->num_rew_terms > WL_MAX_REW_TERMS) return fail(WL_EINVAL, "wl_create: num_rew_terms");
     if (cfg->curr_n < 0 || cfg->curr_n > 4) return fail(WL_EINVAL, "wl_create: curr_n must be in [0,4]");

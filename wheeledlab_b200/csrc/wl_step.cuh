@@ -26,12 +26,16 @@ struct EnvState {
     float sums[WL_MAX_REW_TERMS];
     float mass, inv_mass, spare0, spare1;
     float D[4], C[4], kd[4];
+    float inv_Iw[4];  // 1 / wheel spin inertia (read from WL_G_PIW only when the wheel-mass DR is on)
     float cmd[4];     // elevation: goal x,y (world), heading_w, command time_left
     float cmdb[4];    // elevation: command in the yaw frame x,y, heading_b, spare
 };
 
-__device__ __forceinline__ void load_env(const float4* __restrict__ st, int n, int i, EnvState& e, bool with_cmd) {
+__device__ __forceinline__ void load_env(const float4* __restrict__ st, int n, int i, EnvState& e, bool with_cmd, bool with_iw = false,
+                                         float inv_Iw_nominal = 0.0f) {
     float4 g;
+    if (with_iw) { g = ldg4(st, WL_G_PIW, n, i); e.inv_Iw[0] = g.x; e.inv_Iw[1] = g.y; e.inv_Iw[2] = g.z; e.inv_Iw[3] = g.w; }
+    else { e.inv_Iw[0] = e.inv_Iw[1] = e.inv_Iw[2] = e.inv_Iw[3] = inv_Iw_nominal; }
     g = ldg4(st, WL_G_POS, n, i); e.p = V3{g.x, g.y, g.z}; e.ep_len = __float_as_int(g.w);
     g = ldg4(st, WL_G_QUAT, n, i); e.qw = g.x; e.qx = g.y; e.qy = g.z; e.qz = g.w;
     g = ldg4(st, WL_G_LINVEL, n, i); e.v = V3{g.x, g.y, g.z}; e.t_hf = g.w;
@@ -69,8 +73,10 @@ __device__ __forceinline__ void store_env(float4* __restrict__ st, int n, int i,
 
 // ---- quad (4 lanes per env) state access: lane w = wheel [bl,br,fl,fr][w].  Per-wheel scalars live in slot [0]
 // of the lane's EnvState (omega, D, C, kd) and front lanes keep THEIR steer joint in steer[0]/steer_vel[0].
-__device__ __forceinline__ void load_env_quad(const float4* __restrict__ st, int n, int i, int w, EnvState& e, bool with_cmd) {
+__device__ __forceinline__ void load_env_quad(const float4* __restrict__ st, int n, int i, int w, EnvState& e, bool with_cmd,
+                                              bool with_iw = false, float inv_Iw_nominal = 0.0f) {
     float4 g;
+    e.inv_Iw[0] = with_iw ? reinterpret_cast<const float*>(st)[(size_t)WL_G_PIW * n * 4 + (size_t)i * 4 + w] : inv_Iw_nominal;
     g = ldg4(st, WL_G_POS, n, i); e.p = V3{g.x, g.y, g.z}; e.ep_len = __float_as_int(g.w);
     g = ldg4(st, WL_G_QUAT, n, i); e.qw = g.x; e.qx = g.y; e.qy = g.z; e.qz = g.w;
     g = ldg4(st, WL_G_LINVEL, n, i); e.v = V3{g.x, g.y, g.z}; e.t_hf = g.w;
@@ -119,6 +125,7 @@ __device__ __forceinline__ void store_env_quad(float4* __restrict__ st, int n, i
 // ---- A. action term ---------------------------------------------------------------
 __device__ __forceinline__ void process_action(const wl_config& c, float a0, float a1, float wheel_target[4], float steer_target[2]) {
     if (c.bounding == WL_BOUND_CLIP) { a0 = r_clamp(a0, -1.0f, 1.0f); a1 = r_clamp(a1, -1.0f, 1.0f); }
+    else if (c.bounding == WL_BOUND_TANH) { a0 = det_tanh(a0); a1 = det_tanh(a1); }      // ackermann_actions.py:126-127
     float v = a0 * c.act_scale[0] + c.act_offset[0];
     float delta = a1 * c.act_scale[1] + c.act_offset[1];
     if (c.no_reverse) v = r_max(v, 0.0f);
@@ -151,6 +158,14 @@ __device__ __forceinline__ float dc_motor(const wl_config& c, float kd, float ef
     float max_eff = r_clamp(c.dc_saturation * (1.0f - ratio), 0.0f, effort_limit);
     float min_eff = r_clamp(c.dc_saturation * (-1.0f - ratio), -effort_limit, 0.0f);
     return r_clamp(tau, min_eff, max_eff);
+}
+
+// DCMotor speed-dependent effort limits (the clip of dc_motor), evaluated once per physics step like IsaacLab does
+__device__ __forceinline__ void dc_limits(const wl_config& c, float effort_limit, float omega, float& lo, float& hi) {
+    if (!(effort_limit > 0.0f)) { lo = 0.0f; hi = 0.0f; return; }
+    float ratio = omega * c.d_inv_dc_vel_limit;
+    hi = r_clamp(c.dc_saturation * (1.0f - ratio), 0.0f, effort_limit);
+    lo = r_clamp(c.dc_saturation * (-1.0f - ratio), -effort_limit, 0.0f);
 }
 
 // ---- terrain -----------------------------------------------------------------------
@@ -190,10 +205,21 @@ __device__ __forceinline__ void heightfield_at(const wl_config& c, const Terrain
 
 // ---- a8 integrator sub-step ----------------------------------------------------------
 struct Chassis { V3 pc; float qw, qx, qy, qz; V3 v; V3 wb; };
-struct StepConsts { float I[3], invI[3]; };       // mass-dependent only; everything else is c.d_*
+// per-env invariants of the env step: chassis inertia (DR mass ratio) and, per wheel (LANES == 4: slot 0 = this lane's
+// wheel), h / I_w and 1 / (1 + h kd / I_w) of the implicit DC-motor damper
+struct StepConsts { float I[3], invI[3]; float hI[4], idk[4], fxk[4]; };
 
-__device__ __forceinline__ StepConsts make_step_consts(const wl_config& c, float mass, float inv_mass) {
+template <int NW>
+__device__ __forceinline__ StepConsts make_step_consts(const wl_config& c, const EnvState& e) {
     StepConsts k;
+    const float mass = e.mass, inv_mass = e.inv_mass;
+#pragma unroll
+    for (int i = 0; i < NW; ++i) {
+        k.hI[i] = c.dr_wheel_mass_enable ? c.d_h * e.inv_Iw[i] : c.d_hI;
+        k.idk[i] = 1.0f / fm(k.hI[i], e.kd[i], 1.0f);
+        // longitudinal stick cap (tire_mx / h) with this wheel's own spin inertia
+        k.fxk[i] = c.dr_wheel_mass_enable ? c.d_inv_h / fm(c.wheel_radius * c.wheel_radius, e.inv_Iw[i], c.tire_mx_rest) : c.d_fxk;
+    }
     float ms = mass * c.d_inv_mass_nominal;          // inertia scales with the DR mass ratio (a14)
     float ms_inv = c.mass_nominal * inv_mass;
 #pragma unroll
@@ -216,8 +242,8 @@ struct WheelOut { V3 F, Tq; float omega; };
 // [bl, br, fl, fr]; (sn, cs) = sin/cos of its steer angle (front wheels only).
 template <int TASK>
 __device__ __forceinline__ WheelOut wheel_force(const wl_config& c, const Terrain& T, const StepConsts& k, const M3& R,
-                                                const Chassis& b, V3 vb, int i, float sn, float cs, float omega, float tau,
-                                                float Dmu, float Cmu) {
+                                                const Chassis& b, V3 vb, int i, float sn, float cs, float omega, float target,
+                                                float eff_lo, float eff_hi, float kd, float hI, float idk, float fxk, float Dmu, float Cmu) {
     const float rw = c.wheel_radius;
     V3 rho{((i >= 2) ? c.hub_x_front : c.hub_x_rear) - c.com[0], ((i & 1) ? -c.hub_y : c.hub_y) - c.com[1], c.hub_z - c.com[2]};
     float comp; V3 nb;
@@ -233,7 +259,12 @@ __device__ __forceinline__ WheelOut wheel_force(const wl_config& c, const Terrai
         nb = V3{R.r[6], R.r[7], R.r[8]};
     }
     WheelOut o;
-    float om_star = fm(c.d_h, (tau - c.wheel_damping * omega) * c.d_inv_Iw, omega);   // drive torque first
+    // drive torque first.  The DCMotor damper tau = kd (w_t - w) is stiff (kd h / I_w >> 1): implicit in the new wheel
+    // speed; when that torque leaves the motor's effort limits the clipped torque is applied explicitly instead
+    const float os = fm(hI, fm(kd, target, -(c.wheel_damping * omega)), omega) * idk;
+    const float t_imp = kd * (target - os);
+    const float tc = r_clamp(t_imp, eff_lo, eff_hi);
+    float om_star = (tc == t_imp) ? os : fm(hI, tc - c.wheel_damping * omega, omega);
     V3 rc = axpy(rho, -rw, nb);
     V3 vc = cross(b.wb, rc);
     vc.x += vb.x; vc.y += vb.y; vc.z += vb.z;
@@ -258,11 +289,11 @@ __device__ __forceinline__ WheelOut wheel_force(const wl_config& c, const Terrai
     float Fmag = Fz * (Dmu * sm);
     float inv_s = 1.0f / r_max(smag, 1.0e-9f);
     float Fx = (Fmag * sx) * inv_s, Fy = (Fmag * sy) * inv_s;
-    float fxm = c.d_fxk * fabsf(sx), fym = c.d_fyk * fabsf(sy);  // implicit-stick cap
+    float fxm = fxk * fabsf(sx), fym = c.d_fyk * fabsf(sy);  // implicit-stick cap
     Fx = r_clamp(Fx, -fxm, fxm); Fy = r_clamp(Fy, -fym, fym);
     o.F = V3{fm(Fz, nb.x, fm(Fx, ft.x, Fy * lt.x)), fm(Fz, nb.y, fm(Fx, ft.y, Fy * lt.y)), fm(Fz, nb.z, fm(Fx, ft.z, Fy * lt.z))};
     o.Tq = cross(rc, o.F);
-    o.omega = fm(-c.d_h, (rw * Fx) * c.d_inv_Iw, om_star);
+    o.omega = fm(-hI, rw * Fx, om_star);
     return o;
 }
 
@@ -298,7 +329,8 @@ __device__ __forceinline__ void chassis_integrate(const wl_config& c, const Step
 // Both sum as (F0 + F1) + (F2 + F3), the order the oracle uses.
 template <int TASK, int LANES>
 __device__ __forceinline__ void physics_substep(const wl_config& c, const Terrain& T, EnvState& e, Chassis& b,
-                                                const float tau[4], const float steer_target[2], const StepConsts& k) {
+                                                const float wheel_target[4], const float eff_lo[4], const float eff_hi[4],
+                                                const float steer_target[2], const StepConsts& k) {
     M3 R = rotmat(b.qw, b.qx, b.qy, b.qz);
     V3 vb = rotT(R, b.v);
     V3 Fb, Tb;
@@ -310,7 +342,7 @@ __device__ __forceinline__ void physics_substep(const wl_config& c, const Terrai
 #pragma unroll
         for (int i = 0; i < 4; ++i)
             w[i] = wheel_force<TASK>(c, T, k, R, b, vb, i, (i >= 2) ? sn[i - 2] : 0.0f, (i >= 2) ? cs[i - 2] : 1.0f, e.omega[i],
-                                     tau[i], e.D[i], e.C[i]);
+                                     wheel_target[i], eff_lo[i], eff_hi[i], e.kd[i], k.hI[i], k.idk[i], k.fxk[i], e.D[i], e.C[i]);
 #pragma unroll
         for (int i = 0; i < 4; ++i) e.omega[i] = w[i].omega;
         Fb = V3{(w[0].F.x + w[1].F.x) + (w[2].F.x + w[3].F.x), (w[0].F.y + w[1].F.y) + (w[2].F.y + w[3].F.y),
@@ -321,7 +353,8 @@ __device__ __forceinline__ void physics_substep(const wl_config& c, const Terrai
         const int i = threadIdx.x & 3;
         float sn = 0.0f, cs = 1.0f;
         if (i >= 2) steer_step(c, steer_target[0], e.steer[0], e.steer_vel[0], sn, cs);   // lane-local copy of ITS joint
-        WheelOut w = wheel_force<TASK>(c, T, k, R, b, vb, i, sn, cs, e.omega[0], tau[0], e.D[0], e.C[0]);
+        WheelOut w = wheel_force<TASK>(c, T, k, R, b, vb, i, sn, cs, e.omega[0], wheel_target[0], eff_lo[0], eff_hi[0], e.kd[0],
+                                       k.hI[0], k.idk[0], k.fxk[0], e.D[0], e.C[0]);
         e.omega[0] = w.omega;
         float v6[6] = {w.F.x, w.F.y, w.F.z, w.Tq.x, w.Tq.y, w.Tq.z};
 #pragma unroll

@@ -15,8 +15,8 @@ from .tasks import TaskSpec
 
 # state groups (include/wheeledlab_b200.h)
 G_POS, G_QUAT, G_LINVEL, G_ANGVEL, G_WHEEL, G_STEER, G_ACTION, G_SUM0, G_SUM1 = range(9)
-G_PMASS, G_PMU_D, G_PMU_C, G_PKD, G_CMD, G_CMDB = 9, 10, 11, 12, 13, 14
-NUM_GROUPS = 15
+G_PMASS, G_PMU_D, G_PMU_C, G_PKD, G_CMD, G_CMDB, G_PIW = 9, 10, 11, 12, 13, 14, 15
+NUM_GROUPS = 16
 
 
 _raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)     # cudaStream_t as an int, ~0.3 us (Stream object: ~2 us)

@@ -19,7 +19,7 @@ import numpy as np
 
 from ._lib import WlConfig
 
-WL_ABI_VERSION = 1
+WL_ABI_VERSION = 2
 TASK_DRIFT, TASK_ELEVATION, TASK_VISUAL = 0, 1, 2
 ACT_ACKERMANN, ACT_RWD, ACT_4WD = 0, 1, 2
 BOUND_NONE, BOUND_CLIP, BOUND_TANH = 0, 1, 2
@@ -155,6 +155,7 @@ def _mushr_vehicle(cfg: WlConfig) -> None:
     cfg.wheel_radius = 0.0525
     cfg.wheel_inertia = 1.378e-4
     cfg.wheel_damping = 0.0
+    cfg.wheel_mass_nominal, cfg.dr_base_mass_nominal = 0.1, 1.0   # wheel_link / base_link masses in the USD (Appendix A.1)
     # suspension+tyre vertical compliance: static deflection = wheel penetration at spawn (r - hub_z = 3.7 mm)
     cfg.susp_k = m * 9.81 / (4 * 0.0037)
     cfg.susp_c = 2 * 0.7 * math.sqrt(cfg.susp_k * m / 4)
@@ -165,9 +166,20 @@ def _mushr_vehicle(cfg: WlConfig) -> None:
     cfg.steer_inertia = 1.0e-4
     cfg.tire_B = 10.0
     cfg.tire_v0 = 0.5
-    cfg.tire_mx = 1.0 / (cfg.wheel_radius ** 2 / cfg.wheel_inertia + 4.0 / m)
-    cfg.tire_my = m / 4.0
+    _stick_caps(cfg, m)
     cfg.gravity = 9.81
+
+
+def _stick_caps(cfg: WlConfig, m: float) -> None:
+    """Effective masses of the implicit-stick cap (the friction force may at most remove the contact point's slip within one
+    sub-step; a larger cap over-corrects and the contact chatters with period 2 h).  The contact point sits h_c = COM height
+    below the COM, so a lateral force also rolls the chassis and a longitudinal one pitches it and spins the wheel:
+        1 / m_y = 4 (1/m + h_c^2 / I_xx)      (round 1 used m / 4: 2.7x too stiff for the MuSHR -> sustained roll chatter)
+        1 / m_x = r_w^2 / I_w + 4 (1/m + h_c^2 / I_yy)"""
+    hc2 = float(cfg.com[2]) ** 2
+    cfg.tire_mx_rest = 4.0 / m + 4.0 * hc2 / float(cfg.inertia_nominal[1])
+    cfg.tire_mx = 1.0 / (cfg.wheel_radius ** 2 / cfg.wheel_inertia + cfg.tire_mx_rest)
+    cfg.tire_my = 1.0 / (4.0 / m + 4.0 * hc2 / float(cfg.inertia_nominal[0]))
 
 
 def _f1tenth_vehicle(cfg: WlConfig) -> None:
@@ -181,14 +193,14 @@ def _f1tenth_vehicle(cfg: WlConfig) -> None:
     cfg.wheel_radius = 0.055
     cfg.wheel_inertia = 0.5 * 1.8001 * 0.055 ** 2
     cfg.wheel_damping = 0.0
+    cfg.wheel_mass_nominal, cfg.dr_base_mass_nominal = 1.8001, 4.1565
     cfg.hub_z = cfg.wheel_radius - 0.003                    # 3 mm static deflection at spawn
     cfg.susp_k = m * 9.81 / (4 * 0.003)
     cfg.susp_c = 2 * 0.7 * math.sqrt(cfg.susp_k * m / 4)
     cfg.susp_travel, cfg.bump_k, cfg.comp_max, cfg.base_link_z = 0.01, 10 * cfg.susp_k, 0.03, 0.0
     cfg.steer_inertia = 2.0e-3
     cfg.tire_B, cfg.tire_v0 = 10.0, 0.5
-    cfg.tire_mx = 1.0 / (cfg.wheel_radius ** 2 / cfg.wheel_inertia + 4.0 / m)
-    cfg.tire_my = m / 4.0
+    _stick_caps(cfg, m)
     cfg.gravity = 9.81
     cfg.dc_saturation, cfg.dc_vel_limit = 1.0, 400.0
     _set(cfg.dc_effort, (0.25,) * 4)
@@ -363,7 +375,8 @@ def elevation_task(num_envs: int = 1024, seed: int = 42, env_id_offset: int = 0,
 CAMERA_MODES = {None: 0, "off": 0, "raw": 1, "aug": 2}
 
 
-def visual_task(num_envs: int = 1024, seed: int = 42, env_id_offset: int = 0, traversability=None, camera: str | None = None) -> TaskSpec:
+def visual_task(num_envs: int = 1024, seed: int = 42, env_id_offset: int = 0, traversability=None, camera: str | None = None,
+                randomize: bool = False) -> TaskSpec:
     """MushrVisualRLEnvCfg (visual/mushr_visual_env_cfg.py:412-439): flat plane, 4WD MuSHR, traversability-map reward,
     out-of-map termination, random traversable respawn.  ``camera``: None -> the policy observation is the 8
     proprioceptive floats only (physics-side task); "aug" -> the registered PolicyCfg (camera_data_rgb_flattened_aug, 3200
@@ -386,13 +399,20 @@ def visual_task(num_envs: int = 1024, seed: int = 42, env_id_offset: int = 0, tr
     _mushr_vehicle(cfg)
     _hound_actuators(cfg, "4wd")
     cfg.ground_mu_s, cfg.ground_mu_d = 2.0, 2.0                        # :126-135 (combine = multiply)
-    cfg.dr_enable, cfg.dr_num_buckets = 0, 1                           # VisualEventsCfg: reset only (DR variant not registered)
-    D, Cs = material_buckets(1, (1.0, 1.0), (1.0, 1.0), True, cfg.ground_mu_s, cfg.ground_mu_d, seed)   # USD wheel material 1.0/1.0
+    if randomize:                                                      # VisualEventsRandomCfg, :266-299
+        cfg.dr_enable, cfg.dr_num_buckets = 1, 10
+        D, Cs = material_buckets(10, (0.4, 0.6), (0.4, 0.6), False, cfg.ground_mu_s, cfg.ground_mu_d, seed)
+        cfg.dr_mass_mode, cfg.dr_wheel_mass_enable = 1, 1              # operation="abs" on base_link (:280-288) and the wheel links (:290-299)
+        _set(cfg.dr_mass_add, (1.0, 3.0))
+        _set(cfg.dr_wheel_mass, (0.01, 0.3))
+    else:                                                              # VisualEventsCfg: reset only
+        cfg.dr_enable, cfg.dr_num_buckets = 0, 1
+        D, Cs = material_buckets(1, (1.0, 1.0), (1.0, 1.0), True, cfg.ground_mu_s, cfg.ground_mu_d, seed)   # USD wheel material 1.0/1.0
+        _set(cfg.dr_mass_add, (0.0, 0.0))
     _set(cfg.dr_bucket_D, D)
     _set(cfg.dr_bucket_C, Cs)
     _set(cfg.dr_kd_range, (10.0, 50.0))
     cfg.dr_kd_mask = 0
-    _set(cfg.dr_mass_add, (0.0, 0.0))
     cfg.enable_corruption, cfg.push_enable, cfg.num_ref_poses = 0, 0, 1
     if traversability is None:
         traversability = traversability_map(seed)
@@ -445,6 +465,8 @@ def make_task(name_or_id: str, **kw) -> TaskSpec:
         return spec
     if name == "elevation":
         return elevation_task(**kw)
+    if name == "visual_random":
+        return visual_task(randomize=True, **kw)
     if name == "visual":
         if name_or_id in GYM_IDS:                 # the registered task observes through the camera (PolicyCfg, :45-52)
             kw.setdefault("camera", "aug")
