@@ -340,6 +340,8 @@ const char* wl_config_describe(void);
 size_t wl_config_sizeof(void);
 /* set the device-resident step counter (wl_create zeroes it; wl_step advances it) */
 int wl_set_step_counter(wl_sim* sim, int64_t value, void* stream);
+/* ManagerBasedEnv.seed(): re-key the counter-based generator for all later launches (startup draws are not repeated) */
+int wl_set_seed(wl_sim* sim, uint64_t seed);
 /* fill the d_* derived fields from the primary ones (idempotent). */
 int wl_config_finalize(wl_config* cfg);
 
@@ -477,6 +479,8 @@ int wl_gae(const float* d_rewards, const float* d_values, const float* d_last_va
 /* op: 0 sin,1 cos,2 atan,3 atan2(x=in,y=in2),4 log,5 tan,6 asin,7 exp,8 tanh ; out[n] */
 int wl_test_detmath(int32_t op, const float* d_in, const float* d_in2, float* d_out, int32_t n,
                     void* stream);
+/* an empty kernel of the given geometry (launch / event-timing floor of the measurement protocol) */
+int wl_test_null(int32_t grid, int32_t block, void* stream);
 /* philox4x32-10: out[4*n] for counters (c0_base + i, c1, c2, c3), key from seed */
 int wl_test_philox(uint64_t seed, uint32_t c0_base, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t* d_out,
                    int32_t n, void* stream);

@@ -1,0 +1,14 @@
+"""gymnasium.logger stand-in."""
+import warnings
+
+
+def warn(msg, *args):
+    warnings.warn(msg % args if args else msg)
+
+
+def info(msg, *args):
+    pass
+
+
+def error(msg, *args):
+    print(msg % args if args else msg)

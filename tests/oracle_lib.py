@@ -64,6 +64,39 @@ def _p(a):
 
 NUM_GROUPS = 16
 
+_CFG_CLS = None
+
+
+def config_struct():
+    """ctypes mirror of wl_config built from the ORACLE's own field list (wlo_config_describe), so that the reference arm of
+    bench.py can drive the oracle from a committed config blob without importing the product package."""
+    global _CFG_CLS
+    if _CFG_CLS is None:
+        tags = {"i32": C.c_int32, "u64": C.c_uint64, "f32": C.c_float}
+        fields, size = [], None
+        for item in get_lib().wlo_config_describe().decode().split(";"):
+            if not item:
+                continue
+            parts = item.split(":")
+            if parts[0] == "sizeof":
+                size = int(parts[1]); continue
+            ct = tags[parts[1]]
+            fields.append((parts[0], ct if int(parts[2]) == 1 else ct * int(parts[2])))
+        _CFG_CLS = type("WloConfig", (C.Structure,), {"_fields_": fields})
+        assert size is None or C.sizeof(_CFG_CLS) == size
+    return _CFG_CLS
+
+
+def cfg_from_blob(path, **overrides):
+    """wl_config from a binary blob (python -m wheeledlab_b200.dump_config / tests/golden/cfg_blobs) + field overrides."""
+    cls = config_struct()
+    raw = Path(path).read_bytes()
+    assert len(raw) == C.sizeof(cls), f"{path}: {len(raw)} bytes, wl_config is {C.sizeof(cls)} (stale blob? regenerate)"
+    cfg = cls.from_buffer_copy(raw)
+    for k, v in overrides.items():
+        setattr(cfg, k, v)
+    return cfg
+
 
 class Oracle:
     """One oracle instance; mirrors the wl_* calls with host (numpy) buffers."""

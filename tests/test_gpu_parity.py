@@ -783,3 +783,142 @@ def test_c_host_example_matches_python_path(tmp_path):
     assert got["envs"] == n and got["steps"] == steps and "sm_100a" in got["build"]
     assert (got["obs_bits_sum"], got["rew_bits_sum"], got["terminated"], got["truncated"]) == (obs_sum, rew_sum, n_term, n_trunc)
     assert n_trunc > 0 and n_term > 0                              # the run crossed the 250-step time-out and saw off-track resets
+
+
+# ---- oracle parity at BASELINE.json's full sizes and on the action / DR branches (round-2 additions) -------------------
+def _oracle_traj(spec, steps, action_fn, threads=8, check_state=True, heightfield=None):
+    """CUDA (through the C-ABI) vs the oracle on the same seeded inputs: every output bit-exact every step, the full state at
+    the end.  action_fn(sim, t) -> device [N,2] f32.  Returns the number of (env, step) pairs that ended an episode."""
+    import wheeledlab_b200 as wl
+    sim = wl.WheeledSim(spec, "cuda:0"); sim.startup(); sim.reset(None, 0)
+    orc = O.Oracle(spec.cfg, heightfield=spec.heightfield if heightfield is None else heightfield, threads=threads)
+    orc.startup(); orc.reset(None, 0)
+    n_done = 0
+    for t in range(steps):
+        act = action_fn(sim, t)
+        obs, rew, term, trunc = sim.step(act, t)
+        o_obs, o_rew, o_term, o_trunc = orc.step(act.cpu().numpy(), t)
+        assert np.array_equal(term.cpu().numpy(), o_term) and np.array_equal(trunc.cpu().numpy(), o_trunc), f"done masks differ at step {t}"
+        assert np.array_equal(_bits(rew.cpu().numpy()), _bits(o_rew)), f"reward differs at step {t}"
+        assert np.array_equal(_bits(obs.cpu().numpy()), _bits(o_obs)), f"obs differs at step {t}"
+        n_done += int((o_term | o_trunc).sum())
+    if check_state:
+        assert np.array_equal(_bits(_state_groups(sim)), _bits(orc.export_state())), "final state differs"
+    return n_done
+
+
+def _synth(sim, t):
+    return sim.synth_actions(t, dist=t % 2)
+
+
+def _wide_actions(sim, t):
+    """N(0, 2): most samples fall outside [-1, 1], so the action term's own bounding (clip / tanh / none) does the work."""
+    g = torch.Generator(device="cuda").manual_seed(1000 + t)
+    return torch.randn((sim.num_envs, 2), generator=g, device="cuda") * 2.0
+
+
+def test_drift_4096_envs_bit_exact_vs_oracle():
+    """BASELINE configs[1]: RSS_DRIFT_CONFIG at 4096 envs, 60 steps, every output vs the oracle."""
+    _need_gpu()
+    import wheeledlab_b200 as wl
+    assert _oracle_traj(wl.drift_task(num_envs=4096, seed=42), 60, _synth) > 100
+
+
+def test_elevation_4096_envs_bit_exact_vs_oracle():
+    """BASELINE configs[2]: RSS_ELEV_CONFIG at 4096 envs (689-wide observation incl. the 676-ray height scan), 20 steps."""
+    _need_gpu()
+    import wheeledlab_b200 as wl
+    _oracle_traj(wl.elevation_task(num_envs=4096, seed=42), 20, _synth)
+
+
+def test_hound_4wd_8192_envs_bit_exact_vs_oracle():
+    """BASELINE configs[3]: 'HOUND 4WD' = MuSHR with HOUND_SUS_ACTUATOR_CFG (four driven wheels) + Mushr4WDActionCfg + mass /
+    friction DR, 8192 envs, 30 steps."""
+    _need_gpu()
+    import wheeledlab_b200 as wl
+    assert _oracle_traj(wl.make_task("hound_4wd", num_envs=8192, seed=42), 30, _synth) > 100
+
+
+@pytest.mark.parametrize("bounding", [0, 1, 2])        # none / clip / tanh (ackermann_actions.py:123-130)
+@pytest.mark.parametrize("kind", [0, 1, 2])            # base Ackermann / RWD / 4WD action terms
+def test_action_term_branches_bit_exact_with_out_of_range_actions(kind, bounding):
+    """Every (action term, bounding strategy) pair, fed N(0, 2) actions: the in-kernel clip / tanh / linear map is exercised
+    against the oracle (round 1's synthetic actions were pre-clipped)."""
+    _need_gpu()
+    import wheeledlab_b200 as wl
+    spec = wl.drift_task(num_envs=512, seed=5, drive="2wd" if kind == 1 else "4wd")
+    spec.cfg.action_kind, spec.cfg.bounding = kind, bounding
+    if bounding == 0:
+        spec.cfg.act_scale[0], spec.cfg.act_scale[1] = 1.0, 0.15        # unbounded actions: keep |delta| away from tan's poles
+    _oracle_traj(spec, 120, _wide_actions)
+
+
+def test_f1tenth_task_bit_exact_vs_oracle():
+    """Isaac-F1TenthDriftRL-v0: F1Tenth geometry / masses / actuators (wheeledlab_assets/f1tenth.py, common/actions.py:51-71)."""
+    _need_gpu()
+    import wheeledlab_b200 as wl
+    assert _oracle_traj(wl.make_task("Isaac-F1TenthDriftRL-v0", num_envs=1024, seed=3), 300, _synth) > 100
+
+
+@pytest.mark.parametrize("variant", [1, 4])
+def test_visual_random_dr_variant_bit_exact_vs_oracle(variant):
+    """MushrVisualRLRandomEnvCfg (mushr_visual_env_cfg.py:266-299,449-451): abs base mass, abs wheel masses (per-wheel spin
+    inertia group WL_G_PIW), 10 friction buckets."""
+    _need_gpu()
+    import wheeledlab_b200 as wl
+    spec = wl.visual_task(num_envs=300, seed=8, randomize=True)
+    sim = wl.WheeledSim(spec, "cuda:0"); sim.startup(); sim.reset(None, 0); sim.set_kernel_variant(variant)
+    orc = O.Oracle(spec.cfg, heightfield=spec.heightfield); orc.startup(); orc.reset(None, 0)
+    assert np.array_equal(_bits(_state_groups(sim)), _bits(orc.export_state()))
+    m = sim.groups[9, :, 0]
+    assert 3.9 < float(m.min()) and float(m.max()) < 6.9 and float(m.std()) > 0.3
+    for t in range(110):
+        act = sim.synth_actions(t)
+        for x, y in zip(sim.step(act, t), orc.step(act.cpu().numpy(), t)):
+            x = x.cpu().numpy()
+            assert np.array_equal(_bits(x) if x.dtype == np.float32 else x, _bits(y) if y.dtype == np.float32 else y), t
+    assert np.array_equal(_bits(_state_groups(sim)), _bits(orc.export_state()))
+
+
+def test_vehicle_at_rest_stays_at_rest_on_the_gpu():
+    """The implicit DC-motor damper on the CUDA path: zero action, 4WD configuration, the car does not creep (|v| < 1 mm/s)."""
+    _need_gpu()
+    import wheeledlab_b200 as wl
+    spec = wl.visual_task(num_envs=64, seed=3, traversability=np.ones((500, 500), dtype=bool))
+    sim = wl.WheeledSim(spec, "cuda:0"); sim.startup(); sim.reset(None, 0)
+    sim.groups[2, :, 0:3] = 0; sim.groups[3, :, 0:3] = 0; sim.groups[4] = 0
+    zero = torch.zeros((64, 2), device="cuda")
+    for t in range(10):
+        sim.step(zero, t)
+    p0 = sim.root_pos_w.clone()
+    for t in range(10, 15):
+        sim.step(zero, t)
+    assert float((sim.root_pos_w - p0)[:, :2].norm(dim=1).max()) < 1e-3 * 1.0 and float(sim.root_lin_vel_w.abs().max()) < 1e-3
+    assert float(sim.wheel_vel.abs().max()) < 1e-2
+
+
+def test_two_process_nccl_gather_equals_single_rank(tmp_path):
+    """BASELINE configs[4] at test size: 2 ranks x 2048 envs over NCCL, the all-gathered rollout slab == the slab of one
+    4096-env process, bit for bit (skipped when the box has a single GPU)."""
+    _need_gpu()
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import subprocess, sys
+    root = Path(__file__).resolve().parent.parent
+    out = tmp_path / "slab.pt"
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29731", str(root / "tools" / "nccl_slab_check.py"), "--out", str(out), "--envs", "2048", "--steps", "16"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    import wheeledlab_b200 as wl
+    from wheeledlab_b200.distributed import RolloutSlab
+    got = torch.load(out)
+    sim = wl.WheeledSim(wl.drift_task(num_envs=4096, seed=42), "cuda:0"); sim.startup(); sim.reset(None, 0)
+    slab = RolloutSlab(16, 4096, sim.obs_dim, 2, "cuda:0")
+    for t in range(16):
+        act = sim.synth_actions(t)
+        slab.actions[t].copy_(act)
+        sim.step(act, t, out=slab.step_outputs(t))
+    torch.cuda.synchronize()
+    for name in ("obs", "actions", "rewards", "terminated", "truncated"):
+        assert torch.equal(getattr(slab, name).cpu(), got[name]), name

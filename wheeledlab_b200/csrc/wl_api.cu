@@ -68,7 +68,9 @@ __device__ __forceinline__ bool log_accumulate(float* __restrict__ acc, bool con
     if ((threadIdx.x & 31) == 0) {
 #pragma unroll
         for (int k = 0; k < 16; ++k) if (vals[k] != 0.0f) atomicAdd(&acc[k], vals[k]);
+#ifndef WL_EXP_NOFENCE
         __threadfence();          // order this warp's accumulation before its CTA's ticket (only warps that contributed pay)
+#endif
     }
     return true;
 }
@@ -84,6 +86,9 @@ __device__ __forceinline__ void apply_curriculum(const wl_config& c, wl_globals*
 }
 // Last CTA of the launch turns the accumulators into the extras["log"] row and re-arms them.
 __device__ __forceinline__ void log_finalize(const wl_config& c, wl_globals* __restrict__ gl, float* __restrict__ d_log, uint32_t t) {
+#ifdef WL_EXP_NOFINAL
+    return;
+#endif
     __syncthreads();              // all warps of the CTA are past their (fenced) accumulation
     if (threadIdx.x != 0) return;
     const unsigned tk = atomicAdd(&gl->ticket, 1u);
@@ -904,6 +909,7 @@ __global__ void wl_detmath_kernel(int op, const float* __restrict__ in, const fl
     }
     out[i] = r;
 }
+__global__ void wl_null_kernel(int* p) { if (p != nullptr && threadIdx.x == 1024) *p = 0; }
 __global__ void wl_philox_kernel(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint4* __restrict__ out, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -1092,6 +1098,12 @@ int wl_set_step_counter(wl_sim* sim, int64_t value, void* stream) {
                       "wl_set_step_counter");
 }
 
+int wl_set_seed(wl_sim* sim, uint64_t seed) {
+    if (!sim) return fail(WL_EINVAL, "wl_set_seed: null handle");
+    sim->cfg.seed = seed;
+    return WL_OK;
+}
+
 int wl_config_finalize(wl_config* c) {
     if (!c) return fail(WL_EINVAL, "wl_config_finalize: null");
     if (c->substeps <= 0 || !(c->sim_dt > 0.0f)) return fail(WL_EINVAL, "wl_config_finalize: bad sim timing");
@@ -1248,7 +1260,10 @@ int wl_step(wl_sim* sim, const float* d_action, float* d_obs, float* d_rew, uint
     const uint32_t t = (uint32_t)step_counter;
     const bool elev = sim->cfg.task == WL_TASK_ELEVATION, vis = sim->cfg.task == WL_TASK_VISUAL;
     if (variant == 4) {
-        const int bs = 32, threads = 4 * n, grid = (threads + bs - 1) / bs;
+#ifndef WL_QUAD_BS
+#define WL_QUAD_BS 32
+#endif
+        const int bs = WL_QUAD_BS, threads = 4 * n, grid = (threads + bs - 1) / bs;
         if (elev) wl_step_quad_kernel<WL_TASK_ELEVATION><<<grid, bs, 0, cs>>>(sim->cfg, sim->state, sim->globals, T, act, d_obs, d_rew, d_terminated, d_truncated, d_log, t);
         else if (vis) wl_step_quad_kernel<WL_TASK_VISUAL><<<grid, bs, 0, cs>>>(sim->cfg, sim->state, sim->globals, T, act, d_obs, d_rew, d_terminated, d_truncated, d_log, t);
         else wl_step_quad_kernel<WL_TASK_DRIFT><<<grid, bs, 0, cs>>>(sim->cfg, sim->state, sim->globals, T, act, d_obs, d_rew, d_terminated, d_truncated, d_log, t);
@@ -1478,6 +1493,10 @@ int wl_test_detmath(int32_t op, const float* d_in, const float* d_in2, float* d_
     if (n <= 0) return WL_OK;
     wl_detmath_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(op, d_in, d_in2 ? d_in2 : d_in, d_out, n);
     return cuda_check(cudaGetLastError(), "wl_detmath_kernel");
+}
+int wl_test_null(int32_t grid, int32_t block, void* stream) {
+    wl_null_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(nullptr);
+    return cuda_check(cudaGetLastError(), "wl_null_kernel");
 }
 int wl_test_philox(uint64_t seed, uint32_t c0_base, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t* d_out, int32_t n,
                    void* stream) {

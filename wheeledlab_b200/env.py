@@ -236,7 +236,8 @@ class _Scene:
 class ManagerBasedRLEnv:
     """Drop-in for ``isaaclab.envs.ManagerBasedRLEnv`` on the Drift/Elevation/Visual gym ids."""
 
-    _RING = 512      # step_host() output buffers are reused after this many steps
+    _RING = 512      # step() / step_host() output buffers are reused after this many steps (fewer when rows are wide, see _ring_len)
+    _HOST_OBS_RING = 4   # pinned host observation buffers of step_host(host_obs=True)
 
     metadata = {"render_modes": [None, "human", "rgb_array"], "isaac_sim_version": "b200-native"}
 
@@ -266,10 +267,14 @@ class ManagerBasedRLEnv:
         self.log_episode_info = True
         self._log_index = {"Episode_Reward/" + n: k for k, n in enumerate(self.spec.reward_names)}
         self._log_index.update({"Episode_Termination/" + n: 9 + j for j, (n, _) in enumerate(self.spec.termination_names)})
+        self._ring_len = max(8, min(self._RING, (2 << 30) // max(1, 4 * self.num_envs * self.spec.obs_dim)))
+        self._step_ring = None
         self._host_io = None
         self._pinned_ptrs = {}                   # data_ptr -> c_void_p of caller buffers known to be pinned [N,2] f32
         self._ring = None
         self.host_transport = "zero_copy"        # or "copy": staged H2D / D2H copies (wl_step_host)
+        self.host_obs = False                    # step_host: True -> observations are returned in pinned host memory too
+        self._host_obs_ring = None
         # host-side (Python) MDP terms: evaluated between the two halves of the staged step (see add_reward_term)
         self._py_rewards, self._py_terms, self._py_obs = [], [], []
         self._py_sums = {}
@@ -296,12 +301,18 @@ class ManagerBasedRLEnv:
         self.sim.episode_length_buf.copy_(value.to(torch.int32))
 
     def seed(self, seed: int = -1) -> int:
+        """ManagerBasedEnv.seed: re-key the counter-based generator for every draw from now on (resets, pushes, observation
+        noise, commands).  What startup already sampled (DR scatter, the reference-pose table) is not re-drawn -- the reference
+        seeds before construction (hydra.py:30 overrides cfg.seed with the agent seed; pass seed= to make()/the task for that)."""
+        if seed is not None and seed >= 0:
+            self.sim.set_seed(int(seed))
         return int(self.spec.cfg.seed)
 
     def close(self):
         self.sim.close()
 
     def render(self, recompute=False):
+        """No viewport: the reference renders through Omniverse RTX (video recording only, train_rl.py --video); returns None."""
         return None
 
     def reset(self, seed=None, options=None):
@@ -413,8 +424,17 @@ class ManagerBasedRLEnv:
         if self._py_rewards or self._py_terms:
             return self._step_staged(action)
         t = self.common_step_counter
-        log = torch.empty(16, dtype=torch.float32, device=self.device) if self.log_episode_info else None
-        obs, rew, term_u8, trunc_u8 = self.sim.step(action, t, log=log)
+        # outputs live in a ring of preallocated buffers (no allocator call per step; a returned tensor stays valid for
+        # _ring_len steps -- rsl_rl copies into its storage at once, play_policy.py keeps at most one episode of references)
+        if self._step_ring is None:
+            n, dev = self.num_envs, self.device
+            self._step_ring = [((torch.empty((n, self.spec.obs_dim), dtype=torch.float32, device=dev), torch.empty(n, dtype=torch.float32, device=dev),
+                                 torch.empty(n, dtype=torch.uint8, device=dev), torch.empty(n, dtype=torch.uint8, device=dev)),
+                                torch.empty(16, dtype=torch.float32, device=dev)) for _ in range(self._ring_len)]
+        out, log = self._step_ring[t % self._ring_len]
+        if not self.log_episode_info:
+            log = None
+        obs, rew, term_u8, trunc_u8 = self.sim.step(action, t, out=out, log=log)
         self.common_step_counter = t + 1
         # curriculum: applied by the step kernel's last CTA (uses the incremented counter and fires only if >= 1 env
         # reset, like the reference's call from _reset_idx) -- no host logic, no sync
@@ -434,7 +454,9 @@ class ManagerBasedRLEnv:
         """env.step() for a HOST-side caller: `action_host` is a CPU tensor [N,2] (pinned for best speed).  One C call
         does H2D(actions) -> fused step -> D2H(reward, terminated, truncated) -> sync.  Returns
         (obs_dict [device], rew [pinned host], terminated [pinned host], truncated [pinned host], extras); the host
-        result views are overwritten by the next step_host call."""
+        result views are overwritten by the next step_host call.  With ``env.host_obs = True`` the observations are returned in
+        pinned HOST memory as well (a ring of _RING buffers): D2H copy after the step (transport "copy") or written by the
+        kernel over PCIe (transport "zero_copy")."""
         if self._py_rewards or self._py_terms:
             raise NotImplementedError("step_host: host-side Python terms need the staged step (use env.step)")
         if self._needs_reset:
@@ -460,21 +482,33 @@ class ManagerBasedRLEnv:
             io["h_action"].copy_(action_host)
         t = self.common_step_counter
         # outputs come from a ring of preallocated device buffers (valid for _RING steps, like IsaacLab's own reuse)
-        k = t % self._RING
+        k = t % self._ring_len
         if self._ring is None:
             import ctypes as C
             self._ring = []
-            for _ in range(self._RING):
+            for _ in range(self._ring_len):
                 o = torch.empty((self.num_envs, self.spec.obs_dim), dtype=torch.float32, device=self.device)
                 lg = torch.empty(16, dtype=torch.float32, device=self.device)
                 self._ring.append((o, lg, C.c_void_p(o.data_ptr()), C.c_void_p(lg.data_ptr()), _LazyLog(lg, self._log_index)))
         obs, log, p_obs, p_log, lazy = self._ring[k]
         if not self.log_episode_info:
             log, p_log = None, None
+        h_obs = None
+        if self.host_obs:                                # the caller lives on the host: observations come back too
+            if self._host_obs_ring is None:
+                self._host_obs_ring = [torch.empty((self.num_envs, self.spec.obs_dim), dtype=torch.float32).pin_memory()
+                                       for _ in range(self._HOST_OBS_RING)]
+            h_obs = self._host_obs_ring[t % self._HOST_OBS_RING]
         if self.host_transport == "zero_copy":
-            self.sim.step_host_zero_copy(io, t, obs, log, p_obs, p_log, p_action)
+            if h_obs is not None:                        # the kernel writes the observation rows straight into pinned host memory
+                import ctypes as C
+                self.sim.step_host_zero_copy(io, t, h_obs, log, C.c_void_p(h_obs.data_ptr()), p_log, p_action)
+            else:
+                self.sim.step_host_zero_copy(io, t, obs, log, p_obs, p_log, p_action)
         else:
-            self.sim.step_host(io, t, obs, log, p_action=p_action)
+            self.sim.step_host(io, t, obs, log, h_obs=h_obs, p_action=p_action)
+        if h_obs is not None:
+            obs = h_obs
         self.common_step_counter = t + 1
         tm = self.termination_manager
         tm.terminated, tm.time_outs = io["terminated"], io["truncated"]

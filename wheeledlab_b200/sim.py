@@ -93,6 +93,11 @@ class WheeledSim:
 
     DEVICE_COUNTER = -1
 
+    def set_seed(self, seed: int):
+        """Re-key the counter-based generator (ManagerBasedEnv.seed); applies to every launch from now on."""
+        check(lib.wl_set_seed(self._h, seed), "wl_set_seed")
+        self.cfg.seed = seed
+
     def set_step_counter(self, value: int):
         check(lib.wl_set_step_counter(self._h, value, _stream_ptr(self.device)), "wl_set_step_counter")
 
