@@ -315,15 +315,25 @@ typedef struct wl_config {
 #define WL_G_PIW    15  /* 1 / wheel spin inertia per wheel (DR param; read only when dr_wheel_mass_enable) */
 #define WL_NUM_GROUPS 16
 
-/* small global (not per-env) device block appended after the groups */
+/* small global (not per-env) device block appended after the groups.  There is NO grid-wide synchronisation in a step:
+ * the kernel of step t reads what step t-1 left (weights slot (t-1) & 1, accumulator row (t-1) % 3), finished envs
+ * accumulate into row t % 3, and one warp (the "janitor", under the shadow of the state loads) publishes the weights of
+ * step t into slot t & 1, turns row (t-1) % 3 into the extras["log"] row of step t-1 at the pointer that step
+ * registered, and clears row (t+1) % 3 for the next launch.  Steps must therefore be issued with consecutive counters
+ * on one stream; the host side re-arms the block (wl_step does it transparently) when a counter jumps.
+ * Curriculum boundaries (counter % max_episode_length == 0): with a host-supplied counter wl_step adds a 1-thread kernel
+ * after the boundary step that applies the terms in place, so the host sees the new weights as soon as the step has run
+ * (the reference mutates them inside _reset_idx); with the device-resident counter the next step's threads apply them. */
 typedef struct wl_globals {
-    float rew_weight[WL_MAX_REW_TERMS];   /* live reward weights (curriculum mutates)                      */
-    float acc[16];                        /* this step: [0..7] sum over reset envs of their episode sums,   */
-                                          /* [8] #reset, [9+j] #envs whose termination term j fired          */
-    uint32_t ticket;                      /* CTAs finished in the current launch (last one finalises)       */
-    int32_t any_reset_last;               /* 1 if the previous step reset >= 1 env (read by wl_curriculum)  */
-    uint32_t step_counter;                /* common_step_counter on the device (= last step's counter + 1)  */
-    int32_t _pad[1];
+    float rew_weight[2][WL_MAX_REW_TERMS]; /* live reward weights: slot (t & 1) = weights step t used (the curriculum     */
+                                           /* mutates them on the way from slot to slot)                               */
+    float acc[3][16];                      /* row t % 3, step t: [0..7] sum over reset envs of their episode sums,       */
+                                           /* [8] #reset, [9+j] #envs whose termination term j fired                    */
+    float* log_ptr[3];                     /* d_log pointer registered by step t (row t % 3); written one launch later   */
+    uint32_t step_base;                    /* device-resident base of common_step_counter (CUDA-graph replay)            */
+    uint32_t ticket;                       /* CTAs finished (wl_rollout only: its K-step launch ends with a last-CTA pass)  */
+    uint32_t curr_applied_t;               /* counter value whose curriculum boundary the host path already applied in place  */
+    uint32_t _pad[1];
 } wl_globals;
 #define WL_LOG_FLOATS 16                  /* d_log: [0..7] Episode_Reward means, [8] #reset, [9+j] term counts */
 /* termination term order (bit j of the per-env mask; declaration order of the reference cfgs)
@@ -338,8 +348,16 @@ typedef struct wl_sim wl_sim;   /* opaque handle (host memory) */
 /* "name:tag:count:offset;..." for every wl_config field, plus "sizeof:<n>". */
 const char* wl_config_describe(void);
 size_t wl_config_sizeof(void);
-/* set the device-resident step counter (wl_create zeroes it; wl_step advances it) */
+/* device-resident counter base (wl_create zeroes it): set it / add K to it (a 1-thread kernel, capturable: the last node
+ * of a replayable graph of K steps) / tell the host mirror what the device holds after graph replays the library did
+ * not see (pure host call; `value` = base now in device memory). */
 int wl_set_step_counter(wl_sim* sim, int64_t value, void* stream);
+int wl_advance_counter(wl_sim* sim, int32_t K, void* stream);
+int wl_note_device_counter(wl_sim* sim, int64_t value);
+/* publish the extras["log"] row of the most recent step now (otherwise the next step's launch does it) */
+int wl_log_flush(wl_sim* sim, void* stream);
+/* live reward weights (what the next step will use): device pointer to WL_MAX_REW_TERMS floats inside the state buffer */
+float* wl_reward_weights(wl_sim* sim);
 /* ManagerBasedEnv.seed(): re-key the counter-based generator for all later launches (startup draws are not repeated) */
 int wl_set_seed(wl_sim* sim, uint64_t seed);
 /* fill the d_* derived fields from the primary ones (idempotent). */
@@ -369,14 +387,17 @@ int wl_startup(wl_sim* sim, void* stream);
  * IsaacLab passes them (_reset_idx).  `step_counter` keys the counter-based RNG. */
 int wl_reset(wl_sim* sim, const int64_t* d_env_ids, int32_t n_ids, int64_t step_counter, void* stream);
 /* one env.step(): action[N,2] f32 -> obs[N,obs_dim] f32, rew[N] f32, terminated[N] u8,
- * truncated[N] u8.  `step_counter` = common_step_counter BEFORE this step, or WL_DEVICE_COUNTER to use (and
- * advance) the counter kept in device memory -- then the call carries no per-step host value and a captured CUDA
- * graph of it can be replayed.  Auto-resets finished envs (reward belongs to the pre-reset state, obs to the
- * post-reset state).  The cfg's curriculum terms are applied by the last CTA (reference: inside _reset_idx). */
+ * truncated[N] u8.  `step_counter` = common_step_counter BEFORE this step (>= 0), or WL_DEVICE_COUNTER_PLUS(k): the
+ * counter base kept in device memory plus k -- then the call carries no per-step host value and a captured CUDA graph of
+ * K such calls (k = 0..K-1) followed by wl_advance_counter(K) can be replayed.  Auto-resets finished envs (reward
+ * belongs to the pre-reset state, obs to the post-reset state).  The cfg's curriculum terms are applied on the device
+ * (reference: inside _reset_idx). */
 #define WL_DEVICE_COUNTER (-1)
+#define WL_DEVICE_COUNTER_PLUS(k) (-1 - (int64_t)(k))
 /* d_log: optional float[WL_LOG_FLOATS]: mean over the envs reset in this step of each reward term's episode sum
  * divided by max_episode_length_s (RewardManager.reset -> extras["log"]), then the reset / terminated / time-out
- * counts.  Written by the last CTA of the launch: no extra kernel, no host sync. */
+ * counts.  No extra kernel, no host sync, no grid-wide sync: the row of step t is written by the NEXT launch on the
+ * handle (the step after it, or wl_log_flush), i.e. it is valid once that launch has completed. */
 int wl_step(wl_sim* sim, const float* d_action, float* d_obs, float* d_rew, uint8_t* d_terminated,
             uint8_t* d_truncated, float* d_log, int64_t step_counter, void* stream);
 /* K consecutive env.step()s in ONE launch with the state held in registers (synthetic / scripted-action rollouts:

@@ -105,6 +105,7 @@ def test_step_trajectory_bit_exact(n, steps, kw, variant):
         assert np.array_equal(_bits(a_np), _bits(orc.synth_actions(t, dist=t % 2)))
         log = torch.empty(16, device="cuda")
         obs, rew, term, trunc = sim.step(act, t, log=log)
+        sim.flush_log()                                  # the row of step t is published by the next launch on the handle
         o_obs, o_rew, o_term, o_trunc = orc.step(a_np, t)
         torch.cuda.synchronize()
         assert np.array_equal(term.cpu().numpy(), o_term), f"terminated mask differs at step {t}"
@@ -209,7 +210,8 @@ def test_curriculum_on_device_matches_oracle():
 
 
 def test_device_counter_graph_replay_equals_host_counter():
-    """wl_step(WL_DEVICE_COUNTER) captured ONCE in a CUDA graph and replayed T times == T host-counter steps."""
+    """wl_step on the device-resident counter (base + 0, then base += 1) captured ONCE in a CUDA graph and replayed T times ==
+    T host-counter steps."""
     _need_gpu()
     import wheeledlab_b200 as wl
     n, T = 512, 300
@@ -225,13 +227,16 @@ def test_device_counter_graph_replay_equals_host_counter():
         with torch.cuda.graph(g, stream=stream):
             b.synth_actions(wl.WheeledSim.DEVICE_COUNTER, out=act)
             b.step(act, wl.WheeledSim.DEVICE_COUNTER, out=out)
+            b.advance_counter(1)
     torch.cuda.current_stream().wait_stream(stream)
+    b.set_step_counter(1)                            # capture moved the host mirror of the counter; nothing has run yet
     for t in range(1, T):
         ref = a.step(a.synth_actions(t), t)
         g.replay()
         torch.cuda.synchronize()
         for x, y in zip(ref, out):
             assert torch.equal(x, y), f"graph replay differs at step {t}"
+    b.note_device_counter(T)
     assert torch.equal(a.groups, b.groups) and torch.equal(a.rew_weight, b.rew_weight)
 
 
@@ -320,6 +325,7 @@ def test_elevation_trajectory_bit_exact(variant, tma):
         act = sim.synth_actions(t)
         log = torch.empty(16, device="cuda")
         obs, rew, term, trunc = sim.step(act, t, log=log)
+        sim.flush_log()
         o_obs, o_rew, o_term, o_trunc = orc.step(act.cpu().numpy(), t)
         torch.cuda.synchronize()
         assert np.array_equal(term.cpu().numpy(), o_term) and np.array_equal(trunc.cpu().numpy(), o_trunc), t
@@ -489,7 +495,7 @@ def test_fused_k_step_rollout_equals_k_single_steps():
         for k in range(K):
             act = a.synth_actions(t0 + k)
             log = torch.empty(16, device="cuda")
-            obs, rew, term, trunc = a.step(act, t0 + k, log=log)
+            obs, rew, term, trunc = a.step(act, t0 + k, log=log); a.flush_log()
             assert torch.equal(got[4][k], act) and torch.equal(got[0][k], obs) and torch.equal(got[1][k], rew), (t0, k)
             assert torch.equal(got[2][k], term) and torch.equal(got[3][k], trunc)
             if t0 != 200:
@@ -584,6 +590,16 @@ def test_fused_policy_rollout_graph_equals_eager_act_steps():
             assert torch.equal(slab.obs[k], out[0]) and torch.equal(slab.rewards[k], out[1])
             obs = out[0]
     assert torch.equal(a.groups, b.groups)
+    # storage alignment (rsl_rl RolloutStorage): obs_in[k] is the observation actions[k] / mean[k] / log_prob[k] / values[k]
+    # were computed from -- recompute them with torch from the slab alone
+    with torch.no_grad():
+        for k in (0, 1, T - 1):
+            mu = actor(slab.obs_in[k]); v = critic(slab.obs_in[k]).squeeze(-1)
+            assert torch.allclose(mu, roll.pol.mean[k], atol=3e-5) and torch.allclose(v, roll.pol.values[k], atol=3e-5), k
+            lp_ref = (-0.5 * (((slab.actions[k] - mu) / std.cuda()) ** 2).sum(-1) - torch.log(std.cuda()).sum() - 1.8378770664093453)
+            assert torch.allclose(lp_ref, roll.pol.log_prob[k], atol=2e-3), k
+            if k + 1 < T:
+                assert torch.equal(slab.obs[k], slab.obs_in[k + 1])
     with pytest.raises(wl.WlError):                      # 689-wide elevation observations are not supported by the fused policy
         e = wl.WheeledSim(wl.elevation_task(num_envs=8, seed=1, terrain="procedural"), "cuda:0")
         act_step(e, torch.zeros((8, 689), device=dev), blob, act, mean, lp, val, out, None, 0)
@@ -606,9 +622,9 @@ def test_staged_step_equals_fused_step(task):
     steps = 520 if task == "drift" else 230                # crosses episode ends (250 / 200 steps) -> time-out resets + curriculum
     for t in range(steps):
         act = a.synth_actions(t)
-        obs, rew, term, trunc = a.step(act, t, log=la)
+        obs, rew, term, trunc = a.step(act, t, log=la); a.flush_log()
         rew_b, bits = b.step_stage_a(act, t)
-        obs_b, term_b, trunc_b = b.step_stage_b(bits, t, log=lb)
+        obs_b, term_b, trunc_b = b.step_stage_b(bits, t, log=lb); b.flush_log()
         assert torch.equal(rew, rew_b) and torch.equal(obs, obs_b), (task, t)
         assert torch.equal(term, term_b) and torch.equal(trunc, trunc_b), (task, t)
         assert torch.allclose(la, lb, rtol=1e-4, atol=1e-6), (task, t)    # float atomics across warps: order is not fixed

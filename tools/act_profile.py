@@ -34,11 +34,12 @@ def main():
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s), torch.cuda.graph(g, stream=s):
-            for _ in range(50):
+            for k in range(50):
                 if mode == "step":
-                    sim.step(act, wl.WheeledSim.DEVICE_COUNTER, out=out, log=log)
+                    sim.step(act, wl.WheeledSim.device_counter_plus(k), out=out, log=log)
                 else:
-                    act_step(sim, out[0], blob, act, mean, lp, val, out, log, wl.WheeledSim.DEVICE_COUNTER)
+                    act_step(sim, out[0], blob, act, mean, lp, val, out, log, wl.WheeledSim.device_counter_plus(k))
+            sim.advance_counter(50)
         torch.cuda.current_stream().wait_stream(s)
         g.replay(); torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -22,6 +22,8 @@ struct wl_sim {
     const float* hf;        // device height-field or null
     size_t state_bytes;
     int64_t launches;
+    int64_t last_t;         // counter of the most recent step launched through this handle (-1: none); host mirror
+    int64_t base_host;      // host mirror of wl_globals.step_base
     int obs_dim;
     int variant;            // 0 auto, 1 thread-per-env, 4 quad-per-env
     CUtensorMap tmap;       // 2-D tensor map over the height-field (elevation task)
@@ -45,14 +47,60 @@ static inline size_t align256(size_t x) { return (x + 255u) & ~(size_t)255u; }
 // ---------------------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------------------
+// ---- per-step bookkeeping without a grid-wide sync (layout + protocol: wl_globals in the header) ---------------------
+// step counter of this launch: the host's value, or (negative host value = -1 - k) device base + k
+__device__ __forceinline__ uint32_t decode_step(const wl_globals* __restrict__ gl, uint32_t t_arg) {
+    return ((int32_t)t_arg < 0) ? __ldcg(&gl->step_base) + (0xFFFFFFFFu - t_arg) : t_arg;
+}
+// W(t): the weights step t-1 used, plus increase_reward_weight_over_time (curriculums.py:23-35) for the counter value t
+// reached by the step that just ended -- the reference calls it from _reset_idx, i.e. only if >= 1 env reset in step t-1.
+// Every thread of the launch evaluates this identically (no thread writes what another one reads here).
+__device__ __forceinline__ void load_weights(const wl_config& c, const wl_globals* __restrict__ gl, uint32_t t, float wts[WL_MAX_REW_TERMS]) {
+    const float4* wp = reinterpret_cast<const float4*>(gl->rew_weight[(t + 1u) & 1u]);
+    const float4 w0 = __ldcg(wp), w1 = __ldcg(wp + 1);
+    wts[0] = w0.x; wts[1] = w0.y; wts[2] = w0.z; wts[3] = w0.w; wts[4] = w1.x; wts[5] = w1.y; wts[6] = w1.z; wts[7] = w1.w;
+    if (c.curr_n > 0 && t != 0u && (t % (uint32_t)c.max_episode_length) == 0u) {
+        if (__ldcg(&gl->acc[(t + 2u) % 3u][8]) > 0.0f && __ldcg(&gl->curr_applied_t) != t) {     // (not already applied in place by the host path)
+            const int E = (int)(t / (uint32_t)c.max_episode_length);
+            for (int k = 0; k < c.curr_n; ++k) {
+                if (E / c.curr_every[k] > c.curr_max[k]) continue;
+                if ((E + 1) % c.curr_every[k] == 0) {
+                    const int slot = c.curr_slot[k];
+#pragma unroll
+                    for (int q = 0; q < WL_MAX_REW_TERMS; ++q) if (q == slot) wts[q] += c.curr_inc[k];
+                }
+            }
+        }
+    }
+}
+// extras["log"] row of the step whose accumulators are `row`: means of the episode sums over the reset envs divided by
+// max_episode_length_s (RewardManager.reset), then the counts.  Lanes 0..15 of one warp, one element each.
+__device__ __forceinline__ void publish_log_row(const wl_config& c, wl_globals* __restrict__ gl, uint32_t row, int lane) {
+    const float v = (lane < 16) ? __ldcg(&gl->acc[row][lane]) : 0.0f;
+    const float cnt = __shfl_sync(0xffffffffu, v, 8);
+    float* lp = gl->log_ptr[row];
+    if (lp != nullptr && lane < 16) lp[lane] = (lane < WL_MAX_REW_TERMS) ? v / (r_max(cnt, 1.0f) * c.episode_length_s) : v;
+}
+// The janitor: ONE warp of the launch (warp 0 of CTA 0), right after it has issued its state loads.
+__device__ __forceinline__ void janitor(const wl_config& c, wl_globals* __restrict__ gl, uint32_t t, const float wts[WL_MAX_REW_TERMS],
+                                        float* __restrict__ d_log) {
+    const int lane = threadIdx.x & 31;
+    if (t != 0u) publish_log_row(c, gl, (t + 2u) % 3u, lane);          // step t-1 (complete: its kernel has finished)
+    if (lane < 16) gl->acc[(t + 1u) % 3u][lane] = 0.0f;                // re-arm the row step t+1 will use
+    float w = wts[0];
+#pragma unroll
+    for (int q = 1; q < WL_MAX_REW_TERMS; ++q) w = (lane == q) ? wts[q] : w;
+    if (lane < WL_MAX_REW_TERMS) gl->rew_weight[t & 1u][lane] = w;     // W(t), read by step t+1
+    if (lane == 0) gl->log_ptr[t % 3u] = d_log;
+}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
-
-// Per-step episode log: warp-shuffle reduce over the finished envs, one atomic set per warp.
-// acc layout: [0..7] episode sums, [8] #reset, [9+j] #envs whose termination term j fired (tmask bit j).
+// Finished envs -> this step's accumulator row: warp-shuffle reduce, one RED set per warp (no fence, no ticket: the
+// kernel boundary publishes the row to the next launch).  acc layout: [0..7] episode sums, [8] #reset, [9+j] #envs whose
+// termination term j fired (tmask bit j).
 __device__ __forceinline__ bool log_accumulate(float* __restrict__ acc, bool contrib, uint32_t tmask,
                                                const float sums[WL_MAX_REW_TERMS]) {
     const unsigned any_c = __ballot_sync(0xffffffffu, contrib);
@@ -68,52 +116,8 @@ __device__ __forceinline__ bool log_accumulate(float* __restrict__ acc, bool con
     if ((threadIdx.x & 31) == 0) {
 #pragma unroll
         for (int k = 0; k < 16; ++k) if (vals[k] != 0.0f) atomicAdd(&acc[k], vals[k]);
-#ifndef WL_EXP_NOFENCE
-        __threadfence();          // order this warp's accumulation before its CTA's ticket (only warps that contributed pay)
-#endif
     }
     return true;
-}
-// increase_reward_weight_over_time (curriculums.py:23-35) for the counter value `cn` reached by the step that just ended;
-// the reference calls it from _reset_idx, i.e. only on steps where >= 1 env reset.
-__device__ __forceinline__ void apply_curriculum(const wl_config& c, wl_globals* __restrict__ gl, uint32_t cn, bool any_reset) {
-    if (c.curr_n <= 0 || !any_reset || (cn % (uint32_t)c.max_episode_length) != 0u) return;
-    const int E = (int)(cn / (uint32_t)c.max_episode_length);
-    for (int k = 0; k < c.curr_n; ++k) {
-        if (E / c.curr_every[k] > c.curr_max[k]) continue;
-        if ((E + 1) % c.curr_every[k] == 0) gl->rew_weight[c.curr_slot[k]] += c.curr_inc[k];
-    }
-}
-// Last CTA of the launch turns the accumulators into the extras["log"] row and re-arms them.
-__device__ __forceinline__ void log_finalize(const wl_config& c, wl_globals* __restrict__ gl, float* __restrict__ d_log, uint32_t t) {
-#ifdef WL_EXP_NOFINAL
-    return;
-#endif
-    __syncthreads();              // all warps of the CTA are past their (fenced) accumulation
-    if (threadIdx.x != 0) return;
-    const unsigned tk = atomicAdd(&gl->ticket, 1u);
-    if (tk != gridDim.x - 1) return;
-    __threadfence();
-    float a[16];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) a[k] = __ldcg(&gl->acc[k]);
-    const float cnt = a[8];
-    if (d_log != nullptr) {
-        const float denom = r_max(cnt, 1.0f) * c.episode_length_s;
-#pragma unroll
-        for (int k = 0; k < WL_MAX_REW_TERMS; ++k) d_log[k] = a[k] / denom;
-#pragma unroll
-        for (int k = 8; k < 16; ++k) d_log[k] = a[k];
-    }
-    gl->any_reset_last = (cnt > 0.0f) ? 1 : 0;
-#pragma unroll
-    for (int k = 0; k < 16; ++k) gl->acc[k] = 0.0f;
-    gl->ticket = 0u;
-    // common_step_counter += 1, then the curriculum (increase_reward_weight_over_time, curriculums.py:23-35; the
-    // reference calls it from _reset_idx, i.e. only on steps where >= 1 env reset)
-    const uint32_t cn = t + 1u;
-    gl->step_counter = cn;
-    apply_curriculum(c, gl, cn, cnt > 0.0f);
 }
 
 // One thread per env.  TASK selects the MDP + terrain at compile time.
@@ -133,14 +137,14 @@ wl_step_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st, wl_
     constexpr bool ELEV = (TASK == WL_TASK_ELEVATION), VIS = (TASK == WL_TASK_VISUAL);
     const int n = c.num_envs;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t t = (t_arg == 0xFFFFFFFFu) ? __ldcg(&gl->step_counter) : t_arg;   // device-resident counter (graph replay)
+    const uint32_t t = decode_step(gl, t_arg);
     const VisualMap vm = VIS ? visual_map(c, T.hf) : VisualMap{nullptr, nullptr};
     bool done = false;
     uint32_t tmask = 0u;
     EnvState e;
-    // live reward weights: issued with the state loads so their latency hides behind the integrator
-    const float4 rw0 = __ldg(reinterpret_cast<const float4*>(gl->rew_weight)), rw1 = __ldg(reinterpret_cast<const float4*>(gl->rew_weight) + 1);
-    const float wts[WL_MAX_REW_TERMS] = {rw0.x, rw0.y, rw0.z, rw0.w, rw1.x, rw1.y, rw1.z, rw1.w};
+    float wts[WL_MAX_REW_TERMS];            // W(t): issued with the state loads so the latency hides behind the integrator
+    load_weights(c, gl, t, wts);
+    if (STAGE != 1 && blockIdx.x == 0 && threadIdx.x < 32) janitor(c, gl, t, wts, d_log);
     if (STAGE == 2) {
         if (i < n) {
             load_env(st, n, i, e, ELEV, c.dr_wheel_mass_enable != 0, c.d_inv_Iw);
@@ -212,7 +216,7 @@ wl_step_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st, wl_
     }
     if (STAGE == 1) return;
     // F. auto-reset + per-step episode log (warp-shuffle reduction over the finished envs)
-    log_accumulate(gl->acc, done, tmask, e.sums);
+    log_accumulate(gl->acc[t % 3u], done, tmask, e.sums);
     if (i < n) {
         const uint32_t gid = (uint32_t)(c.env_id_offset + i);
         if (done) {
@@ -236,7 +240,6 @@ wl_step_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st, wl_
         }
         store_env(st, n, i, e, ELEV);
     }
-    log_finalize(c, gl, d_log, t);
 }
 
 // Four lanes per env (lane = wheel).  Same arithmetic, same results; the per-wheel work runs in parallel and the
@@ -352,7 +355,7 @@ wl_step_quad_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st
                     const float2* __restrict__ action, float* __restrict__ obs, float* __restrict__ rew,
                     uint8_t* __restrict__ terminated_o, uint8_t* __restrict__ truncated_o, float* __restrict__ d_log, uint32_t t_arg) {
     constexpr bool ELEV = (TASK == WL_TASK_ELEVATION), VIS = (TASK == WL_TASK_VISUAL);
-    const uint32_t t = (t_arg == 0xFFFFFFFFu) ? __ldcg(&gl->step_counter) : t_arg;
+    const uint32_t t = decode_step(gl, t_arg);
     const VisualMap vm = VIS ? visual_map(c, T.hf) : VisualMap{nullptr, nullptr};
     const int n = c.num_envs;
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -362,13 +365,13 @@ wl_step_quad_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st
     const uint32_t gid = (uint32_t)(c.env_id_offset + ii);
     const unsigned base = (threadIdx.x & 31u) & ~3u;
     EnvState e;
-    const float4 rw0 = __ldg(reinterpret_cast<const float4*>(gl->rew_weight)), rw1 = __ldg(reinterpret_cast<const float4*>(gl->rew_weight) + 1);
-    const float wts[WL_MAX_REW_TERMS] = {rw0.x, rw0.y, rw0.z, rw0.w, rw1.x, rw1.y, rw1.z, rw1.w};
     load_env_quad(st, n, ii, w, e, ELEV, c.dr_wheel_mass_enable != 0, c.d_inv_Iw);
+    float wts[WL_MAX_REW_TERMS];
+    load_weights(c, gl, t, wts);
+    if (blockIdx.x == 0 && threadIdx.x < 32) janitor(c, gl, t, wts, d_log);
     const int od = ELEV ? WL_OBS_DIM_ELEV : VIS ? WL_OBS_DIM_VISUAL + vis_cam_floats(c) : WL_OBS_DIM_BLIND;
-    quad_env_step<TASK>(c, T, vm, gl->acc, wts, e, i, w, live, gid, base, t, action[ii], obs + (size_t)od * ii, rew, terminated_o, truncated_o);
+    quad_env_step<TASK>(c, T, vm, gl->acc[t % 3u], wts, e, i, w, live, gid, base, t, action[ii], obs + (size_t)od * ii, rew, terminated_o, truncated_o);
     if (live) store_env_quad(st, n, i, w, e, ELEV);
-    log_finalize(c, gl, d_log, t);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -476,7 +479,7 @@ wl_act_step_quad_kernel(const __grid_constant__ wl_config c, float4* __restrict_
         bulk_g2s(sw + a1, blob + a1, (uint32_t)(c0 - a1) * 4u, &mbar[1]);
         bulk_g2s(sw + c1, blob + c1, (uint32_t)(blob_floats - c1) * 4u, &mbar[1]);
     }
-    const uint32_t t = (t_arg == 0xFFFFFFFFu) ? __ldcg(&gl->step_counter) : t_arg;
+    const uint32_t t = decode_step(gl, t_arg);
     const VisualMap vm = VIS ? visual_map(c, T.hf) : VisualMap{nullptr, nullptr};
     const int n = c.num_envs;
     const bool stepper = threadIdx.x < 4 * WL_ACT_ENVS;      // warps 0..3 own the env quads; warps 4..7 only help with the MLPs
@@ -489,9 +492,9 @@ wl_act_step_quad_kernel(const __grid_constant__ wl_config c, float4* __restrict_
     EnvState e;
     float wts[WL_MAX_REW_TERMS];
     if (stepper) {
-        const float4 rw0 = __ldg(reinterpret_cast<const float4*>(gl->rew_weight)), rw1 = __ldg(reinterpret_cast<const float4*>(gl->rew_weight) + 1);
-        wts[0] = rw0.x; wts[1] = rw0.y; wts[2] = rw0.z; wts[3] = rw0.w; wts[4] = rw1.x; wts[5] = rw1.y; wts[6] = rw1.z; wts[7] = rw1.w;
         load_env_quad(st, n, ii, w, e, ELEV, c.dr_wheel_mass_enable != 0, c.d_inv_Iw);
+        load_weights(c, gl, t, wts);
+        if (blockIdx.x == 0 && threadIdx.x < 32) janitor(c, gl, t, wts, d_log);
     }
     for (int k = threadIdx.x; k < WL_ACT_ENVS * 16; k += WL_ACT_THREADS) {
         const int eq = k >> 4, j = k & 15, ei = min(blockIdx.x * WL_ACT_ENVS + eq, n - 1);
@@ -552,10 +555,9 @@ wl_act_step_quad_kernel(const __grid_constant__ wl_config c, float4* __restrict_
         }
         // ---- the env step on the sampled action
         const int od = ELEV ? WL_OBS_DIM_ELEV : VIS ? WL_OBS_DIM_VISUAL + vis_cam_floats(c) : WL_OBS_DIM_BLIND;
-        quad_env_step<TASK>(c, T, vm, gl->acc, wts, e, i, w, live, gid, base, t, a, obs + (size_t)od * ii, rew, terminated_o, truncated_o);
+        quad_env_step<TASK>(c, T, vm, gl->acc[t % 3u], wts, e, i, w, live, gid, base, t, a, obs + (size_t)od * ii, rew, terminated_o, truncated_o);
         if (live) store_env_quad(st, n, i, w, e, ELEV);
     }
-    log_finalize(c, gl, d_log, t);
 }
 
 // K consecutive env.step()s in ONE launch (synthetic / scripted-action rollouts): the state stays in registers
@@ -568,9 +570,9 @@ __global__ void __launch_bounds__(128)
 wl_rollout_quad_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st, wl_globals* __restrict__ gl, Terrain T,
                        const float2* __restrict__ action, float2* __restrict__ act_out, float* __restrict__ obs,
                        float* __restrict__ rew, uint8_t* __restrict__ terminated_o, uint8_t* __restrict__ truncated_o,
-                       float* __restrict__ d_log, uint32_t t_arg, int K) {
+                       float* __restrict__ d_log, uint32_t t_arg, int K, unsigned* __restrict__ ticket) {
     constexpr bool ELEV = (TASK == WL_TASK_ELEVATION), VIS = (TASK == WL_TASK_VISUAL);
-    const uint32_t t0 = (t_arg == 0xFFFFFFFFu) ? __ldcg(&gl->step_counter) : t_arg;
+    const uint32_t t0 = decode_step(gl, t_arg);
     const VisualMap vm = VIS ? visual_map(c, T.hf) : VisualMap{nullptr, nullptr};
     const int n = c.num_envs;
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -580,9 +582,10 @@ wl_rollout_quad_kernel(const __grid_constant__ wl_config c, float4* __restrict__
     const uint32_t gid = (uint32_t)(c.env_id_offset + ii);
     const unsigned base = (threadIdx.x & 31u) & ~3u;
     EnvState e;
-    const float4 rw0 = __ldg(reinterpret_cast<const float4*>(gl->rew_weight)), rw1 = __ldg(reinterpret_cast<const float4*>(gl->rew_weight) + 1);
-    const float wts[WL_MAX_REW_TERMS] = {rw0.x, rw0.y, rw0.z, rw0.w, rw1.x, rw1.y, rw1.z, rw1.w};
     load_env_quad(st, n, ii, w, e, ELEV, c.dr_wheel_mass_enable != 0, c.d_inv_Iw);
+    float wts[WL_MAX_REW_TERMS];             // W(t0) holds for the whole window (it never crosses an episode boundary)
+    load_weights(c, gl, t0, wts);
+    if (blockIdx.x == 0 && threadIdx.x < 32) janitor(c, gl, t0, wts, nullptr);      // flushes step t0-1's log row
     const int od = ELEV ? WL_OBS_DIM_ELEV : VIS ? WL_OBS_DIM_VISUAL + vis_cam_floats(c) : WL_OBS_DIM_BLIND;
     for (int k = 0; k < K; ++k) {
         const uint32_t t = t0 + (uint32_t)k;
@@ -598,10 +601,13 @@ wl_rollout_quad_kernel(const __grid_constant__ wl_config c, float4* __restrict__
                             truncated_o + (size_t)k * n);
     }
     if (live) store_env_quad(st, n, i, w, e, ELEV);
-    // last CTA: turn the K accumulator rows into means, publish the counter / any-reset flag
+    // last CTA (ticket, amortised over the K steps of the launch): turn the K accumulator rows into means and leave the
+    // globals as K single steps would have: W of the last step in its slot, its reset count where the next launch looks for
+    // it (the curriculum boundary at t0 + K is evaluated there), nothing pending for the log, the next row re-armed
+    if ((threadIdx.x & 31) == 0) __threadfence();
     __syncthreads();
     if (threadIdx.x != 0) return;
-    const unsigned tk = atomicAdd(&gl->ticket, 1u);
+    const unsigned tk = atomicAdd(ticket, 1u);
     if (tk != gridDim.x - 1) return;
     __threadfence();
     float last_cnt = 0.0f;
@@ -612,10 +618,11 @@ wl_rollout_quad_kernel(const __grid_constant__ wl_config c, float4* __restrict__
         for (int q = 0; q < WL_MAX_REW_TERMS; ++q) row[q] = __ldcg(&row[q]) / denom;
         last_cnt = cnt;
     }
-    gl->any_reset_last = (last_cnt > 0.0f) ? 1 : 0;
-    gl->step_counter = t0 + (uint32_t)K;
-    gl->ticket = 0u;
-    apply_curriculum(c, gl, t0 + (uint32_t)K, last_cnt > 0.0f);
+    const uint32_t tl = t0 + (uint32_t)K - 1u;
+    for (int q = 0; q < WL_MAX_REW_TERMS; ++q) gl->rew_weight[tl & 1u][q] = wts[q];
+    for (int q = 0; q < 16; ++q) { gl->acc[tl % 3u][q] = (q == 8) ? last_cnt : 0.0f; gl->acc[(tl + 1u) % 3u][q] = 0.0f; }
+    gl->log_ptr[tl % 3u] = nullptr;
+    *ticket = 0u;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -835,19 +842,40 @@ __global__ void wl_suspension_kernel(const __grid_constant__ wl_config c, const 
     vel_o[i] = make_float4(sv[0], sv[1], sv[2], sv[3]);
 }
 
-struct CurrArgs { int32_t n; int32_t slots[WL_MAX_REW_TERMS]; float inc[WL_MAX_REW_TERMS]; uint32_t fire_mask; };
+struct CurrArgs { int32_t n; int32_t slots[WL_MAX_REW_TERMS]; float inc[WL_MAX_REW_TERMS]; uint32_t fire_mask; uint32_t wslot, row; };
 __global__ void wl_curriculum_kernel(wl_globals* __restrict__ gl, CurrArgs a) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    if (!gl->any_reset_last) return;
+    if (!(gl->acc[a.row][8] > 0.0f)) return;                 // the reference's call site is _reset_idx: only if >= 1 env reset
     for (int t = 0; t < a.n; ++t)
-        if ((a.fire_mask >> t) & 1u) gl->rew_weight[a.slots[t]] += a.inc[t];
+        if ((a.fire_mask >> t) & 1u) gl->rew_weight[a.wslot][a.slots[t]] += a.inc[t];
 }
+// publish the log row of step t_next - 1 without stepping (idempotent; the next step's janitor would do the same)
+__global__ void wl_flush_kernel(const __grid_constant__ wl_config c, wl_globals* __restrict__ gl, uint32_t t_next) {
+    if (t_next != 0u) publish_log_row(c, gl, (t_next + 2u) % 3u, threadIdx.x & 31);
+}
+// counter jump: carry the weights over to the slot the next step reads, clear the accumulators and the pending log
+__global__ void wl_rearm_kernel(wl_globals* __restrict__ gl, uint32_t from_slot, uint32_t to_slot) {
+    const int lane = threadIdx.x;
+    if (lane < WL_MAX_REW_TERMS && from_slot != to_slot) gl->rew_weight[to_slot][lane] = gl->rew_weight[from_slot][lane];
+    if (lane < 16) { gl->acc[0][lane] = 0.0f; gl->acc[1][lane] = 0.0f; gl->acc[2][lane] = 0.0f; }
+    if (lane < 3) gl->log_ptr[lane] = nullptr;
+}
+// host-counter path, after a step whose successor counter t_next is a curriculum boundary: apply the terms in place to the
+// slot step t_next will read (so the host sees them at once) and mark the boundary as done
+__global__ void wl_boundary_kernel(const __grid_constant__ wl_config c, wl_globals* __restrict__ gl, uint32_t t_next) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    float wts[WL_MAX_REW_TERMS];
+    load_weights(c, gl, t_next, wts);
+    for (int q = 0; q < WL_MAX_REW_TERMS; ++q) gl->rew_weight[(t_next + 1u) & 1u][q] = wts[q];
+    gl->curr_applied_t = t_next;
+}
+__global__ void wl_advance_kernel(wl_globals* __restrict__ gl, uint32_t k) { if (threadIdx.x == 0 && blockIdx.x == 0) gl->step_base += k; }
 
 __global__ void wl_synth_actions_kernel(const __grid_constant__ wl_config c, const wl_globals* __restrict__ gl,
                                         float2* __restrict__ action, uint32_t t_arg, int dist) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= c.num_envs) return;
-    const uint32_t t = (t_arg == 0xFFFFFFFFu) ? __ldcg(&gl->step_counter) : t_arg;
+    const uint32_t t = decode_step(gl, t_arg);
     uint4 r = philox4x32(c.seed, (uint32_t)(c.env_id_offset + i), t, RNG_ACTION, 0u);
     float a0, a1;
     if (dist == 0) { a0 = 2.0f * u01(r.x) - 1.0f; a1 = 2.0f * u01(r.y) - 1.0f; }
@@ -943,7 +971,7 @@ wl_camera_kernel(const __grid_constant__ wl_config c, const float4* __restrict__
     const int RG = WL_CAM_THREADS / W4;                      // row groups (threads >= RG * W4 idle in the 2-D phases)
     const int rg = tid / W4, u4 = tid - rg * W4;
     const bool act = rg < RG;
-    const uint32_t t = (t_arg == 0xFFFFFFFFu) ? __ldcg(&gl->step_counter) - 1u : t_arg;    // the step's epilogue already advanced it
+    const uint32_t t = decode_step(gl, t_arg);
     const VisualMap vm = visual_map(c, aux);
     const float4 gp = ldg4(st, WL_G_POS, n, i), gq = ldg4(st, WL_G_QUAT, n, i);
     const M3 R = rotmat(gq.x, gq.y, gq.z, gq.w);
@@ -1094,9 +1122,31 @@ const char* wl_config_describe(void) {
 int wl_set_step_counter(wl_sim* sim, int64_t value, void* stream) {
     if (!sim) return fail(WL_EINVAL, "wl_set_step_counter: null handle");
     const uint32_t v = (uint32_t)value;
-    return cuda_check(cudaMemcpyAsync(&sim->globals->step_counter, &v, sizeof v, cudaMemcpyHostToDevice, (cudaStream_t)stream),
+    sim->base_host = value;
+    return cuda_check(cudaMemcpyAsync(&sim->globals->step_base, &v, sizeof v, cudaMemcpyHostToDevice, (cudaStream_t)stream),
                       "wl_set_step_counter");
 }
+int wl_advance_counter(wl_sim* sim, int32_t K, void* stream) {
+    if (!sim || K < 0) return fail(WL_EINVAL, "wl_advance_counter: bad argument");
+    wl_advance_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(sim->globals, (uint32_t)K);
+    sim->launches++;
+    sim->base_host += K;
+    return cuda_check(cudaGetLastError(), "wl_advance_kernel");
+}
+int wl_note_device_counter(wl_sim* sim, int64_t value) {
+    if (!sim) return fail(WL_EINVAL, "wl_note_device_counter: null handle");
+    sim->base_host = value;
+    sim->last_t = value - 1;          // the replayed graph ended on step value - 1
+    return WL_OK;
+}
+int wl_log_flush(wl_sim* sim, void* stream) {
+    if (!sim) return fail(WL_EINVAL, "wl_log_flush: null handle");
+    if (sim->last_t < 0) return WL_OK;
+    wl_flush_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(sim->cfg, sim->globals, (uint32_t)(sim->last_t + 1));
+    sim->launches++;
+    return cuda_check(cudaGetLastError(), "wl_flush_kernel");
+}
+float* wl_reward_weights(wl_sim* sim) { return sim ? sim->globals->rew_weight[(uint32_t)sim->last_t & 1u] : nullptr; }
 
 int wl_set_seed(wl_sim* sim, uint64_t seed) {
     if (!sim) return fail(WL_EINVAL, "wl_set_seed: null handle");
@@ -1180,6 +1230,8 @@ int wl_create(const wl_config* cfg, void* d_state, size_t state_bytes, const flo
     s->hf = d_heightfield;
     s->state_bytes = state_bytes;
     s->launches = 0;
+    s->last_t = -1;
+    s->base_host = 0;
     s->variant = 0;
     s->has_tmap = false;
     s->scan_tma = true;
@@ -1203,8 +1255,13 @@ int wl_create(const wl_config* cfg, void* d_state, size_t state_bytes, const flo
     }
     s->obs_dim = (cfg->task == WL_TASK_ELEVATION) ? WL_OBS_DIM_ELEV : (cfg->task == WL_TASK_VISUAL) ? WL_OBS_DIM_VISUAL + (cfg->vis_cam ? cfg->vis_cam_w * (cfg->vis_cam_h - cfg->vis_cam_row0) : 0) : WL_OBS_DIM_BLIND;
     // live reward weights
-    if (int rc = cuda_check(cudaMemcpy(s->globals->rew_weight, cfg->rew_weight, sizeof(float) * WL_MAX_REW_TERMS,
-                                       cudaMemcpyHostToDevice), "upload reward weights")) { delete s; return rc; }
+    for (int slot = 0; slot < 2; ++slot)
+        if (int rc = cuda_check(cudaMemcpy(s->globals->rew_weight[slot], cfg->rew_weight, sizeof(float) * WL_MAX_REW_TERMS,
+                                           cudaMemcpyHostToDevice), "upload reward weights")) { delete s; return rc; }
+    {
+        const uint32_t none = 0xFFFFFFFFu;
+        if (int rc = cuda_check(cudaMemcpy(&s->globals->curr_applied_t, &none, sizeof none, cudaMemcpyHostToDevice), "init globals")) { delete s; return rc; }
+    }
     *out = s;
     return WL_OK;
 }
@@ -1229,6 +1286,32 @@ int64_t wl_launch_count(const wl_sim* sim) { return sim ? sim->launches : 0; }
         (sim)->launches++;                                                             \
         if (int rc_ = cuda_check(cudaGetLastError(), what)) return rc_;                \
     } while (0)
+
+}   // extern "C"
+// Steps are issued with consecutive counters (the janitor protocol, see wl_globals).  Resolve this launch's counter on the host
+// mirror; on a jump publish the pending log row, carry the weights to the slot the step will read and clear the rows.
+static int prep_step(wl_sim* sim, int64_t step_counter, int32_t n_steps, cudaStream_t cs) {
+    const int64_t t = step_counter >= 0 ? step_counter : sim->base_host + (-1 - step_counter);
+    if (t >= ((int64_t)1 << 31) - n_steps) return fail(WL_EINVAL, "step counter out of range (< 2^31)");
+    if (t != sim->last_t + 1) {
+        if (sim->last_t >= 0) wl_flush_kernel<<<1, 32, 0, cs>>>(sim->cfg, sim->globals, (uint32_t)(sim->last_t + 1));
+        wl_rearm_kernel<<<1, 32, 0, cs>>>(sim->globals, (uint32_t)sim->last_t & 1u, (uint32_t)(t - 1) & 1u);
+        sim->launches += 2;
+        if (int rc = cuda_check(cudaGetLastError(), "wl_rearm_kernel")) return rc;
+    }
+    sim->last_t = t + n_steps - 1;
+    return WL_OK;
+}
+// after the step kernel(s): a curriculum boundary reached with a host-supplied counter is applied in place right away
+static int post_step(wl_sim* sim, int64_t step_counter, cudaStream_t cs) {
+    if (step_counter < 0 || sim->cfg.curr_n <= 0) return WL_OK;
+    const int64_t t_next = sim->last_t + 1;
+    if (t_next % sim->cfg.max_episode_length != 0) return WL_OK;
+    wl_boundary_kernel<<<1, 32, 0, cs>>>(sim->cfg, sim->globals, (uint32_t)t_next);
+    sim->launches++;
+    return cuda_check(cudaGetLastError(), "wl_boundary_kernel");
+}
+extern "C" {
 
 int wl_startup(wl_sim* sim, void* stream) {
     if (!sim) return fail(WL_EINVAL, "wl_startup: null handle");
@@ -1257,7 +1340,8 @@ int wl_step(wl_sim* sim, const float* d_action, float* d_obs, float* d_rew, uint
     const int variant = sim->variant ? sim->variant : ((n <= WL_QUAD_MAX_ENVS) ? 4 : 1);
     const float2* act = reinterpret_cast<const float2*>(d_action);
     cudaStream_t cs = (cudaStream_t)stream;
-    const uint32_t t = (uint32_t)step_counter;
+    const uint32_t t = (uint32_t)step_counter;               // negative (device base + k) stays encoded: see decode_step
+    if (int rc = prep_step(sim, step_counter, 1, cs)) return rc;
     const bool elev = sim->cfg.task == WL_TASK_ELEVATION, vis = sim->cfg.task == WL_TASK_VISUAL;
     if (variant == 4) {
 #ifndef WL_QUAD_BS
@@ -1273,14 +1357,10 @@ int wl_step(wl_sim* sim, const float* d_action, float* d_obs, float* d_rew, uint
         else if (vis) wl_step_kernel<WL_TASK_VISUAL><<<grid, bs, 0, cs>>>(sim->cfg, sim->state, sim->globals, T, act, d_obs, d_rew, d_terminated, d_truncated, d_log, t);
         else wl_step_kernel<WL_TASK_DRIFT><<<grid, bs, 0, cs>>>(sim->cfg, sim->state, sim->globals, T, act, d_obs, d_rew, d_terminated, d_truncated, d_log, t);
     }
-    if (elev) {
-        WL_LAUNCH_CHECK(sim, "wl_step_kernel");
-        if (int rc = launch_scan(sim, d_obs, cs)) return rc;
-        return WL_OK;
-    }
     WL_LAUNCH_CHECK(sim, "wl_step_kernel");
-    if (vis && sim->cfg.vis_cam) return launch_camera(sim, d_obs, t, RNG_CAM, 0u, nullptr, cs);   // t may be WL_DEVICE_COUNTER
-    return WL_OK;
+    if (elev) { if (int rc = launch_scan(sim, d_obs, cs)) return rc; }
+    if (vis && sim->cfg.vis_cam) { if (int rc = launch_camera(sim, d_obs, t, RNG_CAM, 0u, nullptr, cs)) return rc; }   // t may be device-relative
+    return post_step(sim, step_counter, cs);
 }
 
 // ---- env.step cut in two (host-side reward / termination terms run in between) ----------------------------------------
@@ -1309,6 +1389,11 @@ int wl_step_stage_a(wl_sim* sim, const float* d_action, float* d_rew, uint8_t* d
     if (!sim || !d_action || !d_rew || !d_term_bits) return fail(WL_EINVAL, "wl_step_stage_a: null argument");
     if ((uintptr_t)d_action & 7u) return fail(WL_EINVAL, "wl_step_stage_a: action must be 8-byte aligned");
     if (step_counter < 0) return fail(WL_EINVAL, "wl_step_stage_a: the staged step takes the host's step counter");
+    {   // stage a reads W(t) like a full step: re-arm on a counter jump, but the step is only committed by stage b
+        const int64_t keep = sim->last_t;
+        if (int rc = prep_step(sim, step_counter, 1, (cudaStream_t)stream)) return rc;
+        sim->last_t = (keep == step_counter - 1) ? keep : step_counter - 1;
+    }
     return launch_stage<1>(sim, reinterpret_cast<const float2*>(d_action), nullptr, d_rew, nullptr, nullptr, nullptr, (uint32_t)step_counter,
                            StageIO{d_term_bits, nullptr, nullptr}, (cudaStream_t)stream);
 }
@@ -1317,13 +1402,14 @@ int wl_step_stage_b(wl_sim* sim, const uint8_t* d_term_bits, const uint8_t* d_ex
                     float* d_obs, uint8_t* d_terminated, uint8_t* d_truncated, float* d_log, int64_t step_counter, void* stream) {
     if (!sim || !d_term_bits || !d_obs || !d_terminated || !d_truncated) return fail(WL_EINVAL, "wl_step_stage_b: null argument");
     if (step_counter < 0) return fail(WL_EINVAL, "wl_step_stage_b: the staged step takes the host's step counter");
+    if (int rc = prep_step(sim, step_counter, 1, (cudaStream_t)stream)) return rc;
     if (int rc = launch_stage<2>(sim, nullptr, d_obs, nullptr, d_terminated, d_truncated, d_log, (uint32_t)step_counter,
                                  StageIO{const_cast<uint8_t*>(d_term_bits), d_extra_terminated, d_extra_truncated}, (cudaStream_t)stream))
         return rc;
-    if (sim->cfg.task == WL_TASK_ELEVATION) return launch_scan(sim, d_obs, (cudaStream_t)stream);
+    if (sim->cfg.task == WL_TASK_ELEVATION) { if (int rc = launch_scan(sim, d_obs, (cudaStream_t)stream)) return rc; }
     if (sim->cfg.task == WL_TASK_VISUAL && sim->cfg.vis_cam)
-        return launch_camera(sim, d_obs, (uint32_t)step_counter, RNG_CAM, 0u, nullptr, (cudaStream_t)stream);
-    return WL_OK;
+        if (int rc = launch_camera(sim, d_obs, (uint32_t)step_counter, RNG_CAM, 0u, nullptr, (cudaStream_t)stream)) return rc;
+    return post_step(sim, step_counter, (cudaStream_t)stream);
 }
 
 int wl_rollout(wl_sim* sim, int32_t K, const float* d_actions, float* d_actions_out, float* d_obs, float* d_rew,
@@ -1344,14 +1430,15 @@ int wl_rollout(wl_sim* sim, int32_t K, const float* d_actions, float* d_actions_
     const int bs = 32, threads = 4 * n, grid = (threads + bs - 1) / bs;
     cudaStream_t cs = (cudaStream_t)stream;
     if (int rc = cuda_check(cudaMemsetAsync(d_log, 0, (size_t)K * WL_LOG_FLOATS * sizeof(float), cs), "wl_rollout: clear log rows")) return rc;
+    if (int rc = prep_step(sim, step_counter, K, cs)) return rc;
     const float2* act = reinterpret_cast<const float2*>(d_actions);
     float2* aout = reinterpret_cast<float2*>(d_actions_out);
     if (sim->cfg.task == WL_TASK_VISUAL)
-        wl_rollout_quad_kernel<WL_TASK_VISUAL><<<grid, bs, 0, cs>>>(sim->cfg, sim->state, sim->globals, T, act, aout, d_obs, d_rew, d_terminated, d_truncated, d_log, (uint32_t)step_counter, K);
+        wl_rollout_quad_kernel<WL_TASK_VISUAL><<<grid, bs, 0, cs>>>(sim->cfg, sim->state, sim->globals, T, act, aout, d_obs, d_rew, d_terminated, d_truncated, d_log, (uint32_t)step_counter, K, &sim->globals->ticket);
     else
-        wl_rollout_quad_kernel<WL_TASK_DRIFT><<<grid, bs, 0, cs>>>(sim->cfg, sim->state, sim->globals, T, act, aout, d_obs, d_rew, d_terminated, d_truncated, d_log, (uint32_t)step_counter, K);
+        wl_rollout_quad_kernel<WL_TASK_DRIFT><<<grid, bs, 0, cs>>>(sim->cfg, sim->state, sim->globals, T, act, aout, d_obs, d_rew, d_terminated, d_truncated, d_log, (uint32_t)step_counter, K, &sim->globals->ticket);
     WL_LAUNCH_CHECK(sim, "wl_rollout_quad_kernel");
-    return WL_OK;
+    return post_step(sim, step_counter, cs);
 }
 
 size_t wl_result_bytes(int32_t num_envs) { return (size_t)num_envs * 6u; }
@@ -1414,6 +1501,8 @@ int wl_curriculum(wl_sim* sim, int32_t n_terms, const int32_t* slots, const floa
     if (n_terms == 0 || fire_mask == 0) return WL_OK;
     CurrArgs a; memset(&a, 0, sizeof a);
     a.n = n_terms; a.fire_mask = fire_mask;
+    if (sim->last_t < 0) return WL_OK;                       // no step yet: no env has reset
+    a.wslot = (uint32_t)sim->last_t & 1u; a.row = (uint32_t)sim->last_t % 3u;
     for (int t = 0; t < n_terms; ++t) {
         if (slots[t] < 0 || slots[t] >= WL_MAX_REW_TERMS) return fail(WL_EINVAL, "wl_curriculum: slot out of range");
         a.slots[t] = slots[t]; a.inc[t] = increases[t];
@@ -1465,6 +1554,7 @@ int wl_act_step(wl_sim* sim, const float* d_obs_in, const float* d_policy_blob, 
     const size_t smem = sizeof(float) * ((size_t)blob_floats + WL_ACT_ENVS * (WL_ACT_XS + WL_ACT_HS));
     Terrain T{sim->hf};
     cudaStream_t cs = (cudaStream_t)stream;
+    if (int rc = prep_step(sim, step_counter, 1, cs)) return rc;
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(wl_act_step_quad_kernel<WL_TASK_VISUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
@@ -1476,7 +1566,7 @@ int wl_act_step(wl_sim* sim, const float* d_obs_in, const float* d_policy_blob, 
     else
         wl_act_step_quad_kernel<WL_TASK_DRIFT><<<grid, WL_ACT_THREADS, smem, cs>>>(sim->cfg, sim->state, sim->globals, T, d_obs_in, d_policy_blob, blob_floats, po, out, d_obs, d_rew, d_terminated, d_truncated, d_log, (uint32_t)step_counter, sim->obs_dim);
     WL_LAUNCH_CHECK(sim, "wl_act_step_quad_kernel");
-    return WL_OK;
+    return post_step(sim, step_counter, cs);
 }
 
 int wl_gae(const float* d_rewards, const float* d_values, const float* d_last_values, const uint8_t* d_dones,

@@ -18,7 +18,11 @@ def shard_offset(rank: int, envs_per_rank: int) -> int:
 
 
 class RolloutSlab:
-    """Per-rank rollout buffer in the layout the learner consumes: obs [T,N,D] f32, actions [T,N,A] f32,
+    """Per-rank rollout buffer in the layout the learner consumes.  Observations are ONE [T+1,N,D] block: ``obs_in[k]`` (rows
+    0..T-1) is the observation the policy saw when it produced ``actions[k]`` -- rsl_rl RolloutStorage.observations[k] --
+    and ``obs[k]`` (rows 1..T) is what env.step k returned, so ``obs[k] is obs_in[k+1]`` and ``obs[T-1]`` is the
+    bootstrap observation (``obs_in[0]`` must be filled with the rollout's first observation by the caller).
+    Other fields: actions [T,N,A] f32,
     rewards [T,N] f32, terminated / truncated [T,N] u8 and -- with ``policy_fields`` -- what alg.act() records per step
     (rsl_rl RolloutStorage: values [T,N], actions_log_prob [T,N], action_mean [T,N,A]; written by wl_act_step).  Fields are
     views of ONE flat byte buffer, so ONE all_gather_into_tensor moves the whole slab."""
@@ -34,7 +38,7 @@ class RolloutSlab:
         f = T * n_local
         self._sizes = {}
         for k, (dt, tail) in self._fields.items():
-            n_el = f
+            n_el = f if k != "obs" else (T + 1) * n_local
             for d in tail:
                 n_el *= d
             self._sizes[k] = n_el * (4 if dt == torch.float32 else 1)
@@ -44,7 +48,11 @@ class RolloutSlab:
         for k, nbytes in self._sizes.items():
             dt, tail = self._fields[k]
             raw = self.flat[off: off + nbytes]
-            setattr(self, k, (raw.view(torch.float32) if dt == torch.float32 else raw).view(T, n_local, *tail))
+            if k == "obs":
+                self.obs_all = raw.view(torch.float32).view(T + 1, n_local, *tail)
+                self.obs_in, self.obs = self.obs_all[:T], self.obs_all[1:]
+            else:
+                setattr(self, k, (raw.view(torch.float32) if dt == torch.float32 else raw).view(T, n_local, *tail))
             off += (nbytes + 255) // 256 * 256
 
     @property
@@ -79,6 +87,14 @@ class GatheredRollout:
 
     def field(self, name: str) -> torch.Tensor:
         p = self.p
+        if name == "obs_in":
+            off = 0
+            for k, nbytes in p._sizes.items():
+                if k == "obs":
+                    break
+                off += (nbytes + 255) // 256 * 256
+            raw = self.buf[:, off: off + p._sizes["obs"]]
+            return raw.view(torch.float32).view(self.buf.shape[0], p.T + 1, p.n, p.obs_dim)[:, :p.T]
         off = 0
         for k, nbytes in p._sizes.items():
             if k == name:
@@ -88,6 +104,8 @@ class GatheredRollout:
         else:
             raise KeyError(name)
         dt, tail = p._fields[name]
+        if name == "obs":                          # rows 1..T of the [T+1] block (see RolloutSlab); "obs_in" = rows 0..T-1
+            return raw.view(torch.float32).view(self.buf.shape[0], p.T + 1, p.n, *tail)[:, 1:]
         return (raw.view(torch.float32) if dt == torch.float32 else raw).view(self.buf.shape[0], p.T, p.n, *tail)
 
     def cat(self, name: str) -> torch.Tensor:

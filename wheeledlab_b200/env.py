@@ -28,26 +28,39 @@ class _Box:
 
 
 class _LazyLog(dict):
-    """extras["log"]: keys are known up front, values are 0-dim views of the device row the step kernel's last CTA
-    wrote; the views are only created when somebody reads them (the train loop appends the dict every step and reads it
-    once per iteration, modified_rsl_rl_runner.py:95-98)."""
+    """extras["log"]: keys are known up front, values are 0-dim views of the device row of that step; the views are only
+    created when somebody reads them (the train loop appends the dict every step and reads it once per iteration,
+    modified_rsl_rl_runner.py:95-98).  The row of step t is written by the next launch on the handle (no grid-wide sync in
+    the step): reading the log of the most recent step publishes it first (wl_log_flush, a 32-thread kernel)."""
 
-    def __init__(self, row: torch.Tensor, index: dict, extra: dict | None = None):
+    def __init__(self, row: torch.Tensor, index: dict, extra: dict | None = None, env=None):
         super().__init__((k, None) for k in index)
         self._row, self._index = row, index
+        self._env, self._step = env, (env.common_step_counter if env is not None else None)
         self._extra = extra or {}                # entries of host-side (Python) terms: already 0-dim device tensors
         for k in self._extra:
             dict.__setitem__(self, k, None)
 
+    def _ready(self):
+        # the row of step t is written by the next launch on the handle: if this is still the most recent step, flush now
+        env = self._env
+        if env is not None and env.common_step_counter == self._step:
+            env.sim.flush_log()
+        self._env = None
+
     def __getitem__(self, k):
         if k in self._extra:
             return self._extra[k]
+        if self._env is not None:
+            self._ready()
         return self._row[self._index[k]]
 
     def get(self, k, default=None):
         if k in self._extra:
             return self._extra[k]
-        return self._row[self._index[k]] if k in self._index else default
+        if k not in self._index:
+            return default
+        return self[k]
 
     def items(self):
         return [(k, self[k]) for k in list(self._index) + list(self._extra)]
@@ -413,7 +426,7 @@ class ManagerBasedRLEnv:
                 sums.masked_fill_(done, 0.0)
             for term in self._py_terms:
                 extra["Episode_Termination/" + term.name] = (fired[term.name] & done).sum()
-            self.extras["log"] = _LazyLog(log, self._log_index, extra)
+            self.extras["log"] = _LazyLog(log, self._log_index, extra, env=self)
         return {"policy": self._append_py_obs(obs)}, rew, terminated, truncated, self.extras
 
     def step(self, action: torch.Tensor):
@@ -448,7 +461,7 @@ class ManagerBasedRLEnv:
     def _episode_log(self, log: torch.Tensor):
         """extras["log"] (RewardManager/TerminationManager.reset): lazy views of the row the step
         kernel's last CTA wrote -- device tensors, no extra launches, no host sync."""
-        return _LazyLog(log, self._log_index)
+        return _LazyLog(log, self._log_index, env=self)
 
     def step_host(self, action_host: torch.Tensor):
         """env.step() for a HOST-side caller: `action_host` is a CPU tensor [N,2] (pinned for best speed).  One C call
@@ -513,7 +526,8 @@ class ManagerBasedRLEnv:
         tm = self.termination_manager
         tm.terminated, tm.time_outs = io["terminated"], io["truncated"]
         if log is not None:
-            self.extras["log"] = lazy                    # one lazy view per ring slot (its row tensor never changes)
+            lazy._env, lazy._step = self, t + 1          # one lazy view per ring slot (its row tensor never changes)
+            self.extras["log"] = lazy
         return {"policy": obs}, io["rew"], io["terminated"], io["truncated"], self.extras
 
     @property

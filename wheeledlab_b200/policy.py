@@ -85,17 +85,19 @@ class FusedPolicyRollout:
         self.pol = (SimpleNamespace(values=self.slab.values, log_prob=self.slab.log_prob, mean=self.slab.mean)
                     if hasattr(self.slab, "values") else PolicyBuffers(T, sim.num_envs, sim.device))
         self.logs = torch.zeros((T, 16), dtype=torch.float32, device=sim.device)
-        self.obs0 = torch.empty((sim.num_envs, sim.obs_dim), dtype=torch.float32, device=sim.device)
+        # slab.obs_in[k] = the observation actions[k] / log_prob[k] / values[k] / mean[k] were computed from (rsl_rl
+        # RolloutStorage.observations[k]); slab.obs[k] = obs_in[k+1] = what step k returned
+        self.obs0 = self.slab.obs_in[0]
         self.graph = None
+        self._base = 0
         self._stream = torch.cuda.Stream(device=sim.device)
 
     def _body(self):
-        obs = self.obs0
         for k in range(self.T):
-            act_step(self.sim, obs, self.blob, self.slab.actions[k], self.pol.mean[k], self.pol.log_prob[k], self.pol.values[k],
-                     self.slab.step_outputs(k), self.logs[k], WheeledSim.DEVICE_COUNTER)
-            obs = self.slab.obs[k]
-        self.obs0.copy_(obs)
+            act_step(self.sim, self.slab.obs_in[k], self.blob, self.slab.actions[k], self.pol.mean[k], self.pol.log_prob[k],
+                     self.pol.values[k], self.slab.step_outputs(k), self.logs[k], WheeledSim.device_counter_plus(k))
+        self.sim.advance_counter(self.T)
+        self.obs0.copy_(self.slab.obs[self.T - 1])
 
     def capture(self, step_counter: int):
         sim = self.sim
@@ -108,8 +110,12 @@ class FusedPolicyRollout:
             with torch.cuda.graph(self.graph, stream=s):
                 self._body()
         torch.cuda.current_stream(sim.device).wait_stream(s)
+        sim.set_step_counter(step_counter)       # (the captured advance_counter moved the HOST mirror; put both back)
+        self._base = step_counter
         return self
 
     def run(self) -> RolloutSlab:
         self.graph.replay()
+        self._base += self.T
+        self.sim.note_device_counter(self._base)
         return self.slab

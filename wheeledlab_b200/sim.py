@@ -62,7 +62,6 @@ class WheeledSim:
         self.groups = self._buf[: NUM_GROUPS * n * 4].view(NUM_GROUPS, n, 4)
         goff = lib.wl_globals_offset(n) // 4
         self._globals = self._buf[goff: goff + C.sizeof(_lib.WlGlobals) // 4]
-        self.rew_weight = self._globals[0:8]
         self.obs_dim = int(lib.wl_obs_dim(self._h))
 
     # -- lifetime ------------------------------------------------------------------
@@ -103,8 +102,10 @@ class WheeledSim:
 
     def step(self, action: torch.Tensor, step_counter: int = -1, out=None, log: torch.Tensor | None = None):
         """action [N,2] f32 (device, contiguous) -> (obs [N,D] f32, rew [N] f32, terminated [N] u8, truncated [N] u8).
-        `step_counter` = common_step_counter before the step, or DEVICE_COUNTER (-1): use and advance the counter kept on
-        the device (CUDA-graph replayable).  `log`: optional float32[16] device tensor receiving the episode log row."""
+        `step_counter` = common_step_counter before the step, or device_counter_plus(k): the counter base kept on the device
+        + k (CUDA-graph replayable: capture K steps k = 0..K-1, then advance_counter(K)).  Steps are issued with consecutive
+        counters (a jump re-arms the episode log).  `log`: optional float32[16] device tensor receiving the episode-log row;
+        it is written by the NEXT launch on this handle (the next step or flush_log())."""
         n = self.num_envs
         if out is None:
             obs = torch.empty((n, self.obs_dim), dtype=torch.float32, device=self.device)
