@@ -1,26 +1,35 @@
 #!/usr/bin/env python
 """bench.py -- env-steps/s of the fused WheeledLab step (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--envs E] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload drift|elev|hound4wd] [--envs E] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-One "step" = one env.step() of the RSS_DRIFT_CONFIG workload (MushrDriftRL: dt 5 ms x 4, DR + pushes +
-obs noise on, auto-reset) over E envs per GPU (default 4096 = BASELINE configs[1]) with synthetic
-U[-1,1]^2 actions from the counter-based generator.  Rank 0 prints ONE JSON line.
+One "step" = one env.step() of the workload over E envs per GPU with synthetic U[-1,1]^2 actions from the counter-based
+generator.  Workloads (BASELINE.json configs):
+    drift     configs[1]  RSS_DRIFT_CONFIG  MushrDriftRL, 4096 envs, dt 5 ms x 4, DR + pushes + obs noise  (the headline metric)
+    elev      configs[2]  RSS_ELEV_CONFIG   MushrElevationRL, 4096 envs, height-field terrain + 676-ray height scan
+    hound4wd  configs[3]  "HOUND 4WD"       MuSHR + HOUND_SUS_ACTUATOR_CFG (4 driven wheels) + Mushr4WDActionCfg, 8192 envs
+(configs[4] = drift at --gpus 8; configs[0] is the reference's CPU plumbing case, a parity-test size.)  Rank 0 prints ONE JSON line.
 
-  value     whole-job env-steps/s, inputs resident in HBM, L2 flushed between timed steps, per-step CUDA
-            events on the launch stream, max over ranks.
-  e2e       same metric through the public ManagerBasedRLEnv.step() with HOST (pinned) action buffers:
-            H2D of the actions and D2H of reward + done masks inside the timed region, every step.
-  roofline  algorithmic bytes of the step kernel / its measured duration vs the measured HBM peak.
+  value     whole-job env-steps/s, inputs resident in HBM.  Timed region = EXACTLY K steps issued back to back between two
+            CUDA events (barrier + synchronize on both sides), max over ranks.  Cold caches WITHOUT a flush kernel: the
+            working set is larger than L2 -- M independent env sets (state + parameters) are stepped round-robin and every
+            step writes a fresh rollout-slab row, so no step finds its inputs in L2 (`config.l2`).  With N > 1 the timed
+            region contains the all-gather of the rollout slab every T_ROLL steps (overlapped with the next steps).
+  flush_protocol  the round-1 protocol kept for comparison: per-step events with a 256 MiB L2-flush fill between steps, and
+            the same measurement around an EMPTY kernel (the floor of that protocol: ~6 us on B200).
+  e2e       same metric through the public ManagerBasedRLEnv.step_host() with HOST (pinned) buffers: H2D of the actions and
+            D2H of observations + reward + done masks inside the timed region, every step, stream-synchronised.
+  roofline  algorithmic bytes of the step kernel(s) / average step duration in the timed region vs the measured HBM peak.
   cpu_baseline  the CPU oracle (oracle/wl_oracle.c, "port") timed on this box's host cores.
---impl reference times that same CPU implementation (all host threads) as the reference arm: the
-reference's own PhysX pipeline is a closed binary that is not in /root/reference.
+--impl reference times that same CPU implementation (all physical cores) as the reference arm: the reference's own PhysX
+pipeline is a closed binary that is not in /root/reference.  It does not import the product package.
 """
 from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -34,9 +43,22 @@ sys.path.insert(0, str(ROOT))
 
 METRIC = "env_steps_per_sec"
 UNIT = "env-steps/s"
-# algorithmic bytes per env-step of the Drift step kernel (DESIGN.md "Kernels"):
-# reads 13 state/param groups x16 B + action 8 B; writes 9 state groups x16 B + obs 56 + rew 4 + 2 masks
+# algorithmic bytes per env-step (DESIGN.md "Kernels"):
+#   drift / hound4wd: reads 13 state+param groups x16 B + action 8 B; writes 9 state groups x16 B + obs 56 + rew 4 + 2 masks
+#   elev: reads 15 groups + action; writes 11 groups + the 689-float observation row + rew + masks
 BYTES_PER_ENV_STEP = (13 * 16 + 8) + (9 * 16 + 56 + 4 + 2)
+WORKLOADS = {
+    "drift": {"task": "drift", "envs": 4096, "bytes": BYTES_PER_ENV_STEP, "obs_dim": 14, "blob": "drift.bin",
+              "label": "RSS_DRIFT_CONFIG MushrDriftRL, dt 5ms x4, DR+push+noise on", "kernel": "wl_step_quad_kernel<DRIFT>",
+              "traffic_profile": "profiles/r02_ncu_step_drift_4096.txt"},
+    "elev": {"task": "elevation", "envs": 4096, "bytes": (15 * 16 + 8) + (11 * 16 + 689 * 4 + 4 + 2), "obs_dim": 689, "blob": "elevation.bin",
+             "label": "RSS_ELEV_CONFIG MushrElevationRL, dt 10ms x10 (5 ms sub-steps), reference terrain raster + 676-ray height scan",
+             "kernel": "wl_step_quad_kernel<ELEVATION> + wl_scan_kernel<TMA>", "traffic_profile": "profiles/r02_ncu_step_elev_4096.txt"},
+    "hound4wd": {"task": "hound_4wd", "envs": 8192, "bytes": BYTES_PER_ENV_STEP, "obs_dim": 14, "blob": "hound_4wd.bin",
+                 "label": "HOUND 4WD: MuSHR + HOUND_SUS_ACTUATOR_CFG (4 driven wheels) + Mushr4WDActionCfg, mass/friction DR, dt 5ms x4",
+                 "kernel": "wl_step_quad_kernel<DRIFT> (4WD action map)", "traffic_profile": "profiles/r02_ncu_step_hound_8192.txt"},
+}
+L2_BYTES = 126 * 1024 * 1024
 
 
 def _peaks():
@@ -47,6 +69,20 @@ def _peaks():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def _traffic(path):
+    """dram bytes per launch recorded in the committed `ncu --set full` summary of this workload (or None)."""
+    p = ROOT / path
+    if not p.exists():
+        return None
+    tot = 0.0
+    for line in p.read_text().splitlines():
+        for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            if line.strip().startswith(key + " ="):
+                val, unit = line.split("=")[1].split()[:2]
+                tot += float(val) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
+    return tot or None
 
 
 class ClockSampler:
@@ -98,78 +134,101 @@ class ClockSampler:
         return out
 
 
-def _oracle(spec, native=True, threads=1):
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU side (the oracle): test infrastructure used here as the reported CPU baseline / reference arm only
+# ---------------------------------------------------------------------------------------------------------------------
+def _physical_cores() -> int:
+    """Physical cores this process may run on (SMT siblings counted once)."""
+    try:
+        allowed = os.sched_getaffinity(0)
+    except Exception:
+        allowed = set(range(os.cpu_count() or 1))
+    cores = set()
+    try:
+        for cpu in allowed:
+            base = Path(f"/sys/devices/system/cpu/cpu{cpu}/topology")
+            cores.add((base.joinpath("physical_package_id").read_text().strip(), base.joinpath("core_id").read_text().strip()))
+    except Exception:
+        return max(1, len(allowed) // 2)
+    return max(1, len(cores))
+
+
+def _cpu_oracle(workload: str, envs: int, seed: int, threads: int):
+    """The oracle on `envs` envs of the workload, built from the committed config blob (no product import)."""
+    os.environ.setdefault("OMP_PROC_BIND", "close")
+    os.environ.setdefault("OMP_PLACES", "cores")
     sys.path.insert(0, str(ROOT / "tests"))
-    from oracle_lib import Oracle
-    return Oracle(spec.cfg, kind="native" if native else "f32", threads=threads)
-
-
-def _best_threads(spec, probe_s: float = 0.4) -> int:
-    """The box's cores may be shared/limited: probe a few OpenMP widths and keep the fastest."""
-    ncpu = os.cpu_count() or 1
-    cands = sorted({1, 2, 4, 8, 16, 32, 64, ncpu} & set(range(1, ncpu + 1)) | {ncpu})
-    best, best_rate = 1, 0.0
-    for th in cands:
-        orc = _oracle(spec, native=True, threads=th)
-        orc.startup(); orc.reset(None, 0)
-        a = orc.synth_actions(0)
-        orc.step(a, 0)
-        t0 = time.perf_counter(); k = 0
-        while time.perf_counter() - t0 < probe_s:
-            orc.step(a, 1 + k); k += 1
-        rate = k / (time.perf_counter() - t0)
-        if rate > best_rate:
-            best, best_rate = th, rate
-    return best
-
-
-def cpu_baseline(envs: int, seed: int, budget_s: float = 12.0, threads: int | None = None):
-    """Time the CPU oracle on a bounded sample: `envs` envs, as many steps as fit in ~budget_s."""
-    import wheeledlab_b200 as wl
-    spec = wl.drift_task(num_envs=envs, seed=seed)
-    threads = threads or _best_threads(spec)
-    orc = _oracle(spec, native=True, threads=threads)
+    import numpy as np
+    import oracle_lib as O
+    w = WORKLOADS[workload]
+    O.get_lib("native")                                        # -O3 -march=native build (made on this box)
+    cfg = O.cfg_from_blob(ROOT / "tests" / "golden" / "cfg_blobs" / w["blob"], num_envs=envs, seed=seed, env_id_offset=0)
+    hf = None
+    if w["task"] == "elevation":                               # the shipped raster of the reference's terrain mesh, padded like the product does
+        d = np.load(ROOT / "wheeledlab_b200" / "data" / "terrain_huge_compact_0p1m.npz")
+        h = d["heights"].astype(np.float32)
+        pitch = (h.shape[1] + 3) & ~3
+        hf = np.zeros((h.shape[0], pitch), np.float32); hf[:, :h.shape[1]] = h
+        if pitch > h.shape[1]:
+            hf[:, h.shape[1]:] = h[:, -1:]
+    orc = O.Oracle(cfg, heightfield=hf, kind="native", threads=threads)
     orc.startup(); orc.reset(None, 0)
+    return orc
+
+
+def _time_oracle(orc, warm: int, min_steps: int, min_s: float, max_s: float):
     acts = [orc.synth_actions(t) for t in range(8)]
-    for t in range(3):
+    for t in range(warm):
         orc.step(acts[t % 8], t)
     t0 = time.perf_counter(); steps = 0
     while True:
-        orc.step(acts[steps % 8], 3 + steps); steps += 1
+        orc.step(acts[steps % 8], warm + steps); steps += 1
         el = time.perf_counter() - t0
-        if el > budget_s or steps >= 2000:
+        if (steps >= min_steps and el >= min_s) or el > max_s:
             break
+    return steps, el
+
+
+def cpu_baseline(workload: str, envs: int, seed: int, budget_s: float = 12.0):
+    """Time the CPU oracle on a bounded sample: `envs` envs, as many steps as fit in ~budget_s, all physical cores."""
+    threads = _physical_cores()
+    orc = _cpu_oracle(workload, envs, seed, threads)
+    steps, el = _time_oracle(orc, 3, 20, budget_s, budget_s)
     return {"value": envs * steps / el, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"{envs} envs x {steps} env-steps of RSS_DRIFT (oracle/wl_oracle.c -O3 -march=native, OpenMP {threads} threads), {el:.1f} s"}
+            "sample": f"{envs} envs x {steps} env-steps of {workload} (oracle/wl_oracle.c -O3 -march=native, OpenMP {threads} threads = physical cores, "
+                      f"OMP_PROC_BIND=close), {el:.1f} s"}
 
 
 def run_reference(args):
-    """Reference arm: the CPU implementation of the path on this box's host cores (rank 0 only)."""
+    """Reference arm: the CPU implementation of the path on this box's host cores (rank 0 only), same workload and the same
+    GLOBAL env count as the GPU arm at this N."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import wheeledlab_b200 as wl
-    envs = args.envs
-    spec = wl.drift_task(num_envs=envs, seed=args.seed)
-    threads = _best_threads(spec)        # "all the host threads it can use": widest setting that actually scales
-    orc = _oracle(spec, native=True, threads=threads)
-    orc.startup(); orc.reset(None, 0)
+    w = WORKLOADS[args.workload]
+    envs = (args.envs or w["envs"]) * max(1, args.gpus)
+    threads = _physical_cores()
+    orc = _cpu_oracle(args.workload, envs, args.seed, threads)
+    # one reference "step" = `reps` consecutive env.steps (a bounded sample sized so that K steps take >= ~1 s in total)
+    probe_steps, probe_el = _time_oracle(orc, args.warmup, 5, 0.2, 2.0)
+    per = probe_el / probe_steps
+    reps = max(1, math.ceil(1.0 / (per * args.steps)))
     acts = [orc.synth_actions(t) for t in range(8)]
-    for t in range(args.warmup):
-        orc.step(acts[t % 8], t)
+    t = args.warmup + probe_steps
     t0 = time.perf_counter()
-    for k in range(args.steps):
-        orc.step(acts[k % 8], args.warmup + k)
+    for k in range(args.steps * reps):
+        orc.step(acts[k % 8], t + k)
     el = time.perf_counter() - t0
-    val = envs * args.steps / el
+    val = envs * args.steps * reps / el
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": 1e3 * el / (args.steps * reps), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"RSS_DRIFT_CONFIG {envs} envs (CPU, one box)", "envs_per_step": envs,
-                   "note": "PhysX is not runnable here; this is the CPU restatement of the same step"},
+        "config": {"workload": f"{w['label']}: {envs} envs (CPU, one box)", "envs_per_step": envs, "same_config": True,
+                   "note": "PhysX is not runnable here; this is the CPU restatement of the same step (oracle/wl_oracle.c)"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{envs} envs x {args.steps} env-steps, OpenMP {threads} of {os.cpu_count()} threads (best of a width probe)"},
+                         "sample": f"{envs} envs x {args.steps} steps x {reps} env-steps each, OpenMP {threads} threads = physical cores of "
+                                   f"{os.cpu_count()} logical, OMP_PROC_BIND=close, {el:.2f} s timed"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -194,6 +253,8 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     import wheeledlab_b200 as wl
+    from wheeledlab_b200.distributed import RolloutSlab
+    from wheeledlab_b200.sim import _stream_ptr
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -207,18 +268,9 @@ def run_ours(args):
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # NCCL's version/warn lines must not pollute the ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device(dev))
 
-    E, K, W = args.envs, args.steps, args.warmup
-    spec = wl.drift_task(num_envs=E, seed=args.seed, env_id_offset=rank * E)
-    sim = wl.WheeledSim(spec, dev)
-    sim.startup(); sim.reset(None, 0)
-    from wheeledlab_b200.distributed import RolloutSlab
-    T_ROLL = 128                                                                  # rsl_rl num_steps_per_env (rsl_rl_ppo_cfg.py:6)
-    acts = torch.stack([sim.synth_actions(t) for t in range(W + K)])           # resident in HBM
-    slabs = [RolloutSlab(T_ROLL, E, sim.obs_dim, 2, dev) for _ in range(2 if world > 1 else 1)]   # the step writes straight into
-    slab = slabs[0]                                                               # the send buffer; two of them so that the
-    outs = slab.step_outputs(0)                                                   # gather of iteration i overlaps rollout i+1
-    sim.step(acts[0], 0, out=outs)
-    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # 256 MiB > 126 MB L2
+    w = WORKLOADS[args.workload]
+    E, K, W = args.envs or w["envs"], args.steps, args.warmup
+    mk = lambda seed_off=0: wl.make_task(w["task"], num_envs=E, seed=args.seed + seed_off, env_id_offset=rank * E)
     peak, peak_src = _peaks()
 
     def barrier():
@@ -233,231 +285,257 @@ def run_ours(args):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         return float(tt.item())
 
-    # ---- device-resident timing: per-step events around the step launch, L2 flushed between steps ----
-    t = 1
-    for _ in range(W):
-        sim.step(acts[t % (W + K)], t, out=outs); flush.fill_(0.0); t += 1
-    if world > 1:                                       # untimed: NCCL communicator / channel set-up, receive buffers
-        for _ in range(2):
-            for sl in slabs:
-                sl.all_gather()
+    # ---- M independent env sets: the working set (state + parameters) exceeds L2, so round-robin stepping is cold ----
+    sim0 = wl.WheeledSim(mk(), dev)
+    set_bytes = sim0._buf.numel() * 4
+    M = max(4, math.ceil(2.2 * L2_BYTES / set_bytes))
+    sims = [sim0] + [wl.WheeledSim(mk(1000 * m), dev) for m in range(1, M)]
+    for s in sims:
+        s.startup(); s.reset(None, 0)
+    T_ROLL = min(128, max(4, K // 2))                         # rsl_rl num_steps_per_env is 128 (rsl_rl_ppo_cfg.py:6); shortened so
+    n_slabs = 2                                               # that the driver's short runs still time >= 1 all-gather
+    slabs = [RolloutSlab(T_ROLL, E, sim0.obs_dim, 2, dev) for _ in range(n_slabs)]
+    acts = torch.stack([sim0.synth_actions(t) for t in range(max(8, min(W + K, 64)))])   # resident in HBM
+    NA = acts.shape[0]
+    tcount = [0] * M
+
+    def make_bound(k):                                        # step k: env set k % M, slab row k % T_ROLL of slab (k // T_ROLL) % 2
+        return sims[k % M].bind_step(acts[k % NA], slabs[(k // T_ROLL) % n_slabs].step_outputs(k % T_ROLL))
+
+    bound_w = [make_bound(k) for k in range(W)]
+    bound = [make_bound(W + k) for k in range(K)]
+    gstream = torch.cuda.Stream(device=dev) if world > 1 else None
+    main = torch.cuda.current_stream()
+
+    def run_steps(fns, k0, timed):
+        """Issue the steps back to back; with N > 1, ONE all-gather of the filled slab per T_ROLL steps on its own stream
+        (it overlaps the next steps; the step stream only waits when a slab is about to be refilled before its gather is done)."""
+        gev, gdone = [], [None] * n_slabs
+        for j, fn in enumerate(fns):
+            k = k0 + j
+            row, cur = k % T_ROLL, (k // T_ROLL) % n_slabs
+            if world > 1 and row == 0 and gdone[cur] is not None:
+                main.wait_event(gdone[cur])
+            m = k % M
+            fn(tcount[m]); tcount[m] += 1
+            if world > 1 and row == T_ROLL - 1:
+                filled = torch.cuda.Event(); filled.record()
+                with torch.cuda.stream(gstream):
+                    gstream.wait_event(filled)
+                    g0, g1 = torch.cuda.Event(enable_timing=timed), torch.cuda.Event(enable_timing=timed)
+                    g0.record(); slabs[cur].all_gather(); g1.record(); gev.append((g0, g1))
+                    gdone[cur] = g1
+        for g in gdone:                                       # the last gathers must be finished before the clock stops
+            if g is not None:
+                main.wait_event(g)
+        return gev
+
+    if world > 1:                                             # untimed: NCCL communicator / channel set-up, receive buffers
+        for sl in slabs:
+            sl.all_gather()
+    run_steps(bound_w, 0, False)
     sampler = ClockSampler(list(range(world)) if world > 1 else local)
     barrier()
     if rank == 0:
         sampler.start()
-    l0 = sim.launch_count
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    l0 = sum(s.launch_count for s in sims)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
-    gev, wev, gathered = [], [], None
-    gstream = torch.cuda.Stream(device=dev) if world > 1 else None
-    gdone = [None] * len(slabs)                         # per slab: event after which its rows may be overwritten again
-    main = torch.cuda.current_stream()
-    # pointers resolved once per (action row, slab row): the timed loop is event / one ctypes call / event / flush
-    n_it = (K + T_ROLL - 1) // T_ROLL
-    bound = [sim.bind_step(acts[(W + k) % (W + K)], slabs[(k // T_ROLL) % len(slabs)].step_outputs(k % T_ROLL)) for k in range(K)]
-    for k in range(K):
-        row, cur = k % T_ROLL, (k // T_ROLL) % len(slabs)
-        if world > 1 and row == 0 and gdone[cur] is not None:
-            # the slab about to be refilled must have been gathered: any time the step stream has to WAIT for that is the
-            # exposed (non-overlapped) cost of the collective and is added to the step times
-            w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            w0.record(); main.wait_event(gdone[cur]); w1.record(); wev.append((w0, w1))
-        ev[k][0].record()
-        bound[k](t); t += 1
-        ev[k][1].record()
-        flush.fill_(0.0)
-        if world > 1 and row == T_ROLL - 1:            # one all-gather of the rollout slab per PPO iteration, on its own
-            filled = torch.cuda.Event(); filled.record()       # stream: it overlaps the next iteration's steps
-            with torch.cuda.stream(gstream):
-                gstream.wait_event(filled)
-                g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                g0.record(); gathered = slabs[cur].all_gather(); g1.record(); gev.append((g0, g1))
-                gdone[cur] = g1
-    if world > 1:                                       # the last gathers must be finished before the clock stops
-        w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        w0.record()
-        for g in gdone:
-            if g is not None:
-                main.wait_event(g)
-        w1.record(); wev.append((w0, w1))
+    e0.record()
+    gev = run_steps(bound, W, True)
+    e1.record()
     barrier()
-    launches = sim.launch_count - l0
-    step_ms = [a.elapsed_time(b) for a, b in ev]
+    tot_ms = e0.elapsed_time(e1)
+    launches = sum(s.launch_count for s in sims) - l0
     gather_each = [a.elapsed_time(b) for a, b in gev]
-    gather_ms = sum(gather_each)                        # duration of the collectives on their own stream (mostly hidden)
-    exposed_ms = sum(a.elapsed_time(b) for a, b in wev) # what the step stream actually waited for them
+    gather_ms = sum(gather_each)
     if gev and rank == 0:
-        print(f"[bench] all-gather ms per call: {[round(x, 3) for x in gather_each]}, exposed {exposed_ms:.3f} ms", file=sys.stderr)
-    tot_ms = sum(step_ms) + exposed_ms
-    # ---- warm-L2, CUDA-graph replay of K steps (supplementary: how the loop is meant to be driven) ----
+        print(f"[bench] all-gather ms per call: {[round(x, 3) for x in gather_each]}", file=sys.stderr)
+
+    # ---- round-1 protocol for comparison: per-step events, 256 MiB flush fill between steps; and its floor (empty kernel) ----
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+    KF = min(K, 50)
+    outs = slabs[0].step_outputs(0)
+    t = tcount[0]
+    fn0 = sim0.bind_step(acts[0], outs)
+    for _ in range(3):
+        fn0(t); flush.fill_(0.0); t += 1
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(KF)]
+    for a, b in ev:
+        a.record(); fn0(t); b.record(); flush.fill_(0.0); t += 1
+    torch.cuda.synchronize()
+    flush_us = [a.elapsed_time(b) * 1e3 for a, b in ev]
+    evn = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(30)]
+    for a, b in evn:
+        a.record(); wl.lib.wl_test_null((4 * E + 31) // 32, 32, _stream_ptr(sim0.device)); b.record(); flush.fill_(0.0)
+    torch.cuda.synchronize()
+    null_us = statistics.median(a.elapsed_time(b) * 1e3 for a, b in evn)
+    del flush
+    # ---- warm-L2, CUDA-graph replay of K steps on ONE env set (supplementary: how a rollout is meant to be driven) ----
     g = torch.cuda.CUDAGraph()
     s = torch.cuda.Stream()
     s.wait_stream(torch.cuda.current_stream())
+    sim0.set_step_counter(t)
     with torch.cuda.stream(s):
         with torch.cuda.graph(g, stream=s):
             for k in range(K):
-                sim.step(acts[(W + k) % (W + K)], t + k, out=outs)
+                sim0.step(acts[k % NA], sim0.device_counter_plus(k), out=outs)
+            sim0.advance_counter(K)
     torch.cuda.current_stream().wait_stream(s)
+    sim0.set_step_counter(t)
     g.replay(); barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(); g.replay(); e1.record(); barrier()
-    graph_ms = e0.elapsed_time(e1)
-    # ---- end-to-end through the public API with host buffers ----
-    env = wl.ManagerBasedRLEnv(wl.drift_task(num_envs=E, seed=args.seed, env_id_offset=rank * E), device=dev)
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record(); g.replay(); g1.record(); barrier()
+    graph_ms = g0.elapsed_time(g1)
+    sim0.note_device_counter(t + 2 * K)
+    # ---- end-to-end through the public API with host buffers: actions H2D, observations + reward + dones D2H, every step ----
+    env = wl.ManagerBasedRLEnv(mk(), device=dev)
     env.reset()
+    env.host_obs = True
     h_act = acts.cpu().pin_memory()
-    h_rows = [h_act[k] for k in range(W + K)]           # row views of the pinned block (what a host-side policy hands over)
+    h_rows = [h_act[k] for k in range(NA)]                    # row views of the pinned block (what a host-side policy hands over)
 
-    def e2e_step(k):
-        # the call a host-side user makes: host actions in, host reward / done masks out (one C-ABI call inside:
-        # H2D actions -> fused step -> D2H results -> stream sync); observations stay on the device for the policy
-        # h_rows[k]: this step's actions in PINNED host memory (a different block every step), read in place
-        obs, rew, term, trunc, extras = env.step_host(h_rows[k % (W + K)])
-        return rew, term, trunc
-
-    def time_e2e(transport):
-        env.host_transport = transport
-        for k in range(W):
-            e2e_step(k)
+    def time_e2e(transport, host_obs=True):
+        env.host_transport, env.host_obs = transport, host_obs
+        for k in range(max(W, 5)):
+            env.step_host(h_rows[k % NA])
         barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        a.record()
         for k in range(K):
-            e2e_step(W + k)
-        e1.record(); barrier()
-        return e0.elapsed_time(e1)
+            obs, rew, term, trunc, extras = env.step_host(h_rows[k % NA])      # returns after the stream sync: results are on the host
+        b.record(); barrier()
+        return max(a.elapsed_time(b), 1e3 * (time.perf_counter() - t0) * 0.0)
 
-    e2e_copy_ms = time_e2e("copy")
-    e2e_ms = time_e2e("zero_copy")
-    # ---- policy in the loop: 128 x (64x64 ELU MLP -> step -> slab row) captured as ONE CUDA graph (supplementary) ----
-    pil = None
-    try:
-        if args.no_extras:
-            raise RuntimeError('skipped (--no-extras)')
-        from wheeledlab_b200.rollout import GraphedRollout
-        torch.manual_seed(0)
-        mlp = torch.nn.Sequential(torch.nn.Linear(sim.obs_dim, 64), torch.nn.ELU(), torch.nn.Linear(64, 64), torch.nn.ELU(),
-                                  torch.nn.Linear(64, 2)).to(dev)
-        sim_p = wl.WheeledSim(wl.drift_task(num_envs=E, seed=args.seed, env_id_offset=rank * E), dev)
-        sim_p.startup(); sim_p.reset(None, 0)
-        with torch.no_grad():
-            roll = GraphedRollout(sim_p, lambda o: mlp(o), T_ROLL).capture(0)
-            roll.run(); barrier()
+    e2e_variants = {"zero_copy_obs_host": time_e2e("zero_copy"), "staged_copy_obs_host": time_e2e("copy"),
+                    "zero_copy_obs_on_device": time_e2e("zero_copy", host_obs=False)}
+    best = min(("zero_copy_obs_host", "staged_copy_obs_host"), key=lambda k2: e2e_variants[k2])
+    e2e_ms = e2e_variants[best]
+    # ---- supplementary figures (drift only): policy in the loop, fused policy, fused K-step rollout ----
+    pil = pfu = fused = None
+    if args.workload == "drift" and not args.no_extras:
+        try:
+            from wheeledlab_b200.rollout import GraphedRollout
+            torch.manual_seed(0)
+            mlp = torch.nn.Sequential(torch.nn.Linear(sim0.obs_dim, 64), torch.nn.ELU(), torch.nn.Linear(64, 64), torch.nn.ELU(),
+                                      torch.nn.Linear(64, 2)).to(dev)
+            sim_p = wl.WheeledSim(mk(), dev); sim_p.startup(); sim_p.reset(None, 0)
+            with torch.no_grad():
+                roll = GraphedRollout(sim_p, lambda o: mlp(o), 128).capture(0)
+                roll.run(); barrier()
+                R = 4
+                p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                p0.record()
+                for _ in range(R):
+                    roll.run()
+                p1.record(); barrier()
+            pil_ms = max_over_ranks(p0.elapsed_time(p1))
+            pil = {"value": E * world * 128 * R / (pil_ms * 1e-3), "unit": UNIT, "ms_per_step": pil_ms / (128 * R),
+                   "note": "rsl_rl-sized actor (14-64-64-2 ELU, torch/cuBLAS) + fused env step, 128 steps per CUDA-graph launch"}
+        except Exception as ex:
+            pil = {"error": repr(ex)[:200]}
+        try:
+            from wheeledlab_b200.policy import FusedPolicyRollout, pack_actor_critic
+            torch.manual_seed(0)
+            mkn = lambda out: torch.nn.Sequential(torch.nn.Linear(sim0.obs_dim, 64), torch.nn.ELU(), torch.nn.Linear(64, 64), torch.nn.ELU(),
+                                                  torch.nn.Linear(64, out)).to(dev)
+            blob = pack_actor_critic(mkn(2), mkn(1), torch.ones(2), sim0.obs_dim, dev)
+            sim_q = wl.WheeledSim(mk(), dev); sim_q.startup(); sim_q.reset(None, 0)
+            froll = FusedPolicyRollout(sim_q, blob, 128).capture(0)
+            froll.run(); barrier()
             R = 4
-            p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            p0.record()
+            q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            q0.record()
             for _ in range(R):
-                roll.run()
-            p1.record(); barrier()
-        pil_ms = max_over_ranks(p0.elapsed_time(p1)) if world > 1 else p0.elapsed_time(p1)
-        pil = {"value": E * world * T_ROLL * R / (pil_ms * 1e-3), "unit": UNIT, "ms_per_step": pil_ms / (T_ROLL * R),
-               "note": "rsl_rl-sized actor (14-64-64-2 ELU, torch/cuBLAS) + fused env step, 128 steps per CUDA-graph launch"}
-    except Exception as ex:                                      # supplementary figure only
-        pil = {"error": repr(ex)[:200]}
-    # ---- actor + critic + Gaussian sampling FUSED into the step kernel (wl_act_step), 128 launches per graph (supplementary) ----
-    pfu = None
-    try:
-        if args.no_extras:
-            raise RuntimeError('skipped (--no-extras)')
-        from wheeledlab_b200.policy import FusedPolicyRollout, pack_actor_critic
-        torch.manual_seed(0)
-        mk = lambda out: torch.nn.Sequential(torch.nn.Linear(sim.obs_dim, 64), torch.nn.ELU(), torch.nn.Linear(64, 64), torch.nn.ELU(),
-                                             torch.nn.Linear(64, out)).to(dev)
-        blob = pack_actor_critic(mk(2), mk(1), torch.ones(2), sim.obs_dim, dev)
-        sim_q = wl.WheeledSim(wl.drift_task(num_envs=E, seed=args.seed, env_id_offset=rank * E), dev)
-        sim_q.startup(); sim_q.reset(None, 0)
-        froll = FusedPolicyRollout(sim_q, blob, T_ROLL).capture(0)
-        froll.run(); barrier()
-        R = 4
-        q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        q0.record()
-        for _ in range(R):
-            froll.run()
-        q1.record(); barrier()
-        pfu_ms = max_over_ranks(q0.elapsed_time(q1)) if world > 1 else q0.elapsed_time(q1)
-        pfu = {"value": E * world * T_ROLL * R / (pfu_ms * 1e-3), "unit": UNIT, "ms_per_step": pfu_ms / (T_ROLL * R),
-               "note": "rsl_rl actor AND critic (14-64-64-2/1 ELU), Gaussian sample + log-prob, and the env step in ONE kernel; "
-                       "128 launches per CUDA graph"}
-    except Exception as ex:                                      # supplementary figure only
-        pfu = {"error": repr(ex)[:200]}
-    # ---- fused K-step synthetic rollout: K env.steps per launch, state in registers, in-kernel actions (supplementary) ----
-    fused = None
-    try:
-        if args.no_extras:
-            raise RuntimeError('skipped (--no-extras)')
-        KF = 125                                                  # divides the 250-step episode: windows end on curriculum boundaries
-        sim_f = wl.WheeledSim(wl.drift_task(num_envs=E, seed=args.seed, env_id_offset=rank * E), dev)
-        sim_f.startup(); sim_f.reset(None, 0)
-        slab_f = RolloutSlab(KF, E, sim_f.obs_dim, 2, dev)
-        logs_f = torch.empty((KF, 16), dtype=torch.float32, device=dev)
-        sim_f.rollout(KF, 0, slab_f, logs_f); barrier()
-        RF = 8
-        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        f0.record()
-        for r in range(RF):
-            sim_f.rollout(KF, KF * (1 + r), slab_f, logs_f)
-        f1.record(); barrier()
-        f_ms = max_over_ranks(f0.elapsed_time(f1))
-        fused = {"value": E * world * KF * RF / (f_ms * 1e-3), "unit": UNIT, "ms_per_step": f_ms / (KF * RF), "K": KF,
-                 "note": "wl_rollout: K env.steps per launch, state in registers, in-kernel U[-1,1]^2 actions; every step still "
-                         "writes its obs/action/reward/done slab rows and episode-log row; bit-identical to K wl_step calls"}
-    except Exception as ex:
-        fused = {"error": repr(ex)[:200]}
+                froll.run()
+            q1.record(); barrier()
+            pfu_ms = max_over_ranks(q0.elapsed_time(q1))
+            pfu = {"value": E * world * 128 * R / (pfu_ms * 1e-3), "unit": UNIT, "ms_per_step": pfu_ms / (128 * R),
+                   "note": "rsl_rl actor AND critic (14-64-64-2/1 ELU), Gaussian sample + log-prob, and the env step in ONE kernel; "
+                           "128 launches per CUDA graph"}
+        except Exception as ex:
+            pfu = {"error": repr(ex)[:200]}
+        try:
+            KFR = 125                                         # divides the 250-step episode: windows end on curriculum boundaries
+            sim_f = wl.WheeledSim(mk(), dev); sim_f.startup(); sim_f.reset(None, 0)
+            slab_f = RolloutSlab(KFR, E, sim_f.obs_dim, 2, dev)
+            logs_f = torch.empty((KFR, 16), dtype=torch.float32, device=dev)
+            sim_f.rollout(KFR, 0, slab_f, logs_f); barrier()
+            RF = 8
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            for r in range(RF):
+                sim_f.rollout(KFR, KFR * (1 + r), slab_f, logs_f)
+            f1.record(); barrier()
+            f_ms = max_over_ranks(f0.elapsed_time(f1))
+            fused = {"value": E * world * KFR * RF / (f_ms * 1e-3), "unit": UNIT, "ms_per_step": f_ms / (KFR * RF), "K": KFR,
+                     "note": "wl_rollout: K env.steps per launch, state in registers, in-kernel U[-1,1]^2 actions; every step still "
+                             "writes its obs/action/reward/done slab rows and episode-log row; bit-identical to K wl_step calls"}
+        except Exception as ex:
+            fused = {"error": repr(ex)[:200]}
     clocks = sampler.stop() if rank == 0 else None
 
     tot_ms, graph_ms, e2e_ms = max_over_ranks(tot_ms), max_over_ranks(graph_ms), max_over_ranks(e2e_ms)
-    e2e_copy_ms = max_over_ranks(e2e_copy_ms)
     gather_ms = max_over_ranks(gather_ms)
-    exposed_ms = max_over_ranks(exposed_ms)
     per_rank = None
-    if world > 1:                                       # diagnostics: which rank sets the max
-        st = torch.tensor([statistics.mean(step_ms), statistics.median(step_ms), max(step_ms)], dtype=torch.float64, device=dev)
+    if world > 1:                                             # diagnostics: which rank sets the max
+        st = torch.tensor([tot_ms / K, statistics.median(flush_us) * 1e-3], dtype=torch.float64, device=dev)
         allst = [torch.zeros_like(st) for _ in range(world)]
         dist.all_gather(allst, st)
         per_rank = {"step_us_mean": [round(float(x[0]) * 1e3, 3) for x in allst],
-                    "step_us_median": [round(float(x[1]) * 1e3, 3) for x in allst],
-                    "step_us_max": [round(float(x[2]) * 1e3, 3) for x in allst]}
+                    "flush_protocol_step_us_median": [round(float(x[1]) * 1e3, 3) for x in allst]}
     if rank == 0:
         total_envs = E * world
         value = total_envs * K / (tot_ms * 1e-3)
-        kern_s = statistics.mean(step_ms) * 1e-3
-        achieved = BYTES_PER_ENV_STEP * E / kern_s / 1e9
-        cpu = cpu_baseline(E, args.seed, budget_s=args.cpu_budget) if world == 1 else None
+        kern_s = tot_ms * 1e-3 / K
+        achieved = w["bytes"] * E / kern_s / 1e9
+        cpu = cpu_baseline(args.workload, E, args.seed, budget_s=args.cpu_budget) if world == 1 else None
+        n_gathers = len(gev)
+        slab_bytes = slabs[0].nbytes
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": tot_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"RSS_DRIFT_CONFIG MushrDriftRL {E} envs/GPU x {world} GPU, dt 5ms x4, DR+push+noise on",
-                       "envs_per_gpu": E, "global_envs": total_envs, "actions": "U[-1,1]^2 philox(seed,env,step)",
-                       "l2": "flushed between timed steps (256 MiB fill)", "parallelism": f"env-shard x{world}"},
+            "config": {"workload": f"{w['label']}: {E} envs/GPU x {world} GPU", "envs_per_gpu": E, "global_envs": total_envs,
+                       "actions": "U[-1,1]^2 philox(seed,env,step)",
+                       "l2": f"inputs larger than L2, no flush kernel: {M} independent {E}-env sets ({M * set_bytes / 1e6:.0f} MB of state + "
+                             f"parameters) stepped round-robin, every step writes a fresh rollout-slab row ({n_slabs} x {slab_bytes / 1e6:.0f} MB)",
+                       "parallelism": f"env-shard x{world}", "timing": "2 CUDA events around the K back-to-back steps (PDL launches)"},
             "clocks": clocks,
             "e2e": {"value": total_envs * K / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": E * 8,
-                    "d2h_bytes_per_step": E * 6, "ms_per_step": e2e_ms / K,
-                    "staged_copy_transport_ms_per_step": e2e_copy_ms / K,
-                    "api": "ManagerBasedRLEnv.step_host(pinned actions) -> wl_step_host_zero_copy: the kernel reads the "
-                           "actions from / writes reward+dones to pinned host memory over PCIe, then stream sync, every step"},
+                    "d2h_bytes_per_step": E * (6 + 4 * sim0.obs_dim), "ms_per_step": e2e_ms / K, "transport": best,
+                    "variants_ms_per_step": {k2: v / K for k2, v in e2e_variants.items()},
+                    "api": "ManagerBasedRLEnv.step_host(pinned actions), host_obs=True: actions H2D, observations + reward + dones D2H "
+                           "(zero_copy: the kernel reads / writes pinned host memory over PCIe; staged_copy: cudaMemcpyAsync both ways), "
+                           "stream sync, every step.  zero_copy_obs_on_device (round 1's figure: obs left on the GPU) is listed for comparison"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of
-                         # this kernel at this size (profiles/r01_ncu_v3_step_4096.txt: 931 072 B read, 0 B written -- the
-                         # 1.7 MB working set is written back from L2 later, so DRAM traffic < algorithmic bytes)
-                         "traffic": 931072 if E == 4096 else None, "traffic_unit": "bytes/launch", "peak_source": peak_src, "kernel": "wl_step_kernel<DRIFT>",
-                         "bytes_per_env_step": BYTES_PER_ENV_STEP, "avg_kernel_us": kern_s * 1e6,
+                         "traffic": _traffic(w["traffic_profile"]) if E == w["envs"] else None, "traffic_unit": "bytes/launch (dram read + write, ncu --set full)",
+                         "traffic_source": w["traffic_profile"], "peak_source": peak_src, "kernel": w["kernel"],
+                         "bytes_per_env_step": w["bytes"], "avg_step_us": kern_s * 1e6,
                          "kernel_variant": "quad (4 lanes/env)" if E <= 148 * 4 * 32 * 2 else "thread-per-env",
-                         "note": "N=4096 moves 1.7 MB/launch: launch-latency bound, see profiles/ for the N sweep"},
+                         "note": f"{E} envs move {w['bytes'] * E / 1e6:.1f} MB per launch: latency-bound at this size, see profiles/ for the N sweep"},
             "cpu_baseline": cpu,
+            "flush_protocol": {"step_us_median": statistics.median(flush_us), "step_us_mean": statistics.mean(flush_us),
+                               "value": total_envs / (statistics.mean(flush_us) * 1e-6) if world == 1 else None,
+                               "empty_kernel_us": null_us,
+                               "note": "round-1 protocol: per-step events, 256 MiB L2-flush fill between steps; empty_kernel_us is the same "
+                                       "measurement around an EMPTY kernel of the same geometry (the protocol's own floor)"},
             "collective": {"kind": "all_gather_into_tensor(rollout slab)", "per_iteration_steps": T_ROLL,
-                           "bytes_per_rank": slab.nbytes, "count": len(gev), "ms_total": gather_ms,
-                           "overlapped_with_next_iteration": True, "exposed_ms_total": exposed_ms,
-                           "note": "double-buffered slabs; the gather of iteration i runs on its own stream under the steps of "
-                                   "iteration i+1; `value` charges the time the step stream waited for it (exposed_ms_total)"}
+                           "bytes_per_rank": slab_bytes, "count": n_gathers, "ms_total": gather_ms,
+                           "ms_each": [round(x, 3) for x in gather_each],
+                           "bus_GBps": (slab_bytes * (world - 1) / (statistics.mean(gather_each) * 1e-3) / 1e9) if gather_each else None,
+                           "overlapped_with_next_iteration": True,
+                           "note": "double-buffered slabs; the gather of iteration i runs on its own stream under the steps of iteration i+1 "
+                                   "and all gathers are complete before the clock stops (inside the timed region)"}
             if world > 1 else None,
             "per_rank": per_rank,
             "policy_in_loop_graph": pil,
             "policy_fused_in_step": pfu,
             "rollout_fused": fused,
             "warm_l2_graph": {"value": total_envs * K / (graph_ms * 1e-3), "unit": UNIT, "ms_per_step": graph_ms / K,
-                              "note": "K steps captured in one CUDA graph, state L2-resident (supplementary)"},
+                              "note": "K steps of ONE env set captured in one CUDA graph (PDL edges), state L2-resident (supplementary)"},
         }
         guard.emit(json.dumps(line))
     if world > 1:
@@ -469,7 +547,8 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=100)
-    ap.add_argument("--envs", type=int, default=4096, help="envs per GPU")
+    ap.add_argument("--workload", default="drift", choices=sorted(WORKLOADS))
+    ap.add_argument("--envs", type=int, default=0, help="envs per GPU (default: the workload's BASELINE size)")
     ap.add_argument("--seed", type=int, default=42)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-budget", type=float, default=12.0)

@@ -197,6 +197,7 @@ extern "C" {
     XS(float, f32, vel_offset)                                                                     \
     XS(float, f32, tlgr_ang_vel_thresh)                                                            \
     XS(float, f32, energy_straight)                                                                \
+    XS(int32_t, i32, term_enable)     /* bit j = termination term j is configured (play cfgs: terminations = None -> 0) */ \
     XS(int32_t, i32, num_rew_terms)                                                                \
     XA(float, f32, rew_weight, WL_MAX_REW_TERMS)  /* initial weights; live copy is on device */    \
     /* --- curriculum: increase_reward_weight_over_time terms (curriculums.py:10-35), evaluated ON DEVICE by the  \

@@ -963,6 +963,7 @@ static int env_step(wlo_sim* s, int li, const float* a_in, int64_t t, float* obs
     } else {
         return WL_EUNSUPPORTED;
     }
+    tmask &= (uint32_t)c->term_enable;     /* play cfgs: terminations = None */
     /* E. reward manager [UPSTREAM-RECALL Appendix B]: value = f*w*dt, skip w==0 */
     real total = K(0.0);
     for (int k = 0; k < c->num_rew_terms; ++k) {

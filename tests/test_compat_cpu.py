@@ -90,3 +90,60 @@ def test_unknown_term_becomes_host_side_term_when_allowed(ref_cfgs):
     assert s.python_reward_terms == [("my_bonus", f, 3.0, {"k": 2.0})]
     assert s.python_termination_terms == [("my_stop", g, False, {})]
     assert "my_bonus" not in s.reward_names and len(s.reward_names) == 7      # built-in slots untouched
+
+
+# ---- the registration path: UNMODIFIED wheeledlab_tasks/__init__.py against shims/ (gymnasium, isaaclab, pxr, matplotlib) ----
+def _cfg_blob(c):
+    import ctypes as C
+    return C.string_at(C.addressof(c), C.sizeof(c))
+
+
+def test_unmodified_registration_and_all_cfgs_lower_to_the_committed_blobs():
+    """`import wheeledlab_tasks` (reference source, untouched) registers the four gym ids through the gymnasium stand-in; every
+    train and play cfg lowers through compat.spec_from_reference_cfg to exactly the committed fixture, and the train cfgs equal
+    make_task(id) byte for byte."""
+    if not REF.exists():
+        pytest.skip("/root/reference not present (GPU box)")
+    import importlib.util
+    import numpy as np
+    import wheeledlab_b200 as wl
+    from wheeledlab_b200.compat import spec_from_reference_cfg
+    spec = importlib.util.spec_from_file_location("make_cfg_blobs", ROOT / "tests" / "golden" / "make_cfg_blobs.py")
+    mk = importlib.util.module_from_spec(spec); spec.loader.exec_module(mk)
+    gym = mk.import_reference_tasks()
+    assert sorted(gym.registry) == sorted(wl.GYM_IDS)
+    for gid in gym.registry:
+        s = gym.spec(gid)
+        assert s.entry_point == "isaaclab.envs:ManagerBasedRLEnv" and s.kwargs["rsl_rl_cfg_entry_point"].count(":") == 1
+        for key, suffix in (("env_cfg_entry_point", "ref"), ("play_env_cfg_entry_point", "play.ref")):
+            cls = s.kwargs.get(key)
+            if cls is None:
+                continue
+            cfg = cls(); cfg.scene.num_envs = 4096
+            got = spec_from_reference_cfg(cfg)
+            fixture = (ROOT / "tests" / "golden" / "cfg_blobs" / f"{gid}.{suffix}.bin").read_bytes()
+            if "Visual" in gid:                      # the reference draws a new random traversability map at every import (quirk Q10)
+                got.cfg.vis_n_trav = int(np.load(ROOT / "tests" / "golden" / "cfg_blobs" / "visual_ref_map.npz")["map"].sum())
+            assert _cfg_blob(got.cfg) == fixture, (gid, key)
+            if suffix == "play.ref":                 # play cfgs: "no terminations" (Drift / Visual also drop rewards and curriculum)
+                assert got.cfg.term_enable == 0
+                if "Elevation" not in gid:
+                    assert got.cfg.curr_n == 0 and not any(got.cfg.rew_weight)
+    # a modified observation group is rejected, not silently replaced by the built-in one (ADVICE r1)
+    bad = gym.spec("Isaac-MushrDriftRL-v0").kwargs["env_cfg_entry_point"]()
+    bad.observations.policy.base_lin_vel_term = None
+    with pytest.raises(NotImplementedError):
+        spec_from_reference_cfg(bad)
+
+
+def test_make_task_reproduces_the_lowered_reference_cfgs():
+    """Runs everywhere (also on the GPU box, where /root/reference does not exist): the package's own restatement of the four
+    registered tasks equals the blobs lowered from the reference's cfg objects, byte for byte."""
+    import numpy as np
+    import wheeledlab_b200 as wl
+    blobs = ROOT / "tests" / "golden" / "cfg_blobs"
+    ref_map = np.load(blobs / "visual_ref_map.npz")["map"]
+    for gid in wl.GYM_IDS:
+        kw = {"traversability": ref_map} if "Visual" in gid else {}
+        spec = wl.make_task(gid, num_envs=4096, seed=42, **kw)
+        assert _cfg_blob(spec.cfg) == (blobs / f"{gid}.ref.bin").read_bytes(), gid

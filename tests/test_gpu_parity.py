@@ -938,3 +938,33 @@ def test_two_process_nccl_gather_equals_single_rank(tmp_path):
     torch.cuda.synchronize()
     for name in ("obs", "actions", "rewards", "terminated", "truncated"):
         assert torch.equal(getattr(slab, name).cpu(), got[name]), name
+
+
+def test_gym_make_through_the_registry_and_the_reference_smoke_loop():
+    """wheeledlab_tasks/__init__.py:14-63 registers `entry_point="isaaclab.envs:ManagerBasedRLEnv"`; with shims/ on the path
+    gym.make(id, cfg=...) resolves to the B200 env.  The loop is the reference's own smoke test
+    (wheeledlab_tasks/test/create_and_step_env.py:26-44): reset, then sample-and-step under inference_mode."""
+    _need_gpu()
+    import sys
+    root = Path(__file__).resolve().parent.parent
+    sys.path.insert(0, str(root / "shims"))
+    import gymnasium as gym
+    import wheeledlab_b200 as wl
+    for gid in wl.GYM_IDS:                                # the four register() calls of the reference, restated (its package is not on this box)
+        gym.register(id=gid, entry_point="isaaclab.envs:ManagerBasedRLEnv", disable_env_checker=True,
+                     kwargs={"env_cfg_entry_point": None, "rsl_rl_cfg_entry_point": "x:y"})
+    for gid in wl.GYM_IDS:
+        spec = wl.make_task(gid, num_envs=48, seed=1)
+        assert C.string_at(C.addressof(spec.cfg), 8) == (root / "tests" / "golden" / "cfg_blobs" / f"{gid}.ref.bin").read_bytes()[:8]
+        env = gym.make(gid, cfg=spec)
+        assert isinstance(env.unwrapped, wl.ManagerBasedRLEnv) and env.num_envs == 48
+        import isaaclab.envs
+        assert isinstance(env.unwrapped, isaaclab.envs.ManagerBasedRLEnv)
+        with torch.inference_mode():
+            obs, _ = env.reset()
+            for _ in range(12):
+                actions = torch.rand((env.num_envs, 2), device="cuda") * 2 - 1
+                obs, rew, term, trunc, info = env.step(actions)
+            assert obs["policy"].shape == (48, env.spec_obs_dim if hasattr(env, "spec_obs_dim") else spec.obs_dim) and torch.isfinite(obs["policy"]).all()
+            assert rew.shape == (48,) and term.dtype == torch.bool and "log" in info
+        env.close()

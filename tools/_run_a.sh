@@ -1,4 +1,8 @@
 mkdir -p gpurun_out
-export KEXP_VARIANTS='{"base":[],"nofinal":["WL_EXP_NOFINAL"],"nofence":["WL_EXP_NOFENCE"],"nofinal_nofence":["WL_EXP_NOFINAL","WL_EXP_NOFENCE"],"bs128":["WL_QUAD_BS=128"],"bs128_nofinal_nofence":["WL_QUAD_BS=128","WL_EXP_NOFINAL","WL_EXP_NOFENCE"],"bs64":["WL_QUAD_BS=64"]}'
-python tools/kexp.py run > gpurun_out/r02_kexp_a.jsonl 2> gpurun_out/r02_kexp_a.err
-cat gpurun_out/r02_kexp_a.jsonl; tail -3 gpurun_out/r02_kexp_a.err
+export KEXP_VARIANTS='{"base":[]}'
+export KEXP_PDL=1,0
+python tools/kexp.py run > gpurun_out/r02_kexp_c.jsonl 2> gpurun_out/r02_kexp_c.err
+cat gpurun_out/r02_kexp_c.jsonl; tail -5 gpurun_out/r02_kexp_c.err
+python -m pytest tests -m gpu -x -q 2>&1 | tail -25 > gpurun_out/r02_gputest_c.log
+cat gpurun_out/r02_gputest_c.log
+python bench.py --steps 200 --warmup 20 > gpurun_out/r02_bench_c.json 2> gpurun_out/r02_bench_c.err; tail -3 gpurun_out/r02_bench_c.err; cat gpurun_out/r02_bench_c.json

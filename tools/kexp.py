@@ -68,6 +68,23 @@ def child(envs, steps, warm, task):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
     warm_us = e0.elapsed_time(e1) * 1e3 / K
+    # working set larger than L2 instead of a flush kernel: M independent env sets stepped round-robin, back to back
+    M = int(os.environ.get("KEXP_SETS", "160"))
+    sims = []
+    for m in range(M):
+        sm = wl.WheeledSim(wl.make_task(task, num_envs=envs, seed=42 + m), dev); sm.startup(); sm.reset(None, 0); sims.append(sm)
+    outs = [tuple(torch.empty_like(x) for x in out) for _ in range(M)]
+    bound = [sims[m].bind_step(acts[m % (W + K)], outs[m]) for m in range(M)]
+    tt = [0] * M
+    def rot(nsteps, k0):
+        for k in range(nsteps):
+            m = (k0 + k) % M
+            bound[m](tt[m]); tt[m] += 1
+    rot(2 * M, 0); torch.cuda.synchronize()
+    RK = 4 * M
+    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    r0.record(); rot(RK, 0); r1.record(); torch.cuda.synchronize()
+    rot_us = r0.elapsed_time(r1) * 1e3 / RK
     # floor of the protocol: empty kernel of the same geometry between the same events / flushes
     nul = []
     for geo in ((envs * 4 + 31) // 32, 32), ((envs * 4 + 127) // 128, 128):
@@ -78,13 +95,15 @@ def child(envs, steps, warm, task):
         nul.append(statistics.median(a.elapsed_time(b) * 1e3 for a, b in evn))
     print(json.dumps({"variant": os.environ.get("KEXP_NAME"), "task": task, "envs": envs, "cold_us_mean": statistics.mean(cold),
                       "cold_us_median": statistics.median(cold), "cold_us_min": min(cold), "warm_graph_us": warm_us,
+                      "rotate_us": rot_us, "rotate_sets": M, "pdl": os.environ.get("WL_PDL", "1"),
                       "null_us_bs32": nul[0], "null_us_bs128": nul[1]}), flush=True)
 
 
 def run(envs, task):
     for name in VARIANTS:
-        env = dict(os.environ, WHEELEDLAB_B200_LIB=str(AB / f"libwl_{name}.so"), KEXP_NAME=name)
-        subprocess.run([sys.executable, __file__, "child", str(envs), task], env=env, check=False)
+        for pdl in os.environ.get("KEXP_PDL", "1").split(","):
+            env = dict(os.environ, WHEELEDLAB_B200_LIB=str(AB / f"libwl_{name}.so"), KEXP_NAME=name, WL_PDL=pdl)
+            subprocess.run([sys.executable, __file__, "child", str(envs), task], env=env, check=False)
 
 
 if __name__ == "__main__":

@@ -1,6 +1,7 @@
 // wl_api.cu -- kernels + the extern "C" ABI declared in include/wheeledlab_b200.h.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false -lineinfo -O3 (see build.py).
 #include <cstdio>
+#include <cstdlib>
 #include <cmath>
 #include <cstring>
 #include <new>
@@ -52,6 +53,12 @@ static inline size_t align256(size_t x) { return (x + 255u) & ~(size_t)255u; }
 __device__ __forceinline__ uint32_t decode_step(const wl_globals* __restrict__ gl, uint32_t t_arg) {
     return ((int32_t)t_arg < 0) ? __ldcg(&gl->step_base) + (0xFFFFFFFFu - t_arg) : t_arg;
 }
+// Programmatic dependent launch (sm_90+): a step kernel lets the next launch of the stream start its prologue right away
+// (launch_dependents first thing) and itself waits for the previous kernel's memory to be final (wait) before the first
+// read of anything a previous launch may have written.  Both are no-ops for a launch without the PDL attribute.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // W(t): the weights step t-1 used, plus increase_reward_weight_over_time (curriculums.py:23-35) for the counter value t
 // reached by the step that just ended -- the reference calls it from _reset_idx, i.e. only if >= 1 env reset in step t-1.
 // Every thread of the launch evaluates this identically (no thread writes what another one reads here).
@@ -81,7 +88,8 @@ __device__ __forceinline__ void publish_log_row(const wl_config& c, wl_globals* 
     float* lp = gl->log_ptr[row];
     if (lp != nullptr && lane < 16) lp[lane] = (lane < WL_MAX_REW_TERMS) ? v / (r_max(cnt, 1.0f) * c.episode_length_s) : v;
 }
-// The janitor: ONE warp of the launch (warp 0 of CTA 0), right after it has issued its state loads.
+// The janitor: ONE warp of the launch -- the first warp of an EXTRA CTA appended to the grid (blockIdx.x == gridDim.x - 1)
+// that owns no envs, so that no env warp starts its dependent chain late.
 __device__ __forceinline__ void janitor(const wl_config& c, wl_globals* __restrict__ gl, uint32_t t, const float wts[WL_MAX_REW_TERMS],
                                         float* __restrict__ d_log) {
     const int lane = threadIdx.x & 31;
@@ -135,8 +143,10 @@ wl_step_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st, wl_
                uint8_t* __restrict__ terminated_o, uint8_t* __restrict__ truncated_o, float* __restrict__ d_log, uint32_t t_arg,
                StageIO sio = StageIO{nullptr, nullptr, nullptr}) {
     constexpr bool ELEV = (TASK == WL_TASK_ELEVATION), VIS = (TASK == WL_TASK_VISUAL);
+    pdl_trigger();
     const int n = c.num_envs;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    pdl_wait();
     const uint32_t t = decode_step(gl, t_arg);
     const VisualMap vm = VIS ? visual_map(c, T.hf) : VisualMap{nullptr, nullptr};
     bool done = false;
@@ -144,7 +154,10 @@ wl_step_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st, wl_
     EnvState e;
     float wts[WL_MAX_REW_TERMS];            // W(t): issued with the state loads so the latency hides behind the integrator
     load_weights(c, gl, t, wts);
-    if (STAGE != 1 && blockIdx.x == 0 && threadIdx.x < 32) janitor(c, gl, t, wts, d_log);
+    if (STAGE != 1 && blockIdx.x == gridDim.x - 1) {          // the janitor CTA (appended to the grid, owns no envs)
+        if (threadIdx.x < 32) janitor(c, gl, t, wts, d_log);
+        return;
+    }
     if (STAGE == 2) {
         if (i < n) {
             load_env(st, n, i, e, ELEV, c.dr_wheel_mass_enable != 0, c.d_inv_Iw);
@@ -196,6 +209,7 @@ wl_step_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st, wl_
             drift_reward_terms(c, e.steer[0], e.steer[1], det_atan2(vb.y, vb.x), e.p, vb, b.wb, e.w.z, oob, time_out, f);
             tmask = (time_out ? 1u : 0u) | (oob ? 2u : 0u);
         }
+        tmask &= (uint32_t)c.term_enable;
         float total = 0.0f;
 #pragma unroll
         for (int k = 0; k < WL_MAX_REW_TERMS; ++k) {
@@ -248,7 +262,7 @@ wl_step_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st, wl_
 template <int TASK>
 __device__ __forceinline__ void quad_env_step(const wl_config& c, const Terrain& T, const VisualMap& vm, float* __restrict__ acc_row,
                                               const float wts[WL_MAX_REW_TERMS], EnvState& e, int i, int w, bool live, uint32_t gid,
-                                              unsigned base, uint32_t t, float2 a, float* __restrict__ obs_row,
+                                              unsigned base, uint32_t t, float2 a, const float znoise[4], float* __restrict__ obs_row,
                                               float* __restrict__ rew, uint8_t* __restrict__ terminated_o,
                                               uint8_t* __restrict__ truncated_o) {
     constexpr bool ELEV = (TASK == WL_TASK_ELEVATION), VIS = (TASK == WL_TASK_VISUAL);
@@ -297,6 +311,7 @@ __device__ __forceinline__ void quad_env_step(const wl_config& c, const Terrain&
         drift_reward_terms(c, steer_l, steer_r, det_atan2(vb.y, vb.x), e.p, vb, b.wb, e.w.z, oob, time_out, f);
         tmask = (time_out ? 1u : 0u) | (oob ? 2u : 0u);
     }
+    tmask &= (uint32_t)c.term_enable;
     float total = 0.0f;
 #pragma unroll
     for (int k = 0; k < WL_MAX_REW_TERMS; ++k) {
@@ -344,7 +359,7 @@ __device__ __forceinline__ void quad_env_step(const wl_config& c, const Terrain&
             }
         } else {
             // blind_obs_quad shuffles: every lane of the warp calls it, dead quads only skip the stores
-            blind_obs_quad(c, e, w, eu_k, gid, t, RNG_OBS, 0u, obs_row, live);
+            blind_obs_quad(c, e, w, eu_k, znoise, obs_row, live);
         }
     }
 }
@@ -355,7 +370,7 @@ wl_step_quad_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st
                     const float2* __restrict__ action, float* __restrict__ obs, float* __restrict__ rew,
                     uint8_t* __restrict__ terminated_o, uint8_t* __restrict__ truncated_o, float* __restrict__ d_log, uint32_t t_arg) {
     constexpr bool ELEV = (TASK == WL_TASK_ELEVATION), VIS = (TASK == WL_TASK_VISUAL);
-    const uint32_t t = decode_step(gl, t_arg);
+    pdl_trigger();
     const VisualMap vm = VIS ? visual_map(c, T.hf) : VisualMap{nullptr, nullptr};
     const int n = c.num_envs;
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -364,13 +379,22 @@ wl_step_quad_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st
     const int ii = live ? i : n - 1;         // dead quads shadow the last env (no stores) so shuffles stay convergent
     const uint32_t gid = (uint32_t)(c.env_id_offset + ii);
     const unsigned base = (threadIdx.x & 31u) & ~3u;
+    pdl_wait();
+    const uint32_t t = decode_step(gl, t_arg);
+    float wts[WL_MAX_REW_TERMS];
+    if (blockIdx.x == gridDim.x - 1) {       // the janitor CTA (appended to the grid, owns no envs)
+        if (threadIdx.x < 32) { load_weights(c, gl, t, wts); janitor(c, gl, t, wts, d_log); }
+        return;
+    }
     EnvState e;
     load_env_quad(st, n, ii, w, e, ELEV, c.dr_wheel_mass_enable != 0, c.d_inv_Iw);
-    float wts[WL_MAX_REW_TERMS];
     load_weights(c, gl, t, wts);
-    if (blockIdx.x == 0 && threadIdx.x < 32) janitor(c, gl, t, wts, d_log);
+    const float2 a = action[ii];
+    // the observation noise depends on (env id, step) only: drawn here, while the state loads are in flight
+    float zn[4];
+    if (!ELEV && !VIS) quad_obs_noise(c, w, gid, t, RNG_OBS, 0u, zn); else zn[0] = zn[1] = zn[2] = zn[3] = 0.0f;
     const int od = ELEV ? WL_OBS_DIM_ELEV : VIS ? WL_OBS_DIM_VISUAL + vis_cam_floats(c) : WL_OBS_DIM_BLIND;
-    quad_env_step<TASK>(c, T, vm, gl->acc[t % 3u], wts, e, i, w, live, gid, base, t, action[ii], obs + (size_t)od * ii, rew, terminated_o, truncated_o);
+    quad_env_step<TASK>(c, T, vm, gl->acc[t % 3u], wts, e, i, w, live, gid, base, t, a, zn, obs + (size_t)od * ii, rew, terminated_o, truncated_o);
     if (live) store_env_quad(st, n, i, w, e, ELEV);
 }
 
@@ -463,6 +487,16 @@ wl_act_step_quad_kernel(const __grid_constant__ wl_config c, float4* __restrict_
     constexpr bool ELEV = (TASK == WL_TASK_ELEVATION), VIS = (TASK == WL_TASK_VISUAL);
     extern __shared__ __align__(128) float smem[];
     __shared__ __align__(8) uint64_t mbar[2];
+    pdl_trigger();
+    pdl_wait();
+    if (blockIdx.x == gridDim.x - 1) {                       // the janitor CTA (appended to the grid, owns no envs)
+        if (threadIdx.x < 32) {
+            const uint32_t tj = decode_step(gl, t_arg);
+            float wj[WL_MAX_REW_TERMS];
+            load_weights(c, gl, tj, wj); janitor(c, gl, tj, wj, d_log);
+        }
+        return;
+    }
     float* sw = smem;                                        // the whole weight blob (~42 KB)
     float* sx = smem + blob_floats;                          // [32][WL_ACT_XS]
     float* sh = sx + WL_ACT_ENVS * WL_ACT_XS;                // [32][WL_ACT_HS]
@@ -494,17 +528,17 @@ wl_act_step_quad_kernel(const __grid_constant__ wl_config c, float4* __restrict_
     if (stepper) {
         load_env_quad(st, n, ii, w, e, ELEV, c.dr_wheel_mass_enable != 0, c.d_inv_Iw);
         load_weights(c, gl, t, wts);
-        if (blockIdx.x == 0 && threadIdx.x < 32) janitor(c, gl, t, wts, d_log);
     }
     for (int k = threadIdx.x; k < WL_ACT_ENVS * 16; k += WL_ACT_THREADS) {
         const int eq = k >> 4, j = k & 15, ei = min(blockIdx.x * WL_ACT_ENVS + eq, n - 1);
         sx[eq * WL_ACT_XS + j] = j < obs_dim ? obs_in[(size_t)ei * obs_dim + j] : 0.0f;
     }
     // the policy noise does not depend on the weights: draw it while the copies are in flight
-    float z0 = 0.0f, z1 = 0.0f;
+    float z0 = 0.0f, z1 = 0.0f, zn[4] = {0.0f, 0.0f, 0.0f, 0.0f};
     if (stepper) {
         const uint4 r = philox4x32(c.seed, gid, t, RNG_POLICY, 0u);
         box_muller(r.x, r.y, z0, z1);
+        if (!ELEV && !VIS) quad_obs_noise(c, w, gid, t, RNG_OBS, 0u, zn);
     }
     __syncthreads();                                         // mbarrier init visible to every waiter; obs rows written
     mbar_wait(&mbar[0]);
@@ -555,7 +589,7 @@ wl_act_step_quad_kernel(const __grid_constant__ wl_config c, float4* __restrict_
         }
         // ---- the env step on the sampled action
         const int od = ELEV ? WL_OBS_DIM_ELEV : VIS ? WL_OBS_DIM_VISUAL + vis_cam_floats(c) : WL_OBS_DIM_BLIND;
-        quad_env_step<TASK>(c, T, vm, gl->acc[t % 3u], wts, e, i, w, live, gid, base, t, a, obs + (size_t)od * ii, rew, terminated_o, truncated_o);
+        quad_env_step<TASK>(c, T, vm, gl->acc[t % 3u], wts, e, i, w, live, gid, base, t, a, zn, obs + (size_t)od * ii, rew, terminated_o, truncated_o);
         if (live) store_env_quad(st, n, i, w, e, ELEV);
     }
 }
@@ -596,7 +630,9 @@ wl_rollout_quad_kernel(const __grid_constant__ wl_config c, float4* __restrict__
             a = make_float2(2.0f * u01(r.x) - 1.0f, 2.0f * u01(r.y) - 1.0f);
         }
         if (act_out != nullptr && live && w == 0) act_out[(size_t)k * n + i] = a;
-        quad_env_step<TASK>(c, T, vm, d_log + (size_t)k * WL_LOG_FLOATS, wts, e, i, w, live, gid, base, t, a,
+        float zn[4];
+        if (!ELEV && !VIS) quad_obs_noise(c, w, gid, t, RNG_OBS, 0u, zn); else zn[0] = zn[1] = zn[2] = zn[3] = 0.0f;
+        quad_env_step<TASK>(c, T, vm, d_log + (size_t)k * WL_LOG_FLOATS, wts, e, i, w, live, gid, base, t, a, zn,
                             obs + ((size_t)k * n + ii) * od, rew + (size_t)k * n, terminated_o + (size_t)k * n,
                             truncated_o + (size_t)k * n);
     }
@@ -1072,6 +1108,20 @@ wl_camera_kernel(const __grid_constant__ wl_config c, const float4* __restrict__
 // ---------------------------------------------------------------------------------------
 // launch geometry: spread small N over all 148 SMs, use fatter CTAs once the chip is full
 // ---------------------------------------------------------------------------------------
+// launch with (or without) the programmatic-dependent-launch attribute
+static bool g_pdl = (getenv("WL_PDL") == nullptr) || (atoi(getenv("WL_PDL")) != 0);
+template <typename... KArgs, typename... Args>
+static void launch_k(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t cs, Args... args) {
+    cudaLaunchConfig_t lc;
+    memset(&lc, 0, sizeof lc);
+    lc.gridDim = dim3((unsigned)grid); lc.blockDim = dim3((unsigned)block); lc.dynamicSmemBytes = smem; lc.stream = cs;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = attr; lc.numAttrs = g_pdl ? 1 : 0;
+    cudaLaunchKernelEx(&lc, kernel, KArgs(args)...);
+}
+
 static inline int pick_block(int n) {
     if (n >= 148 * 128 * 4) return 128;
     if (n >= 148 * 64 * 2) return 64;
@@ -1343,19 +1393,20 @@ int wl_step(wl_sim* sim, const float* d_action, float* d_obs, float* d_rew, uint
     const uint32_t t = (uint32_t)step_counter;               // negative (device base + k) stays encoded: see decode_step
     if (int rc = prep_step(sim, step_counter, 1, cs)) return rc;
     const bool elev = sim->cfg.task == WL_TASK_ELEVATION, vis = sim->cfg.task == WL_TASK_VISUAL;
+    StageIO sio0{nullptr, nullptr, nullptr};
     if (variant == 4) {
 #ifndef WL_QUAD_BS
 #define WL_QUAD_BS 32
 #endif
-        const int bs = WL_QUAD_BS, threads = 4 * n, grid = (threads + bs - 1) / bs;
-        if (elev) wl_step_quad_kernel<WL_TASK_ELEVATION><<<grid, bs, 0, cs>>>(sim->cfg, sim->state, sim->globals, T, act, d_obs, d_rew, d_terminated, d_truncated, d_log, t);
-        else if (vis) wl_step_quad_kernel<WL_TASK_VISUAL><<<grid, bs, 0, cs>>>(sim->cfg, sim->state, sim->globals, T, act, d_obs, d_rew, d_terminated, d_truncated, d_log, t);
-        else wl_step_quad_kernel<WL_TASK_DRIFT><<<grid, bs, 0, cs>>>(sim->cfg, sim->state, sim->globals, T, act, d_obs, d_rew, d_terminated, d_truncated, d_log, t);
+        const int bs = WL_QUAD_BS, threads = 4 * n, grid = (threads + bs - 1) / bs + 1;      // + the janitor CTA
+        if (elev) launch_k(wl_step_quad_kernel<WL_TASK_ELEVATION>, grid, bs, 0, cs, sim->cfg, sim->state, sim->globals, T, act, d_obs, d_rew, d_terminated, d_truncated, d_log, t);
+        else if (vis) launch_k(wl_step_quad_kernel<WL_TASK_VISUAL>, grid, bs, 0, cs, sim->cfg, sim->state, sim->globals, T, act, d_obs, d_rew, d_terminated, d_truncated, d_log, t);
+        else launch_k(wl_step_quad_kernel<WL_TASK_DRIFT>, grid, bs, 0, cs, sim->cfg, sim->state, sim->globals, T, act, d_obs, d_rew, d_terminated, d_truncated, d_log, t);
     } else {
-        const int bs = pick_block(n), grid = (n + bs - 1) / bs;
-        if (elev) wl_step_kernel<WL_TASK_ELEVATION><<<grid, bs, 0, cs>>>(sim->cfg, sim->state, sim->globals, T, act, d_obs, d_rew, d_terminated, d_truncated, d_log, t);
-        else if (vis) wl_step_kernel<WL_TASK_VISUAL><<<grid, bs, 0, cs>>>(sim->cfg, sim->state, sim->globals, T, act, d_obs, d_rew, d_terminated, d_truncated, d_log, t);
-        else wl_step_kernel<WL_TASK_DRIFT><<<grid, bs, 0, cs>>>(sim->cfg, sim->state, sim->globals, T, act, d_obs, d_rew, d_terminated, d_truncated, d_log, t);
+        const int bs = pick_block(n), grid = (n + bs - 1) / bs + 1;
+        if (elev) launch_k(wl_step_kernel<WL_TASK_ELEVATION, 0>, grid, bs, 0, cs, sim->cfg, sim->state, sim->globals, T, act, d_obs, d_rew, d_terminated, d_truncated, d_log, t, sio0);
+        else if (vis) launch_k(wl_step_kernel<WL_TASK_VISUAL, 0>, grid, bs, 0, cs, sim->cfg, sim->state, sim->globals, T, act, d_obs, d_rew, d_terminated, d_truncated, d_log, t, sio0);
+        else launch_k(wl_step_kernel<WL_TASK_DRIFT, 0>, grid, bs, 0, cs, sim->cfg, sim->state, sim->globals, T, act, d_obs, d_rew, d_terminated, d_truncated, d_log, t, sio0);
     }
     WL_LAUNCH_CHECK(sim, "wl_step_kernel");
     if (elev) { if (int rc = launch_scan(sim, d_obs, cs)) return rc; }
@@ -1368,7 +1419,7 @@ int wl_step(wl_sim* sim, const float* d_action, float* d_obs, float* d_rew, uint
 template <int STAGE>
 static int launch_stage(wl_sim* sim, const float2* act, float* d_obs, float* d_rew, uint8_t* d_terminated, uint8_t* d_truncated,
                         float* d_log, uint32_t t, StageIO sio, cudaStream_t cs) {
-    const int n = sim->cfg.num_envs, bs = pick_block(n), grid = (n + bs - 1) / bs;
+    const int n = sim->cfg.num_envs, bs = pick_block(n), grid = (n + bs - 1) / bs + (STAGE == 2 ? 1 : 0);   // stage b: + the janitor CTA
     Terrain T{sim->hf};
     switch (sim->cfg.task) {
     case WL_TASK_ELEVATION:
@@ -1550,7 +1601,7 @@ int wl_act_step(wl_sim* sim, const float* d_obs_in, const float* d_policy_blob, 
         return fail(WL_EINVAL, "wl_act_step: policy blob must be 16-byte aligned, actions/mean 8-byte aligned");
     PolicyOffsets po;
     const int blob_floats = policy_offsets(sim->obs_dim, po.o);
-    const int n = sim->cfg.num_envs, grid = (n + WL_ACT_ENVS - 1) / WL_ACT_ENVS;
+    const int n = sim->cfg.num_envs, grid = (n + WL_ACT_ENVS - 1) / WL_ACT_ENVS + 1;      // + the janitor CTA
     const size_t smem = sizeof(float) * ((size_t)blob_floats + WL_ACT_ENVS * (WL_ACT_XS + WL_ACT_HS));
     Terrain T{sim->hf};
     cudaStream_t cs = (cudaStream_t)stream;
@@ -1562,9 +1613,9 @@ int wl_act_step(wl_sim* sim, const float* d_obs_in, const float* d_policy_blob, 
         attr_set = true;
     }
     if (sim->cfg.task == WL_TASK_VISUAL)
-        wl_act_step_quad_kernel<WL_TASK_VISUAL><<<grid, WL_ACT_THREADS, smem, cs>>>(sim->cfg, sim->state, sim->globals, T, d_obs_in, d_policy_blob, blob_floats, po, out, d_obs, d_rew, d_terminated, d_truncated, d_log, (uint32_t)step_counter, sim->obs_dim);
+        launch_k(wl_act_step_quad_kernel<WL_TASK_VISUAL>, grid, WL_ACT_THREADS, smem, cs, sim->cfg, sim->state, sim->globals, T, d_obs_in, d_policy_blob, blob_floats, po, out, d_obs, d_rew, d_terminated, d_truncated, d_log, (uint32_t)step_counter, sim->obs_dim);
     else
-        wl_act_step_quad_kernel<WL_TASK_DRIFT><<<grid, WL_ACT_THREADS, smem, cs>>>(sim->cfg, sim->state, sim->globals, T, d_obs_in, d_policy_blob, blob_floats, po, out, d_obs, d_rew, d_terminated, d_truncated, d_log, (uint32_t)step_counter, sim->obs_dim);
+        launch_k(wl_act_step_quad_kernel<WL_TASK_DRIFT>, grid, WL_ACT_THREADS, smem, cs, sim->cfg, sim->state, sim->globals, T, d_obs_in, d_policy_blob, blob_floats, po, out, d_obs, d_rew, d_terminated, d_truncated, d_log, (uint32_t)step_counter, sim->obs_dim);
     WL_LAUNCH_CHECK(sim, "wl_act_step_quad_kernel");
     return post_step(sim, step_counter, cs);
 }

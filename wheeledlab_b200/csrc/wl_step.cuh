@@ -351,8 +351,11 @@ __device__ __forceinline__ void physics_substep(const wl_config& c, const Terrai
                 (w[0].Tq.z + w[1].Tq.z) + (w[2].Tq.z + w[3].Tq.z)};
     } else {
         const int i = threadIdx.x & 3;
-        float sn = 0.0f, cs = 1.0f;
-        if (i >= 2) steer_step(c, steer_target[0], e.steer[0], e.steer_vel[0], sn, cs);   // lane-local copy of ITS joint
+        float sn, cs;
+        // every lane steps the joint it holds (rear lanes carry a copy of the left joint that is never stored): no divergent
+        // region inside the sub-step; rear wheels then take (sin, cos) = (0, 1)
+        steer_step(c, steer_target[0], e.steer[0], e.steer_vel[0], sn, cs);
+        sn = (i >= 2) ? sn : 0.0f; cs = (i >= 2) ? cs : 1.0f;
         WheelOut w = wheel_force<TASK>(c, T, k, R, b, vb, i, sn, cs, e.omega[0], wheel_target[0], eff_lo[0], eff_hi[0], e.kd[0],
                                        k.hI[0], k.idk[0], k.fxk[0], e.D[0], e.C[0]);
         e.omega[0] = w.omega;
@@ -640,30 +643,33 @@ __device__ __forceinline__ void blind_obs(const wl_config& c, const EnvState& e,
     for (int k = 0; k < 7; ++k) o2[k] = make_float2(o[2 * k], o[2 * k + 1]);
 }
 
-// quad version: lane k in {0,1,2} draws Philox block k (4 normals) and writes obs[4k..4k+3]; lane 3 writes the
-// last action.  `eu_k` = this lane's euler angle (lane0 roll, lane1 pitch, lane2 yaw), already wrapped.
-__device__ __forceinline__ void blind_obs_quad(const wl_config& c, const EnvState& e, int w, float eu_k, uint32_t gid, uint32_t t,
-                                               uint32_t stream, uint32_t sub0, float* __restrict__ obs, bool live) {
-    M3 R = rotmat(e.qw, e.qx, e.qy, e.qz);
-    V3 vb = rotT(R, e.v), wb = rotT(R, e.w);
-    float z0 = 0.0f, z1 = 0.0f, z2 = 0.0f, z3 = 0.0f;
+// quad version: lane k in {0,1,2} owns Philox block k (4 normals, drawn by quad_obs_noise at the TOP of the kernel, under
+// the shadow of the state loads) and writes obs[4k..4k+3]; lane 3 writes the last action.  `eu_k` = this lane's euler angle
+// (lane0 roll, lane1 pitch, lane2 yaw), already wrapped.
+__device__ __forceinline__ void quad_obs_noise(const wl_config& c, int w, uint32_t gid, uint32_t t, uint32_t stream, uint32_t sub0, float z[4]) {
+    z[0] = z[1] = z[2] = z[3] = 0.0f;
     if (c.enable_corruption) {
         uint4 r = philox4x32(c.seed, gid, t, stream, sub0 + (uint32_t)(w < 3 ? w : 0));
-        box_muller(r.x, r.y, z0, z1);
-        box_muller(r.z, r.w, z2, z3);
+        box_muller(r.x, r.y, z[0], z[1]);
+        box_muller(r.z, r.w, z[2], z[3]);
     }
+}
+__device__ __forceinline__ void blind_obs_quad(const wl_config& c, const EnvState& e, int w, float eu_k, const float z[4],
+                                               float* __restrict__ obs, bool live) {
+    M3 R = rotmat(e.qw, e.qx, e.qy, e.qz);
+    V3 vb = rotT(R, e.v), wb = rotT(R, e.w);
     const unsigned base = (threadIdx.x & 31u) & ~3u;
     float eu1 = __shfl_sync(0xffffffffu, eu_k, base + 1), eu2 = __shfl_sync(0xffffffffu, eu_k, base + 2);
     float b0, b1, b2, b3, s0, s1, s2, s3;
     if (w == 0) { b0 = e.p.x; b1 = e.p.y; b2 = e.p.z; b3 = eu_k; s0 = s1 = s2 = c.noise_std[0]; s3 = c.noise_std[1]; }
     else if (w == 1) { b0 = eu1; b1 = eu2; b2 = vb.x; b3 = vb.y; s0 = s1 = c.noise_std[1]; s2 = s3 = c.noise_std[2]; }
     else if (w == 2) { b0 = vb.z; b1 = wb.x; b2 = wb.y; b3 = wb.z; s0 = c.noise_std[2]; s1 = s2 = s3 = c.noise_std[3]; }
-    else { b0 = r_clamp(e.action[0], -1.0f, 1.0f); b1 = r_clamp(e.action[1], -1.0f, 1.0f); b2 = b3 = 0.0f; s0 = s1 = s2 = s3 = 0.0f; z0 = z1 = 0.0f; }
+    else { b0 = r_clamp(e.action[0], -1.0f, 1.0f); b1 = r_clamp(e.action[1], -1.0f, 1.0f); b2 = b3 = 0.0f; s0 = s1 = s2 = s3 = 0.0f; }
     float2* o2 = reinterpret_cast<float2*>(obs + 4 * w);
     if (!live) return;
     if (w < 3) {
-        o2[0] = make_float2(b0 + s0 * z0, b1 + s1 * z1);
-        o2[1] = make_float2(b2 + s2 * z2, b3 + s3 * z3);
+        o2[0] = make_float2(b0 + s0 * z[0], b1 + s1 * z[1]);
+        o2[1] = make_float2(b2 + s2 * z[2], b3 + s3 * z[3]);
     } else {
         o2[0] = make_float2(b0, b1);
     }

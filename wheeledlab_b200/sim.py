@@ -97,8 +97,32 @@ class WheeledSim:
         check(lib.wl_set_seed(self._h, seed), "wl_set_seed")
         self.cfg.seed = seed
 
+    @staticmethod
+    def device_counter_plus(k: int) -> int:
+        """step_counter value meaning "the counter base kept in device memory + k" (WL_DEVICE_COUNTER_PLUS)."""
+        return -1 - k
+
     def set_step_counter(self, value: int):
         check(lib.wl_set_step_counter(self._h, value, _stream_ptr(self.device)), "wl_set_step_counter")
+
+    def advance_counter(self, k: int):
+        """device counter base += k (a 1-thread kernel: capturable as the last node of a K-step graph)."""
+        check(lib.wl_advance_counter(self._h, k, _stream_ptr(self.device)), "wl_advance_counter")
+
+    def note_device_counter(self, value: int):
+        """Tell the host mirror what the device counter base is after graph replays the library did not see."""
+        check(lib.wl_note_device_counter(self._h, value), "wl_note_device_counter")
+
+    def flush_log(self):
+        """Publish the extras["log"] row of the most recent step now (otherwise the next step's launch does it)."""
+        check(lib.wl_log_flush(self._h, _stream_ptr(self.device)), "wl_log_flush")
+
+    @property
+    def rew_weight(self) -> torch.Tensor:
+        """Live reward weights (float32[8] view into the state buffer): what the next step will use / the last one used.
+        The curriculum moves them between two slots on the device; the handle knows which one is current."""
+        off = (int(lib.wl_reward_weights(self._h)) - self._buf.data_ptr()) // 4
+        return self._buf[off: off + 8]
 
     def step(self, action: torch.Tensor, step_counter: int = -1, out=None, log: torch.Tensor | None = None):
         """action [N,2] f32 (device, contiguous) -> (obs [N,D] f32, rew [N] f32, terminated [N] u8, truncated [N] u8).

@@ -281,6 +281,7 @@ def drift_task(num_envs: int = 1024, seed: int = 42, env_id_offset: int = 0, ran
     cfg.tlgr_ang_vel_thresh = 1.0                                      # :270-274
     cfg.energy_straight = STRAIGHT                                     # :276-280
     reward_names = ["side_slip", "vel", "progress", "tlgr", "turn_energy", "cross_track", "term_pens"]
+    cfg.term_enable = 0b11                                             # time_out, out_of_bounds (:351-362)
     cfg.num_rew_terms = len(reward_names)
     _set(cfg.rew_weight, (10.0, -5.0, 40.0, 0.0, 20.0, -50.0, -5000.0))  # :243-299
     curriculum = [                                                     # :306-337
@@ -354,6 +355,7 @@ def elevation_task(num_envs: int = 1024, seed: int = 42, env_id_offset: int = 0,
     cfg.elev_fall_vel = 0.10                                           # :251
     cfg.elev_plane_z = 0.19                                            # :168
     reward_names = ["vel_towards_goal", "height_z", "falling_penalty", "termination_penalty"]   # :283-305
+    cfg.term_enable = 0b11111                                          # time_out, cart_out_of_bounds, stuck, rollover, at_goal (:349-376)
     cfg.num_rew_terms = len(reward_names)
     _set(cfg.rew_weight, (200.0, 5000.0, 0.0, -200.0))
     curriculum = [                                                     # :311-333
@@ -442,6 +444,7 @@ def visual_task(num_envs: int = 1024, seed: int = 42, env_id_offset: int = 0, tr
     _set(cfg.vis_aug_sigma, (0.1, 5.0))                                # GaussianBlur(5, sigma=(0.1, 5.0)), observations.py:23
     cam_floats = cfg.vis_cam_w * (cfg.vis_cam_h - cfg.vis_cam_row0) if cfg.vis_cam else 0
     reward_names = ["traversablility", "vel_rew"]                     # :376-387 (sic)
+    cfg.term_enable = 0b11                                             # time_out, out_range (:404-409)
     cfg.num_rew_terms = len(reward_names)
     _set(cfg.rew_weight, (5.0, 7.0))
     spec = TaskSpec(name="visual", cfg=cfg, reward_names=reward_names,
