@@ -501,7 +501,7 @@ def run_ours(args):
                        "actions": "U[-1,1]^2 philox(seed,env,step)",
                        "l2": f"inputs larger than L2, no flush kernel: {M} independent {E}-env sets ({M * set_bytes / 1e6:.0f} MB of state + "
                              f"parameters) stepped round-robin, every step writes a fresh rollout-slab row ({n_slabs} x {slab_bytes / 1e6:.0f} MB)",
-                       "parallelism": f"env-shard x{world}", "timing": "2 CUDA events around the K back-to-back steps (PDL launches)"},
+                       "parallelism": f"env-shard x{world}", "timing": "2 CUDA events around the K back-to-back steps"},
             "clocks": clocks,
             "e2e": {"value": total_envs * K / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": E * 8,
                     "d2h_bytes_per_step": E * (6 + 4 * sim0.obs_dim), "ms_per_step": e2e_ms / K, "transport": best,

@@ -331,6 +331,8 @@ typedef struct wl_globals {
     float acc[3][16];                      /* row t % 3, step t: [0..7] sum over reset envs of their episode sums,       */
                                            /* [8] #reset, [9+j] #envs whose termination term j fired                    */
     float* log_ptr[3];                     /* d_log pointer registered by step t (row t % 3); written one launch later   */
+    float last_log[16];                    /* the most recent log row of a step that reset >= 1 env: IsaacLab's extras["log"] */
+                                           /* persists until the next _reset_idx, so steps without a reset repeat it      */
     uint32_t step_base;                    /* device-resident base of common_step_counter (CUDA-graph replay)            */
     uint32_t ticket;                       /* CTAs finished (wl_rollout only: its K-step launch ends with a last-CTA pass)  */
     uint32_t curr_applied_t;               /* counter value whose curriculum boundary the host path already applied in place  */
@@ -359,6 +361,9 @@ int wl_note_device_counter(wl_sim* sim, int64_t value);
 int wl_log_flush(wl_sim* sim, void* stream);
 /* live reward weights (what the next step will use): device pointer to WL_MAX_REW_TERMS floats inside the state buffer */
 float* wl_reward_weights(wl_sim* sim);
+/* optional per-env output of wl_step / wl_step_host*: one byte of termination-term bits per env (bit j = term j fired this
+ * step, order below) -- what TerminationManager.get_term(name) needs; NULL (default) disables it */
+int wl_set_term_bits(wl_sim* sim, uint8_t* d_term_bits);
 /* ManagerBasedEnv.seed(): re-key the counter-based generator for all later launches (startup draws are not repeated) */
 int wl_set_seed(wl_sim* sim, uint64_t seed);
 /* fill the d_* derived fields from the primary ones (idempotent). */
@@ -397,7 +402,8 @@ int wl_reset(wl_sim* sim, const int64_t* d_env_ids, int32_t n_ids, int64_t step_
 #define WL_DEVICE_COUNTER_PLUS(k) (-1 - (int64_t)(k))
 /* d_log: optional float[WL_LOG_FLOATS]: mean over the envs reset in this step of each reward term's episode sum
  * divided by max_episode_length_s (RewardManager.reset -> extras["log"]), then the reset / terminated / time-out
- * counts.  No extra kernel, no host sync, no grid-wide sync: the row of step t is written by the NEXT launch on the
+ * counts; a step in which no env reset repeats the row of the last step that did (the reference's extras["log"] is only
+ * rebuilt inside _reset_idx).  No extra kernel, no host sync, no grid-wide sync: the row of step t is written by the NEXT launch on the
  * handle (the step after it, or wl_log_flush), i.e. it is valid once that launch has completed. */
 int wl_step(wl_sim* sim, const float* d_action, float* d_obs, float* d_rew, uint8_t* d_terminated,
             uint8_t* d_truncated, float* d_log, int64_t step_counter, void* stream);

@@ -1115,9 +1115,11 @@ int wlo_step(wlo_sim* s, const float* action, float* obs, float* rew, uint8_t* t
             for (int j = 0; j < WL_MAX_TERM_TERMS; ++j) tot.n_term[j] += lg.n_term[j];
         }
     }
-    for (int k = 0; k < WL_MAX_REW_TERMS; ++k) s->log_sum[k] = tot.sum[k];
-    s->log_term[0] = tot.n_reset;
-    for (int j = 0; j < WL_MAX_TERM_TERMS; ++j) s->log_term[1 + j] = tot.n_term[j];
+    if (tot.any) {      /* extras["log"] is rebuilt inside _reset_idx only: a step without a reset keeps the previous row */
+        for (int k = 0; k < WL_MAX_REW_TERMS; ++k) s->log_sum[k] = tot.sum[k];
+        s->log_term[0] = tot.n_reset;
+        for (int j = 0; j < WL_MAX_TERM_TERMS; ++j) s->log_term[1 + j] = tot.n_term[j];
+    }
     s->any_reset_last = tot.any;
     /* common_step_counter += 1, then the curriculum terms (curriculums.py:23-35), only if >= 1 env reset this step */
     {
@@ -1236,6 +1238,8 @@ void wlo_get_log(const wlo_sim* s, double* out) {
     for (int k = 0; k < WL_MAX_REW_TERMS; ++k) out[k] = s->log_sum[k] / (cnt * (double)s->cfg.episode_length_s);
     for (int j = 0; j < 8; ++j) out[8 + j] = s->log_term[j];
 }
+
+int wlo_any_reset_last(const wlo_sim* s) { return s->any_reset_last; }
 
 /* ---- unit-level hooks for golden-vector and det-math tests -------------------- */
 int wlo_detmath(int32_t op, const float* in, const float* in2, float* out, int32_t n) {

@@ -33,6 +33,7 @@ def _load(name):
     lib.wlo_get_weights.argtypes = [vp, vp]
     lib.wlo_set_weights.argtypes = [vp, vp]
     lib.wlo_get_log.argtypes = [vp, vp]
+    lib.wlo_any_reset_last.argtypes = [vp]
     lib.wlo_detmath.argtypes = [i32, vp, vp, vp, i32]
     lib.wlo_philox.argtypes = [u64, u32, u32, u32, u32, vp, i32]
     lib.wlo_action_map.argtypes = [vp, vp, vp, vp, i32]
@@ -189,6 +190,10 @@ class Oracle:
         out = np.zeros(npix, np.uint8)
         assert self.lib.wlo_camera_render(self._h, li, _p(out)) == 0
         return out
+
+    def any_reset(self) -> bool:
+        """>= 1 env reset in the most recent step (the log row itself persists over steps without a reset)."""
+        return bool(self.lib.wlo_any_reset_last(self._h))
 
     def log(self):
         out = np.zeros(16, np.float64)

@@ -197,7 +197,7 @@ def test_curriculum_on_device_matches_oracle():
         assert np.array_equal(_bits(rew.cpu().numpy()), _bits(o_rew)), t
         if (t + 1) % 250 == 0:                       # episode boundary of the GLOBAL counter
             E = (t + 1) // 250
-            if orc.log()[8] > 0:                     # the reference only evaluates the terms when >= 1 env reset this step
+            if orc.any_reset():                      # the reference only evaluates the terms when >= 1 env reset this step
                 exp[0] += 20.0                       # every episode
                 if (E + 1) % 2 == 0:
                     exp[6] += -1000.0                # every 2nd episode
@@ -968,3 +968,28 @@ def test_gym_make_through_the_registry_and_the_reference_smoke_loop():
             assert obs["policy"].shape == (48, env.spec_obs_dim if hasattr(env, "spec_obs_dim") else spec.obs_dim) and torch.isfinite(obs["policy"]).all()
             assert rew.shape == (48,) and term.dtype == torch.bool and "log" in info
         env.close()
+
+
+def test_elevation_per_term_termination_masks():
+    """TerminationManager.get_term(name) returns the term's OWN mask: the union of the non-time-out masks is
+    `terminated`, time_out is `truncated`, and each mask's population equals the episode-log count of that term."""
+    _need_gpu()
+    import wheeledlab_b200 as wl
+    env = wl.make("Isaac-MushrElevationRL-v0", num_envs=512, seed=3)
+    env.reset()
+    names = [n for n, _ in env.spec.termination_names]
+    assert names == ["time_out", "cart_out_of_bounds", "stuck", "rollover", "at_goal"]
+    seen = {n: 0 for n in names}
+    for t in range(230):
+        obs, rew, term, trunc, info = env.step(env.sim.synth_actions(t))
+        m = {n: env.termination_manager.get_term(n) for n in names}
+        assert torch.equal(trunc, m["time_out"])
+        assert torch.equal(term, m["cart_out_of_bounds"] | m["stuck"] | m["rollover"] | m["at_goal"])
+        if bool((term | trunc).any()):
+            for n in names:
+                assert int(info["log"]["Episode_Termination/" + n].item()) == int(m[n].sum().item()), (t, n)
+        for n in names:
+            seen[n] += int(m[n].sum().item())
+    assert seen["time_out"] > 0 and seen["stuck"] > 0 and seen["stuck"] != seen["time_out"]
+    with pytest.raises(ValueError):
+        env.termination_manager.get_term("no_such_term")

@@ -25,6 +25,8 @@ struct wl_sim {
     int64_t launches;
     int64_t last_t;         // counter of the most recent step launched through this handle (-1: none); host mirror
     int64_t base_host;      // host mirror of wl_globals.step_base
+    uint8_t* term_bits;     // optional per-env termination-term bits output of wl_step (wl_set_term_bits)
+    int device;             // CUDA device ordinal the handle lives on
     int obs_dim;
     int variant;            // 0 auto, 1 thread-per-env, 4 quad-per-env
     CUtensorMap tmap;       // 2-D tensor map over the height-field (elevation task)
@@ -42,6 +44,10 @@ static int cuda_check(cudaError_t e, const char* what) {
     return fail(WL_ECUDA, std::string(what) + ": " + cudaGetErrorString(e));
 }
 
+static inline void ensure_device(const wl_sim* sim) {
+    int cur = -1;
+    if (cudaGetDevice(&cur) == cudaSuccess && cur != sim->device) cudaSetDevice(sim->device);   // launches go to the handle's device
+}
 static inline size_t groups_bytes(int n) { return (size_t)WL_NUM_GROUPS * (size_t)n * 16u; }
 static inline size_t align256(size_t x) { return (x + 255u) & ~(size_t)255u; }
 
@@ -86,7 +92,12 @@ __device__ __forceinline__ void publish_log_row(const wl_config& c, wl_globals* 
     const float v = (lane < 16) ? __ldcg(&gl->acc[row][lane]) : 0.0f;
     const float cnt = __shfl_sync(0xffffffffu, v, 8);
     float* lp = gl->log_ptr[row];
-    if (lp != nullptr && lane < 16) lp[lane] = (lane < WL_MAX_REW_TERMS) ? v / (r_max(cnt, 1.0f) * c.episode_length_s) : v;
+    float out = (lane < WL_MAX_REW_TERMS) ? v / (r_max(cnt, 1.0f) * c.episode_length_s) : v;
+    if (lane < 16) {
+        if (cnt > 0.0f) gl->last_log[lane] = out;            // extras["log"] persists until the next step that resets an env
+        else out = gl->last_log[lane];
+        if (lp != nullptr) lp[lane] = out;
+    }
 }
 // The janitor: ONE warp of the launch -- the first warp of an EXTRA CTA appended to the grid (blockIdx.x == gridDim.x - 1)
 // that owns no envs, so that no env warp starts its dependent chain late.
@@ -226,6 +237,7 @@ wl_step_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st, wl_
         }
         terminated_o[i] = (tmask & ~1u) ? 1 : 0;
         truncated_o[i] = (tmask & 1u) ? 1 : 0;
+        if (STAGE == 0 && sio.tmask != nullptr) sio.tmask[i] = (uint8_t)tmask;      // per-term masks (wl_set_term_bits)
         done = tmask != 0u;
     }
     if (STAGE == 1) return;
@@ -264,7 +276,7 @@ __device__ __forceinline__ void quad_env_step(const wl_config& c, const Terrain&
                                               const float wts[WL_MAX_REW_TERMS], EnvState& e, int i, int w, bool live, uint32_t gid,
                                               unsigned base, uint32_t t, float2 a, const float znoise[4], float* __restrict__ obs_row,
                                               float* __restrict__ rew, uint8_t* __restrict__ terminated_o,
-                                              uint8_t* __restrict__ truncated_o) {
+                                              uint8_t* __restrict__ truncated_o, uint8_t* __restrict__ term_bits = nullptr) {
     constexpr bool ELEV = (TASK == WL_TASK_ELEVATION), VIS = (TASK == WL_TASK_VISUAL);
     // A. action manager (redundant in the 4 lanes)
     e.prev_action[0] = e.action[0]; e.prev_action[1] = e.action[1];
@@ -321,7 +333,10 @@ __device__ __forceinline__ void quad_env_step(const wl_config& c, const Terrain&
         }
     }
     const bool done = tmask != 0u;
-    if (live && w == 0) { rew[i] = total; terminated_o[i] = (tmask & ~1u) ? 1 : 0; truncated_o[i] = (tmask & 1u) ? 1 : 0; }
+    if (live && w == 0) {
+        rew[i] = total; terminated_o[i] = (tmask & ~1u) ? 1 : 0; truncated_o[i] = (tmask & 1u) ? 1 : 0;
+        if (term_bits != nullptr) term_bits[i] = (uint8_t)tmask;      // per-term masks for TerminationManager.get_term
+    }
     // F. per-step episode log: one contribution per env (lane 0 of each live quad), then auto-reset
     log_accumulate(acc_row, done && live && (w == 0), tmask, e.sums);
     if (done) {
@@ -368,7 +383,8 @@ template <int TASK>
 __global__ void __launch_bounds__(128)
 wl_step_quad_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st, wl_globals* __restrict__ gl, Terrain T,
                     const float2* __restrict__ action, float* __restrict__ obs, float* __restrict__ rew,
-                    uint8_t* __restrict__ terminated_o, uint8_t* __restrict__ truncated_o, float* __restrict__ d_log, uint32_t t_arg) {
+                    uint8_t* __restrict__ terminated_o, uint8_t* __restrict__ truncated_o, float* __restrict__ d_log, uint32_t t_arg,
+                    uint8_t* __restrict__ term_bits) {
     constexpr bool ELEV = (TASK == WL_TASK_ELEVATION), VIS = (TASK == WL_TASK_VISUAL);
     pdl_trigger();
     const VisualMap vm = VIS ? visual_map(c, T.hf) : VisualMap{nullptr, nullptr};
@@ -394,7 +410,7 @@ wl_step_quad_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st
     float zn[4];
     if (!ELEV && !VIS) quad_obs_noise(c, w, gid, t, RNG_OBS, 0u, zn); else zn[0] = zn[1] = zn[2] = zn[3] = 0.0f;
     const int od = ELEV ? WL_OBS_DIM_ELEV : VIS ? WL_OBS_DIM_VISUAL + vis_cam_floats(c) : WL_OBS_DIM_BLIND;
-    quad_env_step<TASK>(c, T, vm, gl->acc[t % 3u], wts, e, i, w, live, gid, base, t, a, zn, obs + (size_t)od * ii, rew, terminated_o, truncated_o);
+    quad_env_step<TASK>(c, T, vm, gl->acc[t % 3u], wts, e, i, w, live, gid, base, t, a, zn, obs + (size_t)od * ii, rew, terminated_o, truncated_o, term_bits);
     if (live) store_env_quad(st, n, i, w, e, ELEV);
 }
 
@@ -650,8 +666,13 @@ wl_rollout_quad_kernel(const __grid_constant__ wl_config c, float4* __restrict__
     for (int k = 0; k < K; ++k) {
         float* row = d_log + (size_t)k * WL_LOG_FLOATS;
         const float cnt = __ldcg(&row[8]);
-        const float denom = r_max(cnt, 1.0f) * c.episode_length_s;
-        for (int q = 0; q < WL_MAX_REW_TERMS; ++q) row[q] = __ldcg(&row[q]) / denom;
+        if (cnt > 0.0f) {
+            const float denom = cnt * c.episode_length_s;
+            for (int q = 0; q < WL_MAX_REW_TERMS; ++q) row[q] = __ldcg(&row[q]) / denom;
+            for (int q = 0; q < 16; ++q) gl->last_log[q] = row[q];
+        } else {
+            for (int q = 0; q < 16; ++q) row[q] = gl->last_log[q];         // no reset in this step: the previous row persists
+        }
         last_cnt = cnt;
     }
     const uint32_t tl = t0 + (uint32_t)K - 1u;
@@ -1109,7 +1130,10 @@ wl_camera_kernel(const __grid_constant__ wl_config c, const float4* __restrict__
 // launch geometry: spread small N over all 148 SMs, use fatter CTAs once the chip is full
 // ---------------------------------------------------------------------------------------
 // launch with (or without) the programmatic-dependent-launch attribute
-static bool g_pdl = (getenv("WL_PDL") == nullptr) || (atoi(getenv("WL_PDL")) != 0);
+// (measured on B200, 4096-env Drift step, back-to-back launches: 9.0 us/step with the attribute vs 6.65 us without --
+// profiles/r02_kexp_c_pdl.jsonl -- the dependent grid's early-resident CTAs cost more than the launch gap they hide; the
+// attribute is therefore OFF unless WL_PDL=1)
+static bool g_pdl = (getenv("WL_PDL") != nullptr) && (atoi(getenv("WL_PDL")) != 0);
 template <typename... KArgs, typename... Args>
 static void launch_k(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t cs, Args... args) {
     cudaLaunchConfig_t lc;
@@ -1178,6 +1202,7 @@ int wl_set_step_counter(wl_sim* sim, int64_t value, void* stream) {
 }
 int wl_advance_counter(wl_sim* sim, int32_t K, void* stream) {
     if (!sim || K < 0) return fail(WL_EINVAL, "wl_advance_counter: bad argument");
+    ensure_device(sim);
     wl_advance_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(sim->globals, (uint32_t)K);
     sim->launches++;
     sim->base_host += K;
@@ -1191,6 +1216,7 @@ int wl_note_device_counter(wl_sim* sim, int64_t value) {
 }
 int wl_log_flush(wl_sim* sim, void* stream) {
     if (!sim) return fail(WL_EINVAL, "wl_log_flush: null handle");
+    ensure_device(sim);
     if (sim->last_t < 0) return WL_OK;
     wl_flush_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(sim->cfg, sim->globals, (uint32_t)(sim->last_t + 1));
     sim->launches++;
@@ -1198,6 +1224,11 @@ int wl_log_flush(wl_sim* sim, void* stream) {
 }
 float* wl_reward_weights(wl_sim* sim) { return sim ? sim->globals->rew_weight[(uint32_t)sim->last_t & 1u] : nullptr; }
 
+int wl_set_term_bits(wl_sim* sim, uint8_t* d_term_bits) {
+    if (!sim) return fail(WL_EINVAL, "wl_set_term_bits: null handle");
+    sim->term_bits = d_term_bits;
+    return WL_OK;
+}
 int wl_set_seed(wl_sim* sim, uint64_t seed) {
     if (!sim) return fail(WL_EINVAL, "wl_set_seed: null handle");
     sim->cfg.seed = seed;
@@ -1282,6 +1313,8 @@ int wl_create(const wl_config* cfg, void* d_state, size_t state_bytes, const flo
     s->launches = 0;
     s->last_t = -1;
     s->base_host = 0;
+    s->term_bits = nullptr;
+    cudaGetDevice(&s->device);
     s->variant = 0;
     s->has_tmap = false;
     s->scan_tma = true;
@@ -1341,6 +1374,7 @@ int64_t wl_launch_count(const wl_sim* sim) { return sim ? sim->launches : 0; }
 // Steps are issued with consecutive counters (the janitor protocol, see wl_globals).  Resolve this launch's counter on the host
 // mirror; on a jump publish the pending log row, carry the weights to the slot the step will read and clear the rows.
 static int prep_step(wl_sim* sim, int64_t step_counter, int32_t n_steps, cudaStream_t cs) {
+    ensure_device(sim);
     const int64_t t = step_counter >= 0 ? step_counter : sim->base_host + (-1 - step_counter);
     if (t >= ((int64_t)1 << 31) - n_steps) return fail(WL_EINVAL, "step counter out of range (< 2^31)");
     if (t != sim->last_t + 1) {
@@ -1365,6 +1399,7 @@ extern "C" {
 
 int wl_startup(wl_sim* sim, void* stream) {
     if (!sim) return fail(WL_EINVAL, "wl_startup: null handle");
+    ensure_device(sim);
     const int n = sim->cfg.num_envs, bs = 128;
     wl_startup_kernel<<<(n + bs - 1) / bs, bs, 0, (cudaStream_t)stream>>>(sim->cfg, sim->state);
     WL_LAUNCH_CHECK(sim, "wl_startup_kernel");
@@ -1373,6 +1408,7 @@ int wl_startup(wl_sim* sim, void* stream) {
 
 int wl_reset(wl_sim* sim, const int64_t* d_env_ids, int32_t n_ids, int64_t step_counter, void* stream) {
     if (!sim) return fail(WL_EINVAL, "wl_reset: null handle");
+    ensure_device(sim);
     const int n = d_env_ids ? n_ids : sim->cfg.num_envs;
     if (n <= 0) return WL_OK;
     const int bs = 128;
@@ -1393,15 +1429,15 @@ int wl_step(wl_sim* sim, const float* d_action, float* d_obs, float* d_rew, uint
     const uint32_t t = (uint32_t)step_counter;               // negative (device base + k) stays encoded: see decode_step
     if (int rc = prep_step(sim, step_counter, 1, cs)) return rc;
     const bool elev = sim->cfg.task == WL_TASK_ELEVATION, vis = sim->cfg.task == WL_TASK_VISUAL;
-    StageIO sio0{nullptr, nullptr, nullptr};
+    StageIO sio0{sim->term_bits, nullptr, nullptr};
     if (variant == 4) {
 #ifndef WL_QUAD_BS
 #define WL_QUAD_BS 32
 #endif
         const int bs = WL_QUAD_BS, threads = 4 * n, grid = (threads + bs - 1) / bs + 1;      // + the janitor CTA
-        if (elev) launch_k(wl_step_quad_kernel<WL_TASK_ELEVATION>, grid, bs, 0, cs, sim->cfg, sim->state, sim->globals, T, act, d_obs, d_rew, d_terminated, d_truncated, d_log, t);
-        else if (vis) launch_k(wl_step_quad_kernel<WL_TASK_VISUAL>, grid, bs, 0, cs, sim->cfg, sim->state, sim->globals, T, act, d_obs, d_rew, d_terminated, d_truncated, d_log, t);
-        else launch_k(wl_step_quad_kernel<WL_TASK_DRIFT>, grid, bs, 0, cs, sim->cfg, sim->state, sim->globals, T, act, d_obs, d_rew, d_terminated, d_truncated, d_log, t);
+        if (elev) launch_k(wl_step_quad_kernel<WL_TASK_ELEVATION>, grid, bs, 0, cs, sim->cfg, sim->state, sim->globals, T, act, d_obs, d_rew, d_terminated, d_truncated, d_log, t, sim->term_bits);
+        else if (vis) launch_k(wl_step_quad_kernel<WL_TASK_VISUAL>, grid, bs, 0, cs, sim->cfg, sim->state, sim->globals, T, act, d_obs, d_rew, d_terminated, d_truncated, d_log, t, sim->term_bits);
+        else launch_k(wl_step_quad_kernel<WL_TASK_DRIFT>, grid, bs, 0, cs, sim->cfg, sim->state, sim->globals, T, act, d_obs, d_rew, d_terminated, d_truncated, d_log, t, sim->term_bits);
     } else {
         const int bs = pick_block(n), grid = (n + bs - 1) / bs + 1;
         if (elev) launch_k(wl_step_kernel<WL_TASK_ELEVATION, 0>, grid, bs, 0, cs, sim->cfg, sim->state, sim->globals, T, act, d_obs, d_rew, d_terminated, d_truncated, d_log, t, sio0);
@@ -1529,6 +1565,7 @@ int wl_step_host_zero_copy(wl_sim* sim, const float* h_action, float* d_obs, flo
 
 int wl_observe(wl_sim* sim, float* d_obs, int64_t step_counter, int32_t call_idx, void* stream) {
     if (!sim || !d_obs) return fail(WL_EINVAL, "wl_observe: null argument");
+    ensure_device(sim);
     const int n = sim->cfg.num_envs, bs = 128;
     wl_observe_kernel<<<(n + bs - 1) / bs, bs, 0, (cudaStream_t)stream>>>(sim->cfg, sim->state, d_obs, (uint32_t)step_counter,
                                                                          (uint32_t)call_idx);
@@ -1541,6 +1578,7 @@ int wl_observe(wl_sim* sim, float* d_obs, int64_t step_counter, int32_t call_idx
 
 int wl_camera(wl_sim* sim, float* d_obs, int64_t step_counter, const float* d_aug, void* stream) {
     if (!sim || !d_obs) return fail(WL_EINVAL, "wl_camera: null argument");
+    ensure_device(sim);
     if (sim->cfg.task != WL_TASK_VISUAL || !sim->cfg.vis_cam) return fail(WL_EUNSUPPORTED, "wl_camera: the handle has no camera term");
     return launch_camera(sim, d_obs, (uint32_t)step_counter, RNG_CAM, 0u, d_aug, (cudaStream_t)stream);
 }
@@ -1548,6 +1586,7 @@ int wl_camera(wl_sim* sim, float* d_obs, int64_t step_counter, const float* d_au
 int wl_curriculum(wl_sim* sim, int32_t n_terms, const int32_t* slots, const float* increases, uint32_t fire_mask,
                   void* stream) {
     if (!sim) return fail(WL_EINVAL, "wl_curriculum: null handle");
+    ensure_device(sim);
     if (n_terms < 0 || n_terms > WL_MAX_REW_TERMS) return fail(WL_EINVAL, "wl_curriculum: n_terms");
     if (n_terms == 0 || fire_mask == 0) return WL_OK;
     CurrArgs a; memset(&a, 0, sizeof a);
@@ -1565,6 +1604,7 @@ int wl_curriculum(wl_sim* sim, int32_t n_terms, const int32_t* slots, const floa
 
 int wl_synth_actions(wl_sim* sim, float* d_action, int64_t step_counter, int32_t dist, void* stream) {
     if (!sim || !d_action) return fail(WL_EINVAL, "wl_synth_actions: null argument");
+    ensure_device(sim);
     const int n = sim->cfg.num_envs, bs = 128;
     wl_synth_actions_kernel<<<(n + bs - 1) / bs, bs, 0, (cudaStream_t)stream>>>(sim->cfg, sim->globals, reinterpret_cast<float2*>(d_action),
                                                                                (uint32_t)step_counter, dist);
@@ -1574,6 +1614,7 @@ int wl_synth_actions(wl_sim* sim, float* d_action, int64_t step_counter, int32_t
 
 int wl_derive_suspension(wl_sim* sim, float* d_susp_pos, float* d_susp_vel, void* stream) {
     if (!sim || !d_susp_pos || !d_susp_vel) return fail(WL_EINVAL, "wl_derive_suspension: null argument");
+    ensure_device(sim);
     if (((uintptr_t)d_susp_pos & 15u) || ((uintptr_t)d_susp_vel & 15u)) return fail(WL_EINVAL, "wl_derive_suspension: outputs must be 16-byte aligned");
     const int n = sim->cfg.num_envs, bs = 128;
     Terrain T{sim->hf};
@@ -1606,11 +1647,11 @@ int wl_act_step(wl_sim* sim, const float* d_obs_in, const float* d_policy_blob, 
     Terrain T{sim->hf};
     cudaStream_t cs = (cudaStream_t)stream;
     if (int rc = prep_step(sim, step_counter, 1, cs)) return rc;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {false};                       // the attribute is per device
+    if (sim->device >= 0 && sim->device < 64 && !attr_set[sim->device]) {
         cudaFuncSetAttribute(wl_act_step_quad_kernel<WL_TASK_VISUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
         cudaFuncSetAttribute(wl_act_step_quad_kernel<WL_TASK_DRIFT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-        attr_set = true;
+        attr_set[sim->device] = true;
     }
     if (sim->cfg.task == WL_TASK_VISUAL)
         launch_k(wl_act_step_quad_kernel<WL_TASK_VISUAL>, grid, WL_ACT_THREADS, smem, cs, sim->cfg, sim->state, sim->globals, T, d_obs_in, d_policy_blob, blob_floats, po, out, d_obs, d_rew, d_terminated, d_truncated, d_log, (uint32_t)step_counter, sim->obs_dim);

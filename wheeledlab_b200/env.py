@@ -126,9 +126,22 @@ class TerminationManager:
         return self.terminated | self.time_outs
 
     def get_term(self, name):
-        for n, is_to in self._env.spec.termination_names:
+        """The term's OWN mask for the last step (IsaacLab TerminationManager.get_term), not the union: from the per-term bits
+        the step kernel writes when the task has more than one non-time-out term (Elevation: cart_out_of_bounds, stuck,
+        rollover, at_goal); host-side (Python) terms keep their own masks."""
+        env = self._env
+        if name in getattr(env, "_py_term_masks", {}):
+            return env._py_term_masks[name]
+        names = env.spec.termination_names
+        for j, (n, is_to) in enumerate(names):
             if n == name:
-                return self.time_outs if is_to else self.terminated
+                bits = getattr(env, "_term_bits_staged", None) if (env._py_rewards or env._py_terms) else getattr(env, "_term_bits", None)
+                if bits is not None:
+                    return ((bits >> j) & 1).to(torch.bool)
+                others = [m for m, to in names if to == is_to]
+                if len(others) == 1:                       # the only term of its kind: its mask is the union
+                    return self.time_outs if is_to else self.terminated
+                raise RuntimeError(f"termination term {name!r}: per-term masks are not being recorded for this env")
         raise ValueError(f"Termination term '{name}' not found.")
 
 
@@ -255,7 +268,7 @@ class ManagerBasedRLEnv:
     metadata = {"render_modes": [None, "human", "rgb_array"], "isaac_sim_version": "b200-native"}
 
     def __init__(self, cfg: TaskSpec | str = "Isaac-MushrDriftRL-v0", render_mode=None, device="cuda:0", **task_kw):
-        self.spec: TaskSpec = make_task(cfg, **task_kw) if isinstance(cfg, str) else cfg
+        self._task_spec: TaskSpec = make_task(cfg, **task_kw) if isinstance(cfg, str) else cfg
         self.cfg = SimpleNamespace(is_finite_horizon=False, seed=int(self.spec.cfg.seed), spec=self.spec)
         self.render_mode = render_mode
         self.device = str(torch.device(device))
@@ -295,11 +308,31 @@ class ManagerBasedRLEnv:
             self.add_reward_term(name, func, weight, params)
         for name, func, time_out, params in self.spec.python_termination_terms:
             self.add_termination_term(name, func, time_out, params)
+        # per-term termination masks (TerminationManager.get_term): recorded by the step kernel when a union is not enough
+        self._term_bits = None
+        if sum(1 for _, to in self.spec.termination_names if not to) > 1:
+            import ctypes as C
+            from ._lib import check, lib
+            self._term_bits = torch.zeros(self.num_envs, dtype=torch.uint8, device=self.device)
+            check(lib.wl_set_term_bits(self.sim._h, C.c_void_p(self._term_bits.data_ptr())), "wl_set_term_bits")
         # event_manager.apply(mode="startup")
         self.sim.startup()
         self._needs_reset = True
 
     # -- gym surface ---------------------------------------------------------------------------
+    @property
+    def spec(self) -> TaskSpec:
+        """The task description (TaskSpec).  gymnasium's make() assigns ITS EnvSpec to `env.spec`: that one is kept as
+        `gym_spec` so that the assignment cannot clobber the task description the env works from."""
+        return self._task_spec
+
+    @spec.setter
+    def spec(self, value):
+        if isinstance(value, TaskSpec):
+            self._task_spec = value
+        else:
+            self.gym_spec = value
+
     @property
     def unwrapped(self):
         return self
@@ -393,8 +426,10 @@ class ManagerBasedRLEnv:
         rew, bits = sim.step_stage_a(action, t)
         built_in_to = (bits & 1).bool()
         built_in_term = (bits & 0xFE).bool()
+        self._term_bits_staged = bits            # per-term masks of the built-in terms (get_term)
         extra_term = extra_to = None
         fired = {}
+        self._py_term_masks = fired
         for term in self._py_terms:
             v = term.func(self, **term.params).to(torch.bool)
             fired[term.name] = v

@@ -87,12 +87,13 @@ class FusedPolicyRollout:
         self.logs = torch.zeros((T, 16), dtype=torch.float32, device=sim.device)
         # slab.obs_in[k] = the observation actions[k] / log_prob[k] / values[k] / mean[k] were computed from (rsl_rl
         # RolloutStorage.observations[k]); slab.obs[k] = obs_in[k+1] = what step k returned
-        self.obs0 = self.slab.obs_in[0]
+        self.obs0 = torch.empty((sim.num_envs, sim.obs_dim), dtype=torch.float32, device=sim.device)    # carried to the next replay
         self.graph = None
         self._base = 0
         self._stream = torch.cuda.Stream(device=sim.device)
 
     def _body(self):
+        self.slab.obs_in[0].copy_(self.obs0)
         for k in range(self.T):
             act_step(self.sim, self.slab.obs_in[k], self.blob, self.slab.actions[k], self.pol.mean[k], self.pol.log_prob[k],
                      self.pol.values[k], self.slab.step_outputs(k), self.logs[k], WheeledSim.device_counter_plus(k))

@@ -21,12 +21,15 @@ class GraphedRollout:
         self.sim, self.policy, self.T = sim, policy, T
         self.slab = slab or RolloutSlab(T, sim.num_envs, sim.obs_dim, 2, sim.device)
         self.logs = torch.zeros((T, 16), dtype=torch.float32, device=sim.device)
-        self.obs0 = self.slab.obs_in[0]          # the rollout's first observation lives in the slab itself
+        # the observation the next replay starts from; copied into slab.obs_in[0] first thing in the graph, so that after a
+        # replay the slab is self-consistent (obs_in[k] is what actions[k] were computed from, for every k)
+        self.obs0 = torch.empty((sim.num_envs, sim.obs_dim), dtype=torch.float32, device=sim.device)
         self.graph = None
         self._base = 0
         self._stream = torch.cuda.Stream(device=sim.device)
 
     def _body(self):
+        self.slab.obs_in[0].copy_(self.obs0)
         for k in range(self.T):
             act = self.policy(self.slab.obs_in[k])
             self.slab.actions[k].copy_(act)
