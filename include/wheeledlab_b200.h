@@ -275,6 +275,7 @@ extern "C" {
     XS(float, f32, d_sden)            /* 1 / (J + h kd + h^2 kp) */                                \
     XS(float, f32, d_inv_Iw)                                                                       \
     XS(float, f32, d_hI)              /* h / wheel_inertia */                                      \
+    XS(float, f32, d_inv_hf_cell)     /* 1 / hf_cell (0 without a height-field) */                 \
     XS(float, f32, d_fxk)             /* tire_mx / h */                                            \
     XS(float, f32, d_fyk)                                                                          \
     XS(float, f32, d_inv_wheel_radius_cfg)                                                         \
@@ -509,6 +510,7 @@ int wl_test_detmath(int32_t op, const float* d_in, const float* d_in2, float* d_
                     void* stream);
 /* an empty kernel of the given geometry (launch / event-timing floor of the measurement protocol) */
 int wl_test_null(int32_t grid, int32_t block, void* stream);
+int wl_test_null_cfg(wl_sim* sim, int32_t grid, int32_t block, void* stream);   /* same, with the wl_config kernel parameter */
 /* philox4x32-10: out[4*n] for counters (c0_base + i, c1, c2, c3), key from seed */
 int wl_test_philox(uint64_t seed, uint32_t c0_base, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t* d_out,
                    int32_t n, void* stream);

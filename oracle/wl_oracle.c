@@ -399,6 +399,7 @@ static void config_finalize(wl_config* c) {
     c->d_sden = 1.0f / fmaf(c->d_h, c->d_hkp, fmaf(c->d_h, c->steer_kd, c->steer_inertia));
     c->d_inv_Iw = 1.0f / c->wheel_inertia;
     c->d_hI = c->d_h * c->d_inv_Iw;
+    c->d_inv_hf_cell = c->hf_cell > 0.0f ? 1.0f / c->hf_cell : 0.0f;
     c->d_fxk = c->tire_mx * c->d_inv_h;
     c->d_fyk = c->tire_my * c->d_inv_h;
     c->d_inv_wheel_radius_cfg = 1.0f / c->wheel_radius_cfg;
@@ -473,7 +474,7 @@ static void physics_substep(const wlo_sim* s, wlo_env* e, chassis_t* b, const re
         real lt[3]; cross(nb, ft, lt);
         real vx = vdot(vc, ft), vy = vdot(vc, lt);
         real sx = fm(om_star, rw, -vx), sy = -vy;     /* slip velocity of the tyre surface */
-        real smag = r_sqrt(fm(sx, sx, sy * sy));
+        real smag = r_sqrt(r_max(fm(sx, sx, sy * sy), K(1.0e-24)));   /* |s| >= 1e-12: all operands below stay normal-range */
         real den = r_max(r_fabs(vx), (real)c->tire_v0);
         real sm = det_sin_0_pi(e->C[i] * det_atan_ratio((real)c->tire_B * smag, den));
         real Fmag = Fz * (e->D[i] * sm);

@@ -993,3 +993,35 @@ def test_elevation_per_term_termination_masks():
     assert seen["time_out"] > 0 and seen["stuck"] > 0 and seen["stuck"] != seen["time_out"]
     with pytest.raises(ValueError):
         env.termination_manager.get_term("no_such_term")
+
+
+def test_fast_div_sqrt_are_ieee():
+    """fdiv_norm / fsqrt_norm (the compiler's own MUFU + FFMA fast path, emitted without the range check and slow-path call) give
+    the correctly rounded IEEE result over the operand ranges the integrator sub-step feeds them (normal-range operands,
+    quotient and intermediates; see wheel_force), and det_atan_ratio<NORM> equals the checked variant."""
+    _need_gpu()
+    import wheeledlab_b200 as wl
+    rng = np.random.default_rng(5)
+
+    def run(op, x, y):
+        dx, dy = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda(); out = torch.empty_like(dx)
+        wl._lib.check(wl.lib.wl_test_detmath(op, dx.data_ptr(), dy.data_ptr(), out.data_ptr(), x.size, None))
+        torch.cuda.synchronize()
+        return out.cpu().numpy()
+
+    n = 4_000_000
+    for lo_e, hi_e in ((-40, 14), (-1, 14), (-30, -20)):       # POSITIVE denominators (the sub-step's are), numerators of either sign
+        b = (2.0 ** rng.uniform(lo_e, hi_e, n)).astype(np.float32)
+        a = (2.0 ** rng.uniform(-40, 14, n)).astype(np.float32) * rng.choice([-1.0, 1.0], n).astype(np.float32)
+        a[:1000] = 0.0; a[1000:2000] = 1.0                     # (+0 numerator: the only zero the sub-step can produce)
+        assert np.array_equal(_bits(run(9, b, a)), _bits(a / b))
+    # mantissa corner cases: all-ones / power-of-two denominators and numerators
+    m = np.array([0x3f800000, 0x3fffffff, 0x3f800001, 0x3fc00000, 0x3f7fffff, 0x40490fdb], np.uint32).view(np.float32)
+    bb, aa = np.meshgrid(m, m); bb, aa = bb.ravel().copy(), -aa.ravel().copy()
+    assert np.array_equal(_bits(run(9, bb, aa)), _bits(aa / bb))
+    x = (2.0 ** rng.uniform(-80, 27, n)).astype(np.float32)
+    x[:6] = m
+    assert np.array_equal(_bits(run(10, x, x)), _bits(np.sqrt(x)))
+    den = rng.uniform(0.5, 1.0e3, n).astype(np.float32)
+    num = (10.0 * 2.0 ** rng.uniform(-40, 12, n)).astype(np.float32)
+    assert np.array_equal(_bits(run(11, den, num)), _bits(run(12, den, num)))

@@ -85,6 +85,29 @@ def child(envs, steps, warm, task):
     r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     r0.record(); rot(RK, 0); r1.record(); torch.cuda.synchronize()
     rot_us = r0.elapsed_time(r1) * 1e3 / RK
+    # launch floors: graphs of 200 empty kernels (no parameter / the 1.5 KB wl_config parameter), and stream launches of the same
+    floors = {}
+    geo = ((envs * 4 + 31) // 32 + 1, 32)
+    for name, fn in (("null", lambda: wl.lib.wl_test_null(geo[0], geo[1], _stream_ptr(sim.device))),
+                     ("null_cfg", lambda: wl.lib.wl_test_null_cfg(sim._h, geo[0], geo[1], _stream_ptr(sim.device)))):
+        gg = torch.cuda.CUDAGraph(); ss = torch.cuda.Stream(); ss.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(ss):
+            with torch.cuda.graph(gg, stream=ss):
+                for _ in range(200):
+                    fn()
+        torch.cuda.current_stream().wait_stream(ss)
+        gg.replay(); torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); gg.replay(); b.record(); torch.cuda.synchronize()
+        floors[name + "_graph_us"] = a.elapsed_time(b) * 1e3 / 200
+        for _ in range(50):
+            fn()
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(400):
+            fn()
+        b.record(); torch.cuda.synchronize()
+        floors[name + "_stream_us"] = a.elapsed_time(b) * 1e3 / 400
     # floor of the protocol: empty kernel of the same geometry between the same events / flushes
     nul = []
     for geo in ((envs * 4 + 31) // 32, 32), ((envs * 4 + 127) // 128, 128):
@@ -95,7 +118,7 @@ def child(envs, steps, warm, task):
         nul.append(statistics.median(a.elapsed_time(b) * 1e3 for a, b in evn))
     print(json.dumps({"variant": os.environ.get("KEXP_NAME"), "task": task, "envs": envs, "cold_us_mean": statistics.mean(cold),
                       "cold_us_median": statistics.median(cold), "cold_us_min": min(cold), "warm_graph_us": warm_us,
-                      "rotate_us": rot_us, "rotate_sets": M, "pdl": os.environ.get("WL_PDL", "1"),
+                      "rotate_us": rot_us, "floors": floors, "rotate_sets": M, "pdl": os.environ.get("WL_PDL", "1"),
                       "null_us_bs32": nul[0], "null_us_bs128": nul[1]}), flush=True)
 
 

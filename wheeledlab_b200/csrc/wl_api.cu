@@ -271,6 +271,18 @@ wl_step_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st, wl_
 // Four lanes per env (lane = wheel).  Same arithmetic, same results; the per-wheel work runs in parallel and the
 // chassis is integrated redundantly in the 4 lanes.  Used when N is too small to fill the chip with one thread/env.
 // quad_env_step = sections A..I of ONE env.step() on register-resident state `e` (lane-local view, see load_env_quad).
+// lane w of an env's quad computes ONE of the three euler angles (lane 0 roll, 1 pitch, 2 and 3 yaw), wrapped to [0, 2 pi)
+__device__ __forceinline__ float euler_lane(float qw, float qx, float qy, float qz, int w) {
+    float sin_roll = 2.0f * fm(qw, qx, qy * qz), cos_roll = fm(-2.0f, fm(qx, qx, qy * qy), 1.0f);
+    float sin_pitch = 2.0f * fm(qw, qy, -(qz * qx));
+    float sin_yaw = 2.0f * fm(qw, qz, qx * qy), cos_yaw = fm(-2.0f, fm(qy, qy, qz * qz), 1.0f);
+    float ay = (w == 0) ? sin_roll : (w == 1) ? sin_pitch : sin_yaw;
+    float ax = (w == 0) ? cos_roll : (w == 1) ? sqrtf((1.0f - sin_pitch) * (1.0f + sin_pitch)) : cos_yaw;
+    float ang = det_atan2(ay, ax);
+    if (w == 1 && fabsf(sin_pitch) >= 1.0f) ang = (sin_pitch < 0.0f) ? -1.57079632679489661923f : 1.57079632679489661923f;
+    return wrap_2pi(ang);
+}
+
 template <int TASK>
 __device__ __forceinline__ void quad_env_step(const wl_config& c, const Terrain& T, const VisualMap& vm, float* __restrict__ acc_row,
                                               const float wts[WL_MAX_REW_TERMS], EnvState& e, int i, int w, bool live, uint32_t gid,
@@ -323,6 +335,12 @@ __device__ __forceinline__ void quad_env_step(const wl_config& c, const Terrain&
         drift_reward_terms(c, steer_l, steer_r, det_atan2(vb.y, vb.x), e.p, vb, b.wb, e.w.z, oob, time_out, f);
         tmask = (time_out ? 1u : 0u) | (oob ? 2u : 0u);
     }
+    // I'. observation inputs from the post-physics state, formed HERE so that this lane's euler atan2 overlaps the reward
+    // terms' atan2 / sqrt chains in one basic block; an env that resets (or gets pushed) redoes them below -- the rare path
+    float eu_k = 0.0f;
+    V3 wbo{0.0f, 0.0f, 0.0f};
+    if (!VIS) eu_k = euler_lane(e.qw, e.qx, e.qy, e.qz, w);
+    if (!VIS && !ELEV) wbo = rotT(R, e.w);                        // (R^T of the WORLD rate, as the oracle forms it: not b.wb bit for bit)
     tmask &= (uint32_t)c.term_enable;
     float total = 0.0f;
 #pragma unroll
@@ -341,41 +359,34 @@ __device__ __forceinline__ void quad_env_step(const wl_config& c, const Terrain&
     log_accumulate(acc_row, done && live && (w == 0), tmask, e.sums);
     if (done) {
         if (ELEV) elev_reset_env(c, e, gid, t); else if (VIS) visual_reset_env(c, vm, e, gid, t); else drift_reset_env(c, e, gid, t);
+        if (!VIS) eu_k = euler_lane(e.qw, e.qx, e.qy, e.qz, w);
+        if (!VIS && !ELEV) { R = rotmat(e.qw, e.qx, e.qy, e.qz); vb = rotT(R, e.v); wbo = rotT(R, e.w); }   // (the oracle's own operations: signed zeros)
     }
-    if (ELEV) elev_command_update(c, e, gid, t, c.d_step_dt); else if (!VIS) interval_pushes(c, e, gid, t, c.d_step_dt);
+    if (ELEV) elev_command_update(c, e, gid, t, c.d_step_dt);
+    else if (!VIS) {
+        // H. interval pushes: never on the step an env resets (fresh timers exceed step_dt), so R is still the rotation of e.q
+        if (interval_pushes(c, e, gid, t, c.d_step_dt)) { vb = rotT(R, e.v); wbo = rotT(R, e.w); }
+    }
     if (VIS) {      // 8 proprioceptive floats, no noise, no euler: lanes 0 and 1 write one float4 each
         float o[8]; visual_proprio(c, e, o);
         if (live && w < 2) {
             float4* row = reinterpret_cast<float4*>(obs_row + vis_cam_floats(c));
             row[w] = (w == 0) ? make_float4(o[0], o[1], o[2], o[3]) : make_float4(o[4], o[5], o[6], o[7]);
         }
-    } else
-    // I. observations: the three euler angles are three atan2 calls -> one per lane
-    {
-        float qw = e.qw, qx = e.qx, qy = e.qy, qz = e.qz;
-        float sin_roll = 2.0f * fm(qw, qx, qy * qz), cos_roll = fm(-2.0f, fm(qx, qx, qy * qy), 1.0f);
-        float sin_pitch = 2.0f * fm(qw, qy, -(qz * qx));
-        float sin_yaw = 2.0f * fm(qw, qz, qx * qy), cos_yaw = fm(-2.0f, fm(qy, qy, qz * qz), 1.0f);
-        float ay = (w == 0) ? sin_roll : (w == 1) ? sin_pitch : sin_yaw;
-        float ax = (w == 0) ? cos_roll : (w == 1) ? sqrtf((1.0f - sin_pitch) * (1.0f + sin_pitch)) : cos_yaw;
-        float ang = det_atan2(ay, ax);
-        if (w == 1 && fabsf(sin_pitch) >= 1.0f) ang = (sin_pitch < 0.0f) ? -1.57079632679489661923f : 1.57079632679489661923f;
-        float eu_k = wrap_2pi(ang);
-        if (ELEV) {
-            V3 eu{__shfl_sync(0xffffffffu, eu_k, base + 0), __shfl_sync(0xffffffffu, eu_k, base + 1), __shfl_sync(0xffffffffu, eu_k, base + 2)};
-            float o[13]; elev_proprio(c, e, eu, o);
-            if (live) {
-                // lane w writes o[w], o[w+4], o[w+8] (and lane 0 also o[12]): 4-byte rows, scalar stores
-                const float v0 = (w == 0) ? o[0] : (w == 1) ? o[1] : (w == 2) ? o[2] : o[3];
-                const float v1 = (w == 0) ? o[4] : (w == 1) ? o[5] : (w == 2) ? o[6] : o[7];
-                const float v2 = (w == 0) ? o[8] : (w == 1) ? o[9] : (w == 2) ? o[10] : o[11];
-                obs_row[w] = v0; obs_row[w + 4] = v1; obs_row[w + 8] = v2;
-                if (w == 0) obs_row[12] = o[12];
-            }
-        } else {
-            // blind_obs_quad shuffles: every lane of the warp calls it, dead quads only skip the stores
-            blind_obs_quad(c, e, w, eu_k, znoise, obs_row, live);
+    } else if (ELEV) {
+        V3 eu{__shfl_sync(0xffffffffu, eu_k, base + 0), __shfl_sync(0xffffffffu, eu_k, base + 1), __shfl_sync(0xffffffffu, eu_k, base + 2)};
+        float o[13]; elev_proprio(c, e, eu, o);
+        if (live) {
+            // lane w writes o[w], o[w+4], o[w+8] (and lane 0 also o[12]): 4-byte rows, scalar stores
+            const float v0 = (w == 0) ? o[0] : (w == 1) ? o[1] : (w == 2) ? o[2] : o[3];
+            const float v1 = (w == 0) ? o[4] : (w == 1) ? o[5] : (w == 2) ? o[6] : o[7];
+            const float v2 = (w == 0) ? o[8] : (w == 1) ? o[9] : (w == 2) ? o[10] : o[11];
+            obs_row[w] = v0; obs_row[w + 4] = v1; obs_row[w + 8] = v2;
+            if (w == 0) obs_row[12] = o[12];
         }
+    } else {
+        // blind_obs_quad shuffles: every lane of the warp calls it, dead quads only skip the stores
+        blind_obs_quad(c, e, w, eu_k, vb, wbo, znoise, obs_row, live);
     }
 }
 
@@ -403,12 +414,15 @@ wl_step_quad_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st
         return;
     }
     EnvState e;
-    load_env_quad(st, n, ii, w, e, ELEV, c.dr_wheel_mass_enable != 0, c.d_inv_Iw);
-    load_weights(c, gl, t, wts);
+    QuadRaw raw;
+    quad_issue_loads(st, n, ii, w, raw, ELEV, c.dr_wheel_mass_enable != 0);
     const float2 a = action[ii];
-    // the observation noise depends on (env id, step) only: drawn here, while the state loads are in flight
+    load_weights(c, gl, t, wts);
+    // the observation noise depends on (env id, step) only: drawn here, while the state loads are in flight (nothing above
+    // has consumed a loaded value yet)
     float zn[4];
     if (!ELEV && !VIS) quad_obs_noise(c, w, gid, t, RNG_OBS, 0u, zn); else zn[0] = zn[1] = zn[2] = zn[3] = 0.0f;
+    quad_unpack(raw, w, e, ELEV, c.dr_wheel_mass_enable != 0, c.d_inv_Iw);
     const int od = ELEV ? WL_OBS_DIM_ELEV : VIS ? WL_OBS_DIM_VISUAL + vis_cam_floats(c) : WL_OBS_DIM_BLIND;
     quad_env_step<TASK>(c, T, vm, gl->acc[t % 3u], wts, e, i, w, live, gid, base, t, a, zn, obs + (size_t)od * ii, rew, terminated_o, truncated_o, term_bits);
     if (live) store_env_quad(st, n, i, w, e, ELEV);
@@ -710,7 +724,7 @@ wl_scan_kernel(const __grid_constant__ wl_config c, const __grid_constant__ CUte
     // ray-caster parent = base_link (root + R (0,0,base_link_z)); rays are yaw-aligned (attach_yaw_only)
     const float bx = fm(c.base_link_z, R.r[2], e.p.x), by = fm(c.base_link_z, R.r[5], e.p.y), bz = fm(c.base_link_z, R.r[8], e.p.z);
     float cy, sy; yaw_cs(e, cy, sy);
-    const float inv = 1.0f / c.hf_cell;
+    const float inv = c.d_inv_hf_cell;
     // window origin (in samples): covers base +- (half*sqrt2 + 1 cell)
     const float reach = c.scan_half * 1.41421356237f + c.hf_cell;
     const int ox = ((int)floorf((bx - reach - c.hf_x0) * inv)) & ~3;      // two's complement: rounds toward -inf
@@ -991,10 +1005,15 @@ __global__ void wl_detmath_kernel(int op, const float* __restrict__ in, const fl
         case 6: r = det_asin(x); break;
         case 7: r = det_exp(x); break;
         case 8: r = det_tanh(x); break;
+        case 9: r = fdiv_norm(in2[i], x); break;          // in2 / in
+        case 10: r = fsqrt_norm(x); break;
+        case 11: r = det_atan_ratio<true>(in2[i], x); break;
+        case 12: r = det_atan_ratio<false>(in2[i], x); break;
     }
     out[i] = r;
 }
 __global__ void wl_null_kernel(int* p) { if (p != nullptr && threadIdx.x == 1024) *p = 0; }
+__global__ void wl_null_cfg_kernel(const __grid_constant__ wl_config c, int* p) { if (p != nullptr && threadIdx.x == 1024) *p = c.num_envs; }
 __global__ void wl_philox_kernel(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint4* __restrict__ out, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -1245,6 +1264,7 @@ int wl_config_finalize(wl_config* c) {
     c->d_sden = 1.0f / fmaf(c->d_h, c->d_hkp, fmaf(c->d_h, c->steer_kd, c->steer_inertia));
     c->d_inv_Iw = 1.0f / c->wheel_inertia;
     c->d_hI = c->d_h * c->d_inv_Iw;
+    c->d_inv_hf_cell = c->hf_cell > 0.0f ? 1.0f / c->hf_cell : 0.0f;
     c->d_fxk = c->tire_mx * c->d_inv_h;
     c->d_fyk = c->tire_my * c->d_inv_h;
     c->d_inv_wheel_radius_cfg = 1.0f / c->wheel_radius_cfg;
@@ -1679,6 +1699,11 @@ int wl_test_detmath(int32_t op, const float* d_in, const float* d_in2, float* d_
 int wl_test_null(int32_t grid, int32_t block, void* stream) {
     wl_null_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(nullptr);
     return cuda_check(cudaGetLastError(), "wl_null_kernel");
+}
+int wl_test_null_cfg(wl_sim* sim, int32_t grid, int32_t block, void* stream) {      /* same, carrying the 1.5 KB wl_config parameter */
+    if (!sim) return fail(WL_EINVAL, "wl_test_null_cfg: null handle");
+    wl_null_cfg_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(sim->cfg, nullptr);
+    return cuda_check(cudaGetLastError(), "wl_null_cfg_kernel");
 }
 int wl_test_philox(uint64_t seed, uint32_t c0_base, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t* d_out, int32_t n,
                    void* stream) {

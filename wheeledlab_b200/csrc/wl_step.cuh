@@ -73,31 +73,48 @@ __device__ __forceinline__ void store_env(float4* __restrict__ st, int n, int i,
 
 // ---- quad (4 lanes per env) state access: lane w = wheel [bl,br,fl,fr][w].  Per-wheel scalars live in slot [0]
 // of the lane's EnvState (omega, D, C, kd) and front lanes keep THEIR steer joint in steer[0]/steer_vel[0].
-__device__ __forceinline__ void load_env_quad(const float4* __restrict__ st, int n, int i, int w, EnvState& e, bool with_cmd,
-                                              bool with_iw = false, float inv_Iw_nominal = 0.0f) {
-    float4 g;
-    e.inv_Iw[0] = with_iw ? reinterpret_cast<const float*>(st)[(size_t)WL_G_PIW * n * 4 + (size_t)i * 4 + w] : inv_Iw_nominal;
-    g = ldg4(st, WL_G_POS, n, i); e.p = V3{g.x, g.y, g.z}; e.ep_len = __float_as_int(g.w);
-    g = ldg4(st, WL_G_QUAT, n, i); e.qw = g.x; e.qx = g.y; e.qy = g.z; e.qz = g.w;
-    g = ldg4(st, WL_G_LINVEL, n, i); e.v = V3{g.x, g.y, g.z}; e.t_hf = g.w;
-    g = ldg4(st, WL_G_ANGVEL, n, i); e.w = V3{g.x, g.y, g.z}; e.t_lf = g.w;
-    g = ldg4(st, WL_G_ACTION, n, i); e.action[0] = g.x; e.action[1] = g.y; e.prev_action[0] = g.z; e.prev_action[1] = g.w;
-    g = ldg4(st, WL_G_SUM0, n, i); e.sums[0] = g.x; e.sums[1] = g.y; e.sums[2] = g.z; e.sums[3] = g.w;
-    g = ldg4(st, WL_G_SUM1, n, i); e.sums[4] = g.x; e.sums[5] = g.y; e.sums[6] = g.z; e.sums[7] = g.w;
-    g = ldg4(st, WL_G_PMASS, n, i); e.mass = g.x; e.inv_mass = g.y; e.spare0 = g.z; e.spare1 = g.w;
+// Two phases: quad_issue_loads() puts every load in flight into a register block and quad_unpack() consumes it -- whatever is
+// written between the two calls (the observation noise) executes under the shadow of the loads.
+struct QuadRaw { float4 pos, quat, linvel, angvel, action, sum0, sum1, pmass, steer, cmd, cmdb; float omega, D, C, kd, inv_Iw; };
+__device__ __forceinline__ void quad_issue_loads(const float4* __restrict__ st, int n, int i, int w, QuadRaw& r, bool with_cmd, bool with_iw) {
+    r.pos = ldg4(st, WL_G_POS, n, i); r.quat = ldg4(st, WL_G_QUAT, n, i);
+    r.linvel = ldg4(st, WL_G_LINVEL, n, i); r.angvel = ldg4(st, WL_G_ANGVEL, n, i);
+    r.action = ldg4(st, WL_G_ACTION, n, i); r.sum0 = ldg4(st, WL_G_SUM0, n, i); r.sum1 = ldg4(st, WL_G_SUM1, n, i);
+    r.pmass = ldg4(st, WL_G_PMASS, n, i); r.steer = ldg4(st, WL_G_STEER, n, i);
     const float* f = reinterpret_cast<const float*>(st);
     const size_t lane_off = (size_t)i * 4 + w;                       // 32 lanes -> 128 contiguous bytes
-    e.omega[0] = f[(size_t)WL_G_WHEEL * n * 4 + lane_off];
-    e.D[0] = f[(size_t)WL_G_PMU_D * n * 4 + lane_off];
-    e.C[0] = f[(size_t)WL_G_PMU_C * n * 4 + lane_off];
-    e.kd[0] = f[(size_t)WL_G_PKD * n * 4 + lane_off];
-    g = ldg4(st, WL_G_STEER, n, i);
+    r.omega = f[(size_t)WL_G_WHEEL * n * 4 + lane_off];
+    r.D = f[(size_t)WL_G_PMU_D * n * 4 + lane_off];
+    r.C = f[(size_t)WL_G_PMU_C * n * 4 + lane_off];
+    r.kd = f[(size_t)WL_G_PKD * n * 4 + lane_off];
+    r.inv_Iw = with_iw ? f[(size_t)WL_G_PIW * n * 4 + lane_off] : 0.0f;
+    if (with_cmd) { r.cmd = ldg4(st, WL_G_CMD, n, i); r.cmdb = ldg4(st, WL_G_CMDB, n, i); }
+}
+__device__ __forceinline__ void quad_unpack(const QuadRaw& r, int w, EnvState& e, bool with_cmd, bool with_iw, float inv_Iw_nominal) {
+    float4 g;
+    e.inv_Iw[0] = with_iw ? r.inv_Iw : inv_Iw_nominal;
+    g = r.pos; e.p = V3{g.x, g.y, g.z}; e.ep_len = __float_as_int(g.w);
+    g = r.quat; e.qw = g.x; e.qx = g.y; e.qy = g.z; e.qz = g.w;
+    g = r.linvel; e.v = V3{g.x, g.y, g.z}; e.t_hf = g.w;
+    g = r.angvel; e.w = V3{g.x, g.y, g.z}; e.t_lf = g.w;
+    g = r.action; e.action[0] = g.x; e.action[1] = g.y; e.prev_action[0] = g.z; e.prev_action[1] = g.w;
+    g = r.sum0; e.sums[0] = g.x; e.sums[1] = g.y; e.sums[2] = g.z; e.sums[3] = g.w;
+    g = r.sum1; e.sums[4] = g.x; e.sums[5] = g.y; e.sums[6] = g.z; e.sums[7] = g.w;
+    g = r.pmass; e.mass = g.x; e.inv_mass = g.y; e.spare0 = g.z; e.spare1 = g.w;
+    e.omega[0] = r.omega; e.D[0] = r.D; e.C[0] = r.C; e.kd[0] = r.kd;
+    g = r.steer;
     e.steer[0] = (w == 3) ? g.y : g.x; e.steer_vel[0] = (w == 3) ? g.w : g.z;   // lanes 0-2 see the LEFT joint, lane 3 the right
     e.steer[1] = g.y; e.steer_vel[1] = g.w;
     if (with_cmd) {
-        g = ldg4(st, WL_G_CMD, n, i); e.cmd[0] = g.x; e.cmd[1] = g.y; e.cmd[2] = g.z; e.cmd[3] = g.w;
-        g = ldg4(st, WL_G_CMDB, n, i); e.cmdb[0] = g.x; e.cmdb[1] = g.y; e.cmdb[2] = g.z; e.cmdb[3] = g.w;
+        g = r.cmd; e.cmd[0] = g.x; e.cmd[1] = g.y; e.cmd[2] = g.z; e.cmd[3] = g.w;
+        g = r.cmdb; e.cmdb[0] = g.x; e.cmdb[1] = g.y; e.cmdb[2] = g.z; e.cmdb[3] = g.w;
     }
+}
+__device__ __forceinline__ void load_env_quad(const float4* __restrict__ st, int n, int i, int w, EnvState& e, bool with_cmd,
+                                              bool with_iw = false, float inv_Iw_nominal = 0.0f) {
+    QuadRaw r;
+    quad_issue_loads(st, n, i, w, r, with_cmd, with_iw);
+    quad_unpack(r, w, e, with_cmd, with_iw, inv_Iw_nominal);
 }
 __device__ __forceinline__ void store_env_quad(float4* __restrict__ st, int n, int i, int w, const EnvState& e, bool with_cmd) {
     float* f = reinterpret_cast<float*>(st);
@@ -175,7 +192,7 @@ struct Terrain { const float* __restrict__ hf; };
 // the z = hf_outside_z ground plane for the wheels).  gx, gy = d z / d x, d z / d y.
 __device__ __forceinline__ bool hf_sample(const wl_config& c, const float* __restrict__ hf, float x, float y, float& z, float& gx,
                                           float& gy) {
-    float inv = 1.0f / c.hf_cell;
+    const float inv = c.d_inv_hf_cell;
     float fx = (x - c.hf_x0) * inv, fy = (y - c.hf_y0) * inv;
     if (!((fx >= 0.0f) && (fy >= 0.0f) && (fx <= (float)(c.hf_nx - 1)) && (fy <= (float)(c.hf_ny - 1)))) return false;
     int ix = (int)floorf(fx), iy = (int)floorf(fy);
@@ -195,7 +212,7 @@ __device__ __forceinline__ bool hf_sample(const wl_config& c, const float* __res
 __device__ __forceinline__ void heightfield_at(const wl_config& c, const Terrain& T, float x, float y, float& z, V3& n) {
     float gx, gy;
     if (T.hf != nullptr && hf_sample(c, T.hf, x, y, z, gx, gy)) {
-        float ninv = 1.0f / sqrtf(fm(gx, gx, fm(gy, gy, 1.0f)));
+        float ninv = fdiv_norm(1.0f, fsqrt_norm(fm(gx, gx, fm(gy, gy, 1.0f))));       // argument >= 1: normal range
         n = V3{-gx * ninv, -gy * ninv, ninv};
         return;
     }
@@ -283,11 +300,13 @@ __device__ __forceinline__ WheelOut wheel_force(const wl_config& c, const Terrai
     V3 lt = cross(nb, ft);
     float vx = dot(vc, ft), vy = dot(vc, lt);
     float sx = fm(om_star, rw, -vx), sy = -vy;               // slip velocity of the tyre surface
-    float smag = sqrtf(fm(sx, sx, sy * sy));
+    // |s| >= 1e-12 keeps every operand below in the normal range (the fast IEEE sequences need no slow path); at exactly
+    // zero slip the force is zero through sx = sy = 0 either way
+    float smag = fsqrt_norm(r_max(fm(sx, sx, sy * sy), 1.0e-24f));
     float den = r_max(fabsf(vx), c.tire_v0);
-    float sm = det_sin_0_pi(Cmu * det_atan_ratio(c.tire_B * smag, den));
+    float sm = det_sin_0_pi(Cmu * det_atan_ratio<true>(c.tire_B * smag, den));
     float Fmag = Fz * (Dmu * sm);
-    float inv_s = 1.0f / r_max(smag, 1.0e-9f);
+    float inv_s = fdiv_norm(1.0f, r_max(smag, 1.0e-9f));
     float Fx = (Fmag * sx) * inv_s, Fy = (Fmag * sy) * inv_s;
     float fxm = fxk * fabsf(sx), fym = c.d_fyk * fabsf(sy);  // implicit-stick cap
     Fx = r_clamp(Fx, -fxm, fxm); Fy = r_clamp(Fy, -fym, fym);
@@ -599,8 +618,10 @@ __device__ __forceinline__ void drift_reset_env(const wl_config& c, EnvState& e,
     uint4 r2 = philox4x32(c.seed, gid, t, RNG_RESET, 1u);
     sample_interval_timers(c, e, r2.x, r2.y);
 }
-__device__ __forceinline__ void interval_pushes(const wl_config& c, EnvState& e, uint32_t gid, uint32_t t, float step_dt) {
-    if (!c.push_enable) return;
+// returns true when a push changed the velocities
+__device__ __forceinline__ bool interval_pushes(const wl_config& c, EnvState& e, uint32_t gid, uint32_t t, float step_dt) {
+    if (!c.push_enable) return false;
+    bool fired = false;
     e.t_hf = e.t_hf - step_dt;
     if (e.t_hf < 1.0e-6f) {
         uint4 r = philox4x32(c.seed, gid, t, RNG_PUSH_HF, 0u);
@@ -608,13 +629,16 @@ __device__ __forceinline__ void interval_pushes(const wl_config& c, EnvState& e,
         e.v.y = e.v.y + uniform(r.y, -c.push_hf_range[1], c.push_hf_range[1]);
         e.w.z = e.w.z + uniform(r.z, -c.push_hf_range[2], c.push_hf_range[2]);
         e.t_hf = uniform(r.w, c.push_hf_interval[0], c.push_hf_interval[1]);
+        fired = true;
     }
     e.t_lf = e.t_lf - step_dt;
     if (e.t_lf < 1.0e-6f) {
         uint4 r = philox4x32(c.seed, gid, t, RNG_PUSH_LF, 0u);
         e.w.z = e.w.z + uniform(r.x, -c.push_lf_yaw, c.push_lf_yaw);
         e.t_lf = uniform(r.y, c.push_lf_interval[0], c.push_lf_interval[1]);
+        fired = true;
     }
+    return fired;
 }
 // writes 14 floats (obs must be 8-byte aligned: 14 floats = 7 x float2 per env)
 __device__ __forceinline__ void blind_obs(const wl_config& c, const EnvState& e, uint32_t gid, uint32_t t, uint32_t stream,
@@ -654,10 +678,8 @@ __device__ __forceinline__ void quad_obs_noise(const wl_config& c, int w, uint32
         box_muller(r.z, r.w, z[2], z[3]);
     }
 }
-__device__ __forceinline__ void blind_obs_quad(const wl_config& c, const EnvState& e, int w, float eu_k, const float z[4],
+__device__ __forceinline__ void blind_obs_quad(const wl_config& c, const EnvState& e, int w, float eu_k, V3 vb, V3 wb, const float z[4],
                                                float* __restrict__ obs, bool live) {
-    M3 R = rotmat(e.qw, e.qx, e.qy, e.qz);
-    V3 vb = rotT(R, e.v), wb = rotT(R, e.w);
     const unsigned base = (threadIdx.x & 31u) & ~3u;
     float eu1 = __shfl_sync(0xffffffffu, eu_k, base + 1), eu2 = __shfl_sync(0xffffffffu, eu_k, base + 2);
     float b0, b1, b2, b3, s0, s1, s2, s3;
