@@ -365,6 +365,11 @@ float* wl_reward_weights(wl_sim* sim);
 /* optional per-env output of wl_step / wl_step_host*: one byte of termination-term bits per env (bit j = term j fired this
  * step, order below) -- what TerminationManager.get_term(name) needs; NULL (default) disables it */
 int wl_set_term_bits(wl_sim* sim, uint8_t* d_term_bits);
+/* Fused rollout-slab fan-out (multi-GPU): every output row wl_step writes (observation, reward, terminated,
+ * truncated) is ALSO stored at `pointer + byte_deltas[k]` for k < n_peers -- byte_deltas[k] = base of peer k's symmetric
+ * (P2P-mapped, NVLink) gathered buffer minus the base of the local one -- so the learner-facing concat of the rollout is
+ * complete when the step kernels are: no separate collective.  n_peers = 0 switches it off.  Drift-family tasks. */
+int wl_set_peer_fanout(wl_sim* sim, int32_t n_peers, const int64_t* byte_deltas);
 /* ManagerBasedEnv.seed(): re-key the counter-based generator for all later launches (startup draws are not repeated) */
 int wl_set_seed(wl_sim* sim, uint64_t seed);
 /* fill the d_* derived fields from the primary ones (idempotent). */
@@ -446,7 +451,8 @@ int wl_curriculum(wl_sim* sim, int32_t n_terms, const int32_t* slots, const floa
 int wl_synth_actions(wl_sim* sim, float* d_action, int64_t step_counter, int32_t dist, void* stream);
 /* derived joint state for the Python articulation view: suspension pos/vel [N,4]x2 */
 int wl_derive_suspension(wl_sim* sim, float* d_susp_pos, float* d_susp_vel, void* stream);
-/* step-kernel geometry: 0 = auto (by num_envs), 1 = one thread per env, 4 = four lanes (one per wheel) per env.
+/* step-kernel geometry: 0 = auto (by num_envs and task), 1 = one thread per env, 4 = four lanes (one per wheel) per env,
+ * 8 = the quad plus an auxiliary warp per 8 envs that takes everything off the dependent chain (Drift family only).
  * Results are bit-identical across variants. */
 int wl_set_kernel_variant(wl_sim* sim, int32_t lanes_per_env);
 /* height-scan tile staging: 1 = TMA (cp.async.bulk.tensor.2d, default), 0 = plain loads (A/B comparison) */

@@ -86,7 +86,7 @@ def test_startup_and_reset_state_bit_exact():
     assert np.array_equal(_bits(_state_groups(sim)), _bits(orc.export_state()))
 
 
-@pytest.mark.parametrize("variant", [1, 4])      # one thread per env / four lanes (one per wheel) per env
+@pytest.mark.parametrize("variant", [1, 4, 8])   # one thread per env / four lanes (one per wheel) per env / quad + aux warp
 @pytest.mark.parametrize("n,steps,kw", [
     (256, 1000, {}),                               # RSS_DRIFT settings, DR + pushes + noise on
     (333, 300, {"randomize": False}),              # ragged N (not a multiple of the CTA), DR off
@@ -149,14 +149,16 @@ def test_kernel_variants_agree_at_full_size():
     _need_gpu()
     import wheeledlab_b200 as wl
     a = wl.WheeledSim(wl.drift_task(num_envs=4096, seed=42), "cuda:0"); b = wl.WheeledSim(wl.drift_task(num_envs=4096, seed=42), "cuda:0")
-    a.set_kernel_variant(1); b.set_kernel_variant(4)
-    for s in (a, b):
+    d = wl.WheeledSim(wl.drift_task(num_envs=4096, seed=42), "cuda:0")
+    a.set_kernel_variant(1); b.set_kernel_variant(4); d.set_kernel_variant(8)
+    for s in (a, b, d):
         s.startup(); s.reset(None, 0)
     for t in range(400):
         act = a.synth_actions(t)
-        for x, y in zip(a.step(act, t), b.step(act, t)):
-            assert torch.equal(x, y), f"variant mismatch at step {t}"
-    assert torch.equal(a.groups, b.groups)
+        ra, rb, rd = a.step(act, t), b.step(act, t), d.step(act, t)
+        for x, y, z in zip(ra, rb, rd):
+            assert torch.equal(x, y) and torch.equal(x, z), f"variant mismatch at step {t}"
+    assert torch.equal(a.groups, b.groups) and torch.equal(a.groups, d.groups) and torch.equal(a.rew_weight, d.rew_weight)
 
 
 def test_sharding_invariance_two_shards_equal_one():
@@ -913,9 +915,11 @@ def test_vehicle_at_rest_stays_at_rest_on_the_gpu():
     assert float(sim.wheel_vel.abs().max()) < 1e-2
 
 
-def test_two_process_nccl_gather_equals_single_rank(tmp_path):
-    """BASELINE configs[4] at test size: 2 ranks x 2048 envs over NCCL, the all-gathered rollout slab == the slab of one
-    4096-env process, bit for bit (skipped when the box has a single GPU)."""
+@pytest.mark.parametrize("mode", ["nccl", "fanout"])
+def test_two_process_nccl_gather_equals_single_rank(tmp_path, mode):
+    """BASELINE configs[4] at test size: 2 ranks x 2048 envs, the exchanged rollout slab == the slab of one 4096-env process,
+    bit for bit (skipped when the box has a single GPU).  mode "nccl": one all_gather_into_tensor of the slab; "fanout": the
+    step kernel stores its output rows into the peer's symmetric buffer over NVLink (no collective)."""
     _need_gpu()
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
@@ -923,7 +927,8 @@ def test_two_process_nccl_gather_equals_single_rank(tmp_path):
     root = Path(__file__).resolve().parent.parent
     out = tmp_path / "slab.pt"
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-           "--master-port", "29731", str(root / "tools" / "nccl_slab_check.py"), "--out", str(out), "--envs", "2048", "--steps", "16"]
+           "--master-port", "29731" if mode == "nccl" else "29733", str(root / "tools" / "nccl_slab_check.py"), "--out", str(out), "--envs", "2048",
+           "--steps", "16", "--mode", mode]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     import wheeledlab_b200 as wl
@@ -936,7 +941,7 @@ def test_two_process_nccl_gather_equals_single_rank(tmp_path):
         slab.actions[t].copy_(act)
         sim.step(act, t, out=slab.step_outputs(t))
     torch.cuda.synchronize()
-    for name in ("obs", "actions", "rewards", "terminated", "truncated"):
+    for name in got:
         assert torch.equal(getattr(slab, name).cpu(), got[name]), name
 
 

@@ -42,6 +42,8 @@ def child(envs, steps, warm, task):
     dev = "cuda:0"
     spec = wl.make_task(task, num_envs=envs, seed=42)
     sim = wl.WheeledSim(spec, dev); sim.startup(); sim.reset(None, 0)
+    KV = int(os.environ.get("KEXP_KVARIANT", "0"))
+    sim.set_kernel_variant(KV)
     K, W = steps, warm
     acts = torch.stack([sim.synth_actions(t) for t in range(W + K)])
     out = (torch.empty((envs, sim.obs_dim), device=dev), torch.empty(envs, device=dev), torch.empty(envs, dtype=torch.uint8, device=dev),
@@ -72,7 +74,7 @@ def child(envs, steps, warm, task):
     M = int(os.environ.get("KEXP_SETS", "160"))
     sims = []
     for m in range(M):
-        sm = wl.WheeledSim(wl.make_task(task, num_envs=envs, seed=42 + m), dev); sm.startup(); sm.reset(None, 0); sims.append(sm)
+        sm = wl.WheeledSim(wl.make_task(task, num_envs=envs, seed=42 + m), dev); sm.startup(); sm.reset(None, 0); sm.set_kernel_variant(KV); sims.append(sm)
     outs = [tuple(torch.empty_like(x) for x in out) for _ in range(M)]
     bound = [sims[m].bind_step(acts[m % (W + K)], outs[m]) for m in range(M)]
     tt = [0] * M
@@ -118,15 +120,16 @@ def child(envs, steps, warm, task):
         nul.append(statistics.median(a.elapsed_time(b) * 1e3 for a, b in evn))
     print(json.dumps({"variant": os.environ.get("KEXP_NAME"), "task": task, "envs": envs, "cold_us_mean": statistics.mean(cold),
                       "cold_us_median": statistics.median(cold), "cold_us_min": min(cold), "warm_graph_us": warm_us,
-                      "rotate_us": rot_us, "floors": floors, "rotate_sets": M, "pdl": os.environ.get("WL_PDL", "1"),
+                      "rotate_us": rot_us, "floors": floors, "kernel_variant": KV, "rotate_sets": M, "pdl": os.environ.get("WL_PDL", "1"),
                       "null_us_bs32": nul[0], "null_us_bs128": nul[1]}), flush=True)
 
 
 def run(envs, task):
     for name in VARIANTS:
-        for pdl in os.environ.get("KEXP_PDL", "1").split(","):
-            env = dict(os.environ, WHEELEDLAB_B200_LIB=str(AB / f"libwl_{name}.so"), KEXP_NAME=name, WL_PDL=pdl)
-            subprocess.run([sys.executable, __file__, "child", str(envs), task], env=env, check=False)
+        for pdl in os.environ.get("KEXP_PDL", "0").split(","):
+            for kv in os.environ.get("KEXP_KVARIANTS", "0").split(","):
+                env = dict(os.environ, WHEELEDLAB_B200_LIB=str(AB / f"libwl_{name}.so"), KEXP_NAME=name, WL_PDL=pdl, KEXP_KVARIANT=kv)
+                subprocess.run([sys.executable, __file__, "child", str(envs), task], env=env, check=False)
 
 
 if __name__ == "__main__":

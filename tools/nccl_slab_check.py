@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--envs", type=int, default=2048)
     ap.add_argument("--steps", type=int, default=16)
     ap.add_argument("--seed", type=int, default=42)
+    ap.add_argument("--mode", default="nccl", choices=["nccl", "fanout"])
     a = ap.parse_args()
     import wheeledlab_b200 as wl
     from wheeledlab_b200.distributed import RolloutSlab
@@ -30,15 +31,26 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device(dev))
     sim = wl.WheeledSim(wl.drift_task(num_envs=a.envs, seed=a.seed, env_id_offset=rank * a.envs), dev)
     sim.startup(); sim.reset(None, 0)
-    slab = RolloutSlab(a.steps, a.envs, sim.obs_dim, 2, dev)
+    fields = ("obs", "actions", "rewards", "terminated", "truncated")
+    if a.mode == "fanout":                       # fused: the step kernel stores its rows into every peer's symmetric buffer
+        from wheeledlab_b200.distributed import SymmetricRolloutSlab
+        sym = SymmetricRolloutSlab(a.steps, a.envs, sim.obs_dim, 2, dev).attach(sim)
+        slab = sym.slab
+        fields = ("obs", "rewards", "terminated", "truncated")       # (actions are written by the caller, not by env.step)
+    else:
+        slab = RolloutSlab(a.steps, a.envs, sim.obs_dim, 2, dev)
     for t in range(a.steps):
         act = sim.synth_actions(t)
         slab.actions[t].copy_(act)
         sim.step(act, t, out=slab.step_outputs(t))
-    g = slab.all_gather()
+    if a.mode == "fanout":
+        sym.barrier(); torch.cuda.synchronize(); dist.barrier()
+        g = sym.gathered()
+    else:
+        g = slab.all_gather()
     torch.cuda.synchronize()
     if rank == 0:
-        torch.save({k: g.cat(k).cpu() for k in ("obs", "actions", "rewards", "terminated", "truncated")}, a.out)
+        torch.save({k: g.cat(k).cpu() for k in fields}, a.out)
     dist.barrier()
     dist.destroy_process_group()
 

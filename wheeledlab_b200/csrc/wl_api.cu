@@ -26,6 +26,7 @@ struct wl_sim {
     int64_t last_t;         // counter of the most recent step launched through this handle (-1: none); host mirror
     int64_t base_host;      // host mirror of wl_globals.step_base
     uint8_t* term_bits;     // optional per-env termination-term bits output of wl_step (wl_set_term_bits)
+    PeerFan fan;            // peers every output row of wl_step is also stored to (wl_set_peer_fanout); n = 0: none
     int device;             // CUDA device ordinal the handle lives on
     int obs_dim;
     int variant;            // 0 auto, 1 thread-per-env, 4 quad-per-env
@@ -426,6 +427,222 @@ wl_step_quad_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st
     const int od = ELEV ? WL_OBS_DIM_ELEV : VIS ? WL_OBS_DIM_VISUAL + vis_cam_floats(c) : WL_OBS_DIM_BLIND;
     quad_env_step<TASK>(c, T, vm, gl->acc[t % 3u], wts, e, i, w, live, gid, base, t, a, zn, obs + (size_t)od * ii, rew, terminated_o, truncated_o, term_bits);
     if (live) store_env_quad(st, n, i, w, e, ELEV);
+}
+
+// ---------------------------------------------------------------------------------------
+// Drift-family step in the latency-optimised geometry for small N: CTA = 2 warps for 8 envs.  Warp 0 (the "env warp")
+// is the quad (lane = wheel) and carries ONLY what is on the dependent chain: state loads -> integrator sub-steps ->
+// terminations -> reset -> pushes -> observations -> state stores.  Warp 1 (the "aux warp", lane = env) does everything
+// that is not on that chain, concurrently on another scheduler: the action map (ready before the first sub-step needs the
+// targets), the observation-noise and push draws (counter based: functions of (env, step) only) and -- once the env warp
+// has published the post-physics state in shared memory -- reward terms, episode sums, reward / done stores and the
+// episode log.  Hand-offs are named barriers (bar.arrive / bar.sync), each used once per launch.  Same arithmetic as
+// wl_step_quad_kernel, operation for operation.
+// ---------------------------------------------------------------------------------------
+#define WL_DUO_ENVS 8
+struct DuoShared {
+    float tgt[WL_DUO_ENVS][8];      // wheel_target[4], steer_target[2]
+    float noise[WL_DUO_ENVS][12];   // observation noise normals (Philox blocks 0..2)
+    float push[WL_DUO_ENVS][8];     // hf fired, dvx, dvy, dwz_hf, t_hf_new, lf fired, dwz_lf, t_lf_new
+    float fin[WL_DUO_ENVS][16];     // post-physics: p(3) vb(3) wb(3) wz_world steer_l steer_r raw-tmask(bits)
+};
+__device__ __forceinline__ void bar_arrive(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void bar_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+
+__global__ void __launch_bounds__(64)
+wl_step_duo_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st, wl_globals* __restrict__ gl,
+                   const float2* __restrict__ action, float* __restrict__ obs, float* __restrict__ rew,
+                   uint8_t* __restrict__ terminated_o, uint8_t* __restrict__ truncated_o, float* __restrict__ d_log, uint32_t t_arg,
+                   uint8_t* __restrict__ term_bits, const __grid_constant__ PeerFan pf) {
+    __shared__ DuoShared sh;
+    const int n = c.num_envs;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t t = decode_step(gl, t_arg);
+    if (blockIdx.x == gridDim.x - 1) {       // the janitor CTA (appended to the grid, owns no envs)
+        if (threadIdx.x < 32) { float wj[WL_MAX_REW_TERMS]; load_weights(c, gl, t, wj); janitor(c, gl, t, wj, d_log); }
+        return;
+    }
+    const int env0 = blockIdx.x * WL_DUO_ENVS;
+    const Terrain T{nullptr};
+    if (warp == 1) {
+        // ================= aux warp: lane j < 8 <-> env env0 + j =================
+        const int j = lane & 7;
+        const int i = env0 + j;
+        const bool live = (lane < 8) && (i < n);
+        const int ii = (i < n) ? i : n - 1;
+        const uint32_t gid = (uint32_t)(c.env_id_offset + ii);
+        float2 a = make_float2(0.0f, 0.0f);
+        float4 s0 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), s1 = s0;
+        float t_hf = 0.0f, t_lf = 0.0f;
+        if (lane < 8) {
+            a = action[ii];
+            s0 = ldg4(st, WL_G_SUM0, n, ii); s1 = ldg4(st, WL_G_SUM1, n, ii);
+            const float* fst = reinterpret_cast<const float*>(st);
+            t_hf = fst[((size_t)WL_G_LINVEL * n + ii) * 4 + 3]; t_lf = fst[((size_t)WL_G_ANGVEL * n + ii) * 4 + 3];
+        }
+        float wts[WL_MAX_REW_TERMS];
+        load_weights(c, gl, t, wts);
+        // A. action map -> targets of the whole env step
+        if (lane < 8) {
+            float wt[4], stt[2];
+            process_action(c, a.x, a.y, wt, stt);
+            sh.tgt[j][0] = wt[0]; sh.tgt[j][1] = wt[1]; sh.tgt[j][2] = wt[2]; sh.tgt[j][3] = wt[3];
+            sh.tgt[j][4] = stt[0]; sh.tgt[j][5] = stt[1];
+        }
+        bar_arrive(1);
+        // N. observation noise: lane = (env, Philox block)
+        if (lane < 24) {
+            const int jn = lane / 3, k = lane - 3 * jn;
+            const int in_ = (env0 + jn < n) ? env0 + jn : n - 1;
+            float z[4];
+            quad_obs_noise(c, k, (uint32_t)(c.env_id_offset + in_), t, RNG_OBS, 0u, z);
+            sh.noise[jn][4 * k + 0] = z[0]; sh.noise[jn][4 * k + 1] = z[1]; sh.noise[jn][4 * k + 2] = z[2]; sh.noise[jn][4 * k + 3] = z[3];
+        }
+        // P. interval pushes of an env that does NOT reset this step (the env warp ignores them otherwise)
+        if (lane < 8) {
+            float hf = 0.0f, dvx = 0.0f, dvy = 0.0f, dwh = 0.0f, lf = 0.0f, dwl = 0.0f;
+            if (c.push_enable) {
+                t_hf = t_hf - c.d_step_dt;
+                if (t_hf < 1.0e-6f) {
+                    uint4 r = philox4x32(c.seed, gid, t, RNG_PUSH_HF, 0u);
+                    dvx = uniform(r.x, -c.push_hf_range[0], c.push_hf_range[0]);
+                    dvy = uniform(r.y, -c.push_hf_range[1], c.push_hf_range[1]);
+                    dwh = uniform(r.z, -c.push_hf_range[2], c.push_hf_range[2]);
+                    t_hf = uniform(r.w, c.push_hf_interval[0], c.push_hf_interval[1]);
+                    hf = 1.0f;
+                }
+                t_lf = t_lf - c.d_step_dt;
+                if (t_lf < 1.0e-6f) {
+                    uint4 r = philox4x32(c.seed, gid, t, RNG_PUSH_LF, 0u);
+                    dwl = uniform(r.x, -c.push_lf_yaw, c.push_lf_yaw);
+                    t_lf = uniform(r.y, c.push_lf_interval[0], c.push_lf_interval[1]);
+                    lf = 1.0f;
+                }
+            }
+            sh.push[j][0] = hf; sh.push[j][1] = dvx; sh.push[j][2] = dvy; sh.push[j][3] = dwh; sh.push[j][4] = t_hf;
+            sh.push[j][5] = lf; sh.push[j][6] = dwl; sh.push[j][7] = t_lf;
+        }
+        bar_arrive(3);
+        // R. rewards, episode sums, reward / done stores, episode log -- on the post-physics state the env warp publishes
+        bar_sync(2);
+        uint32_t tmask = 0u;
+        float sums[WL_MAX_REW_TERMS] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+        bool done = false;
+        if (lane < 8) {
+            const float* fi = sh.fin[j];
+            const V3 p{fi[0], fi[1], fi[2]}, vb{fi[3], fi[4], fi[5]}, wb{fi[6], fi[7], fi[8]};
+            const uint32_t raw = __float_as_uint(fi[12]);
+            const bool time_out = (raw & 1u) != 0u, oob = (raw & 2u) != 0u;
+            float f[WL_MAX_REW_TERMS];
+            drift_reward_terms(c, fi[10], fi[11], det_atan2(vb.y, vb.x), p, vb, wb, fi[9], oob, time_out, f);
+            tmask = raw & (uint32_t)c.term_enable;
+            float total = 0.0f;
+#pragma unroll
+            for (int k = 0; k < WL_MAX_REW_TERMS; ++k) {
+                if (k < c.num_rew_terms) {
+                    float wgt = wts[k];
+                    if (wgt != 0.0f) { float val = f[k] * wgt * c.d_step_dt; total += val; sums[k] += val; }
+                }
+            }
+            done = tmask != 0u;
+            if (live) {
+                fan_store(pf, &rew[i], total);
+                fan_store(pf, &terminated_o[i], (uint8_t)((tmask & ~1u) ? 1 : 0));
+                fan_store(pf, &truncated_o[i], (uint8_t)((tmask & 1u) ? 1 : 0));
+                if (term_bits != nullptr) term_bits[i] = (uint8_t)tmask;
+            }
+        }
+        log_accumulate(gl->acc[t % 3u], done && live, tmask, sums);
+        if (live) {
+            if (done) {
+#pragma unroll
+                for (int k = 0; k < WL_MAX_REW_TERMS; ++k) sums[k] = 0.0f;
+            }
+            stg4(st, WL_G_SUM0, n, i, make_float4(sums[0], sums[1], sums[2], sums[3]));
+            stg4(st, WL_G_SUM1, n, i, make_float4(sums[4], sums[5], sums[6], sums[7]));
+        }
+        return;
+    }
+    // ================= env warp: the quad (lane = wheel), 8 envs =================
+    const int q = lane >> 2, w = lane & 3;
+    const int i = env0 + q;
+    const bool live = i < n;
+    const int ii = live ? i : n - 1;
+    const uint32_t gid = (uint32_t)(c.env_id_offset + ii);
+    const unsigned base = (unsigned)lane & ~3u;
+    const bool wm = c.dr_wheel_mass_enable != 0;
+    EnvState e;
+    QuadRaw raw;
+    quad_issue_loads(st, n, ii, w, raw, false, wm, false);
+    const float2 a = action[ii];
+    quad_unpack(raw, w, e, false, wm, c.d_inv_Iw);
+    // A. action manager: only the bookkeeping; the map itself comes from the aux warp
+    e.prev_action[0] = e.action[0]; e.prev_action[1] = e.action[1];
+    e.action[0] = a.x; e.action[1] = a.y;
+    const float my_effort = (w == 0) ? c.dc_effort[0] : (w == 1) ? c.dc_effort[1] : (w == 2) ? c.dc_effort[2] : c.dc_effort[3];
+    // B. decimation x (actuators -> integrator)
+    Chassis b;
+    M3 R = rotmat(e.qw, e.qx, e.qy, e.qz);
+    V3 cw = rot(R, V3{c.com[0], c.com[1], c.com[2]});
+    b.pc = V3{e.p.x + cw.x, e.p.y + cw.y, e.p.z + cw.z};
+    b.v = e.v; b.qw = e.qw; b.qx = e.qx; b.qy = e.qy; b.qz = e.qz;
+    b.wb = rotT(R, e.w);
+    StepConsts kc = make_step_consts<1>(c, e);
+    bar_sync(1);
+    const float my_targets[4] = {sh.tgt[q][w], 0.0f, 0.0f, 0.0f};
+    const float my_steer_target[2] = {sh.tgt[q][(w == 3) ? 5 : 4], 0.0f};
+    for (int d = 0; d < c.decimation; ++d) {
+        float lo[4], hi[4];
+        dc_limits(c, my_effort, e.omega[0], lo[0], hi[0]);
+        for (int jj = 0; jj < c.substeps; ++jj) physics_substep<WL_TASK_DRIFT, 4>(c, T, e, b, my_targets, lo, hi, my_steer_target, kc);
+    }
+    R = rotmat(b.qw, b.qx, b.qy, b.qz);
+    cw = rot(R, V3{c.com[0], c.com[1], c.com[2]});
+    e.p = V3{b.pc.x - cw.x, b.pc.y - cw.y, b.pc.z - cw.z};
+    e.v = b.v; e.qw = b.qw; e.qx = b.qx; e.qy = b.qy; e.qz = b.qz;
+    e.w = rot(R, b.wb);
+    // C./D. counters, terminations (the env warp needs `done` for the reset; the reward side lives in the aux warp)
+    e.ep_len += 1;
+    const bool time_out = e.ep_len >= c.max_episode_length;
+    V3 vb = rotT(R, e.v);
+    const float steer_l = __shfl_sync(0xffffffffu, e.steer[0], base + 2), steer_r = __shfl_sync(0xffffffffu, e.steer[0], base + 3);
+    const bool oob = drift_off_track(c, e.p.x, e.p.y);
+    const uint32_t raw_mask = (time_out ? 1u : 0u) | (oob ? 2u : 0u);
+    if (w == 0) {
+        float* fo = sh.fin[q];
+        fo[0] = e.p.x; fo[1] = e.p.y; fo[2] = e.p.z; fo[3] = vb.x; fo[4] = vb.y; fo[5] = vb.z;
+        fo[6] = b.wb.x; fo[7] = b.wb.y; fo[8] = b.wb.z; fo[9] = e.w.z; fo[10] = steer_l; fo[11] = steer_r;
+        fo[12] = __uint_as_float(raw_mask);
+    }
+    bar_arrive(2);
+    // I'. observation inputs from the post-physics state (an env that resets / gets pushed redoes them below)
+    float eu_k = euler_lane(e.qw, e.qx, e.qy, e.qz, w);
+    V3 wbo = rotT(R, e.w);
+    const bool done = (raw_mask & (uint32_t)c.term_enable) != 0u;
+    // F. auto-reset (sums and log: aux warp)
+    if (done) {
+        drift_reset_env(c, e, gid, t);
+        eu_k = euler_lane(e.qw, e.qx, e.qy, e.qz, w);
+        R = rotmat(e.qw, e.qx, e.qy, e.qz); vb = rotT(R, e.v); wbo = rotT(R, e.w);
+    }
+    // H. interval pushes + noise, drawn by the aux warp
+    bar_sync(3);
+    if (c.push_enable) {
+        if (done) { e.t_hf = e.t_hf - c.d_step_dt; e.t_lf = e.t_lf - c.d_step_dt; }       // fresh timers exceed step_dt: no push on a reset step
+        else {
+            const float* pu = sh.push[q];
+            bool fired = false;
+            if (pu[0] != 0.0f) { e.v.x = e.v.x + pu[1]; e.v.y = e.v.y + pu[2]; e.w.z = e.w.z + pu[3]; fired = true; }
+            e.t_hf = pu[4];
+            if (pu[5] != 0.0f) { e.w.z = e.w.z + pu[6]; fired = true; }
+            e.t_lf = pu[7];
+            if (fired) { vb = rotT(R, e.v); wbo = rotT(R, e.w); }
+        }
+    }
+    const int k4 = (w < 3) ? 4 * w : 0;
+    const float zn[4] = {sh.noise[q][k4], sh.noise[q][k4 + 1], sh.noise[q][k4 + 2], sh.noise[q][k4 + 3]};
+    blind_obs_quad(c, e, w, eu_k, vb, wbo, zn, obs + (size_t)WL_OBS_DIM_BLIND * ii, live, pf);
+    if (live) store_env_quad(st, n, i, w, e, false, false);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1248,6 +1465,14 @@ int wl_set_term_bits(wl_sim* sim, uint8_t* d_term_bits) {
     sim->term_bits = d_term_bits;
     return WL_OK;
 }
+int wl_set_peer_fanout(wl_sim* sim, int32_t n_peers, const int64_t* byte_deltas) {
+    if (!sim || n_peers < 0 || n_peers > WL_MAX_PEERS || (n_peers > 0 && !byte_deltas)) return fail(WL_EINVAL, "wl_set_peer_fanout: bad argument");
+    if (n_peers > 0 && sim->cfg.task != WL_TASK_DRIFT) return fail(WL_EUNSUPPORTED, "wl_set_peer_fanout: Drift-family tasks only");
+    memset(&sim->fan, 0, sizeof sim->fan);
+    sim->fan.n = n_peers;
+    for (int k = 0; k < n_peers; ++k) sim->fan.delta[k] = (long long)byte_deltas[k];
+    return WL_OK;
+}
 int wl_set_seed(wl_sim* sim, uint64_t seed) {
     if (!sim) return fail(WL_EINVAL, "wl_set_seed: null handle");
     sim->cfg.seed = seed;
@@ -1334,6 +1559,7 @@ int wl_create(const wl_config* cfg, void* d_state, size_t state_bytes, const flo
     s->last_t = -1;
     s->base_host = 0;
     s->term_bits = nullptr;
+    memset(&s->fan, 0, sizeof s->fan);
     cudaGetDevice(&s->device);
     s->variant = 0;
     s->has_tmap = false;
@@ -1378,7 +1604,8 @@ int wl_set_scan_tma(wl_sim* sim, int32_t use_tma) {
 }
 int wl_set_kernel_variant(wl_sim* sim, int32_t lanes_per_env) {
     if (!sim) return fail(WL_EINVAL, "wl_set_kernel_variant: null handle");
-    if (lanes_per_env != 0 && lanes_per_env != 1 && lanes_per_env != 4) return fail(WL_EINVAL, "wl_set_kernel_variant: 0, 1 or 4");
+    if (lanes_per_env != 0 && lanes_per_env != 1 && lanes_per_env != 4 && lanes_per_env != 8)
+        return fail(WL_EINVAL, "wl_set_kernel_variant: 0, 1, 4 or 8");
     sim->variant = lanes_per_env;
     return WL_OK;
 }
@@ -1443,14 +1670,21 @@ int wl_step(wl_sim* sim, const float* d_action, float* d_obs, float* d_rew, uint
     if (((uintptr_t)d_action & 7u) || ((uintptr_t)d_obs & 7u)) return fail(WL_EINVAL, "wl_step: action/obs must be 8-byte aligned");
     const int n = sim->cfg.num_envs;
     Terrain T{sim->hf};
-    const int variant = sim->variant ? sim->variant : ((n <= WL_QUAD_MAX_ENVS) ? 4 : 1);
+    // 8 = quad + aux warp (Drift family, small N: shortest dependent chain), 4 = quad, 1 = thread per env
+    int variant = sim->variant ? sim->variant : ((n <= WL_QUAD_MAX_ENVS) ? ((sim->cfg.task == WL_TASK_DRIFT) ? 8 : 4) : 1);
+    if (variant == 8 && sim->cfg.task != WL_TASK_DRIFT) variant = 4;
     const float2* act = reinterpret_cast<const float2*>(d_action);
     cudaStream_t cs = (cudaStream_t)stream;
     const uint32_t t = (uint32_t)step_counter;               // negative (device base + k) stays encoded: see decode_step
     if (int rc = prep_step(sim, step_counter, 1, cs)) return rc;
     const bool elev = sim->cfg.task == WL_TASK_ELEVATION, vis = sim->cfg.task == WL_TASK_VISUAL;
     StageIO sio0{sim->term_bits, nullptr, nullptr};
-    if (variant == 4) {
+    if (variant == 8) {
+        const int grid = (n + WL_DUO_ENVS - 1) / WL_DUO_ENVS + 1;                            // + the janitor CTA
+        launch_k(wl_step_duo_kernel, grid, 64, 0, cs, sim->cfg, sim->state, sim->globals, act, d_obs, d_rew, d_terminated, d_truncated, d_log, t, sim->term_bits, sim->fan);
+    } else if (sim->fan.n > 0) {
+        return fail(WL_EUNSUPPORTED, "wl_step: the peer fan-out is implemented by the Drift-family small-N kernel (variant 8) only");
+    } else if (variant == 4) {
 #ifndef WL_QUAD_BS
 #define WL_QUAD_BS 32
 #endif

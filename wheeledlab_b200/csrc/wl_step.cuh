@@ -76,10 +76,13 @@ __device__ __forceinline__ void store_env(float4* __restrict__ st, int n, int i,
 // Two phases: quad_issue_loads() puts every load in flight into a register block and quad_unpack() consumes it -- whatever is
 // written between the two calls (the observation noise) executes under the shadow of the loads.
 struct QuadRaw { float4 pos, quat, linvel, angvel, action, sum0, sum1, pmass, steer, cmd, cmdb; float omega, D, C, kd, inv_Iw; };
-__device__ __forceinline__ void quad_issue_loads(const float4* __restrict__ st, int n, int i, int w, QuadRaw& r, bool with_cmd, bool with_iw) {
+__device__ __forceinline__ void quad_issue_loads(const float4* __restrict__ st, int n, int i, int w, QuadRaw& r, bool with_cmd, bool with_iw,
+                                                 bool with_sums = true) {
     r.pos = ldg4(st, WL_G_POS, n, i); r.quat = ldg4(st, WL_G_QUAT, n, i);
     r.linvel = ldg4(st, WL_G_LINVEL, n, i); r.angvel = ldg4(st, WL_G_ANGVEL, n, i);
-    r.action = ldg4(st, WL_G_ACTION, n, i); r.sum0 = ldg4(st, WL_G_SUM0, n, i); r.sum1 = ldg4(st, WL_G_SUM1, n, i);
+    r.action = ldg4(st, WL_G_ACTION, n, i);
+    if (with_sums) { r.sum0 = ldg4(st, WL_G_SUM0, n, i); r.sum1 = ldg4(st, WL_G_SUM1, n, i); }
+    else { r.sum0 = make_float4(0.0f, 0.0f, 0.0f, 0.0f); r.sum1 = r.sum0; }
     r.pmass = ldg4(st, WL_G_PMASS, n, i); r.steer = ldg4(st, WL_G_STEER, n, i);
     const float* f = reinterpret_cast<const float*>(st);
     const size_t lane_off = (size_t)i * 4 + w;                       // 32 lanes -> 128 contiguous bytes
@@ -116,7 +119,8 @@ __device__ __forceinline__ void load_env_quad(const float4* __restrict__ st, int
     quad_issue_loads(st, n, i, w, r, with_cmd, with_iw);
     quad_unpack(r, w, e, with_cmd, with_iw, inv_Iw_nominal);
 }
-__device__ __forceinline__ void store_env_quad(float4* __restrict__ st, int n, int i, int w, const EnvState& e, bool with_cmd) {
+__device__ __forceinline__ void store_env_quad(float4* __restrict__ st, int n, int i, int w, const EnvState& e, bool with_cmd,
+                                               bool with_sums = true) {
     float* f = reinterpret_cast<float*>(st);
     f[(size_t)WL_G_WHEEL * n * 4 + (size_t)i * 4 + w] = e.omega[0];
     if (w >= 2) {                                                      // own steer joint: pos at [w-2], vel at [2 + w-2]
@@ -130,8 +134,10 @@ __device__ __forceinline__ void store_env_quad(float4* __restrict__ st, int n, i
         stg4(st, WL_G_ANGVEL, n, i, make_float4(e.w.x, e.w.y, e.w.z, e.t_lf));
     } else if (w == 1) {
         stg4(st, WL_G_ACTION, n, i, make_float4(e.action[0], e.action[1], e.prev_action[0], e.prev_action[1]));
-        stg4(st, WL_G_SUM0, n, i, make_float4(e.sums[0], e.sums[1], e.sums[2], e.sums[3]));
-        stg4(st, WL_G_SUM1, n, i, make_float4(e.sums[4], e.sums[5], e.sums[6], e.sums[7]));
+        if (with_sums) {
+            stg4(st, WL_G_SUM0, n, i, make_float4(e.sums[0], e.sums[1], e.sums[2], e.sums[3]));
+            stg4(st, WL_G_SUM1, n, i, make_float4(e.sums[4], e.sums[5], e.sums[6], e.sums[7]));
+        }
         if (with_cmd) {
             stg4(st, WL_G_CMD, n, i, make_float4(e.cmd[0], e.cmd[1], e.cmd[2], e.cmd[3]));
             stg4(st, WL_G_CMDB, n, i, make_float4(e.cmdb[0], e.cmdb[1], e.cmdb[2], e.cmdb[3]));
@@ -667,6 +673,17 @@ __device__ __forceinline__ void blind_obs(const wl_config& c, const EnvState& e,
     for (int k = 0; k < 7; ++k) o2[k] = make_float2(o[2 * k], o[2 * k + 1]);
 }
 
+// ---- fused rollout-slab fan-out over NVLink peer memory: every output row of the step (observation, reward,
+// done masks) is stored locally AND at the same offset of every peer's symmetric buffer (delta = peer base - local base),
+// so the learner-facing "all-gather" is done by the time the step kernels are: no separate collective, no staging copy.
+#define WL_MAX_PEERS 8
+struct PeerFan { int32_t n; int32_t pad; long long delta[WL_MAX_PEERS]; };
+template <typename TT>
+__device__ __forceinline__ void fan_store(const PeerFan& pf, TT* p, TT v) {
+    *p = v;
+    for (int k = 0; k < pf.n; ++k) *reinterpret_cast<TT*>(reinterpret_cast<char*>(p) + pf.delta[k]) = v;
+}
+
 // quad version: lane k in {0,1,2} owns Philox block k (4 normals, drawn by quad_obs_noise at the TOP of the kernel, under
 // the shadow of the state loads) and writes obs[4k..4k+3]; lane 3 writes the last action.  `eu_k` = this lane's euler angle
 // (lane0 roll, lane1 pitch, lane2 yaw), already wrapped.
@@ -679,7 +696,7 @@ __device__ __forceinline__ void quad_obs_noise(const wl_config& c, int w, uint32
     }
 }
 __device__ __forceinline__ void blind_obs_quad(const wl_config& c, const EnvState& e, int w, float eu_k, V3 vb, V3 wb, const float z[4],
-                                               float* __restrict__ obs, bool live) {
+                                               float* __restrict__ obs, bool live, const PeerFan& pf = PeerFan{0, 0, {0, 0, 0, 0, 0, 0, 0, 0}}) {
     const unsigned base = (threadIdx.x & 31u) & ~3u;
     float eu1 = __shfl_sync(0xffffffffu, eu_k, base + 1), eu2 = __shfl_sync(0xffffffffu, eu_k, base + 2);
     float b0, b1, b2, b3, s0, s1, s2, s3;
@@ -690,10 +707,10 @@ __device__ __forceinline__ void blind_obs_quad(const wl_config& c, const EnvStat
     float2* o2 = reinterpret_cast<float2*>(obs + 4 * w);
     if (!live) return;
     if (w < 3) {
-        o2[0] = make_float2(b0 + s0 * z[0], b1 + s1 * z[1]);
-        o2[1] = make_float2(b2 + s2 * z[2], b3 + s3 * z[3]);
+        fan_store(pf, &o2[0], make_float2(b0 + s0 * z[0], b1 + s1 * z[1]));
+        fan_store(pf, &o2[1], make_float2(b2 + s2 * z[2], b3 + s3 * z[3]));
     } else {
-        o2[0] = make_float2(b0, b1);
+        fan_store(pf, &o2[0], make_float2(b0, b1));
     }
 }
 

@@ -27,7 +27,7 @@ class RolloutSlab:
     (rsl_rl RolloutStorage: values [T,N], actions_log_prob [T,N], action_mean [T,N,A]; written by wl_act_step).  Fields are
     views of ONE flat byte buffer, so ONE all_gather_into_tensor moves the whole slab."""
 
-    def __init__(self, T: int, n_local: int, obs_dim: int, act_dim: int, device, policy_fields: bool = False):
+    def __init__(self, T: int, n_local: int, obs_dim: int, act_dim: int, device, policy_fields: bool = False, flat: torch.Tensor | None = None):
         self.T, self.n, self.obs_dim, self.act_dim = T, n_local, obs_dim, act_dim
         self.device = torch.device(device)
         # name -> (dtype, trailing shape)
@@ -43,7 +43,12 @@ class RolloutSlab:
                 n_el *= d
             self._sizes[k] = n_el * (4 if dt == torch.float32 else 1)
         total = sum((v + 255) // 256 * 256 for v in self._sizes.values())
-        self.flat = torch.zeros(total, dtype=torch.uint8, device=self.device)
+        if flat is not None:                     # caller-provided storage (a slot of a symmetric buffer)
+            if flat.numel() != total or flat.dtype != torch.uint8:
+                raise ValueError(f"flat must be uint8[{total}]")
+            self.flat = flat
+        else:
+            self.flat = torch.zeros(total, dtype=torch.uint8, device=self.device)
         off = 0
         for k, nbytes in self._sizes.items():
             dt, tail = self._fields[k]
@@ -76,6 +81,47 @@ class RolloutSlab:
         else:
             dist.all_gather_into_tensor(out, self.flat, group=group)
         return GatheredRollout(out.view(world, -1), self)
+
+
+def slab_nbytes(T: int, n_local: int, obs_dim: int, act_dim: int, policy_fields: bool = False) -> int:
+    """Size in bytes of a RolloutSlab with this geometry."""
+    sizes = [(T + 1) * n_local * obs_dim * 4, T * n_local * act_dim * 4, T * n_local * 4, T * n_local, T * n_local]
+    if policy_fields:
+        sizes += [T * n_local * 4, T * n_local * 4, T * n_local * act_dim * 4]
+    return sum((v + 255) // 256 * 256 for v in sizes)
+
+
+class SymmetricRolloutSlab:
+    """The fused form of the rollout-slab exchange: ONE symmetric (P2P-mapped over NVLink) buffer of world x slab bytes per
+    rank (torch.distributed._symmetric_memory).  Rank r's slab is slot r of its own buffer; the step kernel stores every
+    output row there AND at the same offset of every peer's buffer (WheeledSim.set_peer_fanout), so after the last step of
+    the rollout plus one barrier every rank holds the concatenated rollout -- no all-gather, no staging copy, the transfer
+    rides along with the steps.  ``slab`` is the local RolloutSlab, ``gathered()`` the [world, ...] views."""
+
+    def __init__(self, T: int, n_local: int, obs_dim: int, act_dim: int, device, group=None, policy_fields: bool = False):
+        import torch.distributed._symmetric_memory as symm
+        group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        nbytes = slab_nbytes(T, n_local, obs_dim, act_dim, policy_fields)
+        self.buf = symm.empty(self.world * nbytes, dtype=torch.uint8, device=torch.device(device))
+        self.buf.zero_()
+        self.handle = symm.rendezvous(self.buf, group.group_name)
+        self.slab = RolloutSlab(T, n_local, obs_dim, act_dim, device, policy_fields, flat=self.buf[self.rank * nbytes:(self.rank + 1) * nbytes])
+        ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        self.peer_deltas = [ptrs[p] - ptrs[self.rank] for p in range(self.world) if p != self.rank]
+
+    def attach(self, sim):
+        """Route the step outputs of `sim` to every peer as well."""
+        sim.set_peer_fanout(self.peer_deltas)
+        return self
+
+    def barrier(self):
+        """All ranks' steps issued so far have completed and their peer stores are visible (device-side barrier on the
+        current stream; the host is not blocked)."""
+        self.handle.barrier()
+
+    def gathered(self) -> "GatheredRollout":
+        return GatheredRollout(self.buf.view(self.world, -1), self.slab)
 
 
 class GatheredRollout:

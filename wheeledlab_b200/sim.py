@@ -102,6 +102,13 @@ class WheeledSim:
         """step_counter value meaning "the counter base kept in device memory + k" (WL_DEVICE_COUNTER_PLUS)."""
         return -1 - k
 
+    def set_peer_fanout(self, byte_deltas):
+        """Every output row of step() is also stored at pointer + delta for each delta (peer symmetric buffers, see
+        distributed.SymmetricRolloutSlab); [] switches the fan-out off."""
+        n = len(byte_deltas)
+        arr = (C.c_int64 * max(1, n))(*byte_deltas)
+        check(lib.wl_set_peer_fanout(self._h, n, arr), "wl_set_peer_fanout")
+
     def set_step_counter(self, value: int):
         check(lib.wl_set_step_counter(self._h, value, _stream_ptr(self.device)), "wl_set_step_counter")
 
@@ -280,7 +287,7 @@ class WheeledSim:
         check(lib.wl_set_scan_tma(self._h, 1 if use_tma else 0), "wl_set_scan_tma")
 
     def set_kernel_variant(self, lanes_per_env: int):
-        """0 auto, 1 thread-per-env, 4 quad-per-env (bit-identical results)."""
+        """0 auto, 1 thread-per-env, 4 quad-per-env, 8 quad + aux warp (Drift family); bit-identical results."""
         check(lib.wl_set_kernel_variant(self._h, lanes_per_env), "wl_set_kernel_variant")
 
     @property
