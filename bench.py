@@ -325,13 +325,31 @@ def run_ours(args):
         s.startup(); s.reset(None, 0)
     T_ROLL = min(128, max(4, K // 2))                         # rsl_rl num_steps_per_env is 128 (rsl_rl_ppo_cfg.py:6); shortened so
     n_slabs = 2                                               # that the driver's short runs still time >= 1 all-gather
-    slabs = [RolloutSlab(T_ROLL, E, sim0.obs_dim, 2, dev) for _ in range(n_slabs)]
+    gather_mode, syms = "nccl", []
+    if world > 1 and args.gather in ("auto", "fanout") and w["task"] in ("drift", "hound_4wd"):
+        try:                                                  # fused exchange: step outputs stored into every peer's symmetric buffer
+            from wheeledlab_b200.distributed import SymmetricRolloutSlab
+            syms = [SymmetricRolloutSlab(T_ROLL, E, sim0.obs_dim, 2, dev) for _ in range(n_slabs)]
+            gather_mode = "fanout"
+        except Exception as ex:
+            if args.gather == "fanout":
+                raise
+            print(f"[bench] symmetric memory unavailable ({ex!r}); using the NCCL all-gather", file=sys.stderr)
+    slabs = [sy.slab for sy in syms] if syms else [RolloutSlab(T_ROLL, E, sim0.obs_dim, 2, dev) for _ in range(n_slabs)]
     acts = torch.stack([sim0.synth_actions(t) for t in range(max(8, min(W + K, 64)))])   # resident in HBM
     NA = acts.shape[0]
     tcount = [0] * M
 
     def make_bound(k):                                        # step k: env set k % M, slab row k % T_ROLL of slab (k // T_ROLL) % 2
-        return sims[k % M].bind_step(acts[k % NA], slabs[(k // T_ROLL) % n_slabs].step_outputs(k % T_ROLL))
+        fn = sims[k % M].bind_step(acts[k % NA], slabs[(k // T_ROLL) % n_slabs].step_outputs(k % T_ROLL))
+        if not syms:
+            return fn
+        sim_k, deltas = sims[k % M], syms[(k // T_ROLL) % n_slabs].peer_deltas
+
+        def fan(tc, _fn=fn, _sim=sim_k, _d=deltas):           # this step's rows also go to the same slab slot of every peer
+            _sim.set_peer_fanout(_d)
+            _fn(tc)
+        return fan
 
     bound_w = [make_bound(k) for k in range(W)]
     bound = [make_bound(W + k) for k in range(K)]
@@ -339,32 +357,56 @@ def run_ours(args):
     main = torch.cuda.current_stream()
 
     def run_steps(fns, k0, timed):
-        """Issue the steps back to back; with N > 1, ONE all-gather of the filled slab per T_ROLL steps on its own stream
-        (it overlaps the next steps; the step stream only waits when a slab is about to be refilled before its gather is done)."""
+        """Issue the steps back to back on the current stream; with N > 1, ONE exchange of the filled slab per T_ROLL steps:
+        gather mode "nccl": all_gather_into_tensor on its own stream (overlaps the next steps; the step stream only waits when
+        a slab is about to be refilled before its gather is done); mode "fanout": the steps have already stored their rows
+        into every peer's symmetric buffer -- only a device-side barrier remains."""
+        cur_stream = torch.cuda.current_stream()
         gev, gdone = [], [None] * n_slabs
         for j, fn in enumerate(fns):
             k = k0 + j
             row, cur = k % T_ROLL, (k // T_ROLL) % n_slabs
-            if world > 1 and row == 0 and gdone[cur] is not None:
-                main.wait_event(gdone[cur])
+            if world > 1 and gather_mode == "nccl" and row == 0 and gdone[cur] is not None:
+                cur_stream.wait_event(gdone[cur])
             m = k % M
             fn(tcount[m]); tcount[m] += 1
             if world > 1 and row == T_ROLL - 1:
-                filled = torch.cuda.Event(); filled.record()
-                with torch.cuda.stream(gstream):
-                    gstream.wait_event(filled)
-                    g0, g1 = torch.cuda.Event(enable_timing=timed), torch.cuda.Event(enable_timing=timed)
-                    g0.record(); slabs[cur].all_gather(); g1.record(); gev.append((g0, g1))
-                    gdone[cur] = g1
+                if gather_mode == "fanout":
+                    syms[cur].barrier(); gev.append(None)
+                else:
+                    filled = torch.cuda.Event(); filled.record()
+                    with torch.cuda.stream(gstream):
+                        gstream.wait_event(filled)
+                        g0, g1 = torch.cuda.Event(enable_timing=timed), torch.cuda.Event(enable_timing=timed)
+                        g0.record(); slabs[cur].all_gather(); g1.record(); gev.append((g0, g1))
+                        gdone[cur] = g1
         for g in gdone:                                       # the last gathers must be finished before the clock stops
             if g is not None:
-                main.wait_event(g)
+                cur_stream.wait_event(g)
         return gev
 
-    if world > 1:                                             # untimed: NCCL communicator / channel set-up, receive buffers
+    if world > 1 and gather_mode == "nccl":                   # untimed: NCCL communicator / channel set-up, receive buffers
         for sl in slabs:
             sl.all_gather()
     run_steps(bound_w, 0, False)
+    # the K timed steps are captured into ONE CUDA graph (how a rollout is meant to be driven: the Python + driver launch path
+    # costs ~8 us per step here, more than the kernel) and replayed once inside the timed region; eager launches if capture fails
+    graph, timing_mode = None, "eager stream launches"
+    if not args.eager:
+        keep = list(tcount)
+        try:
+            graph = torch.cuda.CUDAGraph()
+            cs_ = torch.cuda.Stream(device=dev)
+            cs_.wait_stream(main)
+            with torch.cuda.stream(cs_):
+                with torch.cuda.graph(graph, stream=cs_):
+                    gev = run_steps(bound, W, False)
+            main.wait_stream(cs_)
+            timing_mode = "one CUDA graph of the K steps, replayed once"
+        except Exception as ex:
+            print(f"[bench] graph capture failed ({ex!r}); timing eager launches", file=sys.stderr)
+            graph = None
+            tcount[:] = keep
     sampler = ClockSampler(list(range(world)) if world > 1 else local)
     barrier()
     if rank == 0:
@@ -372,16 +414,35 @@ def run_ours(args):
     l0 = sum(s.launch_count for s in sims)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    # a short spin kernel BEFORE the first event keeps the GPU busy while the host enqueues the graph launch, so that the
+    # timed region (e0 .. e1) holds the K steps and not the host's launch latency (the spin itself is outside the region)
+    torch.cuda._sleep(400_000)
     e0.record()
-    gev = run_steps(bound, W, True)
+    if graph is not None:
+        graph.replay()
+    else:
+        gev = run_steps(bound, W, True)
     e1.record()
     barrier()
     tot_ms = e0.elapsed_time(e1)
-    launches = sum(s.launch_count for s in sims) - l0
-    gather_each = [a.elapsed_time(b) for a, b in gev]
+    launches = (sum(s.launch_count for s in sims) - l0) if graph is None else K
+    n_exchanges = len(gev)
+    # duration of one exchange on its own (eager, outside the timed region): all-gather ms / barrier ms
+    gather_each = []
+    if world > 1:
+        for _ in range(3):
+            a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            a_.record()
+            if gather_mode == "fanout":
+                syms[0].barrier()
+            else:
+                slabs[0].all_gather()
+            b_.record(); torch.cuda.synchronize()
+            gather_each.append(a_.elapsed_time(b_))
     gather_ms = sum(gather_each)
-    if gev and rank == 0:
-        print(f"[bench] all-gather ms per call: {[round(x, 3) for x in gather_each]}", file=sys.stderr)
+    if gather_each and rank == 0:
+        print(f"[bench] slab exchange ({gather_mode}) ms per call, measured alone: {[round(x, 3) for x in gather_each]}", file=sys.stderr)
 
     # ---- round-1 protocol for comparison: per-step events, 256 MiB flush fill between steps; and its floor (empty kernel) ----
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
@@ -522,7 +583,6 @@ def run_ours(args):
         kern_s = tot_ms * 1e-3 / K
         achieved = w["bytes"] * E / kern_s / 1e9
         cpu = cpu_baseline(args.workload, E, args.seed, budget_s=args.cpu_budget) if world == 1 else None
-        n_gathers = len(gev)
         slab_bytes = slabs[0].nbytes
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
@@ -532,7 +592,7 @@ def run_ours(args):
                        "actions": "U[-1,1]^2 philox(seed,env,step)",
                        "l2": f"inputs larger than L2, no flush kernel: {M} independent {E}-env sets ({M * set_bytes / 1e6:.0f} MB of state + "
                              f"parameters) stepped round-robin, every step writes a fresh rollout-slab row ({n_slabs} x {slab_bytes / 1e6:.0f} MB)",
-                       "parallelism": f"env-shard x{world}", "timing": "2 CUDA events around the K back-to-back steps"},
+                       "parallelism": f"env-shard x{world}", "timing": f"2 CUDA events around the K back-to-back steps ({timing_mode})"},
             "clocks": clocks,
             "e2e": {"value": total_envs * K / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": E * 8,
                     "d2h_bytes_per_step": E * (6 + 4 * sim0.obs_dim), "ms_per_step": e2e_ms / K, "transport": best,
@@ -553,13 +613,15 @@ def run_ours(args):
                                "empty_kernel_us": null_us,
                                "note": "round-1 protocol: per-step events, 256 MiB L2-flush fill between steps; empty_kernel_us is the same "
                                        "measurement around an EMPTY kernel of the same geometry (the protocol's own floor)"},
-            "collective": {"kind": "all_gather_into_tensor(rollout slab)", "per_iteration_steps": T_ROLL,
-                           "bytes_per_rank": slab_bytes, "count": n_gathers, "ms_total": gather_ms,
-                           "ms_each": [round(x, 3) for x in gather_each],
-                           "bus_GBps": (slab_bytes * (world - 1) / (statistics.mean(gather_each) * 1e-3) / 1e9) if gather_each else None,
-                           "overlapped_with_next_iteration": True,
-                           "note": "double-buffered slabs; the gather of iteration i runs on its own stream under the steps of iteration i+1 "
-                                   "and all gathers are complete before the clock stops (inside the timed region)"}
+            "collective": {"kind": ("fused peer-memory fan-out: every step stores its slab rows into each peer's symmetric buffer over NVLink; "
+                                    "one device-side barrier per iteration") if gather_mode == "fanout" else "all_gather_into_tensor(rollout slab)",
+                           "mode": gather_mode, "per_iteration_steps": T_ROLL, "bytes_per_rank": slab_bytes, "count": n_exchanges,
+                           "ms_each_measured_alone": [round(x, 3) for x in gather_each],
+                           "nvlink_bytes_per_step_per_rank": (E * (4 * sim0.obs_dim + 6) * (world - 1)) if gather_mode == "fanout" else None,
+                           "bus_GBps": (slab_bytes * (world - 1) / (statistics.mean(gather_each) * 1e-3) / 1e9) if (gather_each and gather_mode == "nccl") else None,
+                           "inside_timed_region": True,
+                           "note": "every exchange of the K steps (count) completes before the clock stops; nccl mode: double-buffered slabs, the "
+                                   "gather of iteration i runs on its own stream under the steps of iteration i+1"}
             if world > 1 else None,
             "per_rank": per_rank,
             "policy_in_loop_graph": pil,
@@ -584,6 +646,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     ap.add_argument("--no-extras", action="store_true", help="skip the supplementary figures (policy-in-loop, fused rollout)")
+    ap.add_argument("--eager", action="store_true", help="time eager stream launches instead of one CUDA graph of the K steps")
+    ap.add_argument("--gather", default="auto", choices=["auto", "nccl", "fanout"],
+                    help="N > 1 slab exchange: NCCL all-gather, or the fused peer-memory fan-out (auto: fan-out when available)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

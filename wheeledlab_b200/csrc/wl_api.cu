@@ -6,6 +6,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <type_traits>
 
 #include <cuda.h>
 
@@ -27,6 +28,9 @@ struct wl_sim {
     int64_t base_host;      // host mirror of wl_globals.step_base
     uint8_t* term_bits;     // optional per-env termination-term bits output of wl_step (wl_set_term_bits)
     PeerFan fan;            // peers every output row of wl_step is also stored to (wl_set_peer_fanout); n = 0: none
+    const void* hp_host[8]; // wl_step_host_zero_copy: pinned host blocks already resolved to their device alias
+    void* hp_dev[8];
+    int hp_n;
     int device;             // CUDA device ordinal the handle lives on
     int obs_dim;
     int variant;            // 0 auto, 1 thread-per-env, 4 quad-per-env
@@ -445,6 +449,7 @@ struct DuoShared {
     float noise[WL_DUO_ENVS][12];   // observation noise normals (Philox blocks 0..2)
     float push[WL_DUO_ENVS][8];     // hf fired, dvx, dvy, dwz_hf, t_hf_new, lf fired, dwz_lf, t_lf_new
     float fin[WL_DUO_ENVS][16];     // post-physics: p(3) vb(3) wb(3) wz_world steer_l steer_r raw-tmask(bits)
+    __align__(16) float obs[WL_DUO_ENVS * WL_OBS_DIM_BLIND];   // the 8 observation rows of the CTA, staged for 128-bit stores
 };
 __device__ __forceinline__ void bar_arrive(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ void bar_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
@@ -641,7 +646,20 @@ wl_step_duo_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st,
     }
     const int k4 = (w < 3) ? 4 * w : 0;
     const float zn[4] = {sh.noise[q][k4], sh.noise[q][k4 + 1], sh.noise[q][k4 + 2], sh.noise[q][k4 + 3]};
-    blind_obs_quad(c, e, w, eu_k, vb, wbo, zn, obs + (size_t)WL_OBS_DIM_BLIND * ii, live, pf);
+    // the CTA's 8 observation rows are 448 contiguous bytes: staged in shared memory and written as 28 x 128-bit stores
+    // (full sectors towards HBM, NVLink peers and -- zero-copy host transport -- PCIe, instead of 8-byte pieces)
+    float* orow0 = obs + (size_t)WL_OBS_DIM_BLIND * env0;
+    if (env0 + WL_DUO_ENVS <= n && (reinterpret_cast<uintptr_t>(orow0) & 15u) == 0) {
+        const float4 v = blind_obs_quad_values(c, e, w, eu_k, vb, wbo, zn);
+        float* so = sh.obs + WL_OBS_DIM_BLIND * q + 4 * w;
+        so[0] = v.x; so[1] = v.y;
+        if (w < 3) { so[2] = v.z; so[3] = v.w; }
+        __syncwarp();
+        if (lane < (WL_DUO_ENVS * WL_OBS_DIM_BLIND) / 4)
+            fan_store(pf, reinterpret_cast<float4*>(orow0) + lane, reinterpret_cast<const float4*>(sh.obs)[lane]);
+    } else {
+        blind_obs_quad(c, e, w, eu_k, vb, wbo, zn, obs + (size_t)WL_OBS_DIM_BLIND * ii, live, pf);
+    }
     if (live) store_env_quad(st, n, i, w, e, false, false);
 }
 
@@ -1371,7 +1389,8 @@ wl_camera_kernel(const __grid_constant__ wl_config c, const float4* __restrict__
 // attribute is therefore OFF unless WL_PDL=1)
 static bool g_pdl = (getenv("WL_PDL") != nullptr) && (atoi(getenv("WL_PDL")) != 0);
 template <typename... KArgs, typename... Args>
-static void launch_k(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t cs, Args... args) {
+static void launch_k(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t cs, const Args&... args) {
+    static_assert(sizeof...(KArgs) == sizeof...(Args), "argument count");
     cudaLaunchConfig_t lc;
     memset(&lc, 0, sizeof lc);
     lc.gridDim = dim3((unsigned)grid); lc.blockDim = dim3((unsigned)block); lc.dynamicSmemBytes = smem; lc.stream = cs;
@@ -1379,7 +1398,11 @@ static void launch_k(void (*kernel)(KArgs...), int grid, int block, size_t smem,
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     lc.attrs = attr; lc.numAttrs = g_pdl ? 1 : 0;
-    cudaLaunchKernelEx(&lc, kernel, KArgs(args)...);
+    // parameters by address: the 1.5 KB wl_config is read in place by the runtime, not copied through a by-value call chain.
+    // (each argument must already have exactly the kernel's parameter type: checked below)
+    static_assert((std::is_same<typename std::decay<KArgs>::type, typename std::decay<Args>::type>::value && ...), "argument types must match the kernel's");
+    void* ptrs[] = {const_cast<void*>(static_cast<const void*>(&args))...};
+    cudaLaunchKernelExC(&lc, reinterpret_cast<const void*>(kernel), ptrs);
 }
 
 static inline int pick_block(int n) {
@@ -1560,6 +1583,7 @@ int wl_create(const wl_config* cfg, void* d_state, size_t state_bytes, const flo
     s->base_host = 0;
     s->term_bits = nullptr;
     memset(&s->fan, 0, sizeof s->fan);
+    s->hp_n = 0;
     cudaGetDevice(&s->device);
     s->variant = 0;
     s->has_tmap = false;
@@ -1801,15 +1825,23 @@ int wl_step_host(wl_sim* sim, const float* h_action, float* d_action, float* d_o
     return cuda_check(cudaStreamSynchronize(cs), "wl_step_host: stream synchronize");
 }
 
+// device alias of a pinned host block (cudaHostGetDevicePointer costs ~0.5 us per call: resolved once per block and cached)
+static void* host_alias(wl_sim* sim, const void* h) {
+    for (int k = 0; k < sim->hp_n; ++k) if (sim->hp_host[k] == h) return sim->hp_dev[k];
+    void* d = nullptr;
+    if (cudaHostGetDevicePointer(&d, const_cast<void*>(h), 0) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    const int slot = sim->hp_n < 8 ? sim->hp_n++ : (int)(((uintptr_t)h >> 6) & 7u);
+    sim->hp_host[slot] = h; sim->hp_dev[slot] = d;
+    return d;
+}
+
 int wl_step_host_zero_copy(wl_sim* sim, const float* h_action, float* d_obs, float* d_log, void* h_result,
                            int64_t step_counter, void* stream) {
     if (!sim || !h_action || !d_obs || !h_result) return fail(WL_EINVAL, "wl_step_host_zero_copy: null argument");
     const size_t n = (size_t)sim->cfg.num_envs;
-    const float* da = nullptr; void* dr = nullptr;
-    if (cudaHostGetDevicePointer((void**)&da, (void*)h_action, 0) != cudaSuccess || cudaHostGetDevicePointer(&dr, h_result, 0) != cudaSuccess) {
-        cudaGetLastError();
-        return fail(WL_EINVAL, "wl_step_host_zero_copy: h_action / h_result must be pinned (device-mapped) host memory");
-    }
+    const float* da = reinterpret_cast<const float*>(host_alias(sim, h_action));
+    void* dr = host_alias(sim, h_result);
+    if (!da || !dr) return fail(WL_EINVAL, "wl_step_host_zero_copy: h_action / h_result must be pinned (device-mapped) host memory");
     float* d_rew = reinterpret_cast<float*>(dr);
     uint8_t* d_term = reinterpret_cast<uint8_t*>(dr) + n * 4;
     uint8_t* d_trunc = d_term + n;

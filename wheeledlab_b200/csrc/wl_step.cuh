@@ -695,23 +695,24 @@ __device__ __forceinline__ void quad_obs_noise(const wl_config& c, int w, uint32
         box_muller(r.z, r.w, z[2], z[3]);
     }
 }
-__device__ __forceinline__ void blind_obs_quad(const wl_config& c, const EnvState& e, int w, float eu_k, V3 vb, V3 wb, const float z[4],
-                                               float* __restrict__ obs, bool live, const PeerFan& pf = PeerFan{0, 0, {0, 0, 0, 0, 0, 0, 0, 0}}) {
+// this lane's slice of the 14-float row: lanes 0..2 four floats (obs[4w..4w+3], noise added), lane 3 the two last-action floats
+__device__ __forceinline__ float4 blind_obs_quad_values(const wl_config& c, const EnvState& e, int w, float eu_k, V3 vb, V3 wb, const float z[4]) {
     const unsigned base = (threadIdx.x & 31u) & ~3u;
     float eu1 = __shfl_sync(0xffffffffu, eu_k, base + 1), eu2 = __shfl_sync(0xffffffffu, eu_k, base + 2);
     float b0, b1, b2, b3, s0, s1, s2, s3;
     if (w == 0) { b0 = e.p.x; b1 = e.p.y; b2 = e.p.z; b3 = eu_k; s0 = s1 = s2 = c.noise_std[0]; s3 = c.noise_std[1]; }
     else if (w == 1) { b0 = eu1; b1 = eu2; b2 = vb.x; b3 = vb.y; s0 = s1 = c.noise_std[1]; s2 = s3 = c.noise_std[2]; }
     else if (w == 2) { b0 = vb.z; b1 = wb.x; b2 = wb.y; b3 = wb.z; s0 = c.noise_std[2]; s1 = s2 = s3 = c.noise_std[3]; }
-    else { b0 = r_clamp(e.action[0], -1.0f, 1.0f); b1 = r_clamp(e.action[1], -1.0f, 1.0f); b2 = b3 = 0.0f; s0 = s1 = s2 = s3 = 0.0f; }
+    else { return make_float4(r_clamp(e.action[0], -1.0f, 1.0f), r_clamp(e.action[1], -1.0f, 1.0f), 0.0f, 0.0f); }
+    return make_float4(b0 + s0 * z[0], b1 + s1 * z[1], b2 + s2 * z[2], b3 + s3 * z[3]);
+}
+__device__ __forceinline__ void blind_obs_quad(const wl_config& c, const EnvState& e, int w, float eu_k, V3 vb, V3 wb, const float z[4],
+                                               float* __restrict__ obs, bool live, const PeerFan& pf = PeerFan{0, 0, {0, 0, 0, 0, 0, 0, 0, 0}}) {
+    const float4 v = blind_obs_quad_values(c, e, w, eu_k, vb, wb, z);
     float2* o2 = reinterpret_cast<float2*>(obs + 4 * w);
     if (!live) return;
-    if (w < 3) {
-        fan_store(pf, &o2[0], make_float2(b0 + s0 * z[0], b1 + s1 * z[1]));
-        fan_store(pf, &o2[1], make_float2(b2 + s2 * z[2], b3 + s3 * z[3]));
-    } else {
-        fan_store(pf, &o2[0], make_float2(b0, b1));
-    }
+    fan_store(pf, &o2[0], make_float2(v.x, v.y));
+    if (w < 3) fan_store(pf, &o2[1], make_float2(v.z, v.w));
 }
 
 }  // namespace wl
