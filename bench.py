@@ -326,14 +326,15 @@ def run_ours(args):
     T_ROLL = min(128, max(4, K // 2))                         # rsl_rl num_steps_per_env is 128 (rsl_rl_ppo_cfg.py:6); shortened so
     n_slabs = 2                                               # that the driver's short runs still time >= 1 all-gather
     gather_mode, syms = "nccl", []
-    if world > 1 and args.gather in ("auto", "fanout") and w["task"] in ("drift", "hound_4wd"):
-        try:                                                  # fused exchange: step outputs stored into every peer's symmetric buffer
+    if world > 1 and args.gather in ("auto", "fanout", "ce"):
+        try:                                                  # symmetric (P2P-mapped) slabs: copy-engine pull, or the fused fan-out
             from wheeledlab_b200.distributed import SymmetricRolloutSlab
             syms = [SymmetricRolloutSlab(T_ROLL, E, sim0.obs_dim, 2, dev) for _ in range(n_slabs)]
-            gather_mode = "fanout"
+            gather_mode = "fanout" if (args.gather == "fanout" and w["task"] in ("drift", "hound_4wd")) else "ce"
         except Exception as ex:
-            if args.gather == "fanout":
+            if args.gather != "auto":
                 raise
+            syms = []
             print(f"[bench] symmetric memory unavailable ({ex!r}); using the NCCL all-gather", file=sys.stderr)
     slabs = [sy.slab for sy in syms] if syms else [RolloutSlab(T_ROLL, E, sim0.obs_dim, 2, dev) for _ in range(n_slabs)]
     acts = torch.stack([sim0.synth_actions(t) for t in range(max(8, min(W + K, 64)))])   # resident in HBM
@@ -343,6 +344,8 @@ def run_ours(args):
     def make_bound(k):                                        # step k: env set k % M, slab row k % T_ROLL of slab (k // T_ROLL) % 2
         fn = sims[k % M].bind_step(acts[k % NA], slabs[(k // T_ROLL) % n_slabs].step_outputs(k % T_ROLL))
         if not syms:
+            return fn
+        if gather_mode != "fanout":
             return fn
         sim_k, deltas = sims[k % M], syms[(k // T_ROLL) % n_slabs].peer_deltas
 
@@ -366,7 +369,7 @@ def run_ours(args):
         for j, fn in enumerate(fns):
             k = k0 + j
             row, cur = k % T_ROLL, (k // T_ROLL) % n_slabs
-            if world > 1 and gather_mode == "nccl" and row == 0 and gdone[cur] is not None:
+            if world > 1 and gather_mode != "fanout" and row == 0 and gdone[cur] is not None:
                 cur_stream.wait_event(gdone[cur])
             m = k % M
             fn(tcount[m]); tcount[m] += 1
@@ -378,7 +381,12 @@ def run_ours(args):
                     with torch.cuda.stream(gstream):
                         gstream.wait_event(filled)
                         g0, g1 = torch.cuda.Event(enable_timing=timed), torch.cuda.Event(enable_timing=timed)
-                        g0.record(); slabs[cur].all_gather(); g1.record(); gev.append((g0, g1))
+                        g0.record()
+                        if gather_mode == "ce":
+                            syms[cur].gather_ce()
+                        else:
+                            slabs[cur].all_gather()
+                        g1.record(); gev.append((g0, g1))
                         gdone[cur] = g1
         for g in gdone:                                       # the last gathers must be finished before the clock stops
             if g is not None:
@@ -436,6 +444,8 @@ def run_ours(args):
             a_.record()
             if gather_mode == "fanout":
                 syms[0].barrier()
+            elif gather_mode == "ce":
+                syms[0].gather_ce()
             else:
                 slabs[0].all_gather()
             b_.record(); torch.cuda.synchronize()
@@ -613,12 +623,14 @@ def run_ours(args):
                                "empty_kernel_us": null_us,
                                "note": "round-1 protocol: per-step events, 256 MiB L2-flush fill between steps; empty_kernel_us is the same "
                                        "measurement around an EMPTY kernel of the same geometry (the protocol's own floor)"},
-            "collective": {"kind": ("fused peer-memory fan-out: every step stores its slab rows into each peer's symmetric buffer over NVLink; "
-                                    "one device-side barrier per iteration") if gather_mode == "fanout" else "all_gather_into_tensor(rollout slab)",
+            "collective": {"kind": {"fanout": "fused peer-memory fan-out: every step stores its slab rows into each peer's symmetric buffer over NVLink; "
+                                              "one device-side barrier per iteration",
+                                    "ce": "copy-engine pull: barrier, world-1 P2P memcpys of the peers' slabs over NVLink (no SM), barrier",
+                                    "nccl": "all_gather_into_tensor(rollout slab)"}[gather_mode],
                            "mode": gather_mode, "per_iteration_steps": T_ROLL, "bytes_per_rank": slab_bytes, "count": n_exchanges,
                            "ms_each_measured_alone": [round(x, 3) for x in gather_each],
                            "nvlink_bytes_per_step_per_rank": (E * (4 * sim0.obs_dim + 6) * (world - 1)) if gather_mode == "fanout" else None,
-                           "bus_GBps": (slab_bytes * (world - 1) / (statistics.mean(gather_each) * 1e-3) / 1e9) if (gather_each and gather_mode == "nccl") else None,
+                           "bus_GBps": (slab_bytes * (world - 1) / (statistics.mean(gather_each) * 1e-3) / 1e9) if (gather_each and gather_mode != "fanout") else None,
                            "inside_timed_region": True,
                            "note": "every exchange of the K steps (count) completes before the clock stops; nccl mode: double-buffered slabs, the "
                                    "gather of iteration i runs on its own stream under the steps of iteration i+1"}
@@ -631,8 +643,10 @@ def run_ours(args):
                               "note": "K steps of ONE env set captured in one CUDA graph (PDL edges), state L2-resident (supplementary)"},
         }
         guard.emit(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    if world > 1:                                             # (symmetric-memory / graph teardown can stall at interpreter exit: leave at once)
+        dist.barrier()
+        sys.stdout.flush(); sys.stderr.flush()
+        os._exit(0)
 
 
 def main():
@@ -647,8 +661,9 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     ap.add_argument("--no-extras", action="store_true", help="skip the supplementary figures (policy-in-loop, fused rollout)")
     ap.add_argument("--eager", action="store_true", help="time eager stream launches instead of one CUDA graph of the K steps")
-    ap.add_argument("--gather", default="auto", choices=["auto", "nccl", "fanout"],
-                    help="N > 1 slab exchange: NCCL all-gather, or the fused peer-memory fan-out (auto: fan-out when available)")
+    ap.add_argument("--gather", default="auto", choices=["auto", "nccl", "ce", "fanout"],
+                    help="N > 1 slab exchange: NCCL all-gather, copy-engine pull over symmetric memory (auto, when available), or the "
+                         "fan-out fused into the step kernel")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

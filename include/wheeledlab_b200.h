@@ -510,6 +510,15 @@ int wl_gae(const float* d_rewards, const float* d_values, const float* d_last_va
            const uint8_t* d_time_outs, float gamma, float lam, float* d_returns, float* d_advantages, int32_t T,
            int32_t N, void* stream);
 
+/* ---- the learner's data-parallel step for the small policy networks --------------------------------------
+ * Gradient all-reduce fused with the Adam update, one kernel over peer memory: d_grads[r] = rank r's flat fp32 gradient
+ * (this rank's own buffer and the P2P-mapped buffers of its peers, e.g. slices of one torch symmetric-memory allocation; the
+ * same rank order on every rank, so every replica forms the identical mean); d_param / d_m / d_v = this rank's flat
+ * parameters and Adam moments, n floats each.  `step` = 1, 2, ... (bias correction).  The caller brackets the launch with
+ * barriers (all gradients written before; none overwritten until every rank has read them).  n_ranks = 1 is plain Adam. */
+int wl_dp_adam_step(float* d_param, float* d_m, float* d_v, int32_t n_ranks, const float* const* d_grads, float lr, float beta1,
+                    float beta2, float eps, float weight_decay, int32_t step, int32_t n, void* stream);
+
 /* ---- test hooks (bit-exactness of the deterministic math vs the oracle) ------ */
 /* op: 0 sin,1 cos,2 atan,3 atan2(x=in,y=in2),4 log,5 tan,6 asin,7 exp,8 tanh ; out[n] */
 int wl_test_detmath(int32_t op, const float* d_in, const float* d_in2, float* d_out, int32_t n,

@@ -5,6 +5,10 @@ state accessors only).  Run in the authoring container:
 
     python tests/golden/make_golden.py          # writes tests/golden/*.npz
 
+Two kinds of fixture: values produced by the REFERENCE'S OWN functions (action terms, drift / elevation /
+visual term functions, reset_root_state_along_track, the curriculum term, the camera post-processing), and values that pass
+through an IsaacLab function restated in shims/ ([UPSTREAM-RECALL]: is_terminated_term, euler_xyz_from_quat,
+quat_from_euler_xyz) -- the latter pin the oracle to the restatement, not to IsaacLab.
 The vectors pin the oracle's restatement of: the action terms (ackermann_actions.py, rc_car_actions.py), the
 drift reward/termination terms (mushr_drift_env_cfg.py:160-240,343-348), reset_root_state_along_track
 (drifting/mdp/events.py), increase_reward_weight_over_time (curriculums.py), root_euler_xyz.  They cannot
@@ -149,7 +153,9 @@ def golden_drift_terms():
     out["w_term_pens"] = np.float32(R.term_pens.weight)
     oob = T.out_of_bounds.func(env, **T.out_of_bounds.params)
     out["out_of_bounds"] = oob.numpy().astype(np.uint8)
-    # is_terminated_term via the stand-in manager semantics
+    # is_terminated_term: [UPSTREAM-RECALL] -- evaluated through shims/isaaclab/envs/mdp/rewards.py (IsaacLab's function restated
+    # from memory: sum of the named terms' masks times ~time_outs), NOT through the reference's own code; this fixture pins the
+    # oracle to that restatement only
     env.termination_manager.active_terms = ["time_out", "out_of_bounds"]
     env.termination_manager.get_term = lambda k: oob if k == "out_of_bounds" else torch.zeros(n, dtype=torch.bool)
     env.termination_manager.time_outs = (torch.arange(n) % 7 == 0)
@@ -217,6 +223,8 @@ def golden_elevation():
     g = torch.Generator().manual_seed(9)
     pos = torch.cat([torch.rand(n, 2, generator=g) * 38 - 19, torch.rand(n, 1, generator=g) * 0.6 + 0.05], -1)
     rpy = torch.randn(n, 3, generator=g) * torch.tensor([0.5, 0.5, 2.0])
+    # [UPSTREAM-RECALL]: quat_from_euler_xyz / euler_xyz_from_quat live in shims/isaaclab/utils/math.py (IsaacLab's functions
+    # restated from memory); only root_euler_xyz itself (wheeledlab/envs/mdp/observations.py:9-12) is the reference's own code
     quat = math_utils.quat_from_euler_xyz(rpy[:, 0], rpy[:, 1], rpy[:, 2])
     vel_w = torch.randn(n, 3, generator=g) * torch.tensor([1.0, 1.0, 0.3])
     ang_w = torch.randn(n, 3, generator=g)

@@ -510,7 +510,7 @@ def test_gae_matches_rsl_rl_formula():
     _need_gpu()
     from wheeledlab_b200.learner import compute_returns
     torch.manual_seed(0)
-    for T, N in ((128, 4096), (5, 33), (1, 1)):
+    for T, N in ((128, 4096), (100, 1000), (256, 64), (24, 8192), (300, 512), (5, 33), (1, 1)):   # segment-parallel (T <= 256) and streaming scans
         rew = torch.randn(T, N, device="cuda"); val = torch.randn(T, N, device="cuda"); last = torch.randn(N, device="cuda")
         done = torch.rand(T, N, device="cuda") < 0.05
         tout = done & (torch.rand(T, N, device="cuda") < 0.5)
@@ -915,11 +915,12 @@ def test_vehicle_at_rest_stays_at_rest_on_the_gpu():
     assert float(sim.wheel_vel.abs().max()) < 1e-2
 
 
-@pytest.mark.parametrize("mode", ["nccl", "fanout"])
+@pytest.mark.parametrize("mode", ["nccl", "fanout", "ce"])
 def test_two_process_nccl_gather_equals_single_rank(tmp_path, mode):
     """BASELINE configs[4] at test size: 2 ranks x 2048 envs, the exchanged rollout slab == the slab of one 4096-env process,
     bit for bit (skipped when the box has a single GPU).  mode "nccl": one all_gather_into_tensor of the slab; "fanout": the
-    step kernel stores its output rows into the peer's symmetric buffer over NVLink (no collective)."""
+    step kernel stores its output rows into the peer's symmetric buffer over NVLink (no collective); "ce": copy-engine pull of the peer's slab
+    out of symmetric memory (no SM)."""
     _need_gpu()
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
@@ -927,7 +928,7 @@ def test_two_process_nccl_gather_equals_single_rank(tmp_path, mode):
     root = Path(__file__).resolve().parent.parent
     out = tmp_path / "slab.pt"
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-           "--master-port", "29731" if mode == "nccl" else "29733", str(root / "tools" / "nccl_slab_check.py"), "--out", str(out), "--envs", "2048",
+           "--master-port", {"nccl": "29731", "fanout": "29733", "ce": "29735"}[mode], str(root / "tools" / "nccl_slab_check.py"), "--out", str(out), "--envs", "2048",
            "--steps", "16", "--mode", mode]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
@@ -1030,3 +1031,35 @@ def test_fast_div_sqrt_are_ieee():
     den = rng.uniform(0.5, 1.0e3, n).astype(np.float32)
     num = (10.0 * 2.0 ** rng.uniform(-40, 12, n)).astype(np.float32)
     assert np.array_equal(_bits(run(11, den, num)), _bits(run(12, den, num)))
+
+
+def test_fused_adam_matches_torch_adam_single_rank():
+    """wl_dp_adam_step with one rank == torch.optim.Adam (the data-parallel form is covered by the 2-GPU test below)."""
+    _need_gpu()
+    from wheeledlab_b200.learner import DataParallelAdam
+    torch.manual_seed(0)
+    mk = lambda: torch.nn.Sequential(torch.nn.Linear(14, 64), torch.nn.ELU(), torch.nn.Linear(64, 64), torch.nn.ELU(), torch.nn.Linear(64, 2)).cuda()
+    net, ref = mk(), mk()
+    ref.load_state_dict(net.state_dict())
+    opt, ropt = DataParallelAdam(net.parameters(), lr=3e-3), torch.optim.Adam(ref.parameters(), lr=3e-3)
+    for it in range(20):
+        x, y = torch.randn(512, 14, device="cuda"), torch.randn(512, 2, device="cuda")
+        opt.zero_grad(); ((net(x) - y) ** 2).mean().backward(); opt.step()
+        ropt.zero_grad(); ((ref(x) - y) ** 2).mean().backward(); ropt.step()
+    err = max(float((p - q).abs().max()) for p, q in zip(net.parameters(), ref.parameters()))
+    assert err < 5e-6, err
+
+
+def test_two_process_fused_allreduce_adam(tmp_path):
+    """DP learner step: gradient all-reduce fused into the Adam kernel over symmetric memory, 2 ranks, vs
+    torch.optim.Adam on the NCCL-averaged gradient; replicas stay bit-identical (skipped on a single-GPU box)."""
+    _need_gpu()
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import subprocess, sys
+    root = Path(__file__).resolve().parent.parent
+    out = tmp_path / "ok.txt"
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29737", str(root / "tools" / "dp_adam_check.py"), "--out", str(out)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and out.read_text().startswith("ok"), r.stderr[-2000:]

@@ -1,14 +1,19 @@
-# multi-GPU run: $1 = number of GPUs
-N=${1:-2}
+# multi-GPU run: $1 = number of GPUs, $2 = what (tests|bench|all); every command has a SHORT timeout (a hung collective must not burn the budget)
+N=${1:-2}; WHAT=${2:-all}
 mkdir -p gpurun_out
-nvidia-smi topo -m > gpurun_out/r02_topo_n$N.txt 2>&1
-timeout 600 python -m pytest tests -m gpu -x -q -k "two_process" 2>&1 | tail -8 > gpurun_out/r02_gputest_mg_n$N.log; cat gpurun_out/r02_gputest_mg_n$N.log | tail -5
-for mode in fanout nccl; do
-  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29811 bench.py --gpus $N --steps 20 --warmup 5 --no-extras --gather $mode > gpurun_out/r02_bench_n${N}_${mode}_k20.json 2> gpurun_out/r02_bench_n${N}_${mode}_k20.err
-  tail -4 gpurun_out/r02_bench_n${N}_${mode}_k20.err
-  python -c "
-import json; d=json.load(open('gpurun_out/r02_bench_n${N}_${mode}_k20.json')); print('$mode K=20', d['value'], d['ms_per_step'], d['collective']['count'], d['collective']['ms_each_measured_alone'], d['collective'].get('bus_GBps'), d['per_rank'])"
-  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29813 bench.py --gpus $N --steps 300 --warmup 20 --no-extras --gather $mode > gpurun_out/r02_bench_n${N}_${mode}_k300.json 2> gpurun_out/r02_bench_n${N}_${mode}_k300.err
-  python -c "
-import json; d=json.load(open('gpurun_out/r02_bench_n${N}_${mode}_k300.json')); print('$mode K=300', d['value'], d['ms_per_step'], d['collective']['count'], d['collective']['ms_each_measured_alone'], d['collective'].get('bus_GBps'))"
-done
+export TORCH_NCCL_ASYNC_ERROR_HANDLING=1 NCCL_DEBUG=WARN
+if [ "$WHAT" = tests ] || [ "$WHAT" = all ]; then
+  for t in "two_process_nccl_gather_equals_single_rank and nccl" "two_process_nccl_gather_equals_single_rank and fanout" "two_process_fused_allreduce_adam"; do
+    timeout 170 python -m pytest tests -m gpu -x -q -k "$t" 2>&1 | tail -12 > gpurun_out/r02_gputest_mg_n$N.log; echo "== $t"; tail -6 gpurun_out/r02_gputest_mg_n$N.log
+  done
+fi
+if [ "$WHAT" = bench ] || [ "$WHAT" = all ]; then
+  for mode in fanout nccl; do
+    for K in 20 300; do
+      timeout 170 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 298$K bench.py --gpus $N --steps $K --warmup 5 --no-extras --gather $mode > gpurun_out/r02_bench_n${N}_${mode}_k$K.json 2> gpurun_out/r02_bench_n${N}_${mode}_k$K.err
+      echo "== $mode K=$K rc=$?"; grep -v "^$" gpurun_out/r02_bench_n${N}_${mode}_k$K.err | tail -4
+      python -c "
+import json; d=json.load(open('gpurun_out/r02_bench_n${N}_${mode}_k$K.json')); print('$mode K=$K', d['value'], d['ms_per_step'], d['config']['timing'][-40:], d['collective']['count'], d['collective']['ms_each_measured_alone'], d['collective'].get('bus_GBps'), d['per_rank'])" 2>&1 | tail -1
+    done
+  done
+fi

@@ -20,7 +20,7 @@ def main():
     ap.add_argument("--envs", type=int, default=2048)
     ap.add_argument("--steps", type=int, default=16)
     ap.add_argument("--seed", type=int, default=42)
-    ap.add_argument("--mode", default="nccl", choices=["nccl", "fanout"])
+    ap.add_argument("--mode", default="nccl", choices=["nccl", "fanout", "ce"])
     a = ap.parse_args()
     import wheeledlab_b200 as wl
     from wheeledlab_b200.distributed import RolloutSlab
@@ -32,11 +32,13 @@ def main():
     sim = wl.WheeledSim(wl.drift_task(num_envs=a.envs, seed=a.seed, env_id_offset=rank * a.envs), dev)
     sim.startup(); sim.reset(None, 0)
     fields = ("obs", "actions", "rewards", "terminated", "truncated")
-    if a.mode == "fanout":                       # fused: the step kernel stores its rows into every peer's symmetric buffer
+    if a.mode in ("fanout", "ce"):
         from wheeledlab_b200.distributed import SymmetricRolloutSlab
-        sym = SymmetricRolloutSlab(a.steps, a.envs, sim.obs_dim, 2, dev).attach(sim)
+        sym = SymmetricRolloutSlab(a.steps, a.envs, sim.obs_dim, 2, dev)
         slab = sym.slab
-        fields = ("obs", "rewards", "terminated", "truncated")       # (actions are written by the caller, not by env.step)
+        if a.mode == "fanout":                   # fused: the step kernel stores its rows into every peer's symmetric buffer
+            sym.attach(sim)
+            fields = ("obs", "rewards", "terminated", "truncated")   # (actions are written by the caller, not by env.step)
     else:
         slab = RolloutSlab(a.steps, a.envs, sim.obs_dim, 2, dev)
     for t in range(a.steps):
@@ -46,6 +48,8 @@ def main():
     if a.mode == "fanout":
         sym.barrier(); torch.cuda.synchronize(); dist.barrier()
         g = sym.gathered()
+    elif a.mode == "ce":                         # copy-engine pull of the peers' slabs
+        g = sym.gather_ce()
     else:
         g = slab.all_gather()
     torch.cuda.synchronize()

@@ -26,6 +26,21 @@ def timed(fn, reps=50, warm=5):
     return statistics.median(a.elapsed_time(b) for a, b in ev) * 1e3      # us
 
 
+def timed_graph(fn, reps=20):
+    """Device time per call with the host out of the picture: `reps` calls captured in ONE CUDA graph, replayed."""
+    fn(); torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph(); s = torch.cuda.Stream(); s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        with torch.cuda.graph(g, stream=s):
+            for _ in range(reps):
+                fn()
+    torch.cuda.current_stream().wait_stream(s)
+    g.replay(); torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(); g.replay(); b.record(); torch.cuda.synchronize()
+    return a.elapsed_time(b) * 1e3 / reps
+
+
 def main():
     dev = "cuda:0"
     peak, src = _peaks()
@@ -36,9 +51,17 @@ def main():
         r, v = torch.randn(T, N, device=dev), torch.randn(T, N, device=dev)
         lv = torch.randn(N, device=dev)
         d = (torch.rand(T, N, device=dev) < 0.02).to(torch.uint8); to = (torch.rand(T, N, device=dev) < 0.01).to(torch.uint8)
-        us = timed(lambda: compute_returns(r, v, lv, d, 0.99, 0.95, to), reps=20)
+        import ctypes as C
+        ret, adv = torch.empty_like(r), torch.empty_like(r)
+        P = lambda x: C.c_void_p(x.data_ptr())
+
+        def gae():
+            wl.lib.wl_gae(P(r), P(v), P(lv), P(d), P(to), 0.99, 0.95, P(ret), P(adv), T, N, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        us = timed_graph(gae)
+        us_eager = timed(lambda: compute_returns(r, v, lv, d, 0.99, 0.95, to), reps=20)
         nbytes = T * N * (4 + 4 + 1 + 1 + 4 + 4) + 4 * N
-        rows.append({"T": T, "N": N, "us": us, "bytes": nbytes, "GBps": nbytes / us / 1e3, "frac_of_peak": nbytes / us / 1e3 / peak})
+        rows.append({"T": T, "N": N, "us": us, "us_eager_incl_python_and_alloc": us_eager, "bytes": nbytes, "GBps": nbytes / us / 1e3,
+                     "frac_of_peak": nbytes / us / 1e3 / peak, "kernel": "wl_gae_seg_kernel" if N <= 65536 else "wl_gae_kernel"})
     out["wl_gae"] = rows
     # ---- f-3: staged step (a + b) vs the fused step, and env.step with one Python reward term
     n = 4096

@@ -951,39 +951,40 @@ wl_scan_kernel(const __grid_constant__ wl_config c, const __grid_constant__ CUte
                const float* __restrict__ hf, float* __restrict__ obs) {
     __shared__ __align__(128) float tile[WL_TILE_W * WL_TILE_H];
     __shared__ __align__(8) unsigned long long mbar;
+    __shared__ float sp[8];                  // per-env constants of the scan, formed ONCE by thread 0: bx by bz cy sy pz ox oy
     const int n = c.num_envs;
     const int i = blockIdx.x;
-    float4 g0 = ldg4(st, WL_G_POS, n, i), g1 = ldg4(st, WL_G_QUAT, n, i);
-    EnvState e; e.p = V3{g0.x, g0.y, g0.z}; e.qw = g1.x; e.qx = g1.y; e.qy = g1.z; e.qz = g1.w;
-    M3 R = rotmat(e.qw, e.qx, e.qy, e.qz);
-    // ray-caster parent = base_link (root + R (0,0,base_link_z)); rays are yaw-aligned (attach_yaw_only)
-    const float bx = fm(c.base_link_z, R.r[2], e.p.x), by = fm(c.base_link_z, R.r[5], e.p.y), bz = fm(c.base_link_z, R.r[8], e.p.z);
-    float cy, sy; yaw_cs(e, cy, sy);
     const float inv = c.d_inv_hf_cell;
-    // window origin (in samples): covers base +- (half*sqrt2 + 1 cell)
-    const float reach = c.scan_half * 1.41421356237f + c.hf_cell;
-    const int ox = ((int)floorf((bx - reach - c.hf_x0) * inv)) & ~3;      // two's complement: rounds toward -inf
-    const int oy = (int)floorf((by - reach - c.hf_y0) * inv);
-    if (USE_TMA) {
-        if (threadIdx.x == 0) {
-            const uint32_t mb = smem_u32(&mbar);
+    if (threadIdx.x == 0) {
+        float4 g0 = ldg4(st, WL_G_POS, n, i), g1 = ldg4(st, WL_G_QUAT, n, i);
+        EnvState e0; e0.p = V3{g0.x, g0.y, g0.z}; e0.qw = g1.x; e0.qx = g1.y; e0.qy = g1.z; e0.qz = g1.w;
+        M3 R = rotmat(e0.qw, e0.qx, e0.qy, e0.qz);
+        // ray-caster parent = base_link (root + R (0,0,base_link_z)); rays are yaw-aligned (attach_yaw_only)
+        const float bx0 = fm(c.base_link_z, R.r[2], e0.p.x), by0 = fm(c.base_link_z, R.r[5], e0.p.y), bz0 = fm(c.base_link_z, R.r[8], e0.p.z);
+        float cy0, sy0; yaw_cs(e0, cy0, sy0);
+        // window origin (in samples): covers base +- (half*sqrt2 + 1 cell)
+        const float reach = c.scan_half * 1.41421356237f + c.hf_cell;
+        const int ox0 = ((int)floorf((bx0 - reach - c.hf_x0) * inv)) & ~3;      // two's complement: rounds toward -inf
+        const int oy0 = (int)floorf((by0 - reach - c.hf_y0) * inv);
+        sp[0] = bx0; sp[1] = by0; sp[2] = bz0; sp[3] = cy0; sp[4] = sy0; sp[5] = e0.p.z; sp[6] = __int_as_float(ox0); sp[7] = __int_as_float(oy0);
+        if (USE_TMA) {
+            const uint32_t mb = smem_u32(&mbar), dst = smem_u32(tile);
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb));
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            const uint32_t mb = smem_u32(&mbar), dst = smem_u32(tile);
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"((uint32_t)(WL_TILE_W * WL_TILE_H * 4)) : "memory");
             asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                         ::"r"(dst), "l"(&tmap), "r"(ox), "r"(oy), "r"(mb) : "memory");
+                         ::"r"(dst), "l"(&tmap), "r"(ox0), "r"(oy0), "r"(mb) : "memory");
         }
-        {   // all threads wait for the bytes (phase 0)
-            const uint32_t mb = smem_u32(&mbar);
-            uint32_t ok = 0;
-            while (!ok) {
-                asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-                             : "=r"(ok) : "r"(mb), "r"(0u) : "memory");
-            }
+    }
+    __syncthreads();                         // constants + mbarrier visible to everyone
+    const float bx = sp[0], by = sp[1], bz = sp[2], cy = sp[3], sy = sp[4], pz = sp[5];
+    const int ox = __float_as_int(sp[6]), oy = __float_as_int(sp[7]);
+    if (USE_TMA) {
+        const uint32_t mb = smem_u32(&mbar);     // all threads wait for the bytes (phase 0)
+        uint32_t ok = 0;
+        while (!ok) {
+            asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                         : "=r"(ok) : "r"(mb), "r"(0u) : "memory");
         }
     } else {
         for (int k = threadIdx.x; k < WL_TILE_W * WL_TILE_H; k += WL_SCAN_THREADS) {
@@ -1014,7 +1015,7 @@ wl_scan_kernel(const __grid_constant__ wl_config c, const __grid_constant__ CUte
                 const float za = fm(z10 - z00, tx, z00), zb = fm(z11 - z01, tx, z01);
                 const float hit = fm(zb - za, ty, za);
                 const float hs = bz - hit - c.scan_offset;                           // mdp.height_scan
-                v = r_clamp(-hs + (e.p.z - c.scan_plane_init), -c.obs_clip, c.obs_clip);   // world_height_map, clip
+                v = r_clamp(-hs + (pz - c.scan_plane_init), -c.obs_clip, c.obs_clip);     // world_height_map, clip
             }
             row[ry * WL_SCAN_SIDE + rx] = v;
         }
@@ -1224,6 +1225,91 @@ wl_gae_kernel(const float* __restrict__ rew, const float* __restrict__ val, cons
             }
         }
     }
+}
+
+// GAE for SMALL N (the reference's 128 x 4096 rollout): the backward recurrence a_t = delta_t + k_t a_{t+1} is affine, so
+// the T steps of an env are cut into segments of WL_GAE_SEG steps, one thread per (env, segment): every thread loads its
+// whole segment at once (one exposed memory latency instead of T / WL_GAE_CHUNK), reduces it to (c, p) with
+// a_start = c + p * a_in, the S segments of an env are chained through shared memory (S - 1 dependent FMAs), and the
+// outputs are formed from registers.  CTA = 32 envs x S segments (warp = segment: every load / store is coalesced over envs).
+// Rounding differs from the sequential scan by a few ulp (two-level association).
+#define WL_GAE_SEG 16
+__global__ void __launch_bounds__(512)
+wl_gae_seg_kernel(const float* __restrict__ rew, const float* __restrict__ val, const float* __restrict__ last_val,
+                  const uint8_t* __restrict__ done, const uint8_t* __restrict__ tout, float gamma, float lam,
+                  float* __restrict__ ret, float* __restrict__ adv, int T, int N) {
+    __shared__ float s_c[16][33], s_p[16][33], s_in[16][33];
+    const int lane = threadIdx.x & 31, seg = threadIdx.x >> 5, S = blockDim.x >> 5;
+    const int i = blockIdx.x * 32 + lane;
+    const bool live = i < N;
+    const int ii = live ? i : N - 1;
+    const int t0 = seg * WL_GAE_SEG;                       // this thread owns steps [t0, t0 + WL_GAE_SEG) intersected with [0, T)
+    float r[WL_GAE_SEG], v[WL_GAE_SEG], kk[WL_GAE_SEG];
+    uint8_t d[WL_GAE_SEG], to[WL_GAE_SEG];
+#pragma unroll
+    for (int k = 0; k < WL_GAE_SEG; ++k) {
+        const int t = t0 + k;
+        if (t < T) {
+            const size_t o = (size_t)t * N + ii;
+            r[k] = rew[o]; v[k] = val[o]; d[k] = done[o]; to[k] = tout ? tout[o] : (uint8_t)0;
+        } else { r[k] = 0.0f; v[k] = 0.0f; d[k] = 1; to[k] = 0; }
+    }
+    const int t_end = min(t0 + WL_GAE_SEG, T);             // value that follows the segment: V(t_end) or the bootstrap value
+    float next_v = (t_end < T) ? val[(size_t)t_end * N + ii] : last_val[ii];
+    // backward over the segment: c = contribution with a_in = 0, p = product of the k_t
+    float c = 0.0f, p = 1.0f;
+#pragma unroll
+    for (int k = WL_GAE_SEG - 1; k >= 0; --k) {
+        if (t0 + k < T) {
+            const float nt = d[k] ? 0.0f : 1.0f;
+            const float rr = to[k] ? r[k] + gamma * v[k] : r[k];           // time-out bootstrap
+            const float delta = rr + nt * gamma * next_v - v[k];
+            const float kt = nt * gamma * lam;
+            c = delta + kt * c; p = kt * p;
+            r[k] = c; kk[k] = p;                                           // a_t = r[k] + kk[k] * a_in
+            next_v = v[k];
+        }
+    }
+    s_c[seg][lane] = c; s_p[seg][lane] = p;
+    __syncthreads();
+    if (seg == 0) {                                        // chain the env's segments: a_in of segment s = a at the start of segment s + 1
+        float a_in = 0.0f;
+        for (int q = S - 1; q >= 0; --q) { s_in[q][lane] = a_in; a_in = s_c[q][lane] + s_p[q][lane] * a_in; }
+    }
+    __syncthreads();
+    const float a_in = s_in[seg][lane];
+    if (live) {
+#pragma unroll
+        for (int k = 0; k < WL_GAE_SEG; ++k) {
+            const int t = t0 + k;
+            if (t < T) {
+                const float a = r[k] + kk[k] * a_in;
+                const size_t o = (size_t)t * N + i;
+                ret[o] = a + v[k]; adv[o] = a;
+            }
+        }
+    }
+}
+
+// Data-parallel learner step for the small rsl_rl networks: gradient all-reduce FUSED with the Adam update in
+// one kernel over peer memory.  Every rank keeps its flat gradient in a symmetric (P2P-mapped) buffer; each thread reads
+// element i of every rank's gradient (NVLink loads, fixed rank order -> every rank forms the identical mean), and applies
+// Adam to its own replica of the parameters.  10.5 K parameters = 42 KB per rank: one launch instead of NCCL all-reduce +
+// optimizer kernels.  The caller brackets the launch with barriers (gradients complete / safe to overwrite).
+struct GradPeers { int32_t n; int32_t pad; const float* g[WL_MAX_PEERS]; };
+__global__ void wl_dp_adam_kernel(float* __restrict__ param, float* __restrict__ m, float* __restrict__ v, const __grid_constant__ GradPeers gp,
+                                  float lr, float beta1, float beta2, float eps, float weight_decay, float bc1, float bc2, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float g = 0.0f;
+    for (int r = 0; r < gp.n; ++r) g += __ldcg(gp.g[r] + i);           // (L2-coherent loads: peers have just written)
+    g = g / (float)gp.n;
+    float p = param[i];
+    if (weight_decay != 0.0f) g = fmaf(weight_decay, p, g);
+    const float mi = fmaf(beta1, m[i], (1.0f - beta1) * g);
+    const float vi = fmaf(beta2, v[i], (1.0f - beta2) * g * g);
+    m[i] = mi; v[i] = vi;
+    param[i] = p - lr * (mi / bc1) / (sqrtf(vi / bc2) + eps);          // torch.optim.Adam's update (bias corrections bc = 1 - beta^t)
 }
 
 __global__ void wl_detmath_kernel(int op, const float* __restrict__ in, const float* __restrict__ in2, float* __restrict__ out, int n) {
@@ -1952,9 +2038,26 @@ int wl_gae(const float* d_rewards, const float* d_values, const float* d_last_va
            void* stream) {
     if (!d_rewards || !d_values || !d_last_values || !d_dones || !d_returns || !d_advantages) return fail(WL_EINVAL, "wl_gae: null argument");
     if (T < 1 || N < 1) return fail(WL_EINVAL, "wl_gae: T and N must be >= 1");
-    wl_gae_kernel<<<(N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(d_rewards, d_values, d_last_values, d_dones, d_time_outs, gamma,
-                                                                     lam, d_returns, d_advantages, T, N);
+    const int S = (T + WL_GAE_SEG - 1) / WL_GAE_SEG;
+    if (N <= 65536 && S >= 2 && S <= 16)      // small N: latency-bound -> segment-parallel scan; large N: the streaming scan is bandwidth-bound
+        wl_gae_seg_kernel<<<(N + 31) / 32, 32 * S, 0, (cudaStream_t)stream>>>(d_rewards, d_values, d_last_values, d_dones, d_time_outs, gamma,
+                                                                              lam, d_returns, d_advantages, T, N);
+    else
+        wl_gae_kernel<<<(N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(d_rewards, d_values, d_last_values, d_dones, d_time_outs, gamma,
+                                                                         lam, d_returns, d_advantages, T, N);
     return cuda_check(cudaGetLastError(), "wl_gae_kernel");
+}
+
+int wl_dp_adam_step(float* d_param, float* d_m, float* d_v, int32_t n_ranks, const float* const* d_grads, float lr, float beta1,
+                    float beta2, float eps, float weight_decay, int32_t step, int32_t n, void* stream) {
+    if (!d_param || !d_m || !d_v || !d_grads || n_ranks < 1 || n_ranks > WL_MAX_PEERS || n < 1 || step < 1)
+        return fail(WL_EINVAL, "wl_dp_adam_step: bad argument");
+    GradPeers gp; memset(&gp, 0, sizeof gp);
+    gp.n = n_ranks;
+    for (int r = 0; r < n_ranks; ++r) { if (!d_grads[r]) return fail(WL_EINVAL, "wl_dp_adam_step: null gradient pointer"); gp.g[r] = d_grads[r]; }
+    const float bc1 = 1.0f - powf(beta1, (float)step), bc2 = 1.0f - powf(beta2, (float)step);
+    wl_dp_adam_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_param, d_m, d_v, gp, lr, beta1, beta2, eps, weight_decay, bc1, bc2, n);
+    return cuda_check(cudaGetLastError(), "wl_dp_adam_kernel");
 }
 
 int wl_test_detmath(int32_t op, const float* d_in, const float* d_in2, float* d_out, int32_t n, void* stream) {

@@ -120,6 +120,20 @@ class SymmetricRolloutSlab:
         current stream; the host is not blocked)."""
         self.handle.barrier()
 
+    def gather_ce(self) -> "GatheredRollout":
+        """Pull form of the exchange, on the COPY ENGINES: after a device-side barrier (every rank's slab is complete) each rank
+        copies slot p of peer p's buffer into slot p of its own with plain P2P memcpys over NVLink -- no SM is used, so the
+        step kernels of the next iteration run undisturbed -- and a second barrier releases the slabs for refilling.  Issued
+        on the current stream."""
+        nb = self.slab.nbytes
+        self.handle.barrier()
+        for p in range(self.world):
+            if p != self.rank:
+                src = self.handle.get_buffer(p, (nb,), torch.uint8, p * nb)
+                self.buf[p * nb:(p + 1) * nb].copy_(src, non_blocking=True)
+        self.handle.barrier()
+        return self.gathered()
+
     def gathered(self) -> "GatheredRollout":
         return GatheredRollout(self.buf.view(self.world, -1), self.slab)
 
