@@ -12,10 +12,14 @@ generator.  Workloads (BASELINE.json configs):
 (configs[4] = drift at --gpus 8; configs[0] is the reference's CPU plumbing case, a parity-test size.)  Rank 0 prints ONE JSON line.
 
   value     whole-job env-steps/s, inputs resident in HBM.  Timed region = EXACTLY K steps issued back to back between two
-            CUDA events (barrier + synchronize on both sides), max over ranks.  Cold caches WITHOUT a flush kernel: the
-            working set is larger than L2 -- M independent env sets (state + parameters) are stepped round-robin and every
-            step writes a fresh rollout-slab row, so no step finds its inputs in L2 (`config.l2`).  With N > 1 the timed
-            region contains the all-gather of the rollout slab every T_ROLL steps (overlapped with the next steps).
+            CUDA events (barrier + synchronize on both sides), max over ranks; the K steps are one CUDA graph (uploaded at
+            set-up) that starts right behind the graph of the W warm-up steps, so the region holds no host launch latency.
+            Cold caches WITHOUT a flush kernel: the working set is larger than L2 -- M independent env sets (state +
+            parameters) are stepped round-robin and every step writes a fresh rollout-slab row, so no step finds its inputs
+            in L2 (`config.l2`).  With N > 1 the run exchanges the rollout slab after every T_ROLL-th step, inside the timed
+            region: fused into the step kernels as peer-memory stores + one device barrier ("fanout", Drift family), a
+            copy-engine pull ("ce") or NCCL all-gather ("nccl") overlapped with the next rollout's steps; the ranks'
+            clocks are aligned on the device before the warm-up steps.
   flush_protocol  the round-1 protocol kept for comparison: per-step events with a 256 MiB L2-flush fill between steps, and
             the same measurement around an EMPTY kernel (the floor of that protocol: ~6 us on B200).
   e2e       same metric through the public ManagerBasedRLEnv.step_host() with HOST (pinned) buffers: H2D of the actions and
@@ -323,14 +327,25 @@ def run_ours(args):
     sims = [sim0] + [wl.WheeledSim(mk(1000 * m), dev) for m in range(1, M)]
     for s in sims:
         s.startup(); s.reset(None, 0)
-    T_ROLL = min(128, max(4, K // 2))                         # rsl_rl num_steps_per_env is 128 (rsl_rl_ppo_cfg.py:6); shortened so
-    n_slabs = 2                                               # that the driver's short runs still time >= 1 all-gather
+    # rollout length: rsl_rl num_steps_per_env is 128 (rsl_rl_ppo_cfg.py:6), shortened so that the driver's short runs still hold
+    # exchanges inside the K steps.  The run is continuous: step k (warm-up steps included) fills row k % T_ROLL of slab
+    # (k // T_ROLL) % 2 and an exchange follows every T_ROLL-th step, so a window of K steps holds ~K / T_ROLL of them
+    fam = w["task"] in ("drift", "hound_4wd")
+    want = args.gather if args.gather != "auto" else ("mcast" if fam else "ce")   # mcast falls back to per-peer stores, then NCCL
+    if want in ("fanout", "mcast") and not fam:
+        want = "ce"                                           # the height-scan rows are written by wl_scan_kernel (no fan-out)
+    T_ROLL = min(128, max(4, K // 2))
+    n_slabs = 2
     gather_mode, syms = "nccl", []
-    if world > 1 and args.gather in ("auto", "fanout", "ce"):
-        try:                                                  # symmetric (P2P-mapped) slabs: copy-engine pull, or the fused fan-out
+    use_mc = False
+    if world > 1 and want in ("fanout", "mcast", "ce"):
+        try:                                                  # symmetric (P2P-mapped) slabs: the fused fan-out, or a copy-engine pull
             from wheeledlab_b200.distributed import SymmetricRolloutSlab
             syms = [SymmetricRolloutSlab(T_ROLL, E, sim0.obs_dim, 2, dev) for _ in range(n_slabs)]
-            gather_mode = "fanout" if (args.gather == "fanout" and w["task"] in ("drift", "hound_4wd")) else "ce"
+            gather_mode = "fanout" if want == "mcast" else want
+            use_mc = want == "mcast" and all(sy.mc_delta != 0 for sy in syms)
+            if want == "mcast" and not use_mc:
+                print("[bench] no NVSwitch multicast alias for the symmetric buffers; per-peer stores", file=sys.stderr)
         except Exception as ex:
             if args.gather != "auto":
                 raise
@@ -341,16 +356,18 @@ def run_ours(args):
     NA = acts.shape[0]
     tcount = [0] * M
 
-    def make_bound(k):                                        # step k: env set k % M, slab row k % T_ROLL of slab (k // T_ROLL) % 2
+    def make_bound(k):                                        # step k of the run: env set k % M, slab (k // T_ROLL) % 2, row k % T_ROLL
         fn = sims[k % M].bind_step(acts[k % NA], slabs[(k // T_ROLL) % n_slabs].step_outputs(k % T_ROLL))
         if not syms:
             return fn
         if gather_mode != "fanout":
             return fn
-        sim_k, deltas = sims[k % M], syms[(k // T_ROLL) % n_slabs].peer_deltas
+        sim_k, sy_k = sims[k % M], syms[(k // T_ROLL) % n_slabs]
+        deltas, mcd = sy_k.peer_deltas, (sy_k.mc_delta if use_mc else 0)
 
-        def fan(tc, _fn=fn, _sim=sim_k, _d=deltas):           # this step's rows also go to the same slab slot of every peer
+        def fan(tc, _fn=fn, _sim=sim_k, _d=deltas, _m=mcd):   # this step's rows also go to the same slab slot of every peer
             _sim.set_peer_fanout(_d)
+            _sim.set_multicast_fanout(_m)
             _fn(tc)
         return fan
 
@@ -369,51 +386,68 @@ def run_ours(args):
         for j, fn in enumerate(fns):
             k = k0 + j
             row, cur = k % T_ROLL, (k // T_ROLL) % n_slabs
-            if world > 1 and gather_mode != "fanout" and row == 0 and gdone[cur] is not None:
-                cur_stream.wait_event(gdone[cur])
+            if world > 1 and row == 0 and gdone[cur] is not None:
+                cur_stream.wait_event(gdone[cur])             # this slab's previous exchange must be over before it is refilled
             m = k % M
             fn(tcount[m]); tcount[m] += 1
             if world > 1 and row == T_ROLL - 1:
-                if gather_mode == "fanout":
-                    syms[cur].barrier(); gev.append(None)
-                else:
-                    filled = torch.cuda.Event(); filled.record()
-                    with torch.cuda.stream(gstream):
-                        gstream.wait_event(filled)
-                        g0, g1 = torch.cuda.Event(enable_timing=timed), torch.cuda.Event(enable_timing=timed)
-                        g0.record()
-                        if gather_mode == "ce":
-                            syms[cur].gather_ce()
-                        else:
-                            slabs[cur].all_gather()
-                        g1.record(); gev.append((g0, g1))
-                        gdone[cur] = g1
+                filled = torch.cuda.Event(); filled.record()
+                with torch.cuda.stream(gstream):              # the exchange runs beside the next rollout's steps
+                    gstream.wait_event(filled)
+                    g0, g1 = torch.cuda.Event(enable_timing=timed), torch.cuda.Event(enable_timing=timed)
+                    g0.record()
+                    if gather_mode == "fanout":
+                        syms[cur].barrier()                   # the rows are already in every peer's buffer: completion barrier only
+                    elif gather_mode == "ce":
+                        syms[cur].gather_ce()
+                    else:
+                        slabs[cur].all_gather()
+                    g1.record(); gev.append((g0, g1))
+                    gdone[cur] = g1
         for g in gdone:                                       # the last gathers must be finished before the clock stops
             if g is not None:
                 cur_stream.wait_event(g)
         return gev
 
-    if world > 1 and gather_mode == "nccl":                   # untimed: NCCL communicator / channel set-up, receive buffers
-        for sl in slabs:
-            sl.all_gather()
-    run_steps(bound_w, 0, False)
-    # the K timed steps are captured into ONE CUDA graph (how a rollout is meant to be driven: the Python + driver launch path
-    # costs ~8 us per step here, more than the kernel) and replayed once inside the timed region; eager launches if capture fails
-    graph, timing_mode = None, "eager stream launches"
+    if world > 1:                                             # untimed set-up: one exchange per slab (NCCL channels / receive
+        for i_s in range(n_slabs):                            # buffers, the barrier kernel's module load, peer mappings touched)
+            if gather_mode == "fanout":
+                syms[i_s].barrier()
+            elif gather_mode == "ce":
+                syms[i_s].gather_ce()
+            else:
+                slabs[i_s].all_gather()
+    # Both the W warm-up steps and the K timed steps are captured into CUDA graphs (how a rollout is meant to be driven: the
+    # Python + driver launch path costs ~8 us per step here, more than the kernel), instantiated and uploaded at set-up.  On the
+    # device the sequence is  [spin][rank alignment][W warm-up steps] e0 [K steps] e1 : the warm-up runs IMMEDIATELY before the
+    # clock starts (caches, clocks and -- N > 1 -- the NVLink lanes are in their steady state: idle lanes take ~0.1 ms to wake),
+    # and the spin keeps the GPU busy while the host enqueues everything, so e0..e1 holds no host launch latency.
+    sim_x = wl.WheeledSim(mk(777), dev); sim_x.startup(); sim_x.reset(None, 0)        # loads the step kernels' module before capture
+    sim_x.bind_step(acts[0], RolloutSlab(1, E, sim0.obs_dim, 2, dev).step_outputs(0))(0)
+    torch.cuda.synchronize()
+    del sim_x
+    graph, graph_w, timing_mode, gev = None, None, "eager stream launches", []
+
+    def capture(fns, k0):
+        g = torch.cuda.CUDAGraph()
+        cs_ = torch.cuda.Stream(device=dev)
+        cs_.wait_stream(main)
+        with torch.cuda.stream(cs_):
+            with torch.cuda.graph(g, stream=cs_):
+                ev = run_steps(fns, k0, False)
+        main.wait_stream(cs_)
+        wl.upload_graph(g, main)                              # set-up, not steps: the first replay would otherwise pay the upload
+        return g, ev
+
     if not args.eager:
         keep = list(tcount)
         try:
-            graph = torch.cuda.CUDAGraph()
-            cs_ = torch.cuda.Stream(device=dev)
-            cs_.wait_stream(main)
-            with torch.cuda.stream(cs_):
-                with torch.cuda.graph(graph, stream=cs_):
-                    gev = run_steps(bound, W, False)
-            main.wait_stream(cs_)
-            timing_mode = "one CUDA graph of the K steps, replayed once"
+            graph_w, _ = capture(bound_w, 0)
+            graph, gev = capture(bound, W)
+            timing_mode = "one CUDA graph of the K steps (instantiated + uploaded at set-up), replayed once right after the graph of the W warm-up steps"
         except Exception as ex:
             print(f"[bench] graph capture failed ({ex!r}); timing eager launches", file=sys.stderr)
-            graph = None
+            graph = graph_w = None
             tcount[:] = keep
     sampler = ClockSampler(list(range(world)) if world > 1 else local)
     barrier()
@@ -421,14 +455,21 @@ def run_ours(args):
         sampler.start()
     l0 = sum(s.launch_count for s in sims)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_tok = torch.zeros(1, device=dev)
+    if world > 1:
+        dist.all_reduce(sync_tok)                             # (untimed: first use of this buffer)
     barrier()
-    # a short spin kernel BEFORE the first event keeps the GPU busy while the host enqueues the graph launch, so that the
-    # timed region (e0 .. e1) holds the K steps and not the host's launch latency (the spin itself is outside the region)
-    torch.cuda._sleep(400_000)
-    e0.record()
+    torch.cuda._sleep(400_000 if world == 1 else 800_000)
+    if world > 1:                                             # device-side alignment of the ranks: the hosts leave dist.barrier()
+        dist.all_reduce(sync_tok)                             # up to ~0.1 ms apart, which the first exchange would otherwise absorb
     if graph is not None:
+        graph_w.replay()
+        e0.record()
         graph.replay()
     else:
+        run_steps(bound_w, 0, False)
+        l0 = sum(s.launch_count for s in sims)
+        e0.record()
         gev = run_steps(bound, W, True)
     e1.record()
     barrier()
@@ -578,11 +619,12 @@ def run_ours(args):
             fused = {"error": repr(ex)[:200]}
     clocks = sampler.stop() if rank == 0 else None
 
+    tot_ms_own = tot_ms
     tot_ms, graph_ms, e2e_ms = max_over_ranks(tot_ms), max_over_ranks(graph_ms), max_over_ranks(e2e_ms)
     gather_ms = max_over_ranks(gather_ms)
     per_rank = None
     if world > 1:                                             # diagnostics: which rank sets the max
-        st = torch.tensor([tot_ms / K, statistics.median(flush_us) * 1e-3], dtype=torch.float64, device=dev)
+        st = torch.tensor([tot_ms_own / K, statistics.median(flush_us) * 1e-3], dtype=torch.float64, device=dev)
         allst = [torch.zeros_like(st) for _ in range(world)]
         dist.all_gather(allst, st)
         per_rank = {"step_us_mean": [round(float(x[0]) * 1e3, 3) for x in allst],
@@ -623,13 +665,16 @@ def run_ours(args):
                                "empty_kernel_us": null_us,
                                "note": "round-1 protocol: per-step events, 256 MiB L2-flush fill between steps; empty_kernel_us is the same "
                                        "measurement around an EMPTY kernel of the same geometry (the protocol's own floor)"},
-            "collective": {"kind": {"fanout": "fused peer-memory fan-out: every step stores its slab rows into each peer's symmetric buffer over NVLink; "
+            "collective": {"kind": {"fanout": ("fused NVSwitch-multicast fan-out: every step stores its slab rows ONCE to the multicast alias of the "
+                                               "symmetric buffers (multimem.st; the switch replicates them into every rank's copy); one device-side "
+                                               "barrier per iteration") if use_mc else
+                                              "fused peer-memory fan-out: every step stores its slab rows into each peer's symmetric buffer over NVLink; "
                                               "one device-side barrier per iteration",
                                     "ce": "copy-engine pull: barrier, world-1 P2P memcpys of the peers' slabs over NVLink (no SM), barrier",
                                     "nccl": "all_gather_into_tensor(rollout slab)"}[gather_mode],
-                           "mode": gather_mode, "per_iteration_steps": T_ROLL, "bytes_per_rank": slab_bytes, "count": n_exchanges,
+                           "mode": ("mcast" if use_mc else gather_mode), "per_iteration_steps": T_ROLL, "bytes_per_rank": slab_bytes, "count": n_exchanges,
                            "ms_each_measured_alone": [round(x, 3) for x in gather_each],
-                           "nvlink_bytes_per_step_per_rank": (E * (4 * sim0.obs_dim + 6) * (world - 1)) if gather_mode == "fanout" else None,
+                           "nvlink_bytes_per_step_per_rank": (E * (4 * sim0.obs_dim + 6) * (1 if use_mc else world - 1)) if gather_mode == "fanout" else None,
                            "bus_GBps": (slab_bytes * (world - 1) / (statistics.mean(gather_each) * 1e-3) / 1e9) if (gather_each and gather_mode != "fanout") else None,
                            "inside_timed_region": True,
                            "note": "every exchange of the K steps (count) completes before the clock stops; nccl mode: double-buffered slabs, the "
@@ -661,9 +706,10 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     ap.add_argument("--no-extras", action="store_true", help="skip the supplementary figures (policy-in-loop, fused rollout)")
     ap.add_argument("--eager", action="store_true", help="time eager stream launches instead of one CUDA graph of the K steps")
-    ap.add_argument("--gather", default="auto", choices=["auto", "nccl", "ce", "fanout"],
-                    help="N > 1 slab exchange: NCCL all-gather, copy-engine pull over symmetric memory (auto, when available), or the "
-                         "fan-out fused into the step kernel")
+    ap.add_argument("--gather", default="auto", choices=["auto", "nccl", "ce", "fanout", "mcast"],
+                    help="N > 1 slab exchange: fused into the step kernel as NVSwitch-multicast stores (mcast; auto for the Drift family, "
+                         "falling back to per-peer stores = fanout, then to NCCL), copy-engine pull over symmetric memory (ce; auto "
+                         "for Elevation), or NCCL all-gather")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

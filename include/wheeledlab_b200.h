@@ -370,6 +370,12 @@ int wl_set_term_bits(wl_sim* sim, uint8_t* d_term_bits);
  * (P2P-mapped, NVLink) gathered buffer minus the base of the local one -- so the learner-facing concat of the rollout is
  * complete when the step kernels are: no separate collective.  n_peers = 0 switches it off.  Drift-family tasks. */
 int wl_set_peer_fanout(wl_sim* sim, int32_t n_peers, const int64_t* byte_deltas);
+/* NVSwitch multicast form of the fan-out: `mc_byte_delta` = (multicast alias of the symmetric buffer) - (this rank's mapping of
+ * it); the 8-envs-per-CTA step kernel (variant 8) then sends every full, aligned output row with ONE multimem.st that the
+ * switch replicates into all ranks' buffers (NVLink egress 1x instead of (world-1)x); rows it cannot send that way (partial
+ * CTA, unaligned pointers, other kernel variants) still go peer by peer through wl_set_peer_fanout's deltas, so set both.
+ * 0 switches it off.  torch: _SymmetricMemory.multicast_ptr. */
+int wl_set_multicast_fanout(wl_sim* sim, int64_t mc_byte_delta);
 /* ManagerBasedEnv.seed(): re-key the counter-based generator for all later launches (startup draws are not repeated) */
 int wl_set_seed(wl_sim* sim, uint64_t seed);
 /* fill the d_* derived fields from the primary ones (idempotent). */
@@ -455,7 +461,8 @@ int wl_derive_suspension(wl_sim* sim, float* d_susp_pos, float* d_susp_vel, void
  * 8 = the quad plus an auxiliary warp per 8 envs that takes everything off the dependent chain (Drift family only).
  * Results are bit-identical across variants. */
 int wl_set_kernel_variant(wl_sim* sim, int32_t lanes_per_env);
-/* height-scan tile staging: 1 = TMA (cp.async.bulk.tensor.2d, default), 0 = plain loads (A/B comparison) */
+/* height-scan tile staging: 1 = one TMA tile per CTA (default), 2 = TMA producer/consumer pipeline over persistent CTAs,
+ * 0 = plain loads (A/B comparison); identical outputs */
 int wl_set_scan_tma(wl_sim* sim, int32_t use_tma);
 /* observation width for the configured task */
 int32_t wl_obs_dim(const wl_sim* sim);
@@ -518,6 +525,11 @@ int wl_gae(const float* d_rewards, const float* d_values, const float* d_last_va
  * barriers (all gradients written before; none overwritten until every rank has read them).  n_ranks = 1 is plain Adam. */
 int wl_dp_adam_step(float* d_param, float* d_m, float* d_v, int32_t n_ranks, const float* const* d_grads, float lr, float beta1,
                     float beta2, float eps, float weight_decay, int32_t step, int32_t n, void* stream);
+
+/* A caller that drives wl_step through a CUDA graph of K steps (how a rollout is meant to be issued: one launch per K steps)
+ * pays the upload of the instantiated graph to the device on its FIRST launch (~10 us for 20 kernel nodes); this moves that
+ * upload to set-up time.  graph_exec = cudaGraphExec_t (torch: CUDAGraph.raw_cuda_graph_exec()). */
+int wl_graph_upload(void* graph_exec, void* stream);
 
 /* ---- test hooks (bit-exactness of the deterministic math vs the oracle) ------ */
 /* op: 0 sin,1 cos,2 atan,3 atan2(x=in,y=in2),4 log,5 tan,6 asin,7 exp,8 tanh ; out[n] */

@@ -313,7 +313,24 @@ def _elev_pair(n, seed=42):
     return spec, sim, orc
 
 
-@pytest.mark.parametrize("variant,tma", [(1, True), (4, True), (4, False)])
+def test_scan_pipeline_walks_several_envs_per_cta():
+    """The pipelined ray-caster runs 888 persistent CTAs: with more envs than that every CTA re-uses its two stages
+    (mbarrier phases flip), and the rows must still equal the oracle's and the plain-load kernel's bit for bit."""
+    _need_gpu()
+    n = 4000
+    spec, sim, orc = _elev_pair(n)
+    for t in range(3):
+        act = sim.synth_actions(t)
+        sim.set_scan_tma(2); sim.step(act, t)
+        o_obs = orc.step(act.cpu().numpy(), t)[0]
+    a2 = sim.observe(3).cpu().numpy()
+    sim.set_scan_tma(0); a0 = sim.observe(3).cpu().numpy()
+    sim.set_scan_tma(1); a1 = sim.observe(3).cpu().numpy()
+    ref = orc.observe(3)
+    assert np.array_equal(_bits(a2), _bits(ref)) and np.array_equal(_bits(a0), _bits(ref)) and np.array_equal(_bits(a1), _bits(ref))
+
+
+@pytest.mark.parametrize("variant,tma", [(1, 2), (4, 2), (4, 1), (4, 0)])
 def test_elevation_trajectory_bit_exact(variant, tma):
     _need_gpu()
     n, steps = 96, 260
@@ -915,11 +932,12 @@ def test_vehicle_at_rest_stays_at_rest_on_the_gpu():
     assert float(sim.wheel_vel.abs().max()) < 1e-2
 
 
-@pytest.mark.parametrize("mode", ["nccl", "fanout", "ce"])
+@pytest.mark.parametrize("mode", ["nccl", "fanout", "mcast", "ce"])
 def test_two_process_nccl_gather_equals_single_rank(tmp_path, mode):
     """BASELINE configs[4] at test size: 2 ranks x 2048 envs, the exchanged rollout slab == the slab of one 4096-env process,
     bit for bit (skipped when the box has a single GPU).  mode "nccl": one all_gather_into_tensor of the slab; "fanout": the
-    step kernel stores its output rows into the peer's symmetric buffer over NVLink (no collective); "ce": copy-engine pull of the peer's slab
+    step kernel stores its output rows into the peer's symmetric buffer over NVLink (no collective); "mcast": the same with one
+    multimem.st per row, replicated by the NVSwitch (skipped where the fabric has no multicast); "ce": copy-engine pull of the peer's slab
     out of symmetric memory (no SM)."""
     _need_gpu()
     if torch.cuda.device_count() < 2:
@@ -928,9 +946,11 @@ def test_two_process_nccl_gather_equals_single_rank(tmp_path, mode):
     root = Path(__file__).resolve().parent.parent
     out = tmp_path / "slab.pt"
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-           "--master-port", {"nccl": "29731", "fanout": "29733", "ce": "29735"}[mode], str(root / "tools" / "nccl_slab_check.py"), "--out", str(out), "--envs", "2048",
+           "--master-port", {"nccl": "29731", "fanout": "29733", "ce": "29735", "mcast": "29737"}[mode], str(root / "tools" / "nccl_slab_check.py"), "--out", str(out), "--envs", "2048",
            "--steps", "16", "--mode", mode]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    if mode == "mcast" and "NO_MULTICAST" in r.stdout:
+        pytest.skip("no NVSwitch multicast on this box")
     assert r.returncode == 0, r.stderr[-2000:]
     import wheeledlab_b200 as wl
     from wheeledlab_b200.distributed import RolloutSlab

@@ -20,7 +20,7 @@ def main():
     ap.add_argument("--envs", type=int, default=2048)
     ap.add_argument("--steps", type=int, default=16)
     ap.add_argument("--seed", type=int, default=42)
-    ap.add_argument("--mode", default="nccl", choices=["nccl", "fanout", "ce"])
+    ap.add_argument("--mode", default="nccl", choices=["nccl", "fanout", "mcast", "ce"])
     a = ap.parse_args()
     import wheeledlab_b200 as wl
     from wheeledlab_b200.distributed import RolloutSlab
@@ -32,12 +32,15 @@ def main():
     sim = wl.WheeledSim(wl.drift_task(num_envs=a.envs, seed=a.seed, env_id_offset=rank * a.envs), dev)
     sim.startup(); sim.reset(None, 0)
     fields = ("obs", "actions", "rewards", "terminated", "truncated")
-    if a.mode in ("fanout", "ce"):
+    if a.mode in ("fanout", "mcast", "ce"):
         from wheeledlab_b200.distributed import SymmetricRolloutSlab
         sym = SymmetricRolloutSlab(a.steps, a.envs, sim.obs_dim, 2, dev)
         slab = sym.slab
-        if a.mode == "fanout":                   # fused: the step kernel stores its rows into every peer's symmetric buffer
-            sym.attach(sim)
+        if a.mode in ("fanout", "mcast"):        # fused: the step kernel stores its rows into every peer's symmetric buffer
+            if a.mode == "mcast" and sym.mc_delta == 0:              # (mcast: one multimem.st replicated by the NVSwitch)
+                print("NO_MULTICAST", flush=True)
+                dist.barrier(); dist.destroy_process_group(); sys.exit(77)
+            sym.attach(sim, multicast=(a.mode == "mcast"))
             fields = ("obs", "rewards", "terminated", "truncated")   # (actions are written by the caller, not by env.step)
     else:
         slab = RolloutSlab(a.steps, a.envs, sim.obs_dim, 2, dev)
@@ -45,7 +48,7 @@ def main():
         act = sim.synth_actions(t)
         slab.actions[t].copy_(act)
         sim.step(act, t, out=slab.step_outputs(t))
-    if a.mode == "fanout":
+    if a.mode in ("fanout", "mcast"):
         sym.barrier(); torch.cuda.synchronize(); dist.barrier()
         g = sym.gathered()
     elif a.mode == "ce":                         # copy-engine pull of the peers' slabs

@@ -83,6 +83,7 @@ lib.wl_set_step_counter.argtypes = [_vp, _i64, _vp]
 lib.wl_set_seed.argtypes = [_vp, _u64]
 lib.wl_set_term_bits.argtypes = [_vp, _vp]
 lib.wl_set_peer_fanout.argtypes = [_vp, _i32, C.POINTER(_i64)]
+lib.wl_set_multicast_fanout.argtypes = [_vp, C.c_int64]
 lib.wl_advance_counter.argtypes = [_vp, _i32, _vp]
 lib.wl_note_device_counter.argtypes = [_vp, _i64]
 lib.wl_log_flush.argtypes = [_vp, _vp]
@@ -130,11 +131,12 @@ lib.wl_test_detmath.argtypes = [_i32, _vp, _vp, _vp, _i32, _vp]
 lib.wl_test_philox.argtypes = [_u64, _u32, _u32, _u32, _u32, _vp, _i32, _vp]
 lib.wl_test_null.argtypes = [_i32, _i32, _vp]
 lib.wl_test_null_cfg.argtypes = [_vp, _i32, _i32, _vp]
+lib.wl_graph_upload.argtypes = [_vp, _vp]
 
 EXPORTED_SYMBOLS = [
-    "wl_config_describe", "wl_config_sizeof", "wl_config_finalize", "wl_set_step_counter", "wl_advance_counter", "wl_note_device_counter", "wl_log_flush", "wl_reward_weights", "wl_set_seed", "wl_set_term_bits", "wl_set_peer_fanout", "wl_state_bytes", "wl_globals_offset", "wl_create", "wl_destroy",
+    "wl_config_describe", "wl_config_sizeof", "wl_config_finalize", "wl_set_step_counter", "wl_advance_counter", "wl_note_device_counter", "wl_log_flush", "wl_reward_weights", "wl_set_seed", "wl_set_term_bits", "wl_set_peer_fanout", "wl_set_multicast_fanout", "wl_state_bytes", "wl_globals_offset", "wl_create", "wl_destroy",
     "wl_last_error", "wl_build_info", "wl_startup", "wl_reset", "wl_step", "wl_step_host", "wl_step_host_zero_copy", "wl_rollout", "wl_result_bytes", "wl_observe", "wl_curriculum",
-    "wl_synth_actions", "wl_derive_suspension", "wl_set_kernel_variant", "wl_set_scan_tma", "wl_obs_dim", "wl_launch_count", "wl_policy_blob_floats", "wl_act_step", "wl_step_stage_a", "wl_step_stage_b", "wl_camera", "wl_gae", "wl_dp_adam_step", "wl_test_detmath", "wl_test_philox", "wl_test_null", "wl_test_null_cfg",
+    "wl_synth_actions", "wl_derive_suspension", "wl_set_kernel_variant", "wl_set_scan_tma", "wl_obs_dim", "wl_launch_count", "wl_policy_blob_floats", "wl_act_step", "wl_step_stage_a", "wl_step_stage_b", "wl_camera", "wl_gae", "wl_dp_adam_step", "wl_graph_upload", "wl_test_detmath", "wl_test_philox", "wl_test_null", "wl_test_null_cfg",
 ]
 
 

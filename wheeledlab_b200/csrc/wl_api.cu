@@ -36,7 +36,7 @@ struct wl_sim {
     int variant;            // 0 auto, 1 thread-per-env, 4 quad-per-env
     CUtensorMap tmap;       // 2-D tensor map over the height-field (elevation task)
     bool has_tmap;
-    bool scan_tma;          // ray-cast tile staged by TMA (true) or by plain loads (false; A/B + fallback for tests)
+    int scan_mode;          // ray-cast tile staging: 1 one TMA tile per CTA (default), 2 TMA producer/consumer pipeline, 0 plain loads (A/B)
 };
 
 // below this many envs one thread/env cannot fill 148 SMs x 4 schedulers; use 4 lanes per env
@@ -450,6 +450,8 @@ struct DuoShared {
     float push[WL_DUO_ENVS][8];     // hf fired, dvx, dvy, dwz_hf, t_hf_new, lf fired, dwz_lf, t_lf_new
     float fin[WL_DUO_ENVS][16];     // post-physics: p(3) vb(3) wb(3) wz_world steer_l steer_r raw-tmask(bits)
     __align__(16) float obs[WL_DUO_ENVS * WL_OBS_DIM_BLIND];   // the 8 observation rows of the CTA, staged for 128-bit stores
+    __align__(16) float rewrow[WL_DUO_ENVS];                    // the CTA's 8 rewards and 2 x 8 done bytes, staged the same way
+    __align__(8) uint8_t maskrow[2][WL_DUO_ENVS];
 };
 __device__ __forceinline__ void bar_arrive(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ void bar_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
@@ -550,12 +552,23 @@ wl_step_duo_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st,
                 }
             }
             done = tmask != 0u;
-            if (live) {
+            // full CTA with aligned rows: 32 + 8 + 8 contiguous bytes leave as four wide stores (HBM, and -- fan-out -- one
+            // NVLink / multicast write each instead of 24 small ones); otherwise element by element
+            const bool packed = (env0 + WL_DUO_ENVS <= n) && ((reinterpret_cast<uintptr_t>(rew + env0) & 15u) == 0) &&
+                                (((reinterpret_cast<uintptr_t>(terminated_o + env0) | reinterpret_cast<uintptr_t>(truncated_o + env0)) & 7u) == 0);
+            const uint8_t tb = (uint8_t)((tmask & ~1u) ? 1 : 0), ub = (uint8_t)((tmask & 1u) ? 1 : 0);
+            if (packed) {
+                sh.rewrow[lane] = total; sh.maskrow[0][lane] = tb; sh.maskrow[1][lane] = ub;
+                __syncwarp(0xffu);
+                if (lane < 2) fan_store16(pf, reinterpret_cast<float4*>(rew + env0) + lane, reinterpret_cast<const float4*>(sh.rewrow)[lane]);
+                else if (lane == 2) fan_store8(pf, reinterpret_cast<float2*>(terminated_o + env0), *reinterpret_cast<const float2*>(sh.maskrow[0]));
+                else if (lane == 3) fan_store8(pf, reinterpret_cast<float2*>(truncated_o + env0), *reinterpret_cast<const float2*>(sh.maskrow[1]));
+            } else if (live) {
                 fan_store(pf, &rew[i], total);
-                fan_store(pf, &terminated_o[i], (uint8_t)((tmask & ~1u) ? 1 : 0));
-                fan_store(pf, &truncated_o[i], (uint8_t)((tmask & 1u) ? 1 : 0));
-                if (term_bits != nullptr) term_bits[i] = (uint8_t)tmask;
+                fan_store(pf, &terminated_o[i], tb);
+                fan_store(pf, &truncated_o[i], ub);
             }
+            if (live && term_bits != nullptr) term_bits[i] = (uint8_t)tmask;
         }
         log_accumulate(gl->acc[t % 3u], done && live, tmask, sums);
         if (live) {
@@ -656,7 +669,7 @@ wl_step_duo_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st,
         if (w < 3) { so[2] = v.z; so[3] = v.w; }
         __syncwarp();
         if (lane < (WL_DUO_ENVS * WL_OBS_DIM_BLIND) / 4)
-            fan_store(pf, reinterpret_cast<float4*>(orow0) + lane, reinterpret_cast<const float4*>(sh.obs)[lane]);
+            fan_store16(pf, reinterpret_cast<float4*>(orow0) + lane, reinterpret_cast<const float4*>(sh.obs)[lane]);
     } else {
         blind_obs_quad(c, e, w, eu_k, vb, wbo, zn, obs + (size_t)WL_OBS_DIM_BLIND * ii, live, pf);
     }
@@ -945,8 +958,60 @@ wl_rollout_quad_kernel(const __grid_constant__ wl_config c, float4* __restrict__
 #define WL_SCAN_THREADS 128
 
 
+// The 676 rays of one env out of its shared-memory window: thread t takes rays t, t+128, ... (linear order: all 32 lanes busy,
+// fully coalesced stores).  The SIX rays of a thread are independent chains, written branch-free (window indices clamped into
+// the tile, the miss value selected at the end) and fully unrolled so that the compiler interleaves them: the loop is bound by
+// instruction latency (F2I, LDS, dependent FFMAs), not by bytes.  Per-ray arithmetic unchanged (bit-identical outputs).
+struct ScanPose { float bx, by, bz, cy, sy, pz; int ox, oy; };
+__device__ __forceinline__ void scan_rays(const wl_config& c, const float* __restrict__ tl, const ScanPose& q, float* __restrict__ row, int tid) {
+    constexpr int ITER = (WL_SCAN_RAYS + WL_SCAN_THREADS - 1) / WL_SCAN_THREADS;
+    const float inv = c.d_inv_hf_cell;
+    const float fxmax = (float)(c.hf_nx - 1), fymax = (float)(c.hf_ny - 1);
+    const float base = q.pz - c.scan_plane_init;
+    float v[ITER], tx[ITER], ty[ITER];
+    const float* t0[ITER];
+    bool inside[ITER];
+#pragma unroll
+    for (int j = 0; j < ITER; ++j) {                                              // phase 1: ray -> window address, weights
+        int r = tid + WL_SCAN_THREADS * j;
+        if (r > WL_SCAN_RAYS - 1) r = WL_SCAN_RAYS - 1;                           // the tail threads recompute the last ray (not stored)
+        const int ry = (r * 2521) >> 16, rx = r - ry * WL_SCAN_SIDE;             // r / 26, r % 26 for r < 676
+        const float lx = fm((float)rx, c.scan_res, -c.scan_half), ly = fm((float)ry, c.scan_res, -c.scan_half);
+        const float wx = fm(q.cy, lx, fm(-q.sy, ly, q.bx)), wy = fm(q.sy, lx, fm(q.cy, ly, q.by));
+        const float fx = (wx - c.hf_x0) * inv, fy = (wy - c.hf_y0) * inv;
+        inside[j] = (fx >= 0.0f) && (fy >= 0.0f) && (fx <= fxmax) && (fy <= fymax);
+        int ix = (int)floorf(fx), iy = (int)floorf(fy);
+        ix = min(ix, c.hf_nx - 2); iy = min(iy, c.hf_ny - 2);
+        tx[j] = fx - (float)ix; ty[j] = fy - (float)iy;
+        // (the six F2I/I2F per ray run on the 16-lane pipe, 48 of its cycles per warp-iteration against 64 issue slots: the loop
+        //  is issue-bound, and the 2^23-binade tricks that avoid the conversions cost 16 more issue slots per ray -- not taken)
+        const int ux = min(max(ix - q.ox, 0), WL_TILE_W - 2), uy = min(max(iy - q.oy, 0), WL_TILE_H - 2);   // no-op for a hit
+        t0[j] = tl + uy * WL_TILE_W + ux;
+    }
+    float z00[ITER], z10[ITER], z01[ITER], z11[ITER];
+    asm volatile("" ::: "memory"); __syncwarp();                                  // (compiler fences: keep the phases apart)
+#pragma unroll
+    for (int j = 0; j < ITER; ++j) {                                              // phase 2: the 24 shared-memory reads in flight together
+        z00[j] = t0[j][0]; z10[j] = t0[j][1]; z01[j] = t0[j][WL_TILE_W]; z11[j] = t0[j][WL_TILE_W + 1];
+    }
+    asm volatile("" ::: "memory"); __syncwarp();
+#pragma unroll
+    for (int j = 0; j < ITER; ++j) {                                              // phase 3: bilinear sample, height, clip
+        const float za = fm(z10[j] - z00[j], tx[j], z00[j]), zb = fm(z11[j] - z01[j], tx[j], z01[j]);
+        const float hit = fm(zb - za, ty[j], za);
+        const float hs = q.bz - hit - c.scan_offset;                              // mdp.height_scan
+        const float hv = r_clamp(-hs + base, -c.obs_clip, c.obs_clip);           // world_height_map, clip
+        v[j] = inside[j] ? hv : c.obs_clip;                                       // miss: +inf clipped
+    }
+#pragma unroll
+    for (int j = 0; j < ITER; ++j) {
+        const int r = tid + WL_SCAN_THREADS * j;
+        if (r < WL_SCAN_RAYS) row[r] = v[j];
+    }
+}
+
 template <bool USE_TMA>
-__global__ void __launch_bounds__(WL_SCAN_THREADS)
+__global__ void __launch_bounds__(WL_SCAN_THREADS, 8)
 wl_scan_kernel(const __grid_constant__ wl_config c, const __grid_constant__ CUtensorMap tmap, const float4* __restrict__ st,
                const float* __restrict__ hf, float* __restrict__ obs) {
     __shared__ __align__(128) float tile[WL_TILE_W * WL_TILE_H];
@@ -994,31 +1059,86 @@ wl_scan_kernel(const __grid_constant__ wl_config c, const __grid_constant__ CUte
         __syncthreads();
     }
     float* row = obs + (size_t)WL_OBS_DIM_ELEV * i + 13;
-    // lane = ray column (26 of 32 lanes active), warp w takes ray rows w, w+4, ...: no integer div/mod per ray and every
-    // warp store is one contiguous 104-byte run of the observation row
-    const int rx = threadIdx.x & 31, wrp = threadIdx.x >> 5;
-    if (rx < WL_SCAN_SIDE) {
-        const float lx = fm((float)rx, c.scan_res, -c.scan_half);
-        const float fxmax = (float)(c.hf_nx - 1), fymax = (float)(c.hf_ny - 1);
-        for (int ry = wrp; ry < WL_SCAN_SIDE; ry += WL_SCAN_THREADS / 32) {
-            const float ly = fm((float)ry, c.scan_res, -c.scan_half);
-            const float wx = fm(cy, lx, fm(-sy, ly, bx)), wy = fm(sy, lx, fm(cy, ly, by));
-            const float fx = (wx - c.hf_x0) * inv, fy = (wy - c.hf_y0) * inv;
-            float v = c.obs_clip;                                                // miss: +inf clipped
-            if ((fx >= 0.0f) && (fy >= 0.0f) && (fx <= fxmax) && (fy <= fymax)) {
-                int ix = (int)floorf(fx), iy = (int)floorf(fy);
-                if (ix > c.hf_nx - 2) ix = c.hf_nx - 2;
-                if (iy > c.hf_ny - 2) iy = c.hf_ny - 2;
-                const float tx = fx - (float)ix, ty = fy - (float)iy;
-                const float* t0 = tile + (iy - oy) * WL_TILE_W + (ix - ox);
-                const float z00 = t0[0], z10 = t0[1], z01 = t0[WL_TILE_W], z11 = t0[WL_TILE_W + 1];
-                const float za = fm(z10 - z00, tx, z00), zb = fm(z11 - z01, tx, z01);
-                const float hit = fm(zb - za, ty, za);
-                const float hs = bz - hit - c.scan_offset;                           // mdp.height_scan
-                v = r_clamp(-hs + (pz - c.scan_plane_init), -c.obs_clip, c.obs_clip);     // world_height_map, clip
-            }
-            row[ry * WL_SCAN_SIDE + rx] = v;
+    ScanPose q{bx, by, bz, cy, sy, pz, ox, oy};
+    scan_rays(c, tile, q, row, threadIdx.x);
+}
+
+// ---------------------------------------------------------------------------------------
+// The same ray-caster as a TMA producer / consumer PIPELINE (wl_set_scan_tma(2); measured 13.2 us vs 12.4 us for one tile per
+// CTA at 4096 envs, 150 vs 135 us at 65536 -- 16 resident one-tile CTAs per SM already hide the set-up + TMA latency, and the
+// ray loop is issue-bound -- so it is NOT the default; profiles/r02_scan_ab.jsonl): persistent CTAs (a few per SM) walk the envs; warp 4 is
+// the producer -- it reads the next env's pose, forms the per-env constants and issues the cp.async.bulk.tensor.2d of that
+// env's window into the other shared-memory stage -- while warps 0..3 take the 676 rays of the current env out of the stage
+// that has landed.  full[s] (TMA transaction bytes) and empty[s] (one arrival per consumer warp) are mbarriers; the pose load,
+// the constant set-up and the TMA latency of env k+1 hide behind the rays of env k instead of heading every CTA's life.
+// Rays are taken in linear order (r = thread + 128 j: all 32 lanes busy, fully coalesced stores).  Same arithmetic.
+// ---------------------------------------------------------------------------------------
+#define WL_SCAN_STAGES 2
+__device__ __forceinline__ void mbar_arrive(uint64_t* b) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory"); }
+__device__ __forceinline__ void mbar_wait_parity(uint64_t* b, uint32_t parity) {
+    const uint32_t mb = smem_u32(b);
+    uint32_t ok = 0;
+    while (!ok)
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(mb), "r"(parity) : "memory");
+}
+__global__ void __launch_bounds__(WL_SCAN_THREADS + 32)
+wl_scan_pipe_kernel(const __grid_constant__ wl_config c, const __grid_constant__ CUtensorMap tmap, const float4* __restrict__ st,
+                    float* __restrict__ obs) {
+    __shared__ __align__(128) float tile[WL_SCAN_STAGES][WL_TILE_W * WL_TILE_H];
+    __shared__ __align__(8) uint64_t full[WL_SCAN_STAGES], empty[WL_SCAN_STAGES];
+    __shared__ float sp[WL_SCAN_STAGES][8];                  // bx by bz cy sy pz ox oy of the env in the stage
+    const int n = c.num_envs;
+    const float inv = c.d_inv_hf_cell;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < WL_SCAN_STAGES; ++s) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&full[s])));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&empty[s])), "r"(WL_SCAN_THREADS / 32));
         }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == WL_SCAN_THREADS / 32) {
+        // ---------------- producer ----------------
+        if (lane != 0) return;
+        int k = 0;
+        for (int i = blockIdx.x; i < n; i += gridDim.x, ++k) {
+            const int s = k % WL_SCAN_STAGES;
+            const uint32_t ph = (uint32_t)(k / WL_SCAN_STAGES) & 1u;
+            mbar_wait_parity(&empty[s], ph ^ 1u);                        // stage free (passes at once on its first use)
+            float4 g0 = ldg4(st, WL_G_POS, n, i), g1 = ldg4(st, WL_G_QUAT, n, i);
+            EnvState e0; e0.p = V3{g0.x, g0.y, g0.z}; e0.qw = g1.x; e0.qx = g1.y; e0.qy = g1.z; e0.qz = g1.w;
+            M3 R = rotmat(e0.qw, e0.qx, e0.qy, e0.qz);
+            const float bx0 = fm(c.base_link_z, R.r[2], e0.p.x), by0 = fm(c.base_link_z, R.r[5], e0.p.y), bz0 = fm(c.base_link_z, R.r[8], e0.p.z);
+            float cy0, sy0; yaw_cs(e0, cy0, sy0);
+            const float reach = c.scan_half * 1.41421356237f + c.hf_cell;
+            const int ox0 = ((int)floorf((bx0 - reach - c.hf_x0) * inv)) & ~3;
+            const int oy0 = (int)floorf((by0 - reach - c.hf_y0) * inv);
+            float* p = sp[s];
+            p[0] = bx0; p[1] = by0; p[2] = bz0; p[3] = cy0; p[4] = sy0; p[5] = e0.p.z; p[6] = __int_as_float(ox0); p[7] = __int_as_float(oy0);
+            const uint32_t mb = smem_u32(&full[s]), dst = smem_u32(tile[s]);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"((uint32_t)(WL_TILE_W * WL_TILE_H * 4)) : "memory");
+            asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                         ::"r"(dst), "l"(&tmap), "r"(ox0), "r"(oy0), "r"(mb) : "memory");
+        }
+        return;
+    }
+    // ---------------- consumers (warps 0..3) ----------------
+    int k = 0;
+    for (int i = blockIdx.x; i < n; i += gridDim.x, ++k) {
+        const int s = k % WL_SCAN_STAGES;
+        const uint32_t ph = (uint32_t)(k / WL_SCAN_STAGES) & 1u;
+        mbar_wait_parity(&full[s], ph);
+        const float bx = sp[s][0], by = sp[s][1], bz = sp[s][2], cy = sp[s][3], sy = sp[s][4], pz = sp[s][5];
+        const int ox = __float_as_int(sp[s][6]), oy = __float_as_int(sp[s][7]);
+        const float* tl = tile[s];
+        float* row = obs + (size_t)WL_OBS_DIM_ELEV * i + 13;
+        ScanPose q{bx, by, bz, cy, sy, pz, ox, oy};
+        scan_rays(c, tl, q, row, threadIdx.x);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);                           // this warp is done with the stage
     }
 }
 
@@ -1499,7 +1619,11 @@ static inline int pick_block(int n) {
 
 static int launch_scan(wl_sim* sim, float* d_obs, cudaStream_t cs) {
     const int n = sim->cfg.num_envs;
-    if (sim->scan_tma && sim->has_tmap)
+    if (sim->scan_mode == 2 && sim->has_tmap) {              // TMA producer/consumer pipeline, persistent CTAs
+        static const int per_sm = [] { const char* e = getenv("WL_SCAN_CTAS_PER_SM"); int v = e ? atoi(e) : 6; return v < 1 ? 1 : (v > 12 ? 12 : v); }();
+        const int grid = n < 148 * per_sm ? n : 148 * per_sm;    // (WL_SCAN_CTAS_PER_SM: tuning experiments only)
+        wl_scan_pipe_kernel<<<grid, WL_SCAN_THREADS + 32, 0, cs>>>(sim->cfg, sim->tmap, sim->state, d_obs);
+    } else if (sim->scan_mode >= 1 && sim->has_tmap)
         wl_scan_kernel<true><<<n, WL_SCAN_THREADS, 0, cs>>>(sim->cfg, sim->tmap, sim->state, sim->hf, d_obs);
     else
         wl_scan_kernel<false><<<n, WL_SCAN_THREADS, 0, cs>>>(sim->cfg, sim->tmap, sim->state, sim->hf, d_obs);
@@ -1577,9 +1701,18 @@ int wl_set_term_bits(wl_sim* sim, uint8_t* d_term_bits) {
 int wl_set_peer_fanout(wl_sim* sim, int32_t n_peers, const int64_t* byte_deltas) {
     if (!sim || n_peers < 0 || n_peers > WL_MAX_PEERS || (n_peers > 0 && !byte_deltas)) return fail(WL_EINVAL, "wl_set_peer_fanout: bad argument");
     if (n_peers > 0 && sim->cfg.task != WL_TASK_DRIFT) return fail(WL_EUNSUPPORTED, "wl_set_peer_fanout: Drift-family tasks only");
+    const int32_t mc = sim->fan.mc; const long long mcd = sim->fan.mc_delta;
     memset(&sim->fan, 0, sizeof sim->fan);
+    sim->fan.mc = mc; sim->fan.mc_delta = mcd;
     sim->fan.n = n_peers;
     for (int k = 0; k < n_peers; ++k) sim->fan.delta[k] = (long long)byte_deltas[k];
+    return WL_OK;
+}
+int wl_set_multicast_fanout(wl_sim* sim, int64_t mc_byte_delta) {
+    if (!sim) return fail(WL_EINVAL, "wl_set_multicast_fanout: null handle");
+    if (mc_byte_delta != 0 && sim->cfg.task != WL_TASK_DRIFT) return fail(WL_EUNSUPPORTED, "wl_set_multicast_fanout: Drift-family tasks only");
+    sim->fan.mc = mc_byte_delta != 0 ? 1 : 0;
+    sim->fan.mc_delta = (long long)mc_byte_delta;
     return WL_OK;
 }
 int wl_set_seed(wl_sim* sim, uint64_t seed) {
@@ -1673,7 +1806,7 @@ int wl_create(const wl_config* cfg, void* d_state, size_t state_bytes, const flo
     cudaGetDevice(&s->device);
     s->variant = 0;
     s->has_tmap = false;
-    s->scan_tma = true;
+    s->scan_mode = 1;
     if (cfg->task == WL_TASK_ELEVATION) {
         typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                       const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -1709,7 +1842,8 @@ int wl_destroy(wl_sim* sim) { delete sim; return WL_OK; }
 int32_t wl_obs_dim(const wl_sim* sim) { return sim ? sim->obs_dim : 0; }
 int wl_set_scan_tma(wl_sim* sim, int32_t use_tma) {
     if (!sim) return fail(WL_EINVAL, "wl_set_scan_tma: null handle");
-    sim->scan_tma = use_tma != 0;
+    if (use_tma < 0 || use_tma > 2) return fail(WL_EINVAL, "wl_set_scan_tma: 0, 1 or 2");
+    sim->scan_mode = use_tma;
     return WL_OK;
 }
 int wl_set_kernel_variant(wl_sim* sim, int32_t lanes_per_env) {
@@ -2064,6 +2198,10 @@ int wl_test_detmath(int32_t op, const float* d_in, const float* d_in2, float* d_
     if (n <= 0) return WL_OK;
     wl_detmath_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(op, d_in, d_in2 ? d_in2 : d_in, d_out, n);
     return cuda_check(cudaGetLastError(), "wl_detmath_kernel");
+}
+int wl_graph_upload(void* graph_exec, void* stream) {
+    if (!graph_exec) return fail(WL_EINVAL, "wl_graph_upload: null graph");
+    return cuda_check(cudaGraphUpload((cudaGraphExec_t)graph_exec, (cudaStream_t)stream), "cudaGraphUpload");
 }
 int wl_test_null(int32_t grid, int32_t block, void* stream) {
     wl_null_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(nullptr);

@@ -677,11 +677,33 @@ __device__ __forceinline__ void blind_obs(const wl_config& c, const EnvState& e,
 // done masks) is stored locally AND at the same offset of every peer's symmetric buffer (delta = peer base - local base),
 // so the learner-facing "all-gather" is done by the time the step kernels are: no separate collective, no staging copy.
 #define WL_MAX_PEERS 8
-struct PeerFan { int32_t n; int32_t pad; long long delta[WL_MAX_PEERS]; };
+struct PeerFan { int32_t n; int32_t mc; long long delta[WL_MAX_PEERS]; long long mc_delta; };
 template <typename TT>
 __device__ __forceinline__ void fan_store(const PeerFan& pf, TT* p, TT v) {
     *p = v;
     for (int k = 0; k < pf.n; ++k) *reinterpret_cast<TT*>(reinterpret_cast<char*>(p) + pf.delta[k]) = v;
+}
+// NVSwitch multicast form (pf.mc, wl_set_multicast_fanout): ONE multimem.st to the multicast alias of the buffer, which the
+// switch replicates into every rank's copy -- the GPU's NVLink egress is 1x the row instead of (world-1)x, and the kernel issues
+// one remote store instead of world-1.  The local copy is also stored directly, so readers on this GPU never depend on the
+// loop through the switch (the multicast write lands on the same bytes with the same value).  16- and 8-byte pieces only.
+__device__ __forceinline__ void fan_store16(const PeerFan& pf, float4* p, float4 v) {
+    if (pf.mc) {
+        *p = v;
+        asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};"
+                     ::"l"(reinterpret_cast<char*>(p) + pf.mc_delta), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+    } else {
+        fan_store(pf, p, v);
+    }
+}
+__device__ __forceinline__ void fan_store8(const PeerFan& pf, float2* p, float2 v) {
+    if (pf.mc) {
+        *p = v;
+        asm volatile("multimem.st.relaxed.sys.global.v2.f32 [%0], {%1,%2};"
+                     ::"l"(reinterpret_cast<char*>(p) + pf.mc_delta), "f"(v.x), "f"(v.y) : "memory");
+    } else {
+        fan_store(pf, p, v);
+    }
 }
 
 // quad version: lane k in {0,1,2} owns Philox block k (4 normals, drawn by quad_obs_noise at the TOP of the kernel, under

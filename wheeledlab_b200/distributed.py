@@ -109,10 +109,13 @@ class SymmetricRolloutSlab:
         self.slab = RolloutSlab(T, n_local, obs_dim, act_dim, device, policy_fields, flat=self.buf[self.rank * nbytes:(self.rank + 1) * nbytes])
         ptrs = [int(p) for p in self.handle.buffer_ptrs]
         self.peer_deltas = [ptrs[p] - ptrs[self.rank] for p in range(self.world) if p != self.rank]
+        mc = int(getattr(self.handle, "multicast_ptr", 0) or 0)    # NVSwitch multicast alias of the buffer (0: not available)
+        self.mc_delta = (mc - ptrs[self.rank]) if mc else 0
 
-    def attach(self, sim):
+    def attach(self, sim, multicast: bool = True):
         """Route the step outputs of `sim` to every peer as well."""
         sim.set_peer_fanout(self.peer_deltas)
+        sim.set_multicast_fanout(self.mc_delta if multicast else 0)
         return self
 
     def barrier(self):

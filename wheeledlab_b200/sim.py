@@ -30,6 +30,12 @@ def _stream_ptr(device) -> C.c_void_p:
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
+def upload_graph(graph: "torch.cuda.CUDAGraph", stream=None):
+    """Upload an instantiated CUDA graph to the device now (set-up time) instead of inside its first replay (wl_graph_upload)."""
+    st = stream if stream is not None else torch.cuda.current_stream()
+    check(lib.wl_graph_upload(C.c_void_p(int(graph.raw_cuda_graph_exec())), C.c_void_p(st.cuda_stream)), "wl_graph_upload")
+
+
 class WheeledSim:
     def __init__(self, spec: TaskSpec, device: str | torch.device = "cuda:0", heightfield: torch.Tensor | None = None):
         self.spec = spec
@@ -108,6 +114,11 @@ class WheeledSim:
         n = len(byte_deltas)
         arr = (C.c_int64 * max(1, n))(*byte_deltas)
         check(lib.wl_set_peer_fanout(self._h, n, arr), "wl_set_peer_fanout")
+
+    def set_multicast_fanout(self, mc_byte_delta: int):
+        """NVSwitch multicast alias of the symmetric buffer (SymmetricRolloutSlab.mc_delta): full output rows leave with one
+        multimem.st replicated by the switch; 0 switches it off.  Keep set_peer_fanout's deltas set as well."""
+        check(lib.wl_set_multicast_fanout(self._h, int(mc_byte_delta)), "wl_set_multicast_fanout")
 
     def set_step_counter(self, value: int):
         check(lib.wl_set_step_counter(self._h, value, _stream_ptr(self.device)), "wl_set_step_counter")
@@ -283,8 +294,9 @@ class WheeledSim:
               "wl_derive_suspension")
         return pos, vel
 
-    def set_scan_tma(self, use_tma: bool):
-        check(lib.wl_set_scan_tma(self._h, 1 if use_tma else 0), "wl_set_scan_tma")
+    def set_scan_tma(self, mode):
+        """Height-scan tile staging: 1/True one TMA tile per CTA (default), 2 TMA producer/consumer pipeline, 0/False plain loads."""
+        check(lib.wl_set_scan_tma(self._h, int(mode)), "wl_set_scan_tma")
 
     def set_kernel_variant(self, lanes_per_env: int):
         """0 auto, 1 thread-per-env, 4 quad-per-env, 8 quad + aux warp (Drift family); bit-identical results."""
