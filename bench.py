@@ -53,14 +53,14 @@ UNIT = "env-steps/s"
 BYTES_PER_ENV_STEP = (13 * 16 + 8) + (9 * 16 + 56 + 4 + 2)
 WORKLOADS = {
     "drift": {"task": "drift", "envs": 4096, "bytes": BYTES_PER_ENV_STEP, "obs_dim": 14, "blob": "drift.bin",
-              "label": "RSS_DRIFT_CONFIG MushrDriftRL, dt 5ms x4, DR+push+noise on", "kernel": "wl_step_quad_kernel<DRIFT>",
+              "label": "RSS_DRIFT_CONFIG MushrDriftRL, dt 5ms x4, DR+push+noise on", "kernel": "wl_step_duo_kernel (Drift family, 8 envs per CTA)",
               "traffic_profile": "profiles/r02_ncu_step_drift_4096.txt"},
     "elev": {"task": "elevation", "envs": 4096, "bytes": (15 * 16 + 8) + (11 * 16 + 689 * 4 + 4 + 2), "obs_dim": 689, "blob": "elevation.bin",
              "label": "RSS_ELEV_CONFIG MushrElevationRL, dt 10ms x10 (5 ms sub-steps), reference terrain raster + 676-ray height scan",
              "kernel": "wl_step_quad_kernel<ELEVATION> + wl_scan_kernel<TMA>", "traffic_profile": "profiles/r02_ncu_step_elev_4096.txt"},
     "hound4wd": {"task": "hound_4wd", "envs": 8192, "bytes": BYTES_PER_ENV_STEP, "obs_dim": 14, "blob": "hound_4wd.bin",
                  "label": "HOUND 4WD: MuSHR + HOUND_SUS_ACTUATOR_CFG (4 driven wheels) + Mushr4WDActionCfg, mass/friction DR, dt 5ms x4",
-                 "kernel": "wl_step_quad_kernel<DRIFT> (4WD action map)", "traffic_profile": "profiles/r02_ncu_step_hound_8192.txt"},
+                 "kernel": "wl_step_duo_kernel (4WD action map)", "traffic_profile": "profiles/r02_ncu_step_hound_8192.txt"},
 }
 L2_BYTES = 126 * 1024 * 1024
 
@@ -657,7 +657,8 @@ def run_ours(args):
                          "traffic": _traffic(w["traffic_profile"]) if E == w["envs"] else None, "traffic_unit": "bytes/launch (dram read + write, ncu --set full)",
                          "traffic_source": w["traffic_profile"], "peak_source": peak_src, "kernel": w["kernel"],
                          "bytes_per_env_step": w["bytes"], "avg_step_us": kern_s * 1e6,
-                         "kernel_variant": "quad (4 lanes/env)" if E <= 148 * 4 * 32 * 2 else "thread-per-env",
+                         "kernel_variant": ("duo (8 envs per 64-thread CTA: env warp 4 lanes/env + aux warp)" if (fam and E <= 37888)
+                                            else "quad (4 lanes/env)" if E <= 148 * 4 * 32 * 2 else "thread-per-env"),
                          "note": f"{E} envs move {w['bytes'] * E / 1e6:.1f} MB per launch: latency-bound at this size, see profiles/ for the N sweep"},
             "cpu_baseline": cpu,
             "flush_protocol": {"step_us_median": statistics.median(flush_us), "step_us_mean": statistics.mean(flush_us),

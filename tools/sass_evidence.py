@@ -12,7 +12,7 @@ from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent.parent
 LIB = ROOT / "wheeledlab_b200" / "libwheeledlab_b200.so"
-KEYS = ["INSTR", "UTMALDG", "UBLKCP", "SYNCS", "BAR.ARV", "BAR.SYNC", "REDG", "ATOMG", "MUFU.RCP", "MUFU.RSQ", "FCHK", "SHFL"]
+KEYS = ["INSTR", "UTMALDG", "UBLKCP", "SYNCS", "BAR.ARV", "BAR.SYNC", "REDG", "ATOMG", "MUFU.RCP", "MUFU.RSQ", "FCHK", "SHFL", "STRONG.SYS"]
 
 
 def main():
@@ -30,7 +30,7 @@ def main():
         for k in KEYS[1:]:
             if k in m.group(2):
                 rows[name][k] += 1
-        if "UTMALDG" in m.group(2) or "UBLKCP" in m.group(2):
+        if "UTMALDG" in m.group(2) or "UBLKCP" in m.group(2) or ("STG" in m.group(2) and "STRONG.SYS" in m.group(2)):
             proofs.append(f"{name}: /*{m.group(1)}*/ {m.group(2).strip()}")
     print("# cuobjdump -sass wheeledlab_b200/libwheeledlab_b200.so (sm_100a): static instruction count per kernel and the mnemonics that prove the")
     print("# hardware paths used.  UTMALDG.2D = cp.async.bulk.tensor.2d (TMA tile of the height-field, wl_scan_kernel<true>); UBLKCP = cp.async.bulk")
@@ -38,6 +38,9 @@ def main():
     print("# of the env-warp / aux-warp hand-off (wl_step_duo_kernel); REDG = fire-and-forget reductions of the episode log (no ticket, no fence);")
     print("# ATOMG = the K-step rollout's last-CTA ticket; FCHK = range check of an IEEE division with slow-path call (the integrator sub-step uses")
     print("# fdiv_norm / fsqrt_norm instead).  No tcgen05 / TMEM anywhere: there is no dense contraction on this path (tensor cores unused by design).")
+    print("# STG...STRONG.SYS = multimem.st.relaxed.sys (wl_step_duo_kernel: output rows stored once to the NVSwitch multicast alias of the symmetric")
+    print("# rollout buffers, replicated by the switch into every rank's copy; wl_set_multicast_fanout); in the other kernels STRONG.SYS marks the")
+    print("# system-scope loads/stores of the peer-memory all-reduce (wl_dp_adam_kernel) and of the flag protocols.")
     print("kernel | " + " | ".join(KEYS))
     for n in sorted(rows):
         print(n[:64] + " | " + " | ".join(str(rows[n].get(k, 0)) for k in KEYS))

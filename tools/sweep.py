@@ -16,13 +16,13 @@ from bench import BYTES_PER_ENV_STEP, _peaks  # noqa: E402
 
 TASK = "drift"
 VARIANT = 0
-BYTES = {"drift": BYTES_PER_ENV_STEP, "elevation": (15 * 16 + 8) + (11 * 16 + 689 * 4 + 4 + 2),
+BYTES = {"drift": BYTES_PER_ENV_STEP, "hound_4wd": BYTES_PER_ENV_STEP, "elevation": (15 * 16 + 8) + (11 * 16 + 689 * 4 + 4 + 2),
          "visual_cam": BYTES_PER_ENV_STEP - 14 * 4 + 3208 * 4 + 32,    # step state r/w + obs row written (camera 3200 + 8) + pose re-read
          "camera": 3200 * 4 + 32}                                      # wl_camera_kernel alone: 12.8 KB written + pose (pos, quat) read
 
 
 def one(n, steps, warm, flush):
-    spec = {"drift": lambda: wl.drift_task(num_envs=n, seed=42), "elevation": lambda: wl.elevation_task(num_envs=n, seed=42),
+    spec = {"drift": lambda: wl.drift_task(num_envs=n, seed=42), "hound_4wd": lambda: wl.make_task("hound_4wd", num_envs=n, seed=42), "elevation": lambda: wl.elevation_task(num_envs=n, seed=42),
             "visual_cam": lambda: wl.visual_task(num_envs=n, seed=42, camera="aug"),
             "camera": lambda: wl.visual_task(num_envs=n, seed=42, camera="aug")}[TASK]()
     sim = wl.WheeledSim(spec, "cuda:0")
@@ -55,7 +55,7 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warm", type=int, default=5)
     ap.add_argument("--no-flush", action="store_true")
-    ap.add_argument("--task", default="drift", choices=["drift", "elevation", "visual_cam", "camera"])
+    ap.add_argument("--task", default="drift", choices=["drift", "hound_4wd", "elevation", "visual_cam", "camera"])
     ap.add_argument("--variant", type=int, default=0, help="0 auto, 1 thread/env, 4 quad/env")
     a = ap.parse_args()
     global TASK, VARIANT

@@ -456,6 +456,9 @@ struct DuoShared {
 __device__ __forceinline__ void bar_arrive(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ void bar_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 
+// FAN = false: no peer: the fan-out / multicast / packed-row code is not in the kernel at all (the dependent stream of one warp
+// per scheduler also pays for instruction fetch: 256 static instructions fewer on the single-GPU path)
+template <bool FAN>
 __global__ void __launch_bounds__(64)
 wl_step_duo_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st, wl_globals* __restrict__ gl,
                    const float2* __restrict__ action, float* __restrict__ obs, float* __restrict__ rew,
@@ -552,9 +555,10 @@ wl_step_duo_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st,
                 }
             }
             done = tmask != 0u;
-            // full CTA with aligned rows: 32 + 8 + 8 contiguous bytes leave as four wide stores (HBM, and -- fan-out -- one
-            // NVLink / multicast write each instead of 24 small ones); otherwise element by element
-            const bool packed = (env0 + WL_DUO_ENVS <= n) && ((reinterpret_cast<uintptr_t>(rew + env0) & 15u) == 0) &&
+            // fan-out active, full CTA, aligned rows: 32 + 8 + 8 contiguous bytes leave as four wide stores (one NVLink /
+            // multicast write each instead of 24 small ones); otherwise element by element (without peers the staging round
+            // trip sits at the kernel's tail and costs 0.17 us per step, profiles/r02_kexp_pack.txt)
+            const bool packed = FAN && ((pf.n | pf.mc) != 0) && (env0 + WL_DUO_ENVS <= n) && ((reinterpret_cast<uintptr_t>(rew + env0) & 15u) == 0) &&
                                 (((reinterpret_cast<uintptr_t>(terminated_o + env0) | reinterpret_cast<uintptr_t>(truncated_o + env0)) & 7u) == 0);
             const uint8_t tb = (uint8_t)((tmask & ~1u) ? 1 : 0), ub = (uint8_t)((tmask & 1u) ? 1 : 0);
             if (packed) {
@@ -564,9 +568,8 @@ wl_step_duo_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st,
                 else if (lane == 2) fan_store8(pf, reinterpret_cast<float2*>(terminated_o + env0), *reinterpret_cast<const float2*>(sh.maskrow[0]));
                 else if (lane == 3) fan_store8(pf, reinterpret_cast<float2*>(truncated_o + env0), *reinterpret_cast<const float2*>(sh.maskrow[1]));
             } else if (live) {
-                fan_store(pf, &rew[i], total);
-                fan_store(pf, &terminated_o[i], tb);
-                fan_store(pf, &truncated_o[i], ub);
+                if (FAN) { fan_store(pf, &rew[i], total); fan_store(pf, &terminated_o[i], tb); fan_store(pf, &truncated_o[i], ub); }
+                else { rew[i] = total; terminated_o[i] = tb; truncated_o[i] = ub; }
             }
             if (live && term_bits != nullptr) term_bits[i] = (uint8_t)tmask;
         }
@@ -669,9 +672,13 @@ wl_step_duo_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st,
         if (w < 3) { so[2] = v.z; so[3] = v.w; }
         __syncwarp();
         if (lane < (WL_DUO_ENVS * WL_OBS_DIM_BLIND) / 4)
-            fan_store16(pf, reinterpret_cast<float4*>(orow0) + lane, reinterpret_cast<const float4*>(sh.obs)[lane]);
+        {
+            if (FAN) fan_store16(pf, reinterpret_cast<float4*>(orow0) + lane, reinterpret_cast<const float4*>(sh.obs)[lane]);
+            else reinterpret_cast<float4*>(orow0)[lane] = reinterpret_cast<const float4*>(sh.obs)[lane];
+        }
     } else {
-        blind_obs_quad(c, e, w, eu_k, vb, wbo, zn, obs + (size_t)WL_OBS_DIM_BLIND * ii, live, pf);
+        if (FAN) blind_obs_quad(c, e, w, eu_k, vb, wbo, zn, obs + (size_t)WL_OBS_DIM_BLIND * ii, live, pf);
+        else blind_obs_quad(c, e, w, eu_k, vb, wbo, zn, obs + (size_t)WL_OBS_DIM_BLIND * ii, live);
     }
     if (live) store_env_quad(st, n, i, w, e, false, false);
 }
@@ -1925,7 +1932,10 @@ int wl_step(wl_sim* sim, const float* d_action, float* d_obs, float* d_rew, uint
     StageIO sio0{sim->term_bits, nullptr, nullptr};
     if (variant == 8) {
         const int grid = (n + WL_DUO_ENVS - 1) / WL_DUO_ENVS + 1;                            // + the janitor CTA
-        launch_k(wl_step_duo_kernel, grid, 64, 0, cs, sim->cfg, sim->state, sim->globals, act, d_obs, d_rew, d_terminated, d_truncated, d_log, t, sim->term_bits, sim->fan);
+        if (sim->fan.n > 0 || sim->fan.mc)
+            launch_k(wl_step_duo_kernel<true>, grid, 64, 0, cs, sim->cfg, sim->state, sim->globals, act, d_obs, d_rew, d_terminated, d_truncated, d_log, t, sim->term_bits, sim->fan);
+        else
+            launch_k(wl_step_duo_kernel<false>, grid, 64, 0, cs, sim->cfg, sim->state, sim->globals, act, d_obs, d_rew, d_terminated, d_truncated, d_log, t, sim->term_bits, sim->fan);
     } else if (sim->fan.n > 0) {
         return fail(WL_EUNSUPPORTED, "wl_step: the peer fan-out is implemented by the Drift-family small-N kernel (variant 8) only");
     } else if (variant == 4) {

@@ -729,12 +729,20 @@ __device__ __forceinline__ float4 blind_obs_quad_values(const wl_config& c, cons
     return make_float4(b0 + s0 * z[0], b1 + s1 * z[1], b2 + s2 * z[2], b3 + s3 * z[3]);
 }
 __device__ __forceinline__ void blind_obs_quad(const wl_config& c, const EnvState& e, int w, float eu_k, V3 vb, V3 wb, const float z[4],
-                                               float* __restrict__ obs, bool live, const PeerFan& pf = PeerFan{0, 0, {0, 0, 0, 0, 0, 0, 0, 0}}) {
+                                               float* __restrict__ obs, bool live, const PeerFan& pf) {
     const float4 v = blind_obs_quad_values(c, e, w, eu_k, vb, wb, z);
     float2* o2 = reinterpret_cast<float2*>(obs + 4 * w);
     if (!live) return;
     fan_store(pf, &o2[0], make_float2(v.x, v.y));
     if (w < 3) fan_store(pf, &o2[1], make_float2(v.z, v.w));
+}
+__device__ __forceinline__ void blind_obs_quad(const wl_config& c, const EnvState& e, int w, float eu_k, V3 vb, V3 wb, const float z[4],
+                                               float* __restrict__ obs, bool live) {
+    const float4 v = blind_obs_quad_values(c, e, w, eu_k, vb, wb, z);
+    float2* o2 = reinterpret_cast<float2*>(obs + 4 * w);
+    if (!live) return;
+    o2[0] = make_float2(v.x, v.y);
+    if (w < 3) o2[1] = make_float2(v.z, v.w);
 }
 
 }  // namespace wl
