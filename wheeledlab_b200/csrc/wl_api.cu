@@ -456,9 +456,12 @@ struct DuoShared {
 __device__ __forceinline__ void bar_arrive(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ void bar_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 
-// FAN = false: no peer: the fan-out / multicast / packed-row code is not in the kernel at all (the dependent stream of one warp
-// per scheduler also pays for instruction fetch: 256 static instructions fewer on the single-GPU path)
-template <bool FAN>
+// FAN = 0: no peer: the fan-out / multicast / packed-row code is not in the kernel at all (the dependent stream of one warp per
+// scheduler also pays for instruction fetch: 770 static instructions fewer on the single-GPU path, 0.4 us per step).
+// FAN = 2: multicast only -- the host has checked that num_envs is a multiple of 8 and the output rows are aligned, so every row
+// is a full wide store: local copy + ONE multimem.st, no per-peer loops, no element-wise fallback in the instruction stream.
+// FAN = 1: the general fan-out (per-peer stores; multicast for the rows that qualify).
+template <int FAN>
 __global__ void __launch_bounds__(64)
 wl_step_duo_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st, wl_globals* __restrict__ gl,
                    const float2* __restrict__ action, float* __restrict__ obs, float* __restrict__ rew,
@@ -558,17 +561,17 @@ wl_step_duo_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st,
             // fan-out active, full CTA, aligned rows: 32 + 8 + 8 contiguous bytes leave as four wide stores (one NVLink /
             // multicast write each instead of 24 small ones); otherwise element by element (without peers the staging round
             // trip sits at the kernel's tail and costs 0.17 us per step, profiles/r02_kexp_pack.txt)
-            const bool packed = FAN && ((pf.n | pf.mc) != 0) && (env0 + WL_DUO_ENVS <= n) && ((reinterpret_cast<uintptr_t>(rew + env0) & 15u) == 0) &&
-                                (((reinterpret_cast<uintptr_t>(terminated_o + env0) | reinterpret_cast<uintptr_t>(truncated_o + env0)) & 7u) == 0);
+            const bool packed = (FAN == 2) || ((FAN == 1) && ((pf.n | pf.mc) != 0) && (env0 + WL_DUO_ENVS <= n) && ((reinterpret_cast<uintptr_t>(rew + env0) & 15u) == 0) &&
+                                (((reinterpret_cast<uintptr_t>(terminated_o + env0) | reinterpret_cast<uintptr_t>(truncated_o + env0)) & 7u) == 0));
             const uint8_t tb = (uint8_t)((tmask & ~1u) ? 1 : 0), ub = (uint8_t)((tmask & 1u) ? 1 : 0);
             if (packed) {
                 sh.rewrow[lane] = total; sh.maskrow[0][lane] = tb; sh.maskrow[1][lane] = ub;
                 __syncwarp(0xffu);
-                if (lane < 2) fan_store16(pf, reinterpret_cast<float4*>(rew + env0) + lane, reinterpret_cast<const float4*>(sh.rewrow)[lane]);
-                else if (lane == 2) fan_store8(pf, reinterpret_cast<float2*>(terminated_o + env0), *reinterpret_cast<const float2*>(sh.maskrow[0]));
-                else if (lane == 3) fan_store8(pf, reinterpret_cast<float2*>(truncated_o + env0), *reinterpret_cast<const float2*>(sh.maskrow[1]));
+                if (lane < 2) fan_store16<FAN == 2>(pf, reinterpret_cast<float4*>(rew + env0) + lane, reinterpret_cast<const float4*>(sh.rewrow)[lane]);
+                else if (lane == 2) fan_store8<FAN == 2>(pf, reinterpret_cast<float2*>(terminated_o + env0), *reinterpret_cast<const float2*>(sh.maskrow[0]));
+                else if (lane == 3) fan_store8<FAN == 2>(pf, reinterpret_cast<float2*>(truncated_o + env0), *reinterpret_cast<const float2*>(sh.maskrow[1]));
             } else if (live) {
-                if (FAN) { fan_store(pf, &rew[i], total); fan_store(pf, &terminated_o[i], tb); fan_store(pf, &truncated_o[i], ub); }
+                if (FAN == 1) { fan_store(pf, &rew[i], total); fan_store(pf, &terminated_o[i], tb); fan_store(pf, &truncated_o[i], ub); }
                 else { rew[i] = total; terminated_o[i] = tb; truncated_o[i] = ub; }
             }
             if (live && term_bits != nullptr) term_bits[i] = (uint8_t)tmask;
@@ -665,7 +668,7 @@ wl_step_duo_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st,
     // the CTA's 8 observation rows are 448 contiguous bytes: staged in shared memory and written as 28 x 128-bit stores
     // (full sectors towards HBM, NVLink peers and -- zero-copy host transport -- PCIe, instead of 8-byte pieces)
     float* orow0 = obs + (size_t)WL_OBS_DIM_BLIND * env0;
-    if (env0 + WL_DUO_ENVS <= n && (reinterpret_cast<uintptr_t>(orow0) & 15u) == 0) {
+    if ((FAN == 2) || (env0 + WL_DUO_ENVS <= n && (reinterpret_cast<uintptr_t>(orow0) & 15u) == 0)) {
         const float4 v = blind_obs_quad_values(c, e, w, eu_k, vb, wbo, zn);
         float* so = sh.obs + WL_OBS_DIM_BLIND * q + 4 * w;
         so[0] = v.x; so[1] = v.y;
@@ -673,11 +676,11 @@ wl_step_duo_kernel(const __grid_constant__ wl_config c, float4* __restrict__ st,
         __syncwarp();
         if (lane < (WL_DUO_ENVS * WL_OBS_DIM_BLIND) / 4)
         {
-            if (FAN) fan_store16(pf, reinterpret_cast<float4*>(orow0) + lane, reinterpret_cast<const float4*>(sh.obs)[lane]);
+            if (FAN) fan_store16<FAN == 2>(pf, reinterpret_cast<float4*>(orow0) + lane, reinterpret_cast<const float4*>(sh.obs)[lane]);
             else reinterpret_cast<float4*>(orow0)[lane] = reinterpret_cast<const float4*>(sh.obs)[lane];
         }
     } else {
-        if (FAN) blind_obs_quad(c, e, w, eu_k, vb, wbo, zn, obs + (size_t)WL_OBS_DIM_BLIND * ii, live, pf);
+        if (FAN == 1) blind_obs_quad(c, e, w, eu_k, vb, wbo, zn, obs + (size_t)WL_OBS_DIM_BLIND * ii, live, pf);
         else blind_obs_quad(c, e, w, eu_k, vb, wbo, zn, obs + (size_t)WL_OBS_DIM_BLIND * ii, live);
     }
     if (live) store_env_quad(st, n, i, w, e, false, false);
@@ -1932,10 +1935,14 @@ int wl_step(wl_sim* sim, const float* d_action, float* d_obs, float* d_rew, uint
     StageIO sio0{sim->term_bits, nullptr, nullptr};
     if (variant == 8) {
         const int grid = (n + WL_DUO_ENVS - 1) / WL_DUO_ENVS + 1;                            // + the janitor CTA
-        if (sim->fan.n > 0 || sim->fan.mc)
-            launch_k(wl_step_duo_kernel<true>, grid, 64, 0, cs, sim->cfg, sim->state, sim->globals, act, d_obs, d_rew, d_terminated, d_truncated, d_log, t, sim->term_bits, sim->fan);
+        const bool rows_ok = (n % WL_DUO_ENVS) == 0 && (((uintptr_t)d_obs | (uintptr_t)d_rew) & 15u) == 0 &&
+                             (((uintptr_t)d_terminated | (uintptr_t)d_truncated) & 7u) == 0;
+        if (sim->fan.mc && rows_ok)
+            launch_k(wl_step_duo_kernel<2>, grid, 64, 0, cs, sim->cfg, sim->state, sim->globals, act, d_obs, d_rew, d_terminated, d_truncated, d_log, t, sim->term_bits, sim->fan);
+        else if (sim->fan.n > 0 || sim->fan.mc)
+            launch_k(wl_step_duo_kernel<1>, grid, 64, 0, cs, sim->cfg, sim->state, sim->globals, act, d_obs, d_rew, d_terminated, d_truncated, d_log, t, sim->term_bits, sim->fan);
         else
-            launch_k(wl_step_duo_kernel<false>, grid, 64, 0, cs, sim->cfg, sim->state, sim->globals, act, d_obs, d_rew, d_terminated, d_truncated, d_log, t, sim->term_bits, sim->fan);
+            launch_k(wl_step_duo_kernel<0>, grid, 64, 0, cs, sim->cfg, sim->state, sim->globals, act, d_obs, d_rew, d_terminated, d_truncated, d_log, t, sim->term_bits, sim->fan);
     } else if (sim->fan.n > 0) {
         return fail(WL_EUNSUPPORTED, "wl_step: the peer fan-out is implemented by the Drift-family small-N kernel (variant 8) only");
     } else if (variant == 4) {

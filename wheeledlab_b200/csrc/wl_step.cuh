@@ -687,8 +687,10 @@ __device__ __forceinline__ void fan_store(const PeerFan& pf, TT* p, TT v) {
 // switch replicates into every rank's copy -- the GPU's NVLink egress is 1x the row instead of (world-1)x, and the kernel issues
 // one remote store instead of world-1.  The local copy is also stored directly, so readers on this GPU never depend on the
 // loop through the switch (the multicast write lands on the same bytes with the same value).  16- and 8-byte pieces only.
+// MC_ONLY: the host has checked that every row of the launch is full and aligned -- no per-peer path in the kernel at all
+template <bool MC_ONLY = false>
 __device__ __forceinline__ void fan_store16(const PeerFan& pf, float4* p, float4 v) {
-    if (pf.mc) {
+    if (MC_ONLY || pf.mc) {
         *p = v;
         asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};"
                      ::"l"(reinterpret_cast<char*>(p) + pf.mc_delta), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
@@ -696,8 +698,9 @@ __device__ __forceinline__ void fan_store16(const PeerFan& pf, float4* p, float4
         fan_store(pf, p, v);
     }
 }
+template <bool MC_ONLY = false>
 __device__ __forceinline__ void fan_store8(const PeerFan& pf, float2* p, float2 v) {
-    if (pf.mc) {
+    if (MC_ONLY || pf.mc) {
         *p = v;
         asm volatile("multimem.st.relaxed.sys.global.v2.f32 [%0], {%1,%2};"
                      ::"l"(reinterpret_cast<char*>(p) + pf.mc_delta), "f"(v.x), "f"(v.y) : "memory");
