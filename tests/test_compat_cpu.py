@@ -147,3 +147,18 @@ def test_make_task_reproduces_the_lowered_reference_cfgs():
         kw = {"traversability": ref_map} if "Visual" in gid else {}
         spec = wl.make_task(gid, num_envs=4096, seed=42, **kw)
         assert _cfg_blob(spec.cfg) == (blobs / f"{gid}.ref.bin").read_bytes(), gid
+
+
+def test_torch_ops_front_registers_and_rejects_cpu_tensors():
+    """torch.ops.wheeledlab_b200.* (csrc/wl_torch_ops.cpp): the schemas the PyTorch-extension boundary declares exist, outputs
+    are declared as written in place, and a CPU tensor fails loudly (CUDA dispatch key only: no CPU path)."""
+    import torch
+    from wheeledlab_b200 import torch_ops
+    ops = torch_ops.load()
+    sch = {name: str(getattr(ops, name).default._schema) for name in ("step", "step_out", "observe_out", "reset")}
+    assert "Tensor(a!) obs" in sch["step_out"] and "Tensor(d!) truncated" in sch["step_out"] and "Tensor(e!)? log" in sch["step_out"]
+    assert sch["step"].endswith("-> (Tensor, Tensor, Tensor, Tensor)")
+    assert "Tensor? env_ids" in sch["reset"] and "Tensor(a!) obs" in sch["observe_out"]
+    import pytest
+    with pytest.raises(NotImplementedError):
+        ops.step(1, torch.zeros(4, 2), 0)

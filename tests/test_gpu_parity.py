@@ -1083,3 +1083,62 @@ def test_two_process_fused_allreduce_adam(tmp_path):
            "--master-port", "29737", str(root / "tools" / "dp_adam_check.py"), "--out", str(out)]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and out.read_text().startswith("ok"), r.stderr[-2000:]
+
+
+def test_torch_ops_front_equals_ctypes_host_and_checks_arguments():
+    """torch.ops.wheeledlab_b200.{reset, observe_out, step, step_out} drive the same kernels as the ctypes host: two handles of
+    the same task stepped side by side (one through each front) stay bit-identical, on a non-default stream and inside a CUDA
+    graph; malformed arguments raise RuntimeError naming the argument instead of reaching the kernel."""
+    _need_gpu()
+    import torch
+    import wheeledlab_b200 as wl
+    from wheeledlab_b200 import torch_ops
+    ops = torch_ops.load()
+    n = 1024
+    a = wl.WheeledSim(wl.drift_task(num_envs=n, seed=5), "cuda:0"); a.startup(); a.reset(None, 0)
+    b = wl.WheeledSim(wl.drift_task(num_envs=n, seed=5), "cuda:0"); b.startup()
+    like = torch.empty(1, device="cuda:0")
+    ops.reset(b.handle, None, like, 0)
+    oa = a.observe(0)
+    ob = torch.empty_like(oa); ops.observe_out(b.handle, ob, 0, 0)
+    assert torch.equal(oa.view(torch.int32), ob.view(torch.int32))
+    s = torch.cuda.Stream()
+    for t in range(40):
+        act = a.synth_actions(t)
+        ra = a.step(act, t)
+        if t % 2 == 0:
+            rb = ops.step(b.handle, act, t)
+        else:                                                    # in-place form, on a side stream
+            rb = (torch.empty_like(ra[0]), torch.empty_like(ra[1]), torch.empty_like(ra[2]), torch.empty_like(ra[3]))
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                ops.step_out(b.handle, act, rb[0], rb[1], rb[2], rb[3], None, t)
+            torch.cuda.current_stream().wait_stream(s)
+        for x, y in zip(ra, rb):
+            assert torch.equal(x.view(torch.uint8), y.view(torch.uint8)), t
+    ids = torch.tensor([3, 77, 500], device="cuda:0")
+    a.reset(ids, 40); ops.reset(b.handle, ids, like, 40)
+    assert torch.equal(a.state_snapshot().view(torch.int32)[: 16 * n * 4], b.state_snapshot().view(torch.int32)[: 16 * n * 4])
+    # graph capture through the op
+    act = a.synth_actions(41)
+    outs = tuple(torch.empty_like(x) for x in ra)
+    g = torch.cuda.CUDAGraph(); cs = torch.cuda.Stream(); cs.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(cs), torch.cuda.graph(g, stream=cs):
+        ops.step_out(b.handle, act, outs[0], outs[1], outs[2], outs[3], None, 40)
+    torch.cuda.current_stream().wait_stream(cs)
+    g.replay()
+    ra = a.step(act, 40)
+    torch.cuda.synchronize()
+    for x, y in zip(ra, outs):
+        assert torch.equal(x.view(torch.uint8), y.view(torch.uint8))
+    # argument checks
+    with pytest.raises(RuntimeError, match="action"):
+        ops.step(b.handle, torch.zeros(n, 3, device="cuda:0"), 41)
+    with pytest.raises(RuntimeError, match="dtype"):
+        ops.step(b.handle, torch.zeros(n, 2, device="cuda:0", dtype=torch.float64), 41)
+    with pytest.raises(RuntimeError, match="obs"):
+        ops.step_out(b.handle, act, torch.empty(n, 13, device="cuda:0"), outs[1], outs[2], outs[3], None, 41)
+    with pytest.raises(RuntimeError, match="contiguous"):
+        ops.step(b.handle, torch.zeros(2, n, device="cuda:0").t(), 41)
+    with pytest.raises(RuntimeError, match="null"):
+        ops.step(0, act, 41)

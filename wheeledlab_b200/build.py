@@ -35,6 +35,26 @@ def build_native(force: bool = False, verbose: bool = False) -> Path:
     return LIB
 
 
+TORCH_OPS = PKG / "_wl_torch_ops.so"
+
+
+def build_torch_ops(force: bool = False) -> Path:
+    """The PyTorch-extension front (csrc/wl_torch_ops.cpp, `torch.ops.wheeledlab_b200.*`): plain g++ against torch's headers,
+    linked to the CUDA library next to it (rpath $ORIGIN).  No kernels in it; ~10 s to compile."""
+    import torch
+    from torch.utils import cpp_extension as ce
+    build_native()
+    src = CSRC / "wl_torch_ops.cpp"
+    if force or _stale(TORCH_OPS, [src, ROOT / "include" / "wheeledlab_b200.h"]):
+        tlib = ce.library_paths()[0]
+        cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", f"-D_GLIBCXX_USE_CXX11_ABI={int(torch._C._GLIBCXX_USE_CXX11_ABI)}",
+               *[f"-I{p}" for p in ce.include_paths()], "-I/usr/local/cuda/include", str(src), "-o", str(TORCH_OPS),
+               f"-L{tlib}", "-ltorch", "-ltorch_cpu", "-ltorch_cuda", "-lc10", "-lc10_cuda", f"-L{PKG}", f"-l:{LIB.name}",
+               "-Wl,-rpath,$ORIGIN", f"-Wl,-rpath,{tlib}"]
+        subprocess.run(cmd, check=True, cwd=str(ROOT))
+    return TORCH_OPS
+
+
 def build_oracle(force: bool = False, native: bool = False) -> Path:
     odir = ROOT / "oracle"
     targets = ["libwl_oracle.so", "libwl_oracle_f64.so"] + (["libwl_oracle_native.so"] if native else [])
@@ -46,4 +66,5 @@ def build_oracle(force: bool = False, native: bool = False) -> Path:
 
 if __name__ == "__main__":
     print(build_native(force=True, verbose=True))
+    print(build_torch_ops(force=True))
     print(build_oracle())

@@ -108,6 +108,11 @@ class WheeledSim:
         """step_counter value meaning "the counter base kept in device memory + k" (WL_DEVICE_COUNTER_PLUS)."""
         return -1 - k
 
+    @property
+    def handle(self) -> int:
+        """The wl_sim* as an int (what torch.ops.wheeledlab_b200.* and foreign callers of the C-ABI take)."""
+        return int(self._h.value)
+
     def set_peer_fanout(self, byte_deltas):
         """Every output row of step() is also stored at pointer + delta for each delta (peer symmetric buffers, see
         distributed.SymmetricRolloutSlab); [] switches the fan-out off."""
