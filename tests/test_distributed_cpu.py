@@ -89,3 +89,22 @@ def test_rollout_recording_uses_the_reference_playback_format(tmp_path):
     d = load_rollouts(p)
     assert d["observations"].shape == (4, 5, 14) and d["actions"].shape == (4, 5, 2)
     assert torch.equal(d["observations"], slab.obs[:4]) and float(d["actions"].mean()) == 0.25
+
+
+def test_bench_reference_arm_under_torchrun_prints_one_line(tmp_path):
+    """`bench.py --impl reference` launched the way the driver launches it for N > 1 (torchrun, one process per GPU): rank 0
+    alone times the CPU implementation and prints ONE JSON line with the bench contract's keys; the other ranks exit 0."""
+    import json
+    import subprocess
+    import sys
+    root = Path(__file__).resolve().parent.parent
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29741", str(root / "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "3", "--warmup", "3"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "env_steps_per_sec" and d["n_gpus"] == 2 and d["steps"] == 3
+    assert d["value"] > 0 and d["higher_is_better"] is True and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0

@@ -1,17 +1,7 @@
+# the standard single-GPU check on a B200 box: GPU parity tests, smoke(), the default bench line
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests -m gpu -x -q -k "torch_ops" 2>&1 | tail -15
-timeout 100 python - <<'PY' 2>&1 | tail -3
-import time, torch, wheeledlab_b200 as wl
-from wheeledlab_b200 import torch_ops
-ops = torch_ops.load()
-sim = wl.WheeledSim(wl.drift_task(num_envs=4096, seed=1), "cuda:0"); sim.startup(); sim.reset(None, 0)
-act = sim.synth_actions(0); outs = sim.step(act, 0); t = 1
-f = sim.bind_step(act, outs)
-for name, fn in (("ctypes sim.step", lambda t: sim.step(act, t, out=outs)), ("ctypes bound", lambda t: f(t)),
-                 ("torch.ops step_out", lambda t: ops.step_out(sim.handle, act, outs[0], outs[1], outs[2], outs[3], None, t))):
-    for _ in range(200): fn(t); t += 1
-    torch.cuda.synchronize(); t0 = time.perf_counter()
-    for _ in range(3000): fn(t); t += 1
-    t1 = time.perf_counter(); torch.cuda.synchronize()
-    print(name, "host us per call:", round((t1 - t0) / 3000 * 1e6, 2))
-PY
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -6 > gpurun_out/gputest_1gpu.log; tail -2 gpurun_out/gputest_1gpu.log
+timeout 120 python -c "
+import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+timeout 400 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_1gpu.json 2> gpurun_out/bench_1gpu.err; python -c "
+import json; d=json.load(open('gpurun_out/bench_1gpu.json')); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline']['frac'], d['gpu_launches'])"

@@ -35,13 +35,6 @@ import json; d=json.load(open('gpurun_out/r02_bench_n${N}_${mode}_k$K.json')); p
     done
   done
 fi
-if [ "$WHAT" = toggles ]; then
-  for tg in WL_BENCH_NOUPLOAD WL_BENCH_NOALIGN WL_BENCH_NOSETUPX NONE; do
-    env $tg=1 timeout 170 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29871 bench.py --gpus $N --steps 20 --warmup 5 --no-extras --gather ${MODE:-ce} > gpurun_out/tg.json 2> gpurun_out/tg.err
-    python -c "
-import json; d=json.load(open('gpurun_out/tg.json')); print('$tg', d['value'], d['ms_per_step'], d['per_rank'])" 2>&1 | tail -1
-  done
-fi
 if [ "$WHAT" = mcast ]; then
   timeout 170 python -m pytest tests -m gpu -x -q -k "two_process_nccl_gather_equals_single_rank" 2>&1 | tail -6
   MODES="mcast fanout nccl" KS="20" bash tools/_run_mg.sh $N bench
