@@ -617,6 +617,27 @@ def run_ours(args):
                              "writes its obs/action/reward/done slab rows and episode-log row; bit-identical to K wl_step calls"}
         except Exception as ex:
             fused = {"error": repr(ex)[:200]}
+    # The timed region lasts ~0.1 ms and nvidia-smi needs up to a second to deliver its first row: keep every GPU of the job under
+    # the same step load (a scratch env set, no exchange) until rank 0 has read two rows per GPU, so that the clocks line is never
+    # empty or sampled on an idle (down-clocked) device.
+    def _need_rows():
+        return rank == 0 and sampler.proc is not None and len(sampler.rows) < 2 * world
+    flag = torch.tensor([1.0 if _need_rows() else 0.0], device=dev)
+    if world > 1:
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+    if float(flag.item()) > 0:
+        sim_l = wl.WheeledSim(mk(555), dev); sim_l.startup(); sim_l.reset(None, 0)
+        fn_l = sim_l.bind_step(acts[0], RolloutSlab(1, E, sim0.obs_dim, 2, dev).step_outputs(0))
+        t_l, t_end = 0, time.time() + 4.0
+        while True:
+            for _ in range(500):
+                fn_l(t_l); t_l += 1
+            flag.fill_(1.0 if (_need_rows() and time.time() < t_end) else 0.0)
+            if world > 1:
+                dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+            if float(flag.item()) == 0:
+                break
+        del sim_l
     clocks = sampler.stop() if rank == 0 else None
 
     tot_ms_own = tot_ms
