@@ -79,3 +79,11 @@ def test_plain_c_host_example_builds_against_the_abi(tmp_path):
     from wheeledlab_b200._lib import WlConfig
     import ctypes as C
     assert dump("drift", 64, str(tmp_path / "cfg.bin")) == C.sizeof(WlConfig)
+
+
+def test_every_exported_symbol_is_documented_in_integration_md():
+    """INTEGRATION.md section 3 lists every entry point of the C-ABI with the reference interface it stands for."""
+    from wheeledlab_b200._lib import EXPORTED_SYMBOLS
+    doc = (ROOT / "INTEGRATION.md").read_text()
+    missing = [s for s in EXPORTED_SYMBOLS if s not in doc]
+    assert not missing, f"undocumented entry points: {missing}"
