@@ -528,6 +528,7 @@ def run_ours(args):
     sim0.set_step_counter(t)
     g.replay(); barrier()
     g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda._sleep(200_000)                                # (as above: the host's graph-launch latency stays outside g0..g1)
     g0.record(); g.replay(); g1.record(); barrier()
     graph_ms = g0.elapsed_time(g1)
     sim0.note_device_counter(t + 2 * K)
